@@ -1,0 +1,104 @@
+"""ctypes binding of libcenet_b200.so (the C ABI declared in include/cenet_b200.h).
+
+There is deliberately no fallback: if the library is missing or a kernel reports an error, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcenet_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = range(6)
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
+
+vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `cenet_gemm_args` (include/cenet_b200.h)."""
+    _fields_ = [
+        ("M", i32), ("N", i32), ("K", i32),
+        ("batch", i32), ("batch_inner", i32),
+        ("A", vp), ("a_dtype", i32), ("lda", ll), ("a_bs_outer", ll), ("a_bs_inner", ll),
+        ("conv", i32), ("Bimg", i32), ("H", i32), ("W", i32), ("Cin", i32), ("KH", i32), ("KW", i32),
+        ("stride", i32), ("pad", i32), ("Ho", i32), ("Wo", i32),
+        ("Wt", vp), ("w_dtype", i32), ("ldw", ll), ("w_bs_outer", ll), ("w_bs_inner", ll), ("w_nmajor", i32),
+        ("C", vp), ("c_dtype", i32), ("ldc", ll), ("c_bs_outer", ll), ("c_bs_inner", ll),
+        ("alpha", f32), ("bias", vp), ("bias_per_row", i32), ("row_scale", vp),
+        ("act", i32), ("slope", f32), ("act_after_res", i32),
+        ("res1", vp), ("res1_dtype", i32), ("ldr1", ll), ("res1_cscale", vp), ("res1_scale", f32),
+        ("res2", vp), ("res2_dtype", i32), ("ldr2", ll),
+        ("mul", vp), ("mul_dtype", i32), ("ldmul", ll), ("mul_act", i32),
+        ("impl", i32),
+    ]
+
+
+# name -> argument ctypes (all return int unless noted)
+_SIGS = {
+    "cenet_gemm": [C.POINTER(GemmArgs), vp],
+    "cenet_layernorm": [vp, i32, vp, i32, vp, vp, ll, i32, f32, vp],
+    "cenet_softmax_rows": [vp, i32, ll, i32, ll, vp],
+    "cenet_row_stats": [vp, i32, ll, i32, ll, i32, vp, vp],
+    "cenet_dwconv3x3": [vp, i32, ll, vp, i32, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_nhwc_to_nchw": [vp, i32, ll, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cenet_nchw_to_nhwc": [vp, i32, vp, i32, ll, i32, i32, i32, vp],
+    "cenet_im2col": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "cenet_upsample2x_ac": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
+    "cenet_maxpool2_scale": [vp, i32, vp, i32, ll, i32, vp, i32, i32, i32, i32, vp],
+    "cenet_affine_gate": [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp],
+    "cenet_fea_combine": [vp, vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(f32), i32, vp],
+    "cenet_diff_combine": [vp, i32, ll, ll, f32, vp],
+    "cenet_rmsnorm_seg": [vp, i32, vp, i32, ll, i32, i32, f32, f32, vp],
+    "cenet_diffattn_flash": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp],
+    "cenet_sr_attention": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_nonlocal_flash": [vp, vp, i32, i32, i32, f32, vp],
+    "cenet_ccu_gate": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    "cenet_srm_gate": [vp, vp, vp, vp, f32, f32, i32, i32, i32, vp],
+    "cenet_pool_branch": [vp, i32, ll, i32, vp, i32, ll, i32, vp, vp, vp, f32, vp, i32, i32, i32, i32, vp],
+    "cenet_head_upsample_argmax": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "cenet_dice_ce": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, vp],
+}
+_PLAIN = {  # no stream, different return types
+    "cenet_last_error": ([], C.c_char_p),
+    "cenet_abi_version": ([], i32),
+    "cenet_launch_count": ([], ll),
+    "cenet_ccu_nchunk": ([i32], i32),
+    "cenet_loss_nblocks": ([ll], i32),
+}
+EXPORTS = sorted(list(_SIGS) + list(_PLAIN))
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raises with a build hint when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -m cenet_b200.build` (needs nvcc, sm_100a). "
+                           "cenet_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i32
+    for name, (args, res) in _PLAIN.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().cenet_last_error()
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else 'unknown error'}")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

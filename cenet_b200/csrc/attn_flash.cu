@@ -1,0 +1,424 @@
+// Flash-style attention kernels for the two N x N attentions of the decoder:
+//   * differential attention of the DSE blocks (multihead_diffattn.py:92-124)
+//   * non-local block core (nlb.py:116-137)
+// Neither materialises the N x N maps (the reference writes 2h fp32 maps of N^2 per image and re-reads them ~5x).
+//
+// Why mma.sync and not tcgen05 here: with head_dim 8..32 the contraction depth of Q K^T is one or two k16 steps, so
+// the kernel is bound by the softmax (one MUFU.EX2 per score: 2h*N^2 per image, 16/clk/SM) and by issue slots, not by
+// the tensor pipe.  mma.sync leaves the scores in registers where the softmax needs them; a tcgen05 version would add
+// a TMEM->register round trip per score for no gain.  The GEMM-shaped layers use tcgen05 (gemm_tc.cu).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+constexpr int QT = 64;    // query rows per CTA (4 warps x 16)
+constexpr int KT = 64;    // keys per pipeline stage
+constexpr int NTHREADS = 128;
+
+// =====================================================================================================================
+// One attention "stream": 16 query rows of one warp against a KT-key tile; scores in registers.
+//   HDP: padded q/k depth (multiple of 16), DV: value width (multiple of 16)
+// S = Q K^T -> online softmax (base-2, scale folded) -> O += P V ; l accumulates row sums.
+// =====================================================================================================================
+template <int HDP>
+__device__ __forceinline__ void qk_tile(float (&S)[KT / 8][4], const uint32_t (&qf)[HDP / 16][4], uint32_t k_smem,
+                                        int k_stride, int lane) {
+#pragma unroll
+  for (int j = 0; j < KT / 8; j++) { S[j][0] = S[j][1] = S[j][2] = S[j][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < HDP / 16; ks++) {
+#pragma unroll
+    for (int jp = 0; jp < KT / 16; jp++) {
+      uint32_t b[4];
+      const int key = jp * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int d = ks * 16 + (((lane >> 3) & 1) << 3);
+      ldsm_x4(b, k_smem + key * k_stride + d * 2);
+      mma_16816(S[2 * jp], qf[ks], b[0], b[1]);
+      mma_16816(S[2 * jp + 1], qf[ks], b[2], b[3]);
+    }
+  }
+}
+
+// online softmax update for the 2 rows this thread owns (g and g+8); returns P packed as A fragments
+template <int DV>
+__device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P)[KT / 16][4], float (&m)[2],
+                                             float (&l)[2], float (&O)[DV / 8][4], float scale_log2, int kbase, int N,
+                                             int lane) {
+  const int t = lane & 3;
+  if (kbase + KT > N) {   // ragged last tile: mask keys >= N
+#pragma unroll
+    for (int j = 0; j < KT / 8; j++) {
+      const int key = kbase + j * 8 + 2 * t;
+      if (key >= N) { S[j][0] = -INFINITY; S[j][2] = -INFINITY; }
+      if (key + 1 >= N) { S[j][1] = -INFINITY; S[j][3] = -INFINITY; }
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KT / 8; j++) {
+    mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1]));
+    mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  const float mn0 = fmaxf(m[0], mx0 * scale_log2), mn1 = fmaxf(m[1], mx1 * scale_log2);
+  const float c0 = fast_exp2(m[0] - mn0), c1 = fast_exp2(m[1] - mn1);
+  m[0] = mn0; m[1] = mn1;
+  l[0] *= c0; l[1] *= c1;
+#pragma unroll
+  for (int j = 0; j < DV / 8; j++) { O[j][0] *= c0; O[j][1] *= c0; O[j][2] *= c1; O[j][3] *= c1; }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KT / 8; j++) {
+    const float p0 = fast_exp2(fmaf(S[j][0], scale_log2, -mn0));
+    const float p1 = fast_exp2(fmaf(S[j][1], scale_log2, -mn0));
+    const float p2 = fast_exp2(fmaf(S[j][2], scale_log2, -mn1));
+    const float p3 = fast_exp2(fmaf(S[j][3], scale_log2, -mn1));
+    s0 += p0 + p1; s1 += p2 + p3;
+    P[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+    P[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+  }
+  l[0] += s0; l[1] += s1;
+}
+
+// =====================================================================================================================
+// Differential attention.  grid = (ceil(N/64), heads, B), 128 threads.
+//   HD: real head_dim (8,16,32,64); HDP = max(HD,16); DV = 2*HD
+// smem rows are padded by 16 bytes so that ldmatrix's 8 row addresses fall in distinct 16-byte bank groups.
+// =====================================================================================================================
+template <int HD>
+struct DiffCfg {
+  static constexpr int HDP = HD < 16 ? 16 : HD;
+  static constexpr int DV = 2 * HD;
+  static constexpr int KSTR = HDP * 2 + 16;           // bytes per K/Q smem row
+  static constexpr int VSTR = DV * 2 + 16;            // bytes per V smem row
+  static constexpr int Q_BYTES = 2 * QT * KSTR;       // two maps
+  static constexpr int K_BYTES = 2 * KT * KSTR;       // two maps, one stage
+  static constexpr int V_BYTES = KT * VSTR;
+  static constexpr int STAGE = K_BYTES + V_BYTES;
+  static constexpr int SMEM = Q_BYTES + 2 * STAGE;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(NTHREADS) diffattn_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                  int N, int E, float scale_log2, float lambda,
+                                                                  float eps, float mult) {
+  using Cfg = DiffCfg<HD>;
+  constexpr int HDP = Cfg::HDP, DV = Cfg::DV, KSTR = Cfg::KSTR, VSTR = Cfg::VSTR;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+  const long long row3E = 3LL * E;
+  const bf16* base = qkv + (long long)b * N * row3E;
+  const uint32_t sQ = smem_u32(smem), sKV = sQ + Cfg::Q_BYTES;
+
+  if (HD < 16) {   // zero the padding half of every Q/K row once (cp.async only ever writes the first 16 bytes)
+    for (int i = tid; i < (Cfg::SMEM) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+  }
+  constexpr int QCH = HD / 8;     // 16-byte chunks per real q/k row
+  constexpr int VCH = DV / 8;
+  // ---- Q tile (both maps) ----
+  for (int i = tid; i < 2 * QT * QCH; i += NTHREADS) {
+    const int ch = i % QCH, r = (i / QCH) % QT, mp = i / (QCH * QT);
+    const int n = q0 + r;
+    const bf16* src = base + (long long)(n < N ? n : N - 1) * row3E + (2 * head + mp) * HD + ch * 8;
+    cp_async16(sQ + (mp * QT + r) * KSTR + ch * 16, src, n < N);
+  }
+  auto load_kv = [&](int tile, int stage) {
+    const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + Cfg::K_BYTES;
+    const int k0 = tile * KT;
+    for (int i = tid; i < 2 * KT * QCH; i += NTHREADS) {
+      const int ch = i % QCH, r = (i / QCH) % KT, mp = i / (QCH * KT);
+      const int n = k0 + r;
+      const bf16* src = base + (long long)(n < N ? n : N - 1) * row3E + E + (2 * head + mp) * HD + ch * 8;
+      cp_async16(sK + (mp * KT + r) * KSTR + ch * 16, src, n < N);
+    }
+    for (int i = tid; i < KT * VCH; i += NTHREADS) {
+      const int ch = i % VCH, r = i / VCH;
+      const int n = k0 + r;
+      const bf16* src = base + (long long)(n < N ? n : N - 1) * row3E + 2 * E + head * DV + ch * 8;
+      cp_async16(sV + r * VSTR + ch * 16, src, n < N);
+    }
+  };
+  const int ntiles = (N + KT - 1) / KT;
+  load_kv(0, 0);
+  cp_async_commit();
+  if (ntiles > 1) load_kv(1, 1);
+  cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+
+  // Q fragments for this warp's 16 rows, both maps
+  uint32_t qf[2][HDP / 16][4];
+#pragma unroll
+  for (int mp = 0; mp < 2; mp++)
+#pragma unroll
+    for (int ks = 0; ks < HDP / 16; ks++) {
+      const int r = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int d = ks * 16 + ((lane >> 4) << 3);
+      ldsm_x4(qf[mp][ks], sQ + (mp * QT + r) * KSTR + d * 2);
+    }
+
+  float O[2][DV / 8][4];
+  float m[2][2], l[2][2];
+#pragma unroll
+  for (int mp = 0; mp < 2; mp++) {
+    m[mp][0] = m[mp][1] = -INFINITY;
+    l[mp][0] = l[mp][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV / 8; j++) O[mp][j][0] = O[mp][j][1] = O[mp][j][2] = O[mp][j][3] = 0.f;
+  }
+
+  for (int tile = 0; tile < ntiles; tile++) {
+    const int stage = tile & 1;
+    const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + Cfg::K_BYTES;
+    uint32_t P[2][KT / 16][4];
+#pragma unroll
+    for (int mp = 0; mp < 2; mp++) {
+      float S[KT / 8][4];
+      qk_tile<HDP>(S, qf[mp], sK + mp * KT * KSTR, KSTR, lane);
+      softmax_tile<DV>(S, P[mp], m[mp], l[mp], O[mp], scale_log2, tile * KT, N, lane);
+    }
+    // O_mp += P_mp V   (V fragments shared by the two maps)
+#pragma unroll
+    for (int kk = 0; kk < KT / 16; kk++) {
+#pragma unroll
+      for (int np = 0; np < DV / 16; np++) {
+        uint32_t v[4];
+        const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int dv = np * 16 + ((lane >> 4) << 3);
+        ldsm_x4_t(v, sV + key * VSTR + dv * 2);
+#pragma unroll
+        for (int mp = 0; mp < 2; mp++) {
+          mma_16816(O[mp][2 * np], P[mp][kk], v[0], v[1]);
+          mma_16816(O[mp][2 * np + 1], P[mp][kk], v[2], v[3]);
+        }
+      }
+    }
+    __syncthreads();                       // everyone is done with this stage
+    if (tile + 2 < ntiles) load_kv(tile + 2, stage);
+    cp_async_commit();
+    cp_async_wait<1>();                    // tile+1 has landed
+    __syncthreads();
+  }
+
+  // ---- epilogue: normalise both maps, difference, RMSNorm over DV, scale, store ----
+  float inv[2][2];
+#pragma unroll
+  for (int mp = 0; mp < 2; mp++)
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      float s = l[mp][r];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      inv[mp][r] = 1.f / s;
+    }
+  float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < DV / 8; j++) {
+    O[0][j][0] = O[0][j][0] * inv[0][0] - lambda * O[1][j][0] * inv[1][0];
+    O[0][j][1] = O[0][j][1] * inv[0][0] - lambda * O[1][j][1] * inv[1][0];
+    O[0][j][2] = O[0][j][2] * inv[0][1] - lambda * O[1][j][2] * inv[1][1];
+    O[0][j][3] = O[0][j][3] * inv[0][1] - lambda * O[1][j][3] * inv[1][1];
+    ss0 += O[0][j][0] * O[0][j][0] + O[0][j][1] * O[0][j][1];
+    ss1 += O[0][j][2] * O[0][j][2] + O[0][j][3] * O[0][j][3];
+  }
+  ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+  ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+  const float r0 = rsqrtf(ss0 / (float)DV + eps) * mult, r1 = rsqrtf(ss1 / (float)DV + eps) * mult;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = q0 + warp * 16 + g, n1 = n0 + 8;
+  bf16* ob = out + (long long)b * N * E + head * DV;
+#pragma unroll
+  for (int j = 0; j < DV / 8; j++) {
+    const int col = j * 8 + 2 * t;
+    if (n0 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * E + col) = pack_bf16(O[0][j][0] * r0, O[0][j][1] * r0);
+    if (n1 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * E + col) = pack_bf16(O[0][j][2] * r1, O[0][j][3] * r1);
+  }
+}
+
+// =====================================================================================================================
+// Non-local block core: single head, d = C in {64,128}.  tpg rows are [theta | phi | g].
+// =====================================================================================================================
+template <int D>
+struct NlCfg {
+  static constexpr int STR = D * 2 + 16;
+  static constexpr int Q_BYTES = QT * STR;
+  static constexpr int STAGE = 2 * KT * STR;   // phi + g
+  static constexpr int SMEM = Q_BYTES + 2 * STAGE;
+};
+
+template <int D>
+__global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ out,
+                                                                  int N, float scale_log2) {
+  using Cfg = NlCfg<D>;
+  constexpr int STR = Cfg::STR, CH = D / 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, q0 = blockIdx.x * QT;
+  const long long row = 3LL * D;
+  const bf16* base = tpg + (long long)b * N * row;
+  const uint32_t sQ = smem_u32(smem), sKV = sQ + Cfg::Q_BYTES;
+  for (int i = tid; i < QT * CH; i += NTHREADS) {
+    const int ch = i % CH, r = i / CH, n = q0 + r;
+    cp_async16(sQ + r * STR + ch * 16, base + (long long)(n < N ? n : N - 1) * row + ch * 8, n < N);
+  }
+  auto load_kv = [&](int tile, int stage) {
+    const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + KT * STR;
+    const int k0 = tile * KT;
+    for (int i = tid; i < KT * CH; i += NTHREADS) {
+      const int ch = i % CH, r = i / CH, n = k0 + r;
+      const bf16* src = base + (long long)(n < N ? n : N - 1) * row + ch * 8;
+      cp_async16(sK + r * STR + ch * 16, src + D, n < N);
+      cp_async16(sV + r * STR + ch * 16, src + 2 * D, n < N);
+    }
+  };
+  const int ntiles = (N + KT - 1) / KT;
+  load_kv(0, 0);
+  cp_async_commit();
+  if (ntiles > 1) load_kv(1, 1);
+  cp_async_commit();
+  cp_async_wait<1>();
+  __syncthreads();
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ks++) {
+    const int r = warp * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+    const int d = ks * 16 + ((lane >> 4) << 3);
+    ldsm_x4(qf[ks], sQ + r * STR + d * 2);
+  }
+  float O[D / 8][4];
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < D / 8; j++) O[j][0] = O[j][1] = O[j][2] = O[j][3] = 0.f;
+  for (int tile = 0; tile < ntiles; tile++) {
+    const int stage = tile & 1;
+    const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + KT * STR;
+    float S[KT / 8][4];
+    uint32_t P[KT / 16][4];
+    qk_tile<D>(S, qf, sK, STR, lane);
+    softmax_tile<D>(S, P, m, l, O, scale_log2, tile * KT, N, lane);
+#pragma unroll
+    for (int kk = 0; kk < KT / 16; kk++) {
+#pragma unroll
+      for (int np = 0; np < D / 16; np++) {
+        uint32_t v[4];
+        const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int dv = np * 16 + ((lane >> 4) << 3);
+        ldsm_x4_t(v, sV + key * STR + dv * 2);
+        mma_16816(O[2 * np], P[kk], v[0], v[1]);
+        mma_16816(O[2 * np + 1], P[kk], v[2], v[3]);
+      }
+    }
+    __syncthreads();
+    if (tile + 2 < ntiles) load_kv(tile + 2, stage);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+  }
+  float inv[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    float s = l[r];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    inv[r] = 1.f / s;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = q0 + warp * 16 + g, n1 = n0 + 8;
+  bf16* ob = out + (long long)b * N * D;
+#pragma unroll
+  for (int j = 0; j < D / 8; j++) {
+    const int col = j * 8 + 2 * t;
+    if (n0 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * D + col) = pack_bf16(O[j][0] * inv[0], O[j][1] * inv[0]);
+    if (n1 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * D + col) = pack_bf16(O[j][2] * inv[1], O[j][3] * inv[1]);
+  }
+}
+
+template <int HD>
+int launch_diff(const bf16* qkv, bf16* out, int B, int N, int E, int heads, float lambda, float eps, float mult,
+                cudaStream_t s) {
+  using Cfg = DiffCfg<HD>;
+  auto kern = diffattn_flash_kernel<HD>;
+  if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  dim3 grid(cdiv(N, QT), heads, B);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(qkv, out, N, E, scale_log2, lambda, eps, mult);
+  CENET_LAUNCH_CHECK("diffattn_flash");
+  return 0;
+}
+template <int D>
+int launch_nl(const bf16* tpg, bf16* out, int B, int N, float scale, cudaStream_t s) {
+  using Cfg = NlCfg<D>;
+  auto kern = nonlocal_flash_kernel<D>;
+  if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  dim3 grid(cdiv(N, QT), B);
+  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(tpg, out, N, scale * 1.4426950408889634f);
+  CENET_LAUNCH_CHECK("nonlocal_flash");
+  return 0;
+}
+}  // namespace
+
+extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
+                                    float mult, cenet_stream_t s) {
+  if (B == 0 || N == 0) return 0;
+  CENET_REQUIRE(qkv && out, "cenet_diffattn_flash: null pointer");
+  CENET_REQUIRE(heads >= 1 && E % (2 * heads) == 0, "cenet_diffattn_flash: E=%d not divisible by 2*heads=%d", E, 2 * heads);
+  CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash: grid too large");
+  const int hd = E / (2 * heads);
+  const bf16* q = (const bf16*)qkv;
+  bf16* o = (bf16*)out;
+  switch (hd) {
+    case 8: return launch_diff<8>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 16: return launch_diff<16>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 32: return launch_diff<32>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 64: return launch_diff<64>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    default: CENET_FAIL("cenet_diffattn_flash: head_dim %d not in {8,16,32,64}; use the materialised path", hd);
+  }
+}
+
+extern "C" int cenet_nonlocal_flash(const void* tpg, void* out, int B, int N, int C, float scale, cenet_stream_t s) {
+  if (B == 0 || N == 0) return 0;
+  CENET_REQUIRE(tpg && out, "cenet_nonlocal_flash: null pointer");
+  CENET_REQUIRE(B <= 65535, "cenet_nonlocal_flash: grid too large");
+  switch (C) {
+    case 64: return launch_nl<64>((const bf16*)tpg, (bf16*)out, B, N, scale, to_stream(s));
+    case 128: return launch_nl<128>((const bf16*)tpg, (bf16*)out, B, N, scale, to_stream(s));
+    default: CENET_FAIL("cenet_nonlocal_flash: C=%d not in {64,128}; use the materialised path", C);
+  }
+}

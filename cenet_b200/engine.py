@@ -1,0 +1,543 @@
+"""Launch plan of one CENet forward pass on one B200 (inference: eval-mode BatchNorm, no DropPath).
+
+Host-side mirror of `CENet.forward` (net.py:53-64): packs the module's parameters once (BatchNorm folded into the
+neighbouring GEMM, conv weights permuted to (kh,kw,cin), bf16 copies), owns the activation workspaces, and issues
+the kernels of cenet_b200/csrc through the C ABI on the current torch stream.  The whole pass is a static sequence
+of launches with static buffers, so after the first call it is replayed from a CUDA graph.
+
+Data layout in HBM: every activation is channels-last [B,H,W,C] (== token-major [B*N, C]) in bf16 (fp32 in the
+validation precision); the only NCHW buffers are the DSEB `cat` buffer and its products, because the reference
+*reinterprets* that NCHW buffer as tokens (dseb.py:115).  fp32 per-channel vectors carry biases / folded BN.
+
+precision = "bf16": tcgen05 GEMMs + flash attention (product path).
+precision = "fp32": same launch plan with fp32 storage, CUDA-core GEMMs and materialised attention -- used by the
+                    parity tests to separate logic errors (1e-4) from bf16 rounding (1e-2).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SILU, GEMM_AUTO, GEMM_SIMT
+
+_PVT = dict(embed_dims=(64, 128, 320, 512), heads=(1, 2, 5, 8), mlp_ratios=(8, 8, 4, 4), depths=(3, 4, 6, 3),
+            sr_ratios=(8, 4, 2, 1))
+_MCA_RATES = {64: (2, 3, 5), 128: (1, 2, 4), 320: (1, 2, 3), 512: (1, 2, 2)}
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+def lambda_init(depth):
+    """multihead_diffattn.py:28-29"""
+    return 0.8 - 0.6 * math.exp(-0.3 * depth)
+
+
+class Engine:
+    @staticmethod
+    def default_precision():
+        return os.environ.get("CENET_B200_PRECISION", "bf16")
+
+    def __init__(self, module, device, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        from . import _lib
+        _lib.load()                                   # fail loudly if the CUDA library is missing
+        self.mod = module
+        self.dev = torch.device(device)
+        self.precision = precision
+        self.T = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.gemm_impl = GEMM_AUTO if precision == "bf16" else GEMM_SIMT
+        self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
+        self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
+        self.cfg = module.cfg
+        self.w = {}
+        self._wver = None
+        self._bufs = {}
+        self._graphs = {}
+        self.taps = None                              # dict -> intermediate activations are copied out (tests)
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _weights_version(self):
+        v = 0
+        for t in self.mod.parameters():
+            v += t._version
+        for t in self.mod.buffers():
+            v += t._version
+        return (v, self.mod.training)
+
+    def _sd(self):
+        return {k: v.detach().to(self.dev, torch.float32) for k, v in self.mod.state_dict().items()}
+
+    def _put(self, name, t, dtype=None):
+        """Store a packed tensor, reusing the existing device buffer (CUDA graphs keep their pointers)."""
+        t = t.to(self.dev, dtype or torch.float32).contiguous()
+        old = self.w.get(name)
+        if old is not None and old.shape == t.shape and old.dtype == t.dtype:
+            old.copy_(t)
+        else:
+            self.w[name] = t
+        return self.w[name]
+
+    def _put_mat(self, name, w2d):
+        """[N,K] GEMM weight in the compute dtype, rows padded to a multiple of 8 elements (16-byte TMA pitch)."""
+        N, K = w2d.shape
+        Kp = _rup(K, 8)
+        m = torch.zeros(N, Kp, device=self.dev, dtype=torch.float32)
+        m[:, :K] = w2d
+        return self._put(name, m, self.T)
+
+    @staticmethod
+    def _bn_fold(sd, p, eps=1e-5):
+        s = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + eps)
+        return s, sd[p + ".bias"] - sd[p + ".running_mean"] * s
+
+    @staticmethod
+    def _conv_mat(w4d):
+        """[Cout,Cin,KH,KW] -> [Cout, KH*KW*Cin]"""
+        return w4d.permute(0, 2, 3, 1).reshape(w4d.shape[0], -1)
+
+    def pack(self):
+        sd = self._sd()
+        cfg = self.cfg
+        P, M = self._put, self._put_mat
+        # ---------------- encoder ----------------
+        for s in range(4):
+            pe = f"backbone.patch_embed{s+1}"
+            w = sd[pe + ".proj.weight"]
+            if s == 0 and cfg["input_channels"] == 1:
+                w = w.sum(1, keepdim=True)            # cat([x,x,x]) (net.py:55) == one channel with summed filters
+            M(pe + ".w", self._conv_mat(w))
+            P(pe + ".b", sd[pe + ".proj.bias"])
+            P(pe + ".ln_g", sd[pe + ".norm.weight"]); P(pe + ".ln_b", sd[pe + ".norm.bias"])
+            for i in range(_PVT["depths"][s]):
+                b = f"backbone.block{s+1}.{i}"
+                for n in ("norm1", "norm2"):
+                    P(f"{b}.{n}.g", sd[f"{b}.{n}.weight"]); P(f"{b}.{n}.b", sd[f"{b}.{n}.bias"])
+                for n in ("attn.q", "attn.kv", "attn.proj", "mlp.fc1", "mlp.fc2"):
+                    M(f"{b}.{n}.w", sd[f"{b}.{n}.weight"]); P(f"{b}.{n}.b", sd[f"{b}.{n}.bias"])
+                if _PVT["sr_ratios"][s] > 1:
+                    M(f"{b}.attn.sr.w", self._conv_mat(sd[f"{b}.attn.sr.weight"]))
+                    P(f"{b}.attn.sr.b", sd[f"{b}.attn.sr.bias"])
+                    P(f"{b}.attn.norm.g", sd[f"{b}.attn.norm.weight"]); P(f"{b}.attn.norm.b", sd[f"{b}.attn.norm.bias"])
+                dw = sd[f"{b}.mlp.dwconv.dwconv.weight"]                        # [C,1,3,3] -> [9,C]
+                P(f"{b}.mlp.dw.w", dw.reshape(dw.shape[0], 9).t())
+                P(f"{b}.mlp.dw.b", sd[f"{b}.mlp.dwconv.dwconv.bias"])
+            P(f"backbone.norm{s+1}.g", sd[f"backbone.norm{s+1}.weight"])
+            P(f"backbone.norm{s+1}.b", sd[f"backbone.norm{s+1}.bias"])
+        # ---------------- decoder ----------------
+        for name, Cc in (("dec4", 512), ("dec3", 320), ("dec2", 128), ("dec1", 64)):
+            self._pack_cfam(sd, f"decoder.{name}", Cc)
+        for lvl, depth, hi in ((3, 4, 0), (2, 3, 1), (1, 2, 2)):
+            self._pack_up(sd, f"decoder.up{lvl}", cfg["dec_up_block"])
+            p = f"decoder.skip_enhancer{lvl}"
+            P(p + ".fea_w", sd[p + ".boundary.w"].reshape(-1))
+            d = p + ".diffattn"
+            M(d + ".qkv.w", torch.cat([sd[d + ".q_proj.weight"], sd[d + ".k_proj.weight"], sd[d + ".v_proj.weight"]], 0))
+            M(d + ".out.w", sd[d + ".out_proj.weight"])
+            li = lambda_init(depth)
+            lam = (torch.exp((sd[d + ".lambda_q1"] * sd[d + ".lambda_k1"]).sum())
+                   - torch.exp((sd[d + ".lambda_q2"] * sd[d + ".lambda_k2"]).sum()) + li)
+            self.w[d + ".lambda"] = float(lam.item())          # host scalar (kernel argument)
+            self.w[d + ".lambda_init"] = li
+            M(p + ".mixer.w", sd[p + ".mixer.weight"].flatten(1))
+        # ---------------- head ----------------
+        self._pack_resblock(sd, "out.rb.0", 5)
+        self._pack_resblock(sd, "out.out.0", 3)
+        P("out.w", sd["out.w"].reshape(-1))
+        self._pack_up(sd, "out.up", cfg["out_up_block"])
+        M("out.head.w", sd["out.out.1.conv.conv.weight"].flatten(1))
+        P("out.head.b", sd["out.out.1.conv.conv.bias"])
+        self._wver = self._weights_version()
+        self._graphs.clear()                                   # host scalars are baked into captured launches
+
+    def _pack_resblock(self, sd, p, k):
+        for i in (1, 2, 3):
+            key = f"{p}.conv{i}.conv.weight"
+            if key not in sd:
+                continue
+            s, t = self._bn_fold(sd, f"{p}.norm{i}")
+            self._put_mat(f"{p}.c{i}.w", self._conv_mat(sd[key]) * s[:, None])
+            self._put(f"{p}.c{i}.b", t)
+
+    def _pack_up(self, sd, p, kind):
+        if kind == "eucb":
+            dw = sd[p + ".up_dwc.1.weight"]
+            self._put(p + ".dw.w", dw.reshape(dw.shape[0], 9).t())
+            s, t = self._bn_fold(sd, p + ".up_dwc.2")
+            self._put(p + ".dw.s", s); self._put(p + ".dw.t", t)
+            self._put_mat(p + ".pw.w", sd[p + ".pwc.0.weight"].flatten(1))
+            self._put(p + ".pw.b", sd[p + ".pwc.0.bias"])
+        elif kind == "upcn":
+            s, t = self._bn_fold(sd, p + ".up.2")
+            self._put_mat(p + ".conv.w", self._conv_mat(sd[p + ".up.1.weight"]) * s[:, None])
+            self._put(p + ".conv.b", t)
+        else:
+            raise NotImplementedError(kind)
+
+    def _pack_cfam(self, sd, p, Cc):
+        P, M = self._put, self._put_mat
+        s1, t1 = self._bn_fold(sd, p + ".norm1")
+        P(p + ".bn1.s", s1); P(p + ".bn1.t", t1)
+        ls1, ls2 = sd[p + ".layer_scale_1"].reshape(-1), sd[p + ".layer_scale_2"].reshape(-1)
+        m = p + ".mca"
+        P(m + ".ccu.fc1", sd[m + ".ccu.fc1.weight"].reshape(Cc, 3, 3))
+        P(m + ".ccu.fc2", sd[m + ".ccu.fc2.weight"].reshape(Cc, 3))
+        cs, ct = self._bn_fold(sd, m + ".ccu.bn")
+        P(m + ".ccu.bn.s", cs); P(m + ".ccu.bn.t", ct)
+        M(m + ".gate.w", sd[m + ".gate.weight"].flatten(1)); P(m + ".gate.b", sd[m + ".gate.bias"])
+        v = m + ".value"
+        from .networks.cenet import channel_slices
+        sl = channel_slices(Cc)
+        for i in range(3):
+            d = f"{v}.dlps.{i}"
+            dw = sd[d + ".depthwise.weight"]
+            P(d + ".dw.w", dw.reshape(dw.shape[0], 9).t())
+            s, t = self._bn_fold(sd, d + ".depthwise_bn")
+            P(d + ".dw.s", s); P(d + ".dw.t", t)
+            s, t = self._bn_fold(sd, d + ".pointwise_bn")
+            M(d + ".pw.w", sd[d + ".pointwise.weight"].flatten(1) * s[:, None]); P(d + ".pw.b", t)
+        d = f"{v}.dlps.3"
+        P(d + ".w", sd[d + ".1.weight"].flatten(1))
+        s, t = self._bn_fold(sd, d + ".2")
+        P(d + ".s", s); P(d + ".t", t)
+        M(v + ".PW.w", sd[v + ".PW_conv.weight"].flatten(1)); P(v + ".PW.b", sd[v + ".PW_conv.bias"])
+        # proj_2 + shortcut BN(x):  acc + (b + t1) + x*s1
+        M(m + ".proj2.w", sd[m + ".proj_2.weight"].flatten(1)); P(m + ".proj2.b", sd[m + ".proj_2.bias"] + t1)
+        n = m + ".denoising_module"
+        M(n + ".tpg.w", torch.cat([sd[n + ".conv_theta.weight"], sd[n + ".conv_phi.weight"], sd[n + ".conv_g.weight"]],
+                                  0).flatten(1))
+        P(n + ".tpg.b", torch.cat([sd[n + ".conv_theta.bias"], sd[n + ".conv_phi.bias"], sd[n + ".conv_g.bias"]], 0))
+        ns, nt = self._bn_fold(sd, n + ".bn")
+        wmix = sd[n + ".w"]
+        # x_new = x + ls1*((1-w)*y + w*BN(conv_out(att)))
+        M(n + ".out.w", sd[n + ".conv_out.weight"].flatten(1) * (ls1 * wmix * ns)[:, None])
+        P(n + ".out.b", ls1 * wmix * (ns * sd[n + ".conv_out.bias"] + nt))
+        P(n + ".res_scale", ls1 * (1.0 - wmix))
+        # Mlp: BN2 folded into fc1, layer_scale_2 into fc2
+        s2, t2 = self._bn_fold(sd, p + ".norm2")
+        q = p + ".mlp"
+        w1 = sd[q + ".fc1.weight"].flatten(1)
+        M(q + ".fc1.w", w1 * s2[None, :]); P(q + ".fc1.b", sd[q + ".fc1.bias"] + w1 @ t2)
+        dw = sd[q + ".dwconv.weight"]
+        P(q + ".dw.w", dw.reshape(dw.shape[0], 9).t()); P(q + ".dw.b", sd[q + ".dwconv.bias"])
+        P(q + ".srm.pw", sd[q + ".srm.pwc.weight"].reshape(3))
+        P(q + ".srm.dw", sd[q + ".srm.dwc.weight"].reshape(27))
+        ss, st = self._bn_fold(sd, q + ".srm.bn")
+        self.w[q + ".srm.bn"] = (float(ss.item()), float(st.item()))
+        M(q + ".fc2.w", sd[q + ".fc2.weight"].flatten(1) * ls2[:, None]); P(q + ".fc2.b", sd[q + ".fc2.bias"] * ls2)
+
+    # ------------------------------------------------------------------------------------------------ buffers
+    def buf(self, key, shape, dtype=None):
+        dtype = dtype or self.T
+        k = (self._plan_key, key)
+        t = self._bufs.get(k)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            t = self._bufs[k] = torch.empty(shape, device=self.dev, dtype=dtype)
+        return t
+
+    def _tap(self, name, t_nhwc, B, H, W, Cc):
+        if self.taps is not None:
+            self.taps[name] = t_nhwc.reshape(B, H, W, Cc).permute(0, 3, 1, 2).float().clone()
+
+    # ------------------------------------------------------------------------------------------------ pieces
+    def _lin(self, x, wname, out, bias=True, **kw):
+        return ops.linear(x, self.w[wname + ".w"], out, bias=self.w[wname + ".b"] if bias else None,
+                          impl=self.gemm_impl, **kw)
+
+    def _conv_im2col(self, x_nhwc, B, H, W, Cin, k, stride, pad, wname, out, key):
+        Ho = (H + 2 * pad - k) // stride + 1
+        Wo = (W + 2 * pad - k) // stride + 1
+        wmat = self.w[wname + ".w"]
+        Kp = wmat.shape[1]
+        col = self.buf(key + ".col", (B * Ho * Wo, Kp))
+        ops.im2col(x_nhwc, col, B, H, W, Cin, k, stride, pad, Ho, Wo, Kp)
+        ops.gemm(col, wmat, out, M=B * Ho * Wo, N=wmat.shape[0], K=Kp, lda=Kp, ldw=Kp, ldc=out.shape[-1],
+                 bias=self.w[wname + ".b"], impl=self.gemm_impl)
+        return Ho, Wo
+
+    def _encoder(self, x_nhwc, B, H, W, Cin):
+        """pvtv2.py:312-348 -> four channels-last pyramid maps"""
+        w = self.w
+        feats = []
+        cur, curC = x_nhwc, Cin
+        for s in range(4):
+            Cc, heads, sr = _PVT["embed_dims"][s], _PVT["heads"][s], _PVT["sr_ratios"][s]
+            hid = Cc * _PVT["mlp_ratios"][s]
+            k, st = (7, 4) if s == 0 else (3, 2)
+            pe = f"backbone.patch_embed{s+1}"
+            Ho = (H + 2 * (k // 2) - k) // st + 1
+            Wo = (W + 2 * (k // 2) - k) // st + 1
+            Mtok = B * Ho * Wo
+            traw = self.buf(f"enc{s}.traw", (Mtok, Cc))
+            self._conv_im2col(cur, B, H, W, curC, k, st, k // 2, pe, traw, f"enc{s}.pe")
+            H, W = Ho, Wo
+            t = self.buf(f"enc{s}.t", (Mtok, Cc))
+            ops.layernorm(traw, t, w[pe + ".ln_g"], w[pe + ".ln_b"], 1e-5)
+            xn = self.buf(f"enc{s}.xn", (Mtok, Cc))
+            q = self.buf(f"enc{s}.q", (Mtok, Cc))
+            att = self.buf(f"enc{s}.att", (Mtok, Cc))
+            h1 = self.buf(f"enc{s}.h1", (Mtok, hid))
+            h2 = self.buf(f"enc{s}.h2", (Mtok, hid))
+            Nk = (H // sr) * (W // sr)
+            kv = self.buf(f"enc{s}.kv", (B * Nk, 2 * Cc))
+            for i in range(_PVT["depths"][s]):
+                b = f"backbone.block{s+1}.{i}"
+                ops.layernorm(t, xn, w[b + ".norm1.g"], w[b + ".norm1.b"], 1e-6)
+                self._lin(xn, b + ".attn.q", q)
+                if sr > 1:
+                    xr = self.buf(f"enc{s}.xr", (B * Nk, Cc))
+                    self._conv_im2col(xn, B, H, W, Cc, sr, sr, 0, b + ".attn.sr", xr, f"enc{s}.sr")
+                    xrn = self.buf(f"enc{s}.xrn", (B * Nk, Cc))
+                    ops.layernorm(xr, xrn, w[b + ".attn.norm.g"], w[b + ".attn.norm.b"], 1e-5)
+                    self._lin(xrn, b + ".attn.kv", kv)
+                else:
+                    self._lin(xn, b + ".attn.kv", kv)
+                ops.sr_attention(q, kv, att, B, H * W, Nk, Cc, heads, 64 ** -0.5)
+                self._lin(att, b + ".attn.proj", t, res1=t, ldr1=Cc)                # x += proj(attn)
+                ops.layernorm(t, xn, w[b + ".norm2.g"], w[b + ".norm2.b"], 1e-6)
+                self._lin(xn, b + ".mlp.fc1", h1)
+                ops.dwconv3x3(h1, h2, w[b + ".mlp.dw.w"], B, H, W, hid, bias=w[b + ".mlp.dw.b"], act=ACT_GELU)
+                self._lin(h2, b + ".mlp.fc2", t, res1=t, ldr1=Cc)                   # x += fc2(...)
+            f = self.buf(f"enc{s}.out", (Mtok, Cc))
+            ops.layernorm(t, f, w[f"backbone.norm{s+1}.g"], w[f"backbone.norm{s+1}.b"], 1e-6)
+            self._tap(f"backbone.stage{s+1}", f, B, H, W, Cc)
+            feats.append((f, H, W, Cc))
+            cur, curC = f, Cc
+        return feats
+
+    # ---- attention cores --------------------------------------------------------------------------------------
+    def _diff_attention(self, tok, B, N, E, heads, p, key):
+        """multihead_diffattn.py:70-129 on tokens tok [B*N,E] -> gate [B*N,E]"""
+        w = self.w
+        hd = E // heads // 2
+        lam, li = w[p + ".lambda"], w[p + ".lambda_init"]
+        qkv = self.buf(key + ".qkv", (B * N, 3 * E))
+        ops.linear(tok, w[p + ".qkv.w"], qkv, impl=self.gemm_impl)
+        o = self.buf(key + ".o", (B * N, E))
+        if self.use_flash and hd in (8, 16, 32, 64):
+            ops.diffattn_flash(qkv, o, B, N, E, heads, lam, 1e-5, 1.0 - li)
+        else:
+            S = self.buf(key + ".S", (B * 2 * heads, N, N))
+            ops.gemm(qkv, qkv, S, M=N, N=N, K=hd, lda=3 * E, ldw=3 * E, ldc=N, alpha=hd ** -0.5, batch=B * 2 * heads,
+                     batch_inner=2 * heads, a_bs=(N * 3 * E, hd), w_bs=(N * 3 * E, hd), c_bs=(2 * heads * N * N, N * N),
+                     w_off=E, impl=GEMM_SIMT)
+            ops.softmax_rows_(S, B * 2 * heads * N, N, N)
+            ops.diff_combine_(S, B * heads, N * N, lam)
+            oraw = self.buf(key + ".oraw", (B * N, E))
+            ops.gemm(S, qkv, oraw, M=N, N=2 * hd, K=N, lda=N, ldw=3 * E, ldc=E, batch=B * heads, batch_inner=heads,
+                     a_bs=(2 * heads * N * N, 2 * N * N), w_bs=(N * 3 * E, 2 * hd), c_bs=(N * E, 2 * hd), w_off=2 * E,
+                     w_nmajor=True, impl=GEMM_SIMT)
+            ops.rmsnorm_seg(oraw, o, 2 * hd, 1e-5, 1.0 - li)
+        gate = self.buf(key + ".gate", (B * N, E))
+        ops.linear(o, w[p + ".out.w"], gate, impl=self.gemm_impl)
+        return gate
+
+    def _nonlocal_core(self, tpg, B, N, Cc, key):
+        """nlb.py:116-137: tpg [B*N,3C] = theta|phi|g -> att [B*N,C]"""
+        att = self.buf(key + ".att", (B * N, Cc))
+        if self.use_flash and Cc in (64, 128):
+            ops.nonlocal_flash(tpg, att, B, N, Cc, Cc ** -0.5)
+        else:
+            S = self.buf(key + ".S", (B, N, N))
+            ops.gemm(tpg, tpg, S, M=N, N=N, K=Cc, lda=3 * Cc, ldw=3 * Cc, ldc=N, alpha=Cc ** -0.5, batch=B,
+                     a_bs=(N * 3 * Cc, 0), w_bs=(N * 3 * Cc, 0), c_bs=(N * N, 0), w_off=Cc, impl=GEMM_SIMT)
+            ops.softmax_rows_(S, B * N, N, N)
+            ops.gemm(S, tpg, att, M=N, N=Cc, K=N, lda=N, ldw=3 * Cc, ldc=Cc, batch=B, a_bs=(N * N, 0),
+                     w_bs=(N * 3 * Cc, 0), c_bs=(N * Cc, 0), w_off=2 * Cc, w_nmajor=True, impl=GEMM_SIMT)
+        return att
+
+    # ---- decoder blocks -----------------------------------------------------------------------------------------
+    def _cfam(self, x, B, H, W, Cc, p, key):
+        """cfam.py:365-374 on x [B*HW,C] -> new buffer"""
+        w = self.w
+        HW, Mtok = H * W, B * H * W
+        from .networks.cenet import channel_slices
+        sl = channel_slices(Cc)
+        m = p + ".mca"
+        # CCU(BN(x))
+        gate_bc = self.buf(key + ".ccu_gate", (B, Cc), torch.float32)
+        ws = self.buf(key + ".ccu_ws", (B * ops.ccu_nchunk(HW) * Cc * 3,), torch.float32)
+        bn1d = B > 1                                                     # cfam.py:260-261
+        ops.ccu_gate(x, w[p + ".bn1.s"], w[p + ".bn1.t"], w[m + ".ccu.fc1"], w[m + ".ccu.fc2"],
+                     w[m + ".ccu.bn.s"] if bn1d else None, w[m + ".ccu.bn.t"] if bn1d else None, gate_bc, ws, B, HW, Cc)
+        x1 = self.buf(key + ".x1", (Mtok, Cc))
+        ops.affine_gate(x, x1, w[p + ".bn1.s"], w[p + ".bn1.t"], gate_bc, B, HW, Cc)
+        g = self.buf(key + ".g", (Mtok, Cc))
+        self._lin(x1, m + ".gate", g)
+        # MultiOrderDWConv(x1)
+        v = m + ".value"
+        dwb = self.buf(key + ".dwb", (Mtok, Cc))
+        cat = self.buf(key + ".cat", (Mtok, Cc))
+        for i, rate in enumerate(_MCA_RATES[Cc]):
+            a0, a1 = sl[i]
+            d = f"{v}.dlps.{i}"
+            ops.dwconv3x3(x1, dwb, w[d + ".dw.w"], B, H, W, a1 - a0, ldx=Cc, ldy=Cc, x_off=a0, y_off=a0,
+                          scale=w[d + ".dw.s"], shift=w[d + ".dw.t"], dil=rate, act=ACT_RELU)
+            ops.gemm(dwb, w[d + ".pw.w"], cat, M=Mtok, N=a1 - a0, K=a1 - a0, lda=Cc, ldw=w[d + ".pw.w"].shape[1], ldc=Cc,
+                     bias=w[d + ".pw.b"], act=ACT_RELU, a_off=a0, c_off=a0, impl=self.gemm_impl)
+        r0, r1 = sl[3]
+        d = f"{v}.dlps.3"
+        pooled = self.buf(key + ".pooled", (B * 49 * (r1 - r0),), torch.float32)
+        ops.pool_branch(x1, Cc, r0, cat, Cc, r0, w[d + ".w"], w[d + ".s"], w[d + ".t"], 0.01, pooled, B, H, W, r1 - r0)
+        sv = self.buf(key + ".sv", (Mtok, Cc))
+        self._lin(cat, v + ".PW", sv, act=ACT_SILU, mul=g, ldmul=Cc, mul_act=ACT_SILU)     # SiLU(g)*SiLU(v)
+        y = self.buf(key + ".y", (Mtok, Cc))
+        self._lin(sv, m + ".proj2", y, res1=x, ldr1=Cc, res1_cscale=w[p + ".bn1.s"])        # + BN(x) shortcut
+        # Nonlocal(y) fused with layer_scale_1 and the outer residual
+        n = m + ".denoising_module"
+        tpg = self.buf(key + ".tpg", (Mtok, 3 * Cc))
+        self._lin(y, n + ".tpg", tpg)
+        att = self._nonlocal_core(tpg, B, HW, Cc, key + ".nl")
+        xa = self.buf(key + ".xa", (Mtok, Cc))
+        self._lin(att, n + ".out", xa, res1=y, ldr1=Cc, res1_cscale=w[n + ".res_scale"], res2=x, ldr2=Cc)
+        # Mlp
+        q = p + ".mlp"
+        h1 = self.buf(key + ".h1", (Mtok, 4 * Cc))
+        self._lin(xa, q + ".fc1", h1)
+        h2 = self.buf(key + ".h2", (Mtok, 4 * Cc))
+        ops.dwconv3x3(h1, h2, w[q + ".dw.w"], B, H, W, 4 * Cc, bias=w[q + ".dw.b"], act=ACT_GELU)
+        u = self.buf(key + ".srm_u", (Mtok, 3), torch.float32)
+        ops.row_stats(h2, u, unbiased=True)
+        gm = self.buf(key + ".srm_g", (Mtok,), torch.float32)
+        ss, st = w[q + ".srm.bn"]
+        ops.srm_gate(u, gm, w[q + ".srm.pw"], w[q + ".srm.dw"], ss, st, B, H, W)
+        out = self.buf(key + ".out", (Mtok, Cc))
+        self._lin(h2, q + ".fc2", out, row_scale=gm, res1=xa, ldr1=Cc)
+        self._tap(p, out, B, H, W, Cc)
+        return out
+
+    def _up(self, x, B, H, W, Cin, Cout, p, kind, key, out=None, ldc=None, c_off=0):
+        """EUCB (blocks.py:317-321) or UpConv (blocks.py:206-221): [B,H,W,Cin] -> [B,2H,2W,Cout]"""
+        w = self.w
+        Mo = B * 4 * H * W
+        if out is None:
+            out = self.buf(key + ".out", (Mo, Cout))
+            ldc = Cout
+        if kind == "eucb":
+            t = self.buf(key + ".dw", (Mo, Cin))
+            ops.dwconv3x3(x, t, w[p + ".dw.w"], B, 2 * H, 2 * W, Cin, scale=w[p + ".dw.s"], shift=w[p + ".dw.t"],
+                          up2=True, act=ACT_LEAKY, slope=0.2)
+            ops.gemm(t, w[p + ".pw.w"], out, M=Mo, N=Cout, K=Cin, lda=Cin, ldw=w[p + ".pw.w"].shape[1], ldc=ldc,
+                     bias=w[p + ".pw.b"], c_off=c_off, impl=self.gemm_impl)
+        else:
+            t = self.buf(key + ".up", (B, 2 * H, 2 * W, Cin))
+            ops.upsample2x_ac(x, t, B, H, W, Cin)
+            ops.conv_nhwc(t, w[p + ".conv.w"], out, 3, 1, 1, bias=w[p + ".conv.b"], act=ACT_LEAKY, slope=0.2, N=Cout,
+                          ldc=ldc, c_off=c_off, impl=self.gemm_impl)
+        return out
+
+    def _dseb(self, skip, dec, B, H, W, Cc, p, heads, key):
+        """dseb.py:153-165; returns mixer(z) + skip + dec  (== dec + DSEBlock(skip, dec), decoders.py:95)"""
+        w = self.w
+        HW, E = H * W, 2 * Cc
+        y = self.buf(key + ".y", (B, E, H, W))                         # NCHW cat([dec, skip])
+        ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
+        ops.nhwc_to_nchw(skip, y, B, HW, Cc, E, Cc)
+        tok = y.view(B * HW, E)                                        # the reference's `.view` reinterpretation
+        gate = self._diff_attention(tok, B, HW, E, heads, p + ".diffattn", key + ".da")
+        z = self.buf(key + ".z", (B, E, H, W))
+        ops.fea_combine(y, gate, z, w[p + ".fea_w"], B, E, H, W, self.cfg["scale_factors"])
+        zt = self.buf(key + ".zt", (B * HW, E))
+        ops.nchw_to_nhwc(z, zt, B, HW, E)
+        out = self.buf(key + ".out", (B * HW, Cc))
+        ops.linear(zt, w[p + ".mixer.w"], out, res1=skip, ldr1=Cc, res2=dec, ldr2=Cc, impl=self.gemm_impl)
+        if self.taps is not None:
+            self.taps[p] = (out.float() - dec.float()).reshape(B, H, W, Cc).permute(0, 3, 1, 2).clone()
+        return out
+
+    def _resblock(self, x, B, H, W, Cin, Cout, k, p, key):
+        """modules/unet.py:201-214 with BN folded; x [B,H,W,Cin] -> [B*H*W,Cout]"""
+        w = self.w
+        Mtok = B * H * W
+        x4 = x.view(B, H, W, Cin)
+        o1 = self.buf(key + ".o1", (B, H, W, Cout))
+        ops.conv_nhwc(x4, w[p + ".c1.w"], o1, k, 1, k // 2, bias=w[p + ".c1.b"], act=ACT_LEAKY, slope=0.01,
+                      impl=self.gemm_impl)
+        if (p + ".c3.w") in w:
+            r = self.buf(key + ".r", (Mtok, Cout))
+            ops.gemm(x, w[p + ".c3.w"], r, M=Mtok, N=Cout, K=Cin, lda=Cin, ldw=w[p + ".c3.w"].shape[1], ldc=Cout,
+                     bias=w[p + ".c3.b"], impl=self.gemm_impl)
+        else:
+            r = x
+        o2 = self.buf(key + ".o2", (Mtok, Cout))
+        ops.conv_nhwc(o1, w[p + ".c2.w"], o2, k, 1, k // 2, bias=w[p + ".c2.b"], act=ACT_LEAKY, slope=0.01,
+                      act_after_res=True, res1=r, ldr1=Cout, impl=self.gemm_impl)
+        return o2
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _run(self, x_in, B, H, W, out_logits, out_labels):
+        cfg, w = self.cfg, self.w
+        Cin, ncls = cfg["input_channels"], cfg["num_classes"]
+        # input -> channels-last compute dtype (for Cin == 1 NCHW and NHWC coincide)
+        xc = self.buf("x", (B * H * W, Cin))
+        if Cin == 1:
+            ops.affine_gate(x_in, xc, None, None, None, B, H * W, 1)
+        else:
+            ops.nchw_to_nhwc(x_in, xc, B, H * W, Cin)
+        feats = self._encoder(xc, B, H, W, Cin)
+        (x1, H1, W1, C1), (x2, H2, W2, C2), (x3, H3, W3, C3), (x4, H4, W4, C4) = feats
+        d = self._cfam(x4, B, H4, W4, C4, "decoder.dec4", "dec4")
+        heads = cfg["diffatt_num_heads"]
+        for lvl, (sk, Hs, Ws, Cs), hi, Cprev in ((3, feats[2], 0, C4), (2, feats[1], 1, C3), (1, feats[0], 2, C2)):
+            up = self._up(d, B, Hs // 2, Ws // 2, Cprev, Cs, f"decoder.up{lvl}", cfg["dec_up_block"], f"up{lvl}")
+            self._tap(f"decoder.up{lvl}", up, B, Hs, Ws, Cs)
+            xin = self._dseb(sk, up, B, Hs, Ws, Cs, f"decoder.skip_enhancer{lvl}", heads[hi], f"se{lvl}")
+            d = self._cfam(xin, B, Hs, Ws, Cs, f"decoder.dec{lvl}", f"dec{lvl}")
+        # ---- OutHead (out.py:69-75) ----
+        om = C1 // 2
+        Hh, Wh = H // 2, W // 2
+        z = self.buf("head.z", (B * Hh * Wh, 2 * om))
+        rb = self._resblock(xc, B, H, W, Cin, om, 5, "out.rb.0", "head.rb")
+        ops.maxpool2_scale(rb, z, 2 * om, om, w["out.w"], B, H, W, om)
+        self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
+        o = self._resblock(z, B, Hh, Wh, 2 * om, 2 * om, 3, "out.out.0", "head.out")
+        yh = self.buf("head.y", (B * Hh * Wh, ncls), torch.float32)
+        self._lin(o, "out.head", yh)
+        ops.head_upsample_argmax(yh, out_logits, out_labels, B, Hh, Wh, ncls)
+
+    @torch.no_grad()
+    def forward(self, x, labels=False, out=None):
+        """x: [B,Cin,H,W] float32 CUDA.  Returns logits [B,ncls,H,W] fp32, or int64 labels [B,H,W] if labels."""
+        if x.device != self.dev:
+            raise RuntimeError(f"input on {x.device}, engine on {self.dev}")
+        if x.dim() != 4 or x.shape[1] != self.cfg["input_channels"]:
+            raise ValueError(f"expected [B,{self.cfg['input_channels']},H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 32 or W % 32:
+            raise ValueError("H and W must be multiples of 32 (four stride-2 stages after the stride-4 stem)")
+        if self._wver != self._weights_version():
+            self.pack()
+        ncls = self.cfg["num_classes"]
+        key = (B, H, W, bool(labels))
+        self._plan_key = (B, H, W)
+        x_in = self.buf("x_in", (B, x.shape[1], H, W), torch.float32)
+        x_in.copy_(x if x.dtype == torch.float32 else x.float())
+        if out is None:
+            out = (torch.empty((B, H, W), device=self.dev, dtype=torch.int64) if labels
+                   else torch.empty((B, ncls, H, W), device=self.dev, dtype=torch.float32))
+        res = self.buf("res.labels" if labels else "res.logits", out.shape, out.dtype)
+        args = (x_in, B, H, W, None if labels else res, res if labels else None)
+        if not self.use_graph or self.taps is not None:
+            self._run(*args)
+        else:
+            g = self._graphs.get(key)
+            if g is None:
+                self._run(*args)                                   # eager warm-up: allocates every workspace
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(*args)
+                self._graphs[key] = g
+            g.replay()
+        out.copy_(res)
+        return out
+
+    def forward_train(self, x):
+        raise NotImplementedError(
+            "cenet_b200: the training path (batch-statistics BatchNorm, DropPath, hand-written backward kernels) is "
+            "not built yet; call .eval() for inference.  There is deliberately no autograd / PyTorch fallback.")

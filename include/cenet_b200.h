@@ -1,0 +1,172 @@
+/*
+ * cenet_b200.h -- C ABI of libcenet_b200.so: hand-written sm_100a kernels for the CENet forward hot path.
+ *
+ * The reference (xmindflow/cenet) is pure PyTorch-eager: it owns no native code, so there is no reference
+ * FFI to mirror symbol-for-symbol.  Each entry point below instead replaces the ATen/cuDNN/cuBLAS call
+ * sequence of one reference site (cited as file:line relative to /root/reference/src/networks/cenet/ and
+ * /root/reference/src/utils/).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions:
+ *   - plain pointers + sizes only; the caller owns ALL device memory, including workspaces;
+ *   - kernels never allocate, never synchronise, and enqueue on the stream passed last;
+ *   - return 0 on success, negative on error; cenet_last_error() gives the message (thread-local);
+ *   - activations are channels-last: an image batch [B,H,W,C] is also the row-major matrix [B*H*W, C];
+ *   - dtype codes: CENET_F32 / CENET_BF16; "fp32 vectors" (bias, gains, folded BN) are always float.
+ */
+#ifndef CENET_B200_H
+#define CENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cenet_stream_t; /* cudaStream_t */
+
+enum { CENET_F32 = 0, CENET_BF16 = 1 };
+enum { CENET_ACT_NONE = 0, CENET_ACT_GELU = 1, CENET_ACT_RELU = 2, CENET_ACT_LEAKY = 3, CENET_ACT_SILU = 4,
+       CENET_ACT_SIGMOID = 5 };
+enum { CENET_GEMM_AUTO = -1, CENET_GEMM_SIMT = 0, CENET_GEMM_TCGEN05 = 1 };
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+const char* cenet_last_error(void);
+int cenet_abi_version(void);
+/* number of kernels launched by this library in this process (bench.py's `gpu_launches`) */
+long long cenet_launch_count(void);
+
+/* ---- GEMM / implicit-GEMM convolution with fused epilogue ---------------------------------------------
+ * C[M,N] = epilogue( A[M,K] * W[N,K]^T ).   Replaces every nn.Linear / 1x1 Conv2d / dense Conv2d of the
+ * path (pvtv2.py:41-45,90-106,164-165,68; cfam.py:150-157,301-303; dseb.py:164; unet.py:201-214;
+ * blocks.py:209-214; nlb.py:107-143) together with the bias / BatchNorm(eval, folded) / activation /
+ * residual / gating ops that follow them.
+ *   epilogue, in order:  v = alpha*acc;  v *= row_scale[m];  v += bias[n] (or bias[m]);
+ *                        if(!act_after_res) v = act(v);      v *= mul_act(mul[m,n]);
+ *                        v += res1[m,n]*(res1_cscale ? res1_cscale[n] : res1_scale);  v += res2[m,n];
+ *                        if(act_after_res) v = act(v).
+ * conv != 0: A is an NHWC image [Bimg,H,W,Cin]; M = Bimg*Ho*Wo; K = KH*KW*Cin ordered (kh,kw,cin);
+ *            W is [N, KH*KW*Cin] (the reference's [Cout,Cin,KH,KW] weight permuted once at pack time).
+ * batch > 1: z = zo*batch_inner + zi; pointer offsets are zo*bs_outer + zi*bs_inner elements.
+ * impl: CENET_GEMM_TCGEN05 needs bf16 A and W, K-major W, K % 8 == 0, 16-byte aligned rows.
+ */
+typedef struct {
+  int M, N, K;
+  int batch, batch_inner;
+  const void* A; int a_dtype; long long lda, a_bs_outer, a_bs_inner;
+  int conv, Bimg, H, W, Cin, KH, KW, stride, pad, Ho, Wo;
+  const void* Wt; int w_dtype; long long ldw, w_bs_outer, w_bs_inner; int w_nmajor;
+  void* C; int c_dtype; long long ldc, c_bs_outer, c_bs_inner;
+  float alpha; const float* bias; int bias_per_row; const float* row_scale;
+  int act; float slope; int act_after_res;
+  const void* res1; int res1_dtype; long long ldr1; const float* res1_cscale; float res1_scale;
+  const void* res2; int res2_dtype; long long ldr2;
+  const void* mul; int mul_dtype; long long ldmul; int mul_act;
+  int impl;
+} cenet_gemm_args;
+int cenet_gemm(const cenet_gemm_args* a, cenet_stream_t s);
+
+/* ---- normalisation / row reductions --------------------------------------------------------------------
+ * LayerNorm over the last dim (pvtv2.py:146-147,189,320; eps 1e-6 / 1e-5). */
+int cenet_layernorm(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                    long long rows, int C, float eps, cenet_stream_t s);
+/* in-place softmax over rows of length n (materialised attention path; nlb.py:128, multihead_diffattn.py:108) */
+int cenet_softmax_rows(void* x, int dtype, long long rows, int n, long long ld, cenet_stream_t s);
+/* per-row [max, mean, std] over C channels -> stats[rows,3] fp32 (SRM, cfam.py:94-97; unbiased std) */
+int cenet_row_stats(const void* x, int dtype, long long rows, int C, long long ld, int unbiased, float* stats,
+                    cenet_stream_t s);
+
+/* ---- depthwise 3x3 family -----------------------------------------------------------------------------
+ * y[b,h,w,c] = act( (sum_taps w[tap,c]*x[b,h+dh*dil,w+dw*dil,c] + bias[c]) * scale[c] + shift[c] )
+ * Mix-FFN DWConv+GELU (pvtv2.py:364-370,42-43), CFAM Mlp dwconv+GELU (cfam.py:151-152), SepConvBN depthwise
+ * + BN + ReLU with dilation (blocks.py:169-178), EUCB nearest-x2 + dw3x3 + BN + LeakyReLU (blocks.py:303-311;
+ * up2 = 1: x is [B,H/2,W/2,C]).  w is [9,C] fp32 (tap-major).  ldx/ldy: channel pitch (>= C) so that channel
+ * slices of a wider tensor can be processed in place. */
+int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, const float* w9c,
+                    const float* bias, const float* scale, const float* shift, int B, int H, int W, int C, int dil,
+                    int up2, int act, float slope, cenet_stream_t s);
+
+/* ---- layout ------------------------------------------------------------------------------------------- */
+/* y_nchw[b, coff+c, h, w] = x_nhwc[b,h,w,c]   (torch.cat([dec,skip],1) of dseb.py:156 when called twice) */
+int cenet_nhwc_to_nchw(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, int B, int HW, int C,
+                       int Ctot, int coff, cenet_stream_t s);
+/* y_nhwc[b,hw,c] (pitch ldy) = x_nchw[b,c,hw] */
+int cenet_nchw_to_nhwc(const void* x, int x_dtype, void* y, int y_dtype, long long ldy, int B, int HW, int C,
+                       cenet_stream_t s);
+/* out[m, (kh,kw,ci)] = x_nhwc patch, zero padded, row pitch Kpad >= KH*KW*Cin (strided / non-overlapping convs:
+ * patch embeds pvtv2.py:164-165 and the SR conv pvtv2.py:68 feed cenet_gemm through this) */
+int cenet_im2col(const void* x, int x_dtype, void* out, int o_dtype, int B, int H, int W, int Cin, int KH, int KW,
+                 int stride, int pad, int Ho, int Wo, int Kpad, cenet_stream_t s);
+/* bilinear x2, align_corners=True, NHWC (UpConv, blocks.py:210) */
+int cenet_upsample2x_ac(const void* x, int x_dtype, void* y, int y_dtype, int B, int H, int W, int C,
+                        cenet_stream_t s);
+/* y[b,h/2,w/2,coff+c] = wch[c] * max2x2(x[b,h,w,c])   (out.py:43,70: MaxPool2d then `self.w*`) */
+int cenet_maxpool2_scale(const void* x, int x_dtype, void* y, int y_dtype, long long ldy, int coff, const float* wch,
+                         int B, int H, int W, int C, cenet_stream_t s);
+/* y = (x*scale[c]+shift[c]) * gate[b,c]   (BatchNorm(eval) then CCU gate, cfam.py:370,263-264) */
+int cenet_affine_gate(const void* x, int x_dtype, void* y, int y_dtype, const float* scale, const float* shift,
+                      const float* gate_bc, int B, int HW, int C, cenet_stream_t s);
+
+/* ---- DSEB (dseb.py) -------------------------------------------------------------------------------------
+ * FEA + gate combine on the NCHW buffer y[B,C2,H,W]:  z = 2*y + w[c]*edge(y) + gate*y  (dseb.py:63-76,157,118,162)
+ * scales: up to 3 scale factors.  gate has the same flat layout as y (the `.view` reinterpretation). */
+int cenet_fea_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2, int H,
+                      int W, const float* scales, int nscales, cenet_stream_t s);
+/* P[:, 2i] -= lambda * P[:, 2i+1] over contiguous maps of `map_elems` elements (multihead_diffattn.py:115-116) */
+int cenet_diff_combine(void* P, int dtype, long long npairs, long long map_elems, float lambda, cenet_stream_t s);
+/* y = x * rsqrt(mean_seg(x^2)+eps) * mult over segments of `seg` channels (rms_norm.py:15-22 and the
+ * `*(1-lambda_init)` of multihead_diffattn.py:123) */
+int cenet_rmsnorm_seg(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, int seg, float eps,
+                      float mult, cenet_stream_t s);
+/* Fused differential flash attention (multihead_diffattn.py:92-124 without the N x N maps).
+ * qkv: [B, N, 3E] bf16 rows (q | k | v), heads h, hd = E/(2h).  out: [B, N, E] bf16 =
+ * RMSNorm_{2hd}( softmax(q_{2i}k_{2i}^T/sqrt(hd)) v_i - lambda*softmax(q_{2i+1}k_{2i+1}^T/sqrt(hd)) v_i ) * mult */
+int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
+                         float mult, cenet_stream_t s);
+
+/* ---- encoder attention (pvtv2.py:88-105): softmax(q k^T * scale) v with <= 64 keys, head_dim 64 ------------ */
+int cenet_sr_attention(const void* q, int q_dtype, const void* kv, int kv_dtype, void* out, int o_dtype, int B, int N,
+                       int Nk, int C, int heads, float scale, cenet_stream_t s);
+
+/* ---- non-local block core (nlb.py:116-137): out[b,n,:] = softmax_p(theta_n . phi_p * scale) g_p ------------
+ * tpg: [B, N, 3C] bf16 rows (theta | phi | g); out [B,N,C] bf16.  C in {64,128}. */
+int cenet_nonlocal_flash(const void* tpg, void* out, int B, int N, int C, float scale, cenet_stream_t s);
+
+/* ---- CFAM statistics (cfam.py) ------------------------------------------------------------------------------
+ * CCU (cfam.py:251-264): stats of (x*scale+shift) over HW per (b,c) -> per-channel 3->3->1 MLP -> optional
+ * BN1d(eval affine: bn_scale/bn_shift, pass NULL when B == 1) -> sigmoid -> gate[B,C].
+ * ws: fp32 workspace of B*nchunk*C*3 floats, nchunk = cenet_ccu_nchunk(HW). */
+int cenet_ccu_nchunk(int HW);
+int cenet_ccu_gate(const void* x, int x_dtype, const float* scale, const float* shift, const float* fc1_c33,
+                   const float* fc2_c3, const float* bn_scale, const float* bn_shift, float* gate_bc, float* ws,
+                   int B, int HW, int C, cenet_stream_t s);
+/* SRM gate (cfam.py:97-100): u[B,H,W,3] -> sigmoid(BN(GELU(pwc(u)+dwc3x3(u)))) -> gate[B*H*W]
+ * pw: 3 floats, dw: [3,3,3] (cin,kh,kw) floats, bn: scale, shift */
+int cenet_srm_gate(const float* u, float* gate, const float* pw3, const float* dw27, float bn_scale, float bn_shift,
+                   int B, int H, int W, cenet_stream_t s);
+/* image-pooling branch of MultiOrderDWConv (cfam.py:209-218,231-232):
+ *  step 1: pooled[b,7,7,r] = LeakyReLU(BN(conv1x1(AdaptiveAvgPool7(x[..., coff:coff+r]))))
+ *  step 2: y[b,h,w,coff_y+c] = bilinear(H,W; align False) of bilinear(49x49; align True) of pooled */
+int cenet_pool_branch(const void* x, int x_dtype, long long ldx, int coff, void* y, int y_dtype, long long ldy,
+                      int coff_y, const float* w_rr, const float* bn_scale, const float* bn_shift, float slope,
+                      float* pooled_ws, int B, int H, int W, int r, cenet_stream_t s);
+
+/* ---- head (out.py:74 + metrics_eval.py:52) -------------------------------------------------------------------
+ * y: [B,h,w,ncls] fp32 (NHWC) -> logits [B,ncls,2h,2w] fp32 (bilinear x2, align_corners=False) and / or
+ * labels [B,2h,2w] int64 = argmax over classes, lowest index on ties.  Either output may be NULL. */
+int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls,
+                               cenet_stream_t s);
+
+/* ---- fused Dice + CE (utils/core.py:57-80,176-188) ------------------------------------------------------------
+ * logits [B,ncls,H,W] fp32, labels [B,H,W] int64.  ws: (3*ncls+1)*nblk + 3*ncls+3 floats, nblk =
+ * cenet_loss_nblocks(B*H*W).  loss_out[0] = w_dice*dice + w_ce*ce; loss_out[1+i] = per-class dice score.
+ * dlogits (nullable): d loss / d logits, same shape as logits.  Deterministic (no float atomics). */
+int cenet_loss_nblocks(long long npix);
+int cenet_dice_ce(const float* logits, const long long* labels, float* loss_out, float* dlogits, float* ws, int B,
+                  int ncls, int HW, float w_dice, float w_ce, float grad_scale, cenet_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENET_B200_H */

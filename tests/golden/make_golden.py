@@ -1,0 +1,142 @@
+"""Generates tests/golden/*.pt by running the REAL reference (/root/reference/src/networks, imported through
+oracle/ref_shim.py) in the build container.  Re-run with:  python tests/golden/make_golden.py
+
+Each fixture stores what is needed to re-create the inputs deterministically elsewhere (config name, seeds; the
+weights come from `cenet_b200.networks.CENet` built under torch.manual_seed(seed) and passed through
+oracle.fixtures.perturb_state -- loaded into the reference with strict=True, which also pins the 801-key
+state_dict contract) plus the reference's outputs: strided logits, label histogram and per-module tap statistics.
+Small module-level fixtures (DiffAttn, FEA, Nonlocal, CCU, SRM, ...) store full tensors.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import fixtures, ref_shim  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_pair(nets, name, seed=1234):
+    from cenet_b200.networks import CENet
+    kw = fixtures.CONFIGS[name]
+    torch.manual_seed(seed)
+    mine = CENet(**kw)
+    sd = fixtures.perturb_state(mine.state_dict(), seed)
+    ref = nets.CENet(**kw).eval()
+    ref.load_state_dict(sd, strict=True)
+    return ref, sd, kw
+
+
+def model_fixture(nets, name, batch):
+    ref, sd, kw = build_pair(nets, name)
+    x = fixtures.synth_input(name, batch)
+    taps = {}
+    hooks = []
+    for mod_name in ["decoder.dec4", "decoder.dec3", "decoder.dec2", "decoder.dec1", "decoder.up3", "decoder.up2",
+                     "decoder.up1", "decoder.skip_enhancer3", "decoder.skip_enhancer2", "decoder.skip_enhancer1"]:
+        m = ref.get_submodule(mod_name)
+        hooks.append(m.register_forward_hook(lambda mod, i, o, n=mod_name: taps.__setitem__(n, o.detach())))
+    with torch.no_grad():
+        feats = ref.backbone(torch.cat([x, x, x], 1) if x.shape[1] == 1 else x)
+        y = ref(x)
+    for h in hooks:
+        h.remove()
+    for i, f in enumerate(feats):
+        taps[f"backbone.stage{i+1}"] = f
+    lab = torch.argmax(torch.softmax(y, 1), 1)
+    out = dict(config=name, batch=batch, seed=1234, input_seed=0,
+               logits_strided=y[:, :, ::8, ::8].clone(), logits_mean=y.mean().item(), logits_std=y.std().item(),
+               logits_abs_sum=y.abs().sum().item(),
+               label_hist=torch.bincount(lab.flatten(), minlength=kw["num_classes"]),
+               labels_strided=lab[:, ::4, ::4].clone(),
+               taps={k: dict(mean=v.mean().item(), std=v.std().item(), sample=v.flatten()[:: max(1, v.numel() // 512)][:512].clone())
+                     for k, v in taps.items()})
+    torch.save(out, os.path.join(HERE, f"model_{name}_b{batch}.pt"))
+    print(name, batch, "logits std", out["logits_std"], "hist", out["label_hist"].tolist())
+
+
+def module_fixtures(nets):
+    """Small full-tensor fixtures of the reference's own sub-modules (seeded default init + perturbed BN stats)."""
+    import networks.cenet.modules.cfam as cfam
+    import networks.cenet.modules.dseb as dseb
+    import networks.cenet.modules.multihead_diffattn as mda
+    import networks.cenet.modules.nlb as nlb
+    import networks.cenet.modules.blocks as blocks
+    import networks.cenet.pvtv2 as pvt
+    import networks.cenet.out as outm
+    out = {}
+
+    def run(key, mod, *inputs):
+        mod.eval()
+        sd = fixtures.perturb_state(mod.state_dict(), 7)
+        mod.load_state_dict(sd)
+        with torch.no_grad():
+            y = mod(*inputs)
+        out[key] = dict(state=sd, inputs=[i.clone() if torch.is_tensor(i) else i for i in inputs], output=y.clone())
+
+    g = torch.Generator().manual_seed(11)
+    torch.manual_seed(11)
+    run("diffattn_e64_h2_n80", mda.MultiheadDiffAttn(64, depth=2, num_heads=2), torch.randn(2, 80, 64, generator=g))
+    run("diffattn_e32_h2_n64", mda.MultiheadDiffAttn(32, depth=3, num_heads=2), torch.randn(2, 64, 32, generator=g) * 2)
+    run("fea_2scales", dseb.FEA(16, [0.8, 0.4]), torch.randn(2, 16, 14, 14, generator=g))
+    run("fea_3scales", dseb.FEA(8, [1.0, 0.75, 0.5]), torch.randn(1, 8, 28, 28, generator=g))
+    run("dseb_c16", dseb.DSEBlock(16, [0.8, 0.4], 2, 14, mode="cat", depth=3),
+        torch.randn(2, 16, 14, 14, generator=g), torch.randn(2, 16, 14, 14, generator=g))
+    run("nonlocal_c64", nlb.Nonlocal(64), torch.randn(2, 64, 14, 14, generator=g))
+    run("ccu_c64_b2", cfam.CCU(64), torch.randn(2, 64, 14, 14, generator=g))
+    run("ccu_c64_b1", cfam.CCU(64), torch.randn(1, 64, 14, 14, generator=g))
+    run("srm", cfam.SRM(), torch.randn(2, 64, 14, 14, generator=g))
+    run("modw_c64", cfam.MultiOrderDWConv(64, rates=[2, 3, 5]), torch.randn(2, 64, 28, 28, generator=g))
+    run("cfam_c64", cfam.CFAModule(64, ffn_ratio=4, drop_rate=0, drop_path_rate=0, act_type="GELU", norm_type="BN",
+                                   init_value=1e-6, attn_channel_split=[1, 3, 4], attn_act_type="SiLU",
+                                   mca_rates=[2, 3, 5]), torch.randn(2, 64, 14, 14, generator=g))
+    run("eucb", blocks.EUCB(64, 32, kernel_size=3, stride=1, activation="leakyrelu"), torch.randn(2, 64, 7, 7, generator=g))
+    run("upconv", blocks.UpConv(64, 32, kernel_size=3, stride=1, activation="leakyrelu"), torch.randn(2, 64, 7, 7, generator=g))
+    run("pvt_attn_sr2", pvt.Attention(128, num_heads=2, qkv_bias=True, sr_ratio=2), torch.randn(2, 196, 128, generator=g), 14, 14)
+    run("pvt_block_sr1", pvt.Block(64, 1, mlp_ratio=4, qkv_bias=True, sr_ratio=1), torch.randn(2, 49, 64, generator=g), 7, 7)
+    run("outhead", outm.OutHead(dec_in_channels=64, x_in_channels=1, out_channels=4, up_block="upcn"),
+        torch.randn(1, 64, 16, 16, generator=g), torch.randn(1, 1, 64, 64, generator=g))
+    torch.save(out, os.path.join(HERE, "modules.pt"))
+    print("modules:", list(out))
+
+
+def loss_fixture():
+    import types
+    import importlib.util
+    # utils/utils.py pulls thop/ptflops/fvcore/matplotlib (absent here); core.py only needs `flatten` from it, which
+    # the dice/ce path never calls -> give core.py a stub parent package and load the file itself unmodified
+    pkg = types.ModuleType("refutils")
+    pkg.__path__ = []
+    stub = types.ModuleType("refutils.utils")
+    stub.flatten = None
+    sys.modules["refutils"], sys.modules["refutils.utils"] = pkg, stub
+    spec = importlib.util.spec_from_file_location("refutils.core", "/root/reference/src/utils/core.py")
+    core = importlib.util.module_from_spec(spec)
+    sys.modules["refutils.core"] = core
+    spec.loader.exec_module(core)
+    g = torch.Generator().manual_seed(5)
+    out = {}
+    for ncls, B, S in ((4, 2, 32), (9, 3, 24), (2, 1, 40)):
+        logits = torch.randn(B, ncls, S, S, generator=g) * 2
+        logits.requires_grad_(True)
+        labels = torch.randint(0, ncls, (B, S, S), generator=g).float()
+        args = types.SimpleNamespace(loss_type="dice,ce", loss_weights="0.5,0.5")
+        crit = core.Criterion(ncls, args)
+        loss = crit(logits, labels)
+        loss.backward()
+        out[f"c{ncls}"] = dict(logits=logits.detach().clone(), labels=labels.long(), loss=loss.detach().clone(),
+                               grad=logits.grad.clone())
+    torch.save(out, os.path.join(HERE, "loss.pt"))
+    print("loss:", {k: v["loss"].item() for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    nets = ref_shim.import_reference()
+    module_fixtures(nets)
+    loss_fixture()
+    model_fixture(nets, "acdc", 1)
+    model_fixture(nets, "synapse", 2)
+    model_fixture(nets, "skin", 1)

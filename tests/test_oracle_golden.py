@@ -1,0 +1,107 @@
+"""Pins the CPU oracle (oracle/cenet_oracle.py) to outputs of the REAL reference recorded in tests/golden/ by
+tests/golden/make_golden.py.  Runs on CPU; this is what makes the oracle trustworthy as the GPU tests' checker."""
+import os
+
+import pytest
+import torch
+
+from oracle import cenet_oracle as O
+from oracle import fixtures
+
+from conftest import GOLDEN
+
+TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+def _case(golden_modules, key):
+    c = golden_modules[key]
+    return c["state"], c["inputs"], c["output"]
+
+
+def test_diffattn(golden_modules):
+    for key, heads, depth in (("diffattn_e64_h2_n80", 2, 2), ("diffattn_e32_h2_n64", 2, 3)):
+        sd, (x,), y = _case(golden_modules, key)
+        sd = {"m." + k: v for k, v in sd.items()}
+        torch.testing.assert_close(O.diff_attention(sd, "m", x, heads, depth), y, **TOL)
+
+
+def test_fea(golden_modules):
+    for key, sc in (("fea_2scales", [0.8, 0.4]), ("fea_3scales", [1.0, 0.75, 0.5])):
+        sd, (x,), y = _case(golden_modules, key)
+        torch.testing.assert_close(O.fea({"m." + k: v for k, v in sd.items()}, "m", x, sc), y, **TOL)
+
+
+def test_dseb(golden_modules):
+    sd, (skip, dec), y = _case(golden_modules, "dseb_c16")
+    out = O.dse_block({"m." + k: v for k, v in sd.items()}, "m", skip, dec, [0.8, 0.4], 2, 3)
+    torch.testing.assert_close(out, y, **TOL)
+
+
+def test_nonlocal_ccu_srm(golden_modules):
+    sd, (x,), y = _case(golden_modules, "nonlocal_c64")
+    torch.testing.assert_close(O.nonlocal_block({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+    for key in ("ccu_c64_b2", "ccu_c64_b1"):                       # B == 1 skips BatchNorm1d (cfam.py:260-261)
+        sd, (x,), y = _case(golden_modules, key)
+        torch.testing.assert_close(O.ccu({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+    sd, (x,), y = _case(golden_modules, "srm")
+    torch.testing.assert_close(O.srm({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+
+
+def test_cfam_and_multi_order(golden_modules):
+    sd, (x,), y = _case(golden_modules, "modw_c64")
+    torch.testing.assert_close(O.multi_order_dwconv({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+    sd, (x,), y = _case(golden_modules, "cfam_c64")
+    torch.testing.assert_close(O.cfa_module({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+
+
+def test_up_blocks(golden_modules):
+    sd, (x,), y = _case(golden_modules, "eucb")
+    torch.testing.assert_close(O.eucb({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+    sd, (x,), y = _case(golden_modules, "upconv")
+    torch.testing.assert_close(O.up_conv({"m." + k: v for k, v in sd.items()}, "m", x), y, **TOL)
+
+
+def test_encoder_pieces(golden_modules):
+    sd, (x, H, W), y = _case(golden_modules, "pvt_attn_sr2")
+    torch.testing.assert_close(O.sr_attention({"m." + k: v for k, v in sd.items()}, "m", x, H, W, 2, 2), y, **TOL)
+    sd, (x, H, W), y = _case(golden_modules, "pvt_block_sr1")
+    torch.testing.assert_close(O.pvt_block({"m." + k: v for k, v in sd.items()}, "m", x, H, W, 1, 1), y, **TOL)
+
+
+def test_out_head(golden_modules):
+    sd, (dec, x), y = _case(golden_modules, "outhead")
+    cfg = O.Cfg(input_channels=1, num_classes=4, out_up_block="upcn")
+    torch.testing.assert_close(O.out_head({"out." + k: v for k, v in sd.items()}, cfg, dec, x), y, **TOL)
+
+
+def test_loss(golden_loss):
+    for key, c in golden_loss.items():
+        ncls = int(key[1:])
+        logits = c["logits"].clone().requires_grad_(True)
+        loss = O.criterion_dice_ce(logits, c["labels"], ncls)
+        loss.backward()
+        torch.testing.assert_close(loss.detach(), c["loss"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(logits.grad, c["grad"], rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1)])
+def test_whole_model(name, batch):
+    """Rebuild the deterministic weights, run the oracle, compare with what the reference produced."""
+    from cenet_b200.networks import CENet
+    g = torch.load(os.path.join(GOLDEN, f"model_{name}_b{batch}.pt"), weights_only=False)
+    kw = fixtures.CONFIGS[name]
+    torch.manual_seed(g["seed"])
+    sd = fixtures.perturb_state(CENet(**kw).state_dict(), g["seed"])
+    x = fixtures.synth_input(name, batch, seed=g["input_seed"])
+    taps = {}
+    with torch.no_grad():
+        y = O.cenet_forward(sd, O.Cfg(**kw), x, taps=taps)
+    torch.testing.assert_close(y[:, :, ::8, ::8], g["logits_strided"], rtol=1e-4, atol=1e-5)
+    assert abs(y.std().item() - g["logits_std"]) < 1e-4
+    lab = O.predict_labels(y)
+    assert torch.equal(torch.bincount(lab.flatten(), minlength=kw["num_classes"]), g["label_hist"])
+    assert torch.equal(lab[:, ::4, ::4], g["labels_strided"])
+    for k, ref in g["taps"].items():
+        v = taps[k]
+        samp = v.flatten()[:: max(1, v.numel() // 512)][:512]
+        torch.testing.assert_close(samp, ref["sample"], rtol=1e-4, atol=1e-5, msg=lambda m, k=k: f"tap {k}: {m}")
