@@ -1,0 +1,299 @@
+"""TEST-ONLY torch emulation of the C-ABI ops (same signatures as cenet_b200.ops, same buffer/pitch/offset semantics).
+
+Purpose: run `cenet_b200.engine.Engine`'s launch plan on CPU (`-m "not gpu"`) to check the HOST logic -- weight
+folding, buffer wiring, pitches and offsets -- against the oracle without a GPU.  It is never imported by the
+product; the product ops have no CPU path.  Arithmetic is done in fp32 and rounded to the buffer dtype on store,
+like the kernels do.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = range(6)
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
+F32, BF16 = 0, 1
+_LAUNCHES = [0]
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
+def _v(t, size, stride, off=0):
+    _LAUNCHES[0] += 0
+    return torch.as_strided(t.view(-1) if t.is_contiguous() else t.contiguous().view(-1), size, stride, off)
+
+
+def _flat(t):
+    assert t.is_contiguous()
+    return t.view(-1)
+
+
+def _act(v, act, slope=0.0):
+    if act == ACT_GELU:
+        return F.gelu(v)
+    if act == ACT_RELU:
+        return F.relu(v)
+    if act == ACT_LEAKY:
+        return F.leaky_relu(v, slope)
+    if act == ACT_SILU:
+        return F.silu(v)
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(v)
+    return v
+
+
+def gemm(a, w, out, *, M, N, K, lda, ldw, ldc, bias=None, bias_per_row=False, row_scale=None, alpha=1.0, act=ACT_NONE,
+         slope=0.0, act_after_res=False, res1=None, ldr1=0, res1_cscale=None, res1_scale=1.0, res2=None, ldr2=0, mul=None,
+         ldmul=0, mul_act=ACT_NONE, conv=None, batch=1, batch_inner=1, a_bs=(0, 0), w_bs=(0, 0), c_bs=(0, 0),
+         w_nmajor=False, impl=GEMM_AUTO, a_off=0, w_off=0, c_off=0):
+    _LAUNCHES[0] += 1
+    af, wf, cf = _flat(a), _flat(w), _flat(out)
+    for z in range(batch):
+        zo, zi = z // batch_inner, z % batch_inner
+        ao = a_off + zo * a_bs[0] + zi * a_bs[1]
+        wo = w_off + zo * w_bs[0] + zi * w_bs[1]
+        co = c_off + zo * c_bs[0] + zi * c_bs[1]
+        if conv is not None:
+            Bimg, H, W, Cin, KH, KW, stride, pad, Ho, Wo = conv
+            x = torch.as_strided(af, (Bimg, H, W, Cin), (H * W * lda, W * lda, lda, 1), ao).float().permute(0, 3, 1, 2)
+            wm = torch.as_strided(wf, (N, K), (ldw, 1), wo).float().view(N, KH, KW, Cin).permute(0, 3, 1, 2)
+            acc = F.conv2d(x, wm, stride=stride, padding=pad).permute(0, 2, 3, 1).reshape(M, N)
+        else:
+            A = torch.as_strided(af, (M, K), (lda, 1), ao).float()
+            Wm = torch.as_strided(wf, (K, N), (ldw, 1), wo).float() if w_nmajor else \
+                torch.as_strided(wf, (N, K), (ldw, 1), wo).float().t()
+            acc = A @ Wm
+        v = alpha * acc
+        if row_scale is not None:
+            v = v * row_scale.view(-1)[:M, None]
+        if bias is not None:
+            v = v + (bias[:M, None] if bias_per_row else bias[None, :N])
+        if not act_after_res:
+            v = _act(v, act, slope)
+        if mul is not None:
+            v = v * _act(torch.as_strided(_flat(mul), (M, N), (ldmul, 1), co if batch > 1 else 0).float(), mul_act)
+        if res1 is not None:
+            r = torch.as_strided(_flat(res1), (M, N), (ldr1, 1), co if batch > 1 else 0).float()
+            v = v + r * (res1_cscale[None, :N] if res1_cscale is not None else res1_scale)
+        if res2 is not None:
+            v = v + torch.as_strided(_flat(res2), (M, N), (ldr2, 1), co if batch > 1 else 0).float()
+        if act_after_res:
+            v = _act(v, act, slope)
+        torch.as_strided(cf, (M, N), (ldc, 1), co).copy_(v)
+    return out
+
+
+def linear(x2d, w, out, bias=None, **kw):
+    M, K = x2d.shape
+    return gemm(x2d, w, out, M=M, N=out.shape[1], K=K, lda=x2d.stride(0), ldw=w.stride(0), ldc=out.stride(0), bias=bias, **kw)
+
+
+def conv_nhwc(x, w, out, ksize, stride, pad, bias=None, **kw):
+    B, H, W, Cin = x.shape
+    Ho = (H + 2 * pad - ksize) // stride + 1
+    Wo = (W + 2 * pad - ksize) // stride + 1
+    N = kw.pop("N", w.shape[0])
+    ldc = kw.pop("ldc", out.shape[-1])
+    return gemm(x, w, out, M=B * Ho * Wo, N=N, K=ksize * ksize * Cin, lda=Cin, ldw=w.stride(0), ldc=ldc, bias=bias,
+                conv=(B, H, W, Cin, ksize, ksize, stride, pad, Ho, Wo), **kw)
+
+
+def layernorm(x2d, out, gamma, beta, eps):
+    _LAUNCHES[0] += 1
+    out.copy_(F.layer_norm(x2d.float(), (x2d.shape[1],), gamma, beta, eps))
+    return out
+
+
+def softmax_rows_(x, rows, n, ld):
+    _LAUNCHES[0] += 1
+    v = torch.as_strided(_flat(x), (rows, n), (ld, 1))
+    v.copy_(torch.softmax(v.float(), -1))
+    return x
+
+
+def row_stats(x2d, stats, unbiased=True):
+    _LAUNCHES[0] += 1
+    xf = x2d.float()
+    stats.copy_(torch.stack([xf.max(1)[0], xf.mean(1), xf.std(1, unbiased=unbiased)], 1))
+    return stats
+
+
+def rmsnorm_seg(x2d, out, seg, eps, mult):
+    _LAUNCHES[0] += 1
+    rows, C = x2d.shape
+    xs = x2d.float().view(rows, C // seg, seg)
+    out.copy_((xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + eps) * mult).view(rows, C))
+    return out
+
+
+def dwconv3x3(x, out, w9c, B, H, W, Cc, *, ldx=None, ldy=None, x_off=0, y_off=0, bias=None, scale=None, shift=None,
+              dil=1, up2=False, act=ACT_NONE, slope=0.0):
+    _LAUNCHES[0] += 1
+    ldx = Cc if ldx is None else ldx
+    ldy = Cc if ldy is None else ldy
+    Hi, Wi = (H // 2, W // 2) if up2 else (H, W)
+    xi = torch.as_strided(_flat(x), (B, Hi, Wi, Cc), (Hi * Wi * ldx, Wi * ldx, ldx, 1), x_off).float().permute(0, 3, 1, 2)
+    if up2:
+        xi = F.interpolate(xi, scale_factor=2, mode="nearest")
+    wt = w9c.t().reshape(Cc, 1, 3, 3)
+    v = F.conv2d(xi, wt, bias, padding=dil, dilation=dil, groups=Cc)
+    if scale is not None:
+        v = v * scale[None, :, None, None] + shift[None, :, None, None]
+    v = _act(v, act, slope)
+    torch.as_strided(_flat(out), (B, H, W, Cc), (H * W * ldy, W * ldy, ldy, 1), y_off).copy_(v.permute(0, 2, 3, 1))
+    return out
+
+
+def nhwc_to_nchw(x, out, B, HW, Cc, Ctot, coff, ldx=None):
+    _LAUNCHES[0] += 1
+    ldx = Cc if ldx is None else ldx
+    xi = torch.as_strided(_flat(x), (B, HW, Cc), (HW * ldx, ldx, 1))
+    torch.as_strided(_flat(out), (B, Cc, HW), (Ctot * HW, HW, 1), coff * HW).copy_(xi.transpose(1, 2))
+    return out
+
+
+def nchw_to_nhwc(x, out, B, HW, Cc, ldy=None):
+    _LAUNCHES[0] += 1
+    ldy = Cc if ldy is None else ldy
+    xi = torch.as_strided(_flat(x), (B, Cc, HW), (Cc * HW, HW, 1))
+    torch.as_strided(_flat(out), (B, HW, Cc), (HW * ldy, ldy, 1)).copy_(xi.transpose(1, 2))
+    return out
+
+
+def im2col(x, out, B, H, W, Cin, k, stride, pad, Ho, Wo, Kpad):
+    _LAUNCHES[0] += 1
+    xi = _flat(x).view(B, H, W, Cin).float().permute(0, 3, 1, 2)
+    cols = F.unfold(xi, k, padding=pad, stride=stride)                 # [B, Cin*k*k, L] ordered (ci, kh, kw)
+    cols = cols.view(B, Cin, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * Cin)
+    o = _flat(out).view(B * Ho * Wo, Kpad)
+    o.zero_()
+    o[:, :k * k * Cin].copy_(cols)
+    return out
+
+
+def upsample2x_ac(x, out, B, H, W, Cc):
+    _LAUNCHES[0] += 1
+    xi = _flat(x).view(B, H, W, Cc).float().permute(0, 3, 1, 2)
+    _flat(out).view(B, 2 * H, 2 * W, Cc).copy_(
+        F.interpolate(xi, scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1))
+    return out
+
+
+def maxpool2_scale(x, out, ldy, coff, wch, B, H, W, Cc):
+    _LAUNCHES[0] += 1
+    xi = _flat(x).view(B, H, W, Cc).float().permute(0, 3, 1, 2)
+    v = (F.max_pool2d(xi, 2) * wch[None, :, None, None]).permute(0, 2, 3, 1)
+    torch.as_strided(_flat(out), (B, H // 2, W // 2, Cc), ((H // 2) * (W // 2) * ldy, (W // 2) * ldy, ldy, 1), coff).copy_(v)
+    return out
+
+
+def affine_gate(x, out, scale, shift, gate_bc, B, HW, Cc):
+    _LAUNCHES[0] += 1
+    v = _flat(x).view(B, HW, Cc).float()
+    if scale is not None:
+        v = v * scale + shift
+    if gate_bc is not None:
+        v = v * gate_bc.view(B, 1, Cc)
+    _flat(out).view(B, HW, Cc).copy_(v)
+    return out
+
+
+def fea_combine(y, gate, z, w_c, B, C2, H, W, scales):
+    _LAUNCHES[0] += 1
+    from oracle import cenet_oracle as O
+    yf = _flat(y).view(B, C2, H, W).float()
+    gf = _flat(gate).view(B, C2, H, W).float()
+    _flat(z).view(B, C2, H, W).copy_(O.fea({"m.w": w_c.view(1, C2, 1, 1)}, "m", yf, list(scales)) + yf + gf * yf)
+    return z
+
+
+def diff_combine_(P, npairs, map_elems, lam):
+    _LAUNCHES[0] += 1
+    v = _flat(P).view(npairs, 2, map_elems)
+    v[:, 0].copy_(v[:, 0].float() - lam * v[:, 1].float())
+    return P
+
+
+def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
+    _LAUNCHES[0] += 1
+    hd = E // heads // 2
+    t = _flat(qkv).view(B, N, 3 * E).float()
+    q = t[..., :E].reshape(B, N, 2 * heads, hd).transpose(1, 2) * hd ** -0.5
+    k = t[..., E:2 * E].reshape(B, N, 2 * heads, hd).transpose(1, 2)
+    v = t[..., 2 * E:].reshape(B, N, heads, 2 * hd).transpose(1, 2)
+    s = torch.softmax(q @ k.transpose(-1, -2), -1).view(B, heads, 2, N, N)
+    o = (s[:, :, 0] - lam * s[:, :, 1]) @ v
+    o = o * torch.rsqrt(o.pow(2).mean(-1, keepdim=True) + eps) * mult
+    _flat(out).view(B, N, E).copy_(o.transpose(1, 2).reshape(B, N, E))
+    return out
+
+
+def sr_attention(q, kv, out, B, N, Nk, Cc, heads, scale):
+    _LAUNCHES[0] += 1
+    hd = Cc // heads
+    qf = _flat(q).view(B, N, heads, hd).float().transpose(1, 2)
+    kvf = _flat(kv).view(B, Nk, 2 * Cc).float()
+    kf = kvf[..., :Cc].reshape(B, Nk, heads, hd).transpose(1, 2)
+    vf = kvf[..., Cc:].reshape(B, Nk, heads, hd).transpose(1, 2)
+    o = torch.softmax(qf @ kf.transpose(-1, -2) * scale, -1) @ vf
+    _flat(out).view(B, N, Cc).copy_(o.transpose(1, 2).reshape(B, N, Cc))
+    return out
+
+
+def nonlocal_flash(tpg, out, B, N, Cc, scale):
+    _LAUNCHES[0] += 1
+    t = _flat(tpg).view(B, N, 3 * Cc).float()
+    o = torch.softmax(t[..., :Cc] @ t[..., Cc:2 * Cc].transpose(1, 2) * scale, -1) @ t[..., 2 * Cc:]
+    _flat(out).view(B, N, Cc).copy_(o)
+    return out
+
+
+def ccu_nchunk(HW):
+    return (HW + 127) // 128
+
+
+def ccu_gate(x, scale, shift, fc1, fc2, bn_scale, bn_shift, gate, ws, B, HW, Cc):
+    _LAUNCHES[0] += 2
+    v = _flat(x).view(B, HW, Cc).float()
+    if scale is not None:
+        v = v * scale + shift
+    u = torch.stack([v.max(1)[0], v.mean(1), v.std(1, unbiased=False)], -1)          # [B,C,3]
+    h = F.relu(torch.einsum("cjk,bck->bcj", fc1, u))
+    zz = torch.einsum("cj,bcj->bc", fc2, h)
+    if bn_scale is not None:
+        zz = zz * bn_scale + bn_shift
+    gate.copy_(torch.sigmoid(zz))
+    return gate
+
+
+def srm_gate(u, gate, pw3, dw27, bn_scale, bn_shift, B, H, W):
+    _LAUNCHES[0] += 1
+    uf = u.view(B, H, W, 3).permute(0, 3, 1, 2)
+    f = F.conv2d(uf, pw3.view(1, 3, 1, 1)) + F.conv2d(uf, dw27.view(1, 3, 3, 3), padding=1)
+    gate.copy_(torch.sigmoid(F.gelu(f) * bn_scale + bn_shift).reshape(-1))
+    return gate
+
+
+def pool_branch(x, ldx, coff, y, ldy, coff_y, w_rr, bn_scale, bn_shift, slope, pooled_ws, B, H, W, r):
+    _LAUNCHES[0] += 2
+    xi = torch.as_strided(_flat(x), (B, H, W, r), (H * W * ldx, W * ldx, ldx, 1), coff).float().permute(0, 3, 1, 2)
+    p = F.adaptive_avg_pool2d(xi, (7, 7))
+    p = F.leaky_relu(F.conv2d(p, w_rr.view(r, r, 1, 1)) * bn_scale[None, :, None, None] + bn_shift[None, :, None, None], slope)
+    p = F.interpolate(p, scale_factor=7, mode="bilinear", align_corners=True)
+    if p.shape[2] != H or p.shape[3] != W:
+        p = F.interpolate(p, size=(H, W), mode="bilinear", align_corners=False)
+    torch.as_strided(_flat(y), (B, H, W, r), (H * W * ldy, W * ldy, ldy, 1), coff_y).copy_(p.permute(0, 2, 3, 1))
+    return y
+
+
+def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
+    _LAUNCHES[0] += 1
+    v = F.interpolate(y.view(B, h, w, ncls).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")
+    if logits is not None:
+        logits.copy_(v)
+    if labels is not None:
+        labels.copy_(torch.argmax(torch.softmax(v, 1), 1))

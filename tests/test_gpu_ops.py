@@ -1,0 +1,397 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against the CPU oracle / plain torch fp32 on the same
+seeded inputs.  Integer outputs are compared bit-exactly; floating-point tolerances are written at each check.
+A JSON summary of the measured errors goes to gpurun_out/ops_errors.json."""
+import json
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+_ERR = {}
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def record(name, value):
+    _ERR[name] = value
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ops_errors.json"), "w") as f:
+        json.dump(_ERR, f, indent=1)
+
+
+def g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(128, 64, 64), (300, 64, 64), (1000, 512, 64), (777, 64, 512), (256, 320, 320), (513, 1280, 320),
+               (130, 9, 64), (4096, 192, 64), (2000, 100, 104), (512, 2048, 512), (96, 1024, 512), (3136, 128, 576)]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(impl, M, N, K):
+    from cenet_b200 import ops
+    a = torch.randn(M, K, generator=g(1)).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g(2)) / math.sqrt(K)).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g(3)).to(DEV)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear(a, w, out, bias=bias, impl=ops.GEMM_SIMT if impl == "simt" else ops.GEMM_TCGEN05)
+    ref = a.float() @ w.float().t() + bias
+    e = rel(out, ref)
+    record(f"gemm_{impl}_{M}x{N}x{K}", e)
+    assert e < 4e-3, e          # bf16 output rounding (2^-9 relative) dominates
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_gemm_epilogue_full(impl):
+    """alpha, row_scale, bias, act, mul gate, two residuals, act_after_res, fp32 output, channel-slice operands."""
+    from cenet_b200 import ops
+    M, N, K, LD = 700, 96, 160, 320
+    I = ops.GEMM_SIMT if impl == "simt" else ops.GEMM_TCGEN05
+    abig = torch.randn(M, LD, generator=g(1)).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g(2)) / math.sqrt(K)).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g(3)).to(DEV)
+    rs = torch.rand(M, generator=g(4)).to(DEV)
+    r1 = torch.randn(M, N, generator=g(5)).to(DEV, torch.bfloat16)
+    r2 = torch.randn(M, N, generator=g(6)).to(DEV, torch.bfloat16)
+    cs = torch.randn(N, generator=g(7)).to(DEV)
+    mul = torch.randn(M, N, generator=g(8)).to(DEV, torch.bfloat16)
+    cbig = torch.zeros(M, LD, device=DEV, dtype=torch.float32)
+    for a_off in (0, 100, 36):                      # 100 and 36 are not 16-byte aligned: the TMA K-offset path
+        ops.gemm(abig, w, cbig, M=M, N=N, K=K, lda=LD, ldw=K, ldc=LD, bias=bias, row_scale=rs, alpha=0.5,
+                 act=ops.ACT_SILU, mul=mul, ldmul=N, mul_act=ops.ACT_SILU, res1=r1, ldr1=N, res1_cscale=cs, res2=r2,
+                 ldr2=N, a_off=a_off, c_off=20, impl=I)
+        acc = abig[:, a_off:a_off + K].float() @ w.float().t()
+        ref = F.silu(0.5 * acc * rs[:, None] + bias) * F.silu(mul.float()) + r1.float() * cs + r2.float()
+        e = rel(cbig[:, 20:20 + N], ref)
+        record(f"gemm_epi_{impl}_off{a_off}", e)
+        assert e < 1e-4, e      # fp32 output of bf16 products: only accumulation-order error
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(abig, w, out, M=M, N=N, K=K, lda=LD, ldw=K, ldc=N, bias=bias, act=ops.ACT_LEAKY, slope=0.01,
+             act_after_res=True, res1=r1, ldr1=N, impl=I)
+    ref = F.leaky_relu(abig[:, :K].float() @ w.float().t() + bias + r1.float(), 0.01)
+    assert rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("Cin,Cout,k,H,W", [(32, 32, 5, 40, 48), (64, 64, 3, 24, 32), (64, 32, 3, 21, 19), (128, 64, 3, 16, 16)])
+def test_conv_same(impl, Cin, Cout, k, H, W):
+    from cenet_b200 import ops
+    B = 3
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    wt = torch.randn(Cout, Cin, k, k, generator=g(2)) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g(3))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    wm = wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(DEV, torch.bfloat16)
+    out = torch.empty(B, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.conv_nhwc(xn, wm, out, k, 1, k // 2, bias=bias.to(DEV), act=ops.ACT_LEAKY, slope=0.2,
+                  impl=ops.GEMM_SIMT if impl == "simt" else ops.GEMM_TCGEN05)
+    ref = F.leaky_relu(F.conv2d(xn.float().cpu().permute(0, 3, 1, 2), wm.float().cpu().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2),
+                                bias, padding=k // 2), 0.2).permute(0, 2, 3, 1)
+    e = rel(out, ref)
+    record(f"conv_{impl}_{Cin}_{Cout}_{k}_{H}x{W}", e)
+    assert e < 4e-3, e
+
+
+def test_conv_strided_simt_and_im2col():
+    from cenet_b200 import ops
+    B, Cin, Cout, H, W = 2, 3, 64, 64, 64
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    wt = torch.randn(Cout, Cin, 7, 7, generator=g(2)) / 12
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wm = wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(DEV)
+    out = torch.empty(B, 16, 16, Cout, device=DEV)
+    ops.conv_nhwc(xn, wm, out, 7, 4, 3, impl=ops.GEMM_SIMT)
+    ref = F.conv2d(x, wt, stride=4, padding=3).permute(0, 2, 3, 1)
+    assert rel(out, ref) < 1e-5
+    Kp = 152
+    col = torch.empty(B * 256, Kp, device=DEV)
+    ops.im2col(xn, col, B, H, W, Cin, 7, 4, 3, 16, 16, Kp)
+    wp = torch.zeros(Cout, Kp, device=DEV)
+    wp[:, :147] = wm
+    assert rel((col @ wp.t()).reshape(B, 16, 16, Cout), ref) < 1e-5
+    # non-overlapping (SR conv) in bf16, vector path
+    x2 = torch.randn(2, 16, 16, 64, generator=g(3)).to(DEV, torch.bfloat16)
+    col2 = torch.empty(2 * 4 * 4, 4 * 4 * 64, device=DEV, dtype=torch.bfloat16)
+    ops.im2col(x2, col2, 2, 16, 16, 64, 4, 4, 0, 4, 4, 1024)
+    ref2 = x2.reshape(2, 4, 4, 4, 4, 64).permute(0, 1, 3, 2, 4, 5).reshape(32, 1024)
+    assert torch.equal(col2, ref2)
+
+
+def test_gemm_batched_nmajor():
+    from cenet_b200 import ops
+    Bt, N, d = 6, 50, 24
+    q = torch.randn(Bt, N, d, generator=g(1)).to(DEV)
+    k = torch.randn(Bt, N, d, generator=g(2)).to(DEV)
+    v = torch.randn(Bt, N, 40, generator=g(3)).to(DEV)
+    S = torch.empty(Bt, N, N, device=DEV)
+    ops.gemm(q, k, S, M=N, N=N, K=d, lda=d, ldw=d, ldc=N, alpha=0.3, batch=Bt, batch_inner=2, a_bs=(2 * N * d, N * d),
+             w_bs=(2 * N * d, N * d), c_bs=(2 * N * N, N * N), impl=ops.GEMM_SIMT)
+    assert rel(S, 0.3 * q @ k.transpose(1, 2)) < 1e-5
+    o = torch.empty(Bt, N, 40, device=DEV)
+    ops.gemm(S, v, o, M=N, N=40, K=N, lda=N, ldw=40, ldc=40, batch=Bt, a_bs=(N * N, 0), w_bs=(N * 40, 0),
+             c_bs=(N * 40, 0), w_nmajor=True, impl=ops.GEMM_SIMT)
+    assert rel(o, S @ v) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------ rows
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_softmax_stats_rms(dtype):
+    from cenet_b200 import ops
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    for C in (64, 128, 320, 512):
+        x = (torch.randn(333, C, generator=g(C)) * 2 + 0.5).to(DEV, dtype)
+        gam, bet = torch.randn(C, generator=g(1)).to(DEV), torch.randn(C, generator=g(2)).to(DEV)
+        y = torch.empty_like(x)
+        ops.layernorm(x, y, gam, bet, 1e-6)
+        assert rel(y, F.layer_norm(x.float(), (C,), gam, bet, 1e-6)) < tol
+    x = torch.randn(77, 200, generator=g(5)).to(DEV, dtype)
+    ref = torch.softmax(x.float(), -1)
+    ops.softmax_rows_(x, 77, 200, 200)
+    assert rel(x, ref) < tol
+    x = torch.randn(500, 256, generator=g(6)).to(DEV, dtype)
+    st = torch.empty(500, 3, device=DEV)
+    ops.row_stats(x, st, unbiased=True)
+    xf = x.float()
+    assert rel(st, torch.stack([xf.max(1)[0], xf.mean(1), xf.std(1)], 1)) < 1e-5
+    x = torch.randn(100, 128, generator=g(7)).to(DEV, dtype)
+    y = torch.empty_like(x)
+    ops.rmsnorm_seg(x, y, 32, 1e-5, 0.4)
+    xs = x.float().view(100, 4, 32)
+    assert rel(y, (xs * torch.rsqrt(xs.pow(2).mean(-1, keepdim=True) + 1e-5) * 0.4).view(100, 128)) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv_variants(dtype):
+    from cenet_b200 import ops
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    B, H, W, C = 2, 14, 14, 64
+    x = torch.randn(B, C, H, W, generator=g(1))
+    wt = torch.randn(C, 1, 3, 3, generator=g(2)) / 3
+    bias = torch.randn(C, generator=g(3))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    w9 = wt.reshape(C, 9).t().contiguous().to(DEV)
+    xr = xn.float().cpu().permute(0, 3, 1, 2)
+    y = torch.empty_like(xn)
+    ops.dwconv3x3(xn, y, w9, B, H, W, C, bias=bias.to(DEV), act=ops.ACT_GELU)                    # Mix-FFN
+    assert rel(y, F.gelu(F.conv2d(xr, wt, bias, padding=1, groups=C)).permute(0, 2, 3, 1)) < tol
+    # dilated slice with BN affine + ReLU (SepConvBN depthwise), channels [20,40) of a 64-wide tensor
+    sc, sh = torch.rand(20, generator=g(4)) + 0.5, torch.randn(20, generator=g(5))
+    y2 = torch.zeros_like(xn)
+    ops.dwconv3x3(xn, y2, w9[:, 20:40].contiguous(), B, H, W, 20, ldx=C, ldy=C, x_off=20, y_off=20, scale=sc.to(DEV),
+                  shift=sh.to(DEV), dil=3, act=ops.ACT_RELU)
+    ref = F.relu(F.conv2d(xr[:, 20:40], wt[20:40], padding=3, dilation=3, groups=20) * sc[None, :, None, None] + sh[None, :, None, None])
+    assert rel(y2[..., 20:40], ref.permute(0, 2, 3, 1)) < tol
+    assert float(y2[..., :20].abs().max()) == 0 and float(y2[..., 40:].abs().max()) == 0
+    # EUCB: nearest x2 + dw + BN + LeakyReLU(0.2)
+    sc, sh = torch.rand(C, generator=g(6)) + 0.5, torch.randn(C, generator=g(7))
+    y3 = torch.empty(B, 2 * H, 2 * W, C, device=DEV, dtype=dtype)
+    ops.dwconv3x3(xn, y3, w9, B, 2 * H, 2 * W, C, scale=sc.to(DEV), shift=sh.to(DEV), up2=True, act=ops.ACT_LEAKY, slope=0.2)
+    up = F.interpolate(xr, scale_factor=2, mode="nearest")
+    ref = F.leaky_relu(F.conv2d(up, wt, padding=1, groups=C) * sc[None, :, None, None] + sh[None, :, None, None], 0.2)
+    assert rel(y3, ref.permute(0, 2, 3, 1)) < tol
+
+
+def test_layout_ops():
+    from cenet_b200 import ops
+    B, H, W, C = 2, 10, 12, 24
+    x = torch.randn(B, H * W, C, generator=g(1)).to(DEV, torch.bfloat16)
+    y = torch.zeros(B, 2 * C, H * W, device=DEV, dtype=torch.bfloat16)
+    ops.nhwc_to_nchw(x, y, B, H * W, C, 2 * C, C)
+    assert torch.equal(y[:, C:], x.transpose(1, 2)) and float(y[:, :C].abs().max()) == 0
+    back = torch.empty_like(x)
+    ops.nchw_to_nhwc(y[:, C:].contiguous(), back, B, H * W, C)
+    assert torch.equal(back, x)
+    xi = torch.randn(B, C, H, W, generator=g(2))
+    xn = xi.permute(0, 2, 3, 1).contiguous().to(DEV)
+    up = torch.empty(B, 2 * H, 2 * W, C, device=DEV)
+    ops.upsample2x_ac(xn, up, B, H, W, C)
+    assert rel(up, F.interpolate(xi, scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)) < 1e-6
+    wch = torch.randn(C, generator=g(3))
+    mp = torch.zeros(B, H // 2, W // 2, 2 * C, device=DEV)
+    ops.maxpool2_scale(xn, mp, 2 * C, C, wch.to(DEV), B, H, W, C)
+    assert rel(mp[..., C:], (F.max_pool2d(xi, 2) * wch[None, :, None, None]).permute(0, 2, 3, 1)) < 1e-6
+    sc, sh, gt = torch.randn(C, generator=g(4)), torch.randn(C, generator=g(5)), torch.rand(B, C, generator=g(6))
+    ag = torch.empty_like(xn)
+    ops.affine_gate(xn, ag, sc.to(DEV), sh.to(DEV), gt.to(DEV), B, H * W, C)
+    ref = (xi * sc[None, :, None, None] + sh[None, :, None, None]) * gt[:, :, None, None]
+    assert rel(ag, ref.permute(0, 2, 3, 1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_sr_attention(dtype):
+    from cenet_b200 import ops
+    B, N, Nk, heads = 2, 300, 49, 2
+    C = heads * 64
+    q = torch.randn(B, N, C, generator=g(1)).to(DEV, dtype)
+    kv = torch.randn(B, Nk, 2 * C, generator=g(2)).to(DEV, dtype)
+    out = torch.empty_like(q)
+    ops.sr_attention(q, kv, out, B, N, Nk, C, heads, 0.125)
+    qf = q.float().view(B, N, heads, 64).transpose(1, 2)
+    kf = kv.float()[..., :C].reshape(B, Nk, heads, 64).transpose(1, 2)
+    vf = kv.float()[..., C:].reshape(B, Nk, heads, 64).transpose(1, 2)
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * 0.125, -1) @ vf).transpose(1, 2).reshape(B, N, C)
+    e = rel(out, ref)
+    record(f"sr_attention_{dtype}", e)
+    assert e < (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+def _diff_ref(qkv, B, N, E, heads, lam, mult):
+    hd = E // heads // 2
+    q = qkv[..., :E].view(B, N, 2 * heads, hd).transpose(1, 2) * hd ** -0.5
+    k = qkv[..., E:2 * E].view(B, N, 2 * heads, hd).transpose(1, 2)
+    v = qkv[..., 2 * E:].view(B, N, heads, 2 * hd).transpose(1, 2)
+    s = torch.softmax(q @ k.transpose(-1, -2), -1).view(B, heads, 2, N, N)
+    o = (s[:, :, 0] - lam * s[:, :, 1]) @ v
+    o = o * torch.rsqrt(o.pow(2).mean(-1, keepdim=True) + 1e-5) * mult
+    return o.transpose(1, 2).reshape(B, N, E)
+
+
+@pytest.mark.parametrize("E,heads,N", [(128, 8, 3136), (256, 8, 784), (128, 4, 3136), (256, 4, 784), (128, 2, 200), (256, 2, 130)])
+def test_diffattn_flash(E, heads, N):
+    """head_dim 8,16,32,64; N both a multiple of 64 and ragged.  Scores scaled up so softmax is far from uniform."""
+    from cenet_b200 import ops
+    B = 2
+    qkv = torch.randn(B, N, 3 * E, generator=g(E + heads))
+    qkv[..., :2 * E] *= 2.0
+    qb = qkv.to(DEV, torch.bfloat16)
+    out = torch.empty(B, N, E, device=DEV, dtype=torch.bfloat16)
+    ops.diffattn_flash(qb, out, B, N, E, heads, 0.55, 1e-5, 0.45)
+    ref = _diff_ref(qb.float(), B, N, E, heads, 0.55, 0.45)
+    e = rel(out, ref)
+    record(f"diffattn_flash_E{E}_h{heads}_N{N}", e)
+    assert e < 1.5e-2, e      # bf16 P and bf16 output; the difference of two softmaxes amplifies rounding
+
+
+@pytest.mark.parametrize("C,N", [(64, 3136), (128, 784), (64, 100)])
+def test_nonlocal_flash(C, N):
+    from cenet_b200 import ops
+    B = 2
+    tpg = (torch.randn(B, N, 3 * C, generator=g(C)) * 1.5).to(DEV, torch.bfloat16)
+    out = torch.empty(B, N, C, device=DEV, dtype=torch.bfloat16)
+    ops.nonlocal_flash(tpg, out, B, N, C, C ** -0.5)
+    t = tpg.float()
+    ref = torch.softmax(t[..., :C] @ t[..., C:2 * C].transpose(1, 2) * C ** -0.5, -1) @ t[..., 2 * C:]
+    e = rel(out, ref)
+    record(f"nonlocal_flash_C{C}_N{N}", e)
+    assert e < 8e-3, e
+
+
+# ------------------------------------------------------------------------------------------------------------ DSEB / CFAM pieces
+@pytest.mark.parametrize("scales,H", [([0.8, 0.4], 56), ([1.0, 0.5], 28), ([1.0, 0.75, 0.5], 14), ([0.8, 0.4], 14)])
+def test_fea_combine(scales, H):
+    from cenet_b200 import ops
+    from oracle import cenet_oracle as O
+    B, C2 = 2, 24
+    y = torch.randn(B, C2, H, H, generator=g(H))
+    gate = torch.randn(B, C2, H, H, generator=g(H + 1))
+    wv = torch.randn(1, C2, 1, 1, generator=g(3)) + 0.5
+    z = torch.empty(B, C2, H, H, device=DEV)
+    ops.fea_combine(y.to(DEV), gate.to(DEV), z, wv.reshape(-1).to(DEV), B, C2, H, H, scales)
+    ref = O.fea({"m.w": wv}, "m", y, scales) + y + gate * y
+    e = rel(z, ref)
+    record(f"fea_{scales}_{H}", e)
+    assert e < 1e-5, e
+
+
+def test_ccu_srm_pool(golden_modules):
+    from cenet_b200 import ops
+    from oracle import cenet_oracle as O
+    # CCU gate incl. BN affine prologue, B > 1 and B == 1
+    for key in ("ccu_c64_b2", "ccu_c64_b1"):
+        c = golden_modules[key]
+        sd, x = c["state"], c["inputs"][0]
+        B, C, H, W = x.shape
+        xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        s = sd["bn.weight"] / torch.sqrt(sd["bn.running_var"] + 1e-5)
+        t = sd["bn.bias"] - sd["bn.running_mean"] * s
+        gate = torch.empty(B, C, device=DEV)
+        ws = torch.empty(B * ops.ccu_nchunk(H * W) * C * 3, device=DEV)
+        ops.ccu_gate(xn, None, None, sd["fc1.weight"].reshape(C, 3, 3).contiguous().to(DEV), sd["fc2.weight"].reshape(C, 3).contiguous().to(DEV),
+                     s.to(DEV) if B > 1 else None, t.to(DEV) if B > 1 else None, gate, ws, B, H * W, C)
+        y = torch.empty_like(xn)
+        ops.affine_gate(xn, y, None, None, gate, B, H * W, C)
+        assert rel(y, c["output"].permute(0, 2, 3, 1)) < 1e-5
+    # SRM
+    c = golden_modules["srm"]
+    sd, x = c["state"], c["inputs"][0]
+    B, C, H, W = x.shape
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    u = torch.empty(B * H * W, 3, device=DEV)
+    ops.row_stats(xn.view(-1, C), u, unbiased=True)
+    s = float(sd["bn.weight"] / torch.sqrt(sd["bn.running_var"] + 1e-5))
+    t = float(sd["bn.bias"] - sd["bn.running_mean"] * s)
+    gm = torch.empty(B * H * W, device=DEV)
+    ops.srm_gate(u, gm, sd["pwc.weight"].reshape(3).to(DEV), sd["dwc.weight"].reshape(27).contiguous().to(DEV), s, t, B, H, W)
+    assert rel(xn * gm.view(B, H, W, 1), c["output"].permute(0, 2, 3, 1)) < 1e-5
+    # pooling branch against the oracle's multi_order_dwconv internals
+    for H in (7, 14, 28, 56):
+        r = 8
+        x = torch.randn(2, 16, H, H, generator=g(H))
+        wrr = torch.randn(r, r, generator=g(1)) / 3
+        sc, sh = torch.rand(r, generator=g(2)) + 0.5, torch.randn(r, generator=g(3))
+        p = F.adaptive_avg_pool2d(x[:, 8:16], (7, 7))
+        p = F.leaky_relu(F.conv2d(p, wrr[:, :, None, None]) * sc[None, :, None, None] + sh[None, :, None, None], 0.01)
+        p = F.interpolate(p, scale_factor=7, mode="bilinear", align_corners=True)
+        if H != 49:
+            p = F.interpolate(p, size=(H, H), mode="bilinear", align_corners=False)
+        xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        y = torch.zeros(2, H, H, 16, device=DEV)
+        pooled = torch.empty(2 * 49 * r, device=DEV)
+        ops.pool_branch(xn, 16, 8, y, 16, 8, wrr.to(DEV), sc.to(DEV), sh.to(DEV), 0.01, pooled, 2, H, H, r)
+        assert rel(y[..., 8:], p.permute(0, 2, 3, 1)) < 1e-5, H
+
+
+# ------------------------------------------------------------------------------------------------------------ head / loss
+@pytest.mark.parametrize("ncls", [2, 4, 9, 5])
+def test_head_upsample_argmax_bit_exact(ncls):
+    from cenet_b200 import ops
+    from oracle import cenet_oracle as O
+    B, h, w = 2, 20, 24
+    y = torch.randn(B, ncls, h, w, generator=g(ncls)) * 3
+    yn = y.permute(0, 2, 3, 1).contiguous().to(DEV)
+    logits = torch.empty(B, ncls, 2 * h, 2 * w, device=DEV)
+    labels = torch.empty(B, 2 * h, 2 * w, device=DEV, dtype=torch.int64)
+    ops.head_upsample_argmax(yn, logits, labels, B, h, w, ncls)
+    ref = F.interpolate(y, scale_factor=2, mode="bilinear")
+    torch.testing.assert_close(logits.cpu(), ref, rtol=1e-6, atol=1e-6)
+    # integer contract: labels are bit-exact w.r.t. argmax(softmax(.)) of OUR logits (metrics_eval.py:52)
+    assert torch.equal(labels.cpu(), O.predict_labels(logits.cpu()))
+    # ties resolve to the lowest index
+    yt = torch.zeros(1, 3, 3, ncls, device=DEV)
+    lab = torch.empty(1, 6, 6, device=DEV, dtype=torch.int64)
+    ops.head_upsample_argmax(yt, None, lab, 1, 3, 3, ncls)
+    assert int(lab.abs().max()) == 0
+
+
+def test_dice_ce(golden_loss):
+    from cenet_b200 import ops
+    for key, c in golden_loss.items():
+        ncls = int(key[1:])
+        logits, labels = c["logits"].to(DEV), c["labels"].to(DEV)
+        B, _, H, W = logits.shape
+        nblk = ops.loss_nblocks(B * H * W)
+        ws = torch.empty((3 * ncls + 1) * nblk + 3 * ncls + 3, device=DEV)
+        loss = torch.empty(1 + ncls, device=DEV)
+        grad = torch.empty_like(logits)
+        ops.dice_ce(logits, labels, loss, grad, ws, B, ncls, H * W, 0.5, 0.5)
+        torch.testing.assert_close(loss[0].cpu(), c["loss"], rtol=2e-6, atol=1e-6)
+        assert rel(grad, c["grad"]) < 1e-5
+        # Dice-count reductions are integers: sum_t per class must match exactly
+        tot = ws[(3 * ncls + 1) * nblk:(3 * ncls + 1) * nblk + 3 * ncls].cpu().view(ncls, 3)
+        assert torch.equal(tot[:, 2].long(), torch.bincount(c["labels"].flatten(), minlength=ncls))
+        # determinism: a second run is bit-identical
+        loss2, grad2 = torch.empty_like(loss), torch.empty_like(grad)
+        ops.dice_ce(logits, labels, loss2, grad2, ws, B, ncls, H * W, 0.5, 0.5)
+        assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
