@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
       tmem_ld_wait();
       if (!row_ok) continue;
       const int nbase = n0 + c0;
-      if (p.c_vec8 && nbase + 32 <= p.N) {
+      // columns owned by this tile end at min(N, n0 + bn): never store the TMEM columns past bn (bn % 32 may be 16)
+      const int nlim = min(p.N, n0 + p.bn);
+      if (p.c_vec8 && nbase + 32 <= nlim) {
         // bf16 output, 16-byte stores (4 per thread-chunk)
         bf16* crow = reinterpret_cast<bf16*>(e.C) + m * e.ldc + nbase;
 #pragma unroll
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 #pragma unroll
         for (int c = 0; c < 32; c++) {
           const int n = nbase + c;
-          if (n < p.N) epi_store(e, epi_value(e, __uint_as_float(acc[c]), m, n, 0), m, n, 0);
+          if (n < nlim) epi_store(e, epi_value(e, __uint_as_float(acc[c]), m, n, 0), m, n, 0);
         }
       }
     }
@@ -298,9 +300,8 @@ bool cenet_gemm_tc_eligible(const cenet_gemm_args* a) {
     if (a->lda != a->Cin || ((uintptr_t)a->A & 15)) return false;
     return true;
   }
-  if (a->lda % 8 != 0) return false;
-  // A may start on any 2-byte boundary inside an aligned row (channel slices): handled with a K-coordinate offset,
-  // but the row pitch must keep the aligned base valid for every row
+  // TMA: 16-byte aligned base and row pitch; K padded to 8 elements by the caller (zero columns)
+  if (a->lda % 8 != 0 || a->K % 8 != 0 || ((uintptr_t)a->A & 15)) return false;
   return true;
 }
 
@@ -332,13 +333,9 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   } else {
     p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0;
     p.bk = 64;
-    // aligned base + K-coordinate offset for channel-slice operands
-    const uintptr_t addr = (uintptr_t)a->A;
-    const int mis = (int)((addr & 15) / 2);
-    const void* abase = (const void*)(addr - (uintptr_t)mis * 2);
-    p.a_k0 = mis;
+    const void* abase = a->A;
     p.num_kb = cdiv(a->K, 64);
-    cuuint64_t ad[2] = {(cuuint64_t)(mis + a->K), (cuuint64_t)a->M};
+    cuuint64_t ad[2] = {(cuuint64_t)a->K, (cuuint64_t)a->M};
     cuuint64_t as[1] = {(cuuint64_t)a->lda * 2};
     cuuint32_t ab[2] = {64, BM};
     if (encode_map(&tmA, abase, 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;

@@ -232,12 +232,13 @@ class Engine:
         M(q + ".fc2.w", sd[q + ".fc2.weight"].flatten(1) * ls2[:, None]); P(q + ".fc2.b", sd[q + ".fc2.bias"] * ls2)
 
     # ------------------------------------------------------------------------------------------------ buffers
-    def buf(self, key, shape, dtype=None):
+    def buf(self, key, shape, dtype=None, zero=False):
         dtype = dtype or self.T
         k = (self._plan_key, key)
         t = self._bufs.get(k)
         if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
-            t = self._bufs[k] = torch.empty(shape, device=self.dev, dtype=dtype)
+            alloc = torch.zeros if zero else torch.empty
+            t = self._bufs[k] = alloc(shape, device=self.dev, dtype=dtype)
         return t
 
     def _tap(self, name, t_nhwc, B, H, W, Cc):
@@ -371,15 +372,18 @@ class Engine:
         self._lin(x1, m + ".gate", g)
         # MultiOrderDWConv(x1)
         v = m + ".value"
-        dwb = self.buf(key + ".dwb", (Mtok, Cc))
+        # depthwise outputs live in their own buffer whose slices start on 16-byte boundaries (TMA operand rule);
+        # the pad columns are zero (buffer zeroed once) and meet zero weight columns in the pointwise GEMM
+        ap = _rup(sl[0][1] - sl[0][0], 8)
+        dwb = self.buf(key + ".dwb", (Mtok, 3 * ap), zero=True)
         cat = self.buf(key + ".cat", (Mtok, Cc))
         for i, rate in enumerate(_MCA_RATES[Cc]):
             a0, a1 = sl[i]
             d = f"{v}.dlps.{i}"
-            ops.dwconv3x3(x1, dwb, w[d + ".dw.w"], B, H, W, a1 - a0, ldx=Cc, ldy=Cc, x_off=a0, y_off=a0,
+            ops.dwconv3x3(x1, dwb, w[d + ".dw.w"], B, H, W, a1 - a0, ldx=Cc, ldy=3 * ap, x_off=a0, y_off=i * ap,
                           scale=w[d + ".dw.s"], shift=w[d + ".dw.t"], dil=rate, act=ACT_RELU)
-            ops.gemm(dwb, w[d + ".pw.w"], cat, M=Mtok, N=a1 - a0, K=a1 - a0, lda=Cc, ldw=w[d + ".pw.w"].shape[1], ldc=Cc,
-                     bias=w[d + ".pw.b"], act=ACT_RELU, a_off=a0, c_off=a0, impl=self.gemm_impl)
+            ops.gemm(dwb, w[d + ".pw.w"], cat, M=Mtok, N=a1 - a0, K=ap, lda=3 * ap, ldw=w[d + ".pw.w"].shape[1], ldc=Cc,
+                     bias=w[d + ".pw.b"], act=ACT_RELU, a_off=i * ap, c_off=a0, impl=self.gemm_impl)
         r0, r1 = sl[3]
         d = f"{v}.dlps.3"
         pooled = self.buf(key + ".pooled", (B * 49 * (r1 - r0),), torch.float32)

@@ -22,9 +22,15 @@ def rel(a, b):
 
 
 def _record(key, val):
+    path = os.path.join(ROOT, "gpurun_out", "model_errors.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    if not _ERR and os.path.exists(path):
+        try:
+            _ERR.update(json.load(open(path)))
+        except Exception:
+            pass
     _ERR[key] = val
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "model_errors.json"), "w") as f:
+    with open(path, "w") as f:
         json.dump(_ERR, f, indent=1)
 
 
