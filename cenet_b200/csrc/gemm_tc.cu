@@ -102,7 +102,7 @@ struct TcParams {
   // conv mode
   int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
   EpiParams epi;
-  int c_vec8;        // 16-byte vector stores allowed
+  int epi_vec;       // every epilogue operand is 16-byte addressable -> smem-transposed, vectorised epilogue
 };
 
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   const uint32_t stage_bytes = a_bytes + ((w_bytes + 1023u) & ~1023u);
   const uint32_t bar_base = sbase + p.stages * stage_bytes;          // full[stages], empty[stages], tmem_full
   const uint32_t tmem_slot = bar_base + (2 * p.stages + 1) * 8;
+  const uint32_t slab_base = (tmem_slot + 4 + 15u) & ~15u;           // 4 epilogue warps x 32 x 36 floats
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (p.stages + s) * 8; };
   const uint32_t tmem_full_bar = bar_base + 2 * p.stages * 8;
@@ -194,52 +195,118 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // tcgen05.ld gives each thread 32 consecutive columns of ITS row.  Row-per-thread global accesses would touch 32
+    // different lines per instruction, so the tile is transposed through a per-warp smem slab: phase A (row per
+    // thread) applies alpha / row_scale / bias / act and writes the slab; phase B re-reads it with 4 lanes per row,
+    // 8 columns (16 bytes of bf16) per lane, so residual / gate loads and the output stores are full 32-byte sectors.
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;          // accumulator row == TMEM lane
-    long long m;
-    bool row_ok;
-    if (p.conv) {
-      const int h = h0 + r / TILE_W, w = w0 + r % TILE_W;
-      row_ok = (h < p.H) && (w < p.W);
-      m = ((long long)img * p.H + h) * p.W + w;
-    } else {
+    const int r_own = quarter * 32 + lane;      // accumulator row == TMEM lane
+    float* slab = reinterpret_cast<float*>(smem_raw + (slab_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 36);
+    auto row_index = [&](int r, long long& m) -> bool {
+      if (p.conv) {
+        const int h = h0 + r / TILE_W, w = w0 + r % TILE_W;
+        m = ((long long)img * p.H + h) * p.W + w;
+        return (h < p.H) && (w < p.W);
+      }
       m = (long long)m0 + r;
-      row_ok = m < p.M;
-    }
+      return m < p.M;
+    };
+    long long m_own;
+    const bool own_ok = row_index(r_own, m_own);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const EpiParams& e = p.epi;
+    const int nlim = min(p.N, n0 + p.bn);       // columns owned by this tile (bn % 32 may be 16)
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       if (n0 + c0 >= p.N) break;                 // warp-uniform
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
       tmem_ld_wait();
-      if (!row_ok) continue;
       const int nbase = n0 + c0;
-      // columns owned by this tile end at min(N, n0 + bn): never store the TMEM columns past bn (bn % 32 may be 16)
-      const int nlim = min(p.N, n0 + p.bn);
-      if (p.c_vec8 && nbase + 32 <= nlim) {
-        // bf16 output, 16-byte stores (4 per thread-chunk)
-        bf16* crow = reinterpret_cast<bf16*>(e.C) + m * e.ldc + nbase;
+      if (p.epi_vec) {
+        // ---- phase A: raw accumulators into the slab (row stride 36 floats: 16-byte aligned, conflict-free) ----
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-          uint4 pk;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4*>(slab + lane * 36 + q * 4) =
+              make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
+                          __uint_as_float(acc[4 * q + 3]));
+        __syncwarp();
+        // ---- phase B: 4 lanes per row, 8 columns per lane; the whole epilogue on 8-wide vectors ----
+        const int cg = (lane & 3) * 8;
+        const int n = nbase + cg;
+        float bcol[8];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int c = v * 8 + 2 * j;
-            const float x0 = epi_value(e, __uint_as_float(acc[c]), m, nbase + c, 0);
-            const float x1 = epi_value(e, __uint_as_float(acc[c + 1]), m, nbase + c + 1, 0);
-            h2[j] = __floats2bfloat162_rn(x0, x1);
+        for (int j = 0; j < 8; j++) bcol[j] = (e.bias && !e.bias_per_row && n + j < p.N) ? e.bias[n + j] : 0.f;
+#pragma unroll 1
+        for (int it = 0; it < 4; it++) {
+          const int rr = it * 8 + (lane >> 2);
+          long long m;
+          const bool ok = row_index(quarter * 32 + rr, m);
+          if (!ok || n >= nlim) continue;
+          float v[8];
+          {
+            const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+            const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
           }
-          *reinterpret_cast<uint4*>(crow + v * 8) = pk;
-        }
-      } else {
+          const float rs = e.alpha * (e.row_scale ? e.row_scale[m] : 1.f);
+          const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; c++) {
-          const int n = nbase + c;
-          if (n < nlim) epi_store(e, epi_value(e, __uint_as_float(acc[c]), m, n, 0), m, n, 0);
+          for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
+          if (!e.act_after_res && e.act != CENET_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
+          }
+          const bool full = n + 8 <= nlim;
+          if (e.mul) {
+            float t[8];
+            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, t);
+            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] *= apply_act(t[j], e.mul_act, 0.f);
+          }
+          if (e.res1) {
+            float t[8];
+            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t);
+            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] += t[j] * (e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale);
+          }
+          if (e.res2) {
+            float t[8];
+            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t);
+            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] += t[j];
+          }
+          if (e.act_after_res && e.act != CENET_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
+          }
+          if (full) {
+            if (e.c_dtype == CENET_BF16) stv<8>(reinterpret_cast<bf16*>(e.C) + m * e.ldc + n, v);
+            else stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
+          } else {
+            for (int j = 0; j < 8 && n + j < nlim; j++) epi_store(e, v[j], m, n + j, 0);
+          }
         }
+        __syncwarp();
+      } else {
+        // operands that are not 16-byte addressable (odd pitches / channel-slice outputs): element-wise epilogue
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          *reinterpret_cast<float4*>(slab + lane * 36 + q * 4) =
+              make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
+                          __uint_as_float(acc[4 * q + 3]));
+        __syncwarp();
+        if (own_ok) {
+#pragma unroll 1
+          for (int c = 0; c < 32; c++) {
+            const int n = nbase + c;
+            if (n < nlim) epi_store(e, epi_value(e, slab[lane * 36 + c], m_own, n, 0), m_own, n, 0);
+          }
+        }
+        __syncwarp();
       }
     }
     tc_fence_before();
@@ -354,8 +421,14 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  p.c_vec8 = (a->c_dtype == CENET_BF16) && (a->ldc % 8 == 0) && (((uintptr_t)a->C & 15) == 0) && (p.bn % 8 == 0);
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;   // + alignment slack
+  auto vec_ok = [](const void* ptr, int dtype, long long ld) {
+    return ptr == nullptr || (dtype == CENET_BF16 && ld % 8 == 0 && ((uintptr_t)ptr & 15) == 0);
+  };
+  const bool c_ok = (((uintptr_t)a->C & 15) == 0) && ((a->c_dtype == CENET_BF16 && a->ldc % 8 == 0) ||
+                                                      (a->c_dtype == CENET_F32 && a->ldc % 4 == 0));
+  p.epi_vec = c_ok && vec_ok(a->res1, a->res1_dtype, a->ldr1) && vec_ok(a->res2, a->res2_dtype, a->ldr2) &&
+              vec_ok(a->mul, a->mul_dtype, a->ldmul);
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 4 * 32 * 36 * 4 + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -37,6 +37,38 @@ def lambda_init(depth):
     return 0.8 - 0.6 * math.exp(-0.3 * depth)
 
 
+class _TimedOps:
+    """Proxy over `cenet_b200.ops` that brackets every launch with CUDA events on the launching stream (bench /
+    profiling only; events are not capturable, so this is used with eager launches)."""
+
+    def __init__(self, inner):
+        self._inner = inner
+        self.records = []          # (op name, tag, start event, end event)
+        self.tag = ""
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not callable(fn) or name in ("ccu_nchunk", "loss_nblocks", "launch_count", "dt"):
+            return fn
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            self.records.append((name, self.tag, e0, e1))
+            return r
+        return timed
+
+    def summary(self):
+        """{(op, tag): (total ms, launches)} -- call after a synchronize."""
+        out = {}
+        for name, tag, e0, e1 in self.records:
+            t, n = out.get((name, tag), (0.0, 0))
+            out[(name, tag)] = (t + e0.elapsed_time(e1), n + 1)
+        return out
+
+
 class Engine:
     @staticmethod
     def default_precision():
@@ -60,6 +92,7 @@ class Engine:
         self._bufs = {}
         self._graphs = {}
         self.taps = None                              # dict -> intermediate activations are copied out (tests)
+        self.launches_per_forward = None              # kernels launched by one pass (counted on the eager warm-up)
 
     # ------------------------------------------------------------------------------------------------ packing
     def _weights_version(self):
@@ -267,6 +300,7 @@ class Engine:
         feats = []
         cur, curC = x_nhwc, Cin
         for s in range(4):
+            ops.tag = f"enc{s+1}"
             Cc, heads, sr = _PVT["embed_dims"][s], _PVT["heads"][s], _PVT["sr_ratios"][s]
             hid = Cc * _PVT["mlp_ratios"][s]
             k, st = (7, 4) if s == 0 else (3, 2)
@@ -356,6 +390,7 @@ class Engine:
     def _cfam(self, x, B, H, W, Cc, p, key):
         """cfam.py:365-374 on x [B*HW,C] -> new buffer"""
         w = self.w
+        ops.tag = key
         HW, Mtok = H * W, B * H * W
         from .networks.cenet import channel_slices
         sl = channel_slices(Cc)
@@ -418,6 +453,7 @@ class Engine:
     def _up(self, x, B, H, W, Cin, Cout, p, kind, key, out=None, ldc=None, c_off=0):
         """EUCB (blocks.py:317-321) or UpConv (blocks.py:206-221): [B,H,W,Cin] -> [B,2H,2W,Cout]"""
         w = self.w
+        ops.tag = key
         Mo = B * 4 * H * W
         if out is None:
             out = self.buf(key + ".out", (Mo, Cout))
@@ -438,6 +474,7 @@ class Engine:
     def _dseb(self, skip, dec, B, H, W, Cc, p, heads, key):
         """dseb.py:153-165; returns mixer(z) + skip + dec  (== dec + DSEBlock(skip, dec), decoders.py:95)"""
         w = self.w
+        ops.tag = key
         HW, E = H * W, 2 * Cc
         y = self.buf(key + ".y", (B, E, H, W))                         # NCHW cat([dec, skip])
         ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
@@ -457,6 +494,7 @@ class Engine:
     def _resblock(self, x, B, H, W, Cin, Cout, k, p, key):
         """modules/unet.py:201-214 with BN folded; x [B,H,W,Cin] -> [B*H*W,Cout]"""
         w = self.w
+        ops.tag = key
         Mtok = B * H * W
         x4 = x.view(B, H, W, Cin)
         o1 = self.buf(key + ".o1", (B, H, W, Cout))
@@ -479,6 +517,7 @@ class Engine:
         Cin, ncls = cfg["input_channels"], cfg["num_classes"]
         # input -> channels-last compute dtype (for Cin == 1 NCHW and NHWC coincide)
         xc = self.buf("x", (B * H * W, Cin))
+        ops.tag = "input"
         if Cin == 1:
             ops.affine_gate(x_in, xc, None, None, None, B, H * W, 1)
         else:
@@ -501,6 +540,7 @@ class Engine:
         self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
         o = self._resblock(z, B, Hh, Wh, 2 * om, 2 * om, 3, "out.out.0", "head.out")
         yh = self.buf("head.y", (B * Hh * Wh, ncls), torch.float32)
+        ops.tag = "head.logits"
         self._lin(o, "out.head", yh)
         ops.head_upsample_argmax(yh, out_logits, out_labels, B, Hh, Wh, ncls)
 
@@ -531,7 +571,9 @@ class Engine:
         else:
             g = self._graphs.get(key)
             if g is None:
+                n0 = ops.launch_count()
                 self._run(*args)                                   # eager warm-up: allocates every workspace
+                self.launches_per_forward = ops.launch_count() - n0
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -540,6 +582,26 @@ class Engine:
             g.replay()
         out.copy_(res)
         return out
+
+    @torch.no_grad()
+    def profile_ops(self, x, labels=True, steps=3):
+        """Eager passes with CUDA events around every launch -> {(op, tag): (ms per pass, launches per pass)}."""
+        global ops
+        B, _, H, W = x.shape
+        self.forward(x, labels=labels)                             # make sure weights/buffers exist
+        self._plan_key = (B, H, W)
+        x_in = self.buf("x_in", (B, x.shape[1], H, W), torch.float32)
+        res = self.buf("res.labels" if labels else "res.logits", (B, H, W) if labels else (B, self.cfg["num_classes"], H, W),
+                       torch.int64 if labels else torch.float32)
+        real, timed = ops, _TimedOps(ops)
+        ops = timed
+        try:
+            for _ in range(steps):
+                self._run(x_in, B, H, W, None if labels else res, res if labels else None)
+            torch.cuda.synchronize()
+        finally:
+            ops = real
+        return {k: (t / steps, n // steps) for k, (t, n) in timed.summary().items()}
 
     def forward_train(self, x):
         raise NotImplementedError(

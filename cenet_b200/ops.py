@@ -16,6 +16,7 @@ from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SIL
                    GEMM_TCGEN05, GemmArgs)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
+tag = ""      # free-form region label set by the engine; read only by the profiling proxy (engine._TimedOps)
 
 
 def dt(t: torch.Tensor) -> int:
