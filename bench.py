@@ -96,9 +96,11 @@ def build_model():
     import torch
     from cenet_b200.networks import CENet
     from oracle import fixtures
+    import contextlib
     kw = fixtures.CONFIGS[CONFIG_NAME]
     torch.manual_seed(1234)
-    m = CENet(**kw)
+    with contextlib.redirect_stdout(sys.stderr):          # the constructor prints like the reference does
+        m = CENet(**kw)
     sd = fixtures.perturb_state(m.state_dict(), 1234)
     m.load_state_dict(sd)
     return m, sd, kw

@@ -8,6 +8,8 @@
 // the tensor pipe.  mma.sync leaves the scores in registers where the softmax needs them; a tcgen05 version would add
 // a TMEM->register round trip per score for no gain.  The GEMM-shaped layers use tcgen05 (gemm_tc.cu).
 #include "common.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -41,6 +43,18 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax of 2^f on [-0.5,0.5], rel. err < 1.1e-4, below the
+// 2^-9 rounding of the bf16 probabilities it feeds).  The softmax of these kernels is bound by the MUFU (XU) pipe
+// (ncu: sm__inst_executed_pipe_xu 67% vs fma 23% / alu 26%), so every POLY_EVERY-th exponential is moved over.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                  // 1.5*2^23: round-to-nearest integer lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);            // f in [-0.5, 0.5]
+  float p = fmaf(0.0555041086f, f, 0.2402264923f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 constexpr int QT = 64;    // query rows per CTA (4 warps x 16)
@@ -72,7 +86,7 @@ __device__ __forceinline__ void qk_tile(float (&S)[KT / 8][4], const uint32_t (&
 }
 
 // online softmax update for the 2 rows this thread owns (g and g+8); returns P packed as A fragments
-template <int DV>
+template <int DV, int POLY>
 __device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P)[KT / 16][4], float (&m)[2],
                                              float (&l)[2], float (&O)[DV / 8][4], float scale_log2, int kbase, int N,
                                              int lane) {
@@ -105,9 +119,11 @@ __device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P
 #pragma unroll
   for (int j = 0; j < KT / 8; j++) {
     const float p0 = fast_exp2(fmaf(S[j][0], scale_log2, -mn0));
-    const float p1 = fast_exp2(fmaf(S[j][1], scale_log2, -mn0));
+    const float p1 = (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == 0) ? poly_exp2(fmaf(S[j][1], scale_log2, -mn0))
+                                                   : fast_exp2(fmaf(S[j][1], scale_log2, -mn0));
     const float p2 = fast_exp2(fmaf(S[j][2], scale_log2, -mn1));
-    const float p3 = fast_exp2(fmaf(S[j][3], scale_log2, -mn1));
+    const float p3 = (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == 1 % (POLY > 0 ? POLY : 1)) ? poly_exp2(fmaf(S[j][3], scale_log2, -mn1))
+                                                          : fast_exp2(fmaf(S[j][3], scale_log2, -mn1));
     s0 += p0 + p1; s1 += p2 + p3;
     P[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
     P[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -133,8 +149,8 @@ struct DiffCfg {
   static constexpr int SMEM = Q_BYTES + 2 * STAGE;
 };
 
-template <int HD>
-__global__ void __launch_bounds__(NTHREADS) diffattn_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+template <int HD, int POLY, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                   int N, int E, float scale_log2, float lambda,
                                                                   float eps, float mult) {
   using Cfg = DiffCfg<HD>;
@@ -194,44 +210,98 @@ __global__ void __launch_bounds__(NTHREADS) diffattn_flash_kernel(const bf16* __
       ldsm_x4(qf[mp][ks], sQ + (mp * QT + r) * KSTR + d * 2);
     }
 
-  float O[2][DV / 8][4];
-  float m[2][2], l[2][2];
+  // O accumulators; L[mp] is a 9th "value column" of ones: the tensor pipe accumulates the softmax row sums
+  // (column 0 of that tile = sum_k P[row,k]) and they are rescaled together with O -- 4 HMMA per tile instead of 32 FADD.
+  float O[2][DV / 8][4], L[2][4];
+  float m[2][2];
 #pragma unroll
   for (int mp = 0; mp < 2; mp++) {
     m[mp][0] = m[mp][1] = -INFINITY;
-    l[mp][0] = l[mp][1] = 0.f;
+    L[mp][0] = L[mp][1] = L[mp][2] = L[mp][3] = 0.f;
 #pragma unroll
     for (int j = 0; j < DV / 8; j++) O[mp][j][0] = O[mp][j][1] = O[mp][j][2] = O[mp][j][3] = 0.f;
   }
+  const uint32_t ones_b = (lane < 4) ? 0x3F803F80u : 0u;     // B fragment of the ones column (n = 0 <=> lane/4 == 0)
+  // lane-dependent ldmatrix offsets, hoisted out of the tile loop
+  const uint32_t k_lane = ((lane & 7) + ((lane >> 4) << 3)) * KSTR + (((lane >> 3) & 1) << 4);
+  const uint32_t v_lane = ((lane & 7) + (((lane >> 3) & 1) << 3)) * VSTR + ((lane >> 4) << 4);
+  const int tq = lane & 3;
 
-  for (int tile = 0; tile < ntiles; tile++) {
+  auto process_tile = [&](auto masked_tag, int tile) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
     const int stage = tile & 1;
     const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + Cfg::K_BYTES;
-    uint32_t P[2][KT / 16][4];
 #pragma unroll
     for (int mp = 0; mp < 2; mp++) {
       float S[KT / 8][4];
-      qk_tile<HDP>(S, qf[mp], sK + mp * KT * KSTR, KSTR, lane);
-      softmax_tile<DV>(S, P[mp], m[mp], l[mp], O[mp], scale_log2, tile * KT, N, lane);
-    }
-    // O_mp += P_mp V   (V fragments shared by the two maps)
 #pragma unroll
-    for (int kk = 0; kk < KT / 16; kk++) {
+      for (int j = 0; j < KT / 8; j++) { S[j][0] = S[j][1] = S[j][2] = S[j][3] = 0.f; }
 #pragma unroll
-      for (int np = 0; np < DV / 16; np++) {
-        uint32_t v[4];
-        const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-        const int dv = np * 16 + ((lane >> 4) << 3);
-        ldsm_x4_t(v, sV + key * VSTR + dv * 2);
+      for (int ks = 0; ks < HDP / 16; ks++) {
 #pragma unroll
-        for (int mp = 0; mp < 2; mp++) {
-          mma_16816(O[mp][2 * np], P[mp][kk], v[0], v[1]);
-          mma_16816(O[mp][2 * np + 1], P[mp][kk], v[2], v[3]);
+        for (int jp = 0; jp < KT / 16; jp++) {
+          uint32_t bfr[4];
+          ldsm_x4(bfr, sK + (mp * KT + jp * 16) * KSTR + ks * 32 + k_lane);
+          mma_16816(S[2 * jp], qf[mp][ks], bfr[0], bfr[1]);
+          mma_16816(S[2 * jp + 1], qf[mp][ks], bfr[2], bfr[3]);
+        }
+      }
+      if (MASKED) {   // ragged last tile only: keys >= N
+#pragma unroll
+        for (int j = 0; j < KT / 8; j++) {
+          const int key = tile * KT + j * 8 + 2 * tq;
+          if (key >= N) { S[j][0] = -INFINITY; S[j][2] = -INFINITY; }
+          if (key + 1 >= N) { S[j][1] = -INFINITY; S[j][3] = -INFINITY; }
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KT / 8; j++) {
+        mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m[mp][0], mx0 * scale_log2), mn1 = fmaxf(m[mp][1], mx1 * scale_log2);
+      const float c0 = fast_exp2(m[mp][0] - mn0), c1 = fast_exp2(m[mp][1] - mn1);
+      m[mp][0] = mn0; m[mp][1] = mn1;
+      L[mp][0] *= c0; L[mp][2] *= c1;
+#pragma unroll
+      for (int j = 0; j < DV / 8; j++) { O[mp][j][0] *= c0; O[mp][j][1] *= c0; O[mp][j][2] *= c1; O[mp][j][3] *= c1; }
+      uint32_t P[KT / 16][4];
+#pragma unroll
+      for (int j = 0; j < KT / 8; j++) {
+        const float p0 = fast_exp2(fmaf(S[j][0], scale_log2, -mn0));
+        const float p1 = (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == 0) ? poly_exp2(fmaf(S[j][1], scale_log2, -mn0))
+                                                       : fast_exp2(fmaf(S[j][1], scale_log2, -mn0));
+        const float p2 = fast_exp2(fmaf(S[j][2], scale_log2, -mn1));
+        const float p3 = (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == 1 % (POLY > 0 ? POLY : 1)) ? poly_exp2(fmaf(S[j][3], scale_log2, -mn1))
+                                                              : fast_exp2(fmaf(S[j][3], scale_log2, -mn1));
+        P[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+        P[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int kk = 0; kk < KT / 16; kk++) {
+        mma_16816(L[mp], P[kk], ones_b, ones_b);
+#pragma unroll
+        for (int np = 0; np < DV / 16; np++) {
+          uint32_t v[4];
+          ldsm_x4_t(v, sV + kk * 16 * VSTR + np * 32 + v_lane);
+          mma_16816(O[mp][2 * np], P[kk], v[0], v[1]);
+          mma_16816(O[mp][2 * np + 1], P[kk], v[2], v[3]);
         }
       }
     }
+  };
+
+  const bool ragged = (N % KT) != 0;
+  for (int tile = 0; tile < ntiles; tile++) {
+    if (ragged && tile == ntiles - 1) process_tile(std::true_type{}, tile);
+    else process_tile(std::false_type{}, tile);
     __syncthreads();                       // everyone is done with this stage
-    if (tile + 2 < ntiles) load_kv(tile + 2, stage);
+    if (tile + 2 < ntiles) load_kv(tile + 2, tile & 1);
     cp_async_commit();
     cp_async_wait<1>();                    // tile+1 has landed
     __syncthreads();
@@ -240,14 +310,10 @@ __global__ void __launch_bounds__(NTHREADS) diffattn_flash_kernel(const bf16* __
   // ---- epilogue: normalise both maps, difference, RMSNorm over DV, scale, store ----
   float inv[2][2];
 #pragma unroll
-  for (int mp = 0; mp < 2; mp++)
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      float s = l[mp][r];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      inv[mp][r] = 1.f / s;
-    }
+  for (int mp = 0; mp < 2; mp++) {
+    inv[mp][0] = 1.f / __shfl_sync(0xffffffffu, L[mp][0], lane & ~3);   // column 0 of the ones tile lives in lane 4g
+    inv[mp][1] = 1.f / __shfl_sync(0xffffffffu, L[mp][2], lane & ~3);
+  }
   float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
   for (int j = 0; j < DV / 8; j++) {
@@ -332,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __
     float S[KT / 8][4];
     uint32_t P[KT / 16][4];
     qk_tile<D>(S, qf, sK, STR, lane);
-    softmax_tile<D>(S, P, m, l, O, scale_log2, tile * KT, N, lane);
+    softmax_tile<D, 0>(S, P, m, l, O, scale_log2, tile * KT, N, lane);
 #pragma unroll
     for (int kk = 0; kk < KT / 16; kk++) {
 #pragma unroll
@@ -370,11 +436,11 @@ __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __
   }
 }
 
-template <int HD>
+template <int HD, int POLY, int MINB>
 int launch_diff(const bf16* qkv, bf16* out, int B, int N, int E, int heads, float lambda, float eps, float mult,
                 cudaStream_t s) {
   using Cfg = DiffCfg<HD>;
-  auto kern = diffattn_flash_kernel<HD>;
+  auto kern = diffattn_flash_kernel<HD, POLY, MINB>;
   if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   dim3 grid(cdiv(N, QT), heads, B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
@@ -404,10 +470,25 @@ extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, in
   const bf16* q = (const bf16*)qkv;
   bf16* o = (bf16*)out;
   switch (hd) {
-    case 8: return launch_diff<8>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    case 16: return launch_diff<16>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    case 32: return launch_diff<32>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    case 64: return launch_diff<64>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 8: {
+      // tuning knob for experiments: CENET_DA_VARIANT = <poly><minblocks>
+      static int variant = getenv("CENET_DA_VARIANT") ? atoi(getenv("CENET_DA_VARIANT")) : 4;
+      switch (variant) {
+        case 4: return launch_diff<8, 0, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 5: return launch_diff<8, 0, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 6: return launch_diff<8, 0, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 44: return launch_diff<8, 4, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 45: return launch_diff<8, 4, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 26: return launch_diff<8, 2, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 25: return launch_diff<8, 2, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 15: return launch_diff<8, 1, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        case 16: return launch_diff<8, 1, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+        default: return launch_diff<8, 4, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+      }
+    }
+    case 16: return launch_diff<16, 4, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 32: return launch_diff<32, 4, 2>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
+    case 64: return launch_diff<64, 4, 1>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
     default: CENET_FAIL("cenet_diffattn_flash: head_dim %d not in {8,16,32,64}; use the materialised path", hd);
   }
 }

@@ -20,7 +20,6 @@
 
 namespace {
 constexpr int BM = 128;
-constexpr int NTHREADS = 192;
 constexpr int TILE_H = 8, TILE_W = 16;   // conv-mode M tile (pixels)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -95,49 +94,56 @@ struct TcParams {
   int M, N, K;
   int bn;            // N tile (multiple of 16, <= 256)
   int bk;            // k-block in elements: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
-  int stages;
-  int tmem_cols;     // power of two >= 32
-  int a_k0;          // K coordinate offset of A (alignment workaround for channel slices)
-  int num_kb;        // k-blocks
+  int stages;        // depth of the A (or A+W) ring
+  int tmem_cols;     // power of two >= 2*acc_stride (double-buffered accumulator)
+  int acc_stride;    // TMEM columns per accumulator stage = bn rounded up to 32 (tcgen05.ld reads 32-column chunks)
+  int num_kb;        // k-blocks per tile
+  int num_m_tiles;   // tiles along M (conv: images * tiles_h * tiles_w)
+  int w_resident;    // the whole [bn x K] weight slice stays in shared memory for the CTA's lifetime
+  int n_epi;         // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating column chunks)
   // conv mode
   int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
   EpiParams epi;
   int epi_vec;       // every epilogue operand is 16-byte addressable -> smem-transposed, vectorised epilogue
 };
 
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int NTHREADS_P = 64 + 32 * MAX_EPI_WARPS;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent, warp-specialised: grid = (CTAs along M, N tiles); CTA c walks M tiles c, c+G, c+2G, ...
+//   warp 0   : TMA producer (weights once if resident, then the A ring)
+//   warp 1   : TMEM alloc + tcgen05.mma issue into accumulator stage (tile & 1)
+//   warps 2-9: epilogue of the previous tile out of the other accumulator stage, overlapping the next tile's loads+MMAs
+__global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
-  const uint32_t stage_bytes = a_bytes + ((w_bytes + 1023u) & ~1023u);
-  const uint32_t bar_base = sbase + p.stages * stage_bytes;          // full[stages], empty[stages], tmem_full
-  const uint32_t tmem_slot = bar_base + (2 * p.stages + 1) * 8;
-  const uint32_t slab_base = (tmem_slot + 4 + 15u) & ~15u;           // 4 epilogue warps x 32 x 36 floats
+  const uint32_t wblk = (w_bytes + 1023u) & ~1023u;
+  const uint32_t wres_bytes = p.w_resident ? p.num_kb * wblk : 0;
+  const uint32_t stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
+  const uint32_t ring_base = sbase + wres_bytes;
+  const uint32_t bar_base = ring_base + p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (p.stages + s) * 8; };
-  const uint32_t tmem_full_bar = bar_base + 2 * p.stages * 8;
-
-  // ---- tile coordinates ----
+  const uint32_t tfull_bar = bar_base + 2 * p.stages * 8;            // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                        // [2]
+  const uint32_t wfull_bar = tempty_bar + 16;
+  const uint32_t tmem_slot = wfull_bar + 8;
+  const uint32_t slab_base = (tmem_slot + 4 + 15u) & ~15u;           // n_epi x 32 x 36 floats
   const int n0 = blockIdx.y * p.bn;
-  int m0 = 0, img = 0, h0 = 0, w0 = 0;
-  if (p.conv) {
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    img = t / p.tiles_h;
-    h0 = th * TILE_H; w0 = tw * TILE_W;
-  } else {
-    m0 = blockIdx.x * BM;
-  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, p.n_epi); }
+    mbar_init(wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -151,23 +157,48 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  auto tile_coords = [&](int tile, int& m0, int& img, int& h0, int& w0) {
+    m0 = img = h0 = w0 = 0;
+    if (p.conv) {
+      int t = tile;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h;
+      img = t / p.tiles_h;
+      h0 = th * TILE_H; w0 = tw * TILE_W;
+    } else {
+      m0 = tile * BM;
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < p.num_kb; kb++) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = sbase + s * stage_bytes, sw = sa + a_bytes;
-        mbar_arrive_expect_tx(full_bar(s), a_bytes + w_bytes);
-        if (p.conv) {
-          const int tap = kb / p.cblks, cb = kb % p.cblks;
-          const int kh = tap / p.KW, kw = tap % p.KW;
-          tma_load_4d(sa, &tmA, full_bar(s), cb * p.bk, w0 + kw - p.pad, h0 + kh - p.pad, img);
-          tma_load_2d(sw, &tmW, full_bar(s), tap * p.Cin + cb * p.bk, n0);
-        } else {
-          tma_load_2d(sa, &tmA, full_bar(s), p.a_k0 + kb * p.bk, m0);
-          tma_load_2d(sw, &tmW, full_bar(s), kb * p.bk, n0);
+      if (p.w_resident) {
+        mbar_arrive_expect_tx(wfull_bar, p.num_kb * w_bytes);
+        for (int kb = 0; kb < p.num_kb; kb++) {
+          const int kcoord = p.conv ? (kb / p.cblks) * p.Cin + (kb % p.cblks) * p.bk : kb * p.bk;
+          tma_load_2d(sbase + kb * wblk, &tmW, wfull_bar, kcoord, n0);
+        }
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        int m0, img, h0, w0;
+        tile_coords(tile, m0, img, h0, w0);
+        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = ring_base + s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), a_bytes + (p.w_resident ? 0 : w_bytes));
+          if (p.conv) {
+            const int tap = kb / p.cblks, cb = kb % p.cblks;
+            const int kh = tap / p.KW, kw = tap % p.KW;
+            tma_load_4d(sa, &tmA, full_bar(s), cb * p.bk, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            if (!p.w_resident) tma_load_2d(sa + a_bytes, &tmW, full_bar(s), tap * p.Cin + cb * p.bk, n0);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(s), kb * p.bk, m0);
+            if (!p.w_resident) tma_load_2d(sa + a_bytes, &tmW, full_bar(s), kb * p.bk, n0);
+          }
         }
       }
     }
@@ -178,128 +209,134 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t layout_type = p.bk == 64 ? 2u : 4u;
       const uint32_t sbo = p.bk == 64 ? 1024u : 512u;
-      for (int kb = 0; kb < p.num_kb; kb++) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(full_bar(s), ph);
+      if (p.w_resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
+      uint32_t it = 0, i = 0;
+      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, i++) {
+        const uint32_t as = i & 1, use = i >> 1;
+        mbar_wait(tempty_bar + 8 * as, (use & 1) ^ 1);       // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = sbase + s * stage_bytes, sw = sa + a_bytes;
-        const uint64_t adesc = make_smem_desc(sa, sbo, layout_type), bdesc = make_smem_desc(sw, sbo, layout_type);
-        for (int k = 0; k < p.bk / 16; k++) {
-          // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte start-address field
-          umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
+        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = ring_base + s * stage_bytes;
+          const uint32_t sw = p.w_resident ? sbase + kb * wblk : sa + a_bytes;
+          const uint64_t adesc = make_smem_desc(sa, sbo, layout_type), bdesc = make_smem_desc(sw, sbo, layout_type);
+          for (int k = 0; k < p.bk / 16; k++) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte start-address field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(s));                           // frees the ring slot when these MMAs retire
         }
-        umma_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
-        if (kb == p.num_kb - 1) umma_commit(tmem_full_bar);   // accumulator complete
+        umma_commit(tfull_bar + 8 * as);                       // accumulator of this tile complete
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue warps =====================
     // tcgen05.ld gives each thread 32 consecutive columns of ITS row.  Row-per-thread global accesses would touch 32
-    // different lines per instruction, so the tile is transposed through a per-warp smem slab: phase A (row per
-    // thread) applies alpha / row_scale / bias / act and writes the slab; phase B re-reads it with 4 lanes per row,
-    // 8 columns (16 bytes of bf16) per lane, so residual / gate loads and the output stores are full 32-byte sectors.
+    // different lines per instruction, so each 32x32 block is transposed through a per-warp smem slab and re-read with
+    // 4 lanes per row, 8 columns (16 bytes of bf16) per lane: residual / gate loads and the output stores are then
+    // full 32-byte sectors.  Warps 2..9: TMEM lane quarter = warp % 4, column-chunk parity = (warp - 2) / 4.
+    const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int r_own = quarter * 32 + lane;      // accumulator row == TMEM lane
-    float* slab = reinterpret_cast<float*>(smem_raw + (slab_base - smem_u32(smem_raw))) + (warp - 2) * (32 * 36);
-    auto row_index = [&](int r, long long& m) -> bool {
-      if (p.conv) {
-        const int h = h0 + r / TILE_W, w = w0 + r % TILE_W;
-        m = ((long long)img * p.H + h) * p.W + w;
-        return (h < p.H) && (w < p.W);
-      }
-      m = (long long)m0 + r;
-      return m < p.M;
-    };
-    long long m_own;
-    const bool own_ok = row_index(r_own, m_own);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    const int half = ew >> 2;
+    const int cstep = p.n_epi == 8 ? 64 : 32;
+    float* slab = reinterpret_cast<float*>(smem_raw + (slab_base - smem_u32(smem_raw))) + ew * (32 * 36);
     const EpiParams& e = p.epi;
-    const int nlim = min(p.N, n0 + p.bn);       // columns owned by this tile (bn % 32 may be 16)
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
-      if (n0 + c0 >= p.N) break;                 // warp-uniform
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
-      tmem_ld_wait();
-      const int nbase = n0 + c0;
-      if (p.epi_vec) {
-        // ---- phase A: raw accumulators into the slab (row stride 36 floats: 16-byte aligned, conflict-free) ----
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-          *reinterpret_cast<float4*>(slab + lane * 36 + q * 4) =
-              make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
-                          __uint_as_float(acc[4 * q + 3]));
-        __syncwarp();
-        // ---- phase B: 4 lanes per row, 8 columns per lane; the whole epilogue on 8-wide vectors ----
-        const int cg = (lane & 3) * 8;
-        const int n = nbase + cg;
-        float bcol[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) bcol[j] = (e.bias && !e.bias_per_row && n + j < p.N) ? e.bias[n + j] : 0.f;
-#pragma unroll 1
-        for (int it = 0; it < 4; it++) {
-          const int rr = it * 8 + (lane >> 2);
-          long long m;
-          const bool ok = row_index(quarter * 32 + rr, m);
-          if (!ok || n >= nlim) continue;
-          float v[8];
-          {
-            const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
-            const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
-            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-          }
-          const float rs = e.alpha * (e.row_scale ? e.row_scale[m] : 1.f);
-          const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
-          if (!e.act_after_res && e.act != CENET_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
-          }
-          const bool full = n + 8 <= nlim;
-          if (e.mul) {
-            float t[8];
-            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, t);
-            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] *= apply_act(t[j], e.mul_act, 0.f);
-          }
-          if (e.res1) {
-            float t[8];
-            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t);
-            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] += t[j] * (e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale);
-          }
-          if (e.res2) {
-            float t[8];
-            if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t);
-            else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] += t[j];
-          }
-          if (e.act_after_res && e.act != CENET_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
-          }
-          if (full) {
-            if (e.c_dtype == CENET_BF16) stv<8>(reinterpret_cast<bf16*>(e.C) + m * e.ldc + n, v);
-            else stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
-          } else {
-            for (int j = 0; j < 8 && n + j < nlim; j++) epi_store(e, v[j], m, n + j, 0);
-          }
+    const int nlim = min(p.N, n0 + p.bn);       // columns owned by this CTA (bn % 32 may be 16)
+    uint32_t i = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, i++) {
+      int m0, img, h0, w0;
+      tile_coords(tile, m0, img, h0, w0);
+      auto row_index = [&](int r, long long& m) -> bool {
+        if (p.conv) {
+          const int h = h0 + r / TILE_W, w = w0 + r % TILE_W;
+          m = ((long long)img * p.H + h) * p.W + w;
+          return (h < p.H) && (w < p.W);
         }
-        __syncwarp();
-      } else {
-        // operands that are not 16-byte addressable (odd pitches / channel-slice outputs): element-wise epilogue
+        m = (long long)m0 + r;
+        return m < p.M;
+      };
+      const uint32_t as = i & 1, use = i >> 1;
+      long long m_own;
+      const bool own_ok = row_index(quarter * 32 + lane, m_own);
+      mbar_wait(tfull_bar + 8 * as, use & 1);
+      tc_fence_after();
+      for (int c0 = half * 32; c0 < p.bn; c0 += cstep) {
+        if (n0 + c0 >= p.N) break;                 // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * p.acc_stride + c0), acc);
+        tmem_ld_wait();
+        const int nbase = n0 + c0;
 #pragma unroll
         for (int q = 0; q < 8; q++)
           *reinterpret_cast<float4*>(slab + lane * 36 + q * 4) =
               make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
                           __uint_as_float(acc[4 * q + 3]));
         __syncwarp();
-        if (own_ok) {
+        if (p.epi_vec) {
+          const int cg = (lane & 3) * 8;
+          const int n = nbase + cg;
+          float bcol[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) bcol[j] = (e.bias && !e.bias_per_row && n + j < p.N) ? e.bias[n + j] : 0.f;
+#pragma unroll 1
+          for (int itr = 0; itr < 4; itr++) {
+            const int rr = itr * 8 + (lane >> 2);
+            long long m;
+            const bool ok = row_index(quarter * 32 + rr, m);
+            if (!ok || n >= nlim) continue;
+            float v[8];
+            {
+              const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+              const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+              v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            }
+            const float rs = e.alpha * (e.row_scale ? e.row_scale[m] : 1.f);
+            const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
+            if (!e.act_after_res && e.act != CENET_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
+            }
+            const bool full = n + 8 <= nlim;
+            if (e.mul) {
+              float t[8];
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, t);
+              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] *= apply_act(t[j], e.mul_act, 0.f);
+            }
+            if (e.res1) {
+              float t[8];
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t);
+              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] += t[j] * (e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale);
+            }
+            if (e.res2) {
+              float t[8];
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t);
+              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] += t[j];
+            }
+            if (e.act_after_res && e.act != CENET_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
+            }
+            if (full) {
+              if (e.c_dtype == CENET_BF16) stv<8>(reinterpret_cast<bf16*>(e.C) + m * e.ldc + n, v);
+              else stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
+            } else {
+              for (int j = 0; j < 8 && n + j < nlim; j++) epi_store(e, v[j], m, n + j, 0);
+            }
+          }
+        } else if (own_ok) {
+          // operands that are not 16-byte addressable (odd pitches / channel-slice outputs): element-wise epilogue
 #pragma unroll 1
           for (int c = 0; c < 32; c++) {
             const int n = nbase + c;
@@ -308,9 +345,13 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         }
         __syncwarp();
       }
+      // this warp no longer reads the accumulator stage: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -378,15 +419,14 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   p.bn = pick_bn(a->N);
   p.conv = a->conv;
   p.epi = make_epi(a);
-  p.a_k0 = 0;
   CUtensorMap tmA, tmW;
-  dim3 grid;
   if (a->conv) {
     p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.pad = a->pad;
     p.bk = a->Cin == 32 ? 32 : 64;
     p.cblks = a->Cin / p.bk;
     p.num_kb = a->KH * a->KW * p.cblks;
     p.tiles_h = cdiv(a->H, TILE_H); p.tiles_w = cdiv(a->W, TILE_W);
+    p.num_m_tiles = a->Bimg * p.tiles_h * p.tiles_w;
     const CUtensorMapSwizzle swz = p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->Bimg};
     cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)a->W * a->Cin * 2, (cuuint64_t)a->H * a->W * a->Cin * 2};
@@ -396,30 +436,41 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     cuuint64_t ws[1] = {(cuuint64_t)a->ldw * 2};
     cuuint32_t wb[2] = {(cuuint32_t)p.bk, (cuuint32_t)p.bn};
     if (encode_map(&tmW, a->Wt, 2, wd, ws, wb, swz)) return -1;
-    grid = dim3(a->Bimg * p.tiles_h * p.tiles_w, cdiv(a->N, p.bn), 1);
   } else {
     p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0;
     p.bk = 64;
-    const void* abase = a->A;
     p.num_kb = cdiv(a->K, 64);
+    p.num_m_tiles = cdiv(a->M, BM);
     cuuint64_t ad[2] = {(cuuint64_t)a->K, (cuuint64_t)a->M};
     cuuint64_t as[1] = {(cuuint64_t)a->lda * 2};
     cuuint32_t ab[2] = {64, BM};
-    if (encode_map(&tmA, abase, 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    if (encode_map(&tmA, a->A, 2, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     cuuint64_t wd[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
     cuuint64_t ws[1] = {(cuuint64_t)a->ldw * 2};
     cuuint32_t wb[2] = {64, (cuuint32_t)p.bn};
     if (encode_map(&tmW, a->Wt, 2, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
-    grid = dim3(cdiv(a->M, BM), cdiv(a->N, p.bn), 1);
   }
-  CENET_REQUIRE(grid.y <= 65535, "cenet_gemm_tc: too many N tiles");
+  const int n_tiles = cdiv(a->N, p.bn);
+  CENET_REQUIRE(n_tiles <= 65535, "cenet_gemm_tc: too many N tiles");
+  // ---- shared-memory plan (one persistent CTA per SM, <= ~200 KB) ----
   const int a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
-  const int stage_bytes = a_bytes + ((w_bytes + 1023) & ~1023);
-  int stages = p.num_kb < 4 ? p.num_kb : 4;
-  while (stages > 1 && stages * stage_bytes > 96 * 1024) stages--;
+  const int wblk = (w_bytes + 1023) & ~1023;
+  p.acc_stride = (p.bn + 31) & ~31;
+  // narrow-N problems are epilogue/issue-bound per CTA: two CTAs per SM (TMEM 2 x 256 columns, ~100 KB smem each);
+  // wide tiles get the whole SM and eight epilogue warps
+  const int ctas_per_sm = (2 * p.acc_stride <= 256) ? 2 : 1;
+  p.n_epi = (ctas_per_sm == 1) ? 8 : 4;
+  const int slab_bytes = p.n_epi * 32 * 36 * 4;
+  const int budget = (ctas_per_sm == 1 ? 200 : 100) * 1024 - slab_bytes - 1024 - 256;
+  p.w_resident = (long long)p.num_kb * wblk <= (ctas_per_sm == 1 ? 96 : 56) * 1024 && p.num_m_tiles > 1;
+  const int wres = p.w_resident ? p.num_kb * wblk : 0;
+  const int stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
+  int stages = (budget - wres) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 1) stages = 1;                              // the ring runs ahead across tiles: 8 x 16 KB in flight per SM
   p.stages = stages;
   int cols = 32;
-  while (cols < p.bn) cols <<= 1;
+  while (cols < 2 * p.acc_stride) cols <<= 1;
   p.tmem_cols = cols;
   auto vec_ok = [](const void* ptr, int dtype, long long ld) {
     return ptr == nullptr || (dtype == CENET_BF16 && ld % 8 == 0 && ((uintptr_t)ptr & 15) == 0);
@@ -428,12 +479,16 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
                                                       (a->c_dtype == CENET_F32 && a->ldc % 4 == 0));
   p.epi_vec = c_ok && vec_ok(a->res1, a->res1_dtype, a->ldr1) && vec_ok(a->res2, a->res2_dtype, a->ldr2) &&
               vec_ok(a->mul, a->mul_dtype, a->ldmul);
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 4 * 32 * 36 * 4 + 1024;
+  const size_t smem = (size_t)wres + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 32 + slab_bytes + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   });
-  gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(tmA, tmW, p);
+  int gx = kNumSMs * ctas_per_sm / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_m_tiles) gx = p.num_m_tiles;
+  dim3 grid(gx, n_tiles, 1);
+  gemm_tc_kernel<<<grid, 64 + 32 * p.n_epi, smem, s>>>(tmA, tmW, p);
   CENET_LAUNCH_CHECK("gemm_tc");
   return 0;
 }

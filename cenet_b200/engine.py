@@ -180,6 +180,7 @@ class Engine:
             M(p + ".mixer.w", sd[p + ".mixer.weight"].flatten(1))
         # ---------------- head ----------------
         self._pack_resblock(sd, "out.rb.0", 5)
+        self._pack_stem(sd, "out.rb.0")
         self._pack_resblock(sd, "out.out.0", 3)
         P("out.w", sd["out.w"].reshape(-1))
         self._pack_up(sd, "out.up", cfg["out_up_block"])
@@ -187,6 +188,13 @@ class Engine:
         P("out.head.b", sd["out.out.1.conv.conv.bias"])
         self._wver = self._weights_version()
         self._graphs.clear()                                   # host scalars are baked into captured launches
+
+    def _pack_stem(self, sd, p):
+        """fp32 filters of the CUDA-core stem kernel (first conv of out.rb.0 and its 1x1 residual branch)."""
+        s1, t1 = self._bn_fold(sd, p + ".norm1")
+        self._put(p + ".stem.w1", self._conv_mat(sd[p + ".conv1.conv.weight"]) * s1[:, None]); self._put(p + ".stem.b1", t1)
+        s3, t3 = self._bn_fold(sd, p + ".norm3")
+        self._put(p + ".stem.w3", sd[p + ".conv3.conv.weight"].flatten(1) * s3[:, None]); self._put(p + ".stem.b3", t3)
 
     def _pack_resblock(self, sd, p, k):
         for i in (1, 2, 3):
@@ -535,7 +543,15 @@ class Engine:
         om = C1 // 2
         Hh, Wh = H // 2, W // 2
         z = self.buf("head.z", (B * Hh * Wh, 2 * om))
-        rb = self._resblock(xc, B, H, W, Cin, om, 5, "out.rb.0", "head.rb")
+        # out.rb.0: stem kernel (conv1+BN+LReLU and the 1x1 residual branch), then the 5x5 32->32 conv on tensor cores
+        ops.tag = "head.rb"
+        o1 = self.buf("head.rb.o1", (B, H, W, om))
+        rres = self.buf("head.rb.r", (B * H * W, om))
+        ops.stem5x5(xc, w["out.rb.0.stem.w1"], w["out.rb.0.stem.b1"], w["out.rb.0.stem.w3"], w["out.rb.0.stem.b3"], o1,
+                    rres, B, H, W, Cin, 0.01)
+        rb = self.buf("head.rb.o2", (B * H * W, om))
+        ops.conv_nhwc(o1, w["out.rb.0.c2.w"], rb, 5, 1, 2, bias=w["out.rb.0.c2.b"], act=ACT_LEAKY, slope=0.01,
+                      act_after_res=True, res1=rres, ldr1=om, impl=self.gemm_impl)
         ops.maxpool2_scale(rb, z, 2 * om, om, w["out.w"], B, H, W, om)
         self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
         o = self._resblock(z, B, Hh, Wh, 2 * om, 2 * om, 3, "out.out.0", "head.out")

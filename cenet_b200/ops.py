@@ -227,6 +227,12 @@ def pool_branch(x, ldx, coff, y, ldy, coff_y, w_rr, bn_scale, bn_shift, slope, p
     return y
 
 
+def stem5x5(x, w1, b1, w3, b3, o1, r, B, H, W, Cin, slope):
+    L.call("cenet_stem5x5", _p(x), dt(x), _f32(w1, "w1"), _f32(b1, "b1"), _f32(w3, "w3"), _f32(b3, "b3"), _p(o1), _p(r),
+           dt(o1), B, H, W, Cin, slope, _stream())
+    return o1, r
+
+
 # ------------------------------------------------------------------------------------------------------ head / loss
 def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
     if labels is not None and labels.dtype != torch.int64:

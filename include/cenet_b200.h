@@ -152,6 +152,13 @@ int cenet_pool_branch(const void* x, int x_dtype, long long ldx, int coff, void*
                       int coff_y, const float* w_rr, const float* bn_scale, const float* bn_shift, float slope,
                       float* pooled_ws, int B, int H, int W, int r, cenet_stream_t s);
 
+/* ---- OutHead stem (out.py:41-44, unet.py:201-209): first res-block conv on the raw image -----------------------------
+ * o1 = LeakyReLU(conv5x5(x; w1)+b1)  (BN1 folded into w1 [32, 25*Cin] fp32 with K ordered (kh,kw,ci), and b1),
+ * r  = conv1x1(x; w3)+b3             (BN3 folded; w3 [32,Cin]); r may be NULL.  x [B,H,W,Cin], Cin <= 4; outputs
+ * [B,H,W,32] of dtype o_dtype. */
+int cenet_stem5x5(const void* x, int x_dtype, const float* w1, const float* b1, const float* w3, const float* b3,
+                  void* o1, void* r, int o_dtype, int B, int H, int W, int Cin, float slope, cenet_stream_t s);
+
 /* ---- head (out.py:74 + metrics_eval.py:52) -------------------------------------------------------------------
  * y: [B,h,w,ncls] fp32 (NHWC) -> logits [B,ncls,2h,2w] fp32 (bilinear x2, align_corners=False) and / or
  * labels [B,2h,2w] int64 = argmax over classes, lowest index on ties.  Either output may be NULL. */

@@ -290,6 +290,16 @@ def pool_branch(x, ldx, coff, y, ldy, coff_y, w_rr, bn_scale, bn_shift, slope, p
     return y
 
 
+def stem5x5(x, w1, b1, w3, b3, o1, r, B, H, W, Cin, slope):
+    _LAUNCHES[0] += 1
+    xi = _flat(x).view(B, H, W, Cin).float().permute(0, 3, 1, 2)
+    wk = w1.view(32, 5, 5, Cin).permute(0, 3, 1, 2)
+    _flat(o1).view(B, H, W, 32).copy_(F.leaky_relu(F.conv2d(xi, wk, b1, padding=2), slope).permute(0, 2, 3, 1))
+    if r is not None:
+        _flat(r).view(B, H, W, 32).copy_(F.conv2d(xi, w3.view(32, Cin, 1, 1), b3).permute(0, 2, 3, 1))
+    return o1, r
+
+
 def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
     _LAUNCHES[0] += 1
     v = F.interpolate(y.view(B, h, w, ncls).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")

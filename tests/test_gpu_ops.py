@@ -405,3 +405,22 @@ def test_dice_ce(golden_loss):
         loss2, grad2 = torch.empty_like(loss), torch.empty_like(grad)
         ops.dice_ce(logits, labels, loss2, grad2, ws, B, ncls, H * W, 0.5, 0.5)
         assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
+
+
+@pytest.mark.parametrize("Cin,dtype", [(1, torch.bfloat16), (3, torch.bfloat16), (1, torch.float32)])
+def test_stem5x5(Cin, dtype):
+    from cenet_b200 import ops
+    B, H, W = 2, 40, 52
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    w1 = torch.randn(32, Cin, 5, 5, generator=g(2)) / 5
+    b1, b3 = torch.randn(32, generator=g(3)), torch.randn(32, generator=g(4))
+    w3 = torch.randn(32, Cin, generator=g(5))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    o1 = torch.empty(B, H, W, 32, device=DEV, dtype=dtype)
+    r = torch.empty(B, H, W, 32, device=DEV, dtype=dtype)
+    ops.stem5x5(xn, w1.permute(0, 2, 3, 1).reshape(32, -1).contiguous().to(DEV), b1.to(DEV), w3.contiguous().to(DEV),
+                b3.to(DEV), o1, r, B, H, W, Cin, 0.01)
+    xr = xn.float().cpu().permute(0, 3, 1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    assert rel(o1, F.leaky_relu(F.conv2d(xr, w1, b1, padding=2), 0.01).permute(0, 2, 3, 1)) < tol
+    assert rel(r, F.conv2d(xr, w3[:, :, None, None], b3).permute(0, 2, 3, 1)) < tol
