@@ -136,10 +136,10 @@ __device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P
 //   HD: real head_dim (8,16,32,64); HDP = max(HD,16); DV = 2*HD
 // smem rows are padded by 16 bytes so that ldmatrix's 8 row addresses fall in distinct 16-byte bank groups.
 // =====================================================================================================================
-template <int HD>
+template <int HD, int DVT>
 struct DiffCfg {
   static constexpr int HDP = HD < 16 ? 16 : HD;
-  static constexpr int DV = 2 * HD;
+  static constexpr int DV = DVT;
   static constexpr int KSTR = HDP * 2 + 16;           // bytes per K/Q smem row
   static constexpr int VSTR = DV * 2 + 16;            // bytes per V smem row
   static constexpr int Q_BYTES = 2 * QT * KSTR;       // two maps
@@ -149,16 +149,21 @@ struct DiffCfg {
   static constexpr int SMEM = Q_BYTES + 2 * STAGE;
 };
 
-template <int HD, int POLY, int MINB>
+// Global layout of one token row: [ q: 2h heads x HD | k: 2h x HD | v: h x DV ]; output rows: [ h x DV ].
+// For the reference's natural layout HD = hd, DV = 2 hd; head dims that are not MMA friendly (hd = 20) are zero-padded
+// by the host (HD = 32, DV = 48): `dv_real` restores the RMSNorm mean and `scale_log2` carries the real 1/sqrt(hd).
+template <int HD, int DVT, int POLY, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                                  int N, int E, float scale_log2, float lambda,
-                                                                  float eps, float mult) {
-  using Cfg = DiffCfg<HD>;
+                                                                  int N, int heads, float dv_real, float scale_log2,
+                                                                  float lambda, float eps, float mult) {
+  using Cfg = DiffCfg<HD, DVT>;
+  const int E = 2 * heads * HD;            // width of the q block (= k block)
+  const int EO = heads * DVT;              // output row width
   constexpr int HDP = Cfg::HDP, DV = Cfg::DV, KSTR = Cfg::KSTR, VSTR = Cfg::VSTR;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
-  const long long row3E = 3LL * E;
+  const long long row3E = 2LL * E + EO;
   const bf16* base = qkv + (long long)b * N * row3E;
   const uint32_t sQ = smem_u32(smem), sKV = sQ + Cfg::Q_BYTES;
 
@@ -326,15 +331,15 @@ __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf
   }
   ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
   ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
-  const float r0 = rsqrtf(ss0 / (float)DV + eps) * mult, r1 = rsqrtf(ss1 / (float)DV + eps) * mult;
+  const float r0 = rsqrtf(ss0 / dv_real + eps) * mult, r1 = rsqrtf(ss1 / dv_real + eps) * mult;
   const int g = lane >> 2, t = lane & 3;
   const int n0 = q0 + warp * 16 + g, n1 = n0 + 8;
-  bf16* ob = out + (long long)b * N * E + head * DV;
+  bf16* ob = out + (long long)b * N * EO + head * DV;
 #pragma unroll
   for (int j = 0; j < DV / 8; j++) {
     const int col = j * 8 + 2 * t;
-    if (n0 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * E + col) = pack_bf16(O[0][j][0] * r0, O[0][j][1] * r0);
-    if (n1 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * E + col) = pack_bf16(O[0][j][2] * r1, O[0][j][3] * r1);
+    if (n0 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * EO + col) = pack_bf16(O[0][j][0] * r0, O[0][j][1] * r0);
+    if (n1 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * EO + col) = pack_bf16(O[0][j][2] * r1, O[0][j][3] * r1);
   }
 }
 
@@ -436,15 +441,15 @@ __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __
   }
 }
 
-template <int HD, int POLY, int MINB>
-int launch_diff(const bf16* qkv, bf16* out, int B, int N, int E, int heads, float lambda, float eps, float mult,
+template <int HD, int DVT, int POLY, int MINB>
+int launch_diff(const bf16* qkv, bf16* out, int B, int N, int heads, int hd_real, float lambda, float eps, float mult,
                 cudaStream_t s) {
-  using Cfg = DiffCfg<HD>;
-  auto kern = diffattn_flash_kernel<HD, POLY, MINB>;
+  using Cfg = DiffCfg<HD, DVT>;
+  auto kern = diffattn_flash_kernel<HD, DVT, POLY, MINB>;
   if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   dim3 grid(cdiv(N, QT), heads, B);
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(qkv, out, N, E, scale_log2, lambda, eps, mult);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)hd_real);
+  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(qkv, out, N, heads, (float)(2 * hd_real), scale_log2, lambda, eps, mult);
   CENET_LAUNCH_CHECK("diffattn_flash");
   return 0;
 }
@@ -460,6 +465,16 @@ int launch_nl(const bf16* tpg, bf16* out, int B, int N, float scale, cudaStream_
 }
 }  // namespace
 
+static int diffattn_dispatch(const bf16* q, bf16* o, int B, int N, int heads, int hdp, int dvp, int hd_real, float lambda,
+                             float eps, float mult, cudaStream_t st) {
+  if (hdp == 8 && dvp == 16) return launch_diff<8, 16, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+  if (hdp == 16 && dvp == 32) return launch_diff<16, 32, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+  if (hdp == 32 && dvp == 48) return launch_diff<32, 48, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+  if (hdp == 32 && dvp == 64) return launch_diff<32, 64, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+  if (hdp == 64 && dvp == 128) return launch_diff<64, 128, 0, 1>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+  CENET_FAIL("cenet_diffattn_flash: no kernel for padded head_dim %d / value width %d; use the materialised path", hdp, dvp);
+}
+
 extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
                                     float mult, cenet_stream_t s) {
   if (B == 0 || N == 0) return 0;
@@ -467,30 +482,17 @@ extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, in
   CENET_REQUIRE(heads >= 1 && E % (2 * heads) == 0, "cenet_diffattn_flash: E=%d not divisible by 2*heads=%d", E, 2 * heads);
   CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash: grid too large");
   const int hd = E / (2 * heads);
-  const bf16* q = (const bf16*)qkv;
-  bf16* o = (bf16*)out;
-  switch (hd) {
-    case 8: {
-      // tuning knob for experiments: CENET_DA_VARIANT = <poly><minblocks>
-      static int variant = getenv("CENET_DA_VARIANT") ? atoi(getenv("CENET_DA_VARIANT")) : 4;
-      switch (variant) {
-        case 4: return launch_diff<8, 0, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 5: return launch_diff<8, 0, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 6: return launch_diff<8, 0, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 44: return launch_diff<8, 4, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 45: return launch_diff<8, 4, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 26: return launch_diff<8, 2, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 25: return launch_diff<8, 2, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 15: return launch_diff<8, 1, 5>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        case 16: return launch_diff<8, 1, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-        default: return launch_diff<8, 4, 6>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-      }
-    }
-    case 16: return launch_diff<16, 4, 4>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    case 32: return launch_diff<32, 4, 2>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    case 64: return launch_diff<64, 4, 1>(q, o, B, N, E, heads, lambda, eps, mult, to_stream(s));
-    default: CENET_FAIL("cenet_diffattn_flash: head_dim %d not in {8,16,32,64}; use the materialised path", hd);
-  }
+  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, to_stream(s));
+}
+
+extern "C" int cenet_diffattn_flash_padded(const void* qkv, void* out, int B, int N, int heads, int hd_pad, int dv_pad,
+                                           int hd_real, float lambda, float eps, float mult, cenet_stream_t s) {
+  if (B == 0 || N == 0) return 0;
+  CENET_REQUIRE(qkv && out, "cenet_diffattn_flash_padded: null pointer");
+  CENET_REQUIRE(heads >= 1 && hd_real >= 1 && hd_real <= hd_pad && 2 * hd_real <= dv_pad,
+                "cenet_diffattn_flash_padded: bad head geometry (hd %d pad %d, dv pad %d)", hd_real, hd_pad, dv_pad);
+  CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash_padded: grid too large");
+  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd_pad, dv_pad, hd_real, lambda, eps, mult, to_stream(s));
 }
 
 extern "C" int cenet_nonlocal_flash(const void* tpg, void* out, int B, int N, int C, float scale, cenet_stream_t s) {

@@ -14,56 +14,88 @@ struct FeaScales {
   int off[kMaxScales];                    // smem offset (floats) of each down buffer
 };
 
-// One CTA per (b,c) plane.  Plane and its down-sampled copies live in shared memory; HBM sees y, gate once (read)
-// and z once (write): 3 * H*W * sizeof(T) algorithmic bytes per plane.
+// A CTA handles PPB consecutive (b,c) planes, each by a team of 256/PPB threads (PPB = 1 for 56x56 planes, 4 for 28x28,
+// 8 for 14x14, so small planes do not leave most of the block idle).  Each plane and its down-sampled copies live in
+// shared memory; the bilinear source indices / weights of every row and column are tabulated once per CTA, so the
+// per-pixel work is 4 smem reads + 3 FMAs per scale.  HBM sees y and gate once (read) and z once (write):
+// 3 * H*W * sizeof(T) algorithmic bytes per plane.
+struct LerpTab { short i0, i1; float l; };
+
 template <typename T>
 __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ y, const T* __restrict__ gate,
                                                           T* __restrict__ z, const float* __restrict__ w_c, int C2,
-                                                          int H, int W, const FeaScales sc) {
+                                                          int H, int W, long long nplanes, int ppb, unsigned wmagic,
+                                                          const FeaScales sc, int plane_floats) {
   extern __shared__ float sm[];
-  float* plane = sm;
-  const long long pl = blockIdx.x;
-  const int c = (int)(pl % C2);
-  const int HW = H * W;
-  const T* yp = y + pl * HW;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) plane[i] = ldf(yp + i);
-  __syncthreads();
+  // tables: for each scale: down rows (hd), down cols (wd), up rows (H), up cols (W)
+  LerpTab* tab = reinterpret_cast<LerpTab*>(sm);
+  int toff[kMaxScales][4];
+  int tcount = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxScales; k++) {
+    toff[k][0] = tcount; tcount += (k < sc.n && !sc.identity[k]) ? sc.hd[k] : 0;
+    toff[k][1] = tcount; tcount += (k < sc.n && !sc.identity[k]) ? sc.wd[k] : 0;
+    toff[k][2] = tcount; tcount += (k < sc.n && !sc.identity[k]) ? H : 0;
+    toff[k][3] = tcount; tcount += (k < sc.n && !sc.identity[k]) ? W : 0;
+  }
   for (int k = 0; k < sc.n; k++) {
     if (sc.identity[k]) continue;
-    float* d = sm + sc.off[k];
-    const int hd = sc.hd[k], wd = sc.wd[k];
-    for (int i = threadIdx.x; i < hd * wd; i += blockDim.x) {
-      const int r = i / wd, q = i % wd;
-      int h0, h1, w0, w1;
-      float lh, lw;
-      bilin_src(r, sc.inv_s[k], H, h0, h1, lh);
-      bilin_src(q, sc.inv_s[k], W, w0, w1, lw);
-      d[i] = (1.f - lh) * ((1.f - lw) * plane[h0 * W + w0] + lw * plane[h0 * W + w1]) +
-             lh * ((1.f - lw) * plane[h1 * W + w0] + lw * plane[h1 * W + w1]);
+    for (int i = threadIdx.x; i < sc.hd[k] + sc.wd[k] + H + W; i += blockDim.x) {
+      int i0, i1; float l; int dst;
+      if (i < sc.hd[k]) { bilin_src(i, sc.inv_s[k], H, i0, i1, l); dst = toff[k][0] + i; }
+      else if (i < sc.hd[k] + sc.wd[k]) { bilin_src(i - sc.hd[k], sc.inv_s[k], W, i0, i1, l); dst = toff[k][1] + i - sc.hd[k]; }
+      else if (i < sc.hd[k] + sc.wd[k] + H) { bilin_src(i - sc.hd[k] - sc.wd[k], sc.up_h[k], sc.hd[k], i0, i1, l); dst = toff[k][2] + i - sc.hd[k] - sc.wd[k]; }
+      else { bilin_src(i - sc.hd[k] - sc.wd[k] - H, sc.up_w[k], sc.wd[k], i0, i1, l); dst = toff[k][3] + i - sc.hd[k] - sc.wd[k] - H; }
+      tab[dst].i0 = (short)i0; tab[dst].i1 = (short)i1; tab[dst].l = l;
+    }
+  }
+  const int team = blockDim.x / ppb, tm = threadIdx.x / team, tt = threadIdx.x - tm * team;
+  const long long pl = (long long)blockIdx.x * ppb + tm;
+  const bool live = pl < nplanes;
+  const int HW = H * W;
+  float* plane = sm + 2 * tcount + (size_t)tm * plane_floats;     // LerpTab = 8 bytes = 2 floats
+  if (live) {
+    const T* yp = y + pl * HW;
+    for (int i = tt; i < HW; i += team) plane[i] = ldf(yp + i);
+  }
+  __syncthreads();
+  if (live) {
+    for (int k = 0; k < sc.n; k++) {
+      if (sc.identity[k]) continue;
+      float* d = plane + sc.off[k];
+      const int hd = sc.hd[k], wd = sc.wd[k];
+      const unsigned dmagic = 0xFFFFFFFFu / (unsigned)wd + 1u;
+      for (int i = tt; i < hd * wd; i += team) {
+        const int r = (int)__umulhi((unsigned)i, dmagic), q = i - r * wd;
+        const LerpTab a = tab[toff[k][0] + r], bcol = tab[toff[k][1] + q];
+        const float top = fmaf(bcol.l, plane[a.i0 * W + bcol.i1] - plane[a.i0 * W + bcol.i0], plane[a.i0 * W + bcol.i0]);
+        const float bot = fmaf(bcol.l, plane[a.i1 * W + bcol.i1] - plane[a.i1 * W + bcol.i0], plane[a.i1 * W + bcol.i0]);
+        d[i] = fmaf(a.l, bot - top, top);
+      }
     }
   }
   __syncthreads();
+  if (!live) return;
+  const int c = (int)(pl % C2);
   const float wc = w_c[c];
   const int npair = sc.n * (sc.n - 1) / 2;
+  const float inv_pair = npair > 0 ? 1.f / (float)npair : 0.f;
   const T* gp = gate + pl * HW;
   T* zp = z + pl * HW;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int h = i / W, w = i % W;
+  for (int i = tt; i < HW; i += team) {
+    const int h = (int)__umulhi((unsigned)i, wmagic), w = i - h * W;
     const float x = plane[i];
     float e[kMaxScales];
 #pragma unroll
     for (int k = 0; k < kMaxScales; k++) {
       e[k] = 0.f;
       if (k < sc.n && !sc.identity[k]) {
-        const float* d = sm + sc.off[k];
-        const int hd = sc.hd[k], wd = sc.wd[k];
-        int h0, h1, w0, w1;
-        float lh, lw;
-        bilin_src(h, sc.up_h[k], hd, h0, h1, lh);
-        bilin_src(w, sc.up_w[k], wd, w0, w1, lw);
-        const float up = (1.f - lh) * ((1.f - lw) * d[h0 * wd + w0] + lw * d[h0 * wd + w1]) +
-                         lh * ((1.f - lw) * d[h1 * wd + w0] + lw * d[h1 * wd + w1]);
-        e[k] = fabsf(x - up);
+        const float* d = plane + sc.off[k];
+        const int wd = sc.wd[k];
+        const LerpTab a = tab[toff[k][2] + h], bcol = tab[toff[k][3] + w];
+        const float top = fmaf(bcol.l, d[a.i0 * wd + bcol.i1] - d[a.i0 * wd + bcol.i0], d[a.i0 * wd + bcol.i0]);
+        const float bot = fmaf(bcol.l, d[a.i1 * wd + bcol.i1] - d[a.i1 * wd + bcol.i0], d[a.i1 * wd + bcol.i0]);
+        e[k] = fabsf(x - fmaf(a.l, bot - top, top));
       }
     }
     float edge = 0.f;
@@ -72,8 +104,7 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
 #pragma unroll
       for (int b = a + 1; b < kMaxScales; b++)
         if (b < sc.n) edge += fabsf(e[a] - e[b]);
-    edge = npair > 0 ? edge / (float)npair : 0.f;
-    stf(zp + i, 2.f * x + wc * edge + ldf(gp + i) * x);
+    stf(zp + i, fmaf(wc * inv_pair, edge, fmaf(ldf(gp + i), x, 2.f * x)));
   }
 }
 
@@ -112,13 +143,22 @@ extern "C" int cenet_fea_combine(const void* y, const void* gate, void* z, int d
     sc.off[k] = off;
     if (!sc.identity[k]) off += sc.hd[k] * sc.wd[k];
   }
-  const size_t smem = (size_t)off * sizeof(float);
+  const int plane_floats = off;
+  int tcount = 0;
+  for (int k = 0; k < nscales; k++)
+    if (!sc.identity[k]) tcount += sc.hd[k] + sc.wd[k] + H + W;
+  const int HW = H * W;
+  const int ppb = HW >= 2048 ? 1 : (HW >= 512 ? 4 : 8);
+  const size_t smem = ((size_t)2 * tcount + (size_t)ppb * plane_floats) * sizeof(float);
   CENET_REQUIRE(smem <= 227 * 1024, "cenet_fea_combine: plane %dx%d needs %zu bytes of shared memory", H, W, smem);
+  CENET_REQUIRE(H <= 32767 && W <= 32767 && HW < 65536, "cenet_fea_combine: plane too large");
   const long long planes = (long long)B * C2;
+  const unsigned wmagic = 0xFFFFFFFFu / (unsigned)W + 1u;        // i / W for i < 2^16 via __umulhi
+  const unsigned grid = (unsigned)((planes + ppb - 1) / ppb);
 #define LAUNCH_FEA(T)                                                                                         \
   do {                                                                                                        \
     if (smem > 48 * 1024) cudaFuncSetAttribute(fea_combine_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    fea_combine_kernel<T><<<(unsigned)planes, 256, smem, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, sc); \
+    fea_combine_kernel<T><<<grid, 256, smem, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, planes, ppb, wmagic, sc, plane_floats); \
   } while (0)
   CENET_DISPATCH(dtype, T, LAUNCH_FEA(T));
 #undef LAUNCH_FEA

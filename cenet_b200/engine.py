@@ -125,6 +125,15 @@ class Engine:
         return self._put(name, m, self.T)
 
     @staticmethod
+    def _flash_padding(hd):
+        """(hd_pad, dv_pad) instantiated in attn_flash.cu for a real head_dim, or None -> materialised attention."""
+        if hd in (8, 16, 32, 64):
+            return hd, 2 * hd
+        if hd <= 24:
+            return 32, 48
+        return None
+
+    @staticmethod
     def _bn_fold(sd, p, eps=1e-5):
         s = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + eps)
         return s, sd[p + ".bias"] - sd[p + ".running_mean"] * s
@@ -172,6 +181,24 @@ class Engine:
             d = p + ".diffattn"
             M(d + ".qkv.w", torch.cat([sd[d + ".q_proj.weight"], sd[d + ".k_proj.weight"], sd[d + ".v_proj.weight"]], 0))
             M(d + ".out.w", sd[d + ".out_proj.weight"])
+            # head dims the flash kernel cannot tile (hd = 20 at the 14x14 level of the Synapse config) are zero-padded
+            # in the packed projections: q/k heads -> hd_pad, value heads -> dv_pad, out_proj gets zero columns
+            E = sd[d + ".q_proj.weight"].shape[0]
+            h = cfg["diffatt_num_heads"][hi]
+            hd = E // h // 2
+            pad = self._flash_padding(hd)
+            if pad is not None and pad != (hd, 2 * hd):
+                hdp, dvp = pad
+                def pad_rows(wm, nheads, width, widthp):
+                    o = torch.zeros(nheads, widthp, wm.shape[1], device=wm.device)
+                    o[:, :width] = wm.view(nheads, width, wm.shape[1])
+                    return o.view(nheads * widthp, wm.shape[1])
+                M(d + ".qkvp.w", torch.cat([pad_rows(sd[d + ".q_proj.weight"], 2 * h, hd, hdp),
+                                            pad_rows(sd[d + ".k_proj.weight"], 2 * h, hd, hdp),
+                                            pad_rows(sd[d + ".v_proj.weight"], h, 2 * hd, dvp)], 0))
+                wo = torch.zeros(E, h, dvp, device=self.dev)
+                wo[:, :, :2 * hd] = sd[d + ".out_proj.weight"].view(E, h, 2 * hd)
+                M(d + ".outp.w", wo.view(E, h * dvp))
             li = lambda_init(depth)
             lam = (torch.exp((sd[d + ".lambda_q1"] * sd[d + ".lambda_k1"]).sum())
                    - torch.exp((sd[d + ".lambda_q2"] * sd[d + ".lambda_k2"]).sum()) + li)
@@ -359,10 +386,20 @@ class Engine:
         w = self.w
         hd = E // heads // 2
         lam, li = w[p + ".lambda"], w[p + ".lambda_init"]
+        pad = self._flash_padding(hd) if self.use_flash else None
+        if pad is not None and pad != (hd, 2 * hd):
+            hdp, dvp = pad                                             # zero-padded heads (see pack())
+            qkv = self.buf(key + ".qkvp", (B * N, 4 * heads * hdp + heads * dvp))
+            ops.linear(tok, w[p + ".qkvp.w"], qkv, impl=self.gemm_impl)
+            o = self.buf(key + ".op", (B * N, heads * dvp))
+            ops.diffattn_flash_padded(qkv, o, B, N, heads, hdp, dvp, hd, lam, 1e-5, 1.0 - li)
+            gate = self.buf(key + ".gate", (B * N, E))
+            ops.linear(o, w[p + ".outp.w"], gate, impl=self.gemm_impl)
+            return gate
         qkv = self.buf(key + ".qkv", (B * N, 3 * E))
         ops.linear(tok, w[p + ".qkv.w"], qkv, impl=self.gemm_impl)
         o = self.buf(key + ".o", (B * N, E))
-        if self.use_flash and hd in (8, 16, 32, 64):
+        if pad is not None:
             ops.diffattn_flash(qkv, o, B, N, E, heads, lam, 1e-5, 1.0 - li)
         else:
             S = self.buf(key + ".S", (B * 2 * heads, N, N))

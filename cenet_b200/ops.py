@@ -191,6 +191,13 @@ def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
     return out
 
 
+def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult):
+    if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("diffattn_flash is a bf16 kernel")
+    L.call("cenet_diffattn_flash_padded", _p(qkv), _p(out), B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult, _stream())
+    return out
+
+
 def sr_attention(q, kv, out, B, N, Nk, Cc, heads, scale):
     L.call("cenet_sr_attention", _p(q), dt(q), _p(kv), dt(kv), _p(out), dt(out), B, N, Nk, Cc, heads, scale, _stream())
     return out

@@ -232,6 +232,20 @@ def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
     return out
 
 
+def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult):
+    _LAUNCHES[0] += 1
+    Eq = 2 * heads * hd_pad
+    t = _flat(qkv).view(B, N, 2 * Eq + heads * dv_pad).float()
+    q = t[..., :Eq].reshape(B, N, 2 * heads, hd_pad).transpose(1, 2) * hd_real ** -0.5
+    k = t[..., Eq:2 * Eq].reshape(B, N, 2 * heads, hd_pad).transpose(1, 2)
+    v = t[..., 2 * Eq:].reshape(B, N, heads, dv_pad).transpose(1, 2)
+    s = torch.softmax(q @ k.transpose(-1, -2), -1).view(B, heads, 2, N, N)
+    o = (s[:, :, 0] - lam * s[:, :, 1]) @ v
+    o = o * torch.rsqrt(o.pow(2).sum(-1, keepdim=True) / (2 * hd_real) + eps) * mult
+    _flat(out).view(B, N, heads * dv_pad).copy_(o.transpose(1, 2).reshape(B, N, heads * dv_pad))
+    return out
+
+
 def sr_attention(q, kv, out, B, N, Nk, Cc, heads, scale):
     _LAUNCHES[0] += 1
     hd = Cc // heads

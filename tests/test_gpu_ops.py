@@ -424,3 +424,28 @@ def test_stem5x5(Cin, dtype):
     tol = 1e-5 if dtype == torch.float32 else 4e-3
     assert rel(o1, F.leaky_relu(F.conv2d(xr, w1, b1, padding=2), 0.01).permute(0, 2, 3, 1)) < tol
     assert rel(r, F.conv2d(xr, w3[:, :, None, None], b3).permute(0, 2, 3, 1)) < tol
+
+
+def test_diffattn_flash_padded_hd20():
+    """Synapse 14x14 level: E=640, 16 heads -> head_dim 20, zero-padded to (32, 48) by the host."""
+    from cenet_b200 import ops
+    B, N, h, hd, hdp, dvp = 2, 196, 16, 20, 32, 48
+    E = 2 * h * hd
+    qkv = torch.randn(B, N, 3 * E, generator=g(7))
+    qkv[..., :2 * E] *= 1.5
+    qkv = qkv.to(torch.bfloat16).float()
+    q = qkv[..., :E].view(B, N, 2 * h, hd)
+    k = qkv[..., E:2 * E].view(B, N, 2 * h, hd)
+    v = qkv[..., 2 * E:].view(B, N, h, 2 * hd)
+    pad = torch.zeros(B, N, 4 * h * hdp + h * dvp)
+    pad[..., :2 * h * hdp].view(B, N, 2 * h, hdp)[..., :hd] = q
+    pad[..., 2 * h * hdp:4 * h * hdp].view(B, N, 2 * h, hdp)[..., :hd] = k
+    pad[..., 4 * h * hdp:].view(B, N, h, dvp)[..., :2 * hd] = v
+    out = torch.empty(B, N, h * dvp, device=DEV, dtype=torch.bfloat16)
+    ops.diffattn_flash_padded(pad.to(DEV, torch.bfloat16), out, B, N, h, hdp, dvp, hd, 0.6, 1e-5, 0.38)
+    ref = _diff_ref(qkv, B, N, E, h, 0.6, 0.38)
+    got = out.float().cpu().view(B, N, h, dvp)
+    assert float(got[..., 2 * hd:].abs().max()) == 0.0            # pad columns stay exactly zero
+    e = rel(got[..., :2 * hd].reshape(B, N, E), ref)
+    record("diffattn_flash_padded_hd20", e)
+    assert e < 1.5e-2, e
