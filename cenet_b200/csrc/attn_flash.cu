@@ -354,29 +354,39 @@ struct NlCfg {
   static constexpr int SMEM = Q_BYTES + 2 * STAGE;
 };
 
+// Generic strided single-softmax attention, head width D: out = softmax(q k^T * scale) v.
+//   non-local block: q|k|v are the three column blocks of one [B,N,3D] tensor, one head;
+//   encoder SR attention: q [B,Nq,heads*64], k|v column blocks of kv [B,Nk,2*heads*64], Nk <= 64 reduced keys.
+struct AttnPtrs {
+  const bf16 *q, *k, *v;
+  bf16* o;
+  long long ldq, ldk, ldv, ldo;          // row pitches (elements)
+  long long bq, bk, bv, bo;              // per-image strides (elements)
+};
+
 template <int D>
-__global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __restrict__ tpg, bf16* __restrict__ out,
-                                                                  int N, float scale_log2) {
+__global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const AttnPtrs a, int Nq, int N, float scale_log2) {
   using Cfg = NlCfg<D>;
   constexpr int STR = Cfg::STR, CH = D / 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, q0 = blockIdx.x * QT;
-  const long long row = 3LL * D;
-  const bf16* base = tpg + (long long)b * N * row;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+  const bf16* qb = a.q + (long long)b * a.bq + head * D;
+  const bf16* kb = a.k + (long long)b * a.bk + head * D;
+  const bf16* vb = a.v + (long long)b * a.bv + head * D;
   const uint32_t sQ = smem_u32(smem), sKV = sQ + Cfg::Q_BYTES;
   for (int i = tid; i < QT * CH; i += NTHREADS) {
     const int ch = i % CH, r = i / CH, n = q0 + r;
-    cp_async16(sQ + r * STR + ch * 16, base + (long long)(n < N ? n : N - 1) * row + ch * 8, n < N);
+    cp_async16(sQ + r * STR + ch * 16, qb + (long long)(n < Nq ? n : Nq - 1) * a.ldq + ch * 8, n < Nq);
   }
   auto load_kv = [&](int tile, int stage) {
     const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + KT * STR;
     const int k0 = tile * KT;
     for (int i = tid; i < KT * CH; i += NTHREADS) {
       const int ch = i % CH, r = i / CH, n = k0 + r;
-      const bf16* src = base + (long long)(n < N ? n : N - 1) * row + ch * 8;
-      cp_async16(sK + r * STR + ch * 16, src + D, n < N);
-      cp_async16(sV + r * STR + ch * 16, src + 2 * D, n < N);
+      const long long rr = n < N ? n : N - 1;
+      cp_async16(sK + r * STR + ch * 16, kb + rr * a.ldk + ch * 8, n < N);
+      cp_async16(sV + r * STR + ch * 16, vb + rr * a.ldv + ch * 8, n < N);
     }
   };
   const int ntiles = (N + KT - 1) / KT;
@@ -432,12 +442,12 @@ __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const bf16* __
   }
   const int g = lane >> 2, t = lane & 3;
   const int n0 = q0 + warp * 16 + g, n1 = n0 + 8;
-  bf16* ob = out + (long long)b * N * D;
+  bf16* ob = a.o + (long long)b * a.bo + head * D;
 #pragma unroll
   for (int j = 0; j < D / 8; j++) {
     const int col = j * 8 + 2 * t;
-    if (n0 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * D + col) = pack_bf16(O[j][0] * inv[0], O[j][1] * inv[0]);
-    if (n1 < N) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * D + col) = pack_bf16(O[j][2] * inv[1], O[j][3] * inv[1]);
+    if (n0 < Nq) *reinterpret_cast<uint32_t*>(ob + (long long)n0 * a.ldo + col) = pack_bf16(O[j][0] * inv[0], O[j][1] * inv[0]);
+    if (n1 < Nq) *reinterpret_cast<uint32_t*>(ob + (long long)n1 * a.ldo + col) = pack_bf16(O[j][2] * inv[1], O[j][3] * inv[1]);
   }
 }
 
@@ -454,14 +464,22 @@ int launch_diff(const bf16* qkv, bf16* out, int B, int N, int heads, int hd_real
   return 0;
 }
 template <int D>
-int launch_nl(const bf16* tpg, bf16* out, int B, int N, float scale, cudaStream_t s) {
+int launch_attn(const AttnPtrs& a, int B, int heads, int Nq, int Nk, float scale, cudaStream_t s, const char* name) {
   using Cfg = NlCfg<D>;
   auto kern = nonlocal_flash_kernel<D>;
   if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  dim3 grid(cdiv(N, QT), B);
-  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(tpg, out, N, scale * 1.4426950408889634f);
-  CENET_LAUNCH_CHECK("nonlocal_flash");
+  dim3 grid(cdiv(Nq, QT), heads, B);
+  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(a, Nq, Nk, scale * 1.4426950408889634f);
+  CENET_LAUNCH_CHECK(name);
   return 0;
+}
+template <int D>
+int launch_nl(const bf16* tpg, bf16* out, int B, int N, float scale, cudaStream_t s) {
+  AttnPtrs a;
+  a.q = tpg; a.k = tpg + D; a.v = tpg + 2 * D; a.o = out;
+  a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+  a.bq = a.bk = a.bv = (long long)N * 3 * D; a.bo = (long long)N * D;
+  return launch_attn<D>(a, B, 1, N, N, scale, s, "nonlocal_flash");
 }
 }  // namespace
 
@@ -493,6 +511,16 @@ extern "C" int cenet_diffattn_flash_padded(const void* qkv, void* out, int B, in
                 "cenet_diffattn_flash_padded: bad head geometry (hd %d pad %d, dv pad %d)", hd_real, hd_pad, dv_pad);
   CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash_padded: grid too large");
   return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd_pad, dv_pad, hd_real, lambda, eps, mult, to_stream(s));
+}
+
+// bf16 fast path of cenet_sr_attention (attn_sr.cu): q [B,N,C], kv [B,Nk,2C], head_dim 64
+int cenet_sr_attention_mma(const void* q, const void* kv, void* out, int B, int N, int Nk, int C, int heads, float scale,
+                           cudaStream_t s) {
+  AttnPtrs a;
+  a.q = (const bf16*)q; a.k = (const bf16*)kv; a.v = (const bf16*)kv + C; a.o = (bf16*)out;
+  a.ldq = C; a.ldk = a.ldv = 2 * C; a.ldo = C;
+  a.bq = (long long)N * C; a.bk = a.bv = (long long)Nk * 2 * C; a.bo = (long long)N * C;
+  return launch_attn<64>(a, B, heads, N, Nk, scale, s, "sr_attention_mma");
 }
 
 extern "C" int cenet_nonlocal_flash(const void* tpg, void* out, int B, int N, int C, float scale, cenet_stream_t s) {

@@ -1,7 +1,12 @@
 // Encoder spatial-reduction attention (pvtv2.py:88-105): every query attends to <= 64 reduced keys, head_dim 64.
+// bf16 tensors take the mma.sync kernel of attn_flash.cu (one 64-key tile, K/V of an (image, head) in smem); the CUDA-core
+// kernel below serves the fp32 validation precision.
 // AI ~ 49 FLOP/B -> HBM/L2-bound: K and V of one (image, head) live in shared memory (25 KB fp32), one thread owns
 // one query row and streams the keys with an online softmax, so q is read once and o written once.
 #include "common.cuh"
+
+int cenet_sr_attention_mma(const void* q, const void* kv, void* out, int B, int N, int Nk, int C, int heads, float scale,
+                           cudaStream_t s);
 
 namespace {
 constexpr int HD = 64, MAXK = 64, QT = 128;
@@ -71,6 +76,9 @@ extern "C" int cenet_sr_attention(const void* q, int q_dtype, const void* kv, in
   CENET_REQUIRE(C == heads * HD, "cenet_sr_attention: head_dim must be 64 (C=%d heads=%d)", C, heads);
   CENET_REQUIRE(Nk >= 1 && Nk <= MAXK, "cenet_sr_attention: 1..%d reduced keys supported, got %d", MAXK, Nk);
   CENET_REQUIRE(q_dtype == kv_dtype && q_dtype == o_dtype, "cenet_sr_attention: q/kv/out must share one dtype");
+  CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_sr_attention: grid too large");
+  if (q_dtype == CENET_BF16 && (((uintptr_t)q | (uintptr_t)kv | (uintptr_t)out) & 15) == 0)
+    return cenet_sr_attention_mma(q, kv, out, B, N, Nk, C, heads, scale, to_stream(s));   // tensor-core path (attn_flash.cu)
   dim3 grid(cdiv(N, QT), heads, B);
   CENET_DISPATCH(q_dtype, T, (sr_attention_kernel<T, T, T><<<grid, QT, 0, to_stream(s)>>>((const T*)q, (const T*)kv, (T*)out, N, Nk, C, scale)));
   CENET_LAUNCH_CHECK("sr_attention");

@@ -19,50 +19,104 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float e = 1.0f - p * t * __expf(-z * z);      // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
-__device__ __forceinline__ float dw_act(float v, int act, float slope) {
-  return act == CENET_ACT_GELU ? gelu_fast(v) : apply_act(v, act, slope);
+
+// bf16 storage: tanh-form GELU on the MUFU pipe (1 MUFU.TANH + 5 FMA; |diff to the erf form| < 5e-4, below the bf16
+// rounding of the value it produces).  fp32 storage keeps the erf form (A&S 7.1.26, 1.5e-7).
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608f * fmaf(0.044715f * x, x * x, x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+template <bool FAST>
+__device__ __forceinline__ float dw_act2(float v, int act, float slope) {
+  if (act == CENET_ACT_GELU) return FAST ? gelu_tanh(v) : gelu_fast(v);
+  return apply_act(v, act, slope);
 }
 
-template <typename TI, typename TO, int V>
+// thread = V channels x PW consecutive output pixels of one row: the 3 x (PW+2) input vectors are loaded and unpacked
+// once and feed all PW outputs; filter taps are loaded once per thread.
+template <typename TI, typename TO, int V, int PW>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const TI* __restrict__ x, int ldx, TO* __restrict__ y, int ldy,
                                                         const float* __restrict__ w9c, const float* __restrict__ bias,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         int H, int W, int C, int dil, int up2, int act, float slope) {
+  constexpr bool FAST = sizeof(TO) == 2;
   const int cvi = blockIdx.x * blockDim.x + threadIdx.x;     // channel-vector index
-  const int w = blockIdx.y * blockDim.y + threadIdx.y;
-  if (cvi * V >= C || w >= W) return;
+  const int w0 = (blockIdx.y * blockDim.y + threadIdx.y) * PW;
+  if (cvi * V >= C || w0 >= W) return;
   const int c = cvi * V;
   const int b = blockIdx.z / H, h = blockIdx.z - b * H;
   const int Hi = up2 ? H >> 1 : H, Wi = up2 ? W >> 1 : W;
   const TI* xb = x + (size_t)b * Hi * Wi * ldx + c;
-  float acc[V];
-#pragma unroll
-  for (int v = 0; v < V; v++) acc[v] = bias ? bias[c + v] : 0.f;
-#pragma unroll
-  for (int dh = -1; dh <= 1; dh++) {
-    const int hh = h + dh * dil;
-    if (hh < 0 || hh >= H) continue;
-    const int hs = up2 ? hh >> 1 : hh;                       // nearest x2: src = floor(dst/2)
-#pragma unroll
-    for (int dw = -1; dw <= 1; dw++) {
-      const int ww = w + dw * dil;
-      if (ww < 0 || ww >= W) continue;
-      const int ws = up2 ? ww >> 1 : ww;
-      float xv[V], wv[V];
-      ldv<V>(xb + (size_t)(hs * Wi + ws) * ldx, xv);
-      ldv<V>(w9c + ((dh + 1) * 3 + (dw + 1)) * C + c, wv);
-#pragma unroll
-      for (int v = 0; v < V; v++) acc[v] = fmaf(xv[v], wv[v], acc[v]);
-    }
-  }
-  float o[V];
+  float acc[PW][V];
 #pragma unroll
   for (int v = 0; v < V; v++) {
-    float t = acc[v];
-    if (scale) t = fmaf(t, scale[c + v], shift[c + v]);
-    o[v] = dw_act(t, act, slope);
+    const float bv = bias ? bias[c + v] : 0.f;
+#pragma unroll
+    for (int p = 0; p < PW; p++) acc[p][v] = bv;
   }
-  stv<V>(y + ((size_t)(b * H + h) * W + w) * ldy + c, o);
+  if (dil == 1) {
+    // dense 3x3: sliding window over PW+2 input columns
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int hh = h + dh;
+      if (hh < 0 || hh >= H) continue;
+      const int hs = up2 ? hh >> 1 : hh;
+      float wv[3][V];
+#pragma unroll
+      for (int t = 0; t < 3; t++) ldv<V>(w9c + ((dh + 1) * 3 + t) * C + c, wv[t]);
+#pragma unroll
+      for (int q = 0; q < PW + 2; q++) {
+        const int ww = w0 + q - 1;
+        if (ww < 0 || ww >= W) continue;
+        const int ws = up2 ? ww >> 1 : ww;
+        float xv[V];
+        ldv<V>(xb + (size_t)(hs * Wi + ws) * ldx, xv);
+#pragma unroll
+        for (int p = 0; p < PW; p++) {
+          const int t = q - p;                 // tap column index (0..2) of input column q for output pixel p
+          if (t < 0 || t > 2) continue;
+#pragma unroll
+          for (int v = 0; v < V; v++) acc[p][v] = fmaf(xv[v], wv[t][v], acc[p][v]);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int dh = -1; dh <= 1; dh++) {
+      const int hh = h + dh * dil;
+      if (hh < 0 || hh >= H) continue;
+      const int hs = up2 ? hh >> 1 : hh;
+#pragma unroll
+      for (int dw = -1; dw <= 1; dw++) {
+        float wv[V];
+        ldv<V>(w9c + ((dh + 1) * 3 + (dw + 1)) * C + c, wv);
+#pragma unroll
+        for (int p = 0; p < PW; p++) {
+          const int ww = w0 + p + dw * dil;
+          if (ww < 0 || ww >= W || w0 + p >= W) continue;
+          const int ws = up2 ? ww >> 1 : ww;
+          float xv[V];
+          ldv<V>(xb + (size_t)(hs * Wi + ws) * ldx, xv);
+#pragma unroll
+          for (int v = 0; v < V; v++) acc[p][v] = fmaf(xv[v], wv[v], acc[p][v]);
+        }
+      }
+    }
+  }
+  float sc[V], sh[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) { sc[v] = scale ? scale[c + v] : 1.f; sh[v] = scale ? shift[c + v] : 0.f; }
+#pragma unroll
+  for (int p = 0; p < PW; p++) {
+    if (w0 + p >= W) continue;
+    float o[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) o[v] = dw_act2<FAST>(fmaf(acc[p][v], sc[v], sh[v]), act, slope);
+    stv<V>(y + ((size_t)(b * H + h) * W + w0 + p) * ldy + c, o);
+  }
 }
 }  // namespace
 
@@ -79,12 +133,13 @@ extern "C" int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* 
                     ptr_align_elems(w9c, 4) * 2});
   if (V > 4 && (x_dtype == CENET_F32 || y_dtype == CENET_F32)) V = 4;   // keep fp32 accesses at 16 bytes
   const int cv = C / V;
+  constexpr int PW = 2;
   int tx = 1;
   while (tx < cv && tx < 64) tx <<= 1;                      // channel vectors per block (power of two <= 64)
   const int ty = 256 / tx;
-  dim3 block(tx, ty), grid(cdiv(cv, tx), cdiv(W, ty), B * H);
+  dim3 block(tx, ty), grid(cdiv(cv, tx), cdiv(cdiv(W, PW), ty), B * H);
 #define LAUNCH(VV)                                                                                              \
-  CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(y_dtype, TO, (dwconv3x3_kernel<TI, TO, VV><<<grid, block, 0, to_stream(s)>>>( \
+  CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(y_dtype, TO, (dwconv3x3_kernel<TI, TO, VV, PW><<<grid, block, 0, to_stream(s)>>>( \
       (const TI*)x, (int)ldx, (TO*)y, (int)ldy, w9c, bias, scale, shift, H, W, C, dil, up2, act, slope))))
   if (V == 8) LAUNCH(8); else if (V == 4) LAUNCH(4); else if (V == 2) LAUNCH(2); else LAUNCH(1);
 #undef LAUNCH

@@ -4,46 +4,55 @@
 
 namespace {
 
-// ---- LayerNorm: warp per row, C % 64 == 0, C <= 512 (bf16x2 / float2 per lane per step) ----------------------
-template <typename TI, typename TO>
+// ---- LayerNorm: LPR lanes per row (8 for C=64, 16 for C=128, 32 otherwise), 16-byte vectors, 32/LPR rows per warp -------
+// Each lane keeps its NV 8-element vectors in registers: one HBM read, one write per element.
+template <typename TI, typename TO, int LPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                         const float* __restrict__ g, const float* __restrict__ b,
                                                         long long rows, int C, float eps) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const TI* xr = x + row * C;
-  float v[16];
-  int nit = C >> 6;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool live = row < rows;
+  const TI* xr = x + (live ? row : 0) * C;
+  const int nvec = C >> 3;
+  float v[NV][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if (i < nit) {
-      float t[2];
-      ldv<2>(xr + i * 64 + lane * 2, t);
-      v[2 * i] = t[0]; v[2 * i + 1] = t[1];
-      s += t[0] + t[1];
+  for (int i = 0; i < NV; i++) {
+    const int vi = sub + i * LPR;
+    if (vi < nvec) {
+      ldv<8>(xr + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) s += v[i][j];
     }
   }
-  const float mean = warp_sum(s) / (float)C;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if (i < nit) {
-      float d0 = v[2 * i] - mean, d1 = v[2 * i + 1] - mean;
-      q += d0 * d0 + d1 * d1;
+  for (int i = 0; i < NV; i++) {
+    if (sub + i * LPR < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const float d = v[i][j] - mean; q = fmaf(d, d, q); }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  if (!live) return;
   TO* yr = y + row * C;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if (i < nit) {
-      int c = i * 64 + lane * 2;
-      float o[2];
-      o[0] = (v[2 * i] - mean) * rstd * g[c] + b[c];
-      o[1] = (v[2 * i + 1] - mean) * rstd * g[c + 1] + b[c + 1];
-      stv<2>(yr + c, o);
+  for (int i = 0; i < NV; i++) {
+    const int vi = sub + i * LPR;
+    if (vi < nvec) {
+      float gv[8], bv[8], o[8];
+      ldv<8>(g + vi * 8, gv);
+      ldv<8>(b + vi * 8, bv);
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = fmaf((v[i][j] - mean) * rstd, gv[j], bv[j]);
+      stv<8>(yr + vi * 8, o);
     }
   }
 }
@@ -122,10 +131,20 @@ extern "C" int cenet_layernorm(const void* x, int x_dtype, void* y, int y_dtype,
   if (rows == 0) return 0;
   CENET_REQUIRE(x && y && gamma && beta, "cenet_layernorm: null pointer");
   CENET_REQUIRE(C % 64 == 0 && C <= 512, "cenet_layernorm: C=%d must be a multiple of 64 and <= 512", C);
+  CENET_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+                "cenet_layernorm: pointers must be 16-byte aligned");
   const int wpb = 8;
-  dim3 grid(cdiv(rows, wpb));
-  CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(y_dtype, TO, (layernorm_kernel<TI, TO><<<grid, wpb * 32, 0, to_stream(s)>>>(
-      (const TI*)x, (TO*)y, gamma, beta, rows, C, eps))));
+#define LN_LAUNCH(LPR, NV)                                                                                              \
+  do {                                                                                                                    \
+    dim3 grid(cdiv(rows, (long long)wpb * (32 / LPR)));                                                                   \
+    CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(y_dtype, TO, (layernorm_kernel<TI, TO, LPR, NV><<<grid, wpb * 32, 0, to_stream(s)>>>( \
+        (const TI*)x, (TO*)y, gamma, beta, rows, C, eps))));                                                              \
+  } while (0)
+  if (C == 64) LN_LAUNCH(8, 1);
+  else if (C == 128) LN_LAUNCH(16, 1);
+  else if (C <= 256) LN_LAUNCH(32, 1);
+  else LN_LAUNCH(32, 2);
+#undef LN_LAUNCH
   CENET_LAUNCH_CHECK("layernorm");
   return 0;
 }
