@@ -178,11 +178,10 @@ def run_product(args):
     labels_host = torch.empty((BATCH, SIZE, SIZE), dtype=torch.int64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)        # > 126 MB L2
 
+    from cenet_b200 import replicas
+
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        replicas.barrier(dev)
 
     # ---- warm-up (also captures the CUDA graph) ----
     for _ in range(max(args.warmup, 3)):
@@ -214,15 +213,12 @@ def run_product(args):
     barrier()
     t_e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
 
-    t = torch.tensor([t_dev_ms, t_e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev_ms, t_e2e_ms = t.tolist()
+    t_dev_ms, t_e2e_ms = replicas.max_over_ranks([t_dev_ms, t_e2e_ms], device=dev)
 
     if rank == 0:
         peaks = _peaks()
-        value = world * BATCH * args.steps / (t_dev_ms / 1e3)
-        e2e = world * BATCH * args.steps / (t_e2e_ms / 1e3)
+        value = replicas.job_throughput(BATCH, args.steps, t_dev_ms)
+        e2e = replicas.job_throughput(BATCH, args.steps, t_e2e_ms)
         # ---- roofline of the dominant kernel, timed live (eager launches bracketed by CUDA events) ----
         prof = eng.profile_ops(x_dev, labels=True, steps=2)
         total_ms = sum(v[0] for v in prof.values())
