@@ -105,6 +105,7 @@ struct TcParams {
   int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
   EpiParams epi;
   int epi_vec;       // every epilogue operand is 16-byte addressable -> smem-transposed, vectorised epilogue
+  int epi_fast;      // 1: C = bf16(acc + bias); 2: C = bf16(acc + bias + res1)  (most Linear layers) -- compact code path
 };
 
 constexpr int MAX_EPI_WARPS = 8;
@@ -262,6 +263,16 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       const uint32_t as = i & 1, use = i >> 1;
       long long m_own;
       const bool own_ok = row_index(quarter * 32 + lane, m_own);
+      // fast path bookkeeping: the 4 rows this lane serves in phase B (4 lanes per row, 8 rows per pass)
+      bf16* crow[4];
+      const bf16* rrow[4];
+#pragma unroll
+      for (int itr = 0; itr < 4; itr++) {
+        long long m;
+        const bool ok = row_index(quarter * 32 + itr * 8 + (lane >> 2), m);
+        crow[itr] = ok ? reinterpret_cast<bf16*>(e.C) + m * e.ldc : nullptr;
+        rrow[itr] = reinterpret_cast<const bf16*>(e.res1) + (ok ? m * e.ldr1 : 0);
+      }
       mbar_wait(tfull_bar + 8 * as, use & 1);
       tc_fence_after();
       for (int c0 = half * 32; c0 < p.bn; c0 += cstep) {
@@ -276,7 +287,35 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
                           __uint_as_float(acc[4 * q + 3]));
         __syncwarp();
-        if (p.epi_vec) {
+        if (p.epi_fast) {
+          // C = bf16(acc + bias [+ res1]); N % 8 == 0, so an 8-column group is entirely inside or outside the tile
+          const int cg = (lane & 3) * 8;
+          const int n = nbase + cg;
+          if (n < nlim) {
+            float bcol[8];
+            if (e.bias) ldv<8>(e.bias + n, bcol);
+            else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) bcol[j] = 0.f;
+            }
+#pragma unroll
+            for (int itr = 0; itr < 4; itr++) {
+              if (crow[itr] == nullptr) continue;
+              const int rr = itr * 8 + (lane >> 2);
+              const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+              const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+              float v[8] = {lo.x + bcol[0], lo.y + bcol[1], lo.z + bcol[2], lo.w + bcol[3],
+                            hi.x + bcol[4], hi.y + bcol[5], hi.z + bcol[6], hi.w + bcol[7]};
+              if (p.epi_fast == 2) {
+                float t[8];
+                ldv<8>(rrow[itr] + n, t);
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] += t[j];
+              }
+              stv<8>(crow[itr] + n, v);
+            }
+          }
+        } else if (p.epi_vec) {
           const int cg = (lane & 3) * 8;
           const int n = nbase + cg;
           float bcol[8];
@@ -479,6 +518,11 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
                                                       (a->c_dtype == CENET_F32 && a->ldc % 4 == 0));
   p.epi_vec = c_ok && vec_ok(a->res1, a->res1_dtype, a->ldr1) && vec_ok(a->res2, a->res2_dtype, a->ldr2) &&
               vec_ok(a->mul, a->mul_dtype, a->ldmul);
+  p.epi_fast = 0;
+  if (p.epi_vec && a->c_dtype == CENET_BF16 && a->alpha == 1.0f && !a->row_scale && !a->bias_per_row && a->act == CENET_ACT_NONE &&
+      !a->mul && !a->res2 && a->N % 8 == 0 && (!a->bias || (((uintptr_t)a->bias & 15) == 0)) &&
+      (!a->res1 || (!a->res1_cscale && a->res1_scale == 1.0f)))
+    p.epi_fast = a->res1 ? 2 : 1;
   const size_t smem = (size_t)wres + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 32 + slab_bytes + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
