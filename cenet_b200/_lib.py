@@ -52,8 +52,8 @@ _SIGS = {
     "cenet_fea_combine": [vp, vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(f32), i32, vp],
     "cenet_diff_combine": [vp, i32, ll, ll, f32, vp],
     "cenet_rmsnorm_seg": [vp, i32, vp, i32, ll, i32, i32, f32, f32, vp],
-    "cenet_diffattn_flash": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp],
-    "cenet_diffattn_flash_padded": [vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp],
+    "cenet_diffattn_flash": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp],
+    "cenet_diffattn_flash_padded": [vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
     "cenet_sr_attention": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp],
     "cenet_nonlocal_flash": [vp, vp, i32, i32, i32, f32, vp],
     "cenet_ccu_gate": [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],

@@ -136,6 +136,36 @@ __device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P
 //   HD: real head_dim (8,16,32,64); HDP = max(HD,16); DV = 2*HD
 // smem rows are padded by 16 bytes so that ldmatrix's 8 row addresses fall in distinct 16-byte bank groups.
 // =====================================================================================================================
+// Pre-pass of the bounded-softmax mode: kmax[b, j] = max_n |k_{b,n,j}|_2 for every softmax map j (keys of width HD).
+// With it every score of query row r obeys s <= |q_r| kmax (Cauchy-Schwarz), which serves as a FIXED softmax shift:
+// no running max, no rescaling of the accumulators, and the exponentials no longer wait for a cross-lane reduction.
+template <int HD>
+__global__ void __launch_bounds__(256) kmax_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int N,
+                                                   long long row, int koff) {
+  __shared__ float red[8];
+  const int j = blockIdx.x, b = blockIdx.y;
+  const bf16* kb = qkv + (long long)b * N * row + koff + j * HD;
+  float mx = 0.f;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      float v[8];
+      ldv<8>(kb + (long long)n * row + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) ss = fmaf(v[i], v[i], ss);
+    }
+    mx = fmaxf(mx, ss);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; i++) mx = fmaxf(mx, red[i]);
+    kmax[(long long)b * gridDim.x + j] = sqrtf(mx);
+  }
+}
+
 template <int HD, int DVT>
 struct DiffCfg {
   static constexpr int HDP = HD < 16 ? 16 : HD;
@@ -155,7 +185,8 @@ struct DiffCfg {
 template <int HD, int DVT, int POLY, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                   int N, int heads, float dv_real, float scale_log2,
-                                                                  float lambda, float eps, float mult) {
+                                                                  float lambda, float eps, float mult,
+                                                                  const float* __restrict__ kmax) {
   using Cfg = DiffCfg<HD, DVT>;
   const int E = 2 * heads * HD;            // width of the q block (= k block)
   const int EO = heads * DVT;              // output row width
@@ -227,13 +258,42 @@ __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf
     for (int j = 0; j < DV / 8; j++) O[mp][j][0] = O[mp][j][1] = O[mp][j][2] = O[mp][j][3] = 0.f;
   }
   const uint32_t ones_b = (lane < 4) ? 0x3F803F80u : 0u;     // B fragment of the ones column (n = 0 <=> lane/4 == 0)
+  // ---- bounded-softmax mode: fixed shift |q_r| * max_n|k_n| (log2 units) instead of a running maximum.  The shift
+  // may exceed the true row maximum by up to 2x its own size, so it is only used while 2*shift stays far inside the
+  // fp32 / bf16 exponent range (< 60 => p >= 2^-120); otherwise this warp keeps the online-max path. ----
+  bool bounded = false;
+  if (kmax != nullptr) {
+    float worst = 0.f;
+#pragma unroll
+    for (int mp = 0; mp < 2; mp++) {
+      float q0s = 0.f, q1s = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < HDP / 16; ks++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qf[mp][ks][r]));
+          const float ssq = f.x * f.x + f.y * f.y;
+          if (r & 1) q1s += ssq; else q0s += ssq;          // a0,a2 -> row g ; a1,a3 -> row g+8
+        }
+      }
+      q0s += __shfl_xor_sync(0xffffffffu, q0s, 1); q0s += __shfl_xor_sync(0xffffffffu, q0s, 2);
+      q1s += __shfl_xor_sync(0xffffffffu, q1s, 1); q1s += __shfl_xor_sync(0xffffffffu, q1s, 2);
+      const float km = kmax[(long long)b * (2 * heads) + 2 * head + mp] * scale_log2 * 1.0001f;
+      m[mp][0] = sqrtf(q0s) * km + 1e-3f;
+      m[mp][1] = sqrtf(q1s) * km + 1e-3f;
+      worst = fmaxf(worst, fmaxf(m[mp][0], m[mp][1]));
+    }
+    bounded = __all_sync(0xffffffffu, worst < 60.f);
+    if (!bounded) { m[0][0] = m[0][1] = m[1][0] = m[1][1] = -INFINITY; }
+  }
   // lane-dependent ldmatrix offsets, hoisted out of the tile loop
   const uint32_t k_lane = ((lane & 7) + ((lane >> 4) << 3)) * KSTR + (((lane >> 3) & 1) << 4);
   const uint32_t v_lane = ((lane & 7) + (((lane >> 3) & 1) << 3)) * VSTR + ((lane >> 4) << 4);
   const int tq = lane & 3;
 
-  auto process_tile = [&](auto masked_tag, int tile) {
+  auto process_tile = [&](auto masked_tag, auto bounded_tag, int tile) {
     constexpr bool MASKED = decltype(masked_tag)::value;
+    constexpr bool BOUNDED = decltype(bounded_tag)::value;
     const int stage = tile & 1;
     const uint32_t sK = sKV + stage * Cfg::STAGE, sV = sK + Cfg::K_BYTES;
 #pragma unroll
@@ -259,22 +319,25 @@ __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf
           if (key + 1 >= N) { S[j][1] = -INFINITY; S[j][3] = -INFINITY; }
         }
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      float mn0 = m[mp][0], mn1 = m[mp][1];
+      if (!BOUNDED) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < KT / 8; j++) {
-        mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1]));
-        mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3]));
+        for (int j = 0; j < KT / 8; j++) {
+          mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1]));
+          mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        mn0 = fmaxf(m[mp][0], mx0 * scale_log2); mn1 = fmaxf(m[mp][1], mx1 * scale_log2);
+        const float c0 = fast_exp2(m[mp][0] - mn0), c1 = fast_exp2(m[mp][1] - mn1);
+        m[mp][0] = mn0; m[mp][1] = mn1;
+        L[mp][0] *= c0; L[mp][2] *= c1;
+#pragma unroll
+        for (int j = 0; j < DV / 8; j++) { O[mp][j][0] *= c0; O[mp][j][1] *= c0; O[mp][j][2] *= c1; O[mp][j][3] *= c1; }
       }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m[mp][0], mx0 * scale_log2), mn1 = fmaxf(m[mp][1], mx1 * scale_log2);
-      const float c0 = fast_exp2(m[mp][0] - mn0), c1 = fast_exp2(m[mp][1] - mn1);
-      m[mp][0] = mn0; m[mp][1] = mn1;
-      L[mp][0] *= c0; L[mp][2] *= c1;
-#pragma unroll
-      for (int j = 0; j < DV / 8; j++) { O[mp][j][0] *= c0; O[mp][j][1] *= c0; O[mp][j][2] *= c1; O[mp][j][3] *= c1; }
       uint32_t P[KT / 16][4];
 #pragma unroll
       for (int j = 0; j < KT / 8; j++) {
@@ -303,8 +366,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf
 
   const bool ragged = (N % KT) != 0;
   for (int tile = 0; tile < ntiles; tile++) {
-    if (ragged && tile == ntiles - 1) process_tile(std::true_type{}, tile);
-    else process_tile(std::false_type{}, tile);
+    const bool last_ragged = ragged && tile == ntiles - 1;
+    if (bounded) {
+      if (last_ragged) process_tile(std::true_type{}, std::true_type{}, tile);
+      else process_tile(std::false_type{}, std::true_type{}, tile);
+    } else {
+      if (last_ragged) process_tile(std::true_type{}, std::false_type{}, tile);
+      else process_tile(std::false_type{}, std::false_type{}, tile);
+    }
     __syncthreads();                       // everyone is done with this stage
     if (tile + 2 < ntiles) load_kv(tile + 2, tile & 1);
     cp_async_commit();
@@ -453,13 +522,18 @@ __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const AttnPtrs
 
 template <int HD, int DVT, int POLY, int MINB>
 int launch_diff(const bf16* qkv, bf16* out, int B, int N, int heads, int hd_real, float lambda, float eps, float mult,
-                cudaStream_t s) {
+                float* kmax_ws, cudaStream_t s) {
   using Cfg = DiffCfg<HD, DVT>;
+  if (kmax_ws) {
+    const long long row = 4LL * heads * HD + (long long)heads * DVT;
+    kmax_kernel<HD><<<dim3(2 * heads, B), 256, 0, s>>>(qkv, kmax_ws, N, row, 2 * heads * HD);
+    CENET_LAUNCH_CHECK("diffattn_kmax");
+  }
   auto kern = diffattn_flash_kernel<HD, DVT, POLY, MINB>;
   if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   dim3 grid(cdiv(N, QT), heads, B);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)hd_real);
-  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(qkv, out, N, heads, (float)(2 * hd_real), scale_log2, lambda, eps, mult);
+  kern<<<grid, NTHREADS, Cfg::SMEM, s>>>(qkv, out, N, heads, (float)(2 * hd_real), scale_log2, lambda, eps, mult, kmax_ws);
   CENET_LAUNCH_CHECK("diffattn_flash");
   return 0;
 }
@@ -484,33 +558,39 @@ int launch_nl(const bf16* tpg, bf16* out, int B, int N, float scale, cudaStream_
 }  // namespace
 
 static int diffattn_dispatch(const bf16* q, bf16* o, int B, int N, int heads, int hdp, int dvp, int hd_real, float lambda,
-                             float eps, float mult, cudaStream_t st) {
-  if (hdp == 8 && dvp == 16) return launch_diff<8, 16, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
-  if (hdp == 16 && dvp == 32) return launch_diff<16, 32, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
-  if (hdp == 32 && dvp == 48) return launch_diff<32, 48, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
-  if (hdp == 32 && dvp == 64) return launch_diff<32, 64, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
-  if (hdp == 64 && dvp == 128) return launch_diff<64, 128, 0, 1>(q, o, B, N, heads, hd_real, lambda, eps, mult, st);
+                             float eps, float mult, float* ws, cudaStream_t st) {
+  static const int poly = getenv("CENET_DA_POLY") ? atoi(getenv("CENET_DA_POLY")) : 0;
+  if (hdp == 8 && dvp == 16) {
+    if (poly == 4) return launch_diff<8, 16, 4, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+    if (poly == 2) return launch_diff<8, 16, 2, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+    return launch_diff<8, 16, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+  }
+  if (hdp == 16 && dvp == 32) return launch_diff<16, 32, 0, 4>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+  if (hdp == 32 && dvp == 48) return launch_diff<32, 48, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+  if (hdp == 32 && dvp == 64) return launch_diff<32, 64, 0, 2>(q, o, B, N, heads, hd_real, lambda, eps, mult, ws, st);
+  if (hdp == 64 && dvp == 128) return launch_diff<64, 128, 0, 1>(q, o, B, N, heads, hd_real, lambda, eps, mult, nullptr, st);
   CENET_FAIL("cenet_diffattn_flash: no kernel for padded head_dim %d / value width %d; use the materialised path", hdp, dvp);
 }
 
 extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
-                                    float mult, cenet_stream_t s) {
+                                    float mult, float* kmax_ws, cenet_stream_t s) {
   if (B == 0 || N == 0) return 0;
   CENET_REQUIRE(qkv && out, "cenet_diffattn_flash: null pointer");
   CENET_REQUIRE(heads >= 1 && E % (2 * heads) == 0, "cenet_diffattn_flash: E=%d not divisible by 2*heads=%d", E, 2 * heads);
   CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash: grid too large");
   const int hd = E / (2 * heads);
-  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, to_stream(s));
+  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, kmax_ws, to_stream(s));
 }
 
 extern "C" int cenet_diffattn_flash_padded(const void* qkv, void* out, int B, int N, int heads, int hd_pad, int dv_pad,
-                                           int hd_real, float lambda, float eps, float mult, cenet_stream_t s) {
+                                           int hd_real, float lambda, float eps, float mult, float* kmax_ws,
+                                           cenet_stream_t s) {
   if (B == 0 || N == 0) return 0;
   CENET_REQUIRE(qkv && out, "cenet_diffattn_flash_padded: null pointer");
   CENET_REQUIRE(heads >= 1 && hd_real >= 1 && hd_real <= hd_pad && 2 * hd_real <= dv_pad,
                 "cenet_diffattn_flash_padded: bad head geometry (hd %d pad %d, dv pad %d)", hd_real, hd_pad, dv_pad);
   CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash_padded: grid too large");
-  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd_pad, dv_pad, hd_real, lambda, eps, mult, to_stream(s));
+  return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd_pad, dv_pad, hd_real, lambda, eps, mult, kmax_ws, to_stream(s));
 }
 
 // bf16 fast path of cenet_sr_attention (attn_sr.cu): q [B,N,C], kv [B,Nk,2C], head_dim 64

@@ -392,7 +392,8 @@ class Engine:
             qkv = self.buf(key + ".qkvp", (B * N, 4 * heads * hdp + heads * dvp))
             ops.linear(tok, w[p + ".qkvp.w"], qkv, impl=self.gemm_impl)
             o = self.buf(key + ".op", (B * N, heads * dvp))
-            ops.diffattn_flash_padded(qkv, o, B, N, heads, hdp, dvp, hd, lam, 1e-5, 1.0 - li)
+            ops.diffattn_flash_padded(qkv, o, B, N, heads, hdp, dvp, hd, lam, 1e-5, 1.0 - li,
+                                      self.buf(key + ".kmax", (B * 2 * heads,), torch.float32))
             gate = self.buf(key + ".gate", (B * N, E))
             ops.linear(o, w[p + ".outp.w"], gate, impl=self.gemm_impl)
             return gate
@@ -400,7 +401,8 @@ class Engine:
         ops.linear(tok, w[p + ".qkv.w"], qkv, impl=self.gemm_impl)
         o = self.buf(key + ".o", (B * N, E))
         if pad is not None:
-            ops.diffattn_flash(qkv, o, B, N, E, heads, lam, 1e-5, 1.0 - li)
+            ops.diffattn_flash(qkv, o, B, N, E, heads, lam, 1e-5, 1.0 - li,
+                               self.buf(key + ".kmax", (B * 2 * heads,), torch.float32))
         else:
             S = self.buf(key + ".S", (B * 2 * heads, N, N))
             ops.gemm(qkv, qkv, S, M=N, N=N, K=hd, lda=3 * E, ldw=3 * E, ldc=N, alpha=hd ** -0.5, batch=B * 2 * heads,

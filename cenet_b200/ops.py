@@ -184,17 +184,18 @@ def diff_combine_(P, npairs, map_elems, lam):
     return P
 
 
-def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
+def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult, kmax_ws=None):
     if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
         raise TypeError("diffattn_flash is a bf16 kernel")
-    L.call("cenet_diffattn_flash", _p(qkv), _p(out), B, N, E, heads, lam, eps, mult, _stream())
+    L.call("cenet_diffattn_flash", _p(qkv), _p(out), B, N, E, heads, lam, eps, mult, _f32(kmax_ws, "kmax_ws"), _stream())
     return out
 
 
-def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult):
+def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult, kmax_ws=None):
     if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
         raise TypeError("diffattn_flash is a bf16 kernel")
-    L.call("cenet_diffattn_flash_padded", _p(qkv), _p(out), B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult, _stream())
+    L.call("cenet_diffattn_flash_padded", _p(qkv), _p(out), B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult,
+           _f32(kmax_ws, "kmax_ws"), _stream())
     return out
 
 

@@ -123,14 +123,17 @@ int cenet_rmsnorm_seg(const void* x, int x_dtype, void* y, int y_dtype, long lon
  * qkv: [B, N, 3E] bf16 rows (q | k | v), heads h, hd = E/(2h).  out: [B, N, E] bf16 =
  * RMSNorm_{2hd}( softmax(q_{2i}k_{2i}^T/sqrt(hd)) v_i - lambda*softmax(q_{2i+1}k_{2i+1}^T/sqrt(hd)) v_i ) * mult */
 int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
-                         float mult, cenet_stream_t s);
+                         float mult, float* kmax_ws, cenet_stream_t s);
+/* kmax_ws: NULL, or B*2*heads floats of workspace.  When given, a pre-pass stores max_n|k_n| per softmax map and the
+ * kernel uses the Cauchy-Schwarz bound |q_r|*max|k| as a fixed softmax shift (no running max / rescale) for every warp
+ * whose bound stays inside the safe exponent range, and the online-max path otherwise.  Same result up to rounding. */
 
 /* Same kernel for head dims that are not MMA friendly (Synapse 14x14 level: hd = 20): the host zero-pads the q/k heads to
  * hd_pad and the value heads to dv_pad when packing q_proj/k_proj/v_proj/out_proj.  Row layouts:
  * qkv [B,N, 2h*hd_pad | 2h*hd_pad | h*dv_pad], out [B,N, h*dv_pad].  Supported (hd_pad, dv_pad): (8,16) (16,32) (32,48)
  * (32,64) (64,128). */
 int cenet_diffattn_flash_padded(const void* qkv, void* out, int B, int N, int heads, int hd_pad, int dv_pad, int hd_real,
-                                float lambda, float eps, float mult, cenet_stream_t s);
+                                float lambda, float eps, float mult, float* kmax_ws, cenet_stream_t s);
 
 /* ---- encoder attention (pvtv2.py:88-105): softmax(q k^T * scale) v with <= 64 keys, head_dim 64 ------------ */
 int cenet_sr_attention(const void* q, int q_dtype, const void* kv, int kv_dtype, void* out, int o_dtype, int B, int N,

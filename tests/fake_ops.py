@@ -218,7 +218,7 @@ def diff_combine_(P, npairs, map_elems, lam):
     return P
 
 
-def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
+def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult, kmax_ws=None):
     _LAUNCHES[0] += 1
     hd = E // heads // 2
     t = _flat(qkv).view(B, N, 3 * E).float()
@@ -232,7 +232,7 @@ def diffattn_flash(qkv, out, B, N, E, heads, lam, eps, mult):
     return out
 
 
-def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult):
+def diffattn_flash_padded(qkv, out, B, N, heads, hd_pad, dv_pad, hd_real, lam, eps, mult, kmax_ws=None):
     _LAUNCHES[0] += 1
     Eq = 2 * heads * hd_pad
     t = _flat(qkv).view(B, N, 2 * Eq + heads * dv_pad).float()

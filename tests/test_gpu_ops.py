@@ -282,6 +282,24 @@ def test_diffattn_flash(E, heads, N):
     e = rel(out, ref)
     record(f"diffattn_flash_E{E}_h{heads}_N{N}", e)
     assert e < 1.5e-2, e      # bf16 P and bf16 output; the difference of two softmaxes amplifies rounding
+    # bounded-softmax mode (fixed Cauchy-Schwarz shift instead of the running max): same result up to rounding
+    ws = torch.empty(B * 2 * heads, device=DEV)
+    out_b = torch.empty_like(out)
+    ops.diffattn_flash(qb, out_b, B, N, E, heads, 0.55, 1e-5, 0.45, ws)
+    hd = E // heads // 2
+    if hd < 64:                 # the hd = 64 instantiation (skin 28x28 level) keeps the online maximum
+        kn = qb.float()[..., E:2 * E].view(B, N, 2 * heads, hd).norm(dim=-1).amax(1)
+        torch.testing.assert_close(ws.view(B, 2 * heads), kn, rtol=1e-5, atol=1e-6)
+    eb = rel(out_b, ref)
+    record(f"diffattn_flash_bounded_E{E}_h{heads}_N{N}", eb)
+    assert eb < 1.5e-2, eb
+    # huge logits: the bound leaves the safe exponent range -> warps fall back to the online maximum, no NaN/Inf
+    big = qb.clone()
+    big[..., :2 * E] *= 6.0
+    ops.diffattn_flash(big, out_b, B, N, E, heads, 0.55, 1e-5, 0.45, ws)
+    ops.diffattn_flash(big, out, B, N, E, heads, 0.55, 1e-5, 0.45)
+    assert torch.isfinite(out_b.float()).all()
+    assert rel(out_b, out) < 2e-2
 
 
 @pytest.mark.parametrize("C,N", [(64, 3136), (128, 784), (64, 100)])
