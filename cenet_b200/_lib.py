@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcenet_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = range(6)
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID, ACT_GELU_GRAD = range(7)
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
 
 vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
@@ -33,6 +33,8 @@ class GemmArgs(C.Structure):
         ("res2", vp), ("res2_dtype", i32), ("ldr2", ll),
         ("mul", vp), ("mul_dtype", i32), ("ldmul", ll), ("mul_act", i32),
         ("impl", i32),
+        # training extensions (zero == inference behaviour)
+        ("a_mmajor", i32), ("rs_div", i32), ("post_row_scale", vp), ("post_rs_div", i32),
     ]
 
 
@@ -62,6 +64,45 @@ _SIGS = {
     "cenet_stem5x5": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp],
     "cenet_head_upsample_argmax": [vp, vp, vp, i32, i32, i32, i32, vp],
     "cenet_dice_ce": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, vp],
+    # ---- training (see include/cenet_b200.h) ----
+    "cenet_dwconv3x3_train": [vp, i32, ll, vp, i32, ll, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_gemm_wgrad": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, vp, vp, i32, vp, ll, vp],
+    "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
+    "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, ll, vp],
+    "cenet_affine_act": [vp, i32, ll, vp, vp, vp, i32, ll, vp, vp, vp, i32, ll, ll, i32, i32, f32, vp],
+    "cenet_bn_bwd": [vp, i32, vp, i32, ll, vp, i32, ll, vp, vp, vp, ll, i32, i32, f32, vp, i32, i32, vp, vp, vp, i32, ll,
+                     i32, vp, ll, vp],
+    "cenet_dwconv3x3_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, vp, ll, vp],
+    "cenet_sumpool2": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cenet_col2im": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "cenet_flash_fwd": [vp, ll, vp, ll, vp, ll, vp, ll, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_flash_bwd": [vp, ll, vp, ll, vp, ll, vp, vp, ll, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_softmax_bwd_rows": [vp, vp, i32, ll, i32, vp],
+    "cenet_lambda_fwd": [vp, vp, vp, vp, i32, f32, vp, vp],
+    "cenet_lambda_bwd": [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "cenet_diff_rmsnorm_fwd": [vp, i32, vp, vp, ll, i32, i32, f32, f32, vp],
+    "cenet_diff_rmsnorm_bwd": [vp, vp, i32, vp, vp, vp, ll, i32, i32, f32, f32, vp, ll, vp],
+    "cenet_fea_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, ll, vp],
+    "cenet_nchw_to_nhwc_slice": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+    "cenet_add": [vp, vp, i32, ll, i32, vp],
+    "cenet_ccu_stats": [vp, i32, vp, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_ccu_mlp_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, i32, i32, vp],
+    "cenet_ccu_mlp_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
+    "cenet_ccu_dgate": [vp, vp, i32, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_ccu_apply_bwd": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "cenet_row_stats_arg": [vp, i32, vp, vp, ll, i32, vp],
+    "cenet_srm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_row_dot": [vp, vp, i32, vp, ll, i32, vp],
+    "cenet_srm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_srm_apply_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, vp],
+    "cenet_silu_mul_fwd": [vp, vp, vp, i32, ll, vp],
+    "cenet_silu_mul_bwd": [vp, vp, vp, vp, vp, i32, ll, vp],
+    "cenet_ls_combine_fwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, vp],
+    "cenet_ls_combine_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, ll, i32, vp, ll, vp],
+    "cenet_resample": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp],
+    "cenet_maxpool2_scale_bwd": [vp, i32, ll, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp],
+    "cenet_head_upsample_bwd": [vp, vp, i32, i32, i32, i32, vp],
+    "cenet_adamw": [vp, vp, vp, vp, ll, vp, vp],
 }
 _PLAIN = {  # no stream, different return types
     "cenet_last_error": ([], C.c_char_p),

@@ -53,7 +53,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          bias=None, bias_per_row=False, row_scale=None, alpha=1.0, act=ACT_NONE, slope=0.0, act_after_res=False,
          res1=None, ldr1=0, res1_cscale=None, res1_scale=1.0, res2=None, ldr2=0, mul=None, ldmul=0, mul_act=ACT_NONE,
          conv=None, batch=1, batch_inner=1, a_bs=(0, 0), w_bs=(0, 0), c_bs=(0, 0), w_nmajor=False, impl=GEMM_AUTO,
-         a_off=0, w_off=0, c_off=0):
+         a_off=0, w_off=0, c_off=0, rs_div=1, post_rs=None, post_rs_div=1, a_mmajor=False, r1_off=0):
     """C[M,N] = epilogue(A[M,K] W[N,K]^T); see cenet_gemm in include/cenet_b200.h.  *_off are element offsets."""
     g = GemmArgs()
     g.M, g.N, g.K = M, N, K
@@ -72,13 +72,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.bias, g.bias_per_row, g.row_scale = _f32(bias, "bias"), int(bias_per_row), _f32(row_scale, "row_scale")
     g.act, g.slope, g.act_after_res = act, slope, int(act_after_res)
     if res1 is not None:
-        g.res1, g.res1_dtype, g.ldr1 = _p(res1), dt(res1), ldr1
+        g.res1, g.res1_dtype, g.ldr1 = _p(res1) + r1_off * res1.element_size(), dt(res1), ldr1
         g.res1_cscale, g.res1_scale = _f32(res1_cscale, "res1_cscale"), res1_scale
     if res2 is not None:
         g.res2, g.res2_dtype, g.ldr2 = _p(res2), dt(res2), ldr2
     if mul is not None:
         g.mul, g.mul_dtype, g.ldmul, g.mul_act = _p(mul), dt(mul), ldmul, mul_act
     g.impl = impl
+    g.a_mmajor, g.rs_div, g.post_row_scale, g.post_rs_div = int(a_mmajor), rs_div, _f32(post_rs, "post_rs"), post_rs_div
     L.call("cenet_gemm", C.byref(g), _stream())
     return out
 
@@ -128,10 +129,17 @@ def rmsnorm_seg(x2d, out, seg, eps, mult):
 
 # ------------------------------------------------------------------------------------------------------ dwconv
 def dwconv3x3(x, out, w9c, B, H, W, Cc, *, ldx=None, ldy=None, x_off=0, y_off=0, bias=None, scale=None, shift=None,
-              dil=1, up2=False, act=ACT_NONE, slope=0.0):
-    """H, W are OUTPUT sizes; with up2 the input is [B,H/2,W/2,C]."""
+              dil=1, up2=False, act=ACT_NONE, slope=0.0, zout=None):
+    """H, W are OUTPUT sizes; with up2 the input is [B,H/2,W/2,C].  zout (training): contiguous [B,H,W,C] buffer that
+    receives the pre-activation value."""
     ldx = Cc if ldx is None else ldx
     ldy = Cc if ldy is None else ldy
+    if zout is not None:
+        if scale is not None or up2:
+            raise ValueError("dwconv3x3(zout=...) does not take scale/shift/up2")
+        L.call("cenet_dwconv3x3_train", _p(x) + x_off * x.element_size(), dt(x), ldx, _p(out) + y_off * out.element_size(),
+               dt(out), ldy, _p(zout), _f32(w9c, "w9c"), _f32(bias, "bias"), B, H, W, Cc, dil, act, dt(zout), slope, _stream())
+        return out
     L.call("cenet_dwconv3x3", _p(x) + x_off * x.element_size(), dt(x), ldx, _p(out) + y_off * out.element_size(),
            dt(out), ldy, _f32(w9c, "w9c"), _f32(bias, "bias"), _f32(scale, "scale"), _f32(shift, "shift"), B, H, W, Cc,
            dil, int(up2), act, slope, _stream())

@@ -12,7 +12,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = range(6)
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID, ACT_GELU_GRAD = range(7)
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
 F32, BF16 = 0, 1
 _LAUNCHES = [0]
@@ -24,7 +24,12 @@ def launch_count():
 
 def _v(t, size, stride, off=0):
     _LAUNCHES[0] += 0
-    return torch.as_strided(t.view(-1) if t.is_contiguous() else t.contiguous().view(-1), size, stride, off)
+    return _as(t.view(-1) if t.is_contiguous() else t.contiguous().view(-1), size, stride, off)
+
+
+def _as(t, size, stride, off=0):
+    """as_strided with `off` relative to t's own first element (torch's storage_offset argument is absolute)"""
+    return torch.Tensor.as_strided(t, size, stride, t.storage_offset() + off)
 
 
 def _flat(t):
@@ -43,13 +48,16 @@ def _act(v, act, slope=0.0):
         return F.silu(v)
     if act == ACT_SIGMOID:
         return torch.sigmoid(v)
+    if act == ACT_GELU_GRAD:                                   # d gelu(v) / dv
+        return 0.5 * (1 + torch.erf(v * 0.7071067811865476)) + v * torch.exp(-0.5 * v * v) * 0.3989422804014327
     return v
 
 
 def gemm(a, w, out, *, M, N, K, lda, ldw, ldc, bias=None, bias_per_row=False, row_scale=None, alpha=1.0, act=ACT_NONE,
          slope=0.0, act_after_res=False, res1=None, ldr1=0, res1_cscale=None, res1_scale=1.0, res2=None, ldr2=0, mul=None,
          ldmul=0, mul_act=ACT_NONE, conv=None, batch=1, batch_inner=1, a_bs=(0, 0), w_bs=(0, 0), c_bs=(0, 0),
-         w_nmajor=False, impl=GEMM_AUTO, a_off=0, w_off=0, c_off=0):
+         w_nmajor=False, impl=GEMM_AUTO, a_off=0, w_off=0, c_off=0, rs_div=1, post_rs=None, post_rs_div=1,
+         a_mmajor=False, r1_off=0):
     _LAUNCHES[0] += 1
     af, wf, cf = _flat(a), _flat(w), _flat(out)
     for z in range(batch):
@@ -59,31 +67,36 @@ def gemm(a, w, out, *, M, N, K, lda, ldw, ldc, bias=None, bias_per_row=False, ro
         co = c_off + zo * c_bs[0] + zi * c_bs[1]
         if conv is not None:
             Bimg, H, W, Cin, KH, KW, stride, pad, Ho, Wo = conv
-            x = torch.as_strided(af, (Bimg, H, W, Cin), (H * W * lda, W * lda, lda, 1), ao).float().permute(0, 3, 1, 2)
-            wm = torch.as_strided(wf, (N, K), (ldw, 1), wo).float().view(N, KH, KW, Cin).permute(0, 3, 1, 2)
+            x = _as(af, (Bimg, H, W, Cin), (H * W * lda, W * lda, lda, 1), ao).float().permute(0, 3, 1, 2)
+            wm = _as(wf, (N, K), (ldw, 1), wo).float().view(N, KH, KW, Cin).permute(0, 3, 1, 2)
             acc = F.conv2d(x, wm, stride=stride, padding=pad).permute(0, 2, 3, 1).reshape(M, N)
         else:
-            A = torch.as_strided(af, (M, K), (lda, 1), ao).float()
-            Wm = torch.as_strided(wf, (K, N), (ldw, 1), wo).float() if w_nmajor else \
-                torch.as_strided(wf, (N, K), (ldw, 1), wo).float().t()
+            A = _as(af, (M, K), (1, lda), ao).float() if a_mmajor else \
+                _as(af, (M, K), (lda, 1), ao).float()
+            Wm = _as(wf, (K, N), (ldw, 1), wo).float() if w_nmajor else \
+                _as(wf, (N, K), (ldw, 1), wo).float().t()
             acc = A @ Wm
         v = alpha * acc
+        rows = torch.arange(M)
         if row_scale is not None:
-            v = v * row_scale.view(-1)[:M, None]
+            v = v * row_scale.view(-1)[rows // rs_div][:, None]
         if bias is not None:
             v = v + (bias[:M, None] if bias_per_row else bias[None, :N])
         if not act_after_res:
             v = _act(v, act, slope)
+        bo = co - c_off                                          # batch offset (the kernel adds it to C / res / mul)
         if mul is not None:
-            v = v * _act(torch.as_strided(_flat(mul), (M, N), (ldmul, 1), co if batch > 1 else 0).float(), mul_act)
+            v = v * _act(_as(_flat(mul), (M, N), (ldmul, 1), bo).float(), mul_act)
+        if post_rs is not None:
+            v = v * post_rs.view(-1)[rows // post_rs_div][:, None]
         if res1 is not None:
-            r = torch.as_strided(_flat(res1), (M, N), (ldr1, 1), co if batch > 1 else 0).float()
+            r = _as(_flat(res1), (M, N), (ldr1, 1), bo + r1_off).float()
             v = v + r * (res1_cscale[None, :N] if res1_cscale is not None else res1_scale)
         if res2 is not None:
-            v = v + torch.as_strided(_flat(res2), (M, N), (ldr2, 1), co if batch > 1 else 0).float()
+            v = v + _as(_flat(res2), (M, N), (ldr2, 1), bo).float()
         if act_after_res:
             v = _act(v, act, slope)
-        torch.as_strided(cf, (M, N), (ldc, 1), co).copy_(v)
+        _as(cf, (M, N), (ldc, 1), co).copy_(v)
     return out
 
 
@@ -110,7 +123,7 @@ def layernorm(x2d, out, gamma, beta, eps):
 
 def softmax_rows_(x, rows, n, ld):
     _LAUNCHES[0] += 1
-    v = torch.as_strided(_flat(x), (rows, n), (ld, 1))
+    v = _as(_flat(x), (rows, n), (ld, 1))
     v.copy_(torch.softmax(v.float(), -1))
     return x
 
@@ -131,36 +144,38 @@ def rmsnorm_seg(x2d, out, seg, eps, mult):
 
 
 def dwconv3x3(x, out, w9c, B, H, W, Cc, *, ldx=None, ldy=None, x_off=0, y_off=0, bias=None, scale=None, shift=None,
-              dil=1, up2=False, act=ACT_NONE, slope=0.0):
+              dil=1, up2=False, act=ACT_NONE, slope=0.0, zout=None):
     _LAUNCHES[0] += 1
     ldx = Cc if ldx is None else ldx
     ldy = Cc if ldy is None else ldy
     Hi, Wi = (H // 2, W // 2) if up2 else (H, W)
-    xi = torch.as_strided(_flat(x), (B, Hi, Wi, Cc), (Hi * Wi * ldx, Wi * ldx, ldx, 1), x_off).float().permute(0, 3, 1, 2)
+    xi = _as(_flat(x), (B, Hi, Wi, Cc), (Hi * Wi * ldx, Wi * ldx, ldx, 1), x_off).float().permute(0, 3, 1, 2)
     if up2:
         xi = F.interpolate(xi, scale_factor=2, mode="nearest")
     wt = w9c.t().reshape(Cc, 1, 3, 3)
     v = F.conv2d(xi, wt, bias, padding=dil, dilation=dil, groups=Cc)
     if scale is not None:
         v = v * scale[None, :, None, None] + shift[None, :, None, None]
+    if zout is not None:                                       # pre-activation kept for the backward pass
+        _flat(zout).view(B, H, W, Cc).copy_(v.permute(0, 2, 3, 1))
     v = _act(v, act, slope)
-    torch.as_strided(_flat(out), (B, H, W, Cc), (H * W * ldy, W * ldy, ldy, 1), y_off).copy_(v.permute(0, 2, 3, 1))
+    _as(_flat(out), (B, H, W, Cc), (H * W * ldy, W * ldy, ldy, 1), y_off).copy_(v.permute(0, 2, 3, 1))
     return out
 
 
 def nhwc_to_nchw(x, out, B, HW, Cc, Ctot, coff, ldx=None):
     _LAUNCHES[0] += 1
     ldx = Cc if ldx is None else ldx
-    xi = torch.as_strided(_flat(x), (B, HW, Cc), (HW * ldx, ldx, 1))
-    torch.as_strided(_flat(out), (B, Cc, HW), (Ctot * HW, HW, 1), coff * HW).copy_(xi.transpose(1, 2))
+    xi = _as(_flat(x), (B, HW, Cc), (HW * ldx, ldx, 1))
+    _as(_flat(out), (B, Cc, HW), (Ctot * HW, HW, 1), coff * HW).copy_(xi.transpose(1, 2))
     return out
 
 
 def nchw_to_nhwc(x, out, B, HW, Cc, ldy=None):
     _LAUNCHES[0] += 1
     ldy = Cc if ldy is None else ldy
-    xi = torch.as_strided(_flat(x), (B, Cc, HW), (Cc * HW, HW, 1))
-    torch.as_strided(_flat(out), (B, HW, Cc), (HW * ldy, ldy, 1)).copy_(xi.transpose(1, 2))
+    xi = _as(_flat(x), (B, Cc, HW), (Cc * HW, HW, 1))
+    _as(_flat(out), (B, HW, Cc), (HW * ldy, ldy, 1)).copy_(xi.transpose(1, 2))
     return out
 
 
@@ -187,7 +202,7 @@ def maxpool2_scale(x, out, ldy, coff, wch, B, H, W, Cc):
     _LAUNCHES[0] += 1
     xi = _flat(x).view(B, H, W, Cc).float().permute(0, 3, 1, 2)
     v = (F.max_pool2d(xi, 2) * wch[None, :, None, None]).permute(0, 2, 3, 1)
-    torch.as_strided(_flat(out), (B, H // 2, W // 2, Cc), ((H // 2) * (W // 2) * ldy, (W // 2) * ldy, ldy, 1), coff).copy_(v)
+    _as(_flat(out), (B, H // 2, W // 2, Cc), ((H // 2) * (W // 2) * ldy, (W // 2) * ldy, ldy, 1), coff).copy_(v)
     return out
 
 
@@ -294,13 +309,13 @@ def srm_gate(u, gate, pw3, dw27, bn_scale, bn_shift, B, H, W):
 
 def pool_branch(x, ldx, coff, y, ldy, coff_y, w_rr, bn_scale, bn_shift, slope, pooled_ws, B, H, W, r):
     _LAUNCHES[0] += 2
-    xi = torch.as_strided(_flat(x), (B, H, W, r), (H * W * ldx, W * ldx, ldx, 1), coff).float().permute(0, 3, 1, 2)
+    xi = _as(_flat(x), (B, H, W, r), (H * W * ldx, W * ldx, ldx, 1), coff).float().permute(0, 3, 1, 2)
     p = F.adaptive_avg_pool2d(xi, (7, 7))
     p = F.leaky_relu(F.conv2d(p, w_rr.view(r, r, 1, 1)) * bn_scale[None, :, None, None] + bn_shift[None, :, None, None], slope)
     p = F.interpolate(p, scale_factor=7, mode="bilinear", align_corners=True)
     if p.shape[2] != H or p.shape[3] != W:
         p = F.interpolate(p, size=(H, W), mode="bilinear", align_corners=False)
-    torch.as_strided(_flat(y), (B, H, W, r), (H * W * ldy, W * ldy, ldy, 1), coff_y).copy_(p.permute(0, 2, 3, 1))
+    _as(_flat(y), (B, H, W, r), (H * W * ldy, W * ldy, ldy, 1), coff_y).copy_(p.permute(0, 2, 3, 1))
     return y
 
 
@@ -321,3 +336,18 @@ def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
         logits.copy_(v)
     if labels is not None:
         labels.copy_(torch.argmax(torch.softmax(v, 1), 1))
+
+
+def loss_nblocks(npix):
+    return (npix + 1023) // 1024
+
+
+def dice_ce(logits, labels, loss_out, dlogits, ws, B, ncls, HW, w_dice, w_ce, grad_scale=1.0):
+    _LAUNCHES[0] += 2
+    from oracle import cenet_oracle as O
+    lg = logits.detach().clone().requires_grad_(True)
+    loss = O.criterion_dice_ce(lg, labels, ncls, w_dice, w_ce)
+    loss_out[0] = loss.detach()
+    if dlogits is not None:
+        dlogits.copy_(torch.autograd.grad(loss, lg)[0] * grad_scale)
+    return loss_out

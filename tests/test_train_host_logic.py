@@ -1,0 +1,89 @@
+"""Host logic of the TRAINING launch plan on CPU: `TrainEngine` runs with tests/fake_ops.py + tests/fake_train_ops.py
+(torch emulations of the C-ABI kernels) and must reproduce loss and EVERY parameter gradient of autograd through the
+oracle in train mode (batch-statistics BatchNorm).  This pins the tape order, gradient accumulation across fan-outs,
+channel-slice bookkeeping, weight (re)packing and the flat parameter / gradient buffers; the CUDA kernels themselves
+are checked against the same emulations on the B200 (tests/test_gpu_train_ops.py)."""
+import pytest
+import torch
+
+import fake_ops
+import fake_train_ops
+from oracle import cenet_oracle as O
+from oracle import fixtures
+
+
+@pytest.fixture(autouse=True)
+def _patch_ops(monkeypatch):
+    import cenet_b200.train as T
+    monkeypatch.setattr(T, "ops", fake_ops)
+    monkeypatch.setattr(T, "tops", fake_train_ops)
+    import cenet_b200._lib as L
+    monkeypatch.setattr(L, "load", lambda: None)   # TEMP while the kernels are being written
+
+
+def _build(name, flash=False):
+    import cenet_b200.train as T
+    from cenet_b200.networks import CENet
+    kw = fixtures.CONFIGS[name]
+    torch.manual_seed(1234)
+    m = CENet(**kw)
+    sd = fixtures.perturb_state(m.state_dict(), 1234)
+    m.load_state_dict(sd)
+    m.train()
+    eng = T.TrainEngine(m, "cpu", "fp32")
+    eng.use_graph = False
+    eng.use_flash = flash
+    eng.drop_path = False
+    return m, eng, sd, kw
+
+
+def _oracle_grads(sd, kw, x, labels):
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits = O.cenet_forward(leaf, O.Cfg(**kw), x, training=True)
+    loss = O.criterion_dice_ce(logits, labels, kw["num_classes"])
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
+    return loss.item(), logits.detach(), dict(zip(names, grads))
+
+
+@pytest.mark.parametrize("name,batch,size,flash", [("acdc", 2, 64, False), ("synapse", 2, 64, True), ("skin", 2, 64, True),
+                                                   ("acdc", 1, 224, True)])
+def test_train_step_matches_oracle_autograd(name, batch, size, flash):
+    m, eng, sd, kw = _build(name, flash)
+    x = fixtures.synth_input(name, batch, size=size)
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, kw["num_classes"], (batch, size, size), generator=g)
+    loss_ref, logits_ref, gref = _oracle_grads(sd, kw, x, labels)
+    out = eng.train_step(x, labels, optimize=False)
+    assert abs(out[0].item() - loss_ref) < 2e-5 * max(1.0, abs(loss_ref)), (out[0].item(), loss_ref)
+    bad = []
+    for k, gr in gref.items():
+        mine = eng.GP[k]
+        if gr is None:                                     # CCU BatchNorm1d is skipped at B == 1 (cfam.py:260)
+            assert mine.abs().max().item() == 0.0, k
+            continue
+        # (biases feeding a BatchNorm / softmax have analytically zero gradients: absolute floor)
+        err = (mine - gr).norm().item()
+        if not err < 2e-3 * gr.norm().item() + 1e-6:
+            bad.append((k, err, gr.norm().item()))
+    assert not bad, bad[:20]
+
+
+def test_running_stats_and_adamw_step():
+    m, eng, sd, kw = _build("acdc")
+    x = fixtures.synth_input("acdc", 2, size=64)
+    labels = torch.randint(0, 4, (2, 64, 64), generator=torch.Generator().manual_seed(5))
+    p0 = eng.pflat.clone()
+    out = eng.train_step(x, labels, lr=1e-3, weight_decay=1e-2)
+    g = eng.gflat.clone()
+    # torch.optim.AdamW, first step: p <- p(1 - lr wd) - lr * g / (|g| + eps)
+    ref = p0 * (1 - 1e-3 * 1e-2) - 1e-3 * g / (g.abs() + 1e-8)
+    assert (eng.pflat - ref).abs().max().item() < 1e-6
+    # module parameters ARE the flat buffer
+    for n, p in m.named_parameters():
+        assert p.data_ptr() == eng.P[n].data_ptr()
+    # BatchNorm bookkeeping: momentum 0.1 towards the batch statistics, counters incremented
+    assert int(m.state_dict()["decoder.dec1.norm1.num_batches_tracked"]) == 8
+    rm = m.state_dict()["out.out.0.norm1.running_mean"]
+    assert not torch.allclose(rm, sd["out.out.0.norm1.running_mean"])
+    assert torch.isfinite(out).all()
