@@ -149,6 +149,8 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     case CENET_ACT_LEAKY: return v > 0.0f ? v : v * slope;
     case CENET_ACT_SILU: return v * sigmoidf_(v);
     case CENET_ACT_SIGMOID: return sigmoidf_(v);
+    case CENET_ACT_GELU_GRAD:   // d gelu(v) / dv (training: fused into the dgrad GEMM that produces d(pre-activation))
+      return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * __expf(-0.5f * v * v) * 0.39894228040143267794f;
     default: return v;
   }
 }
@@ -188,6 +190,8 @@ struct EpiParams {
   const float* bias;
   int bias_per_row;
   const float* row_scale;
+  int rs_div;                         // row_scale index = m / rs_div (per-sample scales)
+  const float* post_rs; int post_rs_div;   // applied after bias/act/mul, before the residuals (DropPath)
   int act;
   float slope;
   int act_after_res;
@@ -205,10 +209,11 @@ __device__ __forceinline__ float ld_any(const void* p, int dtype, long long idx)
 // one element; `coff` = batch offset (elements) applied to C / res / mul
 __device__ __forceinline__ float epi_value(const EpiParams& e, float acc, long long m, int n, long long coff) {
   float v = e.alpha * acc;
-  if (e.row_scale) v *= e.row_scale[m];
+  if (e.row_scale) v *= e.row_scale[m / e.rs_div];
   if (e.bias) v += e.bias_per_row ? e.bias[m] : e.bias[n];
   if (!e.act_after_res) v = apply_act(v, e.act, e.slope);
   if (e.mul) v *= apply_act(ld_any(e.mul, e.mul_dtype, coff + m * e.ldmul + n), e.mul_act, 0.f);
+  if (e.post_rs) v *= e.post_rs[m / e.post_rs_div];
   if (e.res1) v += ld_any(e.res1, e.res1_dtype, coff + m * e.ldr1 + n) * (e.res1_cscale ? e.res1_cscale[n] : e.res1_scale);
   if (e.res2) v += ld_any(e.res2, e.res2_dtype, coff + m * e.ldr2 + n);
   if (e.act_after_res) v = apply_act(v, e.act, e.slope);
@@ -223,6 +228,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, float v, long long
 static inline EpiParams make_epi(const cenet_gemm_args* a) {
   EpiParams e;
   e.alpha = a->alpha; e.bias = a->bias; e.bias_per_row = a->bias_per_row; e.row_scale = a->row_scale;
+  e.rs_div = a->rs_div > 0 ? a->rs_div : 1; e.post_rs = a->post_row_scale; e.post_rs_div = a->post_rs_div > 0 ? a->post_rs_div : 1;
   e.act = a->act; e.slope = a->slope; e.act_after_res = a->act_after_res;
   e.res1 = a->res1; e.res1_dtype = a->res1_dtype; e.ldr1 = a->ldr1; e.res1_cscale = a->res1_cscale;
   e.res1_scale = a->res1_scale;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const TI* __restrict__ x
                                                         const float* __restrict__ w9c, const float* __restrict__ bias,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         int H, int W, int C, int dil, int up2, int act, float slope,
-                                                        int nrows) {
+                                                        int nrows, TO* __restrict__ zout) {
   constexpr bool FAST = sizeof(TO) == 2;
   // block = TX channel vectors x (RB rows x blockDim.y/RB pixel groups): neighbouring rows of the 3x3 window are served
   // by the same SM's L1, so each input element crosses the L2->SM fabric ~2x instead of ~4x
@@ -119,15 +119,18 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const TI* __restrict__ x
     if (w0 + p >= W) continue;
     float o[V];
 #pragma unroll
-    for (int v = 0; v < V; v++) o[v] = dw_act2<FAST>(fmaf(acc[p][v], sc[v], sh[v]), act, slope);
+    for (int v = 0; v < V; v++) o[v] = fmaf(acc[p][v], sc[v], sh[v]);
+    if (zout) stv<V>(zout + ((size_t)(b * H + h) * W + w0 + p) * C + c, o);     // training: keep the pre-activation
+#pragma unroll
+    for (int v = 0; v < V; v++) o[v] = dw_act2<FAST>(o[v], act, slope);
     stv<V>(y + ((size_t)(b * H + h) * W + w0 + p) * ldy + c, o);
   }
 }
 }  // namespace
 
-extern "C" int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy,
-                               const float* w9c, const float* bias, const float* scale, const float* shift, int B,
-                               int H, int W, int C, int dil, int up2, int act, float slope, cenet_stream_t s) {
+static int dwconv_launch(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy,
+                         const float* w9c, const float* bias, const float* scale, const float* shift, int B,
+                         int H, int W, int C, int dil, int up2, int act, float slope, void* zout, cenet_stream_t s) {
   if (B == 0) return 0;
   CENET_REQUIRE(x && y && w9c, "cenet_dwconv3x3: null pointer");
   CENET_REQUIRE((scale == nullptr) == (shift == nullptr), "cenet_dwconv3x3: scale and shift come together");
@@ -135,7 +138,7 @@ extern "C" int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* 
   CENET_REQUIRE(ldx >= C && ldy >= C && dil >= 1, "cenet_dwconv3x3: bad pitch / dilation");
   CENET_REQUIRE((long long)B * H <= 65535, "cenet_dwconv3x3: B*H=%lld exceeds the grid limit", (long long)B * H);
   int V = pick_vec({C, ldx, ldy, ptr_align_elems(x, dtype_size(x_dtype)), ptr_align_elems(y, dtype_size(y_dtype)),
-                    ptr_align_elems(w9c, 4) * 2});
+                    ptr_align_elems(w9c, 4) * 2, zout ? ptr_align_elems(zout, dtype_size(y_dtype)) : 8});
   if (V > 4 && (x_dtype == CENET_F32 || y_dtype == CENET_F32)) V = 4;   // keep fp32 accesses at 16 bytes
   const int cv = C / V;
   constexpr int PW = 2;
@@ -149,9 +152,23 @@ extern "C" int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* 
   CENET_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "cenet_dwconv3x3: grid too large");
 #define LAUNCH(VV)                                                                                              \
   CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(y_dtype, TO, (dwconv3x3_kernel<TI, TO, VV, PW, RB><<<grid, block, 0, to_stream(s)>>>( \
-      (const TI*)x, (int)ldx, (TO*)y, (int)ldy, w9c, bias, scale, shift, H, W, C, dil, up2, act, slope, nrows))))
+      (const TI*)x, (int)ldx, (TO*)y, (int)ldy, w9c, bias, scale, shift, H, W, C, dil, up2, act, slope, nrows, (TO*)zout))))
   if (V == 8) LAUNCH(8); else if (V == 4) LAUNCH(4); else if (V == 2) LAUNCH(2); else LAUNCH(1);
 #undef LAUNCH
   CENET_LAUNCH_CHECK("dwconv3x3");
   return 0;
+}
+
+extern "C" int cenet_dwconv3x3(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy,
+                               const float* w9c, const float* bias, const float* scale, const float* shift, int B,
+                               int H, int W, int C, int dil, int up2, int act, float slope, cenet_stream_t s) {
+  return dwconv_launch(x, x_dtype, ldx, y, y_dtype, ldy, w9c, bias, scale, shift, B, H, W, C, dil, up2, act, slope, nullptr, s);
+}
+
+// training forward: also stores the pre-activation z (contiguous [B,H,W,C], dtype z_dtype == y_dtype) for the backward pass
+extern "C" int cenet_dwconv3x3_train(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, void* zout,
+                                     const float* w9c, const float* bias, int B, int H, int W, int C, int dil, int act,
+                                     int z_dtype, float slope, cenet_stream_t s) {
+  CENET_REQUIRE(zout != nullptr && z_dtype == y_dtype, "cenet_dwconv3x3_train: zout must be given with the dtype of y");
+  return dwconv_launch(x, x_dtype, ldx, y, y_dtype, ldy, w9c, bias, nullptr, nullptr, B, H, W, C, dil, 0, act, slope, zout, s);
 }

@@ -9,7 +9,8 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 struct SimtParams {
   int M, N, K;
   int batch_inner;
-  const void* A; int a_dtype; long long lda, a_bso, a_bsi;
+  const void* A; int a_dtype; long long lda, a_bso, a_bsi; int a_mmajor;
+  const float* kscale; int kscale_div; long long kscale_bs;
   int conv, H, W, Cin, KH, KW, stride, pad, Ho, Wo;
   const void* Wt; int w_dtype; long long ldw, w_bso, w_bsi; int w_nmajor;
   long long c_bso, c_bsi;
@@ -65,6 +66,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtParams p) {
           int h = a_h0[i] + kh, w = a_w0[i] + kw;
           if (h >= 0 && h < p.H && w >= 0 && w < p.W)
             v = ld_any(p.A, p.a_dtype, aoff + arow_base[i] + ((long long)h * p.W + w) * p.lda + ci);
+        } else if (p.a_mmajor) {
+          v = ld_any(p.A, p.a_dtype, aoff + (long long)k * p.lda + (m0 + lr + 16 * i));
+          if (p.kscale) v *= p.kscale[((long long)z * p.kscale_bs + k) / p.kscale_div];
         } else {
           v = ld_any(p.A, p.a_dtype, aoff + arow_base[i] + k);
         }
@@ -121,6 +125,8 @@ int cenet_gemm_simt(const cenet_gemm_args* a, cudaStream_t s) {
   SimtParams p;
   p.M = a->M; p.N = a->N; p.K = a->K; p.batch_inner = a->batch_inner;
   p.A = a->A; p.a_dtype = a->a_dtype; p.lda = a->lda; p.a_bso = a->a_bs_outer; p.a_bsi = a->a_bs_inner;
+  p.a_mmajor = a->a_mmajor; p.kscale = a->k_scale; p.kscale_div = a->k_scale_div > 0 ? a->k_scale_div : 1; p.kscale_bs = a->k_scale_bs;
+  CENET_REQUIRE(!(a->a_mmajor && a->conv), "cenet_gemm_simt: a_mmajor and conv are exclusive");
   p.conv = a->conv; p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.stride = a->stride;
   p.pad = a->pad; p.Ho = a->Ho; p.Wo = a->Wo;
   p.Wt = a->Wt; p.w_dtype = a->w_dtype; p.ldw = a->ldw; p.w_bso = a->w_bs_outer; p.w_bsi = a->w_bs_inner;

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
               v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
             }
-            const float rs = e.alpha * (e.row_scale ? e.row_scale[m] : 1.f);
+            const float rs = e.alpha * (e.row_scale ? e.row_scale[m / e.rs_div] : 1.f);
             const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
@@ -348,6 +348,11 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
 #pragma unroll
               for (int j = 0; j < 8; j++) v[j] *= apply_act(t[j], e.mul_act, 0.f);
+            }
+            if (e.post_rs) {
+              const float prs = e.post_rs[m / e.post_rs_div];
+#pragma unroll
+              for (int j = 0; j < 8; j++) v[j] *= prs;
             }
             if (e.res1) {
               float t[8];
@@ -438,7 +443,7 @@ int pick_bn(int N) {
 
 bool cenet_gemm_tc_eligible(const cenet_gemm_args* a) {
   if (a->a_dtype != CENET_BF16 || a->w_dtype != CENET_BF16) return false;
-  if (a->w_nmajor || a->batch != 1) return false;
+  if (a->w_nmajor || a->a_mmajor || a->k_scale || a->batch != 1) return false;
   if (a->ldw % 8 != 0 || ((uintptr_t)a->Wt & 15)) return false;
   if (a->conv) {
     // stride-1 "same" convolutions whose channel count fills a swizzle atom
@@ -519,7 +524,7 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   p.epi_vec = c_ok && vec_ok(a->res1, a->res1_dtype, a->ldr1) && vec_ok(a->res2, a->res2_dtype, a->ldr2) &&
               vec_ok(a->mul, a->mul_dtype, a->ldmul);
   p.epi_fast = 0;
-  if (p.epi_vec && a->c_dtype == CENET_BF16 && a->alpha == 1.0f && !a->row_scale && !a->bias_per_row && a->act == CENET_ACT_NONE &&
+  if (p.epi_vec && a->c_dtype == CENET_BF16 && a->alpha == 1.0f && !a->row_scale && !a->post_row_scale && !a->bias_per_row && a->act == CENET_ACT_NONE &&
       !a->mul && !a->res2 && a->N % 8 == 0 && (!a->bias || (((uintptr_t)a->bias & 15) == 0)) &&
       (!a->res1 || (!a->res1_cscale && a->res1_scale == 1.0f)))
     p.epi_fast = a->res1 ? 2 : 1;

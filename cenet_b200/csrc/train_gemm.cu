@@ -1,0 +1,264 @@
+// Weight-gradient GEMM:  dW[n, k] = sum_m rs[m] * dY[m, n] * X[m, k]   (contraction over the token / pixel dimension).
+//
+// Both operands are row-major over m, i.e. "MN-major" for the tensor core, so the tiles are staged [m][n] / [m][k] in shared
+// memory and read with ldmatrix.trans into mma.sync m16n8k16 bf16 fragments (fp32 accumulate).  The long contraction is
+// split over CTAs (split-M); every split writes an fp32 partial tile into the workspace and a second kernel reduces the
+// partials in fixed order (deterministic) while permuting k = (tap, cin) into the reference's [Cout, Cin, KH, KW] order.
+// Replaces autograd's weight gradients of every nn.Linear / 1x1 / dense conv on the path (pvtv2.py:41-45,90-106;
+// cfam.py:150-157,301-303; dseb.py:164; unet.py:201-214; blocks.py:209-214; nlb.py:107-143).
+// fp32 x fp32 operands (validation precision) go through the CUDA-core GEMM with the same split / reduce.
+#include "train_common.cuh"
+
+namespace {
+constexpr int TN = 64, TK = 64, TM = 64, PITCH = 72;      // +8 bf16 padding: conflict-free ldmatrix
+constexpr int WG_THREADS = 128;
+
+struct WgParams {
+  const void* dy; int dy_dtype; long long ldy;
+  const void* x; int x_dtype; long long ldx;
+  long long M; int N, K;
+  const float* rs; int rs_div;
+  long long m_per_split;
+  float* ws;                       // [S][N][K]
+  int fast_y, fast_x;              // 16-byte vector loads allowed
+};
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf16* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// stage one [TM][64] tile chunk (8 columns) into registers as 8 bf16
+__device__ __forceinline__ uint4 load_chunk(const void* base, int dtype, long long ld, long long m, long long M, int c, int Ccols,
+                                            int fast, float scale) {
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (m >= M || c >= Ccols) return u;
+  if (fast && c + 8 <= Ccols) {
+    u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + m * ld + c);
+    if (scale != 1.f) {
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float2 f = __bfloat1622float2(h[i]);
+        h[i] = __floats2bfloat162_rn(f.x * scale, f.y * scale);
+      }
+    }
+    return u;
+  }
+  bf16 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float v = (c + i < Ccols) ? ld_any(base, dtype, m * ld + c + i) * scale : 0.f;
+    t[i] = __float2bfloat16_rn(v);
+  }
+  return *reinterpret_cast<uint4*>(t);
+}
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_mma_kernel(const WgParams p) {
+  __shared__ __align__(16) bf16 sY[2][TM][PITCH];
+  __shared__ __align__(16) bf16 sX[2][TM][PITCH];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * TN, k0 = blockIdx.y * TK;
+  const long long mb = (long long)blockIdx.z * p.m_per_split;
+  const long long me = min(p.M, mb + p.m_per_split);
+  const int wn = (warp >> 1) * 32, wk = (warp & 1) * 32;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[i][j][q] = 0.f;
+
+  // staging map: 512 chunks per tile (64 rows x 8 column chunks); thread handles 4 of each tile
+  uint4 ry[4], rx[4];
+  auto stage = [&](long long m0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ch = tid + i * WG_THREADS;
+      const int r = ch >> 3, c = (ch & 7) * 8;
+      const long long m = m0 + r;
+      float sc = 1.f;
+      if (p.rs && m < me) sc = p.rs[m / p.rs_div];
+      ry[i] = load_chunk(p.dy, p.dy_dtype, p.ldy, m, me, n0 + c, p.N, p.fast_y, sc);
+      rx[i] = load_chunk(p.x, p.x_dtype, p.ldx, m, me, k0 + c, p.K, p.fast_x, 1.f);
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ch = tid + i * WG_THREADS;
+      const int r = ch >> 3, c = (ch & 7) * 8;
+      *reinterpret_cast<uint4*>(&sY[buf][r][c]) = ry[i];
+      *reinterpret_cast<uint4*>(&sX[buf][r][c]) = rx[i];
+    }
+  };
+  if (mb < me) {
+    stage(mb);
+    commit(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (long long m0 = mb; m0 < me; m0 += TM) {
+    const bool more = m0 + TM < me;
+    if (more) stage(m0 + TM);
+#pragma unroll
+    for (int ks = 0; ks < TM / 16; ks++) {
+      const int mrow = ks * 16;
+      uint32_t a[2][4], b[4][2];
+      const int j = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 2; i++)           // A = dY^T: matrices (n, m), (n+8, m), (n, m+8), (n+8, m+8)
+        ldsm_x4_t(a[i][0], a[i][1], a[i][2], a[i][3], &sY[buf][mrow + r + ((j & 2) ? 8 : 0)][wn + i * 16 + ((j & 1) ? 8 : 0)]);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {         // B = X: (m, k), (m+8, k), (m, k+8), (m+8, k+8)
+        uint32_t t0, t1, t2, t3;
+        ldsm_x4_t(t0, t1, t2, t3, &sX[buf][mrow + r + ((j & 1) ? 8 : 0)][wk + i * 16 + ((j & 2) ? 8 : 0)]);
+        b[2 * i][0] = t0; b[2 * i][1] = t1; b[2 * i + 1][0] = t2; b[2 * i + 1][1] = t3;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) mma_bf16(acc[i][q], a[i][0], a[i][1], a[i][2], a[i][3], b[q][0], b[q][1]);
+    }
+    if (more) commit(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // partial tile -> ws[z][n][k]
+  float* out = p.ws + (size_t)blockIdx.z * p.N * p.K;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int n = n0 + wn + i * 16 + g, k = k0 + wk + q * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int nn = n + h * 8;
+        if (nn < p.N) {
+          if (k < p.K) out[(size_t)nn * p.K + k] = acc[i][q][2 * h];
+          if (k + 1 < p.K) out[(size_t)nn * p.K + k + 1] = acc[i][q][2 * h + 1];
+        }
+      }
+    }
+}
+
+// dw[n, ci, t] = sum_s ws[s][n][t*Cin + ci]
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, int S, int N, int K, int T, float* dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  float s = 0.f;
+  for (int z = 0; z < S; z++) s += ws[(size_t)z * N * K + i];
+  const int n = i / K, k = i % K, Cin = K / T;
+  const int tt = k / Cin, ci = k % Cin;
+  dw[(size_t)n * K + ci * T + tt] = s;
+}
+
+// column sums with optional per-row scale (bias gradients)
+template <typename T, int V>
+__global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int C,
+                                                                     const float* __restrict__ rs, int rs_div, int ngrp, int nrl,
+                                                                     int rows_per_block, float* __restrict__ ws) {
+  __shared__ float smem[V * kColThreads];
+  const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
+  const int c0 = (blockIdx.y * ngrp + grp) * V;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s1[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) s1[v] = 0.f;
+  if (c0 < C) {
+    for (long long r = r0 + rl; r < r1; r += nrl) {
+      float xv[V];
+      ldv<V>(x + r * ld + c0, xv);
+      const float sc = rs ? rs[r / rs_div] : 1.f;
+#pragma unroll
+      for (int v = 0; v < V; v++) s1[v] = fmaf(xv[v], sc, s1[v]);
+    }
+  }
+  col_block_reduce<V>(s1, smem, grp, rl, ngrp, nrl);
+  if (rl == 0 && c0 < C) {
+#pragma unroll
+    for (int v = 0; v < V; v++)
+      if (c0 + v < C) ws[(size_t)blockIdx.x * C + c0 + v] = s1[v];
+  }
+}
+}  // namespace
+
+int launch_colsum(const void* x, int dtype, long long ld, long long rows, int C, const float* rs, int rs_div, float* out, float* ws,
+                  long long ws_elems, cudaStream_t s) {
+  CENET_DISPATCH(dtype, T, {
+    int Vv = pick_vec({C, ld});
+    long long al = ptr_align_elems(x, sizeof(T));
+    while (Vv > al) Vv >>= 1;
+    if (sizeof(T) == 4 && Vv > 4) Vv = 4;
+    ColPlan p = plan_cols(rows, C, Vv);
+    CENET_REQUIRE((long long)p.nrb * C <= ws_elems, "colsum: workspace too small");
+    if (Vv == 8) colsum_partial_kernel<T, 8><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>((const T*)x, ld, rows, C, rs, rs_div, p.ngrp, p.nrl, p.rows_per_block, ws);
+    else if (Vv == 4) colsum_partial_kernel<T, 4><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>((const T*)x, ld, rows, C, rs, rs_div, p.ngrp, p.nrl, p.rows_per_block, ws);
+    else if (Vv == 2) colsum_partial_kernel<T, 2><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>((const T*)x, ld, rows, C, rs, rs_div, p.ngrp, p.nrl, p.rows_per_block, ws);
+    else colsum_partial_kernel<T, 1><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>((const T*)x, ld, rows, C, rs, rs_div, p.ngrp, p.nrl, p.rows_per_block, ws);
+    CENET_LAUNCH_CHECK("colsum_partial");
+    return launch_finalize(ws, p.nrb, C, out, C, nullptr, 1.f, s);
+  });
+  return 0;
+}
+
+extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M,
+                                int N, int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias,
+                                int bias_unscaled, float* ws, long long ws_elems, cenet_stream_t st) {
+  CENET_REQUIRE(dy && x && dw && ws, "cenet_gemm_wgrad: null pointer");
+  CENET_REQUIRE(M > 0 && N > 0 && K > 0 && T >= 1 && K % T == 0, "cenet_gemm_wgrad: bad shape M=%lld N=%d K=%d T=%d", M, N, K, T);
+  CENET_REQUIRE(rs_div >= 1, "cenet_gemm_wgrad: rs_div must be >= 1");
+  cudaStream_t s = to_stream(st);
+  if (dbias) {
+    if (launch_colsum(dy, dy_dtype, ldy, M, N, bias_unscaled ? nullptr : row_scale, rs_div, dbias, ws, ws_elems, s)) return -1;
+  }
+  const long long nk = (long long)N * K;
+  CENET_REQUIRE(nk <= ws_elems, "cenet_gemm_wgrad: workspace too small (N*K = %lld)", nk);
+  int S;
+  if (dy_dtype == CENET_F32 && x_dtype == CENET_F32) {
+    // validation precision: CUDA-core GEMM  C_z[N,K] = A_z^T W_z  over row chunks, z = split
+    CENET_REQUIRE(row_scale == nullptr || rs_div >= 1, "cenet_gemm_wgrad");
+    S = 1;
+    for (int c = 2; c <= 64; c++)
+      if (M % c == 0 && (long long)c * nk <= ws_elems && M / c >= 64) S = c;
+    const long long chunk = M / S;
+    cenet_gemm_args g = {};
+    g.M = N; g.N = K; g.K = (int)chunk; g.batch = S; g.batch_inner = 1;
+    g.A = dy; g.a_dtype = dy_dtype; g.lda = ldy; g.a_bs_outer = chunk * ldy; g.a_mmajor = 1;
+    g.Wt = x; g.w_dtype = x_dtype; g.ldw = ldx; g.w_bs_outer = chunk * ldx; g.w_nmajor = 1;
+    g.C = ws; g.c_dtype = CENET_F32; g.ldc = K; g.c_bs_outer = nk;
+    g.alpha = 1.f; g.res1_scale = 1.f; g.rs_div = 1; g.post_rs_div = 1;
+    g.k_scale = row_scale; g.k_scale_div = rs_div; g.k_scale_bs = chunk;
+    if (cenet_gemm_simt(&g, s)) return -1;
+  } else {
+    const int ntiles = cdiv(N, TN) * cdiv(K, TK);
+    long long want = cdiv(3 * kNumSMs, ntiles);
+    long long maxs = std::max<long long>(1, M / 256);
+    if (want > maxs) want = maxs;
+    if (want * nk > ws_elems) want = ws_elems / nk;
+    if (want > 65535) want = 65535;
+    if (want < 1) want = 1;
+    WgParams p;
+    p.dy = dy; p.dy_dtype = dy_dtype; p.ldy = ldy; p.x = x; p.x_dtype = x_dtype; p.ldx = ldx;
+    p.M = M; p.N = N; p.K = K; p.rs = row_scale; p.rs_div = rs_div;
+    p.m_per_split = ((M + want - 1) / want + TM - 1) / TM * TM;
+    S = (int)((M + p.m_per_split - 1) / p.m_per_split);
+    p.ws = ws;
+    p.fast_y = dy_dtype == CENET_BF16 && ldy % 8 == 0 && ((uintptr_t)dy & 15) == 0;
+    p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
+    dim3 grid(cdiv(N, TN), cdiv(K, TK), S);
+    CENET_REQUIRE(grid.y <= 65535, "cenet_gemm_wgrad: K too large");
+    wgrad_mma_kernel<<<grid, WG_THREADS, 0, s>>>(p);
+    CENET_LAUNCH_CHECK("wgrad_mma");
+  }
+  wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, S, N, K, T, dw);
+  CENET_LAUNCH_CHECK("wgrad_finalize");
+  return 0;
+}

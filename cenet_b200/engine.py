@@ -657,8 +657,3 @@ class Engine:
         finally:
             ops = real
         return {k: (t / steps, n // steps) for k, (t, n) in timed.summary().items()}
-
-    def forward_train(self, x):
-        raise NotImplementedError(
-            "cenet_b200: the training path (batch-statistics BatchNorm, DropPath, hand-written backward kernels) is "
-            "not built yet; call .eval() for inference.  There is deliberately no autograd / PyTorch fallback.")

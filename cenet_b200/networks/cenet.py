@@ -268,6 +268,27 @@ def _out_head(dec_ch, x_ch, ncls, merge_mode, up_block, up_ks):
     return o
 
 
+class _TrainForward(torch.autograd.Function):
+    """autograd boundary of the hand-written training path: `net(x)` in train() mode returns logits whose backward runs
+    the recorded backward kernels of cenet_b200.train.TrainEngine and hands the parameter gradients to autograd, so the
+    reference loop (`loss = criterion(net(x), y); loss.backward(); optimizer.step()`, main_acdc.py:250-262) runs unchanged."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        eng = module.train_engine(x.device)
+        ctx.eng = eng
+        ctx.names = [n for n, _ in module.named_parameters()]
+        ctx.needs = [p.requires_grad for p in params]
+        return eng.forward_logits(x).clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng = ctx.eng
+        eng.backward_from(dlogits.contiguous())
+        grads = tuple(eng.GP[n].clone() if need else None for n, need in zip(ctx.names, ctx.needs))
+        return (None, None) + grads
+
+
 class CENet(nn.Module):
     """Same constructor as the reference `networks.CENet` (net.py:9-22)."""
 
@@ -329,12 +350,27 @@ class CENet(nn.Module):
             eng = self._engines[key] = Engine(self, x.device, key[1])
         return eng
 
+    def train_engine(self, device=None, precision=None):
+        """The training launch plan of this module on `device` (cenet_b200.train.TrainEngine); created on first use.
+        It moves the parameters into one flat fp32 buffer (they stay ordinary nn.Parameters, now views)."""
+        from ..engine import Engine
+        from ..train import TrainEngine
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        key = ("train", dev, precision or Engine.default_precision())
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = TrainEngine(self, dev, key[2])
+        return eng
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("cenet_b200.CENet has no CPU path: move the module and the input to a B200 "
                                "(`.cuda()`); the CPU oracle lives in oracle/ and is test-only")
-        if self.training or (torch.is_grad_enabled() and x.requires_grad):
-            return self._engine(x).forward_train(x)
+        if self.training:
+            if torch.is_grad_enabled():
+                params = [p for p in self.parameters()]
+                return _TrainForward.apply(self, x, *params)
+            return self.train_engine(x.device).forward_logits(x).clone()
         return self._engine(x).forward(x)
 
     @torch.no_grad()

@@ -36,7 +36,7 @@ from .engine import _MCA_RATES, _PVT, _rup, lambda_init
 from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT
 from .train_ops import ACT_GELU_GRAD
 
-FLASH_DIMS = {(8, 16), (16, 32), (32, 64), (64, 64), (128, 128)}       # (dqk, dv) instantiated in attn_train.cu
+FLASH_DIMS = {(8, 16), (16, 32), (32, 64), (64, 64)}       # (dqk, dv) instantiated in train_attn.cu
 
 
 class TrainEngine:
@@ -989,6 +989,32 @@ class TrainEngine:
             tops.adamw(self.pflat, self.gflat, self.adam_m, self.adam_v, self.n_flat, self.hyper)
 
     grad_hook = None
+
+    # ---- autograd-boundary entry points (eager; used by networks.CENet.forward in train() mode) -----------------------
+    def forward_logits(self, x):
+        """train-mode forward; returns the engine-owned logits buffer [B,ncls,H,W] (valid until the next call)"""
+        if x.device != self.dev:
+            raise RuntimeError(f"input on {x.device}, engine on {self.dev}")
+        if x.dim() != 4 or x.shape[1] != self.cfg["input_channels"]:
+            raise ValueError(f"expected [B,{self.cfg['input_channels']},H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 32 or W % 32:
+            raise ValueError("H and W must be multiples of 32")
+        self._plan_key = (B, H, W)
+        x_in = self.buf("x_in", (B, x.shape[1], H, W), torch.float32)
+        x_in.copy_(x.detach().float())
+        self.pack()
+        logits = self.buf("logits", (B, self.cfg["num_classes"], H, W), torch.float32)
+        self.forward(x_in, B, H, W, logits)
+        self._last_logits = logits
+        return logits
+
+    def backward_from(self, dlogits):
+        """run the recorded backward with d(loss)/d(logits); parameter gradients land in self.GP / self.gflat"""
+        logits = self._last_logits
+        self._plan_key = (logits.shape[0], logits.shape[2], logits.shape[3])
+        self.G(logits).copy_(dlogits)
+        self.backward(logits)
 
     def train_step(self, x, labels, *, w_dice=0.5, w_ce=0.5, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4,
                    optimize=True):

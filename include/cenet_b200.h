@@ -28,7 +28,7 @@ typedef void* cenet_stream_t; /* cudaStream_t */
 
 enum { CENET_F32 = 0, CENET_BF16 = 1 };
 enum { CENET_ACT_NONE = 0, CENET_ACT_GELU = 1, CENET_ACT_RELU = 2, CENET_ACT_LEAKY = 3, CENET_ACT_SILU = 4,
-       CENET_ACT_SIGMOID = 5 };
+       CENET_ACT_SIGMOID = 5, CENET_ACT_GELU_GRAD = 6 /* d gelu(v)/dv: `mul_act` of training dgrad GEMMs */ };
 enum { CENET_GEMM_AUTO = -1, CENET_GEMM_SIMT = 0, CENET_GEMM_TCGEN05 = 1 };
 
 /* ---- library ---------------------------------------------------------------------------------------- */
@@ -64,6 +64,11 @@ typedef struct {
   const void* res2; int res2_dtype; long long ldr2;
   const void* mul; int mul_dtype; long long ldmul; int mul_act;
   int impl;
+  /* training extensions; all-zero == inference behaviour */
+  int a_mmajor;                       /* A is stored [K, M] (element (m,k) at A[k*lda + m]); CUDA-core path only */
+  int rs_div;                         /* row_scale index is m / rs_div (0 -> 1) */
+  const float* post_row_scale; int post_rs_div; /* v *= post_row_scale[m / post_rs_div] after bias/act/mul, before the residuals */
+  const float* k_scale; int k_scale_div; long long k_scale_bs; /* A[m,k] *= k_scale[(z*k_scale_bs + k) / k_scale_div]; CUDA-core path */
 } cenet_gemm_args;
 int cenet_gemm(const cenet_gemm_args* a, cenet_stream_t s);
 
@@ -182,6 +187,127 @@ int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* la
 int cenet_loss_nblocks(long long npix);
 int cenet_dice_ce(const float* logits, const long long* labels, float* loss_out, float* dlogits, float* ws, int B,
                   int ncls, int HW, float w_dice, float w_ce, float grad_scale, cenet_stream_t s);
+
+/* ================================================================================================================
+ * TRAINING entry points: train-mode forward pieces and the hand-written backward of every op on the path
+ * (the reference gets these from autograd; main_acdc.py:234-265 `loss.backward(); optimizer.step()`).
+ * Conventions: `ld*` row pitches in elements; pointers are pre-offset to the first element of a channel slice;
+ * `acc` / `acc_*` != 0 means "add to the destination" (gradient fan-in); `ws`/`ws_elems` is caller-owned fp32 scratch for
+ * the two-stage deterministic reductions (no float atomics anywhere).  Parameter gradients are fp32 in the reference's
+ * parameter layout.
+ * ================================================================================================================ */
+
+/* depthwise 3x3 forward that also stores the pre-activation z (contiguous [B,H,W,C], dtype of y) for the backward */
+int cenet_dwconv3x3_train(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, void* zout,
+                          const float* w9c, const float* bias, int B, int H, int W, int C, int dil, int act, int z_dtype,
+                          float slope, cenet_stream_t s);
+/* weight gradient of nn.Linear / 1x1 / dense conv:  dw[n, ci, t] = sum_m rs[m/rs_div] dy[m,n] x[m, t*Cin + ci], K = T*Cin
+ * (T = KH*KW taps of an im2col'ed conv, 1 otherwise); dbias[n] = sum_m (rs) dy[m,n] (nullable; bias_unscaled: without rs).
+ * bf16 operands: mma.sync tensor-core kernel with ldmatrix.trans staging, split over m; fp32 x fp32: CUDA cores. */
+int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
+                     int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias, int bias_unscaled, float* ws,
+                     long long ws_elems, cenet_stream_t s);
+/* LayerNorm backward (pvtv2.py:146-147,189,320): dx (+)= ..., dgamma, dbeta; statistics are recomputed from x.  C in {64,128,320,512} */
+int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, const float* gamma, float eps, long long rows, int C, void* dx,
+                        int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems, cenet_stream_t s);
+/* train-mode BatchNorm statistics of x[rows, C]: mean, rstd (biased var), scale = gamma*rstd, shift = beta - mean*scale; updates
+ * running_mean / running_var (unbiased) with `momentum` and increments num_batches_tracked (all nullable) */
+int cenet_bn_stats(const void* x, int x_dtype, long long ldx, long long rows, int C, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps, float* scale,
+                   float* shift, float* mean, float* rstd, float* ws, long long ws_elems, cenet_stream_t s);
+/* out = act( a*sa+ta [+ (sb ? b*sb+tb : b)] )  -- BatchNorm apply (+ residual branch of UnetResBlock, unet.py:201-214) */
+int cenet_affine_act(const void* a, int a_dtype, long long lda, const float* sa, const float* ta, const void* b, int b_dtype,
+                     long long ldb, const float* sb, const float* tb, void* out, int o_dtype, long long ldo, long long rows, int C,
+                     int act, float slope, cenet_stream_t s);
+/* backward of y = act(BN_train(a) [+ other]): g = dy*act'(y) (act in NONE/RELU/LEAKY; y nullable for NONE);
+ * da (+)= gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)); dgamma, dbeta; optional dres (+)= g for the residual operand.
+ * dy and y share (ldy); a and da share (lda). */
+int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_dtype, long long ldy, const void* a, int a_dtype, long long lda,
+                 const float* mean, const float* rstd, const float* gamma, long long rows, int C, int act, float slope, void* da,
+                 int da_dtype, int acc_da, float* dgamma, float* dbeta, void* dres, int dres_dtype, long long lddres, int acc_dres,
+                 float* ws, long long ws_elems, cenet_stream_t s);
+/* filter / bias gradient of the depthwise 3x3 family: dw [C,1,3,3], dbias [C] (nullable); x as in cenet_dwconv3x3 (up2) */
+int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, const void* dz, int dz_dtype, long long ldz, int B, int H, int W,
+                          int C, int dil, int up2, float* dw, float* dbias, float* ws, long long ws_elems, cenet_stream_t s);
+/* y[b,h,w,c] (+)= sum of the 2x2 block of x[b,2h..,2w..,c]  (adjoint of nearest x2, blocks.py:304) */
+int cenet_sumpool2(const void* x, int x_dtype, void* y, int y_dtype, int B, int Ho, int Wo, int C, int acc, cenet_stream_t s);
+/* adjoint of cenet_im2col: dx[b,h,w,ci] (+)= sum over the taps that read it */
+int cenet_col2im(const void* dcol, int c_dtype, void* dx, int x_dtype, int B, int H, int W, int Cin, int k, int stride, int pad, int Ho,
+                 int Wo, int Kpad, int acc, cenet_stream_t s);
+/* flash attention with saved log2-sum-exp (bf16): O[:, m*dv..] = softmax(scale Q_m K_m^T) V_{m/vdiv}; lse [B,maps,Nq].
+ * (dqk, dv) in {(8,16),(16,32),(32,64),(64,64)}.  Serves pvtv2.py:88-105, nlb.py:116-137, multihead_diffattn.py:92-116. */
+int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O, long long ldo,
+                    float* lse, int B, int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
+/* its backward: delta = rowsum(dO*O) (workspace [B,maps,Nq]); dQ, dK, dV written with the layouts of Q, K, V (no atomics) */
+int cenet_flash_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,
+                    const void* dO, long long ldo, const float* lse, float* delta, void* dQ, void* dK, void* dV, int B, int maps,
+                    int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
+/* materialised attention backward: dP <- P * (dP - rowsum(P*dP)) in place, rows of length n */
+int cenet_softmax_bwd_rows(const void* P, void* dP, int dtype, long long rows, int n, cenet_stream_t s);
+/* lambda = exp(q1.k1) - exp(q2.k2) + lambda_init on the device (multihead_diffattn.py:110-112) and its backward */
+int cenet_lambda_fwd(const float* q1, const float* k1, const float* q2, const float* k2, int hd, float lambda_init, float* lam,
+                     cenet_stream_t s);
+int cenet_lambda_bwd(const float* dlam, const float* q1, const float* k1, const float* q2, const float* k2, int hd, float* g_q1,
+                     float* g_k1, float* g_q2, float* g_k2, cenet_stream_t s);
+/* o[r, h*seg..] = mult * RMSNorm_seg( Om[r, 2h*seg..] - lam * Om[r, (2h+1)*seg..] )  (multihead_diffattn.py:115-123) + backward */
+int cenet_diff_rmsnorm_fwd(const void* Om, int dtype, const float* lam, void* o, long long rows, int heads, int seg, float eps,
+                           float mult, cenet_stream_t s);
+int cenet_diff_rmsnorm_bwd(const void* dO, const void* Om, int dtype, const float* lam, void* dOm, float* dlam, long long rows,
+                           int heads, int seg, float eps, float mult, float* ws, long long ws_elems, cenet_stream_t s);
+/* backward of cenet_fea_combine: dy (+)=, dgate =, dw[c]; mats [nscales][2][nmax][nmax] = per-axis operators Up_s Down_s */
+int cenet_fea_bwd(const void* y, const void* gate, const void* dz, int dtype, const float* w, void* dy, int acc_dy, void* dgate,
+                  float* dw, int B, int C2, int H, int W, const float* mats, int nmax, int nscales, float* ws, long long ws_elems,
+                  cenet_stream_t s);
+/* out_nhwc[b,hw,c] (+)= x_nchw[b, coff+c, hw] */
+int cenet_nchw_to_nhwc_slice(const void* x, int dtype, void* out, int B, int HW, int C, int Ctot, int coff, int acc, cenet_stream_t s);
+/* dst (+)= src */
+int cenet_add(void* dst, const void* src, int dtype, long long n, int acc, cenet_stream_t s);
+/* CCU in train mode (cfam.py:251-264): stats u[B,C,3] = (max, mean, biased std) + arg max; the per-channel MLP with batch-statistics
+ * BatchNorm1d over B (gamma == NULL: skipped, the reference's B == 1 case); and the three backward pieces */
+int cenet_ccu_stats(const void* xb, int dtype, float* u, int* arg, int B, int HW, int C, float* ws, long long ws_elems, cenet_stream_t s);
+int cenet_ccu_mlp_fwd(const float* u, const float* fc1, const float* fc2, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long* nbt, float momentum, float eps, float* gate, float* save_bc8, int B, int C,
+                      cenet_stream_t s);
+int cenet_ccu_dgate(const void* dx1, const void* xb, int dtype, float* dgate, int B, int HW, int C, float* ws, long long ws_elems,
+                    cenet_stream_t s);
+int cenet_ccu_mlp_bwd(const float* dgate, const float* u, const float* fc1, const float* fc2, const float* gamma, const float* beta,
+                      const float* save_bc8, float* du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C,
+                      cenet_stream_t s);
+int cenet_ccu_apply_bwd(const void* dx1, const void* xb, int dtype, const float* gate, const float* u, const int* arg, const float* du,
+                        void* dxb, int acc, int B, int HW, int C, cenet_stream_t s);
+/* SRM in train mode (cfam.py:93-101): per-pixel (max, mean, unbiased std) + arg max; gate with batch-statistics BN(1); backward */
+int cenet_row_stats_arg(const void* x, int dtype, float* u, int* arg, long long rows, int C, cenet_stream_t s);
+int cenet_srm_fwd(const float* u, const float* pw, const float* dw, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, long long* nbt, float momentum, float eps, float* gm, float* save_m2, float* st, int B, int H,
+                  int W, float* ws, long long ws_elems, cenet_stream_t s);
+int cenet_row_dot(const void* a, const void* b, int dtype, float* out, long long rows, int C, cenet_stream_t s);
+int cenet_srm_bwd(const float* dgm, const float* u, const float* gm, float* save_m2, const float* st, const float* pw, const float* dw,
+                  const float* gamma, const float* beta, float* du, float* dpw, float* ddw, float* dgamma, float* dbeta, int B, int H,
+                  int W, float* ws, long long ws_elems, cenet_stream_t s);
+int cenet_srm_apply_bwd(const void* dh3, const void* h2, const void* z, int dtype, const float* gm, const float* u, const int* arg,
+                        const float* du, void* dz, long long rows, int C, cenet_stream_t s);
+/* SiLU(g)*SiLU(v) (cfam.py:303-304) and backward */
+int cenet_silu_mul_fwd(const void* g, const void* v, void* out, int dtype, long long n, cenet_stream_t s);
+int cenet_silu_mul_bwd(const void* dout, const void* g, const void* v, void* dg, void* dv, int dtype, long long n, cenet_stream_t s);
+/* out = x + ls[c] * (y ? (1-w) y + w pz : pz), pz = s ? p*s[c]+t[c] : p   (layer scale + non-local mix, cfam.py:369,373; nlb.py:145-148)
+ * backward: dy (+)= , dp = d(pz), dls[c], dw (scalar); d(x) is the incoming gradient itself (the caller aliases the buffers) */
+int cenet_ls_combine_fwd(const void* x, const void* y, const void* p, int dtype, const float* s, const float* t, const float* ls,
+                         const float* w, void* out, long long rows, int C, cenet_stream_t st);
+int cenet_ls_combine_bwd(const void* dout, const void* y, const void* p, int dtype, const float* s, const float* t, const float* ls,
+                         const float* w, void* dy, int acc_dy, void* dp, float* dls, float* dw, long long rows, int C, float* ws,
+                         long long ws_elems, cenet_stream_t st);
+/* sparse separable resampling with CSR tap tables per axis (start[No+1], idx[nnz], weight[nnz]): adaptive average pooling, bilinear
+ * up-sampling and their adjoints */
+int cenet_resample(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int B, int Hi, int Wi, int Ho, int Wo,
+                   int C, const int* h_start, const int* h_idx, const float* h_w, const int* w_start, const int* w_idx, const float* w_w,
+                   int acc, cenet_stream_t s);
+/* backward of cenet_maxpool2_scale: drb (first arg max of each window), dw[c] */
+int cenet_maxpool2_scale_bwd(const void* dz, int dtype, long long lddz, const void* rb, int rb_dtype, const float* w, void* drb, float* dw,
+                             int B, int H, int W, int C, float* ws, long long ws_elems, cenet_stream_t s);
+/* adjoint of the head's bilinear x2: dlogits [B,ncls,2h,2w] fp32 -> dyh [B,h,w,ncls] fp32 */
+int cenet_head_upsample_bwd(const float* dlogits, float* dyh, int B, int h, int w, int ncls, cenet_stream_t s);
+/* AdamW over the flat fp32 parameter buffer; hyper (device) = [lr, beta1, beta2, eps, weight_decay, step] (utils/core.py:16-18) */
+int cenet_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, cenet_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -3,8 +3,6 @@ import sys, os
 ROOT = "/root/repo"
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, fake_ops, fake_train_ops
-import cenet_b200._lib as L
-L.load = lambda: None
 import cenet_b200.train as T
 T.ops, T.tops = fake_ops, fake_train_ops
 from cenet_b200.networks import CENet
