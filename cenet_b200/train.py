@@ -69,11 +69,25 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------------ parameters
     def _flatten(self):
         """Move every parameter into one flat fp32 buffer (the module's Parameters become views) + a flat grad buffer."""
-        named = [(n, p) for n, p in self.mod.named_parameters()]
+        # flat order = groups in the order their gradients complete LAST-to-FIRST reversed: encoder stage 1..4, decoder,
+        # head.  The backward pass finishes them head -> decoder -> stage 4 .. 1, so each group is one contiguous
+        # all-reduce bucket that can be launched as soon as its backward closures have run (see _bucket_ready).
+        def group(n):
+            if n.startswith("backbone."):
+                for s_ in range(1, 5):
+                    if n.startswith((f"backbone.patch_embed{s_}.", f"backbone.block{s_}.", f"backbone.norm{s_}.")):
+                        return s_ - 1
+                raise KeyError(n)
+            return 4 if n.startswith("decoder.") else 5
+        named = sorted(((n, p) for n, p in self.mod.named_parameters()), key=lambda np_: group(np_[0]))
         offs, tot = {}, 0
+        self.bucket_ranges = {}
         for n, p in named:
             offs[n] = tot
+            g_ = group(n)
             tot += _rup(p.numel(), 4)                                   # 16-byte aligned starts
+            lo, _hi = self.bucket_ranges.get(g_, (offs[n], 0))
+            self.bucket_ranges[g_] = (lo, tot)
         self.pflat = torch.zeros(tot, device=self.dev, dtype=torch.float32)
         self.gflat = torch.zeros(tot, device=self.dev, dtype=torch.float32)
         self.P, self.GP = {}, {}
@@ -478,6 +492,7 @@ class TrainEngine:
         dp_i = 0
         for s in range(4):
             ops.tag = f"enc{s+1}"
+            self._mark_bucket(s)
             Cc, heads, sr = _PVT["embed_dims"][s], _PVT["heads"][s], _PVT["sr_ratios"][s]
             hid = Cc * _PVT["mlp_ratios"][s]
             k, st = (7, 4) if s == 0 else (3, 2)
@@ -885,6 +900,7 @@ class TrainEngine:
             ops.nchw_to_nhwc(x_in, xc, B, H * W, Cin)
         feats = self._encoder(xc, B, H, W, Cin)
         (x1, H1, W1, C1), (x2, H2, W2, C2), (x3, H3, W3, C3), (x4, H4, W4, C4) = feats
+        self._mark_bucket(4)
         d = self._cfam(x4, B, H4, W4, C4, "decoder.dec4", "dec4")
         heads = cfg["diffatt_num_heads"]
         for lvl, (sk, Hs, Ws, Cs, ), hi, Cprev, depth in ((3, feats[2], 0, C4, 4), (2, feats[1], 1, C3, 3), (1, feats[0], 2, C2, 2)):
@@ -896,6 +912,7 @@ class TrainEngine:
         om = C1 // 2
         Hh, Wh = H // 2, W // 2
         Mf, Mh = B * H * W, B * Hh * Wh
+        self._mark_bucket(5)
         ops.tag = "head.rb"
         o1raw = self.buf("head.rb.o1raw", (B, H, W, om))
         rraw = self.buf("head.rb.rraw", (Mf, om))
@@ -970,11 +987,21 @@ class TrainEngine:
         self._sample_drop_path(B)
         self._run_forward(x_in, B, H, W, logits)
 
+    def _mark_bucket(self, g_):
+        """tape marker: when the backward pass reaches it, every parameter gradient of group g_ is final"""
+        self.tape.append(("bucket", g_))
+
     def backward(self, logits):
         """d(logits) must already be in G(logits)."""
         self.wr(logits)
         for fn in reversed(self.tape):
+            if isinstance(fn, tuple):
+                if self.on_bucket is not None:
+                    self.on_bucket(fn[1])
+                continue
             fn()
+
+    on_bucket = None        # callable(group) -> launches the gradient all-reduce of that bucket (see replicas.py)
 
     def _step_body(self, x_in, labels, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, wd, optimize):
         self.pack()
@@ -989,6 +1016,44 @@ class TrainEngine:
             tops.adamw(self.pflat, self.gflat, self.adam_m, self.adam_v, self.n_flat, self.hyper)
 
     grad_hook = None
+
+    def _capture(self, args):
+        """Capture one step as CUDA graph segments.  Without gradient synchronisation it is a single graph; with it
+        (on_bucket / grad_hook set by replicas.GradSync) the capture is cut at every bucket marker so that the NCCL
+        all-reduces are issued eagerly BETWEEN graph replays and overlap with the next backward segment."""
+        segs = []
+        pool = torch.cuda.graph_pool_handle()
+        cur = {}
+        self._user_on_bucket, self._user_grad_hook = self.on_bucket, self.grad_hook
+
+        def begin():
+            cur["g"] = torch.cuda.CUDAGraph()
+            cur["g"].capture_begin(pool=pool)
+
+        def end():
+            cur["g"].capture_end()
+            segs.append(("graph", cur["g"]))
+
+        def cut_bucket(g_):
+            end(); segs.append(("bucket", g_)); begin()
+
+        def cut_hook(_gflat):
+            end(); segs.append(("hook", None)); begin()
+        if self._user_on_bucket is not None:
+            self.on_bucket = cut_bucket
+        if self._user_grad_hook is not None:
+            self.grad_hook = cut_hook
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                begin()
+                self._step_body(*args)
+                end()
+        finally:
+            self.on_bucket, self.grad_hook = self._user_on_bucket, self._user_grad_hook
+        torch.cuda.current_stream().wait_stream(side)
+        return segs
 
     # ---- autograd-boundary entry points (eager; used by networks.CENet.forward in train() mode) -----------------------
     def forward_logits(self, x):
@@ -1039,17 +1104,20 @@ class TrainEngine:
         key = (B, H, W, optimize, w_dice, w_ce)
         if not self.use_graph or self.taps is not None or self.dev.type != "cuda":
             self._step_body(*args)
-        else:
-            g = self._graphs.get(key)
-            if g is None:
-                n0 = ops.launch_count()
-                self._step_body(*args)                                # eager warm-up step (allocates every buffer)
-                self.launches_per_step = ops.launch_count() - n0
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_body(*args)
-                self._graphs[key] = g
-                return loss_out                                       # the warm-up step WAS this iteration
-            g.replay()
+            return loss_out
+        segs = self._graphs.get(key)
+        if segs is None:
+            n0 = ops.launch_count()
+            self._step_body(*args)                                    # eager warm-up step (allocates every buffer)
+            self.launches_per_step = ops.launch_count() - n0
+            torch.cuda.current_stream().synchronize()
+            self._graphs[key] = self._capture(args)
+            return loss_out                                           # the warm-up step WAS this iteration
+        for kind, what in segs:
+            if kind == "graph":
+                what.replay()
+            elif kind == "bucket":
+                self._user_on_bucket(what)
+            else:
+                self._user_grad_hook(self.gflat)
         return loss_out
