@@ -16,6 +16,8 @@ the fused softmax/argmax -> int64 label map.  A step = one forward pass over one
   roofline : dominant kernel (differential flash attention of the 56x56 DSE block) timed live with CUDA events in
           an eager pass; achieved = algorithmic FLOPs / duration against the measured bf16 peak.
   cpu_baseline : the oracle (CPU port of the reference) on this box's host cores, bounded sample, rank 0 only.
+  train    : second half of BASELINE.json's metric -- training images/s on configs[2] (ACDC, batch 24 per GPU, Dice+CE, AdamW),
+          same timing protocol; under torchrun the gradients are all-reduced over NCCL in 6 buckets overlapped with backward.
 """
 from __future__ import annotations
 
@@ -31,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIG_NAME = "synapse"
+TRAIN_CONFIG = "acdc"
+TRAIN_BATCH = 24
 BATCH = 64
 SIZE = 224
 METRIC = "slices_per_s_infer_224"
@@ -147,7 +151,98 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def cpu_oracle_train_throughput(sample_batch, steps):
+    """One training iteration (forward, Dice+CE, autograd backward, AdamW) of the oracle port on the host cores."""
+    import contextlib
+    import torch
+    from cenet_b200.networks import CENet
+    from oracle import cenet_oracle as O
+    from oracle import fixtures
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = fixtures.CONFIGS[TRAIN_CONFIG]
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(sys.stderr):
+        sd = fixtures.perturb_state(CENet(**kw).state_dict(), 1234)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.AdamW([leaf[k] for k in names], lr=1e-4, weight_decay=1e-4)
+    x = fixtures.synth_input(TRAIN_CONFIG, sample_batch, SIZE)
+    y = torch.randint(0, kw["num_classes"], (sample_batch, SIZE, SIZE), generator=torch.Generator().manual_seed(5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = O.criterion_dice_ce(O.cenet_forward(leaf, O.Cfg(**kw), x, training=True), y, kw["num_classes"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    dt = time.perf_counter() - t0
+    return sample_batch * steps / dt, dt / steps * 1e3, cores
+
+
 # ---------------------------------------------------------------------------------------------------- product arm
+def run_train_leg(args, dev, world, rank, flush):
+    """BASELINE.json configs[2]: ACDC 4-class training step (Dice+CE 0.5/0.5, AdamW lr 1e-4 wd 1e-4), 224x224, batch 24 per
+    GPU, train-mode BatchNorm + DropPath, bf16 activations / fp32 master weights.  A step = forward, fused loss, backward,
+    gradient all-reduce (N > 1), AdamW -- all hand-written kernels, replayed from CUDA graph segments."""
+    import contextlib
+    import torch
+    from cenet_b200 import ops, replicas
+    from cenet_b200.networks import CENet
+    from oracle import fixtures
+    kw = fixtures.CONFIGS[TRAIN_CONFIG]
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(sys.stderr):
+        m = CENet(**kw)
+    m.load_state_dict(fixtures.perturb_state(m.state_dict(), 1234))
+    m = m.to(dev).train()
+    eng = m.train_engine(dev)
+    sync = replicas.GradSync(eng) if world > 1 else None
+    x_host = fixtures.synth_input(TRAIN_CONFIG, TRAIN_BATCH, SIZE, seed=100 + rank).pin_memory()
+    y_host = torch.randint(0, kw["num_classes"], (TRAIN_BATCH, SIZE, SIZE), generator=torch.Generator().manual_seed(200 + rank)).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    loss_host = torch.zeros(1 + kw["num_classes"]).pin_memory()
+    n0 = ops.launch_count()
+    for _ in range(max(args.warmup, 3)):
+        eng.train_step(x_dev, y_dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    replicas.barrier(dev)
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        loss = eng.train_step(x_dev, y_dev)
+        e1.record()
+    replicas.barrier(dev)
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    replicas.barrier(dev)
+    for e0, e1 in ev2:
+        flush.zero_()
+        e0.record()
+        xd = x_host.to(dev, non_blocking=True)              # H2D of this step's images and label maps (pinned)
+        yd = y_host.to(dev, non_blocking=True)
+        loss = eng.train_step(xd, yd)                       # public call
+        loss_host.copy_(loss, non_blocking=True)            # D2H of the loss + per-class dice
+        e1.record()
+    replicas.barrier(dev)
+    t_e2e = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
+    t_dev, t_e2e = replicas.max_over_ranks([t_dev, t_e2e], device=dev)
+    torch.cuda.synchronize(dev)
+    return {
+        "metric": "train_imgs_per_s_224", "unit": "img/s",
+        "value": replicas.job_throughput(TRAIN_BATCH, args.steps, t_dev), "ms_per_step": t_dev / args.steps,
+        "e2e": {"value": replicas.job_throughput(TRAIN_BATCH, args.steps, t_e2e), "unit": "img/s",
+                "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": loss_host.numel() * 4,
+                "ms_per_step": t_e2e / args.steps},
+        "config": {"workload": f"CENet (PVTv2-b2) ACDC 4-class training step {SIZE}x{SIZE}, batch {TRAIN_BATCH} per GPU, Dice+CE, AdamW, "
+                               "train-mode BatchNorm, DropPath on", "batch_per_gpu": TRAIN_BATCH, "l2": "flushed between steps",
+                   "cuda_graph": bool(eng.use_graph), "flops_per_image": 76.0e9,
+                   "parallelism": f"dp{world} (gradient all-reduce in 6 buckets overlapped with backward)" if world > 1 else "dp1"},
+        "dtype": "bf16", "launches_per_step": int(eng.launches_per_step or 0),
+        "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(loss_host[0]),
+        "model_tflops": 76.0e9 * TRAIN_BATCH * world / (t_dev / args.steps / 1e3) / 1e12,
+    }
+
+
 def diffattn_flops(N, E, B):
     """Algorithmic FLOPs of the differential attention core: QK^T + PV over 2h maps = 4*N^2*E per image."""
     return 4.0 * N * N * E * B
@@ -214,6 +309,9 @@ def run_product(args):
     t_e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
 
     t_dev_ms, t_e2e_ms = replicas.max_over_ranks([t_dev_ms, t_e2e_ms], device=dev)
+    train = None
+    if not args.no_train:
+        train = run_train_leg(args, dev, world, rank, flush)
 
     if rank == 0:
         peaks = _peaks()
@@ -248,7 +346,7 @@ def run_product(args):
                        "cuda_graph": bool(eng.use_graph), "parallelism": f"replicas x{world} (batch-sharded, no collective)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": labels_host.numel() * 8, "ms_per_step": t_e2e_ms / args.steps},
-            "gpu_launches": int(launches_per_step * args.steps * 2 + launches_per_step * 2),
+            "gpu_launches": int(launches_per_step * args.steps * 2 + launches_per_step * 2) + (train["gpu_launches"] if train else 0),
             "launches_per_step": int(launches_per_step),
             "clocks": clocks.summary(),
             "roofline": roof,
@@ -257,7 +355,12 @@ def run_product(args):
             "op_breakdown_ms": {f"{op}@{tag}": round(ms, 4) for (op, tag), (ms, n) in top},
             "op_family_ms": {op: round(v[0], 4) for op, v in sorted(by_op.items(), key=lambda kv: -kv[1][0])},
             "eager_step_ms": total_ms,
+            "train": train,
         }
+        if train is not None and not args.no_cpu_train:
+            tv, tms, tc = cpu_oracle_train_throughput(2, 1)
+            line["train"]["cpu_baseline"] = {"value": tv, "unit": "img/s", "cores": tc, "kind": "port",
+                                             "sample": "oracle port + autograd + torch AdamW, 2 images/step x 1 step"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -270,6 +373,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
+    ap.add_argument("--no-cpu-train", action="store_true", help="skip the CPU training baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,7 +60,7 @@ class TrainEngine:
         self._g = {}                          # activation data_ptr -> gradient buffer
         self._galias = {}
         self._written = set()
-        self.tape = []
+        self.tape = TrainEngine._Tape()
         self._graphs = {}
         self.taps = None
         self.launches_per_step = None
@@ -967,7 +967,7 @@ class TrainEngine:
     # ------------------------------------------------------------------------------------------------ step
     def _begin(self, B, H, W):
         self._plan_key = (B, H, W)
-        self.tape = []
+        self.tape = TrainEngine._Tape()
         self._written = set()
         self._galias = {}
 
@@ -987,6 +987,12 @@ class TrainEngine:
         self._sample_drop_path(B)
         self._run_forward(x_in, B, H, W, logits)
 
+    class _Tape(list):
+        """backward closures with the profiling region label that was current when they were recorded"""
+
+        def append(self, fn):
+            list.append(self, fn if isinstance(fn, tuple) else (getattr(ops, "tag", ""), fn))
+
     def _mark_bucket(self, g_):
         """tape marker: when the backward pass reaches it, every parameter gradient of group g_ is final"""
         self.tape.append(("bucket", g_))
@@ -994,11 +1000,12 @@ class TrainEngine:
     def backward(self, logits):
         """d(logits) must already be in G(logits)."""
         self.wr(logits)
-        for fn in reversed(self.tape):
-            if isinstance(fn, tuple):
+        for tag, fn in reversed(self.tape):
+            if tag == "bucket":
                 if self.on_bucket is not None:
-                    self.on_bucket(fn[1])
+                    self.on_bucket(fn)
                 continue
+            ops.tag = tag + ".bwd"
             fn()
 
     on_bucket = None        # callable(group) -> launches the gradient all-reduce of that bucket (see replicas.py)

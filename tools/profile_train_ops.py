@@ -27,9 +27,15 @@ class Tagged(_TimedOps):
         if name in ("make_tables", "ACT_GELU_GRAD"):
             return getattr(self._inner, name)
         return super().__getattr__(name)
-t1, t2 = Tagged(real_ops), Tagged(real_tops)
-class TagProxy:
-    pass
+t1 = Tagged(real_ops)
+class Tagged2(Tagged):
+    @property
+    def tag(self):
+        return t1.tag
+    @tag.setter
+    def tag(self, v):
+        pass
+t2 = Tagged2(real_tops)
 T.ops, T.tops = t1, t2
 steps = 3
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -43,11 +49,18 @@ agg = {}
 for prox in (t1, t2):
     for (op, tag), (ms, n) in prox.summary().items():
         a = agg.setdefault(op, [0.0, 0]); a[0] += ms / steps; a[1] += n // steps
+fine = {}
+for prox in (t1, t2):
+    for (op, tag), (ms, n) in prox.summary().items():
+        fine[(op, tag)] = (ms / steps, n // steps)
 tot = sum(v[0] for v in agg.values())
 print(f"config {name} B={B} {prec}: eager step (events) {e0.elapsed_time(e1)/steps:.2f} ms; sum of op times {tot:.2f} ms; "
       f"{sum(v[1] for v in agg.values())} op calls")
 for op, (ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"{ms:8.3f} ms {100*ms/tot:5.1f}%  x{n:<4d} {op}")
+print("---- by (op, region), top 45")
+for (op, tag), (ms, n) in sorted(fine.items(), key=lambda kv: -kv[1][0])[:45]:
+    print(f"{ms:8.3f} ms {100*ms/tot:5.1f}%  x{n:<4d} {op}@{tag}")
 # graph replay timing
 eng.use_graph = True
 for _ in range(3):
