@@ -68,6 +68,7 @@ _SIGS = {
     # ---- training (see include/cenet_b200.h) ----
     "cenet_dwconv3x3_train": [vp, i32, ll, vp, i32, ll, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
     "cenet_gemm_wgrad": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, vp, vp, i32, vp, ll, vp],
+    "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
     "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
     "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, ll, vp],
     "cenet_affine_act": [vp, i32, ll, vp, vp, vp, i32, ll, vp, vp, vp, i32, ll, ll, i32, i32, f32, vp],
@@ -83,7 +84,7 @@ _SIGS = {
     "cenet_lambda_bwd": [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "cenet_diff_rmsnorm_fwd": [vp, i32, vp, vp, ll, i32, i32, f32, f32, vp],
     "cenet_diff_rmsnorm_bwd": [vp, vp, i32, vp, vp, vp, ll, i32, i32, f32, f32, vp, ll, vp],
-    "cenet_fea_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, ll, vp],
+    "cenet_fea_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, ll, vp],
     "cenet_nchw_to_nhwc_slice": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_add": [vp, vp, i32, ll, i32, vp],
     "cenet_ccu_stats": [vp, i32, vp, vp, i32, i32, i32, vp, ll, vp],

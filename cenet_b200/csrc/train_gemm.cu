@@ -8,6 +8,7 @@
 // cfam.py:150-157,301-303; dseb.py:164; unet.py:201-214; blocks.py:209-214; nlb.py:107-143).
 // fp32 x fp32 operands (validation precision) go through the CUDA-core GEMM with the same split / reduce.
 #include "train_common.cuh"
+#include <cstdlib>
 
 namespace {
 constexpr int TN = 64, TK = 64, TM = 64, PITCH = 72;      // +8 bf16 padding: conflict-free ldmatrix
@@ -21,6 +22,8 @@ struct WgParams {
   long long m_per_split;
   float* ws;                       // [S][N][K]
   int fast_y, fast_x;              // 16-byte vector loads allowed
+  // implicit im2col of the X operand (stride-1 "same" conv): x is the NHWC image, k = (tap, ci)
+  int conv, H, W, Cin, KS, pad;
 };
 
 __device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf16* p) {
@@ -58,6 +61,36 @@ __device__ __forceinline__ uint4 load_chunk(const void* base, int dtype, long lo
   return *reinterpret_cast<uint4*>(t);
 }
 
+// X chunk of an implicit-im2col operand: row m = output pixel (b, h, w), columns c..c+7 = tap t = c / Cin, channels c % Cin..
+__device__ __forceinline__ uint4 load_chunk_conv(const WgParams& p, long long m, long long M, int c) {
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (m >= M || c >= p.K) return u;
+  const int w = (int)(m % p.W);
+  const long long t2 = m / p.W;
+  const int h = (int)(t2 % p.H);
+  const long long b = t2 / p.H;
+  if (p.fast_x && (p.Cin & 7) == 0) {
+    const int t = c / p.Cin, ci = c - t * p.Cin;
+    const int hh = h + t / p.KS - p.pad, ww = w + t % p.KS - p.pad;
+    if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+      u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.x) + ((b * p.H + hh) * p.W + ww) * p.ldx + ci);
+    return u;
+  }
+  bf16 tmp[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float v = 0.f;
+    const int cc = c + i;
+    if (cc < p.K) {
+      const int t = cc / p.Cin, ci = cc - t * p.Cin;
+      const int hh = h + t / p.KS - p.pad, ww = w + t % p.KS - p.pad;
+      if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) v = ld_any(p.x, p.x_dtype, ((b * p.H + hh) * p.W + ww) * p.ldx + ci);
+    }
+    tmp[i] = __float2bfloat16_rn(v);
+  }
+  return *reinterpret_cast<uint4*>(tmp);
+}
+
 __global__ void __launch_bounds__(WG_THREADS) wgrad_mma_kernel(const WgParams p) {
   __shared__ __align__(16) bf16 sY[2][TM][PITCH];
   __shared__ __align__(16) bf16 sX[2][TM][PITCH];
@@ -85,7 +118,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_mma_kernel(const WgParams p)
       float sc = 1.f;
       if (p.rs && m < me) sc = p.rs[m / p.rs_div];
       ry[i] = load_chunk(p.dy, p.dy_dtype, p.ldy, m, me, n0 + c, p.N, p.fast_y, sc);
-      rx[i] = load_chunk(p.x, p.x_dtype, p.ldx, m, me, k0 + c, p.K, p.fast_x, 1.f);
+      rx[i] = p.conv ? load_chunk_conv(p, m, me, k0 + c) : load_chunk(p.x, p.x_dtype, p.ldx, m, me, k0 + c, p.K, p.fast_x, 1.f);
     }
   };
   auto commit = [&](int buf) {
@@ -209,6 +242,46 @@ int launch_colsum(const void* x, int dtype, long long ld, long long rows, int C,
   return 0;
 }
 
+bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
+                             int K, const float* rs, int rs_div);
+int cenet_wgrad_tc(const void* dy, long long ldy, const void* x, long long ldx, long long M, int N, int K, const float* rs, int rs_div,
+                   float* ws, long long ws_elems, cudaStream_t s);
+
+static int launch_wgrad_mma(WgParams p, int T, float* dw, long long ws_elems, cudaStream_t s) {
+  const long long nk = (long long)p.N * p.K;
+  const int ntiles = cdiv(p.N, TN) * cdiv(p.K, TK);
+  long long want = cdiv(3 * kNumSMs, ntiles);
+  long long maxs = std::max<long long>(1, p.M / 256);
+  if (want > maxs) want = maxs;
+  if (want * nk > ws_elems) want = ws_elems / nk;
+  if (want > 65535) want = 65535;
+  if (want < 1) want = 1;
+  p.m_per_split = ((p.M + want - 1) / want + TM - 1) / TM * TM;
+  const int S = (int)((p.M + p.m_per_split - 1) / p.m_per_split);
+  dim3 grid(cdiv(p.N, TN), cdiv(p.K, TK), S);
+  CENET_REQUIRE(grid.y <= 65535, "wgrad: K too large");
+  wgrad_mma_kernel<<<grid, WG_THREADS, 0, s>>>(p);
+  CENET_LAUNCH_CHECK("wgrad_mma");
+  wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(p.ws, S, p.N, p.K, T, dw);
+  CENET_LAUNCH_CHECK("wgrad_finalize");
+  return 0;
+}
+
+// weight gradient of a dense stride-1 "same" conv without materialising im2col: x is the NHWC image [B,H,W,Cin] (pitch ldx)
+extern "C" int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int B, int H,
+                                int W, int Cin, int ksize, int N, float* dw, float* ws, long long ws_elems, cenet_stream_t st) {
+  CENET_REQUIRE(dy && x && dw && ws, "cenet_conv_wgrad: null pointer");
+  CENET_REQUIRE(ksize % 2 == 1 && Cin > 0 && N > 0, "cenet_conv_wgrad: bad shape");
+  WgParams p = {};
+  p.dy = dy; p.dy_dtype = dy_dtype; p.ldy = ldy; p.x = x; p.x_dtype = x_dtype; p.ldx = ldx;
+  p.M = (long long)B * H * W; p.N = N; p.K = ksize * ksize * Cin; p.rs = nullptr; p.rs_div = 1; p.ws = ws;
+  p.fast_y = dy_dtype == CENET_BF16 && ldy % 8 == 0 && ((uintptr_t)dy & 15) == 0;
+  p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
+  p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.KS = ksize; p.pad = ksize / 2;
+  CENET_REQUIRE((long long)N * p.K <= ws_elems, "cenet_conv_wgrad: workspace too small");
+  return launch_wgrad_mma(p, ksize * ksize, dw, ws_elems, to_stream(st));
+}
+
 extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M,
                                 int N, int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias,
                                 int bias_unscaled, float* ws, long long ws_elems, cenet_stream_t st) {
@@ -238,25 +311,23 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
     g.k_scale = row_scale; g.k_scale_div = rs_div; g.k_scale_bs = chunk;
     if (cenet_gemm_simt(&g, s)) return -1;
   } else {
-    const int ntiles = cdiv(N, TN) * cdiv(K, TK);
-    long long want = cdiv(3 * kNumSMs, ntiles);
-    long long maxs = std::max<long long>(1, M / 256);
-    if (want > maxs) want = maxs;
-    if (want * nk > ws_elems) want = ws_elems / nk;
-    if (want > 65535) want = 65535;
-    if (want < 1) want = 1;
-    WgParams p;
+    static const bool use_tc = getenv("CENET_B200_WGRAD_TC") == nullptr || atoi(getenv("CENET_B200_WGRAD_TC")) != 0;
+    if (use_tc && cenet_wgrad_tc_eligible(dy, dy_dtype, ldy, x, x_dtype, ldx, M, N, K, row_scale, rs_div)) {
+      const int St = cenet_wgrad_tc(dy, ldy, x, ldx, M, N, K, row_scale, rs_div, ws, ws_elems, s);
+      if (St == -1) return -1;
+      if (St > 0) {
+        wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, St, N, K, T, dw);
+        CENET_LAUNCH_CHECK("wgrad_finalize");
+        return 0;
+      }
+    }
+    WgParams p = {};
     p.dy = dy; p.dy_dtype = dy_dtype; p.ldy = ldy; p.x = x; p.x_dtype = x_dtype; p.ldx = ldx;
     p.M = M; p.N = N; p.K = K; p.rs = row_scale; p.rs_div = rs_div;
-    p.m_per_split = ((M + want - 1) / want + TM - 1) / TM * TM;
-    S = (int)((M + p.m_per_split - 1) / p.m_per_split);
     p.ws = ws;
     p.fast_y = dy_dtype == CENET_BF16 && ldy % 8 == 0 && ((uintptr_t)dy & 15) == 0;
     p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
-    dim3 grid(cdiv(N, TN), cdiv(K, TK), S);
-    CENET_REQUIRE(grid.y <= 65535, "cenet_gemm_wgrad: K too large");
-    wgrad_mma_kernel<<<grid, WG_THREADS, 0, s>>>(p);
-    CENET_LAUNCH_CHECK("wgrad_mma");
+    return launch_wgrad_mma(p, T, dw, ws_elems, s);
   }
   wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, S, N, K, T, dw);
   CENET_LAUNCH_CHECK("wgrad_finalize");

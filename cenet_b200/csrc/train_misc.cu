@@ -14,8 +14,8 @@ __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 template <typename T>
 __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gate, const T* __restrict__ dz,
                                                       const float* __restrict__ wch, T* __restrict__ dy, int acc_dy, T* __restrict__ dgate,
-                                                      int C2, int H, int W, const float* __restrict__ mats, int nmax, int ns,
-                                                      float* __restrict__ ws) {
+                                                      int C2, int H, int W, const float* __restrict__ mats,
+                                                      const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws) {
   extern __shared__ float sm[];
   __shared__ float red[8];
   const int HW = H * W;
@@ -33,17 +33,20 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   for (int s = 0; s < ns; s++) {
     const float* Ah = mats + ((size_t)s * 2 + 0) * nmax * nmax;
     const float* Aw = mats + ((size_t)s * 2 + 1) * nmax * nmax;
+    // the operators are banded (bilinear taps): [lo, hi) of the non-zeros of every row / column comes from the host
+    const int* rbh = bands + (((size_t)s * 2 + 0) * 2 + 0) * nmax * 2;     // row bands of A_h
+    const int* rbw = bands + (((size_t)s * 2 + 1) * 2 + 0) * nmax * 2;     // row bands of A_w
     for (int i = tid; i < HW; i += 256) {
       const int r = i / W, w = i % W;
       float a = 0.f;
-      for (int h = 0; h < H; h++) a = fmaf(__ldg(Ah + r * nmax + h), Y[h * W + w], a);
+      for (int h = rbh[2 * r]; h < rbh[2 * r + 1]; h++) a = fmaf(__ldg(Ah + r * nmax + h), Y[h * W + w], a);
       Tm[i] = a;
     }
     __syncthreads();
     for (int i = tid; i < HW; i += 256) {
       const int r = i / W, j = i % W;
       float a = 0.f;
-      for (int w = 0; w < W; w++) a = fmaf(Tm[r * W + w], __ldg(Aw + j * nmax + w), a);
+      for (int w = rbw[2 * j]; w < rbw[2 * j + 1]; w++) a = fmaf(Tm[r * W + w], __ldg(Aw + j * nmax + w), a);
       R[s * HW + i] = Y[i] - a;
     }
     __syncthreads();
@@ -85,17 +88,19 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
     const float* Ah = mats + ((size_t)s * 2 + 0) * nmax * nmax;
     const float* Aw = mats + ((size_t)s * 2 + 1) * nmax * nmax;
     const float* G = R + s * HW;
+    const int* cbh = bands + (((size_t)s * 2 + 0) * 2 + 1) * nmax * 2;     // column bands of A_h
+    const int* cbw = bands + (((size_t)s * 2 + 1) * 2 + 1) * nmax * 2;     // column bands of A_w
     for (int i = tid; i < HW; i += 256) {
       const int r = i / W, w = i % W;
       float a = 0.f;
-      for (int j = 0; j < W; j++) a = fmaf(G[r * W + j], __ldg(Aw + j * nmax + w), a);
+      for (int j = cbw[2 * w]; j < cbw[2 * w + 1]; j++) a = fmaf(G[r * W + j], __ldg(Aw + j * nmax + w), a);
       Tm[i] = a;
     }
     __syncthreads();
     for (int i = tid; i < HW; i += 256) {
       const int h = i / W, w = i % W;
       float a = 0.f;
-      for (int r = 0; r < H; r++) a = fmaf(__ldg(Ah + r * nmax + h), Tm[r * W + w], a);
+      for (int r = cbh[2 * h]; r < cbh[2 * h + 1]; r++) a = fmaf(__ldg(Ah + r * nmax + h), Tm[r * W + w], a);
       ACC[i] += G[i] - a;
     }
     __syncthreads();
@@ -337,9 +342,9 @@ static int vec_of(int es, std::initializer_list<const void*> ptrs, std::initiali
 static inline int ew_blocks(long long total) { return (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs); }
 
 extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, int dtype, const float* w, void* dy, int acc_dy,
-                             void* dgate, float* dw, int B, int C2, int H, int W, const float* mats, int nmax, int nscales, float* ws,
-                             long long ws_elems, cenet_stream_t st) {
-  CENET_REQUIRE(y && gate && dz && w && dy && dgate && dw && mats && ws, "cenet_fea_bwd: null pointer");
+                             void* dgate, float* dw, int B, int C2, int H, int W, const float* mats, const int* bands, int nmax,
+                             int nscales, float* ws, long long ws_elems, cenet_stream_t st) {
+  CENET_REQUIRE(y && gate && dz && w && dy && dgate && dw && mats && bands && ws, "cenet_fea_bwd: null pointer");
   CENET_REQUIRE(nscales >= 1 && nscales <= 3, "cenet_fea_bwd: 1..3 scales");
   CENET_REQUIRE(H <= nmax && W <= nmax, "cenet_fea_bwd: operator matrices smaller than the plane");
   CENET_REQUIRE((long long)B * C2 <= ws_elems, "cenet_fea_bwd: workspace too small");
@@ -353,7 +358,7 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
       configured.store(200 * 1024);
     }
     fea_bwd_kernel<T><<<B * C2, 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
-                                                nmax, nscales, ws);
+                                                bands, nmax, nscales, ws);
     CENET_LAUNCH_CHECK("fea_bwd");
   });
   fea_dw_finalize_kernel<<<cdiv(C2, 128), 128, 0, s>>>(ws, B, C2, dw);

@@ -1,0 +1,277 @@
+// tcgen05 weight-gradient GEMM for sm_100a:   P_z[n, k] = sum_{m in split z} dY[m, n] * X[m, k]      (bf16 in, fp32 out)
+//
+// Both operands are row-major over the contraction index m, i.e. "MN-major" for the 5th-gen tensor core: a TMA box
+// {64 columns, 64 rows} with SWIZZLE_128B lands in shared memory exactly as the canonical MN-major SW128 layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) [16-byte units] with SBO = 1024 B (8-row groups) and LBO = 8192 B (next 64-column box), so
+// no transpose pass is needed.  One CTA = one 128 (n) x BN (k) accumulator tile in TMEM for one split of the contraction:
+//   warp 0     : TMA producer, 4-stage ring of [64 rows] x (128 + BN) columns
+//   warp 1     : TMEM alloc + single-thread tcgen05.mma (M=128, N=BN, K=16; a_major = b_major = MN), commit frees ring slots
+//   warps 2..5 : epilogue, tcgen05.ld -> (per-sample DropPath scale) -> fp32 partial tile in the workspace
+// The splits are reduced in fixed order by wgrad_finalize (train_gemm.cu) -> deterministic.
+// Rows are addressed through a 3-D tensor map {columns, rows per group, groups}: a group is one sample when a per-sample row
+// scale applies (the scale then multiplies the partial in the epilogue) and the tail rows of a group are zero-filled by TMA.
+#include "train_common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+constexpr int WT_THREADS = 192;
+constexpr int CH = 64;            // contraction rows per pipeline stage
+constexpr int BOX_BYTES = CH * 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp field layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 = stride between 64-element MN blocks | [32,46) SBO>>4 = stride between 8-row K groups |
+//   [46,48) version = 1 | [61,64) layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+struct WtParams {
+  int N, K;               // output rows (dY columns) / columns (X columns)
+  int bn;                 // X-column tile: multiple of 64, <= 256
+  int stages, tmem_cols;
+  int rows_per_group;     // rows of one group (sample)
+  int parts;              // splits per group
+  int rows_per_part;      // multiple of 64
+  const float* rs;        // per-group scale or NULL
+  float* ws;              // [S][N][K]
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                const __grid_constant__ CUtensorMap tmX, const WtParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xboxes = p.bn / 64;
+  const uint32_t stage_bytes = (2 + xboxes) * BOX_BYTES;
+  const uint32_t bar_base = sbase + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (p.stages + s) * 8; };
+  const uint32_t tfull_bar = bar_base + 2 * p.stages * 8;
+  const uint32_t tmem_slot = tfull_bar + 8;
+  const int n0 = blockIdx.x * 128, k0 = blockIdx.y * p.bn;
+  const int z = blockIdx.z, grp = z / p.parts, part = z % p.parts;
+  const int row_lo = part * p.rows_per_part;
+  const int row_hi = min(p.rows_per_group, row_lo + p.rows_per_part);
+  const int nchunks = (row_hi - row_lo + CH - 1) / CH;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; c++) {
+        const int s = c % p.stages;
+        const uint32_t ph = (c / p.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = sbase + s * stage_bytes;
+        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+        const int r0 = row_lo + c * CH;
+        tma_load_3d(sa, &tmY, full_bar(s), n0, r0, grp);
+        tma_load_3d(sa + BOX_BYTES, &tmY, full_bar(s), n0 + 64, r0, grp);
+        for (int j = 0; j < xboxes; j++) tma_load_3d(sa + (2 + j) * BOX_BYTES, &tmX, full_bar(s), k0 + 64 * j, r0, grp);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), A and B MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (int c = 0; c < nchunks; c++) {
+        const int s = c % p.stages;
+        const uint32_t ph = (c / p.stages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = sbase + s * stage_bytes;
+        const uint64_t adesc = make_desc_mn(sa, BOX_BYTES, 1024), bdesc = make_desc_mn(sa + 2 * BOX_BYTES, BOX_BYTES, 1024);
+        for (int k = 0; k < CH / 16; k++)      // 16 contraction rows = two 8-row groups = 2048 bytes = +128 in the address field
+          umma_f16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (c | k) != 0);
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warps 2..5 -> 2,3,0,1)
+    const int n = n0 + quarter * 32 + lane;
+    float scale = 1.f;
+    if (p.rs) scale = p.rs[grp];
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    float* out = p.ws + ((size_t)z * p.N + n) * p.K;
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      if (k0 + c0 >= p.K) break;
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (n < p.N) {
+        if (nchunks == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[j] = 0u;
+        }
+        const int kk = k0 + c0;
+        if (kk + 32 <= p.K && (p.K & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out + kk + j) =
+                make_float4(__uint_as_float(acc[j]) * scale, __uint_as_float(acc[j + 1]) * scale, __uint_as_float(acc[j + 2]) * scale,
+                            __uint_as_float(acc[j + 3]) * scale);
+        } else {
+          for (int j = 0; j < 32 && kk + j < p.K; j++) out[kk + j] = __uint_as_float(acc[j]) * scale;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int encode_3d(CUtensorMap* tm, const void* base, long long cols, long long ld, long long rows_per_group, long long groups) {
+  EncodeTiledFn enc = get_encode();
+  CENET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows_per_group, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows_per_group * ld * 2};
+  cuuint32_t box[3] = {64, CH, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CENET_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad) failed with CUresult %d", (int)r);
+  return 0;
+}
+}  // namespace
+
+// eligibility: bf16 operands, 16-byte aligned bases and pitches, per-sample (or no) row scale
+bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
+                             int K, const float* rs, int rs_div) {
+  if (dy_dtype != CENET_BF16 || x_dtype != CENET_BF16) return false;
+  if (ldy % 8 || ldx % 8 || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15)) return false;
+  if (M < 512 || N < 32 || K < 32) return false;
+  if (rs && (rs_div < 64 || M % rs_div != 0)) return false;
+  return true;
+}
+
+// writes S partial tiles [N][K] into ws and returns S (or -1)
+int cenet_wgrad_tc(const void* dy, long long ldy, const void* x, long long ldx, long long M, int N, int K, const float* rs, int rs_div,
+                   float* ws, long long ws_elems, cudaStream_t s) {
+  const long long nk = (long long)N * K;
+  WtParams p = {};
+  p.N = N; p.K = K; p.rs = rs; p.ws = ws;
+  const int kt = cdiv(K, 256);
+  p.bn = (cdiv(K, kt) + 63) / 64 * 64;
+  const int tiles = cdiv(N, 128) * cdiv(K, p.bn);
+  const long long groups = rs ? M / rs_div : 1;
+  p.rows_per_group = (int)(rs ? rs_div : M);
+  // splits: enough CTAs to fill the machine, at least 256 rows each, bounded by the workspace
+  long long want = cdiv(2 * kNumSMs, tiles);
+  long long max_ws = ws_elems / nk;
+  if (max_ws < groups) return -2;                                   // caller falls back
+  long long parts = std::max<long long>(1, want / groups);
+  parts = std::min<long long>(parts, std::max<long long>(1, p.rows_per_group / 256));
+  parts = std::min<long long>(parts, max_ws / groups);
+  p.rows_per_part = (int)(((p.rows_per_group + parts - 1) / parts + CH - 1) / CH * CH);
+  p.parts = (p.rows_per_group + p.rows_per_part - 1) / p.rows_per_part;
+  const long long S = groups * p.parts;
+  if (S > 65535) return -2;
+  CUtensorMap tmY, tmX;
+  if (encode_3d(&tmY, dy, N, ldy, p.rows_per_group, groups)) return -1;
+  if (encode_3d(&tmX, x, K, ldx, p.rows_per_group, groups)) return -1;
+  const int stage_bytes = (2 + p.bn / 64) * BOX_BYTES;
+  p.stages = 4;
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+  dim3 grid(cdiv(N, 128), cdiv(K, p.bn), (unsigned)S);
+  wgrad_tc_kernel<<<grid, WT_THREADS, smem, s>>>(tmY, tmX, p);
+  CENET_LAUNCH_CHECK("wgrad_tc");
+  return (int)S;
+}

@@ -390,11 +390,14 @@ class TrainEngine:
 
         def bwd():
             dy = self.G(out)
-            Kp = _rup(k * k * Cin, 8)
-            col = self.buf(key + ".col", (B * H * W, Kp))
-            ops.im2col(x4, col, B, H, W, Cin, k, 1, k // 2, H, W, Kp)
-            tops.gemm_wgrad(dy, col, self.GP[name + ".weight"], M=B * H * W, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0, ldx=Kp,
-                            x_off=0, T=k * k, ws=self._ws(0))
+            if self.T == torch.bfloat16:
+                tops.conv_wgrad(dy, x4, self.GP[name + ".weight"], k, self._ws(0))      # taps gathered inside the kernel
+            else:
+                Kp = _rup(k * k * Cin, 8)
+                col = self.buf(key + ".col", (B * H * W, Kp))
+                ops.im2col(x4, col, B, H, W, Cin, k, 1, k // 2, H, W, Kp)
+                tops.gemm_wgrad(dy, col, self.GP[name + ".weight"], M=B * H * W, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0,
+                                ldx=Kp, x_off=0, T=k * k, ws=self._ws(0))
             dx = self.G(x4)
             acc = self.wr(x4)
             ops.conv_nhwc(dy.view(B, H, W, Cout), WT, dx.view(B * H * W, Cin), k, 1, k // 2, res1=dx if acc else None,

@@ -42,6 +42,14 @@ def gemm_wgrad(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=Non
            rs_div, _f32(dw, "dw"), _f32(dbias, "dbias"), int(bias_unscaled), wp, wn, _stream())
 
 
+def conv_wgrad(dy, x4, dw, ksize, ws):
+    """dw [N,Cin,k,k] of a stride-1 'same' conv: dy [B*H*W, N] contiguous, x4 [B,H,W,Cin] contiguous (no im2col buffer)"""
+    B, H, W, Cin = x4.shape
+    N = dy.shape[-1]
+    wp, wn = _ws(ws)
+    L.call("cenet_conv_wgrad", _p(dy), dt(dy), N, _p(x4), dt(x4), Cin, B, H, W, Cin, ksize, N, _f32(dw, "dw"), wp, wn, _stream())
+
+
 def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws):
     rows, Cc = x.shape
     wp, wn = _ws(ws)
@@ -138,10 +146,35 @@ def diff_rmsnorm_bwd(do, Om, lam, dOm, dlam, M, heads, seg, eps, mult, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ DSEB
+_BANDS = {}
+
+
+def _fea_bands(mats):
+    """[lo, hi) of the non-zero entries of every row and column of the per-axis operators (they are banded)"""
+    key = (mats.data_ptr(), tuple(mats.shape))
+    b = _BANDS.get(key)
+    if b is None:
+        m = mats.detach().float().cpu()
+        ns, _, n, _ = m.shape
+        out = torch.zeros(ns, 2, 2, n, 2, dtype=torch.int32)
+        idx = torch.arange(n)
+        for s in range(ns):
+            for ax in range(2):
+                for t, mat in enumerate((m[s, ax], m[s, ax].t())):
+                    nz = mat != 0
+                    any_ = nz.any(1)
+                    lo = torch.where(nz, idx[None, :], torch.full_like(idx, n)[None, :]).min(1)[0]
+                    hi = torch.where(nz, idx[None, :] + 1, torch.zeros_like(idx)[None, :]).max(1)[0]
+                    out[s, ax, t, :, 0] = torch.where(any_, lo, torch.zeros_like(lo)).to(torch.int32)
+                    out[s, ax, t, :, 1] = torch.where(any_, hi, torch.zeros_like(hi)).to(torch.int32)
+        b = _BANDS[key] = out.to(mats.device).contiguous()
+    return b
+
+
 def fea_bwd(y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, nscales, ws):
     wp, wn = _ws(ws)
     L.call("cenet_fea_bwd", _p(y), _p(gate), _p(dz), dt(y), _f32(w, "w"), _p(dy), int(acc), _p(dgate), _f32(dw, "dw"), B, E, H,
-           W, _f32(mats, "mats"), mats.shape[-1], nscales, wp, wn, _stream())
+           W, _f32(mats, "mats"), _i32(_fea_bands(mats), "bands"), mats.shape[-1], nscales, wp, wn, _stream())
 
 
 def nchw_to_nhwc_slice(x, out, B, HW, C_, Ctot, coff, acc):

@@ -207,6 +207,10 @@ int cenet_dwconv3x3_train(const void* x, int x_dtype, long long ldx, void* y, in
 int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
                      int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias, int bias_unscaled, float* ws,
                      long long ws_elems, cenet_stream_t s);
+/* weight gradient of a dense stride-1 "same" conv WITHOUT im2col: x is the NHWC image [B,H,W,Cin] (pitch ldx), dy [B*H*W, N] (pitch
+ * ldy); dw in the reference layout [N, Cin, k, k].  The X operand tile is gathered tap by tap inside the kernel. */
+int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int B, int H, int W,
+                     int Cin, int ksize, int N, float* dw, float* ws, long long ws_elems, cenet_stream_t s);
 /* LayerNorm backward (pvtv2.py:146-147,189,320): dx (+)= ..., dgamma, dbeta; statistics are recomputed from x.  C in {64,128,320,512} */
 int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, const float* gamma, float eps, long long rows, int C, void* dx,
                         int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems, cenet_stream_t s);
@@ -254,10 +258,11 @@ int cenet_diff_rmsnorm_fwd(const void* Om, int dtype, const float* lam, void* o,
                            float mult, cenet_stream_t s);
 int cenet_diff_rmsnorm_bwd(const void* dO, const void* Om, int dtype, const float* lam, void* dOm, float* dlam, long long rows,
                            int heads, int seg, float eps, float mult, float* ws, long long ws_elems, cenet_stream_t s);
-/* backward of cenet_fea_combine: dy (+)=, dgate =, dw[c]; mats [nscales][2][nmax][nmax] = per-axis operators Up_s Down_s */
+/* backward of cenet_fea_combine: dy (+)=, dgate =, dw[c]; mats [nscales][2][nmax][nmax] = per-axis operators Up_s Down_s,
+ * bands [nscales][2 axes][2: rows, columns][nmax][2] = [lo, hi) of the non-zeros of every row / column of those operators */
 int cenet_fea_bwd(const void* y, const void* gate, const void* dz, int dtype, const float* w, void* dy, int acc_dy, void* dgate,
-                  float* dw, int B, int C2, int H, int W, const float* mats, int nmax, int nscales, float* ws, long long ws_elems,
-                  cenet_stream_t s);
+                  float* dw, int B, int C2, int H, int W, const float* mats, const int* bands, int nmax, int nscales, float* ws,
+                  long long ws_elems, cenet_stream_t s);
 /* out_nhwc[b,hw,c] (+)= x_nchw[b, coff+c, hw] */
 int cenet_nchw_to_nhwc_slice(const void* x, int dtype, void* out, int B, int HW, int C, int Ctot, int coff, int acc, cenet_stream_t s);
 /* dst (+)= src */

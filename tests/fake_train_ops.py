@@ -55,6 +55,15 @@ def gemm_wgrad(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=Non
         dbias.view(-1)[:N].copy_((dyv if bias_unscaled else dys).sum(0))
 
 
+def conv_wgrad(dy, x4, dw, ksize, ws):
+    _LAUNCHES[0] += 2
+    B, H, W, Cin = x4.shape
+    N = dy.shape[-1]
+    w = torch.zeros(N, Cin, ksize, ksize, requires_grad=True)
+    out = F.conv2d(x4.float().permute(0, 3, 1, 2), w, padding=ksize // 2)
+    dw.copy_(torch.autograd.grad(out, w, _flat(dy).view(B, H, W, N).float().permute(0, 3, 1, 2))[0])
+
+
 def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws):
     _LAUNCHES[0] += 2
     xf = x.float().detach().requires_grad_(True)

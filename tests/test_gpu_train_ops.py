@@ -103,6 +103,25 @@ def test_gemm_wgrad(dtype, M, N, K, T):
     check("gemm_wgrad", [dy, x, dw], kw, [2, "dbias"], 3e-4 if dtype == F32 else 1.5e-2)
 
 
+@pytest.mark.parametrize("Cin,N,k", [(32, 32, 5), (64, 64, 3), (64, 32, 3)])
+def test_conv_wgrad_implicit_im2col(Cin, N, k):
+    B, H, W = 2, 24, 20
+    dy, x4 = rn((B * H * W, N), BF16, 1), rn((B, H, W, Cin), BF16, 2)
+    check("conv_wgrad", [dy, x4, torch.zeros(N, Cin, k, k), k, ws()], {}, [2], 1.5e-2)
+
+
+@pytest.mark.parametrize("M,N,K,ldy,ldx,rsdiv", [(3 * 3136, 64, 512, 64, 512, 3136), (4 * 784, 1024, 128, 1024, 128, 784),
+                                                 (4704, 1280, 320, 1280, 320, 0), (75264, 64, 64, 192, 64, 0), (1176, 512, 2048, 512, 2048, 49 * 4),
+                                                 (5000, 320, 100, 328, 104, 0)])
+def test_gemm_wgrad_tcgen05(M, N, K, ldy, ldx, rsdiv):
+    """shapes that take the tcgen05 MN-major kernel (bf16, aligned), with and without a per-sample row scale"""
+    dy, x = rn((M, ldy), BF16, 1), rn((M, ldx), BF16, 2)
+    dw, db = torch.zeros(N * K), torch.zeros(N)
+    rs = (torch.rand(M // rsdiv, generator=gen(3)) + 0.5) if rsdiv else None
+    kw = dict(M=M, N=N, K=K, ldy=ldy, y_off=0, ldx=ldx, x_off=0, row_scale=rs, rs_div=rsdiv or 1, dbias=db, ws=torch.zeros(1 << 24))
+    check("gemm_wgrad", [dy, x, dw], kw, [2, "dbias"], 1.5e-2)
+
+
 def test_gemm_wgrad_mixed_dtypes_unscaled_bias():
     M, N, K = 5000, 4, 64                                   # head: fp32 logits gradient x bf16 activations
     dy, x = rn((M, N), F32, 1), rn((M, K), BF16, 2)
