@@ -247,6 +247,11 @@ bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const 
 int cenet_wgrad_tc(const void* dy, long long ldy, const void* x, long long ldx, long long M, int N, int K, const float* rs, int rs_div,
                    float* ws, long long ws_elems, cudaStream_t s);
 
+bool cenet_conv_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int Cin, int N,
+                                  int ksize);
+int cenet_conv_wgrad_tc(const void* dy, const void* x, int B, int H, int W, int Cin, int ksize, int N, float* ws, long long ws_elems,
+                        cudaStream_t s);
+
 static int launch_wgrad_mma(WgParams p, int T, float* dw, long long ws_elems, cudaStream_t s) {
   const long long nk = (long long)p.N * p.K;
   const int ntiles = cdiv(p.N, TN) * cdiv(p.K, TK);
@@ -272,6 +277,17 @@ extern "C" int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, con
                                 int W, int Cin, int ksize, int N, float* dw, float* ws, long long ws_elems, cenet_stream_t st) {
   CENET_REQUIRE(dy && x && dw && ws, "cenet_conv_wgrad: null pointer");
   CENET_REQUIRE(ksize % 2 == 1 && Cin > 0 && N > 0, "cenet_conv_wgrad: bad shape");
+  static const bool use_tc = getenv("CENET_B200_WGRAD_TC") == nullptr || atoi(getenv("CENET_B200_WGRAD_TC")) != 0;
+  if (use_tc && cenet_conv_wgrad_tc_eligible(dy, dy_dtype, ldy, x, x_dtype, ldx, Cin, N, ksize)) {
+    const long long nk = (long long)N * ksize * ksize * Cin;
+    const int St = cenet_conv_wgrad_tc(dy, x, B, H, W, Cin, ksize, N, ws, ws_elems, to_stream(st));
+    if (St == -1) return -1;
+    if (St > 0) {
+      wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, to_stream(st)>>>(ws, St, N, ksize * ksize * Cin, ksize * ksize, dw);
+      CENET_LAUNCH_CHECK("wgrad_finalize");
+      return 0;
+    }
+  }
   WgParams p = {};
   p.dy = dy; p.dy_dtype = dy_dtype; p.ldy = ldy; p.x = x; p.x_dtype = x_dtype; p.ldx = ldx;
   p.M = (long long)B * H * W; p.N = N; p.K = ksize * ksize * Cin; p.rs = nullptr; p.rs_div = 1; p.ws = ws;

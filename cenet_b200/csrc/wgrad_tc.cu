@@ -44,6 +44,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -77,6 +83,136 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// MN-major descriptor with an explicit swizzle mode: layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t make_desc_mn_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
+}
+
+// ---- dense-conv weight gradient -----------------------------------------------------------------------------------------
+// dW[(tap, ci), n] = sum over pixels of X[pixel + tap offset, ci] * dY[pixel, n], accumulated for ALL taps in TMEM:
+// UMMA M = 128 rows = (128 / Cin) taps x Cin channels (one shifted 4-D TMA box per tap, OOB = zero padding), N = Cout,
+// K = the 128 pixels of an 8 x 16 patch.  A persistent CTA streams patches; its whole [T*Cin, Cout] partial lives in TMEM
+// (T*Cin/128 accumulator tiles) and is written once at the end.
+constexpr int CW_TH = 8, CW_TW = 16;
+struct CwParams {
+  int Bimg, H, W, Cin, N, KS, pad, T;
+  int taps_per_tile, mtiles;
+  int tiles_h, tiles_w, npatches;
+  int stages, tmem_cols;
+  uint32_t xbox_bytes, ybox_bytes;
+  float* ws;              // [gridDim.x][N][T*Cin]
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                                     const __grid_constant__ CUtensorMap tmX, const CwParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = p.ybox_bytes + p.taps_per_tile * p.xbox_bytes;
+  const uint32_t bar_base = sbase + p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (p.stages + s) * 8; };
+  const uint32_t tfull_bar = bar_base + 2 * p.stages * 8;
+  const uint32_t tmem_slot = tfull_bar + 8;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  int my_patches = 0;
+  for (int pt = blockIdx.x; pt < p.npatches; pt += gridDim.x) my_patches++;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pt = blockIdx.x; pt < p.npatches; pt += gridDim.x) {
+        int t = pt;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int img = t / p.tiles_h;
+        const int h0 = th * CW_TH, w0 = tw * CW_TW;
+        for (int mt = 0; mt < p.mtiles; mt++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = sbase + s * stage_bytes;
+          const int ntaps = min(p.taps_per_tile, p.T - mt * p.taps_per_tile);
+          mbar_arrive_expect_tx(full_bar(s), p.ybox_bytes + ntaps * p.xbox_bytes);
+          tma_load_4d(sa, &tmY, full_bar(s), 0, w0, h0, img);
+          for (int j = 0; j < ntaps; j++) {
+            const int tap = mt * p.taps_per_tile + j;
+            tma_load_4d(sa + p.ybox_bytes + j * p.xbox_bytes, &tmX, full_bar(s), 0, w0 + tap % p.KS - p.pad, h0 + tap / p.KS - p.pad,
+                        img);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t xrow = p.Cin * 2, yrow = p.N * 2;                 // bytes per pixel row of a box (64 or 128)
+      const uint32_t xlt = xrow == 128 ? 2u : 4u, ylt = yrow == 128 ? 2u : 4u;
+      uint32_t it = 0;
+      int pi = 0;
+      for (int pt = blockIdx.x; pt < p.npatches; pt += gridDim.x, pi++) {
+        for (int mt = 0; mt < p.mtiles; mt++, it++) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = sbase + s * stage_bytes;
+          // A = X boxes of this tile's taps: MN blocks (one per tap) LBO apart; B = dY box
+          const uint64_t adesc = make_desc_mn_sw(sa + p.ybox_bytes, p.xbox_bytes, 8 * xrow, xlt);
+          const uint64_t bdesc = make_desc_mn_sw(sa, p.ybox_bytes, 8 * yrow, ylt);
+          const uint32_t d_tmem = tmem_base + mt * p.N;
+          for (int k = 0; k < (CW_TH * CW_TW) / 16; k++)                // 16 pixels per UMMA: 16 rows of the boxes
+            umma_f16(d_tmem, adesc + (uint64_t)((16 * xrow * k) >> 4), bdesc + (uint64_t)((16 * yrow * k) >> 4), idesc,
+                     (pi | k) != 0);
+          umma_commit(empty_bar(s));
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int Ktot = p.T * p.Cin;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    float* out = p.ws + (size_t)blockIdx.x * p.N * Ktot;
+    for (int mt = 0; mt < p.mtiles; mt++) {
+      const int krow = mt * 128 + quarter * 32 + lane;                    // (tap, ci) index of this thread's accumulator row
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * p.N + c0), acc);
+        tmem_ld_wait();
+        if (krow < Ktot) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) out[(size_t)(c0 + j) * Ktot + krow] = my_patches > 0 ? __uint_as_float(acc[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
 }
 
 struct WtParams {
@@ -225,7 +361,63 @@ int encode_3d(CUtensorMap* tm, const void* base, long long cols, long long ld, l
   CENET_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad) failed with CUresult %d", (int)r);
   return 0;
 }
+
+int encode_4d(CUtensorMap* tm, const void* base, int C, int W, int H, int B, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  CENET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, CW_TW, CW_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CENET_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (conv wgrad) failed with CUresult %d", (int)r);
+  return 0;
+}
 }  // namespace
+
+bool cenet_conv_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int Cin, int N,
+                                  int ksize) {
+  if (dy_dtype != CENET_BF16 || x_dtype != CENET_BF16) return false;
+  if (!(Cin == 32 || Cin == 64) || !(N == 32 || N == 64)) return false;
+  if (ldy != N || ldx != Cin || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15)) return false;
+  const int T = ksize * ksize, tpt = 128 / Cin, mtiles = (T + tpt - 1) / tpt;
+  return mtiles * N <= 512;
+}
+
+// writes gridDim.x partials [N][T*Cin] into ws and returns their number (or -1 / -2)
+int cenet_conv_wgrad_tc(const void* dy, const void* x, int B, int H, int W, int Cin, int ksize, int N, float* ws, long long ws_elems,
+                        cudaStream_t s) {
+  CwParams p = {};
+  p.Bimg = B; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.KS = ksize; p.pad = ksize / 2; p.T = ksize * ksize;
+  p.taps_per_tile = 128 / Cin;
+  p.mtiles = (p.T + p.taps_per_tile - 1) / p.taps_per_tile;
+  p.tiles_h = cdiv(H, CW_TH); p.tiles_w = cdiv(W, CW_TW);
+  p.npatches = B * p.tiles_h * p.tiles_w;
+  p.xbox_bytes = 128 * Cin * 2; p.ybox_bytes = 128 * N * 2;
+  p.ws = ws;
+  int cols = 32;
+  while (cols < p.mtiles * N) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = p.ybox_bytes + p.taps_per_tile * p.xbox_bytes;
+  p.stages = std::min(6, (200 * 1024) / stage_bytes);
+  int grid = std::min(kNumSMs, p.npatches);
+  const long long nk = (long long)N * p.T * Cin;
+  if ((long long)grid * nk > ws_elems) grid = (int)(ws_elems / nk);
+  if (grid < 1) return -2;
+  CUtensorMap tmY, tmX;
+  if (encode_4d(&tmY, dy, N, W, H, B, N == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+  if (encode_4d(&tmX, x, Cin, W, H, B, Cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] { cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+  conv_wgrad_tc_kernel<<<grid, WT_THREADS, smem, s>>>(tmY, tmX, p);
+  CENET_LAUNCH_CHECK("conv_wgrad_tc");
+  return grid;
+}
+
+namespace {
+}
 
 // eligibility: bf16 operands, 16-byte aligned bases and pitches, per-sample (or no) row scale
 bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
