@@ -59,7 +59,7 @@ template <int D>
 __device__ __forceinline__ void load_tile(bf16* __restrict__ sm, const bf16* __restrict__ base, long long ld, int row0, int nrows, int tid) {
   constexpr int CH = D / 8, P = D + 8;
   for (int i = tid; i < 64 * CH; i += FT) {
-    const int r = i / CH, c = (i % CH) * 8;
+    const int r = i / CH, c = (i - r * CH) * 8;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (row0 + r < nrows) u = *reinterpret_cast<const uint4*>(base + (long long)(row0 + r) * ld + c);
     *reinterpret_cast<uint4*>(sm + r * P + c) = u;
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------ dK, dV
-template <int DQK, int DV>
+// MODE 0: dK and dV in one pass; MODE 1: dV only; MODE 2: dK only (large head dims: the two accumulators do not fit together)
+template <int DQK, int DV, int MODE>
 __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
   __shared__ __align__(16) bf16 sQ[BQ * (DQK + 8)];
   __shared__ __align__(16) bf16 sG[BQ * (DV + 8)];
@@ -322,12 +323,15 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
   const int b = blockIdx.z, vh = blockIdx.y, kr0 = blockIdx.x * BKEY + warp * 16;
   const bf16* Vp = p.V + (long long)b * p.Nk * p.ldv + vh * DV;
   constexpr int KS = (DQK + 15) / 16;
-  uint32_t vf[DV / 16][4];
+  constexpr bool DO_DV = MODE != 2, DO_DK = MODE != 1;
+  uint32_t vf[DO_DK ? DV / 16 : 1][4];
+  if constexpr (DO_DK) {
 #pragma unroll
-  for (int ks = 0; ks < DV / 16; ks++) load_a_global<DV>(vf[ks], Vp, p.ldv, kr0, p.Nk, ks * 16, lane);
-  float dv[DV / 8][4];
+    for (int ks = 0; ks < DV / 16; ks++) load_a_global<DV>(vf[ks], Vp, p.ldv, kr0, p.Nk, ks * 16, lane);
+  }
+  float dv[DO_DV ? DV / 8 : 1][4];
 #pragma unroll
-  for (int j = 0; j < DV / 8; j++)
+  for (int j = 0; j < (DO_DV ? DV / 8 : 1); j++)
 #pragma unroll
     for (int e = 0; e < 4; e++) dv[j][e] = 0.f;
   const bool kvalid[2] = {kr0 + g < p.Nk, kr0 + g + 8 < p.Nk};
@@ -341,9 +345,9 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
     uint32_t kf[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ks++) load_a_global<DQK>(kf[ks], Kp, p.ldk, kr0, p.Nk, ks * 16, lane);
-    float dk[DQK / 8][4];
+    float dk[DO_DK ? DQK / 8 : 1][4];
 #pragma unroll
-    for (int j = 0; j < DQK / 8; j++)
+    for (int j = 0; j < (DO_DK ? DQK / 8 : 1); j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) dk[j][e] = 0.f;
     for (int q0 = 0; q0 < p.Nq; q0 += BQ) {
@@ -355,47 +359,65 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
         sD[tid] = q0 + tid < p.Nq ? dlp[q0 + tid] : 0.f;
       }
       __syncthreads();
-      float st[8][4], dpt[8][4];                       // S^T, dP^T: rows = keys of this warp, columns = 64 queries
+      float st[8][4];                                  // S^T: rows = keys of this warp, columns = 64 queries
 #pragma unroll
       for (int j = 0; j < 8; j++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) st[j][e] = dpt[j][e] = 0.f;
+        for (int e = 0; e < 4; e++) st[j][e] = 0.f;
       mma_a_tileT<DQK>(st, kf, sQ, lane);
-      mma_a_tileT<DV>(dpt, vf, sG, lane);
 #pragma unroll
       for (int j = 0; j < 8; j++)
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int qi = j * 8 + 2 * t + (e & 1);
-          const float pr = kvalid[e >> 1] ? ex2(st[j][e] * p.c - sL[qi]) : 0.f;
-          dpt[j][e] = pr * (dpt[j][e] - sD[qi]);       // dS^T
-          st[j][e] = pr;                               // P^T
+          st[j][e] = kvalid[e >> 1] ? ex2(st[j][e] * p.c - sL[qi]) : 0.f;      // P^T
         }
       uint32_t pf[4][4];
-      c_to_a(pf, st);
-      mma_a_tile<DV>(dv, pf, sG, lane);
-      c_to_a(pf, dpt);
-      mma_a_tile<DQK>(dk, pf, sQ, lane);
+      if constexpr (DO_DV) {
+        c_to_a(pf, st);
+        mma_a_tile<DV>(dv, pf, sG, lane);
+      }
+      if constexpr (DO_DK) {
+        float dpt[8][4];                               // dP^T
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) dpt[j][e] = 0.f;
+        mma_a_tileT<DV>(dpt, vf, sG, lane);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int qi = j * 8 + 2 * t + (e & 1);
+            dpt[j][e] = st[j][e] * (dpt[j][e] - sD[qi]);     // dS^T
+          }
+        c_to_a(pf, dpt);
+        mma_a_tile<DQK>(dk, pf, sQ, lane);
+      }
     }
-    bf16* dKp = p.dK + (long long)b * p.Nk * p.ldk + m * DQK;
+    if constexpr (DO_DK) {
+      bf16* dKp = p.dK + (long long)b * p.Nk * p.ldk + m * DQK;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int r = kr0 + g + h * 8;
+        if (r >= p.Nk) continue;
+#pragma unroll
+        for (int j = 0; j < DQK / 8; j++)
+          *reinterpret_cast<uint32_t*>(dKp + (long long)r * p.ldk + j * 8 + 2 * t) =
+              pack_bf16(dk[j][2 * h] * p.scale, dk[j][2 * h + 1] * p.scale);
+      }
+    }
+  }
+  if constexpr (DO_DV) {
+    bf16* dVp = p.dV + (long long)b * p.Nk * p.ldv + vh * DV;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int r = kr0 + g + h * 8;
       if (r >= p.Nk) continue;
 #pragma unroll
-      for (int j = 0; j < DQK / 8; j++)
-        *reinterpret_cast<uint32_t*>(dKp + (long long)r * p.ldk + j * 8 + 2 * t) =
-            pack_bf16(dk[j][2 * h] * p.scale, dk[j][2 * h + 1] * p.scale);
+      for (int j = 0; j < DV / 8; j++)
+        *reinterpret_cast<uint32_t*>(dVp + (long long)r * p.ldv + j * 8 + 2 * t) = pack_bf16(dv[j][2 * h], dv[j][2 * h + 1]);
     }
-  }
-  bf16* dVp = p.dV + (long long)b * p.Nk * p.ldv + vh * DV;
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int r = kr0 + g + h * 8;
-    if (r >= p.Nk) continue;
-#pragma unroll
-    for (int j = 0; j < DV / 8; j++)
-      *reinterpret_cast<uint32_t*>(dVp + (long long)r * p.ldv + j * 8 + 2 * t) = pack_bf16(dv[j][2 * h], dv[j][2 * h + 1]);
   }
 }
 
@@ -535,6 +557,8 @@ int check_flash(const FlashArgs& a, int dqk, int dv, int B) {
     else if (dqk == 16 && dv == 32) { constexpr int DQK = 16, DV = 32; CALL; }     \
     else if (dqk == 32 && dv == 64) { constexpr int DQK = 32, DV = 64; CALL; }     \
     else if (dqk == 64 && dv == 64) { constexpr int DQK = 64, DV = 64; CALL; }     \
+    else if (dqk == 128 && dv == 128) { constexpr int DQK = 128, DV = 128; CALL; } \
+    else if (dqk == 80 && dv == 160) { constexpr int DQK = 80, DV = 160; CALL; }   \
     else CENET_FAIL("flash attention: (dqk, dv) = (%d, %d) not instantiated", dqk, dv); \
   } while (0)
 
@@ -568,8 +592,15 @@ extern "C" int cenet_flash_bwd(const void* Q, long long ldq, const void* K, long
   CENET_LAUNCH_CHECK("flash_delta");
   FLASH_DISPATCH(dqk, dv, (flash_bwd_dq_kernel<DQK, DV><<<dim3(cdiv(Nq, BQ), maps, B), FT, 0, s>>>(a)));
   CENET_LAUNCH_CHECK("flash_bwd_dq");
-  FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
-  CENET_LAUNCH_CHECK("flash_bwd_dkv");
+  if (dqk >= 80) {                      // large head dims: dV and dK in separate passes (register budget)
+    FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 1><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
+    CENET_LAUNCH_CHECK("flash_bwd_dv");
+    FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 2><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
+    CENET_LAUNCH_CHECK("flash_bwd_dk");
+  } else {
+    FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 0><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
+    CENET_LAUNCH_CHECK("flash_bwd_dkv");
+  }
   return 0;
 }
 

@@ -36,7 +36,7 @@ from .engine import _MCA_RATES, _PVT, _rup, lambda_init
 from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT
 from .train_ops import ACT_GELU_GRAD
 
-FLASH_DIMS = {(8, 16), (16, 32), (32, 64), (64, 64)}       # (dqk, dv) instantiated in train_attn.cu
+FLASH_DIMS = {(8, 16), (16, 32), (32, 64), (64, 64), (128, 128), (80, 160)}       # (dqk, dv) instantiated in train_attn.cu
 
 
 class TrainEngine:

@@ -239,7 +239,7 @@ int cenet_sumpool2(const void* x, int x_dtype, void* y, int y_dtype, int B, int 
 int cenet_col2im(const void* dcol, int c_dtype, void* dx, int x_dtype, int B, int H, int W, int Cin, int k, int stride, int pad, int Ho,
                  int Wo, int Kpad, int acc, cenet_stream_t s);
 /* flash attention with saved log2-sum-exp (bf16): O[:, m*dv..] = softmax(scale Q_m K_m^T) V_{m/vdiv}; lse [B,maps,Nq].
- * (dqk, dv) in {(8,16),(16,32),(32,64),(64,64)}.  Serves pvtv2.py:88-105, nlb.py:116-137, multihead_diffattn.py:92-116. */
+ * (dqk, dv) in {(8,16),(16,32),(32,64),(64,64),(128,128),(80,160)}.  Serves pvtv2.py:88-105, nlb.py:116-137, multihead_diffattn.py:92-116. */
 int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O, long long ldo,
                     float* lse, int B, int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
 /* its backward: delta = rowsum(dO*O) (workspace [B,maps,Nq]); dQ, dK, dV written with the layouts of Q, K, V (no atomics) */

@@ -204,7 +204,8 @@ def test_sumpool2_col2im(dtype):
 
 # ------------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("dqk,dv,vdiv,maps,Nq,Nk", [(64, 64, 1, 2, 200, 49), (64, 64, 1, 1, 784, 784), (16, 32, 2, 8, 196, 196),
-                                                    (8, 16, 2, 4, 300, 300), (32, 64, 2, 4, 130, 130)])
+                                                    (8, 16, 2, 4, 300, 300), (32, 64, 2, 4, 130, 130), (128, 128, 1, 1, 784, 784),
+                                                    (80, 160, 2, 8, 196, 196)])
 def test_flash_fwd_bwd(dqk, dv, vdiv, maps, Nq, Nk):
     from cenet_b200 import train_ops as tops
     B = 2

@@ -26,7 +26,22 @@ class Tagged(_TimedOps):
     def __getattr__(self, name):
         if name in ("make_tables", "ACT_GELU_GRAD"):
             return getattr(self._inner, name)
-        return super().__getattr__(name)
+        fn = super().__getattr__(name)
+        if name != "gemm":
+            return fn
+        inner = getattr(self._inner, "gemm")
+
+        def timed(a, w, out, **k):
+            tc = (a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and not k.get("w_nmajor") and not k.get("a_mmajor")
+                  and k.get("batch", 1) == 1 and k["ldw"] % 8 == 0 and (k.get("conv") is not None or (k["lda"] % 8 == 0 and k["K"] % 8 == 0
+                  and (a.data_ptr() + 2 * k.get("a_off", 0)) % 16 == 0)) and k.get("impl", -1) != 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = inner(a, w, out, **k)
+            e1.record()
+            self.records.append(("gemm.tc" if tc else f"gemm.simt[b{k.get('batch', 1) > 1}]", self.tag, e0, e1))
+            return r
+        return timed
 t1 = Tagged(real_ops)
 class Tagged2(Tagged):
     @property
