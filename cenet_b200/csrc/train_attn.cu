@@ -55,10 +55,15 @@ __device__ __forceinline__ void load_a_global(uint32_t (&a)[4], const bf16* __re
 }
 
 // [64][D] tile (row pitch D + 8) from global rows row0.. (rows >= nrows zero-filled); 128 threads, 16-byte chunks
-template <int D>
+// key / query tiles loaded per __syncthreads round: small head dims do little math per 64-row tile, so several tiles are staged at
+// once and the (exposed) load latency is paid once per KT tiles
+template <int DQK>
+struct KTiles { static constexpr int value = DQK <= 16 ? 4 : (DQK <= 32 ? 2 : 1); };
+
+template <int D, int ROWS = 64>
 __device__ __forceinline__ void load_tile(bf16* __restrict__ sm, const bf16* __restrict__ base, long long ld, int row0, int nrows, int tid) {
   constexpr int CH = D / 8, P = D + 8;
-  for (int i = tid; i < 64 * CH; i += FT) {
+  for (int i = tid; i < ROWS * CH; i += FT) {
     const int r = i / CH, c = (i - r * CH) * 8;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (row0 + r < nrows) u = *reinterpret_cast<const uint4*>(base + (long long)(row0 + r) * ld + c);
@@ -142,8 +147,9 @@ struct FlashArgs {
 // ------------------------------------------------------------------------------------------------ forward
 template <int DQK, int DV>
 __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
-  __shared__ __align__(16) bf16 sK[BKEY * (DQK + 8)];
-  __shared__ __align__(16) bf16 sV[BKEY * (DV + 8)];
+  constexpr int KT = KTiles<DQK>::value;
+  __shared__ __align__(16) bf16 sKb[KT * BKEY * (DQK + 8)];
+  __shared__ __align__(16) bf16 sVb[KT * BKEY * (DV + 8)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, m = blockIdx.y, q0 = blockIdx.x * BQ + warp * 16;
   const bf16* Qp = p.Q + (long long)b * p.Nq * p.ldq + m * DQK;
@@ -159,11 +165,16 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
   for (int j = 0; j < DV / 8; j++)
 #pragma unroll
     for (int e = 0; e < 4; e++) o[j][e] = 0.f;
-  for (int k0 = 0; k0 < p.Nk; k0 += BKEY) {
+  for (int kt0 = 0; kt0 < p.Nk; kt0 += KT * BKEY) {
     __syncthreads();
-    load_tile<DQK>(sK, Kp, p.ldk, k0, p.Nk, tid);
-    load_tile<DV>(sV, Vp, p.ldv, k0, p.Nk, tid);
+    load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
+    load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
     __syncthreads();
+   for (int sb = 0; sb < KT; sb++) {
+    const int k0 = kt0 + sb * BKEY;
+    if (k0 >= p.Nk) break;
+    const bf16* sK = sKb + sb * BKEY * (DQK + 8);
+    const bf16* sV = sVb + sb * BKEY * (DV + 8);
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -206,6 +217,7 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
     uint32_t pf[4][4];
     c_to_a(pf, s);
     mma_a_tile<DV>(o, pf, sV, lane);
+   }
   }
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -249,8 +261,9 @@ __global__ void __launch_bounds__(256) flash_delta_kernel(const FlashArgs p, lon
 // ------------------------------------------------------------------------------------------------ dQ
 template <int DQK, int DV>
 __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
-  __shared__ __align__(16) bf16 sK[BKEY * (DQK + 8)];
-  __shared__ __align__(16) bf16 sV[BKEY * (DV + 8)];
+  constexpr int KT = KTiles<DQK>::value;
+  __shared__ __align__(16) bf16 sKb[KT * BKEY * (DQK + 8)];
+  __shared__ __align__(16) bf16 sVb[KT * BKEY * (DV + 8)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, m = blockIdx.y, q0 = blockIdx.x * BQ + warp * 16;
   const bf16* Qp = p.Q + (long long)b * p.Nq * p.ldq + m * DQK;
@@ -276,11 +289,16 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
   for (int j = 0; j < DQK / 8; j++)
 #pragma unroll
     for (int e = 0; e < 4; e++) dq[j][e] = 0.f;
-  for (int k0 = 0; k0 < p.Nk; k0 += BKEY) {
+  for (int kt0 = 0; kt0 < p.Nk; kt0 += KT * BKEY) {
     __syncthreads();
-    load_tile<DQK>(sK, Kp, p.ldk, k0, p.Nk, tid);
-    load_tile<DV>(sV, Vp, p.ldv, k0, p.Nk, tid);
+    load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
+    load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
     __syncthreads();
+   for (int sb = 0; sb < KT; sb++) {
+    const int k0 = kt0 + sb * BKEY;
+    if (k0 >= p.Nk) break;
+    const bf16* sK = sKb + sb * BKEY * (DQK + 8);
+    const bf16* sV = sVb + sb * BKEY * (DV + 8);
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -299,6 +317,7 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
     uint32_t pf[4][4];
     c_to_a(pf, s);
     mma_a_tile<DQK>(dq, pf, sK, lane);
+   }
   }
   bf16* dQp = p.dQ + (long long)b * p.Nq * p.ldq + m * DQK;
 #pragma unroll
@@ -316,9 +335,10 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
 // MODE 0: dK and dV in one pass; MODE 1: dV only; MODE 2: dK only (large head dims: the two accumulators do not fit together)
 template <int DQK, int DV, int MODE>
 __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
-  __shared__ __align__(16) bf16 sQ[BQ * (DQK + 8)];
-  __shared__ __align__(16) bf16 sG[BQ * (DV + 8)];
-  __shared__ float sL[BQ], sD[BQ];
+  constexpr int KT = KTiles<DQK>::value;
+  __shared__ __align__(16) bf16 sQb[KT * BQ * (DQK + 8)];
+  __shared__ __align__(16) bf16 sGb[KT * BQ * (DV + 8)];
+  __shared__ float sLb[KT * BQ], sDb[KT * BQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, vh = blockIdx.y, kr0 = blockIdx.x * BKEY + warp * 16;
   const bf16* Vp = p.V + (long long)b * p.Nk * p.ldv + vh * DV;
@@ -350,15 +370,21 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
     for (int j = 0; j < (DO_DK ? DQK / 8 : 1); j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) dk[j][e] = 0.f;
-    for (int q0 = 0; q0 < p.Nq; q0 += BQ) {
+    for (int qt0 = 0; qt0 < p.Nq; qt0 += KT * BQ) {
       __syncthreads();
-      load_tile<DQK>(sQ, Qp, p.ldq, q0, p.Nq, tid);
-      load_tile<DV>(sG, dOp, p.ldo, q0, p.Nq, tid);
-      if (tid < BQ) {
-        sL[tid] = q0 + tid < p.Nq ? lsep[q0 + tid] : INFINITY;
-        sD[tid] = q0 + tid < p.Nq ? dlp[q0 + tid] : 0.f;
+      load_tile<DQK, KT * BQ>(sQb, Qp, p.ldq, qt0, p.Nq, tid);
+      load_tile<DV, KT * BQ>(sGb, dOp, p.ldo, qt0, p.Nq, tid);
+      for (int i = tid; i < KT * BQ; i += FT) {
+        sLb[i] = qt0 + i < p.Nq ? lsep[qt0 + i] : INFINITY;
+        sDb[i] = qt0 + i < p.Nq ? dlp[qt0 + i] : 0.f;
       }
       __syncthreads();
+     for (int sb = 0; sb < KT; sb++) {
+      if (qt0 + sb * BQ >= p.Nq) break;
+      const bf16* sQ = sQb + sb * BQ * (DQK + 8);
+      const bf16* sG = sGb + sb * BQ * (DV + 8);
+      const float* sL = sLb + sb * BQ;
+      const float* sD = sDb + sb * BQ;
       float st[8][4];                                  // S^T: rows = keys of this warp, columns = 64 queries
 #pragma unroll
       for (int j = 0; j < 8; j++)
@@ -394,6 +420,7 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
         c_to_a(pf, dpt);
         mma_a_tile<DQK>(dk, pf, sQ, lane);
       }
+     }
     }
     if constexpr (DO_DK) {
       bf16* dKp = p.dK + (long long)b * p.Nk * p.ldk + m * DQK;
