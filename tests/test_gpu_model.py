@@ -146,7 +146,8 @@ def test_other_batch_and_dropin_host_behaviour():
     m2 = copy.deepcopy(m)                                            # utils.py:113
     with torch.no_grad():
         assert torch.equal(m2(xb.to(DEV)), y)
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m(xb.to(DEV))
+    m.train()                                                        # train mode runs the training launch plan
+    with torch.no_grad():
+        y_tr = m(xb.to(DEV))
+    assert y_tr.shape == y.shape and torch.isfinite(y_tr).all()
     m.eval()
