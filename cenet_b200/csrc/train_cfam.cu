@@ -583,18 +583,13 @@ __global__ void __launch_bounds__(kColThreads) ls_combine_bwd_kernel(const T* __
       }
   }
 }
-// dls[c] = sum_b ws[b][0][c];  dw = sum_c sum_b ws[b][1][c]   (one block)
-__global__ void __launch_bounds__(256) ls_combine_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* dls, float* dw) {
+// dw = sum_c percol[c]   (one block; percol = the per-channel sums produced by launch_finalize)
+__global__ void __launch_bounds__(256) ls_combine_finalize_kernel(const float* __restrict__ percol, int C, float* dw) {
   __shared__ float red[8];
   float tw = 0.f;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f, b = 0.f;
-    for (int i = 0; i < nblk; i++) { a += ws[((size_t)i * 2) * C + c]; b += ws[((size_t)i * 2 + 1) * C + c]; }
-    dls[c] = a;
-    tw += b;
-  }
+  for (int c = threadIdx.x; c < C; c += 256) tw += percol[c];
   tw = block_sum_256(tw, red);
-  if (threadIdx.x == 0 && dw) dw[0] = tw;
+  if (threadIdx.x == 0) dw[0] = tw;
 }
 }  // namespace
 
@@ -779,13 +774,18 @@ extern "C" int cenet_ls_combine_bwd(const void* dout, const void* y, const void*
     int Vv = vec_of(sizeof(T), {dout, y, p, dy, dp}, {C});
     if (Vv > 4) Vv = 4;
     ColPlan pl = plan_cols(rows, C, Vv);
-    CENET_REQUIRE((long long)pl.nrb * 2 * C <= ws_elems, "cenet_ls_combine_bwd: workspace too small");
+    CENET_REQUIRE((long long)pl.nrb * 2 * C + C <= ws_elems, "cenet_ls_combine_bwd: workspace too small");
     DISPATCH_V(Vv, (ls_combine_bwd_kernel<T, V><<<dim3(pl.nrb, pl.gy), kColThreads, 0, sm>>>(
                         (const T*)dout, (const T*)y, (const T*)p, s, t, ls, w, (T*)dy, acc_dy, (T*)dp, rows, C, pl.ngrp, pl.nrl,
                         pl.rows_per_block, ws)));
     CENET_LAUNCH_CHECK("ls_combine_bwd");
-    ls_combine_finalize_kernel<<<1, 256, 0, sm>>>(ws, pl.nrb, C, dls, y ? dw : nullptr);
-    CENET_LAUNCH_CHECK("ls_combine_finalize");
+    // dls[c] = sum_b ws[b][0][c];  dw = sum_c sum_b ws[b][1][c]
+    float* percol = ws + (size_t)pl.nrb * 2 * C;
+    if (launch_finalize(ws, pl.nrb, 2 * C, dls, C, y ? percol : nullptr, 1.f, sm)) return -1;
+    if (y) {
+      ls_combine_finalize_kernel<<<1, 256, 0, sm>>>(percol, C, dw);
+      CENET_LAUNCH_CHECK("ls_combine_finalize");
+    }
   });
   return 0;
 }

@@ -50,9 +50,40 @@ __device__ __forceinline__ void col_block_reduce(float (&acc)[V], float* smem, i
   }
 }
 
+// Stage 2 helper.  A finalize block is 256 threads = kFinOut outputs x kFinLanes lanes (o = tid % kFinOut, lane = tid /
+// kFinOut): lane l adds the partials b = l, l + kFinLanes, ... (independent loads, 4 in flight), the lanes are then added
+// in lane order through shared memory.  Fixed summation order -> bit-reproducible; the serial chain per output is
+// nblk / kFinLanes long instead of nblk.  K quantities at once; the result is valid in the lane-0 threads.
+constexpr int kFinOut = 8, kFinLanes = 32, kFinThreads = kFinOut * kFinLanes;
+template <int K, typename Acc, typename F>
+__device__ __forceinline__ void fin_lane_sums(int nblk, bool valid, Acc (&tot)[K], Acc* smem /* [K][kFinLanes][kFinOut] */, F&& load) {
+  const int o = threadIdx.x % kFinOut, lane = threadIdx.x / kFinOut;
+  Acc s[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) s[k] = (Acc)0;
+  if (valid) {
+#pragma unroll 4
+    for (int b = lane; b < nblk; b += kFinLanes) {
+#pragma unroll
+      for (int k = 0; k < K; k++) s[k] += (Acc)load(b, k);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) smem[(k * kFinLanes + lane) * kFinOut + o] = s[k];
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      Acc t = (Acc)0;
+      for (int l = 0; l < kFinLanes; l++) t += smem[(k * kFinLanes + l) * kFinOut + o];
+      tot[k] = t;
+    }
+  }
+}
+
 // out[i] = scale * sum_b ws[b * n + i]   (i < n); the first nA go to outA, the rest to outB
-__global__ void __launch_bounds__(256) finalize_partials_kernel(const float* __restrict__ ws, int nblk, int n, float* outA, int nA,
-                                                                float* outB, float scale);
+__global__ void __launch_bounds__(kFinThreads) finalize_partials_kernel(const float* __restrict__ ws, int nblk, int n, float* outA,
+                                                                        int nA, float* outB, float scale);
 
 int launch_finalize(const float* ws, int nblk, int n, float* outA, int nA, float* outB, float scale, cudaStream_t s);
 

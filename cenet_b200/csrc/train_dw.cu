@@ -7,16 +7,33 @@
 #include "train_common.cuh"
 
 namespace {
+// V consecutive elements as one raw vector register (kept packed until use)
 template <typename T, int V>
-__global__ void __launch_bounds__(kColThreads) dw_wgrad_partial_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dz,
+struct alignas(sizeof(T) * V) RawVec { T v[V]; };
+template <typename T, int V>
+__device__ __forceinline__ RawVec<T, V> ld_raw(const T* p) { return *reinterpret_cast<const RawVec<T, V>*>(p); }
+template <typename T, int V>
+__device__ __forceinline__ void unpack_raw(const RawVec<T, V>& r, float (&o)[V]) {
+#pragma unroll
+  for (int i = 0; i < V; i++) o[i] = (float)r.v[i];
+}
+
+// Stage 1 of the filter gradient  dw[c, kh, kw] = sum_{b,h,w} dz[b,h,w,c] * x[b, h+(kh-1)d, w+(kw-1)d, c]  (+ dbias = sum dz).
+// Work unit = one IMAGE ROW (b, h): a thread owns V channels and walks the row left to right, so the pixel index math
+// (one 32-bit division) is paid per row, not per pixel.  For the common case (dilation 1, no fused up-sampling) the 3x3
+// neighbourhood slides through registers: per pixel a thread issues 4 vector loads (dz and one new x column of three
+// rows) instead of 10, and every x element is fetched three times overall (by the rows above / at / below), which L1/L2
+// absorb -- HBM sees x and dz once.  A block is `ngrp` channel groups x `nrl` row lanes; adjacent lanes take adjacent rows.
+template <typename T, int V, bool WINDOW>
+__global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dz,
                                                                        long long ldz, int B, int H, int W, int C, int dil, int up2,
                                                                        int ngrp, int nrl, int rows_per_block, float* __restrict__ ws) {
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
-  const long long rows = (long long)B * H * W;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(rows, r0 + rows_per_block);
+  const int R = B * H;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
   const int Hi = up2 ? H >> 1 : H, Wi = up2 ? W >> 1 : W;
   float acc[10][V];
 #pragma unroll
@@ -24,29 +41,96 @@ __global__ void __launch_bounds__(kColThreads) dw_wgrad_partial_kernel(const T* 
 #pragma unroll
     for (int v = 0; v < V; v++) acc[k][v] = 0.f;
   if (c0 < C) {
-    for (long long r = r0 + rl; r < r1; r += nrl) {
-      const int w = (int)(r % W);
-      const long long t = r / W;
-      const int h = (int)(t % H), b = (int)(t / H);
-      float g[V];
-      ldv<V>(dz + r * ldz + c0, g);
+    for (int r = r0 + rl; r < r1; r += nrl) {
+      const int b = r / H, h = r - b * H;
+      const T* zrow = dz + (long long)r * W * ldz + c0;
+      if constexpr (WINDOW) {
+        // Software pipeline: the loads of step t (dz[t] and the x column t+1 of the three rows) are issued DEPTH steps
+        // ahead into a ring of raw registers, unconditionally (clamped addresses, zeroed on use), so that a warp keeps
+        // DEPTH * 4 vector loads in flight instead of waiting one memory latency per pixel.
+        constexpr int DEPTH = 2;
+        static_assert(6 % DEPTH == 0, "ring depth must divide the unroll factor");
+        const T* xr[3];
+        bool ok[3];
 #pragma unroll
-      for (int v = 0; v < V; v++) acc[9][v] += g[v];
-      const T* xb = x + (long long)b * Hi * Wi * ldx + c0;
+        for (int dh = 0; dh < 3; dh++) {
+          const int hh = h + dh - 1;
+          ok[dh] = hh >= 0 && hh < H;
+          xr[dh] = x + (long long)(b * H + (ok[dh] ? hh : h)) * W * ldx + c0;
+        }
+        RawVec<T, V> rz[DEPTH], rx[DEPTH][3];
 #pragma unroll
-      for (int dh = -1; dh <= 1; dh++) {
-        const int hh = h + dh * dil;
-        if (hh < 0 || hh >= H) continue;
-        const int hs = up2 ? hh >> 1 : hh;
+        for (int t = 0; t < DEPTH; t++) {
+          const int tz = min(t, W - 1), tx = min(t + 1, W - 1);
+          rz[t] = ld_raw<T, V>(zrow + (long long)tz * ldz);
 #pragma unroll
-        for (int dw = -1; dw <= 1; dw++) {
-          const int ww = w + dw * dil;
-          if (ww < 0 || ww >= W) continue;
-          const int wsrc = up2 ? ww >> 1 : ww;
-          float xv[V];
-          ldv<V>(xb + ((long long)hs * Wi + wsrc) * ldx, xv);
+          for (int dh = 0; dh < 3; dh++) rx[t][dh] = ld_raw<T, V>(xr[dh] + (long long)tx * ldx);
+        }
+        float col[3][3][V];                       // [slot][dh][v]: slots rotate over the columns w-1, w, w+1
 #pragma unroll
-          for (int v = 0; v < V; v++) acc[(dh + 1) * 3 + dw + 1][v] = fmaf(g[v], xv[v], acc[(dh + 1) * 3 + dw + 1][v]);
+        for (int dh = 0; dh < 3; dh++) {
+          unpack_raw<T, V>(ld_raw<T, V>(xr[dh]), col[0][dh]);
+#pragma unroll
+          for (int v = 0; v < V; v++) { col[2][dh][v] = 0.f; col[0][dh][v] = ok[dh] ? col[0][dh][v] : 0.f; }
+        }
+        for (int wb = 0; wb < W; wb += 6) {
+#pragma unroll
+          for (int u = 0; u < 6; u++) {
+            const int w = wb + u;
+            if (w < W) {
+              const int sl = (u + 2) % 3, sc = u % 3, sr = (u + 1) % 3;       // window slots of columns w-1, w, w+1
+              const int rs = u % DEPTH;                                        // ring slot of step w (DEPTH divides 6)
+              float g[V];
+              unpack_raw<T, V>(rz[rs], g);
+              const bool last = w + 1 >= W;
+#pragma unroll
+              for (int dh = 0; dh < 3; dh++) {
+                unpack_raw<T, V>(rx[rs][dh], col[sr][dh]);
+#pragma unroll
+                for (int v = 0; v < V; v++) col[sr][dh][v] = (ok[dh] && !last) ? col[sr][dh][v] : 0.f;
+              }
+              {                                                                // refill the slot with step w + DEPTH
+                const int tz = min(w + DEPTH, W - 1), tx = min(w + DEPTH + 1, W - 1);
+                rz[rs] = ld_raw<T, V>(zrow + (long long)tz * ldz);
+#pragma unroll
+                for (int dh = 0; dh < 3; dh++) rx[rs][dh] = ld_raw<T, V>(xr[dh] + (long long)tx * ldx);
+              }
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[9][v] += g[v];
+#pragma unroll
+              for (int dh = 0; dh < 3; dh++)
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                  acc[dh * 3 + 0][v] = fmaf(g[v], col[sl][dh][v], acc[dh * 3 + 0][v]);
+                  acc[dh * 3 + 1][v] = fmaf(g[v], col[sc][dh][v], acc[dh * 3 + 1][v]);
+                  acc[dh * 3 + 2][v] = fmaf(g[v], col[sr][dh][v], acc[dh * 3 + 2][v]);
+                }
+            }
+          }
+        }
+      } else {
+        const T* xb = x + (long long)b * Hi * Wi * ldx + c0;
+        for (int w = 0; w < W; w++) {
+          float g[V];
+          ldv<V>(zrow + (long long)w * ldz, g);
+#pragma unroll
+          for (int v = 0; v < V; v++) acc[9][v] += g[v];
+#pragma unroll
+          for (int dh = -1; dh <= 1; dh++) {
+            const int hh = h + dh * dil;
+            if (hh < 0 || hh >= H) continue;
+            const int hs = up2 ? hh >> 1 : hh;
+#pragma unroll
+            for (int dw = -1; dw <= 1; dw++) {
+              const int ww = w + dw * dil;
+              if (ww < 0 || ww >= W) continue;
+              const int wsrc = up2 ? ww >> 1 : ww;
+              float xv[V];
+              ldv<V>(xb + ((long long)hs * Wi + wsrc) * ldx, xv);
+#pragma unroll
+              for (int v = 0; v < V; v++) acc[(dh + 1) * 3 + dw + 1][v] = fmaf(g[v], xv[v], acc[(dh + 1) * 3 + dw + 1][v]);
+            }
+          }
         }
       }
     }
@@ -63,11 +147,13 @@ __global__ void __launch_bounds__(kColThreads) dw_wgrad_partial_kernel(const T* 
 }
 
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* dw, float* dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 10 * C) return;
+  __shared__ float sm[kFinThreads];
+  const int i = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   const int k = i / C, c = i % C;
-  float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += ws[((size_t)b * 10 + k) * C + c];
+  float t[1];
+  fin_lane_sums<1>(nblk, i < 10 * C, t, sm, [&](int b, int) { return ws[((size_t)b * 10 + k) * C + c]; });
+  if (threadIdx.x >= kFinOut || i >= 10 * C) return;
+  const float s = t[0];
   if (k < 9) dw[c * 9 + k] = s;
   else if (dbias) dbias[c] = s;
 }
@@ -169,12 +255,27 @@ extern "C" int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, 
   CENET_DISPATCH(x_dtype, T, {
     int Vv = vec_of(sizeof(T), {x, dz}, {C, ldx, ldz});
     if (Vv > 4) Vv = 4;                                   // 10 accumulators per channel: keep the register footprint small
+    // rows of the plan are IMAGE rows (b, h); every thread takes whole rows, at least one
     ColPlan p = plan_cols(rows, C, Vv);
+    const int R = B * H;
+    {
+      long long want = (R + p.nrl - 1) / p.nrl;
+      long long cap = std::max(1, 8 * kNumSMs / p.gy);
+      if (want > cap) want = cap;
+      const long long per = (R + want - 1) / want;
+      p.rows_per_block = (int)((per + p.nrl - 1) / p.nrl * p.nrl);
+      p.nrb = (R + p.rows_per_block - 1) / p.rows_per_block;
+    }
     CENET_REQUIRE((long long)p.nrb * 10 * C <= ws_elems, "cenet_dwconv3x3_wgrad: workspace too small");
-    DISPATCH_V(Vv, (dw_wgrad_partial_kernel<T, V><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
-                        (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, ws)));
+    if (dil == 1 && !up2) {
+      DISPATCH_V(Vv, (dw_wgrad_partial_kernel<T, V, true><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
+                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, ws)));
+    } else {
+      DISPATCH_V(Vv, (dw_wgrad_partial_kernel<T, V, false><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
+                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, ws)));
+    }
     CENET_LAUNCH_CHECK("dw_wgrad_partial");
-    dw_wgrad_finalize_kernel<<<cdiv(10 * C, 256), 256, 0, s>>>(ws, p.nrb, C, dw, dbias);
+    dw_wgrad_finalize_kernel<<<cdiv(10 * C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, dw, dbias);
     CENET_LAUNCH_CHECK("dw_wgrad_finalize");
   });
   return 0;

@@ -10,23 +10,29 @@
 namespace {
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 
-// one block per (b, c) plane; dynamic smem: Y, DZ, T, ACC, R[ns] (each HW floats)
+// one block per (b, c) plane; working set: Y, DZ, T, ACC, R[ns] (each HW floats).  It lives in dynamic shared memory when
+// it fits (planes up to 56x56 with 3 scales); larger planes (128x128 at 512x512 inputs) use a per-block slab of the
+// workspace instead (`scratch`, L2-resident) and the blocks stride over the planes.
 template <typename T>
 __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gate, const T* __restrict__ dz,
                                                       const float* __restrict__ wch, T* __restrict__ dy, int acc_dy, T* __restrict__ dgate,
                                                       int C2, int H, int W, const float* __restrict__ mats,
-                                                      const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws) {
-  extern __shared__ float sm[];
+                                                      const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws,
+                                                      int nplanes, float* __restrict__ scratch) {
+  extern __shared__ float sm_dyn[];
   __shared__ float red[8];
   const int HW = H * W;
+  float* sm = scratch ? scratch + (size_t)blockIdx.x * (4 + ns) * HW : sm_dyn;
   float* Y = sm;
   float* DZ = Y + HW;
   float* Tm = DZ + HW;
   float* ACC = Tm + HW;
   float* R = ACC + HW;                 // [ns][HW]
-  const int plane = blockIdx.x, c = plane % C2;
-  const long long base = (long long)plane * HW;
   const int tid = threadIdx.x;
+  for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+  const int c = plane % C2;
+  const long long base = (long long)plane * HW;
+  __syncthreads();                     // the previous plane of this block is done with the working set
   for (int i = tid; i < HW; i += 256) { Y[i] = ldf(y + base + i); DZ[i] = ldf(dz + base + i); }
   __syncthreads();
   // forward residuals R_s = Y - A_h Y A_w^T
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
     float t = 0.f;
     for (int w = 0; w < 8; w++) t += red[w];
     ws[plane] = t;
+  }
   }
 }
 // dw[c] = sum_b ws[b*C2 + c]
@@ -348,8 +355,18 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
   CENET_REQUIRE(nscales >= 1 && nscales <= 3, "cenet_fea_bwd: 1..3 scales");
   CENET_REQUIRE(H <= nmax && W <= nmax, "cenet_fea_bwd: operator matrices smaller than the plane");
   CENET_REQUIRE((long long)B * C2 <= ws_elems, "cenet_fea_bwd: workspace too small");
-  const size_t smem = (size_t)(4 + nscales) * H * W * sizeof(float);
-  CENET_REQUIRE(smem <= 200 * 1024, "cenet_fea_bwd: plane %dx%d does not fit in shared memory", H, W);
+  const size_t slab = (size_t)(4 + nscales) * H * W;            // floats of working set per plane
+  size_t smem = slab * sizeof(float);
+  const int nplanes = B * C2;
+  int blocks = nplanes;
+  float* scratch = nullptr;
+  if (smem > 200 * 1024) {                                      // big planes: working set in the workspace, after the partials
+    const long long room = (ws_elems - nplanes) / (long long)slab;
+    CENET_REQUIRE(room >= 1, "cenet_fea_bwd: plane %dx%d needs %zu workspace floats per block", H, W, slab);
+    blocks = (int)std::min<long long>(std::min<long long>(nplanes, room), 2LL * kNumSMs);
+    scratch = ws + nplanes;
+    smem = 0;
+  }
   cudaStream_t s = to_stream(st);
   CENET_DISPATCH(dtype, T, {
     static std::atomic<size_t> configured{0};
@@ -357,8 +374,8 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
       cudaFuncSetAttribute(fea_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured.store(200 * 1024);
     }
-    fea_bwd_kernel<T><<<B * C2, 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
-                                                bands, nmax, nscales, ws);
+    fea_bwd_kernel<T><<<blocks, 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
+                                                bands, nmax, nscales, ws, nplanes, scratch);
     CENET_LAUNCH_CHECK("fea_bwd");
   });
   fea_dw_finalize_kernel<<<cdiv(C2, 128), 128, 0, s>>>(ws, B, C2, dw);
@@ -428,6 +445,32 @@ extern "C" int cenet_head_upsample_bwd(const float* dlogits, float* dyh, int B, 
   if (total == 0) return 0;
   head_upsample_bwd_kernel<<<cdiv(total, 256), 256, 0, to_stream(st)>>>(dlogits, dyh, B, h, w, ncls);
   CENET_LAUNCH_CHECK("head_upsample_bwd");
+  return 0;
+}
+
+// dst[i] = map[i] ? src[map[i] - 1] : 0 -- the per-step re-pack of the master weights into every compute layout at once
+template <typename TO>
+__global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ map, TO* __restrict__ dst,
+                                                          long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int4 m = reinterpret_cast<const int4*>(map)[i];
+    float v[4];
+    v[0] = m.x ? __ldg(src + m.x - 1) : 0.f;
+    v[1] = m.y ? __ldg(src + m.y - 1) : 0.f;
+    v[2] = m.z ? __ldg(src + m.z - 1) : 0.f;
+    v[3] = m.w ? __ldg(src + m.w - 1) : 0.f;
+    stv<4>(dst + i * 4, v);
+  }
+}
+
+extern "C" int cenet_gather_cast(const float* src, const int* map, void* dst, int dst_dtype, long long n, cenet_stream_t st) {
+  CENET_REQUIRE(src && map && dst, "cenet_gather_cast: null pointer");
+  CENET_REQUIRE(n % 4 == 0 && ((((uintptr_t)map | (uintptr_t)dst) & 15) == 0), "cenet_gather_cast: n %% 4 == 0 and 16-byte aligned buffers");
+  if (n == 0) return 0;
+  CENET_DISPATCH(dst_dtype, T, {
+    gather_cast_kernel<T><<<ew_blocks(n / 4), 256, 0, to_stream(st)>>>(src, map, (T*)dst, n / 4);
+    CENET_LAUNCH_CHECK("gather_cast");
+  });
   return 0;
 }
 

@@ -4,19 +4,20 @@
 // deterministic (train_common.cuh).
 #include "train_common.cuh"
 
-__global__ void __launch_bounds__(256) finalize_partials_kernel(const float* __restrict__ ws, int nblk, int n, float* outA, int nA,
-                                                                float* outB, float scale) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += ws[(size_t)b * n + i];
-  s *= scale;
+__global__ void __launch_bounds__(kFinThreads) finalize_partials_kernel(const float* __restrict__ ws, int nblk, int n, float* outA,
+                                                                        int nA, float* outB, float scale) {
+  __shared__ float sm[kFinThreads];
+  const int i = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
+  float t[1];
+  fin_lane_sums<1>(nblk, i < n, t, sm, [&](int b, int) { return ws[(size_t)b * n + i]; });
+  if (threadIdx.x >= kFinOut || i >= n) return;
+  const float s = t[0] * scale;
   if (i < nA) { if (outA) outA[i] = s; }
   else if (outB) outB[i - nA] = s;
 }
 
 int launch_finalize(const float* ws, int nblk, int n, float* outA, int nA, float* outB, float scale, cudaStream_t s) {
-  finalize_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(ws, nblk, n, outA, nA, outB, scale);
+  finalize_partials_kernel<<<cdiv(n, kFinOut), kFinThreads, 0, s>>>(ws, nblk, n, outA, nA, outB, scale);
   CENET_LAUNCH_CHECK("finalize_partials");
   return 0;
 }
@@ -58,11 +59,14 @@ __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const T* 
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ ws, int nblk, int C, long long rows, const float* gamma,
                                          const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                                          float* scale, float* shift, float* mean, float* rstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double sm[2 * kFinThreads];
+  const int c = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
+  double t[2];
+  fin_lane_sums<2>(nblk, c < C, t, sm, [&](int i, int k) { return ws[((size_t)i * 2 + k) * C + c]; });
+  if (threadIdx.x >= kFinOut) return;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; i++) { a += ws[((size_t)i * 2) * C + c]; b += ws[((size_t)i * 2 + 1) * C + c]; }
+  const double a = t[0], b = t[1];
   const double mu = a / (double)rows;
   double var = b / (double)rows - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -159,10 +163,12 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const T* __
 
 // sums[0..C) = d(beta), sums[C..2C) = d(gamma); also written to the parameter gradients
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* sums, float* dgamma, float* dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int i = 0; i < nblk; i++) { a += ws[((size_t)i * 2) * C + c]; b += ws[((size_t)i * 2 + 1) * C + c]; }
+  __shared__ float sm[2 * kFinThreads];
+  const int c = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
+  float t[2];
+  fin_lane_sums<2>(nblk, c < C, t, sm, [&](int i, int k) { return ws[((size_t)i * 2 + k) * C + c]; });
+  if (threadIdx.x >= kFinOut || c >= C) return;
+  const float a = t[0], b = t[1];
   sums[c] = a;
   sums[C + c] = b;
   if (dbeta) dbeta[c] = a;
@@ -326,7 +332,7 @@ extern "C" int cenet_bn_stats(const void* x, int x_dtype, long long ldx, long lo
     DISPATCH_V(Vv, (bn_stats_partial_kernel<T, V><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
                         (const T*)x, ldx, rows, C, p.ngrp, p.nrl, p.rows_per_block, ws)));
     CENET_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, p.nrb, C, rows, gamma, beta, rmean, rvar, nbt, momentum, eps, scale,
+    bn_stats_finalize_kernel<<<cdiv(C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, rows, gamma, beta, rmean, rvar, nbt, momentum, eps, scale,
                                                           shift, mean, rstd);
     CENET_LAUNCH_CHECK("bn_stats_finalize");
   });
@@ -373,7 +379,7 @@ extern "C" int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_d
                         (const T*)dy, (const T*)y, ldy, (const T*)a, lda, mean, rstd, rows, C, act, slope, p.ngrp, p.nrl,
                         p.rows_per_block, ws)));
     CENET_LAUNCH_CHECK("bn_bwd_partial");
-    bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(ws, p.nrb, C, sums, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<cdiv(C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, sums, dgamma, dbeta);
     CENET_LAUNCH_CHECK("bn_bwd_finalize");
     const long long total = rows * (C / Vv);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);

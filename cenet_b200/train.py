@@ -30,11 +30,110 @@ import os
 
 import torch
 
-from . import ops
-from . import train_ops as tops
+from . import ops as _ops_mod
+from . import train_ops as _tops_mod
 from .engine import _MCA_RATES, _PVT, _rup, lambda_init
 from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT
 from .train_ops import ACT_GELU_GRAD
+
+
+def _storage_ranges(objs, out):
+    """[lo, hi) device address ranges of the storages behind every tensor found in `objs` (recursing into containers)"""
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                st = o.untyped_storage()
+                out.append((st.data_ptr(), st.data_ptr() + st.nbytes()))
+        elif isinstance(o, dict):
+            _storage_ranges(o.values(), out)
+        elif isinstance(o, (list, tuple)):
+            _storage_ranges(o, out)
+    return out
+
+
+class _WgradStream:
+    """Second CUDA stream for the weight-gradient kernels of the backward pass.
+
+    At batch 24 most backward GEMMs occupy a fraction of the 148 SMs; d(weight) of a layer is needed by nobody until the
+    gradient bucket closes, while d(input) is on the critical path.  `run(reads, fn)` launches `fn` (the wgrad kernels)
+    on the side stream, ordered after everything already enqueued on the launching stream, and remembers the storages it
+    READS.  Every later launch on the main stream goes through `guard`: if one of its tensors lives in a storage a
+    pending side launch still reads (e.g. a residual-stream gradient buffer that is about to be accumulated into), the
+    main stream first waits for that side launch.  The check is conservative (a main-stream READ of the same storage
+    also waits).  Outputs of the side launches (parameter gradients, the side workspace) are disjoint from everything
+    the main stream touches before `join`, which the engine calls before a gradient bucket is handed to the all-reduce
+    and before the optimizer.  Inside CUDA graph capture the event record/wait pairs become fork/join edges."""
+
+    def __init__(self, dev):
+        self.stream = torch.cuda.Stream(dev)
+        self.pending = []                       # [(done event, [(lo, hi), ...])] in launch order
+        self.waits = self.launches = 0
+
+    def run(self, reads, fn):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        _hazards.cur = None                     # the guard must not see the side launches themselves
+        try:
+            with torch.cuda.stream(self.stream):
+                fn()
+                done = torch.cuda.Event()
+                done.record(self.stream)
+        finally:
+            _hazards.cur = self
+        self.pending.append((done, _storage_ranges(reads, [])))
+        self.launches += 1
+
+    def guard(self, args, kwargs):
+        mine = _storage_ranges(kwargs.values(), _storage_ranges(args, []))
+        last = -1
+        for i, (_, rs) in enumerate(self.pending):
+            if any(lo < b and a < hi for (lo, hi) in rs for (a, b) in mine):
+                last = i
+        if last >= 0:
+            torch.cuda.current_stream().wait_event(self.pending[last][0])       # in-order stream: covers 0..last
+            del self.pending[:last + 1]
+            self.waits += 1
+
+    def join(self):
+        if self.pending:
+            torch.cuda.current_stream().wait_event(self.pending[-1][0])
+            self.pending.clear()
+
+
+class _Hazards:
+    cur = None                                  # the _WgradStream of the backward pass in flight (None: nothing to check)
+
+
+_hazards = _Hazards()
+
+
+class _Guarded:
+    """Proxy over an ops module: every kernel launch first passes `_WgradStream.guard` (see there)."""
+    _PLAIN = ("ccu_nchunk", "loss_nblocks", "launch_count", "dt", "make_tables")
+
+    def __init__(self, inner):
+        object.__setattr__(self, "_inner", inner)
+
+    def __setattr__(self, name, value):
+        setattr(self._inner, name, value)
+
+    def __getattr__(self, name):
+        fn = getattr(self._inner, name)
+        if not callable(fn) or name in _Guarded._PLAIN:
+            return fn
+
+        def launch(*a, **k):
+            side = _hazards.cur
+            if side is not None and side.pending:
+                side.guard(a, k)
+            return fn(*a, **k)
+        return launch
+
+
+ops = _Guarded(_ops_mod)
+tops = _Guarded(_tops_mod)
 
 FLASH_DIMS = {(8, 16), (16, 32), (32, 64), (64, 64), (128, 128), (80, 160)}       # (dqk, dv) instantiated in train_attn.cu
 
@@ -64,6 +163,11 @@ class TrainEngine:
         self._graphs = {}
         self.taps = None
         self.launches_per_step = None
+        self._pack_maps = None                # [(int32 index map, flat packed buffer)] once built (see pack)
+        self._trace = None
+        # weight-gradient kernels on a second stream (see _WgradStream); CENET_B200_WGRAD_STREAM=0 keeps one stream
+        self.side = (_WgradStream(self.dev) if self.dev.type == "cuda" and
+                     os.environ.get("CENET_B200_WGRAD_STREAM", "1") == "1" else None)
         self._flatten()
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -120,6 +224,9 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------------------ packing
     def _put(self, name, t, dtype=None):
+        if self._trace is not None:                       # index-tracing pass of _build_pack_maps
+            self._trace[name] = t.to(torch.float64).contiguous()
+            return None
         t = t.to(self.dev, dtype or torch.float32).contiguous()
         old = self.w.get(name)
         if old is not None and old.shape == t.shape and old.dtype == t.dtype:
@@ -162,14 +269,71 @@ class TrainEngine:
         self._put(name + ".w9f", m.flip(0))
 
     def pack(self):
-        """Compute-dtype copies of the master weights (once per optimizer step)."""
+        """Compute-dtype copies of the master weights (once per optimizer step).
+
+        The layouts are defined by the torch expressions of `_pack_torch` (cast, transpose, tap permutation, flip, zero
+        padding, concatenation).  On the GPU they are evaluated ONCE: `_build_pack_maps` replays the same expressions on
+        a tensor of element indices, which yields for every packed element the master-weight element it copies; from then
+        on a step re-packs with one `gather_cast` launch per dtype instead of ~600 small torch kernels."""
+        if self._pack_maps is None:
+            self._pack_torch()
+            if self.dev.type == "cuda" and os.environ.get("CENET_B200_PACK_GATHER", "1") == "1":
+                self._build_pack_maps()
+            return
+        for idx, dst in self._pack_maps:
+            tops.gather_cast(self.pflat, idx, dst)
+        self._pack_stem()
+
+    def _pack_stem(self):
+        """patch_embed1: with one input channel the three replicated channels fold into SUMMED filters (not a gather)"""
+        w = self.P["backbone.patch_embed1.proj.weight"]
+        if self.cfg["input_channels"] == 1:
+            w = w.sum(1, keepdim=True)                                           # cat([x,x,x]) == summed filters
+        self._pack_conv("backbone.patch_embed1.proj", w, im2col=True)
+
+    def _build_pack_maps(self):
+        real_P, n = self.P, self.n_flat
+        ids = torch.arange(1, n + 1, dtype=torch.float64, device=self.dev)          # 0 is reserved for "zero padding"
+        self.P = {k: ids[self.param_offsets[k]:self.param_offsets[k] + v.numel()].view(v.shape) for k, v in real_P.items()}
+        self._trace = {}
+        try:
+            self._pack_torch(stem=False)
+        finally:
+            traced, self._trace, self.P = self._trace, None, real_P
+        maps = []
+        for dtype in (torch.bfloat16, torch.float32):
+            names = [k for k in traced if self.w[k].dtype == dtype]
+            if not names:
+                continue
+            offs, tot = {}, 0
+            for k in names:
+                offs[k] = tot
+                tot += _rup(self.w[k].numel(), 64)
+            dst = torch.zeros(tot, device=self.dev, dtype=dtype)
+            idx = torch.zeros(tot, device=self.dev, dtype=torch.int32)
+            for k in names:
+                old, t = self.w[k], traced[k]
+                if t.shape != old.shape:
+                    raise RuntimeError(f"pack map of {k}: traced shape {tuple(t.shape)} != packed shape {tuple(old.shape)}")
+                view = dst[offs[k]:offs[k] + old.numel()].view(old.shape)
+                view.copy_(old)
+                idx[offs[k]:offs[k] + old.numel()] = t.flatten().round().to(torch.int32)
+                self.w[k] = view
+            want = dst.clone()
+            tops.gather_cast(self.pflat, idx, dst)
+            if not torch.equal(want, dst):
+                raise RuntimeError("cenet_b200: the gathered weight pack differs from the torch-evaluated layouts")
+            maps.append((idx, dst))
+        self._pack_maps = maps
+
+    def _pack_torch(self, stem=True):
         P, cfg = self.P, self.cfg
+        if stem:
+            self._pack_stem()
         for s in range(4):
             pe = f"backbone.patch_embed{s+1}"
-            w = P[pe + ".proj.weight"]
-            if s == 0 and cfg["input_channels"] == 1:
-                w = w.sum(1, keepdim=True)                                       # cat([x,x,x]) == summed filters
-            self._pack_conv(pe + ".proj", w, im2col=True)
+            if s > 0:
+                self._pack_conv(pe + ".proj", P[pe + ".proj.weight"], im2col=True)
             for i in range(_PVT["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 for n in ("attn.q", "attn.kv", "attn.proj", "mlp.fc1", "mlp.fc2"):
@@ -266,6 +430,17 @@ class TrainEngine:
         """scratch for two-stage reductions (consumed inside the launching op, so one shared buffer is enough)"""
         return self.buf("ws.reduce", (max(n, 1 << 24),), torch.float32)
 
+    def _wws(self):
+        """workspace of the weight-gradient kernels: their own buffer when they run on the side stream"""
+        return self._ws(0) if self.side is None else self.buf("ws.wgrad", (1 << 24,), torch.float32)
+
+    def _wgrad(self, reads, fn):
+        """launch weight-gradient kernels `fn` (which read the tensors `reads`) off the critical path"""
+        if self.side is None or _hazards.cur is not self.side:
+            fn()
+        else:
+            self.side.run(reads, fn)
+
     # ------------------------------------------------------------------------------------------------ primitives
     def lin(self, x, name, out, *, M=None, N=None, K=None, lda=None, a_off=0, ldc=None, c_off=0, bias=None,
             wname=None, drop=None, drop_div=1, res1=None, dmul=None, x_needs_grad=True, wgrads=None):
@@ -302,10 +477,13 @@ class TrainEngine:
                          row_scale=drop, rs_div=drop_div, mul=dmul, ldmul=dmul.stride(0) if dmul is not None else 0,
                          mul_act=ACT_GELU_GRAD if dmul is not None else ACT_NONE,
                          res1=dx if acc else None, ldr1=lda, r1_off=a_off, impl=self.gemm_impl)
-            for pn, r0, nr in wgrads:
-                gb = self.GP.get(pn + ".bias") if (bias is not None) else None
-                tops.gemm_wgrad(dy, x, self.GP[pn + ".weight"], M=M, N=nr, K=Kr, ldy=ldc, y_off=c_off + r0, ldx=lda,
-                                x_off=a_off, row_scale=drop, rs_div=drop_div, dbias=gb, ws=self._ws(0))
+
+            def wg():
+                for pn, r0, nr in wgrads:
+                    gb = self.GP.get(pn + ".bias") if (bias is not None) else None
+                    tops.gemm_wgrad(dy, x, self.GP[pn + ".weight"], M=M, N=nr, K=Kr, ldy=ldc, y_off=c_off + r0, ldx=lda,
+                                    x_off=a_off, row_scale=drop, rs_div=drop_div, dbias=gb, ws=self._wws())
+            self._wgrad((dy, x), wg)            # (drop is written only before the forward)
         self.tape.append(bwd)
         return out
 
@@ -367,8 +545,6 @@ class TrainEngine:
         def bwd():
             dz = self.G(pre)
             gb = self.GP[name + ".bias"] if bias is not None else None
-            tops.dwconv3x3_wgrad(x, dz, self.GP[name + ".weight"], gb, B, H, W, Cc, dil, up2, ldx or Cc, x_off, ldp, p_off,
-                                 self._ws(0))
             dx = self.G(x)
             if up2:
                 full = self.buf("tmp.dwup." + name, (B * H * W, Cc))
@@ -378,6 +554,8 @@ class TrainEngine:
             else:
                 self.wr(x, x_off)                      # single consumer per channel slice: plain write
                 ops.dwconv3x3(dz, dx, w9f, B, H, W, Cc, ldx=ldp, x_off=p_off, ldy=ldx, y_off=x_off, dil=dil)
+            self._wgrad((x, dz), lambda: tops.dwconv3x3_wgrad(x, dz, self.GP[name + ".weight"], gb, B, H, W, Cc, dil, up2,
+                                                              ldx or Cc, x_off, ldp, p_off, self._wws()))
         self.tape.append(bwd)
         return out
 
@@ -390,18 +568,18 @@ class TrainEngine:
 
         def bwd():
             dy = self.G(out)
-            if self.T == torch.bfloat16:
-                tops.conv_wgrad(dy, x4, self.GP[name + ".weight"], k, self._ws(0))      # taps gathered inside the kernel
+            dx = self.G(x4)
+            acc = self.wr(x4)
+            ops.conv_nhwc(dy.view(B, H, W, Cout), WT, dx.view(B * H * W, Cin), k, 1, k // 2, res1=dx if acc else None,
+                          ldr1=Cin, impl=self.gemm_impl)
+            if self.T == torch.bfloat16:                                                # taps gathered inside the kernel
+                self._wgrad((dy, x4), lambda: tops.conv_wgrad(dy, x4, self.GP[name + ".weight"], k, self._wws()))
             else:
                 Kp = _rup(k * k * Cin, 8)
                 col = self.buf(key + ".col", (B * H * W, Kp))
                 ops.im2col(x4, col, B, H, W, Cin, k, 1, k // 2, H, W, Kp)
                 tops.gemm_wgrad(dy, col, self.GP[name + ".weight"], M=B * H * W, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0,
                                 ldx=Kp, x_off=0, T=k * k, ws=self._ws(0))
-            dx = self.G(x4)
-            acc = self.wr(x4)
-            ops.conv_nhwc(dy.view(B, H, W, Cout), WT, dx.view(B * H * W, Cin), k, 1, k // 2, res1=dx if acc else None,
-                          ldr1=Cin, impl=self.gemm_impl)
         self.tape.append(bwd)
         return out
 
@@ -421,10 +599,13 @@ class TrainEngine:
             dy = self.G(out)
             gw = self.GP[name + ".weight"]
             tgt = gw if wgrad_fix is None else self.buf(key + ".gw1", (Cout, Cin, k, k), torch.float32)
-            tops.gemm_wgrad(dy, col, tgt, M=M, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0, ldx=Kp, x_off=0, T=k * k,
-                            dbias=self.GP[name + ".bias"], ws=self._ws(0))
-            if wgrad_fix is not None:
-                wgrad_fix(tgt, gw)
+
+            def wg():
+                tops.gemm_wgrad(dy, col, tgt, M=M, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0, ldx=Kp, x_off=0, T=k * k,
+                                dbias=self.GP[name + ".bias"], ws=self._wws())
+                if wgrad_fix is not None:
+                    wgrad_fix(tgt, gw)
+            self._wgrad((dy, col), wg)
             if x_needs_grad:
                 WTp = self.w[name + ".wTp"]
                 dcol = self.buf(key + ".dcol", (M, Kp))
@@ -1003,13 +1184,21 @@ class TrainEngine:
     def backward(self, logits):
         """d(logits) must already be in G(logits)."""
         self.wr(logits)
-        for tag, fn in reversed(self.tape):
-            if tag == "bucket":
-                if self.on_bucket is not None:
-                    self.on_bucket(fn)
-                continue
-            ops.tag = tag + ".bwd"
-            fn()
+        _hazards.cur = self.side
+        try:
+            for tag, fn in reversed(self.tape):
+                if tag == "bucket":
+                    if self.on_bucket is not None:
+                        if self.side is not None:
+                            self.side.join()                # the bucket's weight gradients must be final
+                        self.on_bucket(fn)
+                    continue
+                ops.tag = tag + ".bwd"
+                fn()
+            if self.side is not None:
+                self.side.join()
+        finally:
+            _hazards.cur = None
 
     on_bucket = None        # callable(group) -> launches the gradient all-reduce of that bucket (see replicas.py)
 

@@ -273,6 +273,11 @@ def _csr(m):
     return start, idx, m[nz]
 
 
+def gather_cast(src, idx, dst):
+    """dst[i] = idx[i] ? src[idx[i]-1] : 0 (cast to dst.dtype); src flat fp32, idx int32, dst flat bf16/fp32"""
+    L.call("cenet_gather_cast", _f32(src, "src"), _i32(idx, "map"), _p(dst), dt(dst), dst.numel(), _stream())
+
+
 def make_tables(Mh, Mw, dev):
     """Sparse per-axis interpolation tables (CSR) for cenet_resample: out[i,j] = sum_h sum_w Mh[i,h] Mw[j,w] in[h,w].
     The matrices come from applying torch's own interpolation / pooling to an identity at plan time, so the tap

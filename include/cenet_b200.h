@@ -140,7 +140,7 @@ int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int he
 int cenet_diffattn_flash_padded(const void* qkv, void* out, int B, int N, int heads, int hd_pad, int dv_pad, int hd_real,
                                 float lambda, float eps, float mult, float* kmax_ws, cenet_stream_t s);
 
-/* ---- encoder attention (pvtv2.py:88-105): softmax(q k^T * scale) v with <= 64 keys, head_dim 64 ------------ */
+/* ---- encoder attention (pvtv2.py:88-105): softmax(q k^T * scale) v, any number of reduced keys, head_dim 64 --- */
 int cenet_sr_attention(const void* q, int q_dtype, const void* kv, int kv_dtype, void* out, int o_dtype, int B, int N,
                        int Nk, int C, int heads, float scale, cenet_stream_t s);
 
@@ -311,6 +311,11 @@ int cenet_maxpool2_scale_bwd(const void* dz, int dtype, long long lddz, const vo
                              int B, int H, int W, int C, float* ws, long long ws_elems, cenet_stream_t s);
 /* adjoint of the head's bilinear x2: dlogits [B,ncls,2h,2w] fp32 -> dyh [B,h,w,ncls] fp32 */
 int cenet_head_upsample_bwd(const float* dlogits, float* dyh, int B, int h, int w, int ncls, cenet_stream_t s);
+/* Re-pack of the fp32 master weights into the compute layouts (bf16 [N,K] / transposed / tap-permuted / flipped conv
+ * filters, zero padded) in ONE launch: dst[i] = map[i] ? src[map[i]-1] : 0, cast to dst_dtype.  The index map is built once
+ * by the host from the torch expressions the reference applies implicitly (`.weight` used as-is by F.linear / F.conv2d,
+ * pvtv2.py:41-45, blocks.py:209-214); n % 4 == 0, map and dst 16-byte aligned. */
+int cenet_gather_cast(const float* src, const int* map, void* dst, int dst_dtype, long long n, cenet_stream_t s);
 /* AdamW over the flat fp32 parameter buffer; hyper (device) = [lr, beta1, beta2, eps, weight_decay, step] (utils/core.py:16-18) */
 int cenet_adamw(float* p, const float* g, float* m, float* v, long long n, const float* hyper, cenet_stream_t s);
 

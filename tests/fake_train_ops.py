@@ -438,6 +438,11 @@ def ls_combine_bwd(dout, y, p, s, t, ls, w, dy, acc_dy, dp, dls, dw, M, C, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ resampling
+def gather_cast(src, idx, dst):
+    i = idx.long()
+    dst.copy_(torch.where(i > 0, src[(i - 1).clamp_min(0)], torch.zeros((), dtype=src.dtype)).to(dst.dtype))
+
+
 def make_tables(Mh, Mw, dev):
     """test emulation keeps the dense per-axis matrices [Ho,Hi], [Wo,Wi]"""
     return dict(Mh=Mh.float().contiguous(), Mw=Mw.float().contiguous())

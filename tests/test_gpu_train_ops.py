@@ -259,7 +259,8 @@ def test_lambda_fwd_bwd():
 
 # ------------------------------------------------------------------------------------------------------ DSEB
 @pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("scales,H,W", [((1.0, 0.5), 14, 14), ((0.8, 0.4), 28, 28), ((1.0, 0.75, 0.5), 56, 56)])
+@pytest.mark.parametrize("scales,H,W", [((1.0, 0.5), 14, 14), ((0.8, 0.4), 28, 28), ((1.0, 0.75, 0.5), 56, 56),
+                                         ((1.0, 0.75, 0.5), 128, 128)])      # 128x128: the workspace-resident variant
 def test_fea_bwd_matches_autograd_of_oracle_fea(dtype, scales, H, W):
     import torch.nn.functional as F
     from oracle import cenet_oracle as O
@@ -434,3 +435,16 @@ def test_head_upsample_bwd_and_adamw():
     p2, m2, v2 = p.clone(), torch.zeros(n), torch.zeros(n)
     FT.adamw(p2, g_, m2, v2, n, torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1e-2, 1.0, 0, 0]))
     assert (p2 - q.detach()).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------ weight re-pack
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_gather_cast_is_an_exact_indexed_copy(dtype):
+    from cenet_b200 import train_ops as tops
+    n_src, n = 100003, 4 * 50021
+    src = rn((n_src,), F32, 1).to(DEV)
+    idx = torch.randint(0, n_src + 1, (n,), generator=gen(2)).to(torch.int32)       # 0 = zero padding
+    dst = torch.full((n,), 7.0, dtype=dtype, device=DEV)
+    tops.gather_cast(src, idx.to(DEV), dst)
+    want = torch.where(idx > 0, src.cpu()[(idx.long() - 1).clamp_min(0)], torch.zeros(())).to(dtype)
+    assert torch.equal(dst.cpu(), want)                                              # bit-exact (round-to-nearest cast)

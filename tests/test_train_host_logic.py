@@ -85,3 +85,23 @@ def test_running_stats_and_adamw_step():
     rm = m.state_dict()["out.out.0.norm1.running_mean"]
     assert not torch.allclose(rm, sd["out.out.0.norm1.running_mean"])
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("name", ["acdc", "skin"])
+def test_gathered_weight_pack_equals_torch_layouts(name):
+    """pack(): the one-launch index-map re-pack must reproduce every torch-evaluated layout, also after a weight update."""
+    m, eng, sd, kw = _build(name)
+    eng.pack()                                            # CPU engines keep the torch path ...
+    assert eng._pack_maps is None
+    eng._build_pack_maps()                                # ... so build (and self-check) the maps explicitly
+    assert eng._pack_maps and sum(i.numel() for i, _ in eng._pack_maps) > 60e6
+    with torch.no_grad():
+        eng.pflat.mul_(1.5).add_(0.01)                    # what an optimizer step does
+    eng.pack()                                            # gather path
+    got = {k: v.clone() for k, v in eng.w.items()}
+    eng._pack_maps = None
+    eng.w = {}
+    eng._pack_torch()
+    assert set(got) == set(eng.w)
+    for k, v in eng.w.items():
+        assert torch.equal(got[k], v), k
