@@ -41,6 +41,11 @@ METRIC = "slices_per_s_infer_224"
 UNIT = "slices/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures of this workload (profiles/, per round)
+NCU_TRAFFIC = {"source": "profiles/r1_ncu_top_kernels.md, profiles/r1_gemm_traffic.md", "diffattn_flash_kernel": 193.4e6,
+               "gemm_tc_kernel": 39.67e6}     # mean over the 154 launches of one forward
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -71,7 +76,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -287,33 +292,62 @@ def run_product(args):
     # ---- timed region 1: inputs resident in HBM ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
-        for e0, e1 in ev:
-            flush.zero_()                                   # L2 flush between timed iterations (not timed)
-            e0.record()
-            eng.forward(x_dev, labels=True, out=labels_dev)
-            e1.record()
-        barrier()
+    clocks = ClockSampler(local)                            # samples clocks / throttle reasons over ALL timed regions below
+    clocks.__enter__()
+    for e0, e1 in ev:
+        flush.zero_()                                       # L2 flush between timed iterations (not timed)
+        e0.record()
+        eng.forward(x_dev, labels=True, out=labels_dev)
+        e1.record()
+    barrier()
     t_dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     # ---- timed region 2: end to end through the public API with host buffers ----
     for _ in range(max(args.warmup, 3)):
         labels_host.copy_(m.predict(x_host.to(dev, non_blocking=True)), non_blocking=True)
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for e0, e1 in ev2:
-        flush.zero_()
-        e0.record()
-        xd = x_host.to(dev, non_blocking=True)              # H2D of this step's slices (pinned)
-        lab = m.predict(xd)                                 # public call: logits -> argmax(softmax) fused
-        labels_host.copy_(lab, non_blocking=True)           # D2H of the label maps
-        e1.record()
-    barrier()
-    t_e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
+    # Every step: H2D of its slices from pinned host memory, the public call `CENet.predict`, D2H of its int64 label maps.
+    # The copies run on their own streams (double-buffered device input), so the transfer of step i+1 / i-1 overlaps the
+    # kernels of step i, as a serving loop would do; the timed region is ONE bracket around all K steps incl. the last D2H
+    # (and incl. the L2 flush memsets, which a per-step bracket would have excluded).
+    main = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xd = [torch.empty_like(x_dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
 
+    def stage(i):
+        j = i % 2
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_free[j])                 # predict(i-2) has consumed this staging buffer
+            xd[j].copy_(x_host, non_blocking=True)
+            ev_in[j].record(s_in)
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s_in.wait_stream(main); s_out.wait_stream(main)
+    e_start.record(main)
+    stage(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            stage(i + 1)
+        main.wait_event(ev_in[i % 2])
+        flush.zero_()
+        lab = m.predict(xd[i % 2])                          # public call: logits -> argmax(softmax) fused, new tensor
+        ev_free[i % 2].record(main)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            labels_host.copy_(lab, non_blocking=True)       # D2H of the label maps
+        lab.record_stream(s_out)
+    main.wait_stream(s_out)
+    e_end.record(main)
+    barrier()
+    t_e2e_ms = e_start.elapsed_time(e_end)
     t_dev_ms, t_e2e_ms = replicas.max_over_ranks([t_dev_ms, t_e2e_ms], device=dev)
     train = None
     if not args.no_train:
         train = run_train_leg(args, dev, world, rank, flush)
+    clocks.__exit__()
 
     if rank == 0:
         peaks = _peaks()
@@ -326,17 +360,38 @@ def run_product(args):
         for (op, tag), (ms, n) in prof.items():
             a = by_op.setdefault(op, [0.0, 0]); a[0] += ms; a[1] += n
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:12]
+        # (a) the dominant kernel of the step: gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv; every nn.Linear, 1x1,
+        #     3x3 and 5x5 conv) -- all its launches of one forward, algorithmic bytes (each operand once) over the
+        #     summed launch durations.  Mostly K <= 128 shapes -> HBM-bound; the tensor-pipe view is stated next to it.
+        gw = eng.last_gemm_work
+        g_bytes = sum(v[0] for v in gw.values()); g_flops = sum(v[1] for v in gw.values()); g_n = sum(v[2] for v in gw.values())
+        g_ms = sum(by_op.get(op, [0.0, 0])[0] for op in ("linear", "gemm", "conv_nhwc"))
+        roof = None
+        if g_n and g_ms > 0:
+            ach = g_bytes / (g_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": f"gemm_tc_kernel (tcgen05 GEMM / conv), {g_n} launches per forward",
+                    "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": NCU_TRAFFIC.get("gemm_tc_kernel"), "traffic_source": NCU_TRAFFIC.get("source"),
+                    "bytes_per_launch": g_bytes / g_n, "ms_per_launch": g_ms / g_n, "share_of_step": g_ms / total_ms,
+                    "tensor_view": {"achieved_tflops": g_flops / (g_ms / 1e3) / 1e12, "peak_tflops": peaks["tf_sustained"],
+                                    "frac": g_flops / (g_ms / 1e3) / 1e12 / peaks["tf_sustained"]},
+                    "peak_source": peaks["source"] + ", HBM copy",
+                    "note": "op-level times of linear/gemm/conv_nhwc calls; a few fp32/batched calls on the CUDA-core GEMM "
+                            "are in the time but not in the bytes (conservative)"}
+        # (b) the largest single launch: differential flash attention of the 56x56 DSE block (exp-bound)
         E1, N1 = 128, (SIZE // 4) ** 2
         ms_da, n_da = prof.get(("diffattn_flash", "se1"), (None, 0))
-        roof = None
+        roof_attn = None
         if ms_da:
             fl = diffattn_flops(N1, E1, BATCH)
             ach = fl / (ms_da / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": "diffattn_flash_kernel<8> (DSEB 56x56, 16 maps, head_dim 8)",
-                    "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-                    "traffic": None, "ms_per_launch": ms_da, "share_of_step": ms_da / total_ms,
-                    "peak_source": peaks["source"] + ", sustained bf16",
-                    "note": "softmax-bound: 2h*N^2 = 157M exp per image on the 16/clk/SM MUFU pipe; see DESIGN.md"}
+            roof_attn = {"bound": "tensor", "kernel": "diffattn_flash_kernel<8,16> (DSEB 56x56, 16 softmax maps, head_dim 8)",
+                         "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                         "traffic": NCU_TRAFFIC.get("diffattn_flash_kernel"), "ms_per_launch": ms_da,
+                         "share_of_step": ms_da / total_ms, "peak_source": peaks["source"] + ", sustained bf16",
+                         "mufu_bound": {"exp_per_launch": 16.0 * N1 * N1 * BATCH, "peak_exp_per_s": 148 * 16 * 1.965e9,
+                                        "frac": 16.0 * N1 * N1 * BATCH / (ms_da / 1e3) / (148 * 16 * 1.965e9)},
+                         "note": "softmax-bound: one MUFU.EX2 per score (16/clk/SM); see DESIGN.md 4a"}
         _, _, cores = 0, 0, os.cpu_count()
         cpu_v, cpu_ms, cores = cpu_oracle_throughput(sd, kw, 4, 2, 1)
         line = {
@@ -352,6 +407,7 @@ def run_product(args):
             "launches_per_step": int(launches_per_step),
             "clocks": clocks.summary(),
             "roofline": roof,
+            "roofline_attention": roof_attn,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "oracle port, 4 slices/step x 2 steps (1 warm-up) of the same synthetic workload"},
             "op_breakdown_ms": {f"{op}@{tag}": round(ms, 4) for (op, tag), (ms, n) in top},

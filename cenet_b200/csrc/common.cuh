@@ -242,3 +242,13 @@ static inline EpiParams make_epi(const cenet_gemm_args* a) {
 int cenet_gemm_simt(const cenet_gemm_args* a, cudaStream_t s);
 int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s);
 bool cenet_gemm_tc_eligible(const cenet_gemm_args* a);
+
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that cost no registers while in flight; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(a), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+

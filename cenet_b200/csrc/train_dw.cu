@@ -5,6 +5,8 @@
 //   sumpool2        : adjoint of the nearest x2 up-sampling of EUCB (blocks.py:304)
 //   col2im          : adjoint of cenet_im2col (patch-embed / SR-conv data gradients, pvtv2.py:164-165, 68)
 #include "train_common.cuh"
+#include <atomic>
+#include <cstdlib>
 
 namespace {
 // V consecutive elements as one raw vector register (kept packed until use)
@@ -146,6 +148,116 @@ __global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const 
   }
 }
 
+// Shared-memory staged variant of stage 1 (bf16, dilation 1, no fused up-sampling, C % 64 == 0): same structure as
+// dwconv3x3_staged_kernel (dwconv.cu).  A CTA owns 64 channels of a band of rows of one image and streams x rows (ring of
+// 5, zero halo columns) and dz rows (ring of 3) through shared memory with cp.async, two rows ahead of the arithmetic.
+// Thread = 4 channels x 4 consecutive pixels with its 10 x 4 accumulators in registers for the whole band; one shared
+// memory reduction over the 16 pixel groups at the end; partial per (image, band): ws[((b * nbands + band) * 10 + k) * C + c].
+constexpr int WS_C = 64, WS_T = 256, WS_PF = 2, WS_NRX = 3 + WS_PF, WS_NRZ = 1 + WS_PF;
+
+__global__ void __launch_bounds__(WS_T, 2) dw_wgrad_staged_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dz, int ldz,
+                                                                  int H, int W, int C, int rows_per_cta, float* __restrict__ ws) {
+  extern __shared__ __align__(16) unsigned char wsm[];
+  const int tid = threadIdx.x;
+  const int rowX = (W + 2) * 128, rowZ = W * 128;
+  unsigned char* zring = wsm + WS_NRX * rowX;
+  const int c_base = blockIdx.x * WS_C;
+  const int h0 = blockIdx.y * rows_per_cta, h1 = min(H, h0 + rows_per_cta);
+  const int b = blockIdx.z;
+  const bf16* xb = x + (size_t)b * H * W * ldx + c_base;
+  const bf16* zb = dz + (size_t)b * H * W * ldz + c_base;
+  for (int i = tid; i < WS_NRX * 16; i += WS_T) {
+    const int slot = i >> 4, side = (i >> 3) & 1, ch = i & 7;
+    *reinterpret_cast<uint4*>(wsm + slot * rowX + (side ? (W + 1) * 128 : 0) + ch * 16) = make_uint4(0, 0, 0, 0);
+  }
+  // group k = { x row h0-1+k -> x slot k % NRX,  dz row h0-2+k -> z slot (k-2) % NRZ }
+  auto issue = [&](int k) {
+    const int rx = h0 - 1 + k, rz = h0 - 2 + k;
+    if (rx <= h1) {
+      const bool valid = rx >= 0 && rx < H;
+      const bf16* src = xb + (size_t)(valid ? rx : 0) * W * ldx;
+      unsigned char* dst = wsm + (k % WS_NRX) * rowX + 128;
+      for (int i = tid; i < W * 8; i += WS_T) {
+        const int w = i >> 3, ch = i & 7;
+        cp_async16_zfill(dst + w * 128 + ch * 16, src + (size_t)w * ldx + ch * 8, valid ? 16 : 0);
+      }
+    }
+    if (rz >= h0 && rz < h1) {
+      const bf16* src = zb + (size_t)rz * W * ldz;
+      unsigned char* dst = zring + ((k - 2) % WS_NRZ) * rowZ;
+      for (int i = tid; i < W * 8; i += WS_T) {
+        const int w = i >> 3, ch = i & 7;
+        cp_async16_zfill(dst + w * 128 + ch * 16, src + (size_t)w * ldz + ch * 8, 16);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int k = 0; k < WS_PF + 2; k++) issue(k);
+  const int cv = tid & 15, pg0 = tid >> 4;
+  float acc[10][4];
+#pragma unroll
+  for (int k = 0; k < 10; k++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[k][v] = 0.f;
+  for (int h = h0; h < h1; h++) {
+    const int k0 = h - h0;                                     // groups 0 .. k0+2 hold x rows <= h+1 and dz rows <= h
+    cp_async_wait<WS_PF - 1>();
+    __syncthreads();
+    issue(k0 + WS_PF + 2);
+    const unsigned char* rows[3];
+#pragma unroll
+    for (int dh = 0; dh < 3; dh++) rows[dh] = wsm + ((k0 + dh) % WS_NRX) * rowX + cv * 8;
+    const unsigned char* zrow = zring + (k0 % WS_NRZ) * rowZ + cv * 8;
+    for (int pg = pg0; pg * 4 < W; pg += 16) {
+      float g[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        if (pg * 4 + p < W) ldv<4>(reinterpret_cast<const bf16*>(zrow + (pg * 4 + p) * 128), g[p]);
+        else {
+#pragma unroll
+          for (int v = 0; v < 4; v++) g[p][v] = 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[9][v] += g[p][v];
+      }
+#pragma unroll
+      for (int dh = 0; dh < 3; dh++) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const int col = pg * 4 + q;
+          if (col > W + 1) continue;
+          float xv[4];
+          ldv<4>(reinterpret_cast<const bf16*>(rows[dh] + col * 128), xv);
+#pragma unroll
+          for (int p = 0; p < 4; p++) {
+            const int t = q - p;
+            if (t < 0 || t > 2) continue;
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[dh * 3 + t][v] = fmaf(g[p][v], xv[v], acc[dh * 3 + t][v]);
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                             // the rings are free: reuse them for the block reduction
+  float* red = reinterpret_cast<float*>(wsm);                  // [16 pixel groups][16 channel quads * 40]
+#pragma unroll
+  for (int k = 0; k < 10; k++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) red[pg0 * 640 + cv * 40 + k * 4 + v] = acc[k][v];
+  __syncthreads();
+  const int blk = blockIdx.z * gridDim.y + blockIdx.y;
+  for (int o = tid; o < 640; o += WS_T) {
+    float t = 0.f;
+#pragma unroll
+    for (int p = 0; p < 16; p++) t += red[p * 640 + o];
+    const int q = o / 40, k = (o % 40) >> 2, v = o & 3;
+    ws[((size_t)blk * 10 + k) * C + c_base + q * 4 + v] = t;
+  }
+}
+
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* dw, float* dbias) {
   __shared__ float sm[kFinThreads];
   const int i = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
@@ -255,6 +367,29 @@ extern "C" int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, 
   CENET_DISPATCH(x_dtype, T, {
     int Vv = vec_of(sizeof(T), {x, dz}, {C, ldx, ldz});
     if (Vv > 4) Vv = 4;                                   // 10 accumulators per channel: keep the register footprint small
+    static const bool use_staged = getenv("CENET_B200_DW_STAGED") == nullptr || atoi(getenv("CENET_B200_DW_STAGED")) != 0;
+    // (a thread owns 4 consecutive pixels: rows narrower than 48 pixels leave most of the 16 pixel groups idle)
+    if (use_staged && x_dtype == CENET_BF16 && dil == 1 && !up2 && W >= 48 && C % WS_C == 0 && ldx % 8 == 0 && ldz % 8 == 0 &&
+        ((((uintptr_t)x | (uintptr_t)dz) & 15) == 0) && B <= 65535) {
+      int rpc = H;
+      while ((long long)(C / WS_C) * cdiv(H, rpc) * B < 4LL * kNumSMs && rpc > 4) rpc = (rpc + 1) / 2;
+      const int nbands = cdiv(H, rpc);
+      const size_t ring = (size_t)WS_NRX * (W + 2) * 128 + (size_t)WS_NRZ * W * 128;
+      const size_t smem = std::max<size_t>(ring, 16 * 640 * sizeof(float));
+      if (smem <= 200 * 1024 && (long long)B * nbands * 10 * C <= ws_elems) {
+        static std::atomic<size_t> configured{0};
+        if (smem > 48 * 1024 && configured.load() < smem) {
+          cudaFuncSetAttribute(dw_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          configured.store(200 * 1024);
+        }
+        dw_wgrad_staged_kernel<<<dim3(C / WS_C, nbands, B), WS_T, smem, s>>>((const bf16*)x, (int)ldx, (const bf16*)dz, (int)ldz, H, W, C,
+                                                                           rpc, ws);
+        CENET_LAUNCH_CHECK("dw_wgrad_staged");
+        dw_wgrad_finalize_kernel<<<cdiv(10 * C, kFinOut), kFinThreads, 0, s>>>(ws, B * nbands, C, dw, dbias);
+        CENET_LAUNCH_CHECK("dw_wgrad_finalize");
+        return 0;
+      }
+    }
     // rows of the plan are IMAGE rows (b, h); every thread takes whole rows, at least one
     ColPlan p = plan_cols(rows, C, Vv);
     const int R = B * H;

@@ -44,7 +44,31 @@ class _TimedOps:
     def __init__(self, inner):
         self._inner = inner
         self.records = []          # (op name, tag, start event, end event)
+        self.work = {}             # op name -> [algorithmic bytes, FLOPs, launches] of the tensor-core GEMM / conv calls
         self.tag = ""
+
+    @staticmethod
+    def _gemm_work(name, a, k):
+        """algorithmic (bytes, flops) of a GEMM-family call: every operand counted once, or None when the call
+        is routed to the CUDA-core kernel (fp32 validation, batched materialised attention)"""
+        if k.get("impl", GEMM_AUTO) == GEMM_SIMT or k.get("batch", 1) != 1 or a[0].dtype != torch.bfloat16:
+            return None
+        es_o = a[2].element_size()
+        if name == "linear":
+            M, K = a[0].shape
+            N = a[2].shape[1]
+            in_elems = M * K
+        elif name == "conv_nhwc":
+            B, H, W, Cin = a[0].shape
+            ks, st, pd = a[3], a[4], a[5]
+            Ho, Wo = (H + 2 * pd - ks) // st + 1, (W + 2 * pd - ks) // st + 1
+            M, N, K = B * Ho * Wo, k.get("N", a[1].shape[0]), ks * ks * Cin
+            in_elems = B * H * W * Cin
+        else:
+            M, N, K = k["M"], k["N"], k["K"]
+            in_elems = M * K
+        extra = sum(M * N * t.element_size() for t in (k.get("res1"), k.get("res2"), k.get("mul")) if t is not None)
+        return (in_elems + N * K) * 2 + M * N * es_o + extra, 2.0 * M * N * K
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
@@ -57,6 +81,11 @@ class _TimedOps:
             r = fn(*a, **k)
             e1.record()
             self.records.append((name, self.tag, e0, e1))
+            if name in ("linear", "gemm", "conv_nhwc"):
+                wk = self._gemm_work(name, a, k)
+                if wk is not None:
+                    acc = self.work.setdefault(name, [0.0, 0.0, 0])
+                    acc[0] += wk[0]; acc[1] += wk[1]; acc[2] += 1
             return r
         return timed
 
@@ -656,4 +685,5 @@ class Engine:
             torch.cuda.synchronize()
         finally:
             ops = real
+        self.last_gemm_work = {k: (v[0] / steps, v[1] / steps, v[2] // steps) for k, v in timed.work.items()}
         return {k: (t / steps, n // steps) for k, (t, n) in timed.summary().items()}

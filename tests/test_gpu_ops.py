@@ -212,6 +212,31 @@ def test_dwconv_variants(dtype):
     assert rel(y3, ref.permute(0, 2, 3, 1)) < tol
 
 
+@pytest.mark.parametrize("B,H,W,C,ldx,xo", [(3, 56, 56, 128, 128, 0), (2, 14, 14, 320, 320, 0), (1, 7, 7, 64, 64, 0),
+                                            (2, 28, 30, 64, 192, 64), (1, 20, 130, 64, 64, 0)])
+def test_dwconv_staged_rows(B, H, W, C, ldx, xo):
+    """the shared-memory staged kernel (bf16, dilation 1, C % 64 == 0): several row bands per image, widths that are not a
+    multiple of the 4-pixel thread tile, a channel slice of a wider tensor, wide rows (> 64 pixels), with and without the
+    stored pre-activation"""
+    from cenet_b200 import ops
+    x = torch.randn(B, ldx, H, W, generator=g(1))
+    wt = torch.randn(C, 1, 3, 3, generator=g(2)) / 3
+    bias = torch.randn(C, generator=g(3))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    w9 = wt.reshape(C, 9).t().contiguous().to(DEV)
+    xr = xn.float().cpu().permute(0, 3, 1, 2)[:, xo:xo + C]
+    pre = F.conv2d(xr, wt, bias, padding=1, groups=C).permute(0, 2, 3, 1)
+    y = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    z = torch.empty_like(y)
+    ops.dwconv3x3(xn, y, w9, B, H, W, C, ldx=ldx, x_off=xo, bias=bias.to(DEV), act=ops.ACT_GELU, zout=z)
+    assert rel(z, pre) < 6e-3 and rel(y, F.gelu(pre)) < 6e-3
+    sc, sh = torch.rand(C, generator=g(4)) + 0.5, torch.randn(C, generator=g(5))
+    y2 = torch.empty_like(y)
+    ops.dwconv3x3(xn, y2, w9, B, H, W, C, ldx=ldx, x_off=xo, scale=sc.to(DEV), shift=sh.to(DEV), act=ops.ACT_RELU)
+    ref = F.relu(F.conv2d(xr, wt, padding=1, groups=C) * sc[None, :, None, None] + sh[None, :, None, None])
+    assert rel(y2, ref.permute(0, 2, 3, 1)) < 6e-3
+
+
 def test_layout_ops():
     from cenet_b200 import ops
     B, H, W, C = 2, 10, 12, 24

@@ -188,6 +188,15 @@ def test_dwconv_wgrad(dtype, C, ldx, xo, dil, up2, bias):
           [2, 3] if bias else [2], 3e-4 if dtype == F32 else 1.5e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C,ldx,xo", [(3, 56, 56, 128, 128, 0), (2, 14, 14, 320, 320, 0), (1, 7, 7, 64, 64, 0),
+                                            (2, 28, 30, 64, 192, 64), (1, 20, 130, 64, 64, 0)])
+def test_dwconv_wgrad_staged_rows(B, H, W, C, ldx, xo):
+    """shared-memory staged filter gradient (bf16, dilation 1): several bands, ragged widths, channel slice, wide rows"""
+    x, dz = rn((B, H, W, ldx), BF16, 1), rn((B, H, W, C), BF16, 2)
+    dw, db = torch.zeros(C, 1, 3, 3), torch.zeros(C)
+    check("dwconv3x3_wgrad", [x, dz, dw, db, B, H, W, C, 1, False, ldx, xo, C, 0, ws()], {}, [2, 3], 2e-3)
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 def test_sumpool2_col2im(dtype):
     B, Ho, Wo, C = 2, 7, 9, 40
