@@ -65,6 +65,7 @@ _SIGS = {
     "cenet_stem5x5": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp],
     "cenet_head_upsample_argmax": [vp, vp, vp, i32, i32, i32, i32, vp],
     "cenet_dice_ce": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, vp],
+    "cenet_seg_loss": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp],
     # ---- training (see include/cenet_b200.h) ----
     "cenet_dwconv3x3_train": [vp, i32, ll, vp, i32, ll, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
     "cenet_gemm_wgrad": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, vp, vp, i32, vp, ll, vp],

@@ -252,3 +252,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2: two channels per instruction)
+typedef unsigned long long f32x2;                              // two packed floats (lo = even channel)
+
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// bf16x2 word -> packed floats (exact): low half << 16, high half masked
+__device__ __forceinline__ f32x2 bf2_to_f2(unsigned w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ unsigned f2_to_bf2(f32x2 v) {
+  float a, b; upk2(v, a, b);
+  unsigned r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));    // first source -> upper half
+  return r;
+}
+

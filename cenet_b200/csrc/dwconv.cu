@@ -141,19 +141,6 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const TI* __restrict__ x
 //   * shared-memory reads are `ld.shared.v2.b32` from one 32-bit base with immediate offsets, no per-load address math;
 //   * no bounds predicates in the inner loops (W % PW == 0, the halo columns exist in shared memory).
 constexpr int SG_C = 64, SG_T = 256, SG_PF = 2, SG_NR = 3 + SG_PF;
-typedef unsigned long long f32x2;                              // two packed floats (lo = even channel)
-
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// bf16x2 word -> packed floats (exact): low half << 16, high half masked
-__device__ __forceinline__ f32x2 bf2_to_f2(unsigned w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
-__device__ __forceinline__ unsigned f2_to_bf2(f32x2 v) {
-  float a, b; upk2(v, a, b);
-  unsigned r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));    // first source -> upper half
-  return r;
-}
 // tanh-form GELU on two channels: 0.5 x (1 + tanh(x (k0 + k1 x^2)))
 __device__ __forceinline__ f32x2 gelu2(f32x2 x) {
   const f32x2 k0 = pk2(0.7978845608f, 0.7978845608f), k1 = pk2(0.0356774081f, 0.0356774081f), hf = pk2(0.5f, 0.5f);

@@ -195,46 +195,46 @@ __global__ void __launch_bounds__(WS_T, 2) dw_wgrad_staged_kernel(const bf16* __
 #pragma unroll
   for (int k = 0; k < WS_PF + 2; k++) issue(k);
   const int cv = tid & 15, pg0 = tid >> 4;
-  float acc[10][4];
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(wsm);
+  const unsigned zbase = sbase + WS_NRX * rowX;
+  f32x2 acc[10][2];                                            // packed channel pairs (FFMA2)
 #pragma unroll
-  for (int k = 0; k < 10; k++)
-#pragma unroll
-    for (int v = 0; v < 4; v++) acc[k][v] = 0.f;
+  for (int k = 0; k < 10; k++) acc[k][0] = acc[k][1] = pk2(0.f, 0.f);
+  const f32x2 one2 = pk2(1.f, 1.f);
+  const int npg = W / 4;                                       // W % 4 == 0 (dispatch)
   for (int h = h0; h < h1; h++) {
     const int k0 = h - h0;                                     // groups 0 .. k0+2 hold x rows <= h+1 and dz rows <= h
     cp_async_wait<WS_PF - 1>();
     __syncthreads();
     issue(k0 + WS_PF + 2);
-    const unsigned char* rows[3];
+    unsigned rows[3];
 #pragma unroll
-    for (int dh = 0; dh < 3; dh++) rows[dh] = wsm + ((k0 + dh) % WS_NRX) * rowX + cv * 8;
-    const unsigned char* zrow = zring + (k0 % WS_NRZ) * rowZ + cv * 8;
-    for (int pg = pg0; pg * 4 < W; pg += 16) {
-      float g[4][4];
+    for (int dh = 0; dh < 3; dh++) rows[dh] = sbase + ((k0 + dh) % WS_NRX) * rowX + cv * 8;
+    const unsigned zrow = zbase + (k0 % WS_NRZ) * rowZ + cv * 8;
+    for (int pg = pg0; pg < npg; pg += 16) {
+      f32x2 g[4][2];
 #pragma unroll
       for (int p = 0; p < 4; p++) {
-        if (pg * 4 + p < W) ldv<4>(reinterpret_cast<const bf16*>(zrow + (pg * 4 + p) * 128), g[p]);
-        else {
-#pragma unroll
-          for (int v = 0; v < 4; v++) g[p][v] = 0.f;
-        }
-#pragma unroll
-        for (int v = 0; v < 4; v++) acc[9][v] += g[p][v];
+        unsigned w0, w1;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(zrow + pg * 512 + p * 128));
+        g[p][0] = bf2_to_f2(w0); g[p][1] = bf2_to_f2(w1);
+        acc[9][0] = ffma2(g[p][0], one2, acc[9][0]);
+        acc[9][1] = ffma2(g[p][1], one2, acc[9][1]);
       }
 #pragma unroll
       for (int dh = 0; dh < 3; dh++) {
+        const unsigned ra = rows[dh] + pg * 512;
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-          const int col = pg * 4 + q;
-          if (col > W + 1) continue;
-          float xv[4];
-          ldv<4>(reinterpret_cast<const bf16*>(rows[dh] + col * 128), xv);
+          unsigned w0, w1;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(ra + q * 128));
+          const f32x2 x01 = bf2_to_f2(w0), x23 = bf2_to_f2(w1);
 #pragma unroll
           for (int p = 0; p < 4; p++) {
             const int t = q - p;
             if (t < 0 || t > 2) continue;
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[dh * 3 + t][v] = fmaf(g[p][v], xv[v], acc[dh * 3 + t][v]);
+            acc[dh * 3 + t][0] = ffma2(g[p][0], x01, acc[dh * 3 + t][0]);
+            acc[dh * 3 + t][1] = ffma2(g[p][1], x23, acc[dh * 3 + t][1]);
           }
         }
       }
@@ -244,9 +244,11 @@ __global__ void __launch_bounds__(WS_T, 2) dw_wgrad_staged_kernel(const bf16* __
   __syncthreads();                                             // the rings are free: reuse them for the block reduction
   float* red = reinterpret_cast<float*>(wsm);                  // [16 pixel groups][16 channel quads * 40]
 #pragma unroll
-  for (int k = 0; k < 10; k++)
-#pragma unroll
-    for (int v = 0; v < 4; v++) red[pg0 * 640 + cv * 40 + k * 4 + v] = acc[k][v];
+  for (int k = 0; k < 10; k++) {
+    float a0, a1, a2, a3;
+    upk2(acc[k][0], a0, a1); upk2(acc[k][1], a2, a3);
+    *reinterpret_cast<float4*>(red + pg0 * 640 + cv * 40 + k * 4) = make_float4(a0, a1, a2, a3);
+  }
   __syncthreads();
   const int blk = blockIdx.z * gridDim.y + blockIdx.y;
   for (int o = tid; o < 640; o += WS_T) {
@@ -369,7 +371,7 @@ extern "C" int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, 
     if (Vv > 4) Vv = 4;                                   // 10 accumulators per channel: keep the register footprint small
     static const bool use_staged = getenv("CENET_B200_DW_STAGED") == nullptr || atoi(getenv("CENET_B200_DW_STAGED")) != 0;
     // (a thread owns 4 consecutive pixels: rows narrower than 48 pixels leave most of the 16 pixel groups idle)
-    if (use_staged && x_dtype == CENET_BF16 && dil == 1 && !up2 && W >= 48 && C % WS_C == 0 && ldx % 8 == 0 && ldz % 8 == 0 &&
+    if (use_staged && x_dtype == CENET_BF16 && dil == 1 && !up2 && W >= 48 && W % 4 == 0 && C % WS_C == 0 && ldx % 8 == 0 && ldz % 8 == 0 &&
         ((((uintptr_t)x | (uintptr_t)dz) & 15) == 0) && B <= 65535) {
       int rpc = H;
       while ((long long)(C / WS_C) * cdiv(H, rpc) * B < 4LL * kNumSMs && rpc > 4) rpc = (rpc + 1) / 2;

@@ -219,6 +219,21 @@ def nonlocal_flash(tpg, out, B, N, Cc, scale):
     return out
 
 
+def seg_loss_ws(B, ncls, H, W, device):
+    """workspace of `seg_loss` (also large enough for `dice_ce`)"""
+    return torch.empty((4 * ncls + 1) * loss_nblocks(B * H * W) + 5 * ncls + 4, device=device, dtype=torch.float32)
+
+
+def seg_loss(logits, labels, loss_out, dlogits, ws, B, ncls, H, W, w_dice, w_ce, w_boundary, grad_scale=1.0):
+    """Criterion (utils/core.py:161-188): w_dice*DiceLoss + w_ce*CrossEntropy + w_boundary*BoundaryDoULoss, fused with its
+    gradient.  loss_out [1+ncls] = loss, per-class dice scores."""
+    if labels.dtype != torch.int64:
+        raise TypeError("labels must be int64")
+    L.call("cenet_seg_loss", _f32(logits, "logits"), _p(labels), _f32(loss_out, "loss"), _f32(dlogits, "dlogits"),
+           _f32(ws, "ws"), B, ncls, H, W, w_dice, w_ce, w_boundary, grad_scale, _stream())
+    return loss_out
+
+
 # ------------------------------------------------------------------------------------------------------ CFAM
 def ccu_nchunk(HW: int) -> int:
     return int(L.load().cenet_ccu_nchunk(HW))

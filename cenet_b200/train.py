@@ -1202,12 +1202,15 @@ class TrainEngine:
 
     on_bucket = None        # callable(group) -> launches the gradient all-reduce of that bucket (see replicas.py)
 
-    def _step_body(self, x_in, labels, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, wd, optimize):
+    def _step_body(self, x_in, labels, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, wd, optimize, w_boundary=0.0):
         self.pack()
         logits = self.buf("logits", (B, ncls, H, W), torch.float32)
         self.forward(x_in, B, H, W, logits)
-        ws = self.buf("loss.ws", ((3 * ncls + 1) * ops.loss_nblocks(B * H * W) + 3 * ncls + 3,), torch.float32)
-        ops.dice_ce(logits, labels, loss_out, self.G(logits), ws, B, ncls, H * W, w_dice, w_ce, 1.0)
+        ws = self.buf("loss.ws", ((4 * ncls + 1) * ops.loss_nblocks(B * H * W) + 5 * ncls + 4,), torch.float32)
+        if w_boundary:                                  # Criterion with a BoundaryDoULoss term (utils/core.py:83-131,161-188)
+            ops.seg_loss(logits, labels, loss_out, self.G(logits), ws, B, ncls, H, W, w_dice, w_ce, w_boundary, 1.0)
+        else:
+            ops.dice_ce(logits, labels, loss_out, self.G(logits), ws, B, ncls, H * W, w_dice, w_ce, 1.0)
         self.backward(logits)
         if self.grad_hook is not None:
             self.grad_hook(self.gflat)
@@ -1280,9 +1283,10 @@ class TrainEngine:
         self.G(logits).copy_(dlogits)
         self.backward(logits)
 
-    def train_step(self, x, labels, *, w_dice=0.5, w_ce=0.5, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4,
-                   optimize=True):
-        """One fused iteration: forward, Dice+CE (utils/core.py:179-188), backward, AdamW (core.py:16-18).
+    def train_step(self, x, labels, *, w_dice=0.5, w_ce=0.5, w_boundary=0.0, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                   weight_decay=1e-4, optimize=True):
+        """One fused iteration: forward, Criterion (utils/core.py:179-188: w_dice*Dice + w_ce*CE + w_boundary*BoundaryDoU; the
+        ACDC / Synapse scripts run `boundary` alone, the skin script `dice,ce`), backward, AdamW (core.py:16-18).
         Returns the device tensor [1+ncls]: loss, per-class dice.  x [B,Cin,H,W] fp32, labels [B,H,W] int64."""
         if x.device != self.dev:
             raise RuntimeError(f"input on {x.device}, engine on {self.dev}")
@@ -1299,8 +1303,8 @@ class TrainEngine:
         self.step_count += 1
         hp = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, float(self.step_count), 0.0, 0.0], dtype=torch.float32)
         self.hyper.copy_(hp if self.dev.type != "cuda" else hp.pin_memory(), non_blocking=True)
-        args = (x_in, lab, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, weight_decay, optimize)
-        key = (B, H, W, optimize, w_dice, w_ce)
+        args = (x_in, lab, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, weight_decay, optimize, w_boundary)
+        key = (B, H, W, optimize, w_dice, w_ce, w_boundary)
         if not self.use_graph or self.taps is not None or self.dev.type != "cuda":
             self._step_body(*args)
             return loss_out

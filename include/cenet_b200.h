@@ -187,6 +187,12 @@ int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* la
 int cenet_loss_nblocks(long long npix);
 int cenet_dice_ce(const float* logits, const long long* labels, float* loss_out, float* dlogits, float* ws, int B,
                   int ncls, int HW, float w_dice, float w_ce, float grad_scale, cenet_stream_t s);
+/* Same three passes with the third term of Criterion (utils/core.py:161-188): BoundaryDoULoss (core.py:83-131), the loss the
+ * ACDC / Synapse scripts select (`--loss_type boundary`).  loss_out[0] = w_dice*dice + w_ce*ce + w_boundary*boundary_dou.
+ * The per-class boundary pixel counts C_c and class sizes S_c are exact integers (tot[4c+3], tot[4c+2] after the call, tot =
+ * ws + nblk*(4*ncls+1)).  ws: (4*ncls+1)*nblk + 5*ncls+4 floats. */
+int cenet_seg_loss(const float* logits, const long long* labels, float* loss_out, float* dlogits, float* ws, int B,
+                   int ncls, int H, int W, float w_dice, float w_ce, float w_boundary, float grad_scale, cenet_stream_t s);
 
 /* ================================================================================================================
  * TRAINING entry points: train-mode forward pieces and the hand-written backward of every op on the path

@@ -368,3 +368,47 @@ def dice_loss(logits, target, n_classes):
 def criterion_dice_ce(logits, target, n_classes, w_dice=0.5, w_ce=0.5):
     """utils/core.py:179-188 with --loss_type dice,ce."""
     return w_dice * dice_loss(logits, target, n_classes) + w_ce * F.cross_entropy(logits, target.long())
+
+
+def boundary_counts(target, n_classes):
+    """Integer statistics of BoundaryDoULoss._adaptive_size (utils/core.py:96-107): per class i, S_i = #pixels of class i and
+    C_i = #pixels of class i whose 3x3-cross sum over the zero-padded one-hot map is not 5 (a 4-neighbour is another class
+    or outside the image).  Returns (C [n_classes], S [n_classes]) as int64."""
+    kernel = torch.tensor([[0., 1., 0.], [1., 1., 1.], [0., 1., 0.]]).view(1, 1, 3, 3)
+    C, S = [], []
+    for i in range(n_classes):
+        t = (target == i).float()                                   # [B,H,W]
+        y = F.conv2d(t.unsqueeze(1), kernel, padding=1).squeeze(1) * t
+        y = torch.where(y == 5, torch.zeros_like(y), y)
+        C.append(torch.count_nonzero(y))
+        S.append(torch.count_nonzero(t))
+    return torch.stack(C), torch.stack(S)
+
+
+def boundary_dou_loss(logits, target, n_classes):
+    """utils/core.py:83-131 (BoundaryDoULoss.forward + _adaptive_size), batch-vectorised; alpha depends on the labels only."""
+    p = torch.softmax(logits, 1)
+    C, S = boundary_counts(target, n_classes)
+    smooth = 1e-5
+    loss = 0.0
+    for i in range(n_classes):
+        t = (target == i).float()
+        alpha = 1 - (C[i] + smooth) / (S[i] + smooth)
+        alpha = min(float(2 * alpha - 1), 0.8)
+        inter = (p[:, i] * t).sum()
+        y_sum = (t * t).sum()
+        z_sum = (p[:, i] * p[:, i]).sum()
+        loss = loss + (z_sum + y_sum - 2 * inter + smooth) / (z_sum + y_sum - (1 + alpha) * inter + smooth)
+    return loss / n_classes
+
+
+def criterion(logits, target, n_classes, w_dice=0.0, w_ce=0.0, w_boundary=0.0):
+    """utils/core.py:161-188: weighted sum over --loss_type of dice / ce / boundary."""
+    loss = 0.0
+    if w_dice:
+        loss = loss + w_dice * dice_loss(logits, target, n_classes)
+    if w_ce:
+        loss = loss + w_ce * F.cross_entropy(logits, target.long())
+    if w_boundary:
+        loss = loss + w_boundary * boundary_dou_loss(logits, target, n_classes)
+    return loss

@@ -32,6 +32,12 @@ def golden_modules():
 
 
 @pytest.fixture(scope="session")
+def golden_loss_boundary():
+    import torch
+    return torch.load(os.path.join(GOLDEN, "loss_boundary.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def golden_loss():
     import torch
     return torch.load(os.path.join(GOLDEN, "loss.pt"), weights_only=False)

@@ -131,9 +131,33 @@ def loss_fixture():
                                grad=logits.grad.clone())
     torch.save(out, os.path.join(HERE, "loss.pt"))
     print("loss:", {k: v["loss"].item() for k, v in out.items()})
+    # BoundaryDoULoss (core.py:83-131) hard-codes `.cuda()` on its scratch tensors; on this GPU-less container the call is
+    # patched to the identity for the duration of the run (arithmetic untouched).  Labels: smooth blobs (nearest-upsampled
+    # coarse maps) so that interior and boundary pixels both exist, and pure noise (every pixel a boundary pixel).
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        outb = {}
+        for ncls, B, S, blob in ((4, 2, 32, 4), (9, 3, 24, 3), (2, 1, 40, 8), (4, 2, 16, 1)):
+            coarse = torch.randint(0, ncls, (B, 1, S // blob, S // blob), generator=g).float()
+            labels = torch.nn.functional.interpolate(coarse, scale_factor=blob, mode="nearest")[:, 0]
+            for lt, lw in (("boundary", "1.0"), ("dice,ce,boundary", "0.3,0.3,0.4")):
+                logits = (torch.randn(B, ncls, S, S, generator=g) * 2).requires_grad_(True)
+                crit = core.Criterion(ncls, types.SimpleNamespace(loss_type=lt, loss_weights=lw))
+                loss = crit(logits, labels)
+                loss.backward()
+                outb[f"c{ncls}_s{S}_{lt}"] = dict(logits=logits.detach().clone(), labels=labels.long(), loss=loss.detach().clone(),
+                                                 grad=logits.grad.clone(), loss_type=lt, loss_weights=lw)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    torch.save(outb, os.path.join(HERE, "loss_boundary.pt"))
+    print("boundary loss:", {k: round(v["loss"].item(), 6) for k, v in outb.items()})
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":          # only the loss fixtures (no model import needed)
+        loss_fixture()
+        sys.exit(0)
     nets = ref_shim.import_reference()
     module_fixtures(nets)
     loss_fixture()

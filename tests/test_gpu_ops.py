@@ -450,6 +450,44 @@ def test_dice_ce(golden_loss):
         assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
 
 
+def test_seg_loss_boundary_dou(golden_loss_boundary):
+    """fused Criterion with the BoundaryDoULoss term against the reference's own outputs; integer counts bit-exact"""
+    from cenet_b200 import ops
+    from oracle import cenet_oracle as O
+    for key, c in golden_loss_boundary.items():
+        ncls = c["logits"].shape[1]
+        w = dict(zip(c["loss_type"].split(","), (float(v) for v in c["loss_weights"].split(","))))
+        wd, wc, wb = w.get("dice", 0.0), w.get("ce", 0.0), w.get("boundary", 0.0)
+        logits, labels = c["logits"].to(DEV), c["labels"].to(DEV)
+        B, _, H, W = logits.shape
+        ws = ops.seg_loss_ws(B, ncls, H, W, DEV)
+        loss, grad = torch.empty(1 + ncls, device=DEV), torch.empty_like(logits)
+        ops.seg_loss(logits, labels, loss, grad, ws, B, ncls, H, W, wd, wc, wb)
+        torch.testing.assert_close(loss[0].cpu(), c["loss"], rtol=3e-6, atol=1e-6)
+        assert rel(grad, c["grad"]) < 2e-5, key
+        nblk = ops.loss_nblocks(B * H * W)
+        tot = ws[(4 * ncls + 1) * nblk:(4 * ncls + 1) * nblk + 4 * ncls].cpu().view(ncls, 4)
+        C, S = O.boundary_counts(c["labels"], ncls)
+        assert torch.equal(tot[:, 2].long(), S) and torch.equal(tot[:, 3].long(), C), key      # integer reductions: exact
+        loss2, grad2 = torch.empty_like(loss), torch.empty_like(grad)
+        ops.seg_loss(logits, labels, loss2, grad2, ws, B, ncls, H, W, wd, wc, wb)
+        assert torch.equal(loss, loss2) and torch.equal(grad, grad2)
+    # full-size property check (BASELINE configs[2] shape): counts against the oracle on 24 x 224 x 224 labels
+    B, ncls, H, W = 24, 4, 224, 224
+    gg = torch.Generator().manual_seed(11)
+    coarse = torch.randint(0, ncls, (B, 1, H // 8, W // 8), generator=gg).float()
+    labels = F.interpolate(coarse, scale_factor=8, mode="nearest")[:, 0].long()
+    logits = torch.randn(B, ncls, H, W, generator=gg)
+    ws = ops.seg_loss_ws(B, ncls, H, W, DEV)
+    loss = torch.empty(1 + ncls, device=DEV)
+    ops.seg_loss(logits.to(DEV), labels.to(DEV), loss, None, ws, B, ncls, H, W, 0.0, 0.0, 1.0)
+    nblk = ops.loss_nblocks(B * H * W)
+    tot = ws[(4 * ncls + 1) * nblk:(4 * ncls + 1) * nblk + 4 * ncls].cpu().view(ncls, 4)
+    C, S = O.boundary_counts(labels, ncls)
+    assert torch.equal(tot[:, 2].long(), S) and torch.equal(tot[:, 3].long(), C)
+    torch.testing.assert_close(loss[0].cpu(), O.boundary_dou_loss(logits, labels, ncls), rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("Cin,dtype", [(1, torch.bfloat16), (3, torch.bfloat16), (1, torch.float32)])
 def test_stem5x5(Cin, dtype):
     from cenet_b200 import ops

@@ -165,3 +165,48 @@ def test_autograd_boundary_matches_fused_step():
     with torch.no_grad():
         y = m(x.to(DEV))
     assert torch.isfinite(y).all()
+
+
+def test_boundary_criterion_fused_step_and_dropin_module(monkeypatch):
+    """`--loss_type boundary` (the ACDC / Synapse script default, acdc.sh:63): the fused step with the Boundary-DoU term
+    against oracle autograd, and the drop-in `losses.Criterion` on the autograd boundary of the module."""
+    import types
+    from cenet_b200.losses import Criterion
+    name, batch, size = "acdc", 2, 96
+    kw = fixtures.CONFIGS[name]
+    from cenet_b200.networks import CENet
+    torch.manual_seed(1234)
+    sd = fixtures.perturb_state(CENet(**kw).state_dict(), 1234)
+    x = fixtures.synth_input(name, batch, size=size)
+    coarse = torch.randint(0, 4, (batch, 1, size // 8, size // 8), generator=torch.Generator().manual_seed(5)).float()
+    labels = torch.nn.functional.interpolate(coarse, scale_factor=8, mode="nearest")[:, 0].long()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    loss_ref = O.criterion(O.cenet_forward(leaf, O.Cfg(**kw), x, training=True), labels, 4, w_boundary=1.0)
+    gref = dict(zip(names, torch.autograd.grad(loss_ref, [leaf[k] for k in names], allow_unused=True)))
+    monkeypatch.setenv("CENET_B200_PRECISION", "fp32")      # module.train_engine() then hands out the fp32 validation plan
+    m = CENet(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    eng = m.train_engine(DEV)
+    assert eng.precision == "fp32"
+    eng.drop_path = False
+    eng.use_graph = False
+    out = eng.train_step(x.to(DEV), labels.to(DEV), w_dice=0.0, w_ce=0.0, w_boundary=1.0, optimize=False)
+    torch.cuda.synchronize()
+    assert abs(out[0].item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    gn = max(g.norm().item() for g in gref.values() if g is not None)
+    bad = [(k, (eng.GP[k].cpu() - g).norm().item() / max(g.norm().item(), 1e-12)) for k, g in gref.items()
+           if g is not None and not (eng.GP[k].cpu() - g).norm().item() < 2e-3 * g.norm().item() + 1e-6 * gn]
+    assert not bad, bad[:10]
+    # drop-in Criterion through autograd: same loss, same gradients as the fused step
+    crit = Criterion(4, types.SimpleNamespace(loss_type="boundary", loss_weights="1.0"))
+    fused = eng.gflat.clone()
+    m.zero_grad(set_to_none=True)
+    loss = crit(m(x.to(DEV)), labels.to(DEV).float())
+    loss.backward()
+    assert abs(loss.item() - out[0].item()) < 1e-5
+    g_auto = torch.cat([p.grad.flatten() for _, p in sorted(m.named_parameters(), key=lambda np_: eng.param_offsets[np_[0]])])
+    g_fused = torch.cat([fused[eng.param_offsets[n]:eng.param_offsets[n] + p.numel()]
+                         for n, p in sorted(m.named_parameters(), key=lambda np_: eng.param_offsets[np_[0]])])
+    assert ((g_auto - g_fused).norm() / g_fused.norm()).item() < 1e-5

@@ -84,6 +84,24 @@ def test_loss(golden_loss):
         torch.testing.assert_close(logits.grad, c["grad"], rtol=1e-4, atol=1e-8)
 
 
+def _weights(c):
+    w = dict(zip(c["loss_type"].split(","), (float(v) for v in c["loss_weights"].split(","))))
+    return dict(w_dice=w.get("dice", 0.0), w_ce=w.get("ce", 0.0), w_boundary=w.get("boundary", 0.0))
+
+
+def test_boundary_dou_loss(golden_loss_boundary):
+    """BoundaryDoULoss alone and inside Criterion('dice,ce,boundary') as the reference computes them (core.py:83-131,161-188)"""
+    for key, c in golden_loss_boundary.items():
+        ncls = c["logits"].shape[1]
+        logits = c["logits"].clone().requires_grad_(True)
+        loss = O.criterion(logits, c["labels"], ncls, **_weights(c))
+        loss.backward()
+        torch.testing.assert_close(loss.detach(), c["loss"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(logits.grad, c["grad"], rtol=1e-4, atol=1e-8)
+        C, S = O.boundary_counts(c["labels"], ncls)
+        assert torch.equal(S, torch.bincount(c["labels"].flatten(), minlength=ncls)) and bool((C <= S).all())
+
+
 @pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1)])
 def test_whole_model(name, batch):
     """Rebuild the deterministic weights, run the oracle, compare with what the reference produced."""
