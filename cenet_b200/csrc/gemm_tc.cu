@@ -121,6 +121,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   warps 2-9: epilogue of the previous tile out of the other accumulator stage, overlapping the next tile's loads+MMAs
 __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -122,6 +122,7 @@ class Engine:
         self._graphs = {}
         self.taps = None                              # dict -> intermediate activations are copied out (tests)
         self.launches_per_forward = None              # kernels launched by one pass (counted on the eager warm-up)
+        self.pdl_stats = None                         # counters of the programmatic-dependent-launch pass (pdl.py)
 
     # ------------------------------------------------------------------------------------------------ packing
     def _weights_version(self):
@@ -659,9 +660,13 @@ class Engine:
                 self._run(*args)                                   # eager warm-up: allocates every workspace
                 self.launches_per_forward = ops.launch_count() - n0
                 torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run(*args)
+                from . import pdl
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream(self.dev)                 # capture needs a non-default stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g, self.pdl_stats = pdl.capture(lambda: self._run(*args))
+                cur.wait_stream(side)
                 self._graphs[key] = g
             g.replay()
         out.copy_(res)

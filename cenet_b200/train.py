@@ -1228,12 +1228,26 @@ class TrainEngine:
         cur = {}
         self._user_on_bucket, self._user_grad_hook = self.on_bucket, self.grad_hook
 
+        from . import pdl
+        use_pdl = pdl.enabled()
+        self.pdl_stats = []
+
         def begin():
-            cur["g"] = torch.cuda.CUDAGraph()
+            try:
+                cur["g"] = torch.cuda.CUDAGraph(keep_graph=True) if use_pdl else torch.cuda.CUDAGraph()
+                cur["keep"] = use_pdl
+            except TypeError:                                        # torch without keep_graph
+                cur["g"], cur["keep"] = torch.cuda.CUDAGraph(), False
             cur["g"].capture_begin(pool=pool)
 
         def end():
             cur["g"].capture_end()
+            if cur["keep"]:
+                try:
+                    self.pdl_stats.append(pdl.relax(cur["g"]))     # kernel -> kernel edges become programmatic (pdl.py)
+                except Exception as e:
+                    self.pdl_stats.append(dict(error=repr(e)))
+                cur["g"].instantiate()
             segs.append(("graph", cur["g"]))
 
         def cut_bucket(g_):
