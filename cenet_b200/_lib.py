@@ -85,7 +85,7 @@ _SIGS = {
     "cenet_lambda_bwd": [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "cenet_diff_rmsnorm_fwd": [vp, i32, vp, vp, ll, i32, i32, f32, f32, vp],
     "cenet_diff_rmsnorm_bwd": [vp, vp, i32, vp, vp, vp, ll, i32, i32, f32, f32, vp, ll, vp],
-    "cenet_fea_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, ll, vp],
+    "cenet_fea_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, ll, vp],
     "cenet_nchw_to_nhwc_slice": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_add": [vp, vp, i32, ll, i32, vp],
     "cenet_ccu_stats": [vp, i32, vp, vp, i32, i32, i32, vp, ll, vp],

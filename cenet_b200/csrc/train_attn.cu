@@ -491,58 +491,113 @@ __global__ void lambda_bwd_kernel(const float* dlam, const float* q1, const floa
 }
 
 // o[r, h*seg + i] = mult * a_i * rsqrt(mean_i a^2 + eps),  a = Om[r, (2h)*seg + i] - lam * Om[r, (2h+1)*seg + i]
-// thread = one (row, head) segment
+// A group of LPS lanes (power of two <= 32) owns one (row, head) segment; each lane keeps up to MAXV 8-element vectors of
+// both maps in registers (16-byte loads, the two maps of a head are adjacent so their sectors are fully used), the two
+// reductions run over the group with shuffles.  One read of Om (+ dO), one write.  seg % 8 == 0, seg <= 8 * 32 * MAXV.
+constexpr int DR_MAXV = 2;
 template <typename T>
 __global__ void __launch_bounds__(256) diff_rmsnorm_fwd_kernel(const T* __restrict__ Om, const float* __restrict__ lamp, T* __restrict__ o,
-                                                               long long rows, int heads, int seg, float eps, float mult) {
+                                                               long long rows, int heads, int seg, int lps, float eps, float mult) {
   pdl_prologue();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * heads) return;
+  const int sub = threadIdx.x % lps;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lps;
+  const bool live = i < rows * heads;
   const float lam = lamp[0];
-  const long long r = i / heads;
-  const int h = (int)(i % heads);
+  const long long r = live ? i / heads : 0;
+  const int h = live ? (int)(i % heads) : 0;
   const T* a1 = Om + r * (2LL * heads * seg) + (2 * h) * seg;
   const T* a2 = a1 + seg;
+  const int nv = seg >> 3;
+  float a[DR_MAXV][8];
   float ss = 0.f;
-  for (int c = 0; c < seg; c++) { const float a = ldf(a1 + c) - lam * ldf(a2 + c); ss = fmaf(a, a, ss); }
+#pragma unroll
+  for (int k = 0; k < DR_MAXV; k++) {
+    const int v = sub + k * lps;
+    if (v < nv) {
+      float x1[8], x2[8];
+      ldv<8>(a1 + v * 8, x1);
+      ldv<8>(a2 + v * 8, x2);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { a[k][j] = x1[j] - lam * x2[j]; ss = fmaf(a[k][j], a[k][j], ss); }
+    }
+  }
+  for (int off = lps >> 1; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (!live) return;
   const float rs = rsqrtf(ss / seg + eps) * mult;
   T* op = o + r * ((long long)heads * seg) + h * seg;
-  for (int c = 0; c < seg; c++) stf(op + c, (ldf(a1 + c) - lam * ldf(a2 + c)) * rs);
+#pragma unroll
+  for (int k = 0; k < DR_MAXV; k++) {
+    const int v = sub + k * lps;
+    if (v < nv) {
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) out[j] = a[k][j] * rs;
+      stv<8>(op + v * 8, out);
+    }
+  }
 }
 
 // backward: da = mult*rs*(do - a * rs^2 * mean(do*a));  dOm1 = da, dOm2 = -lam*da, dlam -= sum(da * Om2)
 template <typename T>
 __global__ void __launch_bounds__(256) diff_rmsnorm_bwd_kernel(const T* __restrict__ dO, const T* __restrict__ Om,
                                                                const float* __restrict__ lamp, T* __restrict__ dOm, long long rows,
-                                                               int heads, int seg, float eps, float mult, float* __restrict__ ws) {
+                                                               int heads, int seg, int lps, float eps, float mult,
+                                                               float* __restrict__ ws) {
   pdl_prologue();
   __shared__ float red[8];
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  float dl = 0.f;
-  if (i < rows * heads) {
-    const float lam = lamp[0];
-    const long long r = i / heads;
-    const int h = (int)(i % heads);
-    const T* a1 = Om + r * (2LL * heads * seg) + (2 * h) * seg;
-    const T* a2 = a1 + seg;
-    const T* gp = dO + r * ((long long)heads * seg) + h * seg;
-    float ss = 0.f, ga = 0.f;
-    for (int c = 0; c < seg; c++) {
-      const float a = ldf(a1 + c) - lam * ldf(a2 + c);
-      ss = fmaf(a, a, ss);
-      ga = fmaf(a, ldf(gp + c), ga);
+  const int sub = threadIdx.x % lps;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lps;
+  const bool live = i < rows * heads;
+  const float lam = lamp[0];
+  const long long r = live ? i / heads : 0;
+  const int h = live ? (int)(i % heads) : 0;
+  const T* a1 = Om + r * (2LL * heads * seg) + (2 * h) * seg;
+  const T* a2 = a1 + seg;
+  const T* gp = dO + r * ((long long)heads * seg) + h * seg;
+  const int nv = seg >> 3;
+  float a[DR_MAXV][8], x2[DR_MAXV][8], g[DR_MAXV][8];
+  float ss = 0.f, ga = 0.f;
+#pragma unroll
+  for (int k = 0; k < DR_MAXV; k++) {
+    const int v = sub + k * lps;
+    if (v < nv) {
+      float x1[8];
+      ldv<8>(a1 + v * 8, x1);
+      ldv<8>(a2 + v * 8, x2[k]);
+      ldv<8>(gp + v * 8, g[k]);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        a[k][j] = x1[j] - lam * x2[k][j];
+        ss = fmaf(a[k][j], a[k][j], ss);
+        ga = fmaf(a[k][j], g[k][j], ga);
+      }
     }
+  }
+  for (int off = lps >> 1; off > 0; off >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    ga += __shfl_xor_sync(0xffffffffu, ga, off);
+  }
+  float dl = 0.f;
+  if (live) {
     const float rs = rsqrtf(ss / seg + eps);
-    const float k = rs * rs * ga / seg;
+    const float kk = rs * rs * ga / seg;
     T* d1 = dOm + r * (2LL * heads * seg) + (2 * h) * seg;
     T* d2 = d1 + seg;
-    for (int c = 0; c < seg; c++) {
-      const float x2 = ldf(a2 + c);
-      const float a = ldf(a1 + c) - lam * x2;
-      const float da = mult * rs * (ldf(gp + c) - a * k);
-      stf(d1 + c, da);
-      stf(d2 + c, -lam * da);
-      dl = fmaf(-da, x2, dl);
+#pragma unroll
+    for (int k = 0; k < DR_MAXV; k++) {
+      const int v = sub + k * lps;
+      if (v < nv) {
+        float o1[8], o2[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float da = mult * rs * (g[k][j] - a[k][j] * kk);
+          o1[j] = da;
+          o2[j] = -lam * da;
+          dl = fmaf(-da, x2[k][j], dl);
+        }
+        stv<8>(d1 + v * 8, o1);
+        stv<8>(d2 + v * 8, o2);
+      }
     }
   }
   dl = warp_sum(dl);
@@ -668,8 +723,12 @@ extern "C" int cenet_diff_rmsnorm_fwd(const void* Om, int dtype, const float* la
                                       float eps, float mult, cenet_stream_t st) {
   CENET_REQUIRE(Om && lam && o, "cenet_diff_rmsnorm_fwd: null pointer");
   if (rows == 0) return 0;
-  CENET_DISPATCH(dtype, T, (diff_rmsnorm_fwd_kernel<T><<<cdiv(rows * heads, 256), 256, 0, to_stream(st)>>>(
-                               (const T*)Om, lam, (T*)o, rows, heads, seg, eps, mult)));
+  CENET_REQUIRE(seg % 8 == 0 && seg <= 8 * 32 * DR_MAXV && ((((uintptr_t)Om | (uintptr_t)o) & 15) == 0),
+                "cenet_diff_rmsnorm_fwd: segment of %d elements (needs a multiple of 8, <= %d, 16-byte aligned rows)", seg, 8 * 32 * DR_MAXV);
+  int lps = 1;
+  while (lps < 32 && lps * DR_MAXV < seg / 8) lps <<= 1;            // lanes per segment
+  CENET_DISPATCH(dtype, T, (diff_rmsnorm_fwd_kernel<T><<<cdiv(rows * heads * lps, 256), 256, 0, to_stream(st)>>>(
+                               (const T*)Om, lam, (T*)o, rows, heads, seg, lps, eps, mult)));
   CENET_LAUNCH_CHECK("diff_rmsnorm_fwd");
   return 0;
 }
@@ -677,11 +736,15 @@ extern "C" int cenet_diff_rmsnorm_bwd(const void* dO, const void* Om, int dtype,
                                       long long rows, int heads, int seg, float eps, float mult, float* ws, long long ws_elems,
                                       cenet_stream_t st) {
   CENET_REQUIRE(dO && Om && lam && dOm && dlam && ws, "cenet_diff_rmsnorm_bwd: null pointer");
-  const int nb = cdiv(rows * heads, 256);
+  CENET_REQUIRE(seg % 8 == 0 && seg <= 8 * 32 * DR_MAXV && ((((uintptr_t)Om | (uintptr_t)dO | (uintptr_t)dOm) & 15) == 0),
+                "cenet_diff_rmsnorm_bwd: segment of %d elements (needs a multiple of 8, <= %d, 16-byte aligned rows)", seg, 8 * 32 * DR_MAXV);
+  int lps = 1;
+  while (lps < 32 && lps * DR_MAXV < seg / 8) lps <<= 1;            // lanes per segment
+  const int nb = cdiv(rows * heads * lps, 256);
   CENET_REQUIRE(nb <= ws_elems, "cenet_diff_rmsnorm_bwd: workspace too small");
   cudaStream_t s = to_stream(st);
   CENET_DISPATCH(dtype, T, (diff_rmsnorm_bwd_kernel<T><<<nb, 256, 0, s>>>((const T*)dO, (const T*)Om, lam, (T*)dOm, rows, heads, seg,
-                                                                          eps, mult, ws)));
+                                                                          lps, eps, mult, ws)));
   CENET_LAUNCH_CHECK("diff_rmsnorm_bwd");
   sum_partials_kernel<<<1, 256, 0, s>>>(ws, nb, dlam);
   CENET_LAUNCH_CHECK("sum_partials");

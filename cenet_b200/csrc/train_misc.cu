@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
                                                       const float* __restrict__ wch, T* __restrict__ dy, int acc_dy, T* __restrict__ dgate,
                                                       int C2, int H, int W, const float* __restrict__ mats,
                                                       const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws,
-                                                      int nplanes, float* __restrict__ scratch) {
+                                                      int nplanes, float* __restrict__ scratch, int ident_mask) {
   pdl_prologue();
   extern __shared__ float sm_dyn[];
   __shared__ float red[8];
@@ -36,8 +36,13 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   __syncthreads();                     // the previous plane of this block is done with the working set
   for (int i = tid; i < HW; i += 256) { Y[i] = ldf(y + base + i); DZ[i] = ldf(dz + base + i); }
   __syncthreads();
-  // forward residuals R_s = Y - A_h Y A_w^T
+  // forward residuals R_s = Y - A_h Y A_w^T   (scale factor 1.0: the operator is the identity, R_s = 0 exactly and so is its
+  // gradient term -- bit `s` of ident_mask -- which removes four of the separable passes)
   for (int s = 0; s < ns; s++) {
+    if ((ident_mask >> s) & 1) {
+      for (int i = tid; i < HW; i += 256) R[s * HW + i] = 0.f;
+      continue;
+    }
     const float* Ah = mats + ((size_t)s * 2 + 0) * nmax * nmax;
     const float* Aw = mats + ((size_t)s * 2 + 1) * nmax * nmax;
     // the operators are banded (bilinear taps): [lo, hi) of the non-zeros of every row / column comes from the host
@@ -92,6 +97,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   __syncthreads();
   // d(y) += G_s - A_h^T (G_s A_w)
   for (int s = 0; s < ns; s++) {
+    if ((ident_mask >> s) & 1) continue;                      // G_s == 0
     const float* Ah = mats + ((size_t)s * 2 + 0) * nmax * nmax;
     const float* Aw = mats + ((size_t)s * 2 + 1) * nmax * nmax;
     const float* G = R + s * HW;
@@ -358,7 +364,7 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>((
 
 extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, int dtype, const float* w, void* dy, int acc_dy,
                              void* dgate, float* dw, int B, int C2, int H, int W, const float* mats, const int* bands, int nmax,
-                             int nscales, float* ws, long long ws_elems, cenet_stream_t st) {
+                             int nscales, int ident_mask, float* ws, long long ws_elems, cenet_stream_t st) {
   CENET_REQUIRE(y && gate && dz && w && dy && dgate && dw && mats && bands && ws, "cenet_fea_bwd: null pointer");
   CENET_REQUIRE(nscales >= 1 && nscales <= 3, "cenet_fea_bwd: 1..3 scales");
   CENET_REQUIRE(H <= nmax && W <= nmax, "cenet_fea_bwd: operator matrices smaller than the plane");
@@ -383,7 +389,7 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
       configured.store(200 * 1024);
     }
     fea_bwd_kernel<T><<<blocks, 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
-                                                bands, nmax, nscales, ws, nplanes, scratch);
+                                                bands, nmax, nscales, ws, nplanes, scratch, ident_mask);
     CENET_LAUNCH_CHECK("fea_bwd");
   });
   fea_dw_finalize_kernel<<<cdiv(C2, 128), 128, 0, s>>>(ws, B, C2, dw);

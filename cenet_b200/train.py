@@ -1006,7 +1006,7 @@ class TrainEngine:
         def fea_bwd():
             acc = self.wr(y)
             tops.fea_bwd(y, gate, self.G(z), fw.reshape(-1), self.G(y), acc, self.G(gate), GP[p + ".boundary.w"], B, E, H, W,
-                         mats, len(scales), self._ws(0))
+                         mats, len(scales), self._ws(0), ident_mask=sum(1 << i for i, sf in enumerate(scales) if float(sf) == 1.0))
             self.wr(gate)
         self.tape.append(fea_bwd)
         zt = self.buf(key + ".zt", (M, E))

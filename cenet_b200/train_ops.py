@@ -171,10 +171,11 @@ def _fea_bands(mats):
     return b
 
 
-def fea_bwd(y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, nscales, ws):
+def fea_bwd(y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, nscales, ws, ident_mask=0):
+    """ident_mask: bit s set when scale factor s is 1.0 (its operator is the identity; the kernel skips its passes)"""
     wp, wn = _ws(ws)
     L.call("cenet_fea_bwd", _p(y), _p(gate), _p(dz), dt(y), _f32(w, "w"), _p(dy), int(acc), _p(dgate), _f32(dw, "dw"), B, E, H,
-           W, _f32(mats, "mats"), _i32(_fea_bands(mats), "bands"), mats.shape[-1], nscales, wp, wn, _stream())
+           W, _f32(mats, "mats"), _i32(_fea_bands(mats), "bands"), mats.shape[-1], nscales, int(ident_mask), wp, wn, _stream())
 
 
 def nchw_to_nhwc_slice(x, out, B, HW, C_, Ctot, coff, acc):

@@ -265,10 +265,11 @@ int cenet_diff_rmsnorm_fwd(const void* Om, int dtype, const float* lam, void* o,
 int cenet_diff_rmsnorm_bwd(const void* dO, const void* Om, int dtype, const float* lam, void* dOm, float* dlam, long long rows,
                            int heads, int seg, float eps, float mult, float* ws, long long ws_elems, cenet_stream_t s);
 /* backward of cenet_fea_combine: dy (+)=, dgate =, dw[c]; mats [nscales][2][nmax][nmax] = per-axis operators Up_s Down_s,
- * bands [nscales][2 axes][2: rows, columns][nmax][2] = [lo, hi) of the non-zeros of every row / column of those operators */
+ * bands [nscales][2 axes][2: rows, columns][nmax][2] = [lo, hi) of the non-zeros of every row / column of those operators;
+ * bit s of ident_mask: scale factor s is 1.0 (identity operator: its residual and gradient term are exactly zero, skipped) */
 int cenet_fea_bwd(const void* y, const void* gate, const void* dz, int dtype, const float* w, void* dy, int acc_dy, void* dgate,
-                  float* dw, int B, int C2, int H, int W, const float* mats, const int* bands, int nmax, int nscales, float* ws,
-                  long long ws_elems, cenet_stream_t s);
+                  float* dw, int B, int C2, int H, int W, const float* mats, const int* bands, int nmax, int nscales,
+                  int ident_mask, float* ws, long long ws_elems, cenet_stream_t s);
 /* out_nhwc[b,hw,c] (+)= x_nchw[b, coff+c, hw] */
 int cenet_nchw_to_nhwc_slice(const void* x, int dtype, void* out, int B, int HW, int C, int Ctot, int coff, int acc, cenet_stream_t s);
 /* dst (+)= src */

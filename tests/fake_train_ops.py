@@ -228,7 +228,7 @@ def diff_rmsnorm_bwd(do, Om, lam, dOm, dlam, M, heads, seg, eps, mult, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ DSEB
-def fea_bwd(y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, nscales, ws):
+def fea_bwd(y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, nscales, ws, ident_mask=0):
     """z = 2y + w*edge(y) + gate*y with the per-axis operators A_s = mats[s, axis, :n, :n] (up(down(.)))"""
     _LAUNCHES[0] += 2
     yf = _flat(y).view(B, E, H, W).float().detach().requires_grad_(True)

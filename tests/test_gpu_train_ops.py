@@ -243,15 +243,16 @@ def test_softmax_bwd_and_diff_rmsnorm(dtype):
     P = torch.softmax(rn((rows, n), F32, 1), -1).to(dtype)
     dP = rn((rows, n), dtype, 2)
     check("softmax_bwd_rows_", [P, dP, rows, n], {}, [1], TOL[dtype])
-    M, heads, seg = 700, 4, 32
-    Om, lam = rn((M, 2 * heads * seg), dtype, 3), torch.tensor([0.37, 0, 0, 0])
-    o = torch.zeros(M, heads * seg, dtype=dtype)
-    check("diff_rmsnorm_fwd", [Om, lam, o, M, heads, seg, 1e-5, 0.44], {}, [2], TOL[dtype])
-    do, dOm, dlam = rn((M, heads * seg), dtype, 4), torch.zeros_like(Om), torch.zeros(4)
     from cenet_b200 import train_ops as tops
-    ca, ck, ga, gk = run_pair(FT, tops, "diff_rmsnorm_bwd", [do, Om, lam, dOm, dlam, M, heads, seg, 1e-5, 0.44, ws()], {})
-    assert rel(ga[3], ca[3]) < TOL[dtype]
-    assert abs(ga[4][0].item() - ca[4][0].item()) < 2e-3 * max(1.0, abs(ca[4][0].item())) * (1 if dtype == F32 else 20)
+    # segment = 2 * head_dim of the value heads: 16 / 32 (ACDC, Synapse), 40 (Synapse 14x14), 64 / 128 / 320 (skin)
+    for M, heads, seg in ((700, 4, 32), (333, 16, 16), (200, 8, 40), (257, 2, 128), (100, 2, 320)):
+        Om, lam = rn((M, 2 * heads * seg), dtype, 3), torch.tensor([0.37, 0, 0, 0])
+        o = torch.zeros(M, heads * seg, dtype=dtype)
+        check("diff_rmsnorm_fwd", [Om, lam, o, M, heads, seg, 1e-5, 0.44], {}, [2], TOL[dtype])
+        do, dOm, dlam = rn((M, heads * seg), dtype, 4), torch.zeros_like(Om), torch.zeros(4)
+        ca, ck, ga, gk = run_pair(FT, tops, "diff_rmsnorm_bwd", [do, Om, lam, dOm, dlam, M, heads, seg, 1e-5, 0.44, ws()], {})
+        assert rel(ga[3], ca[3]) < TOL[dtype], (M, heads, seg)
+        assert abs(ga[4][0].item() - ca[4][0].item()) < 2e-3 * max(1.0, abs(ca[4][0].item())) * (1 if dtype == F32 else 20)
 
 
 def test_lambda_fwd_bwd():
@@ -283,8 +284,9 @@ def test_fea_bwd_matches_autograd_of_oracle_fea(dtype, scales, H, W):
     w = rn((E,), F32, 4) + 0.5
     dy, dgate, dw = rn((B, E, H, W), dtype, 5), torch.zeros(B, E, H, W, dtype=dtype), torch.zeros(E)
     for acc in (False, True):
-        check("fea_bwd", [y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, len(scales), ws()], {}, [4, 6, 7],
-              5e-4 if dtype == F32 else 2e-2)
+        for mask in (0, sum(1 << i for i, sf in enumerate(scales) if sf == 1.0)):        # with / without the identity shortcut
+            check("fea_bwd", [y, gate, dz, w, dy, acc, dgate, dw, B, E, H, W, mats, len(scales), ws()], dict(ident_mask=mask),
+                  [4, 6, 7], 5e-4 if dtype == F32 else 2e-2)
     if dtype == F32:                                        # the dense-operator formulation IS the oracle's FEA
         yf = y.clone().requires_grad_(True)
         z = O.fea({"m.w": w.view(1, E, 1, 1)}, "m", yf, list(scales)) + yf + gate * yf
