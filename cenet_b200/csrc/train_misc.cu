@@ -14,14 +14,16 @@ __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 // it fits (planes up to 56x56 with 3 scales); larger planes (128x128 at 512x512 inputs) use a per-block slab of the
 // workspace instead (`scratch`, L2-resident) and the blocks stride over the planes.
 template <typename T>
-__global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gate, const T* __restrict__ dz,
+__global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gate, const T* __restrict__ dz,
                                                       const float* __restrict__ wch, T* __restrict__ dy, int acc_dy, T* __restrict__ dgate,
                                                       int C2, int H, int W, const float* __restrict__ mats,
                                                       const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws,
                                                       int nplanes, float* __restrict__ scratch, int ident_mask) {
   pdl_prologue();
   extern __shared__ float sm_dyn[];
-  __shared__ float red[8];
+  __shared__ float red[16];
+  const int nthr = blockDim.x;                               // 256, or 512 for planes >= 2048 pixels (more threads per plane:
+                                                             // the separable passes are latency-bound, shared memory caps the CTAs per SM)
   const int HW = H * W;
   float* sm = scratch ? scratch + (size_t)blockIdx.x * (4 + ns) * HW : sm_dyn;
   float* Y = sm;
@@ -34,13 +36,13 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   const int c = plane % C2;
   const long long base = (long long)plane * HW;
   __syncthreads();                     // the previous plane of this block is done with the working set
-  for (int i = tid; i < HW; i += 256) { Y[i] = ldf(y + base + i); DZ[i] = ldf(dz + base + i); }
+  for (int i = tid; i < HW; i += nthr) { Y[i] = ldf(y + base + i); DZ[i] = ldf(dz + base + i); }
   __syncthreads();
   // forward residuals R_s = Y - A_h Y A_w^T   (scale factor 1.0: the operator is the identity, R_s = 0 exactly and so is its
   // gradient term -- bit `s` of ident_mask -- which removes four of the separable passes)
   for (int s = 0; s < ns; s++) {
     if ((ident_mask >> s) & 1) {
-      for (int i = tid; i < HW; i += 256) R[s * HW + i] = 0.f;
+      for (int i = tid; i < HW; i += nthr) R[s * HW + i] = 0.f;
       continue;
     }
     const float* Ah = mats + ((size_t)s * 2 + 0) * nmax * nmax;
@@ -48,14 +50,14 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
     // the operators are banded (bilinear taps): [lo, hi) of the non-zeros of every row / column comes from the host
     const int* rbh = bands + (((size_t)s * 2 + 0) * 2 + 0) * nmax * 2;     // row bands of A_h
     const int* rbw = bands + (((size_t)s * 2 + 1) * 2 + 0) * nmax * 2;     // row bands of A_w
-    for (int i = tid; i < HW; i += 256) {
+    for (int i = tid; i < HW; i += nthr) {
       const int r = i / W, w = i % W;
       float a = 0.f;
       for (int h = rbh[2 * r]; h < rbh[2 * r + 1]; h++) a = fmaf(__ldg(Ah + r * nmax + h), Y[h * W + w], a);
       Tm[i] = a;
     }
     __syncthreads();
-    for (int i = tid; i < HW; i += 256) {
+    for (int i = tid; i < HW; i += nthr) {
       const int r = i / W, j = i % W;
       float a = 0.f;
       for (int w = rbw[2 * j]; w < rbw[2 * j + 1]; w++) a = fmaf(Tm[r * W + w], __ldg(Aw + j * nmax + w), a);
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   const float invm = npairs > 0 ? 1.f / npairs : 0.f;
   const float wc = wch[c];
   float dwp = 0.f;
-  for (int i = tid; i < HW; i += 256) {
+  for (int i = tid; i < HW; i += nthr) {
     float r[3], e[3], de[3];
 #pragma unroll
     for (int s = 0; s < 3; s++) { r[s] = s < ns ? R[s * HW + i] : 0.f; e[s] = fabsf(r[s]); de[s] = 0.f; }
@@ -103,14 +105,14 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
     const float* G = R + s * HW;
     const int* cbh = bands + (((size_t)s * 2 + 0) * 2 + 1) * nmax * 2;     // column bands of A_h
     const int* cbw = bands + (((size_t)s * 2 + 1) * 2 + 1) * nmax * 2;     // column bands of A_w
-    for (int i = tid; i < HW; i += 256) {
+    for (int i = tid; i < HW; i += nthr) {
       const int r = i / W, w = i % W;
       float a = 0.f;
       for (int j = cbw[2 * w]; j < cbw[2 * w + 1]; j++) a = fmaf(G[r * W + j], __ldg(Aw + j * nmax + w), a);
       Tm[i] = a;
     }
     __syncthreads();
-    for (int i = tid; i < HW; i += 256) {
+    for (int i = tid; i < HW; i += nthr) {
       const int h = i / W, w = i % W;
       float a = 0.f;
       for (int r = cbh[2 * h]; r < cbh[2 * h + 1]; r++) a = fmaf(__ldg(Ah + r * nmax + h), Tm[r * W + w], a);
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
     }
     __syncthreads();
   }
-  for (int i = tid; i < HW; i += 256) {
+  for (int i = tid; i < HW; i += nthr) {
     float v = ACC[i];
     if (acc_dy) v += ldf(dy + base + i);
     stf(dy + base + i, v);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(256) fea_bwd_kernel(const T* __restrict__ y, c
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
-    for (int w = 0; w < 8; w++) t += red[w];
+    for (int w = 0; w < (nthr >> 5); w++) t += red[w];
     ws[plane] = t;
   }
   }
@@ -388,7 +390,7 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
       cudaFuncSetAttribute(fea_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       configured.store(200 * 1024);
     }
-    fea_bwd_kernel<T><<<blocks, 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
+    fea_bwd_kernel<T><<<blocks, H * W >= 2048 ? 512 : 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
                                                 bands, nmax, nscales, ws, nplanes, scratch, ident_mask);
     CENET_LAUNCH_CHECK("fea_bwd");
   });

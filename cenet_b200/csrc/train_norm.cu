@@ -230,46 +230,64 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
-// one warp per row, NI = C/64 bf16x2 / float2 chunks per lane
-template <typename T, int NI>
+// LPR lanes per row (8 for C = 64, 16 for C = 128, 32 otherwise) with 8-element (16-byte bf16) vectors, 32 / LPR rows per warp
+// at a time: the four row reductions cost log2(LPR) shuffles for several rows at once and every load / store is a full
+// vector (the first version used one warp per row with 4-byte accesses: 1 TB/s).  Every lane accumulates d(gamma) / d(beta)
+// of ITS channels over the rows it sees; block partials go through shared memory in fixed order -> deterministic.
+template <typename T, int LPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                            const float* __restrict__ gamma, float eps, long long rows,
+                                                            const float* __restrict__ gamma, float eps, long long rows, int C,
                                                             T* __restrict__ dx, int acc, float* __restrict__ ws) {
   pdl_prologue();
-  constexpr int C = NI * 64;
-  extern __shared__ float dyn[];                          // [8 warps][2][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gsum[NI][2], bsum[NI][2], gam[NI][2];
+  constexpr int RPW = 32 / LPR;                           // rows per warp pass
+  extern __shared__ float dyn[];                          // [8 warps * RPW][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;
+  const int nvec = C >> 3;
+  const float invC = 1.f / (float)C;
+  float gsum[NV][8], bsum[NV][8], gam[NV][8];
 #pragma unroll
-  for (int i = 0; i < NI; i++) {
-    gsum[i][0] = gsum[i][1] = bsum[i][0] = bsum[i][1] = 0.f;
-    gam[i][0] = gamma[i * 64 + lane * 2];
-    gam[i][1] = gamma[i * 64 + lane * 2 + 1];
+  for (int i = 0; i < NV; i++) {
+    const int vi = sub + i * LPR;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { gsum[i][j] = bsum[i][j] = 0.f; gam[i][j] = vi < nvec ? gamma[vi * 8 + j] : 0.f; }
   }
-  const long long wstride = (long long)gridDim.x * 8;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += wstride) {
-    float xv[NI][2], gv[NI][2];
+  const long long rstride = (long long)gridDim.x * 8 * RPW;
+  for (long long r0 = ((long long)blockIdx.x * 8 + warp) * RPW; r0 < rows; r0 += rstride) {
+    const long long r = r0 + grp;
+    const bool live = r < rows;
+    float xv[NV][8], gv[NV][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; i++) {
-      ldv<2>(x + r * C + i * 64 + lane * 2, xv[i]);
-      ldv<2>(dy + r * C + i * 64 + lane * 2, gv[i]);
-      s += xv[i][0] + xv[i][1];
+    for (int i = 0; i < NV; i++) {
+      const int vi = sub + i * LPR;
+      if (live && vi < nvec) {
+        ldv<8>(x + r * C + vi * 8, xv[i]);
+        ldv<8>(dy + r * C + vi * 8, gv[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) xv[i][j] = gv[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) s += xv[i][j];
     }
-    const float mu = warp_sum(s) * (1.f / C);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * invC;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; i++) {
-      xv[i][0] -= mu; xv[i][1] -= mu;
-      q = fmaf(xv[i][0], xv[i][0], q);
-      q = fmaf(xv[i][1], xv[i][1], q);
+    for (int i = 0; i < NV; i++) {
+      const bool in = sub + i * LPR < nvec;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { xv[i][j] = in ? xv[i][j] - mu : 0.f; q = fmaf(xv[i][j], xv[i][j], q); }
     }
-    const float rs = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = rsqrtf(q * invC + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NI; i++)
+    for (int i = 0; i < NV; i++)
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
+      for (int j = 0; j < 8; j++) {
         xv[i][j] *= rs;                                   // x_hat
         gsum[i][j] = fmaf(gv[i][j], xv[i][j], gsum[i][j]);
         bsum[i][j] += gv[i][j];
@@ -277,33 +295,47 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         s1 += gv[i][j];
         s2 = fmaf(gv[i][j], xv[i][j], s2);
       }
-    s1 = warp_sum(s1) * (1.f / C);
-    s2 = warp_sum(s2) * (1.f / C);
 #pragma unroll
-    for (int i = 0; i < NI; i++) {
-      float o[2];
-      o[0] = rs * (gv[i][0] - s1 - xv[i][0] * s2);
-      o[1] = rs * (gv[i][1] - s1 - xv[i][1] * s2);
-      if (acc) {
-        float old[2];
-        ldv<2>(dx + r * C + i * 64 + lane * 2, old);
-        o[0] += old[0]; o[1] += old[1];
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= invC; s2 *= invC;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const int vi = sub + i * LPR;
+      if (live && vi < nvec) {
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o8[j] = rs * (gv[i][j] - s1 - xv[i][j] * s2);
+        if (acc) {
+          float old[8];
+          ldv<8>(dx + r * C + vi * 8, old);
+#pragma unroll
+          for (int j = 0; j < 8; j++) o8[j] += old[j];
+        }
+        stv<8>(dx + r * C + vi * 8, o8);
       }
-      stv<2>(dx + r * C + i * 64 + lane * 2, o);
     }
   }
-  // block partials of d(gamma), d(beta)
+  // block partials of d(gamma), d(beta): one slot per (warp, row group), summed in slot order
+  const int slot = warp * RPW + grp;
 #pragma unroll
-  for (int i = 0; i < NI; i++)
+  for (int i = 0; i < NV; i++) {
+    const int vi = sub + i * LPR;
+    if (vi < nvec) {
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      dyn[(warp * 2 + 0) * C + i * 64 + lane * 2 + j] = gsum[i][j];
-      dyn[(warp * 2 + 1) * C + i * 64 + lane * 2 + j] = bsum[i][j];
+      for (int j = 0; j < 8; j++) {
+        dyn[(slot * 2 + 0) * C + vi * 8 + j] = gsum[i][j];
+        dyn[(slot * 2 + 1) * C + vi * 8 + j] = bsum[i][j];
+      }
     }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int k = i / C, c = i - k * C;
     float t = 0.f;
-    for (int w = 0; w < 8; w++) t += dyn[(w * 2) * C + i];   // (w*2+k)*C + c with i = k*C + c
+    for (int w = 0; w < 8 * RPW; w++) t += dyn[(w * 2 + k) * C + c];
     ws[(size_t)blockIdx.x * 2 * C + i] = t;
   }
 }
@@ -406,16 +438,17 @@ extern "C" int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, con
   CENET_REQUIRE(C == 64 || C == 128 || C == 320 || C == 512, "cenet_layernorm_bwd: C=%d not instantiated (64/128/320/512)", C);
   if (rows == 0) return 0;
   cudaStream_t s = to_stream(st);
-  int nblk = (int)std::min<long long>((rows + 31) / 32, 4LL * kNumSMs);
+  CENET_REQUIRE(((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0), "cenet_layernorm_bwd: rows must be 16-byte aligned");
+  const int lpr = C == 64 ? 8 : C == 128 ? 16 : 32, rpw = 32 / lpr;
+  int nblk = (int)std::min<long long>((rows + 8 * rpw - 1) / (8 * rpw), 8LL * kNumSMs);
   CENET_REQUIRE((long long)nblk * 2 * C <= ws_elems, "cenet_layernorm_bwd: workspace too small");
-  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
-#define LN_CASE(NI)                                                                                                         \
-  layernorm_bwd_kernel<T, NI><<<nblk, 256, smem, s>>>((const T*)dy, (const T*)x, gamma, eps, rows, (T*)dx, acc, ws)
+  const size_t smem = (size_t)8 * rpw * 2 * C * sizeof(float);
+#define LN_CASE(LPR, NV)                                                                                                    \
+  layernorm_bwd_kernel<T, LPR, NV><<<nblk, 256, smem, s>>>((const T*)dy, (const T*)x, gamma, eps, rows, C, (T*)dx, acc, ws)
   CENET_DISPATCH(dtype, T, {
-    if (C == 64) LN_CASE(1);
-    else if (C == 128) LN_CASE(2);
-    else if (C == 320) LN_CASE(5);
-    else LN_CASE(8);
+    if (C == 64) LN_CASE(8, 1);
+    else if (C == 128) LN_CASE(16, 1);
+    else LN_CASE(32, 2);                                   // 320 (40 vectors) and 512 (64 vectors)
     CENET_LAUNCH_CHECK("layernorm_bwd");
   });
 #undef LN_CASE
