@@ -311,8 +311,10 @@ def run_product(args):
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     xd = [torch.empty_like(x_dev) for _ in range(2)]
+    ld = [torch.empty_like(labels_dev) for _ in range(2)]   # rotating device label buffers (no allocator traffic in the loop)
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
     def stage(i):
         j = i % 2
@@ -330,15 +332,17 @@ def run_product(args):
         if i + 1 < args.steps:
             stage(i + 1)
         main.wait_event(ev_in[i % 2])
+        if i >= 2:
+            main.wait_event(ev_out[i % 2])                  # the D2H of step i-2 has drained this label buffer
         flush.zero_()
-        lab = m.predict(xd[i % 2])                          # public call: logits -> argmax(softmax) fused, new tensor
+        lab = m.predict(xd[i % 2], out=ld[i % 2])           # public call: logits -> argmax(softmax) fused
         ev_free[i % 2].record(main)
         done = torch.cuda.Event()
         done.record(main)
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
             labels_host.copy_(lab, non_blocking=True)       # D2H of the label maps
-        lab.record_stream(s_out)
+            ev_out[i % 2].record(s_out)
     main.wait_stream(s_out)
     e_end.record(main)
     barrier()

@@ -374,6 +374,8 @@ class CENet(nn.Module):
         return self._engine(x).forward(x)
 
     @torch.no_grad()
-    def predict(self, x):
-        """logits -> `argmax(softmax(.,1),1)` fused on the device (metrics_eval.py:52); int64 [B,H,W]."""
-        return self._engine(x).forward(x, labels=True)
+    def predict(self, x, out=None):
+        """logits -> `argmax(softmax(.,1),1)` fused on the device (metrics_eval.py:52); int64 [B,H,W].
+        out: optional preallocated int64 [B,H,W] CUDA tensor (a serving loop that overlaps the D2H copy of the previous
+        batch with this call rotates two of them)."""
+        return self._engine(x).forward(x, labels=True, out=out)

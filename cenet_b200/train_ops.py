@@ -146,13 +146,10 @@ def diff_rmsnorm_bwd(do, Om, lam, dOm, dlam, M, heads, seg, eps, mult, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ DSEB
-_BANDS = {}
-
-
 def _fea_bands(mats):
-    """[lo, hi) of the non-zero entries of every row and column of the per-axis operators (they are banded)"""
-    key = (mats.data_ptr(), tuple(mats.shape))
-    b = _BANDS.get(key)
+    """[lo, hi) of the non-zero entries of every row and column of the per-axis operators (they are banded).
+    Cached ON the operator tensor (an address-keyed cache would hand stale bands to a new tensor that reuses the address)."""
+    b = getattr(mats, "_cenet_bands", None)
     if b is None:
         m = mats.detach().float().cpu()
         ns, _, n, _ = m.shape
@@ -167,7 +164,8 @@ def _fea_bands(mats):
                     hi = torch.where(nz, idx[None, :] + 1, torch.zeros_like(idx)[None, :]).max(1)[0]
                     out[s, ax, t, :, 0] = torch.where(any_, lo, torch.zeros_like(lo)).to(torch.int32)
                     out[s, ax, t, :, 1] = torch.where(any_, hi, torch.zeros_like(hi)).to(torch.int32)
-        b = _BANDS[key] = out.to(mats.device).contiguous()
+        b = out.to(mats.device).contiguous()
+        mats._cenet_bands = b
     return b
 
 
