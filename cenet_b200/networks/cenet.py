@@ -285,7 +285,9 @@ class _TrainForward(torch.autograd.Function):
     def backward(ctx, dlogits):
         eng = ctx.eng
         eng.backward_from(dlogits.contiguous())
-        grads = tuple(eng.GP[n].clone() if need else None for n, need in zip(ctx.names, ctx.needs))
+        flat = eng.gflat.clone()                                      # ONE copy; the per-parameter gradients are views of it
+        grads = tuple(flat[eng.param_offsets[n]:eng.param_offsets[n] + eng.GP[n].numel()].view(eng.GP[n].shape) if need else None
+                      for n, need in zip(ctx.names, ctx.needs))
         return (None, None) + grads
 
 

@@ -163,6 +163,7 @@ class TrainEngine:
         self._graphs = {}
         self.taps = None
         self.launches_per_step = None
+        self._ab_graphs = {}                  # (B,H,W) -> forward / backward CUDA graphs of the autograd-boundary path
         self._pack_maps = None                # [(int32 index map, flat packed buffer)] once built (see pack)
         self._trace = None
         # weight-gradient kernels on a second stream (see _WgradStream); CENET_B200_WGRAD_STREAM=0 keeps one stream
@@ -1271,7 +1272,25 @@ class TrainEngine:
         torch.cuda.current_stream().wait_stream(side)
         return segs
 
-    # ---- autograd-boundary entry points (eager; used by networks.CENet.forward in train() mode) -----------------------
+    # ---- autograd-boundary entry points (used by networks.CENet.forward in train() mode) ----------------------------------
+    # `net(x)` ... `loss.backward()` of the unchanged reference loop.  Per input shape: the first call runs eagerly (allocates
+    # every buffer), the second call captures the forward (weight re-pack + forward kernels) and, at its backward, the
+    # backward kernels as two CUDA graphs; later calls replay them.  Gradient-synchronised replicas (on_bucket / grad_hook)
+    # and tap recording stay eager.
+    def _ab_graphable(self):
+        return (self.use_graph and self.taps is None and self.dev.type == "cuda" and self.on_bucket is None
+                and self.grad_hook is None)
+
+    def _ab_capture(self, fn):
+        from . import pdl
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            g, _ = pdl.capture(fn)
+        cur.wait_stream(side)
+        return g
+
     def forward_logits(self, x):
         """train-mode forward; returns the engine-owned logits buffer [B,ncls,H,W] (valid until the next call)"""
         if x.device != self.dev:
@@ -1284,18 +1303,43 @@ class TrainEngine:
         self._plan_key = (B, H, W)
         x_in = self.buf("x_in", (B, x.shape[1], H, W), torch.float32)
         x_in.copy_(x.detach().float())
-        self.pack()
         logits = self.buf("logits", (B, self.cfg["num_classes"], H, W), torch.float32)
-        self.forward(x_in, B, H, W, logits)
+
+        def body():
+            self.pack()
+            self.forward(x_in, B, H, W, logits)
+        st = self._ab_graphs.get((B, H, W)) if self._ab_graphable() else None
+        if not self._ab_graphable():
+            body()
+        elif st is None:                                            # first call for this shape: eager warm-up
+            body()
+            self._ab_graphs[(B, H, W)] = {}
+        elif "fwd" not in st:                                       # second call: capture (records the tape), then run it
+            torch.cuda.current_stream().synchronize()
+            st["fwd"] = self._ab_capture(body)
+            st["tape"], st["written"], st["galias"] = self.tape, self._written, self._galias
+            st["fwd"].replay()
+        else:
+            self.tape, self._written, self._galias = st["tape"], st["written"], st["galias"]
+            st["fwd"].replay()
         self._last_logits = logits
         return logits
 
     def backward_from(self, dlogits):
         """run the recorded backward with d(loss)/d(logits); parameter gradients land in self.GP / self.gflat"""
         logits = self._last_logits
-        self._plan_key = (logits.shape[0], logits.shape[2], logits.shape[3])
+        B, H, W = logits.shape[0], logits.shape[2], logits.shape[3]
+        self._plan_key = (B, H, W)
         self.G(logits).copy_(dlogits)
-        self.backward(logits)
+        st = self._ab_graphs.get((B, H, W)) if self._ab_graphable() else None
+        if st is None or "fwd" not in st:
+            self.backward(logits)
+        elif "bwd" not in st:
+            torch.cuda.current_stream().synchronize()
+            st["bwd"] = self._ab_capture(lambda: self.backward(logits))
+            st["bwd"].replay()
+        else:
+            st["bwd"].replay()
 
     def train_step(self, x, labels, *, w_dice=0.5, w_ce=0.5, w_boundary=0.0, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
                    weight_decay=1e-4, optimize=True):

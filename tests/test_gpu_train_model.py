@@ -160,6 +160,19 @@ def test_autograd_boundary_matches_fused_step():
     p1 = torch.cat([p.detach().flatten() for p in m.parameters()])
     p2 = torch.cat([eng2.P[n].flatten() for n, _ in m2.named_parameters()])
     assert (p1 - p2).abs().max().item() < 2.1e-4                           # one AdamW step moves each weight by <= lr
+    # iterations 2..4 of the reference loop: the second call captures forward / backward as CUDA graphs, later ones replay
+    for it in range(3):
+        loss = O.criterion_dice_ce(m(x.to(DEV)), labels.to(DEV), 4)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        out2 = eng2.train_step(x.to(DEV), labels.to(DEV), lr=1e-4, weight_decay=1e-4)
+        assert abs(loss.item() - out2[0].item()) < 5e-3 * max(1.0, abs(out2[0].item())), (it, loss.item(), out2[0].item())
+    st = m.train_engine(DEV)._ab_graphs[(2, 224, 224)]
+    assert "fwd" in st and "bwd" in st                                     # the graph path really ran
+    p1 = torch.cat([p.detach().flatten() for p in m.parameters()])
+    p2 = torch.cat([eng2.P[n].flatten() for n, _ in m2.named_parameters()])
+    assert (p1 - p2).abs().max().item() < 8.1e-4
     # eval after training uses the updated weights and running statistics through the inference engine
     m.eval()
     with torch.no_grad():
