@@ -71,6 +71,31 @@ __device__ __forceinline__ void load_tile(bf16* __restrict__ sm, const bf16* __r
   }
 }
 
+// The same tile in two steps: fetch this thread's 16-byte chunks into registers (loads stay in flight while the previous
+// tile is being computed), later store them into the shared tile.  ROWS * D / 8 must be a multiple of FT.
+template <int D, int ROWS>
+struct TileRegs { uint4 u[ROWS * (D / 8) / FT]; };
+template <int D, int ROWS>
+__device__ __forceinline__ void fetch_tile(TileRegs<D, ROWS>& t, const bf16* __restrict__ base, long long ld, int row0, int nrows, int tid) {
+  constexpr int CH = D / 8;
+  static_assert((ROWS * CH) % FT == 0, "tile chunks must divide evenly over the CTA");
+#pragma unroll
+  for (int k = 0; k < ROWS * CH / FT; k++) {
+    const int i = tid + k * FT, r = i / CH, c = (i - r * CH) * 8;
+    t.u[k] = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows) t.u[k] = *reinterpret_cast<const uint4*>(base + (long long)(row0 + r) * ld + c);
+  }
+}
+template <int D, int ROWS>
+__device__ __forceinline__ void store_tile(bf16* __restrict__ sm, const TileRegs<D, ROWS>& t, int tid) {
+  constexpr int CH = D / 8, P = D + 8;
+#pragma unroll
+  for (int k = 0; k < ROWS * CH / FT; k++) {
+    const int i = tid + k * FT, r = i / CH, c = (i - r * CH) * 8;
+    *reinterpret_cast<uint4*>(sm + r * P + c) = t.u[k];
+  }
+}
+
 // acc[j] (16 x 8 tiles over 64 "n" rows of the smem tile) += A(16 x D) * tile^T, tile stored [n][D]
 template <int D>
 __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&af)[(D + 15) / 16][4], const bf16* sm, int lane) {
@@ -166,11 +191,31 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
   for (int j = 0; j < DV / 8; j++)
 #pragma unroll
     for (int e = 0; e < 4; e++) o[j][e] = 0.f;
+  // head dims >= 32: the next key / value tile is prefetched into registers while this one is computed (see fetch_tile);
+  // small head dims keep the plain load (their register budget buys occupancy instead)
+  constexpr bool PREF = DQK >= 32;
+  TileRegs<DQK, KT * BKEY> rk;
+  TileRegs<DV, KT * BKEY> rv;
+  if constexpr (PREF) {
+    fetch_tile<DQK, KT * BKEY>(rk, Kp, p.ldk, 0, p.Nk, tid);
+    fetch_tile<DV, KT * BKEY>(rv, Vp, p.ldv, 0, p.Nk, tid);
+  }
   for (int kt0 = 0; kt0 < p.Nk; kt0 += KT * BKEY) {
     __syncthreads();
-    load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
-    load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
+    if constexpr (PREF) {
+      store_tile<DQK, KT * BKEY>(sKb, rk, tid);
+      store_tile<DV, KT * BKEY>(sVb, rv, tid);
+    } else {
+      load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
+      load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
+    }
     __syncthreads();
+    if constexpr (PREF) {
+      if (kt0 + KT * BKEY < p.Nk) {
+        fetch_tile<DQK, KT * BKEY>(rk, Kp, p.ldk, kt0 + KT * BKEY, p.Nk, tid);
+        fetch_tile<DV, KT * BKEY>(rv, Vp, p.ldv, kt0 + KT * BKEY, p.Nk, tid);
+      }
+    }
    for (int sb = 0; sb < KT; sb++) {
     const int k0 = kt0 + sb * BKEY;
     if (k0 >= p.Nk) break;
@@ -292,11 +337,31 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
   for (int j = 0; j < DQK / 8; j++)
 #pragma unroll
     for (int e = 0; e < 4; e++) dq[j][e] = 0.f;
+  // head dims >= 32: the next key / value tile is prefetched into registers while this one is computed (see fetch_tile);
+  // small head dims keep the plain load (their register budget buys occupancy instead)
+  constexpr bool PREF = DQK >= 32;
+  TileRegs<DQK, KT * BKEY> rk;
+  TileRegs<DV, KT * BKEY> rv;
+  if constexpr (PREF) {
+    fetch_tile<DQK, KT * BKEY>(rk, Kp, p.ldk, 0, p.Nk, tid);
+    fetch_tile<DV, KT * BKEY>(rv, Vp, p.ldv, 0, p.Nk, tid);
+  }
   for (int kt0 = 0; kt0 < p.Nk; kt0 += KT * BKEY) {
     __syncthreads();
-    load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
-    load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
+    if constexpr (PREF) {
+      store_tile<DQK, KT * BKEY>(sKb, rk, tid);
+      store_tile<DV, KT * BKEY>(sVb, rv, tid);
+    } else {
+      load_tile<DQK, KT * BKEY>(sKb, Kp, p.ldk, kt0, p.Nk, tid);
+      load_tile<DV, KT * BKEY>(sVb, Vp, p.ldv, kt0, p.Nk, tid);
+    }
     __syncthreads();
+    if constexpr (PREF) {
+      if (kt0 + KT * BKEY < p.Nk) {
+        fetch_tile<DQK, KT * BKEY>(rk, Kp, p.ldk, kt0 + KT * BKEY, p.Nk, tid);
+        fetch_tile<DV, KT * BKEY>(rv, Vp, p.ldv, kt0 + KT * BKEY, p.Nk, tid);
+      }
+    }
    for (int sb = 0; sb < KT; sb++) {
     const int k0 = kt0 + sb * BKEY;
     if (k0 >= p.Nk) break;
@@ -374,15 +439,41 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
     for (int j = 0; j < (DO_DK ? DQK / 8 : 1); j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) dk[j][e] = 0.f;
-    for (int qt0 = 0; qt0 < p.Nq; qt0 += KT * BQ) {
+    // query tiles are prefetched into registers one round ahead: the global loads of round i+1 are in flight while round i
+    // is computed (ncu on the first version: 13 % issue utilisation, 8.5 long-scoreboard stalls per issued instruction)
+    constexpr int QR = KT * BQ;
+    static_assert(QR % FT == 0 || QR < FT, "per-row scalars: one or more rows per thread");
+    constexpr int SR = (QR + FT - 1) / FT;
+    TileRegs<DQK, QR> rq;
+    TileRegs<DV, QR> rg;
+    float rl[SR], rd[SR];
+    auto fetch = [&](int qt0) {
+      fetch_tile<DQK, QR>(rq, Qp, p.ldq, qt0, p.Nq, tid);
+      fetch_tile<DV, QR>(rg, dOp, p.ldo, qt0, p.Nq, tid);
+#pragma unroll
+      for (int k = 0; k < SR; k++) {
+        const int i = tid + k * FT;
+        const bool in = i < QR && qt0 + i < p.Nq;
+        rl[k] = in ? lsep[qt0 + i] : INFINITY;
+        rd[k] = in ? dlp[qt0 + i] : 0.f;
+      }
+    };
+    constexpr bool PREF = DQK >= 32;                      // small head dims: plain load (registers buy occupancy there)
+    if constexpr (PREF) fetch(0);
+    for (int qt0 = 0; qt0 < p.Nq; qt0 += QR) {
       __syncthreads();
-      load_tile<DQK, KT * BQ>(sQb, Qp, p.ldq, qt0, p.Nq, tid);
-      load_tile<DV, KT * BQ>(sGb, dOp, p.ldo, qt0, p.Nq, tid);
-      for (int i = tid; i < KT * BQ; i += FT) {
-        sLb[i] = qt0 + i < p.Nq ? lsep[qt0 + i] : INFINITY;
-        sDb[i] = qt0 + i < p.Nq ? dlp[qt0 + i] : 0.f;
+      if constexpr (!PREF) fetch(qt0);
+      store_tile<DQK, QR>(sQb, rq, tid);
+      store_tile<DV, QR>(sGb, rg, tid);
+#pragma unroll
+      for (int k = 0; k < SR; k++) {
+        const int i = tid + k * FT;
+        if (i < QR) { sLb[i] = rl[k]; sDb[i] = rd[k]; }
       }
       __syncthreads();
+      if constexpr (PREF) {
+        if (qt0 + QR < p.Nq) fetch(qt0 + QR);
+      }
      for (int sb = 0; sb < KT; sb++) {
       if (qt0 + sb * BQ >= p.Nq) break;
       const bf16* sQ = sQb + sb * BQ * (DQK + 8);

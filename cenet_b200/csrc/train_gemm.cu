@@ -194,6 +194,20 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
   dw[(size_t)n * K + ci * T + tt] = s;
 }
 
+// T == 1 (plain GEMM weights, no tap permutation), N*K % 4 == 0: four outputs per thread with 16-byte loads / stores
+__global__ void __launch_bounds__(256) wgrad_finalize4_kernel(const float4* __restrict__ ws, int S, long long nk4, float4* dw) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk4) return;
+  float4 s = ws[i];
+#pragma unroll 4
+  for (int z = 1; z < S; z++) {
+    const float4 v = ws[(size_t)z * nk4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  dw[i] = s;
+}
+
 // column sums with optional per-row scale (bias gradients)
 template <typename T, int V>
 __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int C,
@@ -225,6 +239,14 @@ __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __
   }
 }
 }  // namespace
+
+static inline void launch_wgrad_finalize(const float* ws, int S, int N, int K, int T, float* dw, cudaStream_t s) {
+  const long long nk = (long long)N * K;
+  if (T == 1 && nk % 4 == 0 && ((((uintptr_t)ws | (uintptr_t)dw) & 15) == 0))
+    wgrad_finalize4_kernel<<<cdiv(nk / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(ws), S, nk / 4, reinterpret_cast<float4*>(dw));
+  else
+    wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, S, N, K, T, dw);
+}
 
 int launch_colsum(const void* x, int dtype, long long ld, long long rows, int C, const float* rs, int rs_div, float* out, float* ws,
                   long long ws_elems, cudaStream_t s) {
@@ -270,7 +292,7 @@ static int launch_wgrad_mma(WgParams p, int T, float* dw, long long ws_elems, cu
   CENET_REQUIRE(grid.y <= 65535, "wgrad: K too large");
   wgrad_mma_kernel<<<grid, WG_THREADS, 0, s>>>(p);
   CENET_LAUNCH_CHECK("wgrad_mma");
-  wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(p.ws, S, p.N, p.K, T, dw);
+  launch_wgrad_finalize(p.ws, S, p.N, p.K, T, dw, s);
   CENET_LAUNCH_CHECK("wgrad_finalize");
   return 0;
 }
@@ -286,7 +308,7 @@ extern "C" int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, con
     const int St = cenet_conv_wgrad_tc(dy, x, B, H, W, Cin, ksize, N, ws, ws_elems, to_stream(st));
     if (St == -1) return -1;
     if (St > 0) {
-      wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, to_stream(st)>>>(ws, St, N, ksize * ksize * Cin, ksize * ksize, dw);
+      launch_wgrad_finalize(ws, St, N, ksize * ksize * Cin, ksize * ksize, dw, to_stream(st));
       CENET_LAUNCH_CHECK("wgrad_finalize");
       return 0;
     }
@@ -335,7 +357,7 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
       const int St = cenet_wgrad_tc(dy, ldy, x, ldx, M, N, K, row_scale, rs_div, ws, ws_elems, s);
       if (St == -1) return -1;
       if (St > 0) {
-        wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, St, N, K, T, dw);
+        launch_wgrad_finalize(ws, St, N, K, T, dw, s);
         CENET_LAUNCH_CHECK("wgrad_finalize");
         return 0;
       }
@@ -348,7 +370,7 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
     p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
     return launch_wgrad_mma(p, T, dw, ws_elems, s);
   }
-  wgrad_finalize_kernel<<<cdiv(nk, 256), 256, 0, s>>>(ws, S, N, K, T, dw);
+  launch_wgrad_finalize(ws, S, N, K, T, dw, s);
   CENET_LAUNCH_CHECK("wgrad_finalize");
   return 0;
 }
