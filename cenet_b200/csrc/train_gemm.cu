@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __
 #pragma unroll
   for (int v = 0; v < V; v++) s1[v] = 0.f;
   if (c0 < C) {
+#pragma unroll 4                     // independent row loads in flight (these passes are bound by bytes in flight)
     for (long long r = r0 + rl; r < r1; r += nrl) {
       float xv[V];
       ldv<V>(x + r * ld + c0, xv);

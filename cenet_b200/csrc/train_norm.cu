@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const T* 
 #pragma unroll
   for (int v = 0; v < V; v++) s1[v] = s2[v] = 0.f;
   if (c0 < C) {
+#pragma unroll 4                     // independent row loads in flight (these passes are bound by bytes in flight)
     for (long long r = r0 + rl; r < r1; r += nrl) {
       float xv[V];
       ldv<V>(x + r * ld + c0, xv);
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const T* __
     rs[v] = (c0 + v < C) ? rstd[c0 + v] : 0.f;
   }
   if (c0 < C) {
+#pragma unroll 4                     // independent row loads in flight (these passes are bound by bytes in flight)
     for (long long r = r0 + rl; r < r1; r += nrl) {
       float g[V], av[V];
       ldv<V>(dy + r * ldy + c0, g);
