@@ -227,15 +227,20 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
 #pragma unroll
       for (int e = 0; e < 4; e++) s[j][e] = 0.f;
     mma_a_tileT<DQK>(s, qf, sK, lane);
+    // scores stay raw; the running max lives in the scaled (base-2) domain: one FMNMX + one FFMA + one EX2 + one FADD per score.
+    // Only a ragged last tile pays for the key mask (warp-uniform branch).
+    if (k0 + BKEY > p.Nk) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (k0 + j * 8 + 2 * t + (e & 1) >= p.Nk) s[j][e] = -INFINITY;
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int col = k0 + j * 8 + 2 * t + (e & 1);
-        s[j][e] = col < p.Nk ? s[j][e] * p.c : -INFINITY;
-        mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
-      }
+      for (int e = 0; e < 4; e++) mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
     float al[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const float mn = fmaxf(mi[h], mx[h]);
+      const float mn = fmaxf(mi[h], mx[h] * p.c);              // p.c > 0
       al[h] = ex2(mi[h] - mn);
       mi[h] = mn;
       li[h] *= al[h];
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
     for (int j = 0; j < 8; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        s[j][e] = ex2(s[j][e] - mi[e >> 1]);
+        s[j][e] = ex2(fmaf(s[j][e], p.c, -mi[e >> 1]));
         li[e >> 1] += s[j][e];
       }
 #pragma unroll
@@ -374,12 +379,13 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
       for (int e = 0; e < 4; e++) s[j][e] = dp[j][e] = 0.f;
     mma_a_tileT<DQK>(s, qf, sK, lane);
     mma_a_tileT<DV>(dp, gf, sV, lane);
+    const bool ragged = k0 + BKEY > p.Nk;                       // warp-uniform: only the last key tile masks
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const int col = k0 + j * 8 + 2 * t + (e & 1);
-        const float pr = col < p.Nk ? ex2(s[j][e] * p.c - lse[e >> 1]) : 0.f;
+        float pr = ex2(fmaf(s[j][e], p.c, -lse[e >> 1]));
+        if (ragged && k0 + j * 8 + 2 * t + (e & 1) >= p.Nk) pr = 0.f;
         s[j][e] = pr * (dp[j][e] - dl[e >> 1]);                    // dS (without the softmax scale)
       }
     uint32_t pf[4][4];
@@ -491,7 +497,7 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int qi = j * 8 + 2 * t + (e & 1);
-          st[j][e] = kvalid[e >> 1] ? ex2(st[j][e] * p.c - sL[qi]) : 0.f;      // P^T
+          st[j][e] = kvalid[e >> 1] ? ex2(fmaf(st[j][e], p.c, -sL[qi])) : 0.f;   // P^T
         }
       uint32_t pf[4][4];
       if constexpr (DO_DV) {
