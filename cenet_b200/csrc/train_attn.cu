@@ -379,13 +379,12 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
       for (int e = 0; e < 4; e++) s[j][e] = dp[j][e] = 0.f;
     mma_a_tileT<DQK>(s, qf, sK, lane);
     mma_a_tileT<DV>(dp, gf, sV, lane);
-    const bool ragged = k0 + BKEY > p.Nk;                       // warp-uniform: only the last key tile masks
 #pragma unroll
     for (int j = 0; j < 8; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        float pr = ex2(fmaf(s[j][e], p.c, -lse[e >> 1]));
-        if (ragged && k0 + j * 8 + 2 * t + (e & 1) >= p.Nk) pr = 0.f;
+        const int col = k0 + j * 8 + 2 * t + (e & 1);
+        const float pr = col < p.Nk ? ex2(s[j][e] * p.c - lse[e >> 1]) : 0.f;
         s[j][e] = pr * (dp[j][e] - dl[e >> 1]);                    // dS (without the softmax scale)
       }
     uint32_t pf[4][4];
@@ -497,7 +496,7 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int qi = j * 8 + 2 * t + (e & 1);
-          st[j][e] = kvalid[e >> 1] ? ex2(fmaf(st[j][e], p.c, -sL[qi])) : 0.f;   // P^T
+          st[j][e] = kvalid[e >> 1] ? ex2(st[j][e] * p.c - sL[qi]) : 0.f;      // P^T
         }
       uint32_t pf[4][4];
       if constexpr (DO_DV) {
