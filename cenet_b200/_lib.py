@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         # training extensions (zero == inference behaviour)
         ("a_mmajor", i32), ("rs_div", i32), ("post_row_scale", vp), ("post_rs_div", i32),
         ("k_scale", vp), ("k_scale_div", i32), ("k_scale_bs", ll),
+        ("split_ws", vp), ("split_ws_elems", ll),
     ]
 
 

@@ -106,6 +106,10 @@ struct TcParams {
   EpiParams epi;
   int epi_vec;       // every epilogue operand is 16-byte addressable -> smem-transposed, vectorised epilogue
   int epi_fast;      // 1: C = bf16(acc + bias); 2: C = bf16(acc + bias + res1)  (most Linear layers) -- compact code path
+  // split-K (plain GEMM only): blockIdx.z owns k-blocks [z * kb_per_split, +kb_per_split) and stores its raw fp32 accumulator
+  // tile into split_ws + z * M * N; splitk_reduce_kernel sums the slices in fixed order and applies bias / cast
+  int splits, kb_per_split;
+  float* split_ws;
 };
 
 constexpr int MAX_EPI_WARPS = 8;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
   const uint32_t wblk = (w_bytes + 1023u) & ~1023u;
-  const uint32_t wres_bytes = p.w_resident ? p.num_kb * wblk : 0;
+  const uint32_t wres_bytes = p.w_resident ? (p.splits > 1 ? p.kb_per_split : p.num_kb) * wblk : 0;   // k-blocks one CTA walks
   const uint32_t stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
   const uint32_t ring_base = sbase + wres_bytes;
   const uint32_t bar_base = ring_base + p.stages * stage_bytes;
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
   const uint32_t tmem_slot = wfull_bar + 8;
   const uint32_t slab_base = (tmem_slot + 4 + 15u) & ~15u;           // n_epi x 32 x 36 floats
   const int n0 = blockIdx.y * p.bn;
+  const int kb_begin = p.splits > 1 ? blockIdx.z * p.kb_per_split : 0;
+  const int kb_end = p.splits > 1 ? min(p.num_kb, kb_begin + p.kb_per_split) : p.num_kb;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -176,17 +182,17 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       if (p.w_resident) {
-        mbar_arrive_expect_tx(wfull_bar, p.num_kb * w_bytes);
-        for (int kb = 0; kb < p.num_kb; kb++) {
+        mbar_arrive_expect_tx(wfull_bar, (kb_end - kb_begin) * w_bytes);
+        for (int kb = kb_begin; kb < kb_end; kb++) {
           const int kcoord = p.conv ? (kb / p.cblks) * p.Cin + (kb % p.cblks) * p.bk : kb * p.bk;
-          tma_load_2d(sbase + kb * wblk, &tmW, wfull_bar, kcoord, n0);
+          tma_load_2d(sbase + (kb - kb_begin) * wblk, &tmW, wfull_bar, kcoord, n0);
         }
       }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
         int m0, img, h0, w0;
         tile_coords(tile, m0, img, h0, w0);
-        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
@@ -218,17 +224,17 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
         mbar_wait(tempty_bar + 8 * as, (use & 1) ^ 1);       // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
-        for (int kb = 0; kb < p.num_kb; kb++, it++) {
+        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = ring_base + s * stage_bytes;
-          const uint32_t sw = p.w_resident ? sbase + kb * wblk : sa + a_bytes;
+          const uint32_t sw = p.w_resident ? sbase + (kb - kb_begin) * wblk : sa + a_bytes;
           const uint64_t adesc = make_smem_desc(sa, sbo, layout_type), bdesc = make_smem_desc(sw, sbo, layout_type);
           for (int k = 0; k < p.bk / 16; k++) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte start-address field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, kb != kb_begin || k != 0);
           }
           umma_commit(empty_bar(s));                           // frees the ring slot when these MMAs retire
         }
@@ -288,7 +294,22 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
                           __uint_as_float(acc[4 * q + 3]));
         __syncwarp();
-        if (p.epi_fast) {
+        if (p.splits > 1) {
+          // split-K: raw fp32 partial tile -> split_ws[z][m][n]  (N % 8 == 0; bias / cast happen in the reduce kernel)
+          const int cg = (lane & 3) * 8;
+          const int n = nbase + cg;
+          if (n < nlim) {
+#pragma unroll
+            for (int itr = 0; itr < 4; itr++) {
+              long long m;
+              if (!row_index(quarter * 32 + itr * 8 + (lane >> 2), m)) continue;
+              const int rr = itr * 8 + (lane >> 2);
+              float* dst = p.split_ws + ((long long)blockIdx.z * p.M + m) * p.N + n;
+              *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+              *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+            }
+          }
+        } else if (p.epi_fast) {
           // C = bf16(acc + bias [+ res1]); N % 8 == 0, so an 8-column group is entirely inside or outside the tile
           const int cg = (lane & 3) * 8;
           const int n = nbase + cg;
@@ -458,6 +479,30 @@ bool cenet_gemm_tc_eligible(const cenet_gemm_args* a) {
   return true;
 }
 
+// out[m, n] = bf16( sum_z ws[z][m][n] + bias[n] ), slices added in z order (deterministic); 8 columns per thread
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, long long M, int N, const float* __restrict__ bias,
+                                                            bf16* __restrict__ C, long long ldc) {
+  pdl_prologue();
+  const int ng = N >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * ng) return;
+  const long long m = i / ng;
+  const int n = (int)(i % ng) * 8;
+  float v[8];
+  if (bias) ldv<8>(bias + n, v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = 0.f;
+  }
+  for (int z = 0; z < S; z++) {
+    float t[8];
+    ldv<8>(ws + ((long long)z * M + m) * N + n, t);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] += t[j];
+  }
+  stv<8>(C + m * ldc + n, v);
+}
+
 int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -497,6 +542,25 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   }
   const int n_tiles = cdiv(a->N, p.bn);
   CENET_REQUIRE(n_tiles <= 65535, "cenet_gemm_tc: too many N tiles");
+  // ---- split-K: few output tiles, long contraction, plain bias epilogue, workspace offered by the caller ----
+  p.splits = 1; p.kb_per_split = p.num_kb; p.split_ws = nullptr;
+  {
+    const long long ctas = (long long)p.num_m_tiles * n_tiles;
+    const bool plain_epi = a->c_dtype == CENET_BF16 && a->alpha == 1.0f && !a->row_scale && !a->post_row_scale && !a->bias_per_row &&
+                           a->act == CENET_ACT_NONE && !a->mul && !a->res1 && !a->res2 && a->N % 8 == 0 && a->ldc % 8 == 0 &&
+                           (((uintptr_t)a->C & 15) == 0) && (!a->bias || (((uintptr_t)a->bias & 15) == 0));
+    if (!a->conv && a->split_ws && (((uintptr_t)a->split_ws & 15) == 0) && plain_epi && ctas * 2 <= kNumSMs && p.num_kb >= 8) {
+      int want = (int)std::min<long long>(kNumSMs / ctas, p.num_kb / 4);            // >= 4 k-blocks (256 columns) per slice
+      const long long room = a->split_ws_elems / ((long long)a->M * a->N);
+      if (want > room) want = (int)room;
+      if (want >= 2) {
+        p.kb_per_split = cdiv(p.num_kb, want);
+        p.splits = cdiv(p.num_kb, p.kb_per_split);
+        p.split_ws = a->split_ws;
+      }
+    }
+  }
+  const int kb_cta = p.splits > 1 ? p.kb_per_split : p.num_kb;                      // k-blocks one CTA walks
   // ---- shared-memory plan (one persistent CTA per SM, <= ~200 KB) ----
   const int a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
   const int wblk = (w_bytes + 1023) & ~1023;
@@ -507,8 +571,8 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   p.n_epi = (ctas_per_sm == 1) ? 8 : 4;
   const int slab_bytes = p.n_epi * 32 * 36 * 4;
   const int budget = (ctas_per_sm == 1 ? 200 : 100) * 1024 - slab_bytes - 1024 - 256;
-  p.w_resident = (long long)p.num_kb * wblk <= (ctas_per_sm == 1 ? 96 : 56) * 1024 && p.num_m_tiles > 1;
-  const int wres = p.w_resident ? p.num_kb * wblk : 0;
+  p.w_resident = (long long)kb_cta * wblk <= (ctas_per_sm == 1 ? 96 : 56) * 1024 && p.num_m_tiles > 1;
+  const int wres = p.w_resident ? kb_cta * wblk : 0;
   const int stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
   int stages = (budget - wres) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -537,8 +601,13 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   int gx = kNumSMs * ctas_per_sm / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.num_m_tiles) gx = p.num_m_tiles;
-  dim3 grid(gx, n_tiles, 1);
+  dim3 grid(gx, n_tiles, p.splits);
   gemm_tc_kernel<<<grid, 64 + 32 * p.n_epi, smem, s>>>(tmA, tmW, p);
   CENET_LAUNCH_CHECK("gemm_tc");
+  if (p.splits > 1) {
+    const long long groups = (long long)a->M * (a->N / 8);
+    splitk_reduce_kernel<<<(unsigned)cdiv(groups, 256), 256, 0, s>>>(p.split_ws, p.splits, a->M, a->N, a->bias, (bf16*)a->C, a->ldc);
+    CENET_LAUNCH_CHECK("splitk_reduce");
+  }
   return 0;
 }

@@ -344,9 +344,13 @@ class Engine:
             self.taps[name] = t_nhwc.reshape(B, H, W, Cc).permute(0, 3, 1, 2).float().clone()
 
     # ------------------------------------------------------------------------------------------------ pieces
+    def _split_ws(self):
+        """fp32 scratch the GEMM may use to split a long contraction with few output tiles over more SMs (split-K)"""
+        return self.buf("ws.splitk", (1 << 22,), torch.float32) if self.T == torch.bfloat16 else None
+
     def _lin(self, x, wname, out, bias=True, **kw):
         return ops.linear(x, self.w[wname + ".w"], out, bias=self.w[wname + ".b"] if bias else None,
-                          impl=self.gemm_impl, **kw)
+                          impl=self.gemm_impl, split_ws=self._split_ws(), **kw)
 
     def _conv_im2col(self, x_nhwc, B, H, W, Cin, k, stride, pad, wname, out, key):
         Ho = (H + 2 * pad - k) // stride + 1
@@ -356,7 +360,7 @@ class Engine:
         col = self.buf(key + ".col", (B * Ho * Wo, Kp))
         ops.im2col(x_nhwc, col, B, H, W, Cin, k, stride, pad, Ho, Wo, Kp)
         ops.gemm(col, wmat, out, M=B * Ho * Wo, N=wmat.shape[0], K=Kp, lda=Kp, ldw=Kp, ldc=out.shape[-1],
-                 bias=self.w[wname + ".b"], impl=self.gemm_impl)
+                 bias=self.w[wname + ".b"], impl=self.gemm_impl, split_ws=self._split_ws())
         return Ho, Wo
 
     def _encoder(self, x_nhwc, B, H, W, Cin):

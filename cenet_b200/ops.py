@@ -53,7 +53,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          bias=None, bias_per_row=False, row_scale=None, alpha=1.0, act=ACT_NONE, slope=0.0, act_after_res=False,
          res1=None, ldr1=0, res1_cscale=None, res1_scale=1.0, res2=None, ldr2=0, mul=None, ldmul=0, mul_act=ACT_NONE,
          conv=None, batch=1, batch_inner=1, a_bs=(0, 0), w_bs=(0, 0), c_bs=(0, 0), w_nmajor=False, impl=GEMM_AUTO,
-         a_off=0, w_off=0, c_off=0, rs_div=1, post_rs=None, post_rs_div=1, a_mmajor=False, r1_off=0):
+         a_off=0, w_off=0, c_off=0, rs_div=1, post_rs=None, post_rs_div=1, a_mmajor=False, r1_off=0, split_ws=None):
     """C[M,N] = epilogue(A[M,K] W[N,K]^T); see cenet_gemm in include/cenet_b200.h.  *_off are element offsets."""
     g = GemmArgs()
     g.M, g.N, g.K = M, N, K
@@ -79,6 +79,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     if mul is not None:
         g.mul, g.mul_dtype, g.ldmul, g.mul_act = _p(mul), dt(mul), ldmul, mul_act
     g.impl = impl
+    if split_ws is not None:                                # fp32 scratch that lets the library split long contractions (split-K)
+        g.split_ws, g.split_ws_elems = _f32(split_ws, "split_ws"), split_ws.numel()
     g.a_mmajor, g.rs_div, g.post_row_scale, g.post_rs_div = int(a_mmajor), rs_div, _f32(post_rs, "post_rs"), post_rs_div
     L.call("cenet_gemm", C.byref(g), _stream())
     return out

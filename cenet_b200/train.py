@@ -431,6 +431,10 @@ class TrainEngine:
         """scratch for two-stage reductions (consumed inside the launching op, so one shared buffer is enough)"""
         return self.buf("ws.reduce", (max(n, 1 << 24),), torch.float32)
 
+    def _split_ws(self):
+        """fp32 scratch the forward GEMMs may use for split-K (few output tiles, long contraction: the SR convs)"""
+        return self.buf("ws.splitk", (1 << 22,), torch.float32) if self.T == torch.bfloat16 else None
+
     def _wws(self):
         """workspace of the weight-gradient kernels: their own buffer when they run on the side stream"""
         return self._ws(0) if self.side is None else self.buf("ws.wgrad", (1 << 24,), torch.float32)
@@ -460,7 +464,7 @@ class TrainEngine:
             bias = None
         ops.gemm(x, W, out, M=M, N=N, K=K, lda=lda, ldw=W.stride(0), ldc=ldc, bias=bias, a_off=a_off, c_off=c_off,
                  post_rs=drop, post_rs_div=drop_div, res1=res1, ldr1=res1.stride(0) if res1 is not None else 0,
-                 impl=self.gemm_impl)
+                 impl=self.gemm_impl, split_ws=self._split_ws())
         if res1 is not None:
             self.alias_grad(out, res1)
         if wgrads is None:
@@ -594,7 +598,8 @@ class TrainEngine:
         M = B * Ho * Wo
         col = self.buf(key + ".col", (M, Kp))
         ops.im2col(x, col, B, H, W, Cin, k, stride, pad, Ho, Wo, Kp)
-        ops.gemm(col, Wm, out, M=M, N=Cout, K=Kp, lda=Kp, ldw=Kp, ldc=Cout, bias=self.P[name + ".bias"], impl=self.gemm_impl)
+        ops.gemm(col, Wm, out, M=M, N=Cout, K=Kp, lda=Kp, ldw=Kp, ldc=Cout, bias=self.P[name + ".bias"], impl=self.gemm_impl,
+                 split_ws=self._split_ws())
 
         def bwd():
             dy = self.G(out)

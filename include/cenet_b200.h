@@ -69,6 +69,10 @@ typedef struct {
   int rs_div;                         /* row_scale index is m / rs_div (0 -> 1) */
   const float* post_row_scale; int post_rs_div; /* v *= post_row_scale[m / post_rs_div] after bias/act/mul, before the residuals */
   const float* k_scale; int k_scale_div; long long k_scale_bs; /* A[m,k] *= k_scale[(z*k_scale_bs + k) / k_scale_div]; CUDA-core path */
+  /* optional split-K workspace (fp32, caller-owned): problems with few output tiles and a long contraction (the
+   * spatial-reduction convs: M = B*49 patches, K = 4096) are split over blockIdx.z into k-slices whose fp32 partial tiles
+   * land here and are reduced (+ bias, cast) in fixed order by a second kernel.  NULL: never split. */
+  float* split_ws; long long split_ws_elems;
 } cenet_gemm_args;
 int cenet_gemm(const cenet_gemm_args* a, cenet_stream_t s);
 

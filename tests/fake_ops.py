@@ -57,7 +57,7 @@ def gemm(a, w, out, *, M, N, K, lda, ldw, ldc, bias=None, bias_per_row=False, ro
          slope=0.0, act_after_res=False, res1=None, ldr1=0, res1_cscale=None, res1_scale=1.0, res2=None, ldr2=0, mul=None,
          ldmul=0, mul_act=ACT_NONE, conv=None, batch=1, batch_inner=1, a_bs=(0, 0), w_bs=(0, 0), c_bs=(0, 0),
          w_nmajor=False, impl=GEMM_AUTO, a_off=0, w_off=0, c_off=0, rs_div=1, post_rs=None, post_rs_div=1,
-         a_mmajor=False, r1_off=0):
+         a_mmajor=False, r1_off=0, split_ws=None):
     _LAUNCHES[0] += 1
     af, wf, cf = _flat(a), _flat(w), _flat(out)
     for z in range(batch):

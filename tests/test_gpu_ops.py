@@ -212,6 +212,27 @@ def test_dwconv_variants(dtype):
     assert rel(y3, ref.permute(0, 2, 3, 1)) < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(3136, 64, 4096), (1176, 64, 4096), (1000, 128, 2048), (49, 320, 1280), (3136, 512, 2048)])
+def test_gemm_split_k(M, N, K):
+    """long contraction with few output tiles (the SR convs: M = B*49, K = 4096): k-slices over blockIdx.z, fp32 partials in the
+    caller's workspace, fixed-order reduce + bias.  Same result as the unsplit kernel up to fp32 summation order."""
+    from cenet_b200 import ops
+    a = torch.randn(M, K, generator=g(1)).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g(2)) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g(3))
+    ref = a.float() @ w.float().t() + bias
+    out0 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out1 = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    ws = torch.empty(1 << 22, device=DEV)
+    ops.linear(a.to(DEV), w.to(DEV), out0, bias=bias.to(DEV), impl=ops.GEMM_TCGEN05)
+    ops.linear(a.to(DEV), w.to(DEV), out1, bias=bias.to(DEV), impl=ops.GEMM_TCGEN05, split_ws=ws)
+    assert rel(out0, ref) < 6e-3 and rel(out1, ref) < 6e-3
+    assert rel(out1, out0) < 4e-3
+    out2 = torch.empty_like(out1)
+    ops.linear(a.to(DEV), w.to(DEV), out2, bias=bias.to(DEV), impl=ops.GEMM_TCGEN05, split_ws=ws)
+    assert torch.equal(out1, out2)                                   # deterministic
+
+
 @pytest.mark.parametrize("B,H,W,C,ldx,xo", [(3, 56, 56, 128, 128, 0), (2, 14, 14, 320, 320, 0), (1, 7, 7, 64, 64, 0),
                                             (2, 28, 30, 64, 192, 64), (1, 20, 130, 64, 64, 0)])
 def test_dwconv_staged_rows(B, H, W, C, ldx, xo):
