@@ -111,7 +111,7 @@ def test_conv_wgrad_implicit_im2col(Cin, N, k):
 
 
 @pytest.mark.parametrize("M,N,K,ldy,ldx,rsdiv", [(3 * 3136, 64, 512, 64, 512, 3136), (4 * 784, 1024, 128, 1024, 128, 784),
-                                                 (4704, 1280, 320, 1280, 320, 0), (75264, 64, 64, 192, 64, 0), (1176, 512, 2048, 512, 2048, 49 * 4),
+                                                 (4704, 1280, 320, 1280, 320, 0), (75264, 64, 64, 192, 64, 0), (1176, 512, 2048, 512, 2048, 49 * 4), (1176, 512, 2048, 512, 2048, 49), (1176, 512, 512, 512, 512, 49),
                                                  (5000, 320, 100, 328, 104, 0)])
 def test_gemm_wgrad_tcgen05(M, N, K, ldy, ldx, rsdiv):
     """shapes that take the tcgen05 MN-major kernel (bf16, aligned), with and without a per-sample row scale"""
