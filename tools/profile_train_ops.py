@@ -73,6 +73,12 @@ print(f"config {name} B={B} {prec}: eager step (events) {e0.elapsed_time(e1)/ste
       f"{sum(v[1] for v in agg.values())} op calls")
 for op, (ms, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print(f"{ms:8.3f} ms {100*ms/tot:5.1f}%  x{n:<4d} {op}")
+print("---- by region (eager op time, launches)")
+reg = {}
+for (op, tag), (ms, n) in fine.items():
+    a = reg.setdefault(tag, [0.0, 0]); a[0] += ms; a[1] += n
+for tag, (ms, n) in sorted(reg.items(), key=lambda kv: -kv[1][0]):
+    print(f"{ms:8.3f} ms {100*ms/tot:5.1f}%  x{n:<4d} {tag}")
 print("---- by (op, region), top 45")
 for (op, tag), (ms, n) in sorted(fine.items(), key=lambda kv: -kv[1][0])[:45]:
     print(f"{ms:8.3f} ms {100*ms/tot:5.1f}%  x{n:<4d} {op}@{tag}")
