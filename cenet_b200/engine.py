@@ -131,7 +131,9 @@ class Engine:
             v += t._version
         for t in self.mod.buffers():
             v += t._version
-        return (v, self.mod.training)
+        # raw-pointer writers (TrainEngine: AdamW on the flat parameter buffer, BatchNorm running statistics) do not bump
+        # `_version`; they bump this generation counter on the module instead
+        return (v, self.mod.training, getattr(self.mod, "_cenet_weights_gen", 0))
 
     def _sd(self):
         return {k: v.detach().to(self.dev, torch.float32) for k, v in self.mod.state_dict().items()}
@@ -655,7 +657,7 @@ class Engine:
                    else torch.empty((B, ncls, H, W), device=self.dev, dtype=torch.float32))
         res = self.buf("res.labels" if labels else "res.logits", out.shape, out.dtype)
         args = (x_in, B, H, W, None if labels else res, res if labels else None)
-        if not self.use_graph or self.taps is not None:
+        if not self.use_graph or self.taps is not None or torch.jit.is_tracing():
             self._run(*args)
         else:
             g = self._graphs.get(key)

@@ -344,6 +344,13 @@ class CENet(nn.Module):
         d["_engines"] = {}
         return d
 
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel (main_acdc.py:177-178, a dead branch in the scripts: `--n_gpu` is never passed) shallow-copies the
+        # module per device and per iteration; the launch plans cache packed weights / CUDA graphs per module instance and
+        # the replicas' tensors are not leaf Parameters, so results would silently be computed with stale weights.
+        raise RuntimeError("cenet_b200.CENet does not support nn.DataParallel replicas: run one process per GPU "
+                           "(torchrun) and attach cenet_b200.replicas.GradSync(net.train_engine()) -- see INTEGRATION.md")
+
     def _engine(self, x, precision=None):
         from ..engine import Engine
         key = (x.device, precision or Engine.default_precision())

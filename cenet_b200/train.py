@@ -213,7 +213,7 @@ class TrainEngine:
         self.step_count = 0
         self.zero32 = torch.zeros(32, device=self.dev, dtype=torch.float32)
         probs = self.mod.backbone.drop_path_probs
-        self.dp_keep = (1.0 - torch.tensor(probs, dtype=torch.float32).view(len(probs), 1)).to(self.dev)
+        self.dp_keep = (1.0 - torch.tensor(probs, dtype=torch.float32).repeat_interleave(2).view(2 * len(probs), 1)).to(self.dev)
         # optimizer hyper-parameters live on the device so that a captured step can be replayed with a new lr:
         # [lr, beta1, beta2, eps, weight_decay, step]
         self.hyper = torch.zeros(8, device=self.dev, dtype=torch.float32)
@@ -700,9 +700,9 @@ class TrainEngine:
             for i in range(_PVT["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 kb = f"enc{s}.b{i}"
-                drop = None
-                if self.drop_path and self.mod.backbone.drop_path_probs[dp_i] > 0:
-                    drop = self.dp_scale[dp_i]
+                drop = drop2 = None                                          # two independent draws per block:
+                if self.drop_path and self.mod.backbone.drop_path_probs[dp_i] > 0:   # attention and MLP branch (pvtv2.py:146-147)
+                    drop, drop2 = self.dp_scale[2 * dp_i], self.dp_scale[2 * dp_i + 1]
                 dp_i += 1
                 xn = self.ln(t, b + ".norm1", self.buf(kb + ".xn1", (Mtok, Cc)), 1e-6)
                 q = self.lin(xn, b + ".attn.q", self.buf(kb + ".q", (Mtok, Cc)))
@@ -724,7 +724,7 @@ class TrainEngine:
                 h2 = self.buf(kb + ".h2", (Mtok, hid))
                 self.dwconv(h1, h2, b + ".mlp.dwconv.dwconv", B, H, W, hid, bias=P[b + ".mlp.dwconv.dwconv.bias"], act=ACT_GELU,
                             zout=z)
-                t = self.lin(h2, b + ".mlp.fc2", self.buf(kb + ".t2", (Mtok, Cc)), res1=t1, drop=drop, drop_div=H * W, dmul=z)
+                t = self.lin(h2, b + ".mlp.fc2", self.buf(kb + ".t2", (Mtok, Cc)), res1=t1, drop=drop2, drop_div=H * W, dmul=z)
             f = self.ln(t, f"backbone.norm{s+1}", self.buf(f"enc{s}.out", (Mtok, Cc)), 1e-6)
             self._tap(f"backbone.stage{s+1}", f, B, H, W, Cc)
             feats.append((f, H, W, Cc))
@@ -1163,7 +1163,7 @@ class TrainEngine:
 
     def _sample_drop_path(self, B):
         probs = self.mod.backbone.drop_path_probs
-        n = len(probs)
+        n = 2 * len(probs)                                          # rows 2i / 2i+1: attention / MLP branch of block i
         ds = self.buf("dp_scale", (n, B), torch.float32)
         if self.drop_path:
             keep = self.dp_keep
@@ -1171,6 +1171,11 @@ class TrainEngine:
             rnd.uniform_()
             ds.copy_((rnd < keep).float() / keep)                   # timm DropPath: bernoulli(keep) / keep per sample
         self.dp_scale = ds
+
+    def _touch_weights(self):
+        """tell eval-mode engines of the same module that parameters / BatchNorm statistics were rewritten through raw
+        pointers (no `_version` bump): Engine._weights_version() reads this counter and re-packs"""
+        self.mod._cenet_weights_gen = getattr(self.mod, "_cenet_weights_gen", 0) + 1
 
     def forward(self, x_in, B, H, W, logits):
         self._begin(B, H, W)
@@ -1221,7 +1226,24 @@ class TrainEngine:
         if self.grad_hook is not None:
             self.grad_hook(self.gflat)
         if optimize:
-            tops.adamw(self.pflat, self.gflat, self.adam_m, self.adam_v, self.n_flat, self.hyper)
+            for lo, hi in self._trainable_ranges():
+                tops.adamw(self.pflat[lo:hi], self.gflat[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], hi - lo, self.hyper)
+
+    def _trainable_ranges(self):
+        """contiguous [lo, hi) ranges of the flat parameter buffer whose parameters have requires_grad=True: a frozen
+        backbone (`freeze_bb=True`, encoder.py:82-84) is neither updated nor weight-decayed, as with torch.optim over
+        `filter(requires_grad)`; all-trainable == one range == one AdamW launch"""
+        out = []
+        for n, p in sorted(self.mod.named_parameters(), key=lambda np_: self.param_offsets[np_[0]]):
+            if not p.requires_grad:
+                continue
+            lo = self.param_offsets[n]
+            hi = lo + _rup(p.numel(), 4)
+            if out and out[-1][1] == lo:
+                out[-1][1] = hi
+            else:
+                out.append([lo, hi])
+        return [(a, min(b, self.n_flat)) for a, b in out]
 
     grad_hook = None
 
@@ -1328,6 +1350,7 @@ class TrainEngine:
             self.tape, self._written, self._galias = st["tape"], st["written"], st["galias"]
             st["fwd"].replay()
         self._last_logits = logits
+        self._touch_weights()                                       # BatchNorm running statistics moved
         return logits
 
     def backward_from(self, dlogits):
@@ -1339,6 +1362,8 @@ class TrainEngine:
         st = self._ab_graphs.get((B, H, W)) if self._ab_graphable() else None
         if st is None or "fwd" not in st:
             self.backward(logits)
+            if self.grad_hook is not None:                          # replicas.GradSync.finish: wait for the bucket all-reduces
+                self.grad_hook(self.gflat)
         elif "bwd" not in st:
             torch.cuda.current_stream().synchronize()
             st["bwd"] = self._ab_capture(lambda: self.backward(logits))
@@ -1367,7 +1392,9 @@ class TrainEngine:
         hp = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, float(self.step_count), 0.0, 0.0], dtype=torch.float32)
         self.hyper.copy_(hp if self.dev.type != "cuda" else hp.pin_memory(), non_blocking=True)
         args = (x_in, lab, B, H, W, ncls, loss_out, w_dice, w_ce, lr, betas, eps, weight_decay, optimize, w_boundary)
-        key = (B, H, W, optimize, w_dice, w_ce, w_boundary)
+        # hooks are part of the key: a step captured before replicas.GradSync was attached must not be replayed after
+        key = (B, H, W, optimize, w_dice, w_ce, w_boundary, self.on_bucket is not None, self.grad_hook is not None)
+        self._touch_weights()                                         # AdamW / BatchNorm statistics write raw pointers
         if not self.use_graph or self.taps is not None or self.dev.type != "cuda":
             self._step_body(*args)
             return loss_out

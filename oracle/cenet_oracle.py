@@ -50,9 +50,22 @@ def lambda_init(depth: int) -> float:
 
 
 # ------------------------------------------------------------------------------------------------ norms
-def _bn(sd, p, x, training=False, eps=1e-5):
-    """nn.BatchNorm{1,2}d forward (A13): eval -> running stats; train -> biased batch stats."""
+_STATS_SINK = None        # dict while cenet_forward(..., new_stats=dict) runs in train mode
+
+
+def _bn(sd, p, x, training=False, eps=1e-5, momentum=0.1):
+    """nn.BatchNorm{1,2}d forward (A13): eval -> running stats; train -> biased batch stats, and the running statistics the
+    module would hold afterwards (momentum 0.1, UNBIASED batch variance, num_batches_tracked + 1) go to the stats sink."""
     if training:
+        if _STATS_SINK is not None:
+            with torch.no_grad():
+                dims = [d for d in range(x.dim()) if d != 1]
+                n = x.numel() // x.shape[1]
+                mean = x.mean(dims)
+                var_u = x.var(dims, unbiased=False) * (n / max(n - 1, 1))
+                _STATS_SINK[p + ".running_mean"] = (1 - momentum) * sd[p + ".running_mean"] + momentum * mean
+                _STATS_SINK[p + ".running_var"] = (1 - momentum) * sd[p + ".running_var"] + momentum * var_u
+                _STATS_SINK[p + ".num_batches_tracked"] = sd[p + ".num_batches_tracked"] + 1
         return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, eps)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         False, 0.0, eps)
@@ -340,7 +353,18 @@ def out_head(sd, cfg: Cfg, dec, x, training=False, taps=None):
     return F.interpolate(y, scale_factor=2, mode="bilinear")
 
 
-def cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None):
+def cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None,
+                  new_stats: Optional[dict] = None):
+    """new_stats: dict that receives the BatchNorm buffers after one train-mode forward (only with training=True)"""
+    global _STATS_SINK
+    _STATS_SINK = new_stats if training else None
+    try:
+        return _cenet_forward(sd, cfg, x, training, taps)
+    finally:
+        _STATS_SINK = None
+
+
+def _cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None):
     """net.py:53-64.  x: [B,Cin,H,W] fp32 -> logits [B,ncls,H,W]."""
     y = torch.cat([x, x, x], 1) if x.shape[1] == 1 else x
     x1, x2, x3, x4 = encoder(sd, cfg, y, taps)

@@ -154,7 +154,84 @@ def loss_fixture():
     print("boundary loss:", {k: round(v["loss"].item(), 6) for k, v in outb.items()})
 
 
+TRAIN_GRAD_KEYS = [       # >= 1 tensor from every module family; full gradient norms of all 630 parameters are stored too
+    "backbone.patch_embed1.proj.weight", "backbone.patch_embed3.norm.weight", "backbone.block1.0.attn.q.weight",
+    "backbone.block1.0.attn.sr.weight", "backbone.block1.1.attn.norm.bias", "backbone.block2.1.mlp.dwconv.dwconv.weight",
+    "backbone.block2.3.attn.kv.weight", "backbone.block3.2.mlp.fc1.weight", "backbone.block3.5.attn.proj.bias",
+    "backbone.block4.0.attn.kv.bias", "backbone.block4.2.mlp.fc2.weight", "backbone.norm4.weight",
+    "decoder.dec4.layer_scale_1", "decoder.dec4.mca.ccu.fc1.weight", "decoder.dec4.mca.ccu.bn.weight",
+    "decoder.dec3.mca.gate.weight", "decoder.dec3.mca.value.dlps.1.depthwise.weight", "decoder.dec3.mca.value.dlps.1.pointwise_bn.bias",
+    "decoder.dec2.mca.value.dlps.3.1.weight", "decoder.dec2.mca.value.PW_conv.weight", "decoder.dec2.mca.proj_2.bias",
+    "decoder.dec1.mca.denoising_module.w", "decoder.dec1.mca.denoising_module.conv_theta.weight",
+    "decoder.dec1.mca.denoising_module.bn.weight", "decoder.dec1.norm2.weight", "decoder.dec1.mlp.dwconv.weight",
+    "decoder.dec1.mlp.srm.pwc.weight", "decoder.dec1.mlp.srm.dwc.weight", "decoder.dec1.mlp.srm.bn.bias", "decoder.dec1.layer_scale_2",
+    "decoder.up3.up_dwc.1.weight", "decoder.up2.up_dwc.2.weight", "decoder.up1.pwc.0.bias",
+    "decoder.skip_enhancer1.boundary.w", "decoder.skip_enhancer1.diffattn.lambda_q1", "decoder.skip_enhancer1.diffattn.lambda_k2",
+    "decoder.skip_enhancer1.diffattn.v_proj.weight", "decoder.skip_enhancer2.diffattn.q_proj.weight",
+    "decoder.skip_enhancer3.diffattn.out_proj.weight", "decoder.skip_enhancer2.mixer.weight",
+    "out.w", "out.rb.0.conv1.conv.weight", "out.rb.0.conv2.conv.weight", "out.rb.0.conv3.conv.weight", "out.rb.0.norm3.weight",
+    "out.up.up.1.weight", "out.up.up.2.bias", "out.out.0.conv1.conv.weight", "out.out.0.norm2.weight",
+    "out.out.1.conv.conv.weight", "out.out.1.conv.conv.bias",
+]
+
+
+def _sample(t, n=2048):
+    f = t.detach().flatten()
+    return f[:: max(1, f.numel() // n)][:n].clone()
+
+
+def train_fixture(nets, name, batch, size):
+    """The reference in train() mode (batch-statistics BatchNorm with running-stat updates, the CCU `B > 1` guard, DropPath
+    with drop_prob forced to 0), one forward + `Criterion('dice,ce', 0.5/0.5)` (the reference's own utils/core.py class) +
+    backward: loss, strided logits, gradients (norm of all 630, samples of TRAIN_GRAD_KEYS) and every BatchNorm buffer
+    after the step.  Pins oracle.cenet_forward(training=True) + autograd, which every gradient test compares against."""
+    import importlib.util
+    import types
+    ref, sd, kw = build_pair(nets, name)
+    ref.train()
+    n_dp = 0
+    for m in ref.modules():
+        if type(m).__name__ == "DropPath":
+            m.drop_prob = 0.0
+            n_dp += 1
+    if size != 224:                                            # dseb.py:117 recovers H from a constructor constant
+        for lvl, div in ((3, 16), (2, 8), (1, 4)):
+            getattr(ref.decoder, f"skip_enhancer{lvl}").input_size = size // div
+    pkg = types.ModuleType("refutils")
+    pkg.__path__ = []
+    stub = types.ModuleType("refutils.utils")
+    stub.flatten = None
+    sys.modules["refutils"], sys.modules["refutils.utils"] = pkg, stub
+    spec = importlib.util.spec_from_file_location("refutils.core", "/root/reference/src/utils/core.py")
+    core = importlib.util.module_from_spec(spec)
+    sys.modules["refutils.core"] = core
+    spec.loader.exec_module(core)
+    x = fixtures.synth_input(name, batch, size=size)
+    labels = torch.randint(0, kw["num_classes"], (batch, size, size), generator=torch.Generator().manual_seed(5))
+    crit = core.Criterion(kw["num_classes"], types.SimpleNamespace(loss_type="dice,ce", loss_weights="0.5,0.5"))
+    y = ref(x)
+    loss = crit(y, labels.float())
+    loss.backward()
+    grads = {n: p.grad for n, p in ref.named_parameters()}
+    after = ref.state_dict()
+    out = dict(config=name, batch=batch, size=size, seed=1234, input_seed=0, label_seed=5, drop_path_modules=n_dp,
+               loss=loss.detach().clone(), logits_strided=y.detach()[:, :, ::4, ::4].clone(),
+               logits_std=y.std().item(),
+               grad_norms={n: (g.norm().item() if g is not None else None) for n, g in grads.items()},
+               grad_samples={n: _sample(grads[n]) for n in TRAIN_GRAD_KEYS if grads.get(n) is not None},
+               buffers_after={k: v.clone() for k, v in after.items() if "running_" in k or k.endswith("num_batches_tracked")})
+    torch.save(out, os.path.join(HERE, f"train_{name}_b{batch}_s{size}.pt"))
+    none = [n for n, g in grads.items() if g is None]
+    print("train", name, batch, size, "loss", loss.item(), "params without grad:", none)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":         # only the train-mode fixtures
+        nets = ref_shim.import_reference()
+        train_fixture(nets, "acdc", 2, 224)
+        train_fixture(nets, "synapse", 2, 96)
+        train_fixture(nets, "acdc", 1, 64)                   # B = 1 in train mode: CCU skips BatchNorm1d (cfam.py:260)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "loss":          # only the loss fixtures (no model import needed)
         loss_fixture()
         sys.exit(0)
@@ -164,3 +241,6 @@ if __name__ == "__main__":
     model_fixture(nets, "acdc", 1)
     model_fixture(nets, "synapse", 2)
     model_fixture(nets, "skin", 1)
+    train_fixture(nets, "acdc", 2, 224)
+    train_fixture(nets, "synapse", 2, 96)
+    train_fixture(nets, "acdc", 1, 64)

@@ -223,3 +223,49 @@ def test_boundary_criterion_fused_step_and_dropin_module(monkeypatch):
     g_fused = torch.cat([fused[eng.param_offsets[n]:eng.param_offsets[n] + p.numel()]
                          for n, p in sorted(m.named_parameters(), key=lambda np_: eng.param_offsets[np_[0]])])
     assert ((g_auto - g_fused).norm() / g_fused.norm()).item() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- pinned to the REAL reference
+@pytest.mark.parametrize("fx", ["train_acdc_b2_s224", "train_synapse_b2_s96", "train_acdc_b1_s64"])
+def test_train_step_fp32_matches_reference_train_mode_golden(fx):
+    """One fp32 step on the B200 vs tests/golden/train_*.pt = the reference module itself in train() mode with its own
+    Criterion('dice,ce'): loss, logits, the norm of all 630 gradients, sampled gradients across every module family, and
+    every BatchNorm running_mean / running_var / num_batches_tracked after the step (incl. the CCU B>1 guard at B=1)."""
+    from test_oracle_golden import check_train_against_golden, rebuild_train_case
+    from conftest import GOLDEN
+    g = torch.load(os.path.join(GOLDEN, fx + ".pt"), weights_only=False)
+    sd, kw, x, labels = rebuild_train_case(g)
+    m, eng = _engine(g["config"], "fp32", sd)
+    eng.use_graph = False
+    out = eng.train_step(x.to(DEV), labels.to(DEV), optimize=False)
+    torch.cuda.synchronize()
+    logits = eng.buf("logits", (g["batch"], kw["num_classes"], g["size"], g["size"]), torch.float32).cpu()
+    grads = {k: v.cpu() for k, v in eng.GP.items()}
+    buffers = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    check_train_against_golden(g, out[0].item(), logits, grads, buffers, 1e-4, fx)
+
+
+def test_eval_after_fused_steps_uses_new_weights():
+    """TrainEngine.train_step rewrites parameters and BatchNorm statistics through raw pointers (no tensor
+    `_version` bump).  An eval forward that already packed its weights must re-pack after it: eval -> N fused steps -> eval
+    equals a freshly built module holding the trained state_dict."""
+    from cenet_b200.networks import CENet
+    kw, sd, x, labels, *_ = _ref("acdc", 2, 224)
+    m, eng = _engine("acdc", "bf16", sd)
+    xd, ld = x.to(DEV), labels.to(DEV)
+    m.eval()
+    with torch.no_grad():
+        y0 = m(xd).clone()                                        # packs the inference weights + captures the graph
+    m.train()
+    for _ in range(3):
+        eng.train_step(xd, ld, lr=1e-3)
+    m.eval()
+    with torch.no_grad():
+        y1 = m(xd).clone()
+    fresh = CENet(**kw)
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    fresh = fresh.to(DEV).eval()
+    with torch.no_grad():
+        y2 = fresh(xd)
+    assert (y1 - y0).abs().max().item() > 1e-3                    # training moved the output ...
+    assert torch.equal(y1, y2)                                    # ... and the cached engine followed it exactly

@@ -123,3 +123,75 @@ def test_whole_model(name, batch):
         v = taps[k]
         samp = v.flatten()[:: max(1, v.numel() // 512)][:512]
         torch.testing.assert_close(samp, ref["sample"], rtol=1e-4, atol=1e-5, msg=lambda m, k=k: f"tap {k}: {m}")
+
+
+# ---------------------------------------------------------------------------------------------- train mode
+def _train_golden(fx):
+    return torch.load(os.path.join(GOLDEN, fx + ".pt"), weights_only=False)
+
+
+def rebuild_train_case(g):
+    """state dict / input / labels of a tests/golden/train_*.pt fixture (same recipe as make_golden.train_fixture)"""
+    from cenet_b200.networks import CENet
+    kw = fixtures.CONFIGS[g["config"]]
+    torch.manual_seed(g["seed"])
+    sd = fixtures.perturb_state(CENet(**kw).state_dict(), g["seed"])
+    x = fixtures.synth_input(g["config"], g["batch"], size=g["size"], seed=g["input_seed"])
+    labels = torch.randint(0, kw["num_classes"], (g["batch"], g["size"], g["size"]),
+                           generator=torch.Generator().manual_seed(g["label_seed"]))
+    return sd, kw, x, labels
+
+
+def check_train_against_golden(g, loss, logits, grads, buffers, rtol, what):
+    """shared by the CPU oracle test below and the GPU test (tests/test_gpu_train_model.py): loss, strided logits, the norm
+    of EVERY parameter gradient, sampled gradients of 51 tensors across all module families, and every BatchNorm buffer
+    (running_mean / running_var / num_batches_tracked) after one train-mode step, against the REAL reference."""
+    assert abs(float(loss) - float(g["loss"])) < rtol * max(1.0, abs(float(g["loss"]))), (what, float(loss), float(g["loss"]))
+    ls = logits[:, :, ::4, ::4]
+    e = ((ls - g["logits_strided"]).norm() / g["logits_strided"].norm()).item()
+    assert e < rtol, (what, "logits", e)
+    bad = []
+    gmax = max(v for v in g["grad_norms"].values() if v is not None)
+    for n, ref_norm in g["grad_norms"].items():
+        if ref_norm is None:
+            continue
+        mine = grads[n].float().norm().item()
+        if abs(mine - ref_norm) > rtol * 20 * max(ref_norm, 1e-4 * gmax):
+            bad.append((n, mine, ref_norm))
+    assert not bad, (what, "grad norms", bad[:8], len(bad))
+    for n, ref_s in g["grad_samples"].items():
+        f = grads[n].float().flatten().cpu()
+        mine = f[:: max(1, f.numel() // 2048)][:2048]
+        e = ((mine - ref_s).norm() / max(ref_s.norm().item(), 1e-4 * gmax)).item()
+        if e > rtol * 20:
+            bad.append((n, e))
+    assert not bad, (what, "grad samples", bad[:8], len(bad))
+    for k, v in g["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            if int(buffers[k]) != int(v):
+                bad.append((k, int(buffers[k]), int(v)))
+        else:
+            e = ((buffers[k].float().cpu() - v).norm() / v.norm()).item()
+            if e > rtol:
+                bad.append((k, e))
+    assert not bad, (what, "BatchNorm buffers", bad[:8], len(bad))
+
+
+@pytest.mark.parametrize("fx", ["train_acdc_b2_s224", "train_synapse_b2_s96", "train_acdc_b1_s64"])
+def test_oracle_train_mode_pinned_to_reference(fx):
+    """oracle.cenet_forward(training=True) + autograd + criterion_dice_ce == the reference module in train() mode with its
+    own utils/core.py Criterion('dice,ce'): loss, logits, all 630 gradient norms, gradient samples, BN buffers after."""
+    g = _train_golden(fx)
+    sd, kw, x, labels = rebuild_train_case(g)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    stats = {}
+    logits = O.cenet_forward(leaf, O.Cfg(**kw), x, training=True, new_stats=stats)
+    loss = O.criterion_dice_ce(logits, labels, kw["num_classes"])
+    gr = torch.autograd.grad(loss, [leaf[k] for k in names], allow_unused=True)
+    grads = {k: (v if v is not None else torch.zeros_like(sd[k])) for k, v in zip(names, gr)}
+    buffers = dict(sd)
+    buffers.update(stats)
+    if g["batch"] == 1:                                             # CCU's BatchNorm1d never ran (cfam.py:260-261)
+        assert not any(".ccu.bn." in k for k in stats)
+    check_train_against_golden(g, loss.item(), logits.detach(), grads, buffers, 2e-5, fx)
