@@ -2,7 +2,8 @@
 """bench.py -- CENet hot-path throughput on B200 (BASELINE.json metric: 224^2 slices/s, batched inference).
 
     python bench.py --gpus 1 --steps 20 --warmup 5             # product arm (hand-written sm_100a kernels)
-    python bench.py --impl reference --steps 3 --warmup 1      # reference arm: the CPU oracle port on host cores
+    python bench.py --impl reference --steps 3 --warmup 1      # reference arm: the REAL reference (baseline/_ref) on host cores
+    python bench.py --impl reference-gpu                       # the reference module in PyTorch eager on the same B200 (the bar)
     torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU, weak scaling (batch 64 per GPU)
 
 Workload (BASELINE.json configs[1]): Synapse 9-class batched slice inference, 224x224, batch 64 per GPU, bf16
@@ -15,7 +16,12 @@ the fused softmax/argmax -> int64 label map.  A step = one forward pass over one
           of the label maps inside the timed region.
   roofline : dominant kernel (differential flash attention of the 56x56 DSE block) timed live with CUDA events in
           an eager pass; achieved = algorithmic FLOPs / duration against the measured bf16 peak.
-  cpu_baseline : the oracle (CPU port of the reference) on this box's host cores, bounded sample, rank 0 only.
+  cpu_baseline : the reference itself (baseline/_ref, byte copy of /root/reference/src; the oracle port if that copy is
+          missing) on this box's host cores, bounded sample, rank 0 at N=1 only.
+  eager    : the reference module in PyTorch eager (cuDNN / cuBLAS) on the SAME B200, fp32 and autocast(bf16) -- the bar the
+          hand-written kernels have to beat; `vs_eager` = value / best eager value.  N=1 only.
+  skin512  : BASELINE.json configs[3] (512x512 skin, infer + train), N=1 only.
+  synapse_dp : BASELINE.json configs[4] (Synapse training, batch 32 per GPU, gradient all-reduce overlapped vs exposed), N>1 only.
   train    : second half of BASELINE.json's metric -- training images/s on configs[2] (ACDC, batch 24 per GPU, Dice+CE, AdamW),
           same timing protocol; under torchrun the gradients are all-reduced over NCCL in 6 buckets overlapped with backward.
 """
@@ -44,6 +50,15 @@ UNIT = "slices/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures of this workload (profiles/, per round)
 NCU_TRAFFIC = {"source": "profiles/r1_ncu_top_kernels.md, profiles/r1_gemm_traffic.md", "diffattn_flash_kernel": 193.4e6,
                "gemm_tc_kernel": 39.67e6}     # mean over the 154 launches of one forward
+
+
+def workload_config(world=1):
+    """the `config` object: identical in the product line and the reference line (the driver compares them)"""
+    return {"workload": f"CENet (PVTv2-b2) Synapse 9-class batched slice inference {SIZE}x{SIZE}, batch {BATCH} per GPU, "
+                        "logits -> fused softmax/argmax int64 labels (BASELINE.json configs[1])",
+            "batch_per_gpu": BATCH, "size": SIZE, "num_classes": 9,
+            "l2": "flushed between timed steps (256 MB memset; GPU arms)",
+            "parallelism": "replicas (batch-sharded, no data-path collective); gradient all-reduce only in the train objects"}
 
 
 def _peaks():
@@ -135,25 +150,68 @@ def cpu_oracle_throughput(sd, kw, sample_batch, steps, warmup):
     return sample_batch * steps / dt, dt / steps * 1e3, cores
 
 
+def cpu_reference_throughput(sd, kw, sample_batch, steps, warmup):
+    """-> (slices/s, ms/step, cores, kind): the reference itself when baseline/_ref is present, else the oracle port"""
+    from baseline import reference_arms as R
+    if R.available():
+        v, ms, cores = R.cpu_inference(CONFIG_NAME, sample_batch, steps, warmup)
+        return v, ms, cores, "reference"
+    v, ms, cores = cpu_oracle_throughput(sd, kw, sample_batch, steps, warmup)
+    return v, ms, cores, "port"
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores (all threads), on a bounded
+    sample of the product arm's workload: 8 slices per step (at batch 64 the reference needs ~80 GB of RAM)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _, sd, kw = build_model()
-    sample = 4
-    v, ms, cores = cpu_oracle_throughput(sd, kw, sample, args.steps, args.warmup)
+    sample = 8
+    v, ms, cores, kind = cpu_reference_throughput(sd, kw, sample, args.steps, args.warmup)
+    what = ("the unmodified reference (baseline/_ref/src/networks, PyTorch eager fp32)" if kind == "reference"
+            else "the oracle port (baseline/_ref not present)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CENet Synapse 9-class slice inference {SIZE}x{SIZE}, CPU oracle port, {sample} slices/step",
-                   "batch_per_step": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} slices/step x {args.steps} steps of the same synthetic Synapse workload"},
+        "config": workload_config(),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{what}: {sample} slices/step x {args.steps} steps of the same synthetic Synapse workload "
+                                   "(forward + argmax(softmax))"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the reference module in PyTorch eager on cuda:0 (the real bar); prints ONE JSON object"""
+    from baseline import reference_arms as R
+    if not R.available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref not vendored (tools/vendor_reference.py)"}))
+        return
+    res = R.gpu_eager(args.steps, args.warmup, infer_name=CONFIG_NAME, infer_batch=BATCH, train_name=TRAIN_CONFIG,
+                      train_batch=TRAIN_BATCH, modes=args.eager_modes.split(",") if args.eager_modes else None)
+    res["impl"] = "reference-gpu"
+    res["steps"], res["warmup"] = args.steps, max(args.warmup, 3)
+    print(json.dumps(res))
+
+
+def eager_subprocess(steps, warmup, timeout=900):
+    """runs `bench.py --impl reference-gpu` in its own process (own CUDA context, no cenet_b200 state) and parses its line"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--steps", str(steps), "--warmup", str(warmup)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"rc {r.returncode}: {r.stderr[-400:]}"}
+    except Exception as e:                                       # a failed baseline must not take the product line down
+        return {"error": repr(e)}
 
 
 def cpu_oracle_train_throughput(sample_batch, steps):
@@ -185,24 +243,34 @@ def cpu_oracle_train_throughput(sample_batch, steps):
 
 
 # ---------------------------------------------------------------------------------------------------- product arm
-def run_train_leg(args, dev, world, rank, flush):
-    """BASELINE.json configs[2]: ACDC 4-class training step (Dice+CE 0.5/0.5, AdamW lr 1e-4 wd 1e-4), 224x224, batch 24 per
-    GPU, train-mode BatchNorm + DropPath, bf16 activations / fp32 master weights.  A step = forward, fused loss, backward,
-    gradient all-reduce (N > 1), AdamW -- all hand-written kernels, replayed from CUDA graph segments."""
+def run_train_leg(args, dev, world, rank, flush, name=TRAIN_CONFIG, batch=TRAIN_BATCH, size=SIZE, steps=None,
+                  sync_mode="overlapped", with_e2e=True):
+    """A training leg.  Default = BASELINE.json configs[2]: ACDC 4-class training step (Dice+CE 0.5/0.5, AdamW lr 1e-4 wd
+    1e-4), 224x224, batch 24 per GPU, train-mode BatchNorm + DropPath, bf16 activations / fp32 master weights.  A step =
+    forward, fused loss, backward, gradient all-reduce (N > 1), AdamW -- all hand-written kernels, replayed from CUDA graph
+    segments.  sync_mode (N > 1): "overlapped" = bucketed NCCL all-reduce launched as each bucket completes, "exposed" = each
+    all-reduce waited for inline, "none" = no gradient exchange (compute only)."""
     import contextlib
     import torch
     from cenet_b200 import ops, replicas
     from cenet_b200.networks import CENet
     from oracle import fixtures
-    kw = fixtures.CONFIGS[TRAIN_CONFIG]
+
+    class _A:                                                     # local view of args with this leg's step count
+        pass
+    a_ = _A()
+    a_.steps, a_.warmup = (steps or args.steps), args.warmup
+    args = a_
+    TRAIN_BATCH, SIZE = batch, size                               # (shadow the module constants for this leg)
+    kw = fixtures.CONFIGS[name]
     torch.manual_seed(1234)
     with contextlib.redirect_stdout(sys.stderr):
         m = CENet(**kw)
     m.load_state_dict(fixtures.perturb_state(m.state_dict(), 1234))
     m = m.to(dev).train()
     eng = m.train_engine(dev)
-    sync = replicas.GradSync(eng) if world > 1 else None
-    x_host = fixtures.synth_input(TRAIN_CONFIG, TRAIN_BATCH, SIZE, seed=100 + rank).pin_memory()
+    sync = replicas.GradSync(eng, exposed=(sync_mode == "exposed")) if (world > 1 and sync_mode != "none") else None
+    x_host = fixtures.synth_input(name, TRAIN_BATCH, SIZE, seed=100 + rank).pin_memory()
     y_host = torch.randint(0, kw["num_classes"], (TRAIN_BATCH, SIZE, SIZE), generator=torch.Generator().manual_seed(200 + rank)).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     loss_host = torch.zeros(1 + kw["num_classes"]).pin_memory()
@@ -218,6 +286,18 @@ def run_train_leg(args, dev, world, rank, flush):
         e1.record()
     replicas.barrier(dev)
     t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    if not with_e2e:
+        (t_dev,) = replicas.max_over_ranks([t_dev], device=dev)
+        torch.cuda.synchronize(dev)
+        res = {"value": replicas.job_throughput(TRAIN_BATCH, args.steps, t_dev), "unit": "img/s", "ms_per_step": t_dev / args.steps,
+               "steps": args.steps, "batch_per_gpu": TRAIN_BATCH, "sync_mode": sync_mode if world > 1 else "single GPU",
+               "launches_per_step": int(eng.launches_per_step or 0), "gpu_launches": int(ops.launch_count() - n0)}
+        m._engines.clear()
+        del eng, m, sync
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        return res
     for _ in range(max(args.warmup, 3)):                     # warm-up of the end-to-end path (first-touch allocations)
         loss_host.copy_(eng.train_step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True)), non_blocking=True)
     # end to end: every step copies its images + label maps from pinned host memory (on a copy stream, double-buffered, so the
@@ -260,14 +340,54 @@ def run_train_leg(args, dev, world, rank, flush):
         "e2e": {"value": replicas.job_throughput(TRAIN_BATCH, args.steps, t_e2e), "unit": "img/s",
                 "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": loss_host.numel() * 4,
                 "ms_per_step": t_e2e / args.steps},
-        "config": {"workload": f"CENet (PVTv2-b2) ACDC 4-class training step {SIZE}x{SIZE}, batch {TRAIN_BATCH} per GPU, Dice+CE, AdamW, "
-                               "train-mode BatchNorm, DropPath on", "batch_per_gpu": TRAIN_BATCH, "l2": "flushed between steps",
-                   "cuda_graph": bool(eng.use_graph), "flops_per_image": 76.0e9,
+        "config": {"workload": f"CENet (PVTv2-b2) {name} {kw['num_classes']}-class training step {SIZE}x{SIZE}, batch {TRAIN_BATCH} per GPU, "
+                               "Dice+CE, AdamW, train-mode BatchNorm, DropPath on", "batch_per_gpu": TRAIN_BATCH,
+                   "l2": "flushed between steps", "cuda_graph": bool(eng.use_graph), "flops_per_image": 76.0e9 * (SIZE / 224.0) ** 2,
                    "parallelism": f"dp{world} (gradient all-reduce in 6 buckets overlapped with backward)" if world > 1 else "dp1"},
         "dtype": "bf16", "launches_per_step": int(eng.launches_per_step or 0),
         "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(loss_host[0]),
-        "model_tflops": 76.0e9 * TRAIN_BATCH * world / (t_dev / args.steps / 1e3) / 1e12,
+        "model_tflops": 76.0e9 * TRAIN_BATCH * world / (t_dev / args.steps / 1e3) / 1e12 if SIZE == 224 else None,
+        "steps": args.steps,
     }
+
+
+def run_infer_leg(args, dev, flush, name, batch, size, steps):
+    """an extra inference leg (another BASELINE config) with inputs resident in HBM: CUDA events per step, L2 flushed"""
+    import contextlib
+    import torch
+    from cenet_b200.networks import CENet
+    from oracle import fixtures
+    kw = fixtures.CONFIGS[name]
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(sys.stderr):
+        m = CENet(**kw)
+    m.load_state_dict(fixtures.perturb_state(m.state_dict(), 1234))
+    m = m.to(dev).eval()
+    x = fixtures.synth_input(name, batch, size).to(dev)
+    eng = m._engine(x)
+    out = torch.empty((batch, size, size), device=dev, dtype=torch.int64)
+    for _ in range(3):
+        eng.forward(x, labels=True, out=out)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    for e0, e1 in ev:
+        flush.zero_()
+        e0.record()
+        eng.forward(x, labels=True, out=out)
+        e1.record()
+    torch.cuda.synchronize(dev)
+    t = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    prof = eng.profile_ops(x, labels=True, steps=1) if steps > 1 else {}
+    top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]
+    res = {"value": batch * steps / (t / 1e3), "unit": "img/s", "ms_per_step": t / steps, "steps": steps, "batch": batch,
+           "launches_per_step": int(eng.launches_per_forward or 0),
+           "op_breakdown_ms": {f"{op}@{tag}": round(ms, 4) for (op, tag), (ms, n) in top}, "_prof": prof}
+    m._engines.clear()
+    del eng, m
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
 
 
 def diffattn_flops(N, E, B):
@@ -368,9 +488,71 @@ def run_product(args):
     barrier()
     t_e2e_ms = e_start.elapsed_time(e_end)
     t_dev_ms, t_e2e_ms = replicas.max_over_ranks([t_dev_ms, t_e2e_ms], device=dev)
+    # ---- sustained run (SURVEY 8d asks >= 100 timed iterations; the driver's K is usually 20) and single-slice latency ----
+    n_sus = 100
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_sus)]
+    barrier()
+    for e0, e1 in ev2:
+        flush.zero_()
+        e0.record()
+        eng.forward(x_dev, labels=True, out=labels_dev)
+        e1.record()
+    barrier()
+    (t_sus_ms,) = replicas.max_over_ranks([sum(e0.elapsed_time(e1) for e0, e1 in ev2)], device=dev)
+    x1 = x_dev[:1].contiguous()
+    lab1 = torch.empty((1, SIZE, SIZE), device=dev, dtype=torch.int64)
+    for _ in range(3):
+        eng.forward(x1, labels=True, out=lab1)
+    ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    for e0, e1 in ev3:
+        e0.record()
+        eng.forward(x1, labels=True, out=lab1)
+        e1.record()
+    torch.cuda.synchronize(dev)
+    lat = sorted(e0.elapsed_time(e1) for e0, e1 in ev3)
+    latency_b1 = {"median_ms": lat[len(lat) // 2], "min_ms": lat[0], "launches": int(eng.launches_per_forward or 0),
+                  "note": "B=1 forward + fused argmax, CUDA-graph replay (the reference's per-slice eval mode, metrics_eval.py:48-52)"}
+    eng.forward(x_dev, labels=True, out=labels_dev)                 # restore the batch-64 plan as the engine's current one
+
     train = None
     if not args.no_train:
         train = run_train_leg(args, dev, world, rank, flush)
+    # ---- BASELINE.json configs[4]: Synapse data-parallel training, batch 32 per GPU, all-reduce overlapped vs exposed ----
+    synapse_dp = None
+    if world > 1 and not args.no_train:
+        synapse_dp = {"workload": f"CENet Synapse 9-class training step 224x224, batch 32 per GPU x {world} GPUs = global batch "
+                                  f"{32 * world} (BASELINE.json configs[4]), Dice+CE, AdamW"}
+        for mode in ("overlapped", "exposed", "none"):
+            synapse_dp[mode] = run_train_leg(args, dev, world, rank, flush, name="synapse", batch=32, size=SIZE,
+                                             steps=max(10, args.steps // 2), sync_mode=mode, with_e2e=False)
+        synapse_dp["allreduce_exposed_cost_ms"] = synapse_dp["exposed"]["ms_per_step"] - synapse_dp["none"]["ms_per_step"]
+        synapse_dp["allreduce_overlapped_cost_ms"] = synapse_dp["overlapped"]["ms_per_step"] - synapse_dp["none"]["ms_per_step"]
+    # ---- BASELINE.json configs[3]: 512x512 skin (3-channel, binary), inference + training, one GPU ----
+    skin512 = None
+    if world == 1 and not args.no_skin512:
+        peaks = _peaks()
+        inf = run_infer_leg(args, dev, flush, "skin", 16, 512, max(5, args.steps // 4))
+        prof5 = inf.pop("_prof")
+        N5 = (512 // 4) ** 2
+        k1 = prof5.get(("diffattn_flash", "se1"))
+        k2 = prof5.get(("nonlocal_flash", "dec1"))
+        if k1:
+            fl = diffattn_flops(N5, 128, 16)
+            inf["roofline_K1_diffattn_N16384"] = {"bound": "tensor", "achieved": fl / (k1[0] / 1e3) / 1e12, "peak": peaks["tf_sustained"],
+                                                  "unit": "TFLOP/s", "frac": fl / (k1[0] / 1e3) / 1e12 / peaks["tf_sustained"],
+                                                  "ms_per_launch": k1[0], "flops_per_launch": fl}
+        if k2:
+            fl = 4.0 * N5 * N5 * 64 * 16
+            inf["roofline_K2_nonlocal_N16384"] = {"bound": "tensor", "achieved": fl / (k2[0] / 1e3) / 1e12, "peak": peaks["tf_sustained"],
+                                                  "unit": "TFLOP/s", "frac": fl / (k2[0] / 1e3) / 1e12 / peaks["tf_sustained"],
+                                                  "ms_per_launch": k2[0], "flops_per_launch": fl}
+        inf["model_tflops"] = 330.4e9 * inf["value"] / 1e12
+        skin512 = {"workload": "CENet skin (HAM10000-shaped) binary segmentation 512x512 (BASELINE.json configs[3]): inference batch 16 "
+                               "(fused argmax), training batch 8 (Dice+CE 0.5/0.5, AdamW)", "infer": inf}
+        if not args.no_train:
+            skin512["train"] = run_train_leg(args, dev, world, rank, flush, name="skin", batch=8, size=512,
+                                             steps=max(5, args.steps // 4), with_e2e=False)
+            skin512["train"]["model_tflops"] = 3 * 330.4e9 * skin512["train"]["value"] / 1e12
     clocks.__exit__()
 
     if rank == 0:
@@ -416,34 +598,67 @@ def run_product(args):
                          "mufu_bound": {"exp_per_launch": 16.0 * N1 * N1 * BATCH, "peak_exp_per_s": 148 * 16 * 1.965e9,
                                         "frac": 16.0 * N1 * N1 * BATCH / (ms_da / 1e3) / (148 * 16 * 1.965e9)},
                          "note": "softmax-bound: one MUFU.EX2 per score (16/clk/SM); see DESIGN.md 4a"}
-        _, _, cores = 0, 0, os.cpu_count()
-        cpu_v, cpu_ms, cores = cpu_oracle_throughput(sd, kw, 4, 2, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"CENet (PVTv2-b2) Synapse 9-class batched slice inference {SIZE}x{SIZE}, batch {BATCH} per GPU, "
-                                   "logits -> fused softmax/argmax int64 labels", "batch_per_gpu": BATCH, "l2": "flushed between steps",
-                       "cuda_graph": bool(eng.use_graph), "parallelism": f"replicas x{world} (batch-sharded, no collective)"},
+            "config": workload_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": labels_host.numel() * 8, "ms_per_step": t_e2e_ms / args.steps},
             "gpu_launches": int(launches_per_step * args.steps * 2 + launches_per_step * 2) + (train["gpu_launches"] if train else 0),
             "launches_per_step": int(launches_per_step),
+            "cuda_graph": bool(eng.use_graph),
             "clocks": clocks.summary(),
             "roofline": roof,
             "roofline_attention": roof_attn,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "oracle port, 4 slices/step x 2 steps (1 warm-up) of the same synthetic workload"},
+            "sustained": {"steps": n_sus, "value": replicas.job_throughput(BATCH, n_sus, t_sus_ms), "unit": UNIT,
+                          "ms_per_step": t_sus_ms / n_sus},
+            "latency_b1": latency_b1,
+            "model_tflops": 25.35e9 * value / 1e12,
             "op_breakdown_ms": {f"{op}@{tag}": round(ms, 4) for (op, tag), (ms, n) in top},
             "op_family_ms": {op: round(v[0], 4) for op, v in sorted(by_op.items(), key=lambda kv: -kv[1][0])},
             "eager_step_ms": total_ms,
             "train": train,
         }
-        if train is not None and not args.no_cpu_train:
-            tv, tms, tc = cpu_oracle_train_throughput(2, 1)
-            line["train"]["cpu_baseline"] = {"value": tv, "unit": "img/s", "cores": tc, "kind": "port",
-                                             "sample": "oracle port + autograd + torch AdamW, 2 images/step x 1 step"}
+        if skin512 is not None:
+            line["skin512"] = skin512
+        if synapse_dp is not None:
+            line["synapse_dp"] = synapse_dp
+        if world == 1:
+            # host-core baseline and the same-GPU eager bar: rank 0 at N=1 only (under torchrun the other ranks spin and
+            # OMP_NUM_THREADS is 1, which made the N>1 numbers of round 1 meaningless)
+            cpu_v, cpu_ms, cores, kind = cpu_reference_throughput(sd, kw, 8, 2, 1)
+            line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": ("the unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port")
+                                              + ", 8 slices/step x 2 steps (1 warm-up) of the same synthetic workload"}
+            if train is not None and not args.no_cpu_train:
+                from baseline import reference_arms as R
+                if R.available():
+                    tv, tms, tc = R.cpu_train(TRAIN_CONFIG, 4, 1)
+                    kind_t = "reference"
+                else:
+                    tv, tms, tc = cpu_oracle_train_throughput(2, 1)
+                    kind_t = "port"
+                line["train"]["cpu_baseline"] = {"value": tv, "unit": "img/s", "cores": tc, "kind": kind_t,
+                                                 "sample": "reference module + its Criterion('dice,ce') + torch AdamW, 4 images x 1 step"}
+            if not args.no_eager:
+                torch.cuda.empty_cache()
+                eg = eager_subprocess(args.steps, args.warmup)
+                line["eager"] = eg
+                try:
+                    bi, bt = eg["infer"]["best"], eg["train"]["best"]
+                    line["vs_eager"] = {"value": value / bi["value"], "e2e": e2e / bi["e2e"], "infer_mode": bi["mode"],
+                                        "infer_batch": bi["batch"],
+                                        "train": (train["value"] / bt["value"]) if train else None, "train_mode": bt["mode"],
+                                        "vs_stock_fp32": {"value": value / eg["infer"]["fp32"]["value"],
+                                                          "train": (train["value"] / eg["train"]["fp32"]["value"]) if train else None},
+                                        "note": "product / the reference module in PyTorch eager on the same B200 (best of the eager modes)"}
+                except Exception:
+                    pass
         print(json.dumps(line))
+        if train is not None:                                     # second line (stderr): the collective path's own metric
+            print(json.dumps({"metric": train["metric"], "value": train["value"], "unit": train["unit"], "n_gpus": world,
+                              "ms_per_step": train["ms_per_step"], "scaling": "weak", "higher_is_better": True}), file=sys.stderr)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -454,12 +669,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--impl", default="product", choices=["product", "reference", "reference-gpu"])
+    ap.add_argument("--no-eager", action="store_true", help="skip the reference-in-eager-on-this-GPU bar (N=1)")
+    ap.add_argument("--no-skin512", action="store_true", help="skip the 512x512 skin legs (BASELINE configs[3], N=1)")
+    ap.add_argument("--eager-modes", default="", help="comma list of eager modes for --impl reference-gpu")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     ap.add_argument("--no-cpu-train", action="store_true", help="skip the CPU training baseline sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_product(args)
 

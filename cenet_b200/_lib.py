@@ -107,6 +107,7 @@ _SIGS = {
     "cenet_maxpool2_scale_bwd": [vp, i32, ll, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp],
     "cenet_head_upsample_bwd": [vp, vp, i32, i32, i32, i32, vp],
     "cenet_adamw": [vp, vp, vp, vp, ll, vp, vp],
+    "cenet_volume_labels_counts": [vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
     "cenet_gather_cast": [vp, vp, vp, i32, ll, vp],
 }
 _PLAIN = {  # no stream, different return types

@@ -73,8 +73,10 @@ class GradSync:
     that follow; `finish` (the engine's grad_hook, right before AdamW) waits for all of them.  With CUDA graphs the
     engine cuts its capture at the bucket markers and issues these calls between graph replays."""
 
-    def __init__(self, engine, group=None):
-        self.eng, self.group = engine, group
+    def __init__(self, engine, group=None, exposed=False):
+        """exposed=True is a measurement mode (bench.py `synapse_dp`): every bucket's all-reduce is waited for inline, so
+        the backward kernels that follow cannot overlap it -- the step-time difference to the default is the overlap gain."""
+        self.eng, self.group, self.exposed = engine, group, exposed
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
         self.works, self.pending = [], []
@@ -95,6 +97,8 @@ class GradSync:
         self.works.append(dist.all_reduce(t, op=op, group=self.group, async_op=True))
         if not self.avg:
             self.pending.append(t)
+        if self.exposed:
+            self.works[-1].wait()                     # the compute stream now waits for this all-reduce before going on
 
     def finish(self, _gflat=None):
         for w in self.works:

@@ -1266,9 +1266,16 @@ class TrainEngine:
                 cur["keep"] = use_pdl
             except TypeError:                                        # torch without keep_graph
                 cur["g"], cur["keep"] = torch.cuda.CUDAGraph(), False
+            cur["n0"] = ops.launch_count()
             cur["g"].capture_begin(pool=pool)
 
         def end():
+            if ops.launch_count() == cur["n0"]:                      # two markers back to back (e.g. the last bucket and the
+                import warnings                                      # gradient hook): nothing was captured, drop the segment
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    cur["g"].capture_end()
+                return
             cur["g"].capture_end()
             if cur["keep"]:
                 try:

@@ -184,6 +184,16 @@ int cenet_stem5x5(const void* x, int x_dtype, const float* w1, const float* b1, 
 int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls,
                                cenet_stream_t s);
 
+/* ---- per-volume evaluation tail (utils/metrics_eval.py:53-71, utils_synapse.py:69-84; medpy.metric.binary.dc) -------------
+ * pred_patch [D,ph,pw] int64 = the network's label maps at the patch size.  For every voxel (d,y,x) of the original volume:
+ * pred_out[d,y,x] = pred_patch[d, iy[y], ix[x]]  (iy/ix: the nearest-neighbour source index tables of scipy's
+ * `zoom(order=0)`, built on the host) and, when `label` is given ([D,H,W]; label_kind 0 float32 / 1 int64 / 2 uint8),
+ * counts[0..ncls) += (pred == c && label == c), counts[ncls..2ncls) += (pred == c), counts[2ncls..3ncls) += (label == c).
+ * counts is int64 [3*ncls], zeroed by the call; exact integers, deterministic.  pred_out / label may be NULL. */
+int cenet_volume_labels_counts(const long long* pred_patch, int ph, int pw, const int* iy, const int* ix, const void* label,
+                               int label_kind, long long* pred_out, long long* counts, int D, int H, int W, int ncls,
+                               cenet_stream_t s);
+
 /* ---- fused Dice + CE (utils/core.py:57-80,176-188) ------------------------------------------------------------
  * logits [B,ncls,H,W] fp32, labels [B,H,W] int64.  ws: (3*ncls+1)*nblk + 3*ncls+3 floats, nblk =
  * cenet_loss_nblocks(B*H*W).  loss_out[0] = w_dice*dice + w_ce*ce; loss_out[1+i] = per-class dice score.
