@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) volume_labels_counts_kernel(const long lo
     const long long t = i / W;
     const int y = (int)(t % H);
     const int d = (int)(t / H);
-    const long long p = pred_patch[((long long)d * ph + iy[y]) * pw + ix[x]];
+    const int sy = iy[y], sx = ix[x];            // -1: scipy's coordinate fell outside the patch -> constant 0
+    const long long p = (sy < 0 || sx < 0) ? 0ll : pred_patch[((long long)d * ph + sy) * pw + sx];
     if (pred_out) pred_out[i] = p;
     if (label) {
       const long long l = (long long)label[i];

@@ -121,6 +121,10 @@ class Engine:
         self._bufs = {}
         self._graphs = {}
         self.taps = None                              # dict -> intermediate activations are copied out (tests)
+        # CCU applies its BatchNorm1d only `if B > 1` (cfam.py:260-261), in eval mode too: a batch of slices is NOT the same
+        # function as the slices one by one.  None = follow the batch size like the reference; False = per-slice (B = 1)
+        # semantics for any batch (cenet_b200.volume batches a volume's slices and must match the reference's B = 1 loop)
+        self.ccu_bn1d = None
         self.launches_per_forward = None              # kernels launched by one pass (counted on the eager warm-up)
         self.pdl_stats = None                         # counters of the programmatic-dependent-launch pass (pdl.py)
 
@@ -481,7 +485,7 @@ class Engine:
         # CCU(BN(x))
         gate_bc = self.buf(key + ".ccu_gate", (B, Cc), torch.float32)
         ws = self.buf(key + ".ccu_ws", (B * ops.ccu_nchunk(HW) * Cc * 3,), torch.float32)
-        bn1d = B > 1                                                     # cfam.py:260-261
+        bn1d = B > 1 if self.ccu_bn1d is None else self.ccu_bn1d          # cfam.py:260-261
         ops.ccu_gate(x, w[p + ".bn1.s"], w[p + ".bn1.t"], w[m + ".ccu.fc1"], w[m + ".ccu.fc2"],
                      w[m + ".ccu.bn.s"] if bn1d else None, w[m + ".ccu.bn.t"] if bn1d else None, gate_bc, ws, B, HW, Cc)
         x1 = self.buf(key + ".x1", (Mtok, Cc))
@@ -648,7 +652,7 @@ class Engine:
         if self._wver != self._weights_version():
             self.pack()
         ncls = self.cfg["num_classes"]
-        key = (B, H, W, bool(labels))
+        key = (B, H, W, bool(labels), self.ccu_bn1d)
         self._plan_key = (B, H, W)
         x_in = self.buf("x_in", (B, x.shape[1], H, W), torch.float32)
         x_in.copy_(x if x.dtype == torch.float32 else x.float())

@@ -273,6 +273,24 @@ def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
     L.call("cenet_head_upsample_argmax", _f32(y, "y"), _f32(logits, "logits"), _p(labels), B, h, w, ncls, _stream())
 
 
+def volume_labels_counts(pred_patch, iy, ix, label, pred_out, counts, ncls):
+    """pred_patch [D,ph,pw] int64 -> pred_out [D,H,W] int64 (nearest gather through iy / ix) and the per-class integer
+    counts medpy's `dc` is made of (counts int64 [3*ncls]: intersection | pred size | label size)."""
+    D, ph, pw = pred_patch.shape
+    H, W = iy.numel(), ix.numel()
+    if pred_patch.dtype != torch.int64 or not pred_patch.is_contiguous():
+        raise TypeError("pred_patch must be contiguous int64")
+    if iy.dtype != torch.int32 or ix.dtype != torch.int32:
+        raise TypeError("index tables must be int32")
+    kind = None
+    if label is not None:
+        kind = {torch.float32: 0, torch.int64: 1, torch.uint8: 2}.get(label.dtype)
+        if kind is None or not label.is_contiguous() or tuple(label.shape) != (D, H, W):
+            raise TypeError("label must be a contiguous float32 / int64 / uint8 tensor of shape [D,H,W]")
+    L.call("cenet_volume_labels_counts", _p(pred_patch), ph, pw, _p(iy), _p(ix), _p(label), kind or 0, _p(pred_out), _p(counts),
+           D, H, W, ncls, _stream())
+
+
 def loss_nblocks(npix: int) -> int:
     return int(L.load().cenet_loss_nblocks(npix))
 

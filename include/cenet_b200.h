@@ -187,7 +187,7 @@ int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* la
 /* ---- per-volume evaluation tail (utils/metrics_eval.py:53-71, utils_synapse.py:69-84; medpy.metric.binary.dc) -------------
  * pred_patch [D,ph,pw] int64 = the network's label maps at the patch size.  For every voxel (d,y,x) of the original volume:
  * pred_out[d,y,x] = pred_patch[d, iy[y], ix[x]]  (iy/ix: the nearest-neighbour source index tables of scipy's
- * `zoom(order=0)`, built on the host) and, when `label` is given ([D,H,W]; label_kind 0 float32 / 1 int64 / 2 uint8),
+ * `zoom(order=0)`, built on the host; -1 = outside -> label 0) and, when `label` is given ([D,H,W]; label_kind 0 float32 / 1 int64 / 2 uint8),
  * counts[0..ncls) += (pred == c && label == c), counts[ncls..2ncls) += (pred == c), counts[2ncls..3ncls) += (label == c).
  * counts is int64 [3*ncls], zeroed by the call; exact integers, deterministic.  pred_out / label may be NULL. */
 int cenet_volume_labels_counts(const long long* pred_patch, int ph, int pw, const int* iy, const int* ix, const void* label,
