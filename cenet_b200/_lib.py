@@ -17,6 +17,13 @@ GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
 vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 
 
+class AttnTcArgs(C.Structure):
+    """Mirror of `cenet_attn_tc_args` (include/cenet_b200.h)."""
+    _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp), ("lse", vp),
+                ("ldq", ll), ("ldk", ll), ("ldv", ll), ("ldo", ll), ("bq", ll), ("bk", ll), ("bv", ll), ("bo", ll),
+                ("B", i32), ("heads", i32), ("Nq", i32), ("Nk", i32), ("D", i32), ("scale", f32)]
+
+
 class GemmArgs(C.Structure):
     """Mirror of `cenet_gemm_args` (include/cenet_b200.h)."""
     _fields_ = [
@@ -107,6 +114,7 @@ _SIGS = {
     "cenet_maxpool2_scale_bwd": [vp, i32, ll, vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp],
     "cenet_head_upsample_bwd": [vp, vp, i32, i32, i32, i32, vp],
     "cenet_adamw": [vp, vp, vp, vp, ll, vp, vp],
+    "cenet_attn_tc": [vp, vp],
     "cenet_volume_labels_counts": [vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
     "cenet_gather_cast": [vp, vp, vp, i32, ll, vp],
 }

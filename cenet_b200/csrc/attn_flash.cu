@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+bool cenet_attn_tc_eligible(const cenet_attn_tc_args* a);   // attn_tc.cu
+
 namespace {
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -564,6 +566,13 @@ int launch_diff(const bf16* qkv, bf16* out, int B, int N, int heads, int hd_real
 }
 template <int D>
 int launch_attn(const AttnPtrs& a, int B, int heads, int Nq, int Nk, float scale, cudaStream_t s, const char* name) {
+  {   // tcgen05 / TMEM / TMA kernel (attn_tc.cu) whenever the operands are TMA-addressable; this mma.sync kernel otherwise
+    cenet_attn_tc_args t;
+    t.q = a.q; t.k = a.k; t.v = a.v; t.o = a.o; t.lse = nullptr;
+    t.ldq = a.ldq; t.ldk = a.ldk; t.ldv = a.ldv; t.ldo = a.ldo; t.bq = a.bq; t.bk = a.bk; t.bv = a.bv; t.bo = a.bo;
+    t.B = B; t.heads = heads; t.Nq = Nq; t.Nk = Nk; t.D = D; t.scale = scale;
+    if (cenet_attn_tc_eligible(&t)) return cenet_attn_tc(&t, (cenet_stream_t)s);
+  }
   using Cfg = NlCfg<D>;
   auto kern = nonlocal_flash_kernel<D>;
   if (Cfg::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);

@@ -221,6 +221,23 @@ def nonlocal_flash(tpg, out, B, N, Cc, scale):
     return out
 
 
+def attn_tc(q, k, v, o, *, B, heads, Nq, Nk, D, scale, ldq, ldk, ldv, ldo, bq, bk, bv, bo, q_off=0, k_off=0, v_off=0, o_off=0,
+            lse=None):
+    """tcgen05 flash attention (attn_tc.cu): o = softmax(q k^T * scale) v per (image, head of width D in {64,128}); operands are
+    bf16 buffers addressed by element offset / row pitch / image stride, so q, k, v may be column blocks of one tensor."""
+    for t in (q, k, v, o):
+        if t.dtype != torch.bfloat16:
+            raise TypeError("attn_tc is a bf16 kernel")
+    a = L.AttnTcArgs()
+    a.q, a.k, a.v, a.o = _p(q) + 2 * q_off, _p(k) + 2 * k_off, _p(v) + 2 * v_off, _p(o) + 2 * o_off
+    a.lse = _f32(lse, "lse")
+    a.ldq, a.ldk, a.ldv, a.ldo, a.bq, a.bk, a.bv, a.bo = ldq, ldk, ldv, ldo, bq, bk, bv, bo
+    a.B, a.heads, a.Nq, a.Nk, a.D, a.scale = B, heads, Nq, Nk, D, scale
+    import ctypes
+    L.call("cenet_attn_tc", ctypes.byref(a), _stream())
+    return o
+
+
 def seg_loss_ws(B, ncls, H, W, device):
     """workspace of `seg_loss` (also large enough for `dice_ce`)"""
     return torch.empty((4 * ncls + 1) * loss_nblocks(B * H * W) + 5 * ncls + 4, device=device, dtype=torch.float32)

@@ -184,6 +184,19 @@ int cenet_stem5x5(const void* x, int x_dtype, const float* w1, const float* b1, 
 int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls,
                                cenet_stream_t s);
 
+/* ---- tcgen05 flash attention, head width 64 or 128 (nlb.py:116-137; pvtv2.py:98-103) ---------------------------------------
+ * o[b, n, h*D + :] = softmax_k( q[b,n,h*D+:] . k[b,k,h*D+:] * scale ) v[b,k,h*D+:]   for n < Nq, k < Nk, bf16 in / out, fp32
+ * accumulation in TMEM; nothing Nq x Nk is written to HBM.  ld*: row pitches, b*: per-image strides (elements, multiples
+ * of 8); pointers 16-byte aligned.  lse (nullable): fp32 [B, heads, Nq] natural log-sum-exp of the scaled scores. */
+typedef struct {
+  const void *q, *k, *v; void* o; float* lse;
+  long long ldq, ldk, ldv, ldo;
+  long long bq, bk, bv, bo;
+  int B, heads, Nq, Nk, D;
+  float scale;
+} cenet_attn_tc_args;
+int cenet_attn_tc(const cenet_attn_tc_args* a, cenet_stream_t s);
+
 /* ---- per-volume evaluation tail (utils/metrics_eval.py:53-71, utils_synapse.py:69-84; medpy.metric.binary.dc) -------------
  * pred_patch [D,ph,pw] int64 = the network's label maps at the patch size.  For every voxel (d,y,x) of the original volume:
  * pred_out[d,y,x] = pred_patch[d, iy[y], ix[x]]  (iy/ix: the nearest-neighbour source index tables of scipy's

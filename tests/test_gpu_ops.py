@@ -362,6 +362,39 @@ def test_nonlocal_flash(C, N):
     assert e < 8e-3, e
 
 
+@pytest.mark.parametrize("D,heads,Nq,Nk,amp", [(64, 1, 3136, 3136, 1.5), (64, 2, 300, 49, 1.0), (128, 1, 784, 784, 1.5),
+                                               (64, 1, 130, 100, 1.0), (64, 5, 196, 49, 1.0), (128, 2, 257, 321, 1.0),
+                                               (64, 1, 1000, 1000, 6.0), (64, 1, 128, 1, 1.0), (64, 8, 49, 49, 1.0)])
+def test_attn_tc(D, heads, Nq, Nk, amp):
+    """tcgen05 / TMEM flash attention called directly: ragged query and key counts, several heads, one key, and scores large
+    enough (amp 6 -> |s| ~ 50 in log2 units) that the lazy rescale of the TMEM accumulator runs many times."""
+    from cenet_b200 import ops
+    B = 2
+    C = heads * D
+    q = (torch.randn(B, Nq, C, generator=g(1)) * amp).to(DEV, torch.bfloat16)
+    kv = (torch.randn(B, Nk, 2 * C, generator=g(2)) * amp).to(DEV, torch.bfloat16)
+    kv[..., C:] = (torch.randn(B, Nk, C, generator=g(3))).to(DEV, torch.bfloat16)
+    out = torch.full((B, Nq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, Nq, device=DEV)
+    sc = D ** -0.5
+    ops.attn_tc(q, kv, kv, out, B=B, heads=heads, Nq=Nq, Nk=Nk, D=D, scale=sc, ldq=C, ldk=2 * C, ldv=2 * C, ldo=C, bq=Nq * C,
+                bk=Nk * 2 * C, bv=Nk * 2 * C, bo=Nq * C, v_off=C, lse=lse)
+    qf = q.float().view(B, Nq, heads, D).transpose(1, 2)
+    kf = kv.float()[..., :C].reshape(B, Nk, heads, D).transpose(1, 2)
+    vf = kv.float()[..., C:].reshape(B, Nk, heads, D).transpose(1, 2)
+    s_ = qf @ kf.transpose(-1, -2) * sc
+    ref = (torch.softmax(s_, -1) @ vf).transpose(1, 2).reshape(B, Nq, C)
+    e = rel(out, ref)
+    record(f"attn_tc_D{D}_h{heads}_{Nq}x{Nk}_amp{amp}", e)
+    assert torch.isfinite(out.float()).all()
+    assert e < 8e-3, e
+    torch.testing.assert_close(lse.cpu(), torch.logsumexp(s_, -1).cpu(), rtol=2e-3, atol=2e-3)
+    out2 = torch.empty_like(out)                                  # run-to-run bit-exact
+    ops.attn_tc(q, kv, kv, out2, B=B, heads=heads, Nq=Nq, Nk=Nk, D=D, scale=sc, ldq=C, ldk=2 * C, ldv=2 * C, ldo=C, bq=Nq * C,
+                bk=Nk * 2 * C, bv=Nk * 2 * C, bo=Nq * C, v_off=C)
+    assert torch.equal(out, out2)
+
+
 # ------------------------------------------------------------------------------------------------------------ DSEB / CFAM pieces
 @pytest.mark.parametrize("scales,H", [([0.8, 0.4], 56), ([1.0, 0.5], 28), ([1.0, 0.75, 0.5], 14), ([0.8, 0.4], 14)])
 def test_fea_combine(scales, H):
