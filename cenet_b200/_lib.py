@@ -21,7 +21,7 @@ class AttnTcArgs(C.Structure):
     """Mirror of `cenet_attn_tc_args` (include/cenet_b200.h)."""
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp), ("lse", vp),
                 ("ldq", ll), ("ldk", ll), ("ldv", ll), ("ldo", ll), ("bq", ll), ("bk", ll), ("bv", ll), ("bo", ll),
-                ("B", i32), ("heads", i32), ("Nq", i32), ("Nk", i32), ("D", i32), ("scale", f32)]
+                ("B", i32), ("heads", i32), ("Nq", i32), ("Nk", i32), ("D", i32), ("scale", f32), ("lse_base2", i32)]
 
 
 class GemmArgs(C.Structure):

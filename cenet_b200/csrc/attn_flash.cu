@@ -12,6 +12,8 @@
 #include <type_traits>
 
 bool cenet_attn_tc_eligible(const cenet_attn_tc_args* a);   // attn_tc.cu
+int cenet_diffattn_tc(const void* qkv, void* out, int B, int N, int heads, int hd, float lambda, float eps, float mult,
+                      const float* kmax, cudaStream_t s);        // diffattn_tc.cu: 0 done, 1 not applicable, -1 error
 
 namespace {
 
@@ -570,7 +572,7 @@ int launch_attn(const AttnPtrs& a, int B, int heads, int Nq, int Nk, float scale
     cenet_attn_tc_args t;
     t.q = a.q; t.k = a.k; t.v = a.v; t.o = a.o; t.lse = nullptr;
     t.ldq = a.ldq; t.ldk = a.ldk; t.ldv = a.ldv; t.ldo = a.ldo; t.bq = a.bq; t.bk = a.bk; t.bv = a.bv; t.bo = a.bo;
-    t.B = B; t.heads = heads; t.Nq = Nq; t.Nk = Nk; t.D = D; t.scale = scale;
+    t.B = B; t.heads = heads; t.Nq = Nq; t.Nk = Nk; t.D = D; t.scale = scale; t.lse_base2 = 0;
     if (cenet_attn_tc_eligible(&t)) return cenet_attn_tc(&t, (cenet_stream_t)s);
   }
   using Cfg = NlCfg<D>;
@@ -615,6 +617,22 @@ extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, in
   CENET_REQUIRE(heads >= 1 && E % (2 * heads) == 0, "cenet_diffattn_flash: E=%d not divisible by 2*heads=%d", E, 2 * heads);
   CENET_REQUIRE(B <= 65535 && heads <= 65535, "cenet_diffattn_flash: grid too large");
   const int hd = E / (2 * heads);
+  if (hd == 8 || hd == 16 || hd == 32 || hd == 64) {
+    // tcgen05 / TMEM / TMA kernel (diffattn_tc.cu); the kmax pre-pass feeds its fixed softmax shift
+    if (kmax_ws) {
+      const long long row = 3LL * E;
+      switch (hd) {
+        case 8: kmax_kernel<8><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+        case 16: kmax_kernel<16><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+        case 32: kmax_kernel<32><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+        default: kmax_kernel<64><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+      }
+      CENET_LAUNCH_CHECK("diffattn_kmax");
+    }
+    const int rc = cenet_diffattn_tc(qkv, out, B, N, heads, hd, lambda, eps, mult, kmax_ws, to_stream(s));
+    if (rc <= 0) return rc;
+    return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, nullptr, to_stream(s));
+  }
   return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, kmax_ws, to_stream(s));
 }
 
@@ -646,6 +664,15 @@ extern "C" int cenet_nonlocal_flash(const void* tpg, void* out, int B, int N, in
   switch (C) {
     case 64: return launch_nl<64>((const bf16*)tpg, (bf16*)out, B, N, scale, to_stream(s));
     case 128: return launch_nl<128>((const bf16*)tpg, (bf16*)out, B, N, scale, to_stream(s));
-    default: CENET_FAIL("cenet_nonlocal_flash: C=%d not in {64,128}; use the materialised path", C);
+    default: {
+      cenet_attn_tc_args t;
+      const bf16* tp = (const bf16*)tpg;
+      t.q = tp; t.k = tp + C; t.v = tp + 2 * C; t.o = out; t.lse = nullptr;
+      t.ldq = t.ldk = t.ldv = 3 * C; t.ldo = C;
+      t.bq = t.bk = t.bv = (long long)N * 3 * C; t.bo = (long long)N * C;
+      t.B = B; t.heads = 1; t.Nq = N; t.Nk = N; t.D = C; t.scale = scale; t.lse_base2 = 0;
+      if (cenet_attn_tc_eligible(&t)) return cenet_attn_tc(&t, s);        // wide heads: streamed-contraction tcgen05 kernel
+      CENET_FAIL("cenet_nonlocal_flash: C=%d is neither 64 / 128 nor a multiple of 64 up to 1024; use the materialised path", C);
+    }
   }
 }

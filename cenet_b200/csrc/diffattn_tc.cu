@@ -1,0 +1,448 @@
+// tcgen05 / TMEM / TMA differential flash attention for sm_100a (multihead_diffattn.py:92-124), head_dim HD in {8,16,32,64}.
+//
+//   out[n, head] = RMSNorm_{2HD}( softmax(Q_{2h} K_{2h}^T s) V_h  -  lambda * softmax(Q_{2h+1} K_{2h+1}^T s) V_h ) * mult
+//
+// The two softmax maps of a head run side by side in ONE CTA of 320 threads over 128 query rows:
+//   warp 0      : TMA producer.  Every operand is fetched as boxes of 8 columns (16 bytes) x rows: [rows][16 B] blocks are the
+//                 canonical NO-SWIZZLE core-matrix layout of the tensor core for ANY head_dim >= 8, K-major for Q / K and
+//                 MN-major for V.  head_dim 8 gets its second K chunk (k16 contraction) from a block of zeros.
+//   warp 1      : single-thread tcgen05.mma.  Per 64-key tile and map: S_m = Q_m K_m^T (M=128, N=64, K=max(HD,16)) into TMEM,
+//                 then O_m += P_m [V | 1] (M=128, N=2HD(+16), K=64; A = P_m from shared memory).  For HD <= 16 a ones column
+//                 appended to V makes the tensor pipe accumulate the softmax row sums too.
+//   warps 2..5  : softmax of map 0, one thread per query row (TMEM lane = row);   warps 6..9 : softmax of map 1.
+//                 tcgen05.ld 64 scores -> exp2 -> bf16 P into the swizzled K-major tile.  The kernel is bound by the
+//                 exponentials (2h N^2 per image): a fixed Cauchy-Schwarz shift |q_r| max_n|k_n| (kmax pre-pass) removes the
+//                 running max and every rescale, and PP of every 4 exponential PAIRS are evaluated on the FMA pipe (packed
+//                 fp32 Cody-Waite + cubic) so that MUFU.EX2 (16 lanes/clk/SM) and the FMA pipe work in parallel.  Warps whose
+//                 shift would leave the safe exponent range keep an online max with LAZY rescaling of O in TMEM.
+//   epilogue    : map 1 passes lambda * O_1 / l_1 through shared memory; map 0 forms the difference, the head-wise RMSNorm
+//                 (one thread owns the whole 2HD row) and stores bf16.
+// TMEM: 2 x (64 score + 2HD(+16) output columns) -> 256 columns for HD <= 32 (two CTAs per SM), 512 for HD = 64.
+#include "tc_ptx.cuh"
+#include <cstdlib>
+#include <type_traits>
+
+namespace {
+using namespace tcx;
+constexpr int QT = 128, KT = 64, NTH = 320, STAGES = 3;
+
+template <int HD>
+struct DCfg {
+  static constexpr int DV = 2 * HD;
+  static constexpr int KQ = HD < 16 ? 16 : HD;             // contraction depth of Q K^T
+  static constexpr int QB = KQ / 8;                         // 16-byte column blocks per Q / K row (incl. the zero block)
+  static constexpr bool ONES = HD <= 16;                    // row sums on the tensor pipe
+  static constexpr int NO = DV + (ONES ? 16 : 0);           // N of the P V MMA = output columns per map
+  static constexpr int VB = NO / 8;                         // 16-byte column blocks of the V operand (incl. ones / zeros)
+  static constexpr int Q_BYTES = 2 * QB * QT * 16;          // both maps
+  static constexpr int K_BYTES = 2 * QB * KT * 16;
+  static constexpr int V_BYTES = VB * KT * 16;
+  static constexpr int STAGE = K_BYTES + V_BYTES;
+  static constexpr int P_BYTES = QT * KT * 2;               // per map
+  static constexpr int NOP = (NO + 31) & ~31;               // per-map column stride keeps every region 32-column aligned
+  static constexpr int TCOLS = 2 * (KT + NOP);
+  static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
+  static constexpr int X_BYTES = DV * QT * 4;               // epilogue exchange [DV][128] fp32 (aliases the K/V ring)
+  static constexpr int RING = STAGES * STAGE > X_BYTES ? STAGES * STAGE : X_BYTES;
+  static constexpr int PBUF = HD == 32 ? 1 : 2;             // P buffers per map (HD = 32: one, so that two CTAs fit an SM)
+  static constexpr int SMEM = Q_BYTES + RING + 2 * PBUF * P_BYTES + 256 + 1024;
+};
+
+struct DaParams {
+  bf16* out;
+  const float* kmax;         // [B, 2*heads] max key norm per map, or NULL (online max everywhere)
+  int N, heads;
+  float scale_log2, lambda, eps, mult, dv_real;
+};
+
+// two exponentials on the FMA pipe (packed fp32): Cody-Waite split + cubic minimax of 2^f on [-0.5, 0.5], rel. err < 1.1e-4
+__device__ __forceinline__ void poly_exp2_x2(f32x2 x, float& e0, float& e1) {
+  const f32x2 magic = pk2(12582912.f, 12582912.f), one = pk2(1.f, 1.f), neg = pk2(-1.f, -1.f);
+  // x is finite and >= -120 here: only used with the fixed (bounded) shift on full tiles, so no clamp is needed
+  const f32x2 t = ffma2(x, one, magic);
+  const f32x2 f = ffma2(ffma2(magic, neg, t), neg, x);
+  f32x2 p = ffma2(pk2(0.0555041086f, 0.0555041086f), f, pk2(0.2402264923f, 0.2402264923f));
+  p = ffma2(p, f, pk2(0.6931471806f, 0.6931471806f));
+  p = ffma2(p, f, one);
+  float p0, p1, t0, t1;
+  upk2(p, p0, p1); upk2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+template <int HD, int PP>
+__global__ void __launch_bounds__(NTH, DCfg<HD>::TMEM_COLS <= 256 ? 2 : 1)
+diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const DaParams p) {
+  pdl_prologue();
+  using C = DCfg<HD>;
+  constexpr int DV = C::DV, QB = C::QB, NO = C::NO;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+  const int E = 2 * p.heads * HD;                       // width of the q block (= k block) of a token row
+  const uint32_t sP = sbase;                            // [map][buffer] x 16 KB, 1024-aligned (SWIZZLE_128B tiles)
+  const uint32_t sQ = sP + 2 * C::PBUF * C::P_BYTES;
+  const uint32_t sKV = sQ + C::Q_BYTES;
+  const uint32_t bar = sKV + C::RING;
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8 + s * 8; };
+  auto kv_empty = [&](int s) { return bar + 8 + (STAGES + s) * 8; };
+  const uint32_t s_full = bar + 8 + 2 * STAGES * 8;      // [2 maps]
+  const uint32_t s_empty = s_full + 16;
+  const uint32_t p_full = s_empty + 16;                  // [2 maps][2 buffers]
+  const uint32_t p_empty = p_full + 32;
+  const uint32_t o_ready = p_empty + 32;                 // [2 maps] once per key tile
+  const uint32_t o_final = o_ready + 16;
+  const uint32_t tmem_slot = o_final + 8;
+  const int nt = (p.N + KT - 1) / KT;
+
+  // constant blocks: zeros for the padded K chunk of head_dim 8, ones / zeros columns appended to V (every stage)
+  if (HD < 16) {
+    for (int i = threadIdx.x; i < 2 * QT; i += NTH) {                 // Q: block 1 of each map
+      const int mp = i / QT, r = i % QT;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sQ + (mp * QB + 1) * QT * 16 + r * 16), "r"(0u) : "memory");
+    }
+    for (int i = threadIdx.x; i < STAGES * 2 * KT; i += NTH) {        // K: block 1 of each map, every stage
+      const int s = i / (2 * KT), mp = (i / KT) % 2, r = i % KT;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(sKV + s * C::STAGE + (mp * QB + 1) * KT * 16 + r * 16), "r"(0u) : "memory");
+    }
+  }
+  if (C::ONES) {
+    for (int i = threadIdx.x; i < STAGES * KT; i += NTH) {
+      const int s = i / KT, r = i % KT;
+      const uint32_t vb = sKV + s * C::STAGE + C::K_BYTES;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%2,%2};" ::"r"(vb + (DV / 8) * KT * 16 + r * 16), "r"(0x00003F80u), "r"(0u) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(vb + (DV / 8 + 1) * KT * 16 + r * 16), "r"(0u) : "memory");
+    }
+  }
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 4);
+      for (int k = 0; k < 2; k++) { mbar_init(p_full + 8 * (2 * i + k), 4); mbar_init(p_empty + 8 * (2 * i + k), 1); }
+      mbar_init(o_ready + 8 * i, 1);
+    }
+    mbar_init(o_final, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // TMEM columns of map m: scores at m*(KT+NO), outputs (+ row-sum block) right behind them
+  auto t_s = [&](int m) { return tmem_base + m * (KT + C::NOP); };
+  auto t_o = [&](int m) { return tmem_base + m * (KT + C::NOP) + KT; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * (HD / 8) * QT * 16);
+      for (int mp = 0; mp < 2; mp++)
+        for (int c = 0; c < HD / 8; c++)
+          tma_load_3d(sQ + (mp * QB + c) * QT * 16, &tmQ, q_full, (2 * head + mp) * HD + c * 8, q0, b);
+      for (int j = 0; j < nt; j++) {
+        const int s = j % STAGES;
+        mbar_wait(kv_empty(s), ((j / STAGES) & 1) ^ 1);
+        const uint32_t sk = sKV + s * C::STAGE, sv = sk + C::K_BYTES;
+        mbar_arrive_expect_tx(kv_full(s), (2 * (HD / 8) + DV / 8) * KT * 16);
+        for (int mp = 0; mp < 2; mp++)
+          for (int c = 0; c < HD / 8; c++)
+            tma_load_3d(sk + (mp * QB + c) * KT * 16, &tmKV, kv_full(s), E + (2 * head + mp) * HD + c * 8, j * KT, b);
+        for (int c = 0; c < DV / 8; c++) tma_load_3d(sv + c * KT * 16, &tmKV, kv_full(s), 2 * E + head * DV + c * 8, j * KT, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(NO >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      auto issue_qk = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(kv_full(s), (j / STAGES) & 1);
+        const uint32_t sk = sKV + s * C::STAGE;
+        for (int mp = 0; mp < 2; mp++) {
+          mbar_wait(s_empty + 8 * mp, (j & 1) ^ 1);                   // softmax of map mp holds S(j-1) in registers
+          tc_fence_after();
+          // K-major, no swizzle: 8-row groups 128 B apart (SBO), 16-byte K chunks one block apart (LBO)
+          const uint64_t ad = make_desc(sQ + mp * QB * QT * 16, QT * 16, 128, 0);
+          const uint64_t bd = make_desc(sk + mp * QB * KT * 16, KT * 16, 128, 0);
+#pragma unroll
+          for (int k = 0; k < C::KQ / 16; k++)
+            umma_f16(t_s(mp), ad + (uint64_t)((2 * k * QT * 16) >> 4), bd + (uint64_t)((2 * k * KT * 16) >> 4), idesc_qk, k != 0);
+          umma_commit(s_full + 8 * mp);
+        }
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < nt; j++) {
+        if (j + 1 < nt) issue_qk(j + 1);
+        const int s = j % STAGES;
+        const uint32_t sv = sKV + s * C::STAGE + C::K_BYTES;
+        for (int mp = 0; mp < 2; mp++) {
+          const int pb = C::PBUF == 2 ? (j & 1) : 0, pu = C::PBUF == 2 ? (j >> 1) : j;
+          mbar_wait(p_full + 8 * (2 * mp + pb), pu & 1);
+          tc_fence_after();
+          const uint64_t ad = desc_k(sP + (C::PBUF * mp + pb) * C::P_BYTES);
+          // MN-major, no swizzle: 8-key groups 128 B apart (LBO), 8-column blocks one block apart (SBO)
+          const uint64_t bd = make_desc(sv, 128, KT * 16, 0);
+#pragma unroll
+          for (int k = 0; k < KT / 16; k++) umma_f16(t_o(mp), ad + (uint64_t)(2 * k), bd + (uint64_t)((k * 16 * 16) >> 4), idesc_pv, (j | k) != 0);
+          umma_commit(p_empty + 8 * (2 * mp + pb));
+          umma_commit(o_ready + 8 * mp);
+        }
+        umma_commit(kv_empty(s));
+      }
+      umma_commit(o_final);
+    }
+  } else {
+    // ===================== softmax: warps 2..5 -> map 0, warps 6..9 -> map 1; one thread per query row =====================
+    const int mp = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t ts = t_s(mp) + lane_off, to = t_o(mp) + lane_off;
+    const float sc = p.scale_log2;
+    // ---- fixed softmax shift |q_r| * kmax (log2 units) when it stays inside the safe exponent range for the whole warp ----
+    float m = -INFINITY, l = 0.f;
+    bool bounded = false;
+    mbar_wait(q_full, 0);
+    if (p.kmax != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; c++) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(sQ + (mp * QB + c) * QT * 16 + row * 16));
+        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float a = __uint_as_float(w[i] << 16), bq = __uint_as_float(w[i] & 0xffff0000u);
+          ss = fmaf(a, a, fmaf(bq, bq, ss));
+        }
+      }
+      const float km = p.kmax[(long long)b * (2 * p.heads) + 2 * head + mp] * sc * 1.0001f;
+      const float bound = sqrtf(ss) * km + 1e-3f;
+      bounded = __all_sync(0xffffffffu, bound < 60.f);
+      if (bounded) m = bound;
+    }
+    const uint32_t prow0 = sP + C::PBUF * mp * C::P_BYTES + row * 128;
+    // exponentials of 32 scores (one TMEM load) -> bf16 -> 4 swizzled 16-byte chunks of this row's P tile; PPX of every 4
+    // pairs on the FMA pipe, the rest on MUFU
+    auto exp_store = [&](auto ppx_tag, const uint32_t (&v)[32], uint32_t prow, int half, float neg_m, float& lsum) {
+      constexpr int PPX = decltype(ppx_tag)::value;
+      const f32x2 sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const f32x2 x = ffma2(pk2(__uint_as_float(v[c * 8 + 2 * i]), __uint_as_float(v[c * 8 + 2 * i + 1])), sc2, nm2);
+          float e0, e1;
+          if (i < PPX) {
+            poly_exp2_x2(x, e0, e1);
+          } else {
+            float x0, x1;
+            upk2(x, x0, x1);
+            e0 = ex2(x0); e1 = ex2(x1);
+          }
+          if (!C::ONES) { l0 += trunc_bf16(e0); l1 += trunc_bf16(e1); }
+          w[i] = pack2_trunc(e0, e1);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4)), "r"(w[0]),
+                     "r"(w[1]), "r"(w[2]), "r"(w[3])
+                     : "memory");
+      }
+      if (!C::ONES) lsum += l0 + l1;
+    };
+    for (int j = 0; j < nt; j++) {
+      const int nvalid = p.N - j * KT;
+      const int pb = C::PBUF == 2 ? (j & 1) : 0, pu = C::PBUF == 2 ? (j >> 1) : j;
+      const uint32_t prow = prow0 + pb * C::P_BYTES;
+      const uint32_t pf = p_full + 8 * (2 * mp + pb), pe = p_empty + 8 * (2 * mp + pb);
+      mbar_wait(s_full + 8 * mp, j & 1);
+      tc_fence_after();
+      if (bounded) {
+        // fixed shift: no maximum, no rescale; two independent halves of 32 scores keep the register footprint small
+        mbar_wait(pe, (pu & 1) ^ 1);                                 // the P V MMA that last read this P buffer has retired
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          uint32_t v[32];
+          tmem_ld32(ts + half * 32, v);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + 8 * mp);            // scores are in registers: the next Q K^T may overwrite them
+          }
+          if (nvalid < KT) {
+#pragma unroll
+            for (int c = 0; c < 32; c++)
+              if (half * 32 + c >= nvalid) v[c] = 0xff800000u;        // -inf: TMA zero-filled the keys past the end
+            exp_store(std::integral_constant<int, 0>{}, v, prow, half, -m, l);
+          } else {
+            exp_store(std::integral_constant<int, PP>{}, v, prow, half, -m, l);
+          }
+        }
+      } else {
+        uint32_t lo[32], hi[32];
+        tmem_ld32(ts, lo);
+        tmem_ld32(ts + 32, hi);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + 8 * mp);
+        if (nvalid < KT) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) {
+            if (c >= nvalid) lo[c] = 0xff800000u;
+            if (32 + c >= nvalid) hi[c] = 0xff800000u;
+          }
+        }
+        float mx0 = __uint_as_float(lo[0]), mx1 = __uint_as_float(lo[1]), mx2 = __uint_as_float(hi[0]), mx3 = __uint_as_float(hi[1]);
+#pragma unroll
+        for (int c = 2; c < 32; c += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(lo[c])); mx1 = fmaxf(mx1, __uint_as_float(lo[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(hi[c])); mx3 = fmaxf(mx3, __uint_as_float(hi[c + 1]));
+        }
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc);
+        if (j == 0) {
+          m = m_new;
+        } else if (__any_sync(0xffffffffu, m_new > m + 8.f)) {       // lazy rescale, warp-uniform
+          const float corr = ex2(m - m_new);
+          m = m_new;
+          l *= corr;
+          mbar_wait(o_ready + 8 * mp, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < NO; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(to + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st16(to + c0, o);
+          }
+          tmem_st_wait();
+        }
+        mbar_wait(pe, (pu & 1) ^ 1);
+        exp_store(std::integral_constant<int, 0>{}, lo, prow, 0, -m, l);
+        exp_store(std::integral_constant<int, 0>{}, hi, prow, 1, -m, l);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pf);
+    }
+    // ---- epilogue ----
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    float o[DV];
+#pragma unroll
+    for (int c0 = 0; c0 < DV; c0 += 16) {
+      uint32_t t[16];
+      tmem_ld16(to + c0, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; i++) o[c0 + i] = __uint_as_float(t[i]);
+    }
+    if (C::ONES) {
+      uint32_t t[16];
+      tmem_ld16(to + DV, t);
+      tmem_ld_wait();
+      l = __uint_as_float(t[0]);
+    }
+    const float inv = 1.f / l;
+    float* xch = reinterpret_cast<float*>(smem_raw + (sKV - smem_u32(smem_raw)));      // [DV][128] fp32 (the K/V ring is idle now)
+    if (mp == 1) {
+      const float f = p.lambda * inv;
+#pragma unroll
+      for (int c = 0; c < DV; c++) xch[c * QT + row] = o[c] * f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");                    // the eight softmax warps
+    if (mp == 0) {
+      float ssq = 0.f;
+#pragma unroll
+      for (int c = 0; c < DV; c++) {
+        o[c] = o[c] * inv - xch[c * QT + row];
+        ssq = fmaf(o[c], o[c], ssq);
+      }
+      const float r = rsqrtf(ssq / p.dv_real + p.eps) * p.mult;
+      const int n = q0 + row;
+      if (n < p.N) {
+        bf16* op = p.out + ((long long)b * p.N + n) * ((long long)p.heads * DV) + head * DV;
+#pragma unroll
+        for (int c = 0; c < DV; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = o[c + i] * r;
+          stv<8>(op + c, v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+template <int HD, int PP>
+int launch(const bf16* qkv, bf16* out, int B, int N, int heads, float lambda, float eps, float mult, const float* kmax, cudaStream_t s) {
+  using C = DCfg<HD>;
+  const long long row = 4LL * heads * HD + (long long)heads * C::DV;     // [ q: 2h x HD | k: 2h x HD | v: h x 2HD ]
+  CUtensorMap tmQ, tmKV;
+  if (encode3(&tmQ, qkv, row, N, B, row, (long long)N * row, 8, QT, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  if (encode3(&tmKV, qkv, row, N, B, row, (long long)N * row, 8, KT, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  DaParams p;
+  p.out = out; p.kmax = kmax; p.N = N; p.heads = heads;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+  p.lambda = lambda; p.eps = eps; p.mult = mult; p.dv_real = (float)C::DV;
+  auto kern = diffattn_tc_kernel<HD, PP>;
+  static std::once_flag once;
+  std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); });
+  dim3 grid(cdiv(N, QT), heads, B);
+  kern<<<grid, NTH, C::SMEM, s>>>(tmQ, tmKV, p);
+  CENET_LAUNCH_CHECK("diffattn_tc");
+  return 0;
+}
+}  // namespace
+
+// Called by cenet_diffattn_flash (attn_flash.cu) for the natural (unpadded) layouts.  Returns 1 when this kernel does not
+// apply (the caller falls back to the mma.sync kernel), 0 on success, -1 on error.
+int cenet_diffattn_tc(const void* qkv, void* out, int B, int N, int heads, int hd, float lambda, float eps, float mult,
+                      const float* kmax, cudaStream_t s) {
+  static const int mode = getenv("CENET_B200_DIFFATTN_TC") ? atoi(getenv("CENET_B200_DIFFATTN_TC")) : 1;
+  static const int pp = getenv("CENET_DA_TC_POLY") ? atoi(getenv("CENET_DA_TC_POLY")) : 2;
+  if (mode == 0) return 1;
+  if ((((uintptr_t)qkv | (uintptr_t)out) & 15) != 0 || B > 65535 || heads > 65535) return 1;
+  const bf16* q = (const bf16*)qkv;
+  bf16* o = (bf16*)out;
+#define DA_GO(HD_)                                                                              \
+  do {                                                                                          \
+    if (pp == 0) return launch<HD_, 0>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
+    if (pp == 1) return launch<HD_, 1>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
+    if (pp == 3) return launch<HD_, 3>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
+    return launch<HD_, 2>(q, o, B, N, heads, lambda, eps, mult, kmax, s);                       \
+  } while (0)
+  switch (hd) {
+    case 8: DA_GO(8);
+    case 16: DA_GO(16);
+    case 32: DA_GO(32);
+    case 64: DA_GO(64);
+    default: return 1;
+  }
+#undef DA_GO
+}

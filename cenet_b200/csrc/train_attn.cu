@@ -12,6 +12,8 @@
 // key-parallel kernel for dK / dV (which loops over the vdiv maps that share its V head) -> deterministic.
 #include "train_common.cuh"
 
+bool cenet_attn_tc_eligible(const cenet_attn_tc_args* a);   // attn_tc.cu
+
 namespace {
 constexpr int FT = 128;          // threads per CTA (4 warps x 16 rows)
 constexpr int BQ = 64, BKEY = 64;
@@ -758,6 +760,15 @@ extern "C" int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long
   CENET_REQUIRE(lse, "cenet_flash_fwd: null lse");
   if (check_flash(a, dqk, dv, B)) return -1;
   if (B == 0) return 0;
+  if (dqk == dv && vdiv == 1 && (dqk == 64 || dqk == 128)) {
+    // head widths the 5th-gen tensor core can tile: tcgen05 / TMEM / TMA forward (attn_tc.cu), LSE in log2 units for the backward
+    cenet_attn_tc_args t;
+    t.q = Q; t.k = K; t.v = V; t.o = O; t.lse = lse;
+    t.ldq = ldq; t.ldk = ldk; t.ldv = ldv; t.ldo = ldo;
+    t.bq = (long long)Nq * ldq; t.bk = (long long)Nk * ldk; t.bv = (long long)Nk * ldv; t.bo = (long long)Nq * ldo;
+    t.B = B; t.heads = maps; t.Nq = Nq; t.Nk = Nk; t.D = dqk; t.scale = scale; t.lse_base2 = 1;
+    if (cenet_attn_tc_eligible(&t)) return cenet_attn_tc(&t, st);
+  }
   dim3 grid(cdiv(Nq, BQ), maps, B);
   FLASH_DISPATCH(dqk, dv, (flash_fwd_kernel<DQK, DV><<<grid, FT, 0, to_stream(st)>>>(a)));
   CENET_LAUNCH_CHECK("flash_fwd");

@@ -462,7 +462,9 @@ class Engine:
     def _nonlocal_core(self, tpg, B, N, Cc, key):
         """nlb.py:116-137: tpg [B*N,3C] = theta|phi|g -> att [B*N,C]"""
         att = self.buf(key + ".att", (B * N, Cc))
-        if self.use_flash and Cc in (64, 128):
+        if self.use_flash and Cc % 64 == 0 and Cc <= 1024:
+            # tcgen05 flash attention (attn_tc.cu): d = 64 / 128 with a resident Q tile, wider heads (320, 512 at the coarse
+            # decoder levels) with the contraction streamed in 64-column blocks -- nothing N x N is materialised
             ops.nonlocal_flash(tpg, att, B, N, Cc, Cc ** -0.5)
         else:
             S = self.buf(key + ".S", (B, N, N))

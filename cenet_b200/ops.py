@@ -232,7 +232,7 @@ def attn_tc(q, k, v, o, *, B, heads, Nq, Nk, D, scale, ldq, ldk, ldv, ldo, bq, b
     a.q, a.k, a.v, a.o = _p(q) + 2 * q_off, _p(k) + 2 * k_off, _p(v) + 2 * v_off, _p(o) + 2 * o_off
     a.lse = _f32(lse, "lse")
     a.ldq, a.ldk, a.ldv, a.ldo, a.bq, a.bk, a.bv, a.bo = ldq, ldk, ldv, ldo, bq, bk, bv, bo
-    a.B, a.heads, a.Nq, a.Nk, a.D, a.scale = B, heads, Nq, Nk, D, scale
+    a.B, a.heads, a.Nq, a.Nk, a.D, a.scale, a.lse_base2 = B, heads, Nq, Nk, D, scale, 0
     import ctypes
     L.call("cenet_attn_tc", ctypes.byref(a), _stream())
     return o

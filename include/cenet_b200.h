@@ -184,7 +184,8 @@ int cenet_stem5x5(const void* x, int x_dtype, const float* w1, const float* b1, 
 int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls,
                                cenet_stream_t s);
 
-/* ---- tcgen05 flash attention, head width 64 or 128 (nlb.py:116-137; pvtv2.py:98-103) ---------------------------------------
+/* ---- tcgen05 flash attention, head width 64 or 128, or ONE head of width 192..1024 (multiple of 64; lse must be NULL)
+ *      (nlb.py:116-137; pvtv2.py:98-103) ------------------------------------------------------------------------------------
  * o[b, n, h*D + :] = softmax_k( q[b,n,h*D+:] . k[b,k,h*D+:] * scale ) v[b,k,h*D+:]   for n < Nq, k < Nk, bf16 in / out, fp32
  * accumulation in TMEM; nothing Nq x Nk is written to HBM.  ld*: row pitches, b*: per-image strides (elements, multiples
  * of 8); pointers 16-byte aligned.  lse (nullable): fp32 [B, heads, Nq] natural log-sum-exp of the scaled scores. */
@@ -194,6 +195,7 @@ typedef struct {
   long long bq, bk, bv, bo;
   int B, heads, Nq, Nk, D;
   float scale;
+  int lse_base2;                  /* 1: lse in log2 units (what cenet_flash_bwd reads); 0: natural log */
 } cenet_attn_tc_args;
 int cenet_attn_tc(const cenet_attn_tc_args* a, cenet_stream_t s);
 

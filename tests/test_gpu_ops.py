@@ -348,7 +348,7 @@ def test_diffattn_flash(E, heads, N):
     assert rel(out_b, out) < 2e-2
 
 
-@pytest.mark.parametrize("C,N", [(64, 3136), (128, 784), (64, 100)])
+@pytest.mark.parametrize("C,N", [(64, 3136), (128, 784), (64, 100), (320, 196), (512, 49), (320, 1024), (192, 300)])
 def test_nonlocal_flash(C, N):
     from cenet_b200 import ops
     B = 2
