@@ -122,10 +122,8 @@ __device__ __forceinline__ void softmax_role(uint32_t tmem_base, uint32_t sP, co
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) e[i] = ex2(fmaf(__uint_as_float(sv[c * 8 + i]), sc, nm));
-#pragma unroll
-        for (int i = 0; i < 8; i++) e[i] = trunc_bf16(e[i]);          // the row sum is formed from the values the MMA will see
         l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
-        const uint32_t w0 = pack2_trunc(e[0], e[1]), w1 = pack2_trunc(e[2], e[3]), w2 = pack2_trunc(e[4], e[5]), w3 = pack2_trunc(e[6], e[7]);
+        const uint32_t w0 = pack2(e[0], e[1]), w1 = pack2(e[2], e[3]), w2 = pack2(e[4], e[5]), w3 = pack2(e[6], e[7]);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)((c ^ (row & 7)) << 4)), "r"(w0), "r"(w1),
                      "r"(w2), "r"(w3)
                      : "memory");

@@ -256,8 +256,8 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             upk2(x, x0, x1);
             e0 = ex2(x0); e1 = ex2(x1);
           }
-          if (!C::ONES) { l0 += trunc_bf16(e0); l1 += trunc_bf16(e1); }
-          w[i] = pack2_trunc(e0, e1);
+          if (!C::ONES) { l0 += e0; l1 += e1; }
+          w[i] = pack2(e0, e1);
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4)), "r"(w[0]),
                      "r"(w[1]), "r"(w[2]), "r"(w[3])
@@ -425,7 +425,7 @@ int launch(const bf16* qkv, bf16* out, int B, int N, int heads, float lambda, fl
 int cenet_diffattn_tc(const void* qkv, void* out, int B, int N, int heads, int hd, float lambda, float eps, float mult,
                       const float* kmax, cudaStream_t s) {
   static const int mode = getenv("CENET_B200_DIFFATTN_TC") ? atoi(getenv("CENET_B200_DIFFATTN_TC")) : 1;
-  static const int pp = getenv("CENET_DA_TC_POLY") ? atoi(getenv("CENET_DA_TC_POLY")) : 2;
+  static const int pp = getenv("CENET_DA_TC_POLY") ? atoi(getenv("CENET_DA_TC_POLY")) : 1;
   if (mode == 0) return 1;
   if ((((uintptr_t)qkv | (uintptr_t)out) & 15) != 0 || B > 65535 || heads > 65535) return 1;
   const bf16* q = (const bf16*)qkv;

@@ -14,13 +14,19 @@
 // Convolution mode (stride 1, "same" padding): the M tile is an 8 x 16 pixel patch of one image; for each filter
 // tap the A k-block is the SAME 4-D TMA box shifted by (kh-pad, kw-pad); out-of-image elements are zero-filled by
 // the TMA unit, so there is no im2col buffer and no bounds logic in the kernel.
+// Halo mode (conv == 2; the OutHead 5x5 / 3x3 convs): the M tile is a 16 x 8 pixel patch and its (16+2p) x (8+2p) HALO is
+// fetched ONCE per tile as Cin/8 TMA boxes of 8 channels -> [channel block][halo pixel][16 B] = the tensor core's no-swizzle
+// K-major core-matrix layout.  A filter tap is then only a different START ADDRESS of the A descriptor ((kh*Wh + kw) * 16 B;
+// 8 pixels of a tile row are one core matrix, tile rows are SBO = Wh*16 B apart, channel blocks LBO apart), so the 25 (9)
+// taps re-read shared memory instead of re-fetching the tile from L2 25 (9) times.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace {
 constexpr int BM = 128;
-constexpr int TILE_H = 8, TILE_W = 16;   // conv-mode M tile (pixels)
+constexpr int TILE_H = 8, TILE_W = 16;   // conv-mode M tile (pixels); halo mode uses 16 x 8
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +96,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
          ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
 }
 
+// no-swizzle K-major descriptor: 8-row groups `sbo` bytes apart, 16-byte K chunks `lbo` bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
 struct TcParams {
   int M, N, K;
   int bn;            // N tile (multiple of 16, <= 256)
@@ -103,6 +115,9 @@ struct TcParams {
   int n_epi;         // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating column chunks)
   // conv mode
   int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
+  int tile_h, tile_w;  // M tile in pixels: 8 x 16 (shifted boxes) or 16 x 8 (halo mode)
+  int halo, Hh, Wh;    // halo mode: halo tile extent
+  int ablk;            // bytes of one 8-channel block of a halo tile: Hh*Wh*16 rounded up to 128 (TMA destination alignment)
   EpiParams epi;
   int epi_vec;       // every epilogue operand is 16-byte addressable -> smem-transposed, vectorised epilogue
   int epi_fast;      // 1: C = bf16(acc + bias); 2: C = bf16(acc + bias + res1)  (most Linear layers) -- compact code path
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
+  const uint32_t a_bytes = p.halo ? (uint32_t)(((p.Cin / 8) * p.ablk + 1023) & ~1023) : BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
   const uint32_t wblk = (w_bytes + 1023u) & ~1023u;
   const uint32_t wres_bytes = p.w_resident ? (p.splits > 1 ? p.kb_per_split : p.num_kb) * wblk : 0;   // k-blocks one CTA walks
   const uint32_t stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h;
       img = t / p.tiles_h;
-      h0 = th * TILE_H; w0 = tw * TILE_W;
+      h0 = th * p.tile_h; w0 = tw * p.tile_w;
     } else {
       m0 = tile * BM;
     }
@@ -188,25 +203,37 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
           tma_load_2d(sbase + (kb - kb_begin) * wblk, &tmW, wfull_bar, kcoord, n0);
         }
       }
-      uint32_t it = 0;
+      // ring position kept incrementally (no integer division on the issue path: one thread feeds the whole CTA)
+      int s = 0;
+      uint32_t ph = 0;
+      auto advance = [&]() { if (++s == p.stages) { s = 0; ph ^= 1; } };
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
         int m0, img, h0, w0;
         tile_coords(tile, m0, img, h0, w0);
-        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        if (p.halo) {                                      // one stage = the whole halo tile, Cin/8 boxes of 8 channels
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = ring_base + s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)((p.Cin / 8) * p.Hh * p.Wh * 16));
+          const uint32_t ablk = (uint32_t)p.ablk;
+          for (int cb = 0; cb < p.Cin / 8; cb++) tma_load_4d(sa + cb * ablk, &tmA, full_bar(s), cb * 8, w0 - p.pad, h0 - p.pad, img);
+          advance();
+          continue;
+        }
+        int tap = 0, cb = 0, kh = 0, kw = 0;               // conv mode: (tap, channel block) of the current k-block
+        if (p.conv && kb_begin) { tap = kb_begin / p.cblks; cb = kb_begin % p.cblks; kh = tap / p.KW; kw = tap % p.KW; }
+        for (int kb = kb_begin; kb < kb_end; kb++) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = ring_base + s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), a_bytes + (p.w_resident ? 0 : w_bytes));
           if (p.conv) {
-            const int tap = kb / p.cblks, cb = kb % p.cblks;
-            const int kh = tap / p.KW, kw = tap % p.KW;
             tma_load_4d(sa, &tmA, full_bar(s), cb * p.bk, w0 + kw - p.pad, h0 + kh - p.pad, img);
             if (!p.w_resident) tma_load_2d(sa + a_bytes, &tmW, full_bar(s), tap * p.Cin + cb * p.bk, n0);
+            if (++cb == p.cblks) { cb = 0; tap++; if (++kw == p.KW) { kw = 0; kh++; } }
           } else {
             tma_load_2d(sa, &tmA, full_bar(s), kb * p.bk, m0);
             if (!p.w_resident) tma_load_2d(sa + a_bytes, &tmW, full_bar(s), kb * p.bk, n0);
           }
+          advance();
         }
       }
     }
@@ -218,25 +245,58 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       const uint32_t layout_type = p.bk == 64 ? 2u : 4u;
       const uint32_t sbo = p.bk == 64 ? 1024u : 512u;
       if (p.w_resident) { mbar_wait(wfull_bar, 0); tc_fence_after(); }
-      uint32_t it = 0, i = 0;
+      uint32_t i = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      auto advance = [&]() { if (++s == p.stages) { s = 0; ph ^= 1; } };
+      const uint32_t kmma = (uint32_t)p.bk / 16;              // k16 steps per k-block (2 or 4)
+      const uint64_t wstep = (uint64_t)(wblk >> 4);           // descriptor start-address units (16 B) per resident weight k-block
       for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, i++) {
         const uint32_t as = i & 1, use = i >> 1;
         mbar_wait(tempty_bar + 8 * as, (use & 1) ^ 1);       // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
-        for (int kb = kb_begin; kb < kb_end; kb++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        if (p.halo) {
+          // every tap = the same halo tile read from a different start address: descriptors advance by ADDITIONS only
+          // (one thread issues all MMAs of the CTA; address arithmetic with divisions had made the issue loop the bottleneck)
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = ring_base + s * stage_bytes;
-          const uint32_t sw = p.w_resident ? sbase + (kb - kb_begin) * wblk : sa + a_bytes;
-          const uint64_t adesc = make_smem_desc(sa, sbo, layout_type), bdesc = make_smem_desc(sw, sbo, layout_type);
-          for (int k = 0; k < p.bk / 16; k++) {
+          const uint64_t kstepA = (uint64_t)((2u * (uint32_t)p.ablk) >> 4);          // two 8-channel blocks per k16 step
+          uint64_t a_row = make_smem_desc_ns(sa, (uint32_t)p.ablk, (uint32_t)(p.Wh * 16));
+          uint64_t b_tap = make_smem_desc(sbase, sbo, layout_type);
+          const int ksteps = p.Cin / 16;
+          uint32_t acc = 0;
+          for (int kh = 0; kh < p.KH; kh++, a_row += (uint64_t)p.Wh) {
+            uint64_t a_tap = a_row;
+            for (int kw = 0; kw < p.KW; kw++, a_tap += 1, b_tap += wstep * (uint64_t)p.cblks) {
+              uint64_t ad = a_tap, bd = b_tap;
+              uint32_t kin = 0;
+              for (int k = 0; k < ksteps; k++, ad += kstepA) {
+                umma_f16(d_tmem, ad, bd + (uint64_t)(2 * kin), idesc, acc);
+                acc = 1;
+                if (++kin == kmma) { kin = 0; bd += wstep; }
+              }
+            }
+          }
+          umma_commit(empty_bar(s));
+          advance();
+          umma_commit(tfull_bar + 8 * as);
+          continue;
+        }
+        uint64_t wdesc = make_smem_desc(sbase, sbo, layout_type);                     // resident weights: k-block kb_begin
+        for (int kb = kb_begin; kb < kb_end; kb++, wdesc += wstep) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = ring_base + s * stage_bytes;
+          const uint64_t adesc = make_smem_desc(sa, sbo, layout_type);
+          const uint64_t bdesc = p.w_resident ? wdesc : make_smem_desc(sa + a_bytes, sbo, layout_type);
+          for (uint32_t k = 0; k < kmma; k++) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte start-address field
             umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, kb != kb_begin || k != 0);
           }
           umma_commit(empty_bar(s));                           // frees the ring slot when these MMAs retire
+          advance();
         }
         umma_commit(tfull_bar + 8 * as);                       // accumulator of this tile complete
       }
@@ -260,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       tile_coords(tile, m0, img, h0, w0);
       auto row_index = [&](int r, long long& m) -> bool {
         if (p.conv) {
-          const int h = h0 + r / TILE_W, w = w0 + r % TILE_W;
+          const int h = h0 + r / p.tile_w, w = w0 + r % p.tile_w;
           m = ((long long)img * p.H + h) * p.W + w;
           return (h < p.H) && (w < p.W);
         }
@@ -515,19 +575,35 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     p.bk = a->Cin == 32 ? 32 : 64;
     p.cblks = a->Cin / p.bk;
     p.num_kb = a->KH * a->KW * p.cblks;
-    p.tiles_h = cdiv(a->H, TILE_H); p.tiles_w = cdiv(a->W, TILE_W);
+    // halo mode: the whole filter bank resident in shared memory + halo tiles of (16+2p) x (8+2p) pixels
+    static const bool halo_on = !(getenv("CENET_B200_CONV_HALO") && atoi(getenv("CENET_B200_CONV_HALO")) == 0);
+    const int wblk_h = ((pick_bn(a->N) * p.bk * 2) + 1023) & ~1023;
+    // measured (tools/one_conv.py, B=64): 5x5 32->32 0.79 -> 0.67 ms, 3x3 64->32 0.186 -> 0.176 ms, but 3x3 64->64 0.307 -> 0.336 ms
+    // (its 72 KB filter bank leaves room for one CTA per SM only) -> halo mode for narrow outputs (N <= 32)
+    p.halo = halo_on && a->KH > 1 && a->Cin % 16 == 0 && a->Cin <= 128 && pick_bn(a->N) <= 32 && a->N <= 32 &&
+             (long long)p.num_kb * wblk_h <= 120 * 1024;
+    p.tile_h = p.halo ? 16 : TILE_H; p.tile_w = p.halo ? 8 : TILE_W;
+    p.Hh = p.tile_h + 2 * a->pad; p.Wh = p.tile_w + 2 * a->pad;
+    p.ablk = (p.Hh * p.Wh * 16 + 127) & ~127;
+    p.tiles_h = cdiv(a->H, p.tile_h); p.tiles_w = cdiv(a->W, p.tile_w);
     p.num_m_tiles = a->Bimg * p.tiles_h * p.tiles_w;
     const CUtensorMapSwizzle swz = p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->Bimg};
     cuuint64_t str[3] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)a->W * a->Cin * 2, (cuuint64_t)a->H * a->W * a->Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.bk, TILE_W, TILE_H, 1};
-    if (encode_map(&tmA, a->A, 4, dims, str, box, swz)) return -1;
+    if (p.halo) {
+      cuuint32_t box[4] = {8, (cuuint32_t)p.Wh, (cuuint32_t)p.Hh, 1};
+      if (encode_map(&tmA, a->A, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    } else {
+      cuuint32_t box[4] = {(cuuint32_t)p.bk, TILE_W, TILE_H, 1};
+      if (encode_map(&tmA, a->A, 4, dims, str, box, swz)) return -1;
+    }
     cuuint64_t wd[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
     cuuint64_t ws[1] = {(cuuint64_t)a->ldw * 2};
     cuuint32_t wb[2] = {(cuuint32_t)p.bk, (cuuint32_t)p.bn};
     if (encode_map(&tmW, a->Wt, 2, wd, ws, wb, swz)) return -1;
   } else {
     p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0;
+    p.halo = 0; p.Hh = p.Wh = p.ablk = 0; p.tile_h = TILE_H; p.tile_w = TILE_W;
     p.bk = 64;
     p.num_kb = cdiv(a->K, 64);
     p.num_m_tiles = cdiv(a->M, BM);
@@ -562,20 +638,21 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   }
   const int kb_cta = p.splits > 1 ? p.kb_per_split : p.num_kb;                      // k-blocks one CTA walks
   // ---- shared-memory plan (one persistent CTA per SM, <= ~200 KB) ----
-  const int a_bytes = BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
+  const int a_bytes = p.halo ? (((p.Cin / 8) * p.ablk + 1023) & ~1023) : BM * p.bk * 2, w_bytes = p.bn * p.bk * 2;
   const int wblk = (w_bytes + 1023) & ~1023;
   p.acc_stride = (p.bn + 31) & ~31;
   // narrow-N problems are epilogue/issue-bound per CTA: two CTAs per SM (TMEM 2 x 256 columns, ~100 KB smem each);
   // wide tiles get the whole SM and eight epilogue warps
-  const int ctas_per_sm = (2 * p.acc_stride <= 256) ? 2 : 1;
+  int ctas_per_sm = (2 * p.acc_stride <= 256) ? 2 : 1;
+  if (p.halo && (long long)kb_cta * wblk + 2 * a_bytes > 88 * 1024) ctas_per_sm = 1;   // filter bank + 2 halo tiles must fit
   p.n_epi = (ctas_per_sm == 1) ? 8 : 4;
   const int slab_bytes = p.n_epi * 32 * 36 * 4;
   const int budget = (ctas_per_sm == 1 ? 200 : 100) * 1024 - slab_bytes - 1024 - 256;
-  p.w_resident = (long long)kb_cta * wblk <= (ctas_per_sm == 1 ? 96 : 56) * 1024 && p.num_m_tiles > 1;
+  p.w_resident = p.halo || ((long long)kb_cta * wblk <= (ctas_per_sm == 1 ? 96 : 56) * 1024 && p.num_m_tiles > 1);
   const int wres = p.w_resident ? kb_cta * wblk : 0;
   const int stage_bytes = a_bytes + (p.w_resident ? 0 : wblk);
   int stages = (budget - wres) / stage_bytes;
-  if (stages > 8) stages = 8;
+  if (stages > (p.halo ? 4 : 8)) stages = p.halo ? 4 : 8;
   if (stages < 1) stages = 1;                              // the ring runs ahead across tiles: 8 x 16 KB in flight per SM
   p.stages = stages;
   int cols = 32;

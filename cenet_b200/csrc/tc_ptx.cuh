@@ -102,15 +102,6 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// fp32 pair -> bf16x2 by TRUNCATION on the integer pipe (one PRMT): F2FP (cvt.rn.bf16x2.f32) issues on the same 16-lane/clk
-// XU pipe as MUFU.EX2 and capped the softmax kernels at 16 / 1.5 exponentials per clock.  The softmax row sum is formed from
-// the SAME truncated values (tensor-pipe ones column, or trunc_bf16() below), so the truncation bias cancels in O / l.
-__device__ __forceinline__ uint32_t pack2_trunc(float lo, float hi) {
-  uint32_t w;
-  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(w) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
-  return w;
-}
-__device__ __forceinline__ float trunc_bf16(float v) { return __uint_as_float(__float_as_uint(v) & 0xffff0000u); }
 // K-major SWIZZLE_128B operand (rows of 128 bytes, 8-row groups 1024 bytes apart): Q, K and P tiles
 __device__ __forceinline__ uint64_t desc_k(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |

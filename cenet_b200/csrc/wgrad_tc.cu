@@ -139,26 +139,26 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;                               // ring position kept incrementally: no integer division on the issue path
       for (int pt = blockIdx.x; pt < p.npatches; pt += gridDim.x) {
         int t = pt;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h;
         const int img = t / p.tiles_h;
         const int h0 = th * CW_TH, w0 = tw * CW_TW;
-        for (int mt = 0; mt < p.mtiles; mt++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        int tkh = 0, tkw = 0;                          // (kh, kw) of the next tap
+        for (int mt = 0; mt < p.mtiles; mt++) {
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = sbase + s * stage_bytes;
           const int ntaps = min(p.taps_per_tile, p.T - mt * p.taps_per_tile);
           mbar_arrive_expect_tx(full_bar(s), p.ybox_bytes + ntaps * p.xbox_bytes);
           tma_load_4d(sa, &tmY, full_bar(s), 0, w0, h0, img);
           for (int j = 0; j < ntaps; j++) {
-            const int tap = mt * p.taps_per_tile + j;
-            tma_load_4d(sa + p.ybox_bytes + j * p.xbox_bytes, &tmX, full_bar(s), 0, w0 + tap % p.KS - p.pad, h0 + tap / p.KS - p.pad,
-                        img);
+            tma_load_4d(sa + p.ybox_bytes + j * p.xbox_bytes, &tmX, full_bar(s), 0, w0 + tkw - p.pad, h0 + tkh - p.pad, img);
+            if (++tkw == p.KS) { tkw = 0; tkh++; }
           }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -168,12 +168,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                              ((uint32_t)(128 >> 4) << 24);
       const uint32_t xrow = p.Cin * 2, yrow = p.N * 2;                 // bytes per pixel row of a box (64 or 128)
       const uint32_t xlt = xrow == 128 ? 2u : 4u, ylt = yrow == 128 ? 2u : 4u;
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       int pi = 0;
+      const uint64_t xk = (uint64_t)((16 * xrow) >> 4), yk = (uint64_t)((16 * yrow) >> 4);   // descriptor step per 16 pixels
       for (int pt = blockIdx.x; pt < p.npatches; pt += gridDim.x, pi++) {
-        for (int mt = 0; mt < p.mtiles; mt++, it++) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int mt = 0; mt < p.mtiles; mt++) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = sbase + s * stage_bytes;
@@ -181,10 +181,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           const uint64_t adesc = make_desc_mn_sw(sa + p.ybox_bytes, p.xbox_bytes, 8 * xrow, xlt);
           const uint64_t bdesc = make_desc_mn_sw(sa, p.ybox_bytes, 8 * yrow, ylt);
           const uint32_t d_tmem = tmem_base + mt * p.N;
+#pragma unroll
           for (int k = 0; k < (CW_TH * CW_TW) / 16; k++)                // 16 pixels per UMMA: 16 rows of the boxes
-            umma_f16(d_tmem, adesc + (uint64_t)((16 * xrow * k) >> 4), bdesc + (uint64_t)((16 * yrow * k) >> 4), idesc,
-                     (pi | k) != 0);
+            umma_f16(d_tmem, adesc + xk * (uint64_t)k, bdesc + yk * (uint64_t)k, idesc, (pi | k) != 0);
           umma_commit(empty_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
       umma_commit(tfull_bar);
@@ -265,9 +266,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;                               // ring position kept incrementally: no integer division on the issue path
       for (int c = 0; c < nchunks; c++) {
-        const int s = c % p.stages;
-        const uint32_t ph = (c / p.stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t sa = sbase + s * stage_bytes;
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
         tma_load_3d(sa, &tmY, full_bar(s), n0, r0, grp);
         tma_load_3d(sa + BOX_BYTES, &tmY, full_bar(s), n0 + 64, r0, grp);
         for (int j = 0; j < xboxes; j++) tma_load_3d(sa + (2 + j) * BOX_BYTES, &tmX, full_bar(s), k0 + 64 * j, r0, grp);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -282,16 +284,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
       // D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), A and B MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
       for (int c = 0; c < nchunks; c++) {
-        const int s = c % p.stages;
-        const uint32_t ph = (c / p.stages) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = sbase + s * stage_bytes;
         const uint64_t adesc = make_desc_mn(sa, BOX_BYTES, 1024), bdesc = make_desc_mn(sa + 2 * BOX_BYTES, BOX_BYTES, 1024);
+#pragma unroll
         for (int k = 0; k < CH / 16; k++)      // 16 contraction rows = two 8-row groups = 2048 bytes = +128 in the address field
           umma_f16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (c | k) != 0);
         umma_commit(empty_bar(s));
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       umma_commit(tfull_bar);
     }
