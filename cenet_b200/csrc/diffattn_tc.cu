@@ -31,7 +31,7 @@ struct DCfg {
   static constexpr int DV = 2 * HD;
   static constexpr int KQ = HD < 16 ? 16 : HD;             // contraction depth of Q K^T
   static constexpr int QB = KQ / 8;                         // 16-byte column blocks per Q / K row (incl. the zero block)
-  static constexpr bool ONES = HD <= 16;                    // row sums on the tensor pipe
+  static constexpr bool ONES = HD == 8;                     // row sums on the tensor pipe (HD = 16: the columns go to P instead)
   static constexpr int NO = DV + (ONES ? 16 : 0);           // N of the P V MMA = output columns per map
   static constexpr int VB = NO / 8;                         // 16-byte column blocks of the V operand (incl. ones / zeros)
   static constexpr int Q_BYTES = 2 * QB * QT * 16;          // both maps
@@ -40,11 +40,15 @@ struct DCfg {
   static constexpr int STAGE = K_BYTES + V_BYTES;
   static constexpr int P_BYTES = QT * KT * 2;               // per map
   static constexpr int NOP = (NO + 31) & ~31;               // per-map column stride keeps every region 32-column aligned
-  static constexpr int TCOLS = 2 * (KT + NOP);
+  static constexpr int TCOLS = 2 * (KT + (HD != 32 ? KT / 2 : 0) + NOP);
   static constexpr int TMEM_COLS = TCOLS <= 256 ? 256 : 512;
   static constexpr int X_BYTES = DV * QT * 4;               // epilogue exchange [DV][128] fp32 (aliases the K/V ring)
   static constexpr int RING = STAGES * STAGE > X_BYTES ? STAGES * STAGE : X_BYTES;
-  static constexpr int PBUF = HD == 32 ? 1 : 2;             // P buffers per map (HD = 32: one, so that two CTAs fit an SM)
+  // P in TENSOR MEMORY (TS-mode MMA: A operand from TMEM) where the column budget allows it: the probabilities never touch
+  // shared memory (ncu on the smem version: 25 % of the smem wavefronts were P stores, 19 % the tensor core re-reading them)
+  static constexpr bool TS = HD != 32;                      // HD = 32 would need 320 columns -> one CTA per SM; it keeps P in smem
+  static constexpr int PCOLS = TS ? KT / 2 : 0;             // bf16 pairs
+  static constexpr int PBUF = TS ? 0 : (HD == 32 ? 1 : 2);  // smem P buffers per map (HD = 32: one, so that two CTAs fit an SM)
   static constexpr int SMEM = Q_BYTES + RING + 2 * PBUF * P_BYTES + 256 + 1024;
 };
 
@@ -139,9 +143,10 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // TMEM columns of map m: scores at m*(KT+NO), outputs (+ row-sum block) right behind them
-  auto t_s = [&](int m) { return tmem_base + m * (KT + C::NOP); };
-  auto t_o = [&](int m) { return tmem_base + m * (KT + C::NOP) + KT; };
+  // TMEM columns of map m: [ scores 64 | P 32 (TS mode) | outputs (+ row-sum block) ]
+  auto t_s = [&](int m) { return tmem_base + m * (KT + C::PCOLS + C::NOP); };
+  auto t_p = [&](int m) { return tmem_base + m * (KT + C::PCOLS + C::NOP) + KT; };
+  auto t_o = [&](int m) { return tmem_base + m * (KT + C::PCOLS + C::NOP) + KT + C::PCOLS; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -193,11 +198,16 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int pb = C::PBUF == 2 ? (j & 1) : 0, pu = C::PBUF == 2 ? (j >> 1) : j;
           mbar_wait(p_full + 8 * (2 * mp + pb), pu & 1);
           tc_fence_after();
-          const uint64_t ad = desc_k(sP + (C::PBUF * mp + pb) * C::P_BYTES);
           // MN-major, no swizzle: 8-key groups 128 B apart (LBO), 8-column blocks one block apart (SBO)
           const uint64_t bd = make_desc(sv, 128, KT * 16, 0);
+          if constexpr (C::TS) {
 #pragma unroll
-          for (int k = 0; k < KT / 16; k++) umma_f16(t_o(mp), ad + (uint64_t)(2 * k), bd + (uint64_t)((k * 16 * 16) >> 4), idesc_pv, (j | k) != 0);
+            for (int k = 0; k < KT / 16; k++) umma_f16_ts(t_o(mp), t_p(mp) + 8 * k, bd + (uint64_t)((k * 16 * 16) >> 4), idesc_pv, (j | k) != 0);
+          } else {
+            const uint64_t ad = desc_k(sP + (C::PBUF * mp + pb) * C::P_BYTES);
+#pragma unroll
+            for (int k = 0; k < KT / 16; k++) umma_f16(t_o(mp), ad + (uint64_t)(2 * k), bd + (uint64_t)((k * 16 * 16) >> 4), idesc_pv, (j | k) != 0);
+          }
           umma_commit(p_empty + 8 * (2 * mp + pb));
           umma_commit(o_ready + 8 * mp);
         }
@@ -211,7 +221,7 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t ts = t_s(mp) + lane_off, to = t_o(mp) + lane_off;
+    const uint32_t ts = t_s(mp) + lane_off, to = t_o(mp) + lane_off, tp = t_p(mp) + lane_off;
     const float sc = p.scale_log2;
     // ---- fixed softmax shift |q_r| * kmax (log2 units) when it stays inside the safe exponent range for the whole warp ----
     float m = -INFINITY, l = 0.f;
@@ -243,6 +253,8 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const f32x2 sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
+      uint32_t w16[16];
+#pragma unroll
       for (int c = 0; c < 4; c++) {
         uint32_t w[4];
 #pragma unroll
@@ -258,11 +270,14 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           if (!C::ONES) { l0 += e0; l1 += e1; }
           w[i] = pack2(e0, e1);
+          w16[c * 4 + i] = w[i];
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4)), "r"(w[0]),
-                     "r"(w[1]), "r"(w[2]), "r"(w[3])
-                     : "memory");
+        if constexpr (!C::TS)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4)), "r"(w[0]),
+                       "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
       }
+      if constexpr (C::TS) tmem_st16(tp + half * 16, w16);            // 32 probabilities = 16 packed columns of this row
       if (!C::ONES) lsum += l0 + l1;
     };
     for (int j = 0; j < nt; j++) {
@@ -339,7 +354,7 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         exp_store(std::integral_constant<int, 0>{}, lo, prow, 0, -m, l);
         exp_store(std::integral_constant<int, 0>{}, hi, prow, 1, -m, l);
       }
-      fence_proxy_async();
+      if constexpr (C::TS) tmem_st_wait(); else fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pf);

@@ -697,7 +697,12 @@ class Engine:
         real, timed = ops, _TimedOps(ops)
         ops = timed
         try:
+            # keep the device busy while the host enqueues: with an idle GPU the events around a small launch also contain
+            # the host's launch latency (python + ctypes + tensor-map encoding, ~15 us) and a 5 us kernel reads as 20 us
+            pad = self.buf("profile.pad", (1 << 28,), torch.uint8)
             for _ in range(steps):
+                for _ in range(48):
+                    pad.zero_()                                    # ~0.1 ms each: the host gets ~5 ms ahead of the device
                 self._run(x_in, B, H, W, None if labels else res, res if labels else None)
             torch.cuda.synchronize()
         finally:
