@@ -162,7 +162,6 @@ __device__ __forceinline__ void softmax_tile(float (&S)[KT / 8][4], uint32_t (&P
 template <int HD>
 __global__ void __launch_bounds__(256) kmax_kernel(const bf16* __restrict__ qkv, float* __restrict__ kmax, int N,
                                                    long long row, int koff) {
-  pdl_prologue();
   __shared__ float red[8];
   const int j = blockIdx.x, b = blockIdx.y;
   const bf16* kb = qkv + (long long)b * N * row + koff + j * HD;
@@ -208,7 +207,6 @@ __global__ void __launch_bounds__(NTHREADS, MINB) diffattn_flash_kernel(const bf
                                                                   int N, int heads, float dv_real, float scale_log2,
                                                                   float lambda, float eps, float mult,
                                                                   const float* __restrict__ kmax) {
-  pdl_prologue();
   using Cfg = DiffCfg<HD, DVT>;
   const int E = 2 * heads * HD;            // width of the q block (= k block)
   const int EO = heads * DVT;              // output row width
@@ -463,7 +461,6 @@ struct AttnPtrs {
 
 template <int D>
 __global__ void __launch_bounds__(NTHREADS) nonlocal_flash_kernel(const AttnPtrs a, int Nq, int N, float scale_log2) {
-  pdl_prologue();
   using Cfg = NlCfg<D>;
   constexpr int STR = Cfg::STR, CH = D / 8;
   extern __shared__ __align__(128) unsigned char smem[];

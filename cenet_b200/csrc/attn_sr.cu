@@ -14,7 +14,6 @@ constexpr int HD = 64, MAXK = 64, QT = 128;
 template <typename TQ, typename TKV, typename TO>
 __global__ void __launch_bounds__(QT) sr_attention_kernel(const TQ* __restrict__ q, const TKV* __restrict__ kv,
                                                           TO* __restrict__ out, int N, int Nk, int C, float scale) {
-  pdl_prologue();
   __shared__ __align__(16) float Ks[MAXK][HD];
   __shared__ __align__(16) float Vs[MAXK][HD];
   const int head = blockIdx.y, b = blockIdx.z;

@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(NTH, D == 64 ? 2 : 1) attn_tc_kernel(const __g
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
                                                                       const TcAttnParams p) {
-  pdl_prologue();
   using C = Cfg<D>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -315,7 +314,6 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc_wide_kernel(const __grid_const
                                                              const __grid_constant__ CUtensorMap tmK,
                                                              const __grid_constant__ CUtensorMap tmV, const TcAttnParams p,
                                                              int kqb) {
-  pdl_prologue();
   constexpr int P_BYTES = QT * KT * 2, V_BYTES = KT * 128;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -11,7 +11,6 @@ template <typename T>
 __global__ void __launch_bounds__(256) ccu_partial_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float* __restrict__ ws,
                                                           int HW, int C, int nchunk) {
-  pdl_prologue();
   __shared__ float s_max[4][64], s_mean[4][64], s_m2[4][64], s_n[4][64];
   const int tc = threadIdx.x & 63, tp = threadIdx.x >> 6;
   const int c = blockIdx.z * 64 + tc, b = blockIdx.y, chunk = blockIdx.x;
@@ -51,7 +50,6 @@ __global__ void __launch_bounds__(256) ccu_finalize_kernel(const float* __restri
                                                            const float* __restrict__ fc2, const float* __restrict__ bns,
                                                            const float* __restrict__ bnt, float* __restrict__ gate,
                                                            int B, int HW, int C, int nchunk) {
-  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C) return;
   const int c = idx % C, b = idx / C;
@@ -82,7 +80,6 @@ __global__ void __launch_bounds__(256) ccu_finalize_kernel(const float* __restri
 __global__ void __launch_bounds__(256) srm_gate_kernel(const float* __restrict__ u, float* __restrict__ gate,
                                                        const float* __restrict__ pw3, const float* __restrict__ dw27,
                                                        float bn_scale, float bn_shift, int B, int H, int W) {
-  pdl_prologue();
   __shared__ float sdw[27], spw[3];
   if (threadIdx.x < 27) sdw[threadIdx.x] = dw27[threadIdx.x];
   if (threadIdx.x < 3) spw[threadIdx.x] = pw3[threadIdx.x];
@@ -115,7 +112,6 @@ __global__ void __launch_bounds__(128) pool7_conv_kernel(const T* __restrict__ x
                                                          const float* __restrict__ w_rr, const float* __restrict__ bns,
                                                          const float* __restrict__ bnt, float slope,
                                                          float* __restrict__ pooled, int H, int W, int r) {
-  pdl_prologue();
   extern __shared__ float avg[];   // r floats
   const int bin = blockIdx.x, b = blockIdx.y;
   const int bi = bin / 7, bj = bin % 7;
@@ -141,7 +137,6 @@ __global__ void __launch_bounds__(128) pool7_conv_kernel(const T* __restrict__ x
 template <typename T>
 __global__ void __launch_bounds__(256) pool_upsample_kernel(const float* __restrict__ pooled, T* __restrict__ y,
                                                             long long ldy, int coff_y, int B, int H, int W, int r) {
-  pdl_prologue();
   const long long total = (long long)B * H * W * r;
   const bool same = (H == 49 && W == 49);
   const float s2h = 49.f / (float)H, s2w = 49.f / (float)W;   // size= semantics: in/out

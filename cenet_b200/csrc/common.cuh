@@ -8,18 +8,6 @@
 
 typedef __nv_bfloat16 bf16;
 
-// ---- programmatic dependent launch ---------------------------------------------------------------------------
-// First statement of EVERY kernel of this library.  `launch_dependents` lets the next kernel of the stream / graph be
-// scheduled as soon as all CTAs of this one are running; `wait` blocks until every prerequisite grid has completed and its
-// memory is visible.  Both are no-ops under ordinary (full) dependencies; they take effect on the kernel -> kernel edges that
-// cenet_b200/pdl.py turns into programmatic edges after CUDA-graph capture, where they hide the launch latency and ramp of
-// the ~1800 mostly small kernels of a training step.  Because every kernel waits before touching memory, completion is
-// transitive along a chain (B complete => A complete), so RAW / WAR / WAW ordering is the same as with full edges.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
 // ---- host-side error plumbing -----------------------------------------------------------------------------
 void cenet_set_error(const char* fmt, ...);
 extern std::atomic<long long> g_cenet_launches;

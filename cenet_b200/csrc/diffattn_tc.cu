@@ -77,7 +77,6 @@ __device__ __forceinline__ void poly_exp2_x2(f32x2 x, float& e0, float& e1) {
 template <int HD, int PP>
 __global__ void __launch_bounds__(NTH, DCfg<HD>::TMEM_COLS <= 256 ? 2 : 1)
 diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const DaParams p) {
-  pdl_prologue();
   using C = DCfg<HD>;
   constexpr int DV = C::DV, QB = C::QB, NO = C::NO;
   extern __shared__ __align__(1024) unsigned char smem_raw[];

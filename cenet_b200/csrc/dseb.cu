@@ -26,7 +26,6 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
                                                           T* __restrict__ z, const float* __restrict__ w_c, int C2,
                                                           int H, int W, long long nplanes, int ppb, unsigned wmagic,
                                                           const FeaScales sc, int plane_floats) {
-  pdl_prologue();
   extern __shared__ float sm[];
   // tables: for each scale: down rows (hd), down cols (wd), up rows (H), up cols (W)
   LerpTab* tab = reinterpret_cast<LerpTab*>(sm);
@@ -112,7 +111,6 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) diff_combine_kernel(T* __restrict__ P, long long npairs, long long map_elems,
                                                            float lambda) {
-  pdl_prologue();
   const long long total = npairs * map_elems;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {

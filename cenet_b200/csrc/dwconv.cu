@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const TI* __restrict__ x
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         int H, int W, int C, int dil, int up2, int act, float slope,
                                                         int nrows, TO* __restrict__ zout) {
-  pdl_prologue();
   constexpr bool FAST = sizeof(TO) == 2;
   // block = TX channel vectors x (RB rows x blockDim.y/RB pixel groups): neighbouring rows of the 3x3 window are served
   // by the same SM's L1, so each input element crosses the L2->SM fabric ~2x instead of ~4x
@@ -160,7 +159,6 @@ __global__ void __launch_bounds__(SG_T, 3) dwconv3x3_staged_kernel(const bf16* _
                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                                    int H, int W, int C, int act, float slope, bf16* __restrict__ zout,
                                                                    int rows_per_cta) {
-  pdl_prologue();
   extern __shared__ __align__(16) unsigned char sg_smem[];
   const int tid = threadIdx.x;
   const int rowB = (W + 2) * 128;                              // bytes of one staged row: pixels -1 .. W, 64 channels

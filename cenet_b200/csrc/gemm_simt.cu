@@ -18,7 +18,6 @@ struct SimtParams {
 };
 
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(const SimtParams p) {
-  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;

@@ -140,7 +140,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   warps 2-9: epilogue of the previous tile out of the other accumulator stage, overlapping the next tile's loads+MMAs
 __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
-  pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // swizzle atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,6 +368,31 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
             }
           }
+        } else if (p.epi_fast == 3) {
+          // fp32 residual stream (encoder): C = acc + bias + res1, both fp32 rows (two 16-byte accesses per lane)
+          const int cg = (lane & 3) * 8;
+          const int n = nbase + cg;
+          if (n < nlim) {
+            float bcol[8];
+            if (e.bias) ldv<8>(e.bias + n, bcol);
+            else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) bcol[j] = 0.f;
+            }
+#pragma unroll
+            for (int itr = 0; itr < 4; itr++) {
+              long long m;
+              if (!row_index(quarter * 32 + itr * 8 + (lane >> 2), m)) continue;
+              const int rr = itr * 8 + (lane >> 2);
+              const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+              const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+              float t[8];
+              ldv<8>(reinterpret_cast<const float*>(e.res1) + m * e.ldr1 + n, t);
+              float v[8] = {lo.x + bcol[0] + t[0], lo.y + bcol[1] + t[1], lo.z + bcol[2] + t[2], lo.w + bcol[3] + t[3],
+                            hi.x + bcol[4] + t[4], hi.y + bcol[5] + t[5], hi.z + bcol[6] + t[6], hi.w + bcol[7] + t[7]};
+              stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
+            }
+          }
         } else if (p.epi_fast) {
           // C = bf16(acc + bias [+ res1]); N % 8 == 0, so an 8-column group is entirely inside or outside the tile
           const int cg = (lane & 3) * 8;
@@ -542,7 +566,6 @@ bool cenet_gemm_tc_eligible(const cenet_gemm_args* a) {
 // out[m, n] = bf16( sum_z ws[z][m][n] + bias[n] ), slices added in z order (deterministic); 8 columns per thread
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int S, long long M, int N, const float* __restrict__ bias,
                                                             bf16* __restrict__ C, long long ldc) {
-  pdl_prologue();
   const int ng = N >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * ng) return;
@@ -670,6 +693,10 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
       !a->mul && !a->res2 && a->N % 8 == 0 && (!a->bias || (((uintptr_t)a->bias & 15) == 0)) &&
       (!a->res1 || (!a->res1_cscale && a->res1_scale == 1.0f)))
     p.epi_fast = a->res1 ? 2 : 1;
+  if (c_ok && a->c_dtype == CENET_F32 && a->res1 && a->res1_dtype == CENET_F32 && a->ldr1 % 4 == 0 && (((uintptr_t)a->res1 & 15) == 0) &&
+      !a->res1_cscale && a->res1_scale == 1.0f && a->alpha == 1.0f && !a->row_scale && !a->post_row_scale && !a->bias_per_row &&
+      a->act == CENET_ACT_NONE && !a->mul && !a->res2 && a->N % 8 == 0 && (!a->bias || (((uintptr_t)a->bias & 15) == 0)))
+    p.epi_fast = 3;                                          // fp32 residual stream of the encoder
   const size_t smem = (size_t)wres + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 32 + slab_bytes + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {

@@ -11,7 +11,6 @@ template <int NC>
 __global__ void __launch_bounds__(256) head_upsample_argmax_kernel(const float* __restrict__ y, float* __restrict__ logits,
                                                                    long long* __restrict__ labels, int B, int h, int w,
                                                                    int ncls_rt) {
-  pdl_prologue();
   const int ncls = NC > 0 ? NC : ncls_rt;
   const int Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)B * Ho * Wo;
@@ -67,7 +66,6 @@ __global__ void __launch_bounds__(kLossThreads) seg_loss_partial_kernel(const fl
                                                                         const long long* __restrict__ labels,
                                                                         float* __restrict__ part, int ncls, int nacc, int H,
                                                                         int W, long long npix) {
-  pdl_prologue();
   __shared__ float red[kLossThreads / 32][kAccMax];
   float acc[kAccMax];
 #pragma unroll
@@ -130,7 +128,6 @@ __global__ void __launch_bounds__(kLossThreads) seg_loss_partial_kernel(const fl
 __global__ void __launch_bounds__(128) seg_loss_finalize_kernel(const float* __restrict__ part, float* __restrict__ tot,
                                                                 float* __restrict__ loss_out, int nblk, int ncls, int nacc,
                                                                 long long npix, float w_dice, float w_ce, float w_bd) {
-  pdl_prologue();
   __shared__ float s_tot[kAccMax];
   const int nvals = nacc * ncls + 1;
   if (threadIdx.x < nvals) {
@@ -172,7 +169,6 @@ __global__ void __launch_bounds__(256) seg_loss_grad_kernel(const float* __restr
                                                             const float* __restrict__ tot, float* __restrict__ dlogits,
                                                             int ncls, int nacc, int HW, long long npix, float w_dice, float w_ce,
                                                             float w_bd, float grad_scale) {
-  pdl_prologue();
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const long long b = p / HW, q = p % HW;

@@ -7,7 +7,6 @@ namespace {
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y,
                                                            int HW, int C, int Ctot, int coff) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -24,7 +23,6 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const TI* __restrict_
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long ldy,
                                                            int HW, int C) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -43,7 +41,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TI* __restrict_
 template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) upsample2x_ac_kernel(const TI* __restrict__ x, TO* __restrict__ y, int B, int H,
                                                             int W, int C) {
-  pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W, cv = C / V;
   const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
   const float sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
@@ -78,7 +75,6 @@ template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) maxpool2_scale_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long ldy,
                                                              int coff, const float* __restrict__ wch, int B, int H,
                                                              int W, int C) {
-  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2, cv = C / V;
   const long long total = (long long)B * Ho * Wo * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -106,7 +102,6 @@ template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) affine_gate_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                                           const float* __restrict__ gate, int B, int HW, int C) {
-  pdl_prologue();
   const int cv = C / V;
   const long long total = (long long)B * HW * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -131,7 +126,6 @@ template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, TO* __restrict__ out, int B, int H, int W,
                                                      int Cin, int KH, int KW, int stride, int pad, int Ho, int Wo,
                                                      int Kpad) {
-  pdl_prologue();
   const int kv = Kpad / V;
   const int K = KH * KW * Cin;
   const long long total = (long long)B * Ho * Wo * kv;

@@ -10,7 +10,6 @@ template <typename TI, typename TO, int LPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                         const float* __restrict__ g, const float* __restrict__ b,
                                                         long long rows, int C, float eps) {
-  pdl_prologue();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -61,7 +60,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x
 // ---- in-place row softmax (materialised attention path only) --------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) softmax_rows_kernel(T* __restrict__ x, int n, long long ld) {
-  pdl_prologue();
   __shared__ float red[4];
   T* r = x + (long long)blockIdx.x * ld;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -85,7 +83,6 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(T* __restrict__ x, in
 template <typename T>
 __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x, long long rows, int C, long long ld,
                                                         int unbiased, float* __restrict__ stats) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -117,7 +114,6 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const T* __restrict__ x,
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) rmsnorm_seg_kernel(const TI* __restrict__ x, TO* __restrict__ y,
                                                           long long nseg_total, int seg, float eps, float mult) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long sidx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (sidx >= nseg_total) return;

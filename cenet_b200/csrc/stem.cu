@@ -19,7 +19,6 @@ __global__ void __launch_bounds__(256) stem5x5_kernel(const TI* __restrict__ x, 
                                                       const float* __restrict__ b1, const float* __restrict__ w3,
                                                       const float* __restrict__ b3, TO* __restrict__ o1, TO* __restrict__ r,
                                                       int H, int W, float slope) {
-  pdl_prologue();
   __shared__ __align__(16) float sw[KS * KS * CIN][OC];     // [tap*CIN + ci][oc]
   __shared__ float sx[TIN][TINW][CIN];
   const int tid = threadIdx.y * TS + threadIdx.x;

@@ -174,7 +174,6 @@ struct FlashArgs {
 // ------------------------------------------------------------------------------------------------ forward
 template <int DQK, int DV>
 __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
-  pdl_prologue();
   constexpr int KT = KTiles<DQK>::value;
   __shared__ __align__(16) bf16 sKb[KT * BKEY * (DQK + 8)];
   __shared__ __align__(16) bf16 sVb[KT * BKEY * (DV + 8)];
@@ -293,7 +292,6 @@ __global__ void __launch_bounds__(FT) flash_fwd_kernel(const FlashArgs p) {
 // ------------------------------------------------------------------------------------------------ delta = rowsum(dO * O)
 template <int DV>
 __global__ void __launch_bounds__(256) flash_delta_kernel(const FlashArgs p, long long total) {
-  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // (b, m, r)
   if (i >= total) return;
   const int r = (int)(i % p.Nq);
@@ -315,7 +313,6 @@ __global__ void __launch_bounds__(256) flash_delta_kernel(const FlashArgs p, lon
 // ------------------------------------------------------------------------------------------------ dQ
 template <int DQK, int DV>
 __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
-  pdl_prologue();
   constexpr int KT = KTiles<DQK>::value;
   __shared__ __align__(16) bf16 sKb[KT * BKEY * (DQK + 8)];
   __shared__ __align__(16) bf16 sVb[KT * BKEY * (DV + 8)];
@@ -410,7 +407,6 @@ __global__ void __launch_bounds__(FT) flash_bwd_dq_kernel(const FlashArgs p) {
 // MODE 0: dK and dV in one pass; MODE 1: dV only; MODE 2: dK only (large head dims: the two accumulators do not fit together)
 template <int DQK, int DV, int MODE>
 __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
-  pdl_prologue();
   constexpr int KT = KTiles<DQK>::value;
   __shared__ __align__(16) bf16 sQb[KT * BQ * (DQK + 8)];
   __shared__ __align__(16) bf16 sGb[KT * BQ * (DV + 8)];
@@ -554,7 +550,6 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
 // dS = P * (dP - rowsum(P * dP)), in place over dP; one warp per row
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const T* __restrict__ P, T* __restrict__ dP, long long rows, int n) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -568,7 +563,6 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const T* __restri
 
 // ------------------------------------------------------------------------------------------------ lambda, diff + RMSNorm
 __global__ void lambda_fwd_kernel(const float* q1, const float* k1, const float* q2, const float* k2, int hd, float init, float* lam) {
-  pdl_prologue();
   const int lane = threadIdx.x;
   float a = 0.f, b = 0.f;
   for (int i = lane; i < hd; i += 32) { a = fmaf(q1[i], k1[i], a); b = fmaf(q2[i], k2[i], b); }
@@ -577,7 +571,6 @@ __global__ void lambda_fwd_kernel(const float* q1, const float* k1, const float*
 }
 __global__ void lambda_bwd_kernel(const float* dlam, const float* q1, const float* k1, const float* q2, const float* k2, int hd,
                                   float* g1, float* g2, float* g3, float* g4) {
-  pdl_prologue();
   const int lane = threadIdx.x;
   float a = 0.f, b = 0.f;
   for (int i = lane; i < hd; i += 32) { a = fmaf(q1[i], k1[i], a); b = fmaf(q2[i], k2[i], b); }
@@ -596,7 +589,6 @@ constexpr int DR_MAXV = 2;
 template <typename T>
 __global__ void __launch_bounds__(256) diff_rmsnorm_fwd_kernel(const T* __restrict__ Om, const float* __restrict__ lamp, T* __restrict__ o,
                                                                long long rows, int heads, int seg, int lps, float eps, float mult) {
-  pdl_prologue();
   const int sub = threadIdx.x % lps;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lps;
   const bool live = i < rows * heads;
@@ -641,7 +633,6 @@ __global__ void __launch_bounds__(256) diff_rmsnorm_bwd_kernel(const T* __restri
                                                                const float* __restrict__ lamp, T* __restrict__ dOm, long long rows,
                                                                int heads, int seg, int lps, float eps, float mult,
                                                                float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float red[8];
   const int sub = threadIdx.x % lps;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lps;
@@ -710,7 +701,6 @@ __global__ void __launch_bounds__(256) diff_rmsnorm_bwd_kernel(const T* __restri
 
 // sum of n partials in fixed order -> out[0]
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ ws, int n, float* out) {
-  pdl_prologue();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += ws[i];

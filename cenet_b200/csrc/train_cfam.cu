@@ -9,7 +9,6 @@ namespace {
 template <typename T, int V>
 __global__ void __launch_bounds__(kColThreads) ccu_stats_kernel(const T* __restrict__ x, float* __restrict__ u, int* __restrict__ arg,
                                                                 int HW, int C, int ngrp, int nrl) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   __shared__ int sidx[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
@@ -69,7 +68,6 @@ __global__ void __launch_bounds__(kColThreads) ccu_stats_kernel(const T* __restr
 template <typename T, int V>
 __global__ void __launch_bounds__(kColThreads) ccu_dgate_kernel(const T* __restrict__ dx1, const T* __restrict__ xb, float* __restrict__ dgate,
                                                                 int HW, int C, int ngrp, int nrl) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.x * ngrp + grp) * V;
@@ -98,7 +96,6 @@ __global__ void __launch_bounds__(kColThreads) ccu_dgate_kernel(const T* __restr
 __global__ void ccu_mlp_fwd_kernel(const float* __restrict__ u, const float* __restrict__ fc1, const float* __restrict__ fc2,
                                    const float* gamma, const float* beta, float* rmean, float* rvar, long long* nbt, float momentum,
                                    float eps, float* __restrict__ gate, float* __restrict__ save, int B, int C) {
-  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && gamma && nbt) *nbt += 1;
   if (c >= C) return;
@@ -143,7 +140,6 @@ __global__ void ccu_mlp_fwd_kernel(const float* __restrict__ u, const float* __r
 __global__ void ccu_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ u, const float* __restrict__ fc1,
                                    const float* __restrict__ fc2, const float* gamma, const float* beta, const float* __restrict__ save,
                                    float* __restrict__ du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C) {
-  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float w1[9], w2[3], g1[9], g2[3];
@@ -194,7 +190,6 @@ __global__ void __launch_bounds__(256) ccu_apply_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ u, const int* __restrict__ arg,
                                                             const float* __restrict__ du, T* __restrict__ dxb, int acc, int B, int HW,
                                                             int C) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = (long long)B * HW * groups;
   const float inv = 1.f / HW;
@@ -230,7 +225,6 @@ __global__ void __launch_bounds__(256) ccu_apply_bwd_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) row_stats_arg_kernel(const T* __restrict__ x, float* __restrict__ u, int* __restrict__ arg,
                                                             long long rows, int C) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -268,7 +262,6 @@ __global__ void __launch_bounds__(256) row_stats_arg_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) row_dot_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out,
                                                       long long rows, int C) {
-  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -297,7 +290,6 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // f_pre = pwc(u) + dwc3x3(u), fg = GELU(f_pre); save[m] = (f_pre, fg); block partial sums of fg, fg^2 -> ws[blk*2 + {0,1}]
 __global__ void __launch_bounds__(256) srm_fwd_a_kernel(const float* __restrict__ u, const float* __restrict__ pw, const float* __restrict__ dw,
                                                         float* __restrict__ save, float* __restrict__ ws, int B, int H, int W) {
-  pdl_prologue();
   __shared__ float red[8];
   const long long M = (long long)B * H * W;
   float s1 = 0.f, s2 = 0.f;
@@ -329,7 +321,6 @@ __global__ void __launch_bounds__(256) srm_fwd_a_kernel(const float* __restrict_
 
 __global__ void srm_fwd_b_kernel(const float* __restrict__ ws, int nblk, long long M, float* rmean, float* rvar, long long* nbt,
                                  float momentum, float eps, float* st) {
-  pdl_prologue();
   if (threadIdx.x != 0) return;
   double a = 0.0, b = 0.0;
   for (int i = 0; i < nblk; i++) { a += ws[i * 2]; b += ws[i * 2 + 1]; }
@@ -345,7 +336,6 @@ __global__ void srm_fwd_b_kernel(const float* __restrict__ ws, int nblk, long lo
 
 __global__ void __launch_bounds__(256) srm_fwd_c_kernel(const float* __restrict__ save, const float* __restrict__ st, const float* gamma,
                                                         const float* beta, float* __restrict__ gm, long long M) {
-  pdl_prologue();
   const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
   if (m >= M) return;
   gm[m] = sigmoidf_(fmaf(gamma[0], (save[m * 2 + 1] - st[0]) * st[1], beta[0]));
@@ -354,7 +344,6 @@ __global__ void __launch_bounds__(256) srm_fwd_c_kernel(const float* __restrict_
 // backward stage a: partial sums of dfn = dgm * gm (1 - gm) and dfn * xhat
 __global__ void __launch_bounds__(256) srm_bwd_a_kernel(const float* __restrict__ dgm, const float* __restrict__ gm, const float* __restrict__ save,
                                                         const float* __restrict__ st, float* __restrict__ ws, long long M) {
-  pdl_prologue();
   __shared__ float red[8];
   float s1 = 0.f, s2 = 0.f;
   for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < M; m += (long long)gridDim.x * 256) {
@@ -368,7 +357,6 @@ __global__ void __launch_bounds__(256) srm_bwd_a_kernel(const float* __restrict_
   if (threadIdx.x == 0) { ws[blockIdx.x * 2] = s1; ws[blockIdx.x * 2 + 1] = s2; }
 }
 __global__ void srm_bwd_b_kernel(const float* __restrict__ ws, int nblk, float* sums, float* dgamma, float* dbeta) {
-  pdl_prologue();
   if (threadIdx.x != 0) return;
   float a = 0.f, b = 0.f;
   for (int i = 0; i < nblk; i++) { a += ws[i * 2]; b += ws[i * 2 + 1]; }
@@ -379,7 +367,6 @@ __global__ void srm_bwd_b_kernel(const float* __restrict__ ws, int nblk, float* 
 __global__ void __launch_bounds__(256) srm_bwd_c_kernel(const float* __restrict__ dgm, const float* __restrict__ gm, float* __restrict__ save,
                                                         const float* __restrict__ st, const float* __restrict__ sums, const float* gamma,
                                                         long long M) {
-  pdl_prologue();
   const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
   if (m >= M) return;
   const float g = gm[m];
@@ -392,7 +379,6 @@ __global__ void __launch_bounds__(256) srm_bwd_c_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) srm_bwd_d_kernel(const float* __restrict__ u, const float* __restrict__ save, const float* __restrict__ pw,
                                                         const float* __restrict__ dw, float* __restrict__ du, float* __restrict__ ws, int B,
                                                         int H, int W) {
-  pdl_prologue();
   __shared__ float red[8];
   const long long M = (long long)B * H * W;
   float gp[3] = {0.f, 0.f, 0.f}, gd[27];
@@ -447,7 +433,6 @@ __global__ void __launch_bounds__(256) srm_apply_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ gm, const float* __restrict__ u,
                                                             const int* __restrict__ arg, const float* __restrict__ du, T* __restrict__ dz,
                                                             long long rows, int C) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = rows * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -473,7 +458,6 @@ __global__ void __launch_bounds__(256) srm_apply_bwd_kernel(const T* __restrict_
 // ---------------------------------------------------------------------------------------------- elementwise
 template <typename T, int V>
 __global__ void __launch_bounds__(256) silu_mul_fwd_kernel(const T* __restrict__ g, const T* __restrict__ v, T* __restrict__ out, long long n) {
-  pdl_prologue();
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += (long long)gridDim.x * blockDim.x * V) {
     float a[V], b[V], o[V];
     ldv<V>(g + i, a);
@@ -490,7 +474,6 @@ __device__ __forceinline__ float silu_grad(float x) {
 template <typename T, int V>
 __global__ void __launch_bounds__(256) silu_mul_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ g, const T* __restrict__ v,
                                                            T* __restrict__ dg, T* __restrict__ dv, long long n) {
-  pdl_prologue();
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += (long long)gridDim.x * blockDim.x * V) {
     float d[V], a[V], b[V], oa[V], ob[V];
     ldv<V>(dout + i, d);
@@ -512,7 +495,6 @@ __global__ void __launch_bounds__(256) ls_combine_fwd_kernel(const T* __restrict
                                                              const float* __restrict__ s, const float* __restrict__ t,
                                                              const float* __restrict__ ls, const float* __restrict__ wp, T* __restrict__ out,
                                                              long long rows, int C) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = rows * groups;
   const float w = wp ? wp[0] : 1.f;
@@ -545,7 +527,6 @@ __global__ void __launch_bounds__(kColThreads) ls_combine_bwd_kernel(const T* __
                                                                      const float* __restrict__ ls, const float* __restrict__ wp,
                                                                      T* __restrict__ dy, int acc_dy, T* __restrict__ dp, long long rows,
                                                                      int C, int ngrp, int nrl, int rows_per_block, float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
@@ -604,7 +585,6 @@ __global__ void __launch_bounds__(kColThreads) ls_combine_bwd_kernel(const T* __
 }
 // dw = sum_c percol[c]   (one block; percol = the per-channel sums produced by launch_finalize)
 __global__ void __launch_bounds__(256) ls_combine_finalize_kernel(const float* __restrict__ percol, int C, float* dw) {
-  pdl_prologue();
   __shared__ float red[8];
   float tw = 0.f;
   for (int c = threadIdx.x; c < C; c += 256) tw += percol[c];

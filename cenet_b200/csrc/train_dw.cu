@@ -30,7 +30,6 @@ template <typename T, int V, bool WINDOW>
 __global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dz,
                                                                        long long ldz, int B, int H, int W, int C, int dil, int up2,
                                                                        int ngrp, int nrl, int rows_per_block, float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
@@ -158,7 +157,6 @@ constexpr int WS_C = 64, WS_T = 256, WS_PF = 2, WS_NRX = 3 + WS_PF, WS_NRZ = 1 +
 
 __global__ void __launch_bounds__(WS_T, 2) dw_wgrad_staged_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dz, int ldz,
                                                                   int H, int W, int C, int rows_per_cta, float* __restrict__ ws) {
-  pdl_prologue();
   extern __shared__ __align__(16) unsigned char wsm[];
   const int tid = threadIdx.x;
   const int rowX = (W + 2) * 128, rowZ = W * 128;
@@ -263,7 +261,6 @@ __global__ void __launch_bounds__(WS_T, 2) dw_wgrad_staged_kernel(const bf16* __
 }
 
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* dw, float* dbias) {
-  pdl_prologue();
   __shared__ float sm[kFinThreads];
   const int i = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   const int k = i / C, c = i % C;
@@ -277,7 +274,6 @@ __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ ws, int nblk,
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) sumpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Ho, int Wo, int C, int acc) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = (long long)B * Ho * Wo * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -312,7 +308,6 @@ __global__ void __launch_bounds__(256) sumpool2_kernel(const T* __restrict__ x, 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int B, int H, int W, int Cin, int k,
                                                      int stride, int pad, int Ho, int Wo, int Kp, int acc) {
-  pdl_prologue();
   const int groups = Cin / V;
   const long long total = (long long)B * H * W * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

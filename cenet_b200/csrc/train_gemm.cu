@@ -92,7 +92,6 @@ __device__ __forceinline__ uint4 load_chunk_conv(const WgParams& p, long long m,
 }
 
 __global__ void __launch_bounds__(WG_THREADS) wgrad_mma_kernel(const WgParams p) {
-  pdl_prologue();
   __shared__ __align__(16) bf16 sY[2][TM][PITCH];
   __shared__ __align__(16) bf16 sX[2][TM][PITCH];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -184,7 +183,6 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_mma_kernel(const WgParams p)
 
 // dw[n, ci, t] = sum_s ws[s][n][t*Cin + ci]
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, int S, int N, int K, int T, float* dw) {
-  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   float s = 0.f;
@@ -196,7 +194,6 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
 
 // T == 1 (plain GEMM weights, no tap permutation), N*K % 4 == 0: four outputs per thread with 16-byte loads / stores
 __global__ void __launch_bounds__(256) wgrad_finalize4_kernel(const float4* __restrict__ ws, int S, long long nk4, float4* dw) {
-  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nk4) return;
   float4 s = ws[i];
@@ -213,7 +210,6 @@ template <typename T, int V>
 __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int C,
                                                                      const float* __restrict__ rs, int rs_div, int ngrp, int nrl,
                                                                      int rows_per_block, float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;

@@ -19,7 +19,6 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
                                                       int C2, int H, int W, const float* __restrict__ mats,
                                                       const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws,
                                                       int nplanes, float* __restrict__ scratch, int ident_mask) {
-  pdl_prologue();
   extern __shared__ float sm_dyn[];
   __shared__ float red[16];
   const int nthr = blockDim.x;                               // 256, or 512 for planes >= 2048 pixels (more threads per plane:
@@ -137,7 +136,6 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
 }
 // dw[c] = sum_b ws[b*C2 + c]
 __global__ void fea_dw_finalize_kernel(const float* __restrict__ ws, int B, int C2, float* dw) {
-  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C2) return;
   float s = 0.f;
@@ -149,7 +147,6 @@ __global__ void fea_dw_finalize_kernel(const float* __restrict__ ws, int B, int 
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_slice_kernel(const T* __restrict__ x, T* __restrict__ out, int HW, int C, int Ctot,
                                                                  int coff, int acc) {
-  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -171,7 +168,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_slice_kernel(const T* __rest
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) add_kernel(T* __restrict__ dst, const T* __restrict__ src, long long n, int acc) {
-  pdl_prologue();
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += (long long)gridDim.x * blockDim.x * V) {
     float a[V];
     ldv<V>(src + i, a);
@@ -191,7 +187,6 @@ __global__ void __launch_bounds__(256) resample_kernel(const TI* __restrict__ x,
                                                        int Hi, int Wi, int Ho, int Wo, int C, const int* __restrict__ hs,
                                                        const int* __restrict__ hi, const float* __restrict__ hw, const int* __restrict__ wsx,
                                                        const int* __restrict__ wi, const float* __restrict__ ww, int acc) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = (long long)B * Ho * Wo * groups;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -231,7 +226,6 @@ __global__ void __launch_bounds__(kColThreads) maxpool2_scale_bwd_kernel(const T
                                                                          const float* __restrict__ wch, T* __restrict__ drb, int B, int H,
                                                                          int W, int C, int ngrp, int nrl, int rows_per_block,
                                                                          float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
@@ -280,7 +274,6 @@ __global__ void __launch_bounds__(kColThreads) maxpool2_scale_bwd_kernel(const T
 // adjoint of bilinear x2 (align_corners=False): dlogits [B,ncls,2h,2w] fp32 -> dyh [B,h,w,ncls] fp32
 __global__ void __launch_bounds__(256) head_upsample_bwd_kernel(const float* __restrict__ dl, float* __restrict__ dyh, int B, int h, int w,
                                                                 int ncls) {
-  pdl_prologue();
   const long long total = (long long)B * h * w * ncls;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -325,7 +318,6 @@ __global__ void __launch_bounds__(256) head_upsample_bwd_kernel(const float* __r
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, const float* __restrict__ hyper) {
-  pdl_prologue();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5];
   const float bc1 = 1.f - powf(b1, step), bc2s = sqrtf(1.f - powf(b2, step));
   const float step_size = lr / bc1;
@@ -468,7 +460,6 @@ extern "C" int cenet_head_upsample_bwd(const float* dlogits, float* dyh, int B, 
 template <typename TO>
 __global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ map, TO* __restrict__ dst,
                                                           long long n4) {
-  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int4 m = reinterpret_cast<const int4*>(map)[i];
     float v[4];

@@ -6,7 +6,6 @@
 
 __global__ void __launch_bounds__(kFinThreads) finalize_partials_kernel(const float* __restrict__ ws, int nblk, int n, float* outA,
                                                                         int nA, float* outB, float scale) {
-  pdl_prologue();
   __shared__ float sm[kFinThreads];
   const int i = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   float t[1];
@@ -29,7 +28,6 @@ namespace {
 template <typename T, int V>
 __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int C,
                                                                        int ngrp, int nrl, int rows_per_block, float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
@@ -62,7 +60,6 @@ __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const T* 
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ ws, int nblk, int C, long long rows, const float* gamma,
                                          const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps,
                                          float* scale, float* shift, float* mean, float* rstd) {
-  pdl_prologue();
   __shared__ double sm[2 * kFinThreads];
   const int c = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   double t[2];
@@ -94,7 +91,6 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ a
                                                          const float* __restrict__ sb, const float* __restrict__ tb,
                                                          T* __restrict__ out, long long ldo, long long rows, int C, int act,
                                                          float slope) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = rows * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -127,7 +123,6 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const T* __
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                      long long rows, int C, int act, float slope, int ngrp, int nrl,
                                                                      int rows_per_block, float* __restrict__ ws) {
-  pdl_prologue();
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
@@ -170,7 +165,6 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const T* __
 
 // sums[0..C) = d(beta), sums[C..2C) = d(gamma); also written to the parameter gradients
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* sums, float* dgamma, float* dbeta) {
-  pdl_prologue();
   __shared__ float sm[2 * kFinThreads];
   const int c = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   float t[2];
@@ -190,7 +184,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ sums, long long rows, int C, int act, float slope,
                                                            T* __restrict__ da, int acc_da, T* __restrict__ dres, long long lddres,
                                                            int acc_dres) {
-  pdl_prologue();
   const int groups = C / V;
   const long long total = rows * groups;
   const float inv = 1.f / (float)rows;
@@ -240,7 +233,6 @@ template <typename T, int LPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma, float eps, long long rows, int C,
                                                             T* __restrict__ dx, int acc, float* __restrict__ ws) {
-  pdl_prologue();
   constexpr int RPW = 32 / LPR;                           // rows per warp pass
   extern __shared__ float dyn[];                          // [8 warps * RPW][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, grp = lane / LPR;

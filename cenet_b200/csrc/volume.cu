@@ -15,7 +15,6 @@ __global__ void __launch_bounds__(256) volume_labels_counts_kernel(const long lo
                                                                    const LT* __restrict__ label, long long* __restrict__ pred_out,
                                                                    unsigned long long* __restrict__ counts, int D, int H, int W,
                                                                    int ncls) {
-  pdl_prologue();
   __shared__ unsigned int h[3 * MAXC];
   for (int i = threadIdx.x; i < 3 * ncls; i += blockDim.x) h[i] = 0u;
   __syncthreads();

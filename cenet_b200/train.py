@@ -1256,16 +1256,8 @@ class TrainEngine:
         cur = {}
         self._user_on_bucket, self._user_grad_hook = self.on_bucket, self.grad_hook
 
-        from . import pdl
-        use_pdl = pdl.enabled()
-        self.pdl_stats = []
-
         def begin():
-            try:
-                cur["g"] = torch.cuda.CUDAGraph(keep_graph=True) if use_pdl else torch.cuda.CUDAGraph()
-                cur["keep"] = use_pdl
-            except TypeError:                                        # torch without keep_graph
-                cur["g"], cur["keep"] = torch.cuda.CUDAGraph(), False
+            cur["g"] = torch.cuda.CUDAGraph()
             cur["n0"] = ops.launch_count()
             cur["g"].capture_begin(pool=pool)
 
@@ -1277,12 +1269,6 @@ class TrainEngine:
                     cur["g"].capture_end()
                 return
             cur["g"].capture_end()
-            if cur["keep"]:
-                try:
-                    self.pdl_stats.append(pdl.relax(cur["g"]))     # kernel -> kernel edges become programmatic (pdl.py)
-                except Exception as e:
-                    self.pdl_stats.append(dict(error=repr(e)))
-                cur["g"].instantiate()
             segs.append(("graph", cur["g"]))
 
         def cut_bucket(g_):
@@ -1316,12 +1302,16 @@ class TrainEngine:
                 and self.grad_hook is None)
 
     def _ab_capture(self, fn):
-        from . import pdl
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            g, _ = pdl.capture(fn)
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin()
+            try:
+                fn()
+            finally:
+                g.capture_end()
         cur.wait_stream(side)
         return g
 

@@ -225,6 +225,34 @@ def test_boundary_criterion_fused_step_and_dropin_module(monkeypatch):
     assert ((g_auto - g_fused).norm() / g_fused.norm()).item() < 1e-5
 
 
+def test_benchmarked_batch_24_bf16_step_matches_fp32_step():
+    """Parity AT the benchmarked training shape (BASELINE configs[2]: ACDC, batch 24): train-mode BatchNorm couples the whole
+    batch, and the oracle's autograd at batch 24 would need > 60 GB of host memory (it materialises every N x N map), so the
+    bf16 product step is checked against the fp32 validation engine -- itself pinned to the oracle / reference goldens at batch
+    2 -- on identical weights, inputs and labels: loss, logits, direction and length of the full gradient."""
+    kw = fixtures.CONFIGS["acdc"]
+    from cenet_b200.networks import CENet
+    torch.manual_seed(1234)
+    sd = fixtures.perturb_state(CENet(**kw).state_dict(), 1234)
+    x = fixtures.synth_input("acdc", 24).to(DEV)
+    labels = torch.randint(0, 4, (24, 224, 224), generator=torch.Generator().manual_seed(5)).to(DEV)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        m, eng = _engine("acdc", prec, sd)
+        eng.use_graph = False
+        out = eng.train_step(x, labels, optimize=False)
+        torch.cuda.synchronize()
+        res[prec] = (out[0].item(), eng.buf("logits", (24, 4, 224, 224), torch.float32).clone(), eng.gflat.clone())
+        del m, eng
+        torch.cuda.empty_cache()
+    (l32, y32, g32), (l16, y16, g16) = res["fp32"], res["bf16"]
+    assert abs(l16 - l32) < 1e-2 * max(1.0, abs(l32)), (l16, l32)
+    e = ((y16 - y32).norm() / y32.norm()).item()
+    assert e < 2e-2, e
+    cos = (torch.dot(g16, g32) / (g16.norm() * g32.norm())).item()
+    assert cos > 0.99 and abs(g16.norm().item() / g32.norm().item() - 1.0) < 0.05, (cos, g16.norm().item(), g32.norm().item())
+
+
 # ---------------------------------------------------------------------------------------------- pinned to the REAL reference
 @pytest.mark.parametrize("fx", ["train_acdc_b2_s224", "train_synapse_b2_s96", "train_acdc_b1_s64"])
 def test_train_step_fp32_matches_reference_train_mode_golden(fx):

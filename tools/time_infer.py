@@ -21,4 +21,4 @@ for _ in range(steps):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"{name} B={B}: {ms:.3f} ms/forward -> {B / ms * 1e3:.1f} slices/s; launches {eng.launches_per_forward}; "
-      f"label checksum {int(lab.sum())}; pdl {eng.pdl_stats}")
+      f"label checksum {int(lab.sum())}")

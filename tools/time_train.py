@@ -28,5 +28,4 @@ ms = e0.elapsed_time(e1) / steps
 side = eng.side
 print(f"{name} B={B} wgrad_stream={'on' if side is not None else 'off'}: {ms:.2f} ms/step -> {B / ms * 1e3:.1f} img/s; "
       f"launches/step {eng.launches_per_step}; loss {loss[0].item():.5f}"
-      + (f"; side launches {side.launches} guard waits {side.waits}" if side is not None else "")
-      + f"; pdl {getattr(eng, 'pdl_stats', None)}")
+      + (f"; side launches {side.launches} guard waits {side.waits}" if side is not None else ""))
