@@ -61,6 +61,7 @@ _SIGS = {
     "cenet_maxpool2_scale": [vp, i32, vp, i32, ll, i32, vp, i32, i32, i32, i32, vp],
     "cenet_affine_gate": [vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp],
     "cenet_fea_combine": [vp, vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(f32), i32, vp],
+    "cenet_dog_combine": [vp, vp, vp, i32, vp, i32, i32, i32, i32, C.POINTER(f32), i32, i32, vp],
     "cenet_diff_combine": [vp, i32, ll, ll, f32, vp],
     "cenet_rmsnorm_seg": [vp, i32, vp, i32, ll, i32, i32, f32, f32, vp],
     "cenet_diffattn_flash": [vp, vp, i32, i32, i32, i32, f32, f32, f32, vp, vp],

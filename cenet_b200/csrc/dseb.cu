@@ -25,7 +25,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ y, const T* __restrict__ gate,
                                                           T* __restrict__ z, const float* __restrict__ w_c, int C2,
                                                           int H, int W, long long nplanes, int ppb, unsigned wmagic,
-                                                          const FeaScales sc, int plane_floats) {
+                                                          const FeaScales sc, int plane_floats, int mode) {
+  // mode 0 (CENet, dseb.py:63-76,157): z = 2y + w * mean_{i<j} | |y - y_i| - |y - y_j| | + gate * y
+  // mode 1 (CENetOrg DoGEdge, cenet_org/decoders.py:112-125): z = y + w * |y_0 - y_1|          (gate unused)
+  // mode 2 (CENetOrg SkipEnhancer combine, decoders.py:140-143): z = y + gate * y               (no scales)
+  // y_k = bilinear up(down_k(y)) of scale k
   extern __shared__ float sm[];
   // tables: for each scale: down rows (hd), down cols (wd), up rows (H), up cols (W)
   LerpTab* tab = reinterpret_cast<LerpTab*>(sm);
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
   const float wc = w_c[c];
   const int npair = sc.n * (sc.n - 1) / 2;
   const float inv_pair = npair > 0 ? 1.f / (float)npair : 0.f;
-  const T* gp = gate + pl * HW;
+  const T* gp = gate ? gate + pl * HW : nullptr;
   T* zp = z + pl * HW;
   for (int i = tt; i < HW; i += team) {
     const int h = (int)__umulhi((unsigned)i, wmagic), w = i - h * W;
@@ -88,15 +92,24 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
     float e[kMaxScales];
 #pragma unroll
     for (int k = 0; k < kMaxScales; k++) {
-      e[k] = 0.f;
+      e[k] = mode == 1 ? x : 0.f;                      // identity scale: y_k == y
       if (k < sc.n && !sc.identity[k]) {
         const float* d = plane + sc.off[k];
         const int wd = sc.wd[k];
         const LerpTab a = tab[toff[k][2] + h], bcol = tab[toff[k][3] + w];
         const float top = fmaf(bcol.l, d[a.i0 * wd + bcol.i1] - d[a.i0 * wd + bcol.i0], d[a.i0 * wd + bcol.i0]);
         const float bot = fmaf(bcol.l, d[a.i1 * wd + bcol.i1] - d[a.i1 * wd + bcol.i0], d[a.i1 * wd + bcol.i0]);
-        e[k] = fabsf(x - fmaf(a.l, bot - top, top));
+        const float yk = fmaf(a.l, bot - top, top);
+        e[k] = mode == 1 ? yk : fabsf(x - yk);
       }
+    }
+    if (mode == 1) {
+      stf(zp + i, fmaf(wc, fabsf(e[0] - e[1]), x));
+      continue;
+    }
+    if (mode == 2) {
+      stf(zp + i, fmaf(ldf(gp + i), x, x));
+      continue;
     }
     float edge = 0.f;
 #pragma unroll
@@ -121,11 +134,15 @@ __global__ void __launch_bounds__(256) diff_combine_kernel(T* __restrict__ P, lo
 }
 }  // namespace
 
-extern "C" int cenet_fea_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2,
-                                 int H, int W, const float* scales, int nscales, cenet_stream_t s) {
+static int fea_launch(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2, int H, int W,
+                      const float* scales, int nscales, int mode, cenet_stream_t s) {
   if (B == 0) return 0;
-  CENET_REQUIRE(y && gate && z && w_c && scales, "cenet_fea_combine: null pointer");
-  CENET_REQUIRE(nscales >= 1 && nscales <= kMaxScales, "cenet_fea_combine: 1..3 scale factors supported, got %d", nscales);
+  CENET_REQUIRE(y && z && w_c, "cenet_fea_combine: null pointer");
+  CENET_REQUIRE(mode == 1 || gate, "cenet_fea_combine: null gate");
+  CENET_REQUIRE(mode == 2 || scales, "cenet_fea_combine: null scale factors");
+  if (mode == 2) nscales = 0;
+  CENET_REQUIRE((mode == 2 || nscales >= 1) && nscales <= kMaxScales, "cenet_fea_combine: 1..3 scale factors supported, got %d", nscales);
+  CENET_REQUIRE(mode != 1 || nscales == 2, "cenet_dog_combine: the difference of Gaussians takes exactly two scale factors, got %d", nscales);
   FeaScales sc;
   sc.n = nscales;
   int off = H * W;
@@ -158,12 +175,23 @@ extern "C" int cenet_fea_combine(const void* y, const void* gate, void* z, int d
 #define LAUNCH_FEA(T)                                                                                         \
   do {                                                                                                        \
     if (smem > 48 * 1024) cudaFuncSetAttribute(fea_combine_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    fea_combine_kernel<T><<<grid, 256, smem, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, planes, ppb, wmagic, sc, plane_floats); \
+    fea_combine_kernel<T><<<grid, 256, smem, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, planes, ppb, wmagic, sc, plane_floats, mode); \
   } while (0)
   CENET_DISPATCH(dtype, T, LAUNCH_FEA(T));
 #undef LAUNCH_FEA
   CENET_LAUNCH_CHECK("fea_combine");
   return 0;
+}
+
+extern "C" int cenet_fea_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2,
+                                 int H, int W, const float* scales, int nscales, cenet_stream_t s) {
+  return fea_launch(y, gate, z, dtype, w_c, B, C2, H, W, scales, nscales, 0, s);
+}
+
+extern "C" int cenet_dog_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2, int H,
+                                 int W, const float* scales, int nscales, int mode, cenet_stream_t s) {
+  CENET_REQUIRE(mode == 1 || mode == 2, "cenet_dog_combine: mode %d (1 = DoG edge, 2 = y + gate*y)", mode);
+  return fea_launch(y, gate, z, dtype, w_c, B, C2, H, W, scales, nscales, mode, s);
 }
 
 extern "C" int cenet_diff_combine(void* P, int dtype, long long npairs, long long map_elems, float lambda,

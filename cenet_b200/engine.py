@@ -125,6 +125,11 @@ class Engine:
         # function as the slices one by one.  None = follow the batch size like the reference; False = per-slice (B = 1)
         # semantics for any batch (cenet_b200.volume batches a volume's slices and must match the reference's B = 1 loop)
         self.ccu_bn1d = None
+        # knobs the CENetOrg variant (engine_org.py) turns: MultiOrderDWConv dilation rates (None = per-width table of
+        # decoders.py:64), LeakyReLU slope of the image-pooling branch (cfam.py:216) and of EUCB (blocks.py:76)
+        self.fixed_rates = None
+        self.pool_slope = 0.01
+        self.eucb_slope = 0.2
         self.launches_per_forward = None              # kernels launched by one pass (counted on the eager warm-up)
 
     # ------------------------------------------------------------------------------------------------ packing
@@ -182,11 +187,16 @@ class Engine:
         sd = self._sd()
         cfg = self.cfg
         P, M = self._put, self._put_mat
+        self._pack_encoder(sd, sum_gray=cfg["input_channels"] == 1)
+        self._pack_decoder_and_head(sd)
+
+    def _pack_encoder(self, sd, sum_gray):
+        P, M = self._put, self._put_mat
         # ---------------- encoder ----------------
         for s in range(4):
             pe = f"backbone.patch_embed{s+1}"
             w = sd[pe + ".proj.weight"]
-            if s == 0 and cfg["input_channels"] == 1:
+            if s == 0 and sum_gray:
                 w = w.sum(1, keepdim=True)            # cat([x,x,x]) (net.py:55) == one channel with summed filters
             M(pe + ".w", self._conv_mat(w))
             P(pe + ".b", sd[pe + ".proj.bias"])
@@ -206,6 +216,10 @@ class Engine:
                 P(f"{b}.mlp.dw.b", sd[f"{b}.mlp.dwconv.dwconv.bias"])
             P(f"backbone.norm{s+1}.g", sd[f"backbone.norm{s+1}.weight"])
             P(f"backbone.norm{s+1}.b", sd[f"backbone.norm{s+1}.bias"])
+
+    def _pack_decoder_and_head(self, sd):
+        cfg = self.cfg
+        P, M = self._put, self._put_mat
         # ---------------- decoder ----------------
         for name, Cc in (("dec4", 512), ("dec3", 320), ("dec2", 128), ("dec1", 64)):
             self._pack_cfam(sd, f"decoder.{name}", Cc)
@@ -213,32 +227,7 @@ class Engine:
             self._pack_up(sd, f"decoder.up{lvl}", cfg["dec_up_block"])
             p = f"decoder.skip_enhancer{lvl}"
             P(p + ".fea_w", sd[p + ".boundary.w"].reshape(-1))
-            d = p + ".diffattn"
-            M(d + ".qkv.w", torch.cat([sd[d + ".q_proj.weight"], sd[d + ".k_proj.weight"], sd[d + ".v_proj.weight"]], 0))
-            M(d + ".out.w", sd[d + ".out_proj.weight"])
-            # head dims the flash kernel cannot tile (hd = 20 at the 14x14 level of the Synapse config) are zero-padded
-            # in the packed projections: q/k heads -> hd_pad, value heads -> dv_pad, out_proj gets zero columns
-            E = sd[d + ".q_proj.weight"].shape[0]
-            h = cfg["diffatt_num_heads"][hi]
-            hd = E // h // 2
-            pad = self._flash_padding(hd)
-            if pad is not None and pad != (hd, 2 * hd):
-                hdp, dvp = pad
-                def pad_rows(wm, nheads, width, widthp):
-                    o = torch.zeros(nheads, widthp, wm.shape[1], device=wm.device)
-                    o[:, :width] = wm.view(nheads, width, wm.shape[1])
-                    return o.view(nheads * widthp, wm.shape[1])
-                M(d + ".qkvp.w", torch.cat([pad_rows(sd[d + ".q_proj.weight"], 2 * h, hd, hdp),
-                                            pad_rows(sd[d + ".k_proj.weight"], 2 * h, hd, hdp),
-                                            pad_rows(sd[d + ".v_proj.weight"], h, 2 * hd, dvp)], 0))
-                wo = torch.zeros(E, h, dvp, device=self.dev)
-                wo[:, :, :2 * hd] = sd[d + ".out_proj.weight"].view(E, h, 2 * hd)
-                M(d + ".outp.w", wo.view(E, h * dvp))
-            li = lambda_init(depth)
-            lam = (torch.exp((sd[d + ".lambda_q1"] * sd[d + ".lambda_k1"]).sum())
-                   - torch.exp((sd[d + ".lambda_q2"] * sd[d + ".lambda_k2"]).sum()) + li)
-            self.w[d + ".lambda"] = float(lam.item())          # host scalar (kernel argument)
-            self.w[d + ".lambda_init"] = li
+            self._pack_diffattn(sd, p + ".diffattn", cfg["diffatt_num_heads"][hi], depth)
             M(p + ".mixer.w", sd[p + ".mixer.weight"].flatten(1))
         # ---------------- head ----------------
         self._pack_resblock(sd, "out.rb.0", 5)
@@ -250,6 +239,34 @@ class Engine:
         P("out.head.b", sd["out.out.1.conv.conv.bias"])
         self._wver = self._weights_version()
         self._graphs.clear()                                   # host scalars are baked into captured launches
+
+    def _pack_diffattn(self, sd, d, h, depth):
+        """MultiheadDiffAttn weights (multihead_diffattn.py:32-66): q|k|v projections concatenated, lambda as a host scalar"""
+        P, M = self._put, self._put_mat
+        M(d + ".qkv.w", torch.cat([sd[d + ".q_proj.weight"], sd[d + ".k_proj.weight"], sd[d + ".v_proj.weight"]], 0))
+        M(d + ".out.w", sd[d + ".out_proj.weight"])
+        # head dims the flash kernel cannot tile (hd = 20 at the 14x14 level of the Synapse config) are zero-padded
+        # in the packed projections: q/k heads -> hd_pad, value heads -> dv_pad, out_proj gets zero columns
+        E = sd[d + ".q_proj.weight"].shape[0]
+        hd = E // h // 2
+        pad = self._flash_padding(hd)
+        if pad is not None and pad != (hd, 2 * hd):
+            hdp, dvp = pad
+            def pad_rows(wm, nheads, width, widthp):
+                o = torch.zeros(nheads, widthp, wm.shape[1], device=wm.device)
+                o[:, :width] = wm.view(nheads, width, wm.shape[1])
+                return o.view(nheads * widthp, wm.shape[1])
+            M(d + ".qkvp.w", torch.cat([pad_rows(sd[d + ".q_proj.weight"], 2 * h, hd, hdp),
+                                        pad_rows(sd[d + ".k_proj.weight"], 2 * h, hd, hdp),
+                                        pad_rows(sd[d + ".v_proj.weight"], h, 2 * hd, dvp)], 0))
+            wo = torch.zeros(E, h, dvp, device=self.dev)
+            wo[:, :, :2 * hd] = sd[d + ".out_proj.weight"].view(E, h, 2 * hd)
+            M(d + ".outp.w", wo.view(E, h * dvp))
+        li = lambda_init(depth)
+        lam = (torch.exp((sd[d + ".lambda_q1"] * sd[d + ".lambda_k1"]).sum())
+               - torch.exp((sd[d + ".lambda_q2"] * sd[d + ".lambda_k2"]).sum()) + li)
+        self.w[d + ".lambda"] = float(lam.item())          # host scalar (kernel argument)
+        self.w[d + ".lambda_init"] = li
 
     def _pack_stem(self, sd, p):
         """fp32 filters of the CUDA-core stem kernel (first conv of out.rb.0 and its 1x1 residual branch)."""
@@ -503,7 +520,7 @@ class Engine:
         ap = _rup(sl[0][1] - sl[0][0], 8)
         dwb = self.buf(key + ".dwb", (Mtok, 3 * ap), zero=True)
         cat = self.buf(key + ".cat", (Mtok, Cc))
-        for i, rate in enumerate(_MCA_RATES[Cc]):
+        for i, rate in enumerate(self.fixed_rates or _MCA_RATES[Cc]):
             a0, a1 = sl[i]
             d = f"{v}.dlps.{i}"
             ops.dwconv3x3(x1, dwb, w[d + ".dw.w"], B, H, W, a1 - a0, ldx=Cc, ldy=3 * ap, x_off=a0, y_off=i * ap,
@@ -513,7 +530,7 @@ class Engine:
         r0, r1 = sl[3]
         d = f"{v}.dlps.3"
         pooled = self.buf(key + ".pooled", (B * 49 * (r1 - r0),), torch.float32)
-        ops.pool_branch(x1, Cc, r0, cat, Cc, r0, w[d + ".w"], w[d + ".s"], w[d + ".t"], 0.01, pooled, B, H, W, r1 - r0)
+        ops.pool_branch(x1, Cc, r0, cat, Cc, r0, w[d + ".w"], w[d + ".s"], w[d + ".t"], self.pool_slope, pooled, B, H, W, r1 - r0)
         sv = self.buf(key + ".sv", (Mtok, Cc))
         self._lin(cat, v + ".PW", sv, act=ACT_SILU, mul=g, ldmul=Cc, mul_act=ACT_SILU)     # SiLU(g)*SiLU(v)
         y = self.buf(key + ".y", (Mtok, Cc))
@@ -552,7 +569,7 @@ class Engine:
         if kind == "eucb":
             t = self.buf(key + ".dw", (Mo, Cin))
             ops.dwconv3x3(x, t, w[p + ".dw.w"], B, 2 * H, 2 * W, Cin, scale=w[p + ".dw.s"], shift=w[p + ".dw.t"],
-                          up2=True, act=ACT_LEAKY, slope=0.2)
+                          up2=True, act=ACT_LEAKY, slope=self.eucb_slope)
             ops.gemm(t, w[p + ".pw.w"], out, M=Mo, N=Cout, K=Cin, lda=Cin, ldw=w[p + ".pw.w"].shape[1], ldc=ldc,
                      bias=w[p + ".pw.b"], c_off=c_off, impl=self.gemm_impl)
         else:

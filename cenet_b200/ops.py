@@ -189,6 +189,14 @@ def fea_combine(y, gate, z, w_c, B, C2, H, W, scales: Sequence[float]):
     return z
 
 
+def dog_combine(y, gate, z, w_c, B, C2, H, W, scales: Sequence[float], mode: int):
+    """CENetOrg skip enhancer pieces on NCHW planes: mode 1 z = y + w*|y_s0 - y_s1| (DoGEdge), mode 2 z = y + gate*y"""
+    sc = list(scales) if scales else [1.0]
+    arr = (C.c_float * len(sc))(*[float(v) for v in sc])
+    L.call("cenet_dog_combine", _p(y), _p(gate), _p(z), dt(y), _f32(w_c, "dog.w"), B, C2, H, W, arr, len(sc), mode, _stream())
+    return z
+
+
 def diff_combine_(P, npairs, map_elems, lam):
     L.call("cenet_diff_combine", _p(P), dt(P), npairs, map_elems, lam, _stream())
     return P

@@ -122,6 +122,11 @@ int cenet_affine_gate(const void* x, int x_dtype, void* y, int y_dtype, const fl
  * scales: up to 3 scale factors.  gate has the same flat layout as y (the `.view` reinterpretation). */
 int cenet_fea_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2, int H,
                       int W, const float* scales, int nscales, cenet_stream_t s);
+/* CENetOrg skip enhancer (cenet_org/decoders.py:112-143), same NCHW planes as cenet_fea_combine:
+ * mode 1 (DoGEdge):  z = y + w[c] * | up(down_s0(y)) - up(down_s1(y)) |     (exactly two scale factors; gate unused, may be NULL)
+ * mode 2 (combine):  z = y + gate * y                                       (scales unused) */
+int cenet_dog_combine(const void* y, const void* gate, void* z, int dtype, const float* w_c, int B, int C2, int H, int W,
+                      const float* scales, int nscales, int mode, cenet_stream_t s);
 /* P[:, 2i] -= lambda * P[:, 2i+1] over contiguous maps of `map_elems` elements (multihead_diffattn.py:115-116) */
 int cenet_diff_combine(void* P, int dtype, long long npairs, long long map_elems, float lambda, cenet_stream_t s);
 /* y = x * rsqrt(mean_seg(x^2)+eps) * mult over segments of `seg` channels (rms_norm.py:15-22 and the

@@ -226,6 +226,20 @@ def fea_combine(y, gate, z, w_c, B, C2, H, W, scales):
     return z
 
 
+def dog_combine(y, gate, z, w_c, B, C2, H, W, scales, mode):
+    _LAUNCHES[0] += 1
+    yf = _flat(y).view(B, C2, H, W).float()
+    if mode == 1:
+        def updown(s):
+            d = F.interpolate(yf, scale_factor=s, mode="bilinear")
+            return F.interpolate(d, size=(H, W), mode="bilinear")
+        out = yf + w_c.view(1, C2, 1, 1) * (updown(scales[0]) - updown(scales[1])).abs()
+    else:
+        out = yf + _flat(gate).view(B, C2, H, W).float() * yf
+    _flat(z).view(B, C2, H, W).copy_(out)
+    return z
+
+
 def diff_combine_(P, npairs, map_elems, lam):
     _LAUNCHES[0] += 1
     v = _flat(P).view(npairs, 2, map_elems)

@@ -225,7 +225,48 @@ def train_fixture(nets, name, batch, size):
     print("train", name, batch, size, "loss", loss.item(), "params without grad:", none)
 
 
+ORG_KW = dict(num_classes=9, input_channels=1, scale_factors=[0.8, 0.4], encoder="pvt_v2_b2", pretrain=False,
+              num_heads=[16, 8, 8])           # scripts/synapse.sh TEST_ORG -> main_synapse.py:129-137
+
+
+def org_fixture(nets, batch):
+    """CENetOrg (the reference's cenet_org.net.Net) in eval mode: strided logits, labels and per-module taps.  The weights come
+    from cenet_b200.networks.CENetOrg and are loaded into the reference with strict=True (pins the 822-key contract)."""
+    from cenet_b200.networks import CENetOrg
+    torch.manual_seed(1234)
+    mine = CENetOrg(**ORG_KW)
+    sd = fixtures.perturb_state(mine.state_dict(), 1234)
+    sd["out.conv.conv.weight"] = sd["out.conv.conv.weight"] * 20.0      # trained-like logit margins, as for CENet
+    ref = nets.CENetOrg(**ORG_KW).eval()
+    ref.load_state_dict(sd, strict=True)
+    x = fixtures.synth_input("synapse", batch)
+    taps, hooks = {}, []
+    for mod_name in ["decoder.dec4", "decoder.dec3", "decoder.dec2", "decoder.dec1", "decoder.eucb3", "decoder.eucb2",
+                     "decoder.eucb1", "decoder.skip_enhancer3", "decoder.skip_enhancer2", "decoder.skip_enhancer1"]:
+        m = ref.get_submodule(mod_name)
+        hooks.append(m.register_forward_hook(lambda mod, i, o, n=mod_name: taps.__setitem__(n, o.detach())))
+    with torch.no_grad():
+        feats = ref.backbone(ref.conv(x))
+        y = ref(x)
+    for h in hooks:
+        h.remove()
+    for i, f in enumerate(feats):
+        taps[f"backbone.stage{i+1}"] = f
+    lab = torch.argmax(torch.softmax(y, 1), 1)
+    out = dict(kw=ORG_KW, batch=batch, seed=1234, input_seed=0, n_keys=len(sd),
+               logits_strided=y[:, :, ::4, ::4].clone(), logits_std=y.std().item(),
+               label_hist=torch.bincount(lab.flatten(), minlength=9), labels_strided=lab[:, ::2, ::2].clone(),
+               taps={k: dict(mean=v.mean().item(), std=v.std().item(), norm=v.norm().item(),
+                             sample=v.flatten()[:: max(1, v.numel() // 4096)][:4096].clone()) for k, v in taps.items()})
+    torch.save(out, os.path.join(HERE, f"model_org_synapse_b{batch}.pt"))
+    print("org", batch, "keys", len(sd), "logits std", out["logits_std"], "hist", out["label_hist"].tolist())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "org":
+        nets = ref_shim.import_reference()
+        org_fixture(nets, 2)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train":         # only the train-mode fixtures
         nets = ref_shim.import_reference()
         train_fixture(nets, "acdc", 2, 224)

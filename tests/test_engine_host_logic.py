@@ -61,3 +61,57 @@ def test_repack_on_weight_change_and_batch_keys():
         eng.forward(torch.zeros(1, 1, 100, 100))
     with pytest.raises(ValueError):
         eng.forward(torch.zeros(1, 3, 64, 64))
+
+
+# ---------------------------------------------------------------------------------------------- CENetOrg
+def _org_engine(precision="fp32", flash=True):
+    import os
+    import cenet_b200.engine as E
+    import cenet_b200.engine_org as EO
+    from cenet_b200.networks import CENetOrg
+    from conftest import GOLDEN
+    g = torch.load(os.path.join(GOLDEN, "model_org_synapse_b2.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    m = CENetOrg(**g["kw"])
+    sd = fixtures.perturb_state(m.state_dict(), g["seed"])
+    sd["out.conv.conv.weight"] = sd["out.conv.conv.weight"] * 20.0
+    m.load_state_dict(sd)
+    m.eval()
+    eng = EO.EngineOrg(m, "cpu", precision)
+    eng.use_graph = False
+    eng.use_flash = flash
+    return m, eng, g
+
+
+def test_cenet_org_launch_plan_reproduces_the_reference(monkeypatch):
+    """The CENetOrg launch plan on the torch emulation of the kernels vs the REAL reference's outputs (tests/golden/
+    model_org_synapse_b2.pt: cenet_org.net.Net with the TEST_ORG kwargs of scripts/synapse.sh): 822-key state_dict,
+    strided logits, every decoder tap and the integer label map."""
+    import cenet_b200.engine_org as EO
+    monkeypatch.setattr(EO, "ops", fake_ops)
+    m, eng, g = _org_engine()
+    assert len(m.state_dict()) == g["n_keys"] == 822
+    x = fixtures.synth_input("synapse", g["batch"], seed=g["input_seed"])
+    eng.taps = {}
+    y = eng.forward(x)
+    for k, ref in g["taps"].items():
+        v = eng.taps[k]
+        s = v.flatten()[:: max(1, v.numel() // 4096)][:4096]
+        e = ((s - ref["sample"]).norm() / ref["sample"].norm()).item()
+        assert e < 5e-5, (k, e)
+        assert abs(v.norm().item() - ref["norm"]) < 1e-4 * ref["norm"], k
+    e = ((y[:, :, ::4, ::4] - g["logits_strided"]).norm() / g["logits_strided"].norm()).item()
+    assert e < 5e-5, e
+    lab = eng.forward(x, labels=True)
+    assert torch.equal(lab, O.predict_labels(y))
+    assert (lab[:, ::2, ::2] == g["labels_strided"]).float().mean().item() > 0.9999
+
+
+def test_cenet_org_contract():
+    from cenet_b200.networks import CENetOrg
+    m = CENetOrg(num_classes=9, input_channels=1, scale_factors=[0.8, 0.4], encoder="pvt_v2_b2", pretrain=False, num_heads=[16, 8, 8])
+    assert len(m.state_dict()) == 822 and sum(p.numel() for p in m.parameters()) == 33379849
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(1, 1, 224, 224))                    # no CPU path
+    with pytest.raises(NotImplementedError):
+        CENetOrg(encoder="resnet50")

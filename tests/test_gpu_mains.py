@@ -78,6 +78,24 @@ def test_main_synapse_unchanged(tmp_path):
     assert abs(float(m.group(1)) * 100 - te[-1]) < 0.02, (m.group(1), te)
 
 
+def test_main_synapse_test_org_unchanged(tmp_path):
+    """scripts/synapse.sh TEST_ORG: `main_synapse.py --model_version cenet_org --eval --checkpoint <published layout>` with
+    `networks.CENetOrg` = cenet_b200 (822-key checkpoint, strict load, per-volume B=1 evaluation)."""
+    from cenet_b200.networks import CENetOrg
+    d = str(tmp_path)
+    ds = H.make_synapse(d, size=224, n_train=2, n_vol=1, depth=3)
+    torch.manual_seed(7)
+    ck = os.path.join(d, "cenet_org.pth")
+    torch.save(CENetOrg(num_classes=9, input_channels=1, scale_factors=[0.8, 0.4], encoder="pvt_v2_b2", pretrain=False,
+                        num_heads=[16, 8, 8]).state_dict(), ck)
+    args = ["--root_dir", ds["root_dir"], "--list_dir", ds["list_dir"], "--volume_path", ds["volume_path"],
+            "--save_path", os.path.join(d, "out"), "--tag", "org", "--batch_size", "4", "--img_size", "224", "--num_workers", "0",
+            "--model_version", "cenet_org", "--eval", "--checkpoint", ck]
+    r = H.run_main("main_synapse.py", args)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert "Using CENetOrg model" in r.stdout and re.search(r"Average Dice: ([0-9.]+)", r.stdout), r.stdout[-2000:]
+
+
 def test_main_skin_unchanged(tmp_path):
     d = str(tmp_path)
     ds = H.make_ph2(os.path.join(d, "PH2"), size=224)
