@@ -584,6 +584,16 @@ def run_product(args):
                     "peak_source": peaks["source"] + ", HBM copy",
                     "note": "op-level times of linear/gemm/conv_nhwc calls; a few fp32/batched calls on the CUDA-core GEMM "
                             "are in the time but not in the bytes (conservative)"}
+            # per-launch roofline: each launch against ITS bound, max(bytes / HBM peak, FLOPs / tensor peak)
+            gl = getattr(eng, "last_gemm_launches", [])
+            if gl:
+                t_roof = sum(max(by / (peaks["hbm_gbs"] * 1e9), fl / (peaks["tf_sustained"] * 1e12)) * 1e3 for _, _, by, fl, _ in gl)
+                t_act = sum(ms for *_, ms in gl)
+                roof["per_launch_view"] = {"t_roofline_ms": t_roof, "t_measured_ms": t_act, "frac": t_roof / t_act,
+                                           "note": "sum over launches of max(bytes/HBM peak, FLOPs/bf16 peak) / measured time"}
+                worst = sorted(gl, key=lambda r: -r[4])[:16]
+                roof["top_launches"] = [{"op": op, "tag": tag, "ms": round(ms, 4), "MB": round(by / 1e6, 1), "GFLOP": round(fl / 1e9, 2),
+                                         "GB/s": round(by / ms / 1e6), "TFLOP/s": round(fl / ms / 1e9, 1)} for op, tag, by, fl, ms in worst]
         # (b) the largest single launch: differential flash attention of the 56x56 DSE block (exp-bound)
         E1, N1 = 128, (SIZE // 4) ** 2
         ms_da, n_da = prof.get(("diffattn_flash", "se1"), (None, 0))

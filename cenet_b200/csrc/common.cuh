@@ -155,6 +155,41 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
+// Activation of 8 values with the dispatch OUTSIDE the element loop: a per-element `switch` serialises the eight dependent
+// chains (MUFU + division latency each) -- measured on the GEMM epilogue: SiLU cost 60 us per 12.8 M elements that way.
+// bf16 / tensor-core paths only: sigmoid uses the approximate division (2 ulp), far below the output rounding.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ void apply_act8(float (&v)[8], int act, float slope) {
+  switch (act) {
+    case CENET_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.0f);
+      break;
+    case CENET_ACT_LEAKY:
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = v[j] > 0.0f ? v[j] : v[j] * slope;
+      break;
+    case CENET_ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = v[j] * sigmoid_fast(v[j]);
+      break;
+    case CENET_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = sigmoid_fast(v[j]);
+      break;
+    case CENET_ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = gelu_erf(v[j]);
+      break;
+    case CENET_ACT_GELU_GRAD:
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        v[j] = 0.5f * (1.0f + erff(v[j] * 0.70710678118654752440f)) + v[j] * __expf(-0.5f * v[j] * v[j]) * 0.39894228040143267794f;
+      break;
+    default: break;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -116,6 +116,7 @@ struct TcParams {
   // conv mode
   int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
   int tile_h, tile_w;  // M tile in pixels: 8 x 16 (shifted boxes) or 16 x 8 (halo mode)
+  int tw_shift;        // log2(tile_w)
   int halo, Hh, Wh;    // halo mode: halo tile extent
   int ablk;            // bytes of one 8-channel block of a halo tile: Hh*Wh*16 rounded up to 128 (TMA destination alignment)
   EpiParams epi;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       tile_coords(tile, m0, img, h0, w0);
       auto row_index = [&](int r, long long& m) -> bool {
         if (p.conv) {
-          const int h = h0 + r / p.tile_w, w = w0 + r % p.tile_w;
+          const int h = h0 + (r >> p.tw_shift), w = w0 + (r & (p.tile_w - 1));        // tile_w is 8 or 16
           m = ((long long)img * p.H + h) * p.W + w;
           return (h < p.H) && (w < p.W);
         }
@@ -424,10 +425,14 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
         } else if (p.epi_vec) {
           const int cg = (lane & 3) * 8;
           const int n = nbase + cg;
-          float bcol[8];
+          float bcol[8], cs1[8];
 #pragma unroll
           for (int j = 0; j < 8; j++) bcol[j] = (e.bias && !e.bias_per_row && n + j < p.N) ? e.bias[n + j] : 0.f;
-#pragma unroll 1
+          // per-column residual scale: loaded ONCE per 8-column group (it used to be 8 dependent global loads per row,
+          // which made the decoder GEMMs with a BatchNorm-scaled shortcut 5x slower than their bytes allow)
+#pragma unroll
+          for (int j = 0; j < 8; j++) cs1[j] = e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale;
+#pragma unroll 2
           for (int itr = 0; itr < 4; itr++) {
             const int rr = itr * 8 + (lane >> 2);
             long long m;
@@ -439,45 +444,47 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
               v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
             }
-            const float rs = e.alpha * (e.row_scale ? e.row_scale[m / e.rs_div] : 1.f);
+            // (64-bit divisions only when a per-sample divisor is really in use)
+            const float rs = e.alpha * (e.row_scale ? e.row_scale[e.rs_div > 1 ? m / e.rs_div : m] : 1.f);
             const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
-            if (!e.act_after_res && e.act != CENET_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
-            }
             const bool full = n + 8 <= nlim;
+            // all operand rows are requested BEFORE any of them is used: three dependent load -> use sequences per row
+            // made this path latency-bound (2x the plain epilogue at the same bytes)
+            float tm[8], t1[8], t2[8];
             if (e.mul) {
-              float t[8];
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, t);
-              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, tm);
+              else for (int j = 0; j < 8; j++) tm[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
+            }
+            if (e.res1) {
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t1);
+              else for (int j = 0; j < 8; j++) t1[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
+            }
+            if (e.res2) {
+              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t2);
+              else for (int j = 0; j < 8; j++) t2[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
+            }
+            if (!e.act_after_res) apply_act8(v, e.act, e.slope);
+            if (e.mul) {
+              apply_act8(tm, e.mul_act, 0.f);
 #pragma unroll
-              for (int j = 0; j < 8; j++) v[j] *= apply_act(t[j], e.mul_act, 0.f);
+              for (int j = 0; j < 8; j++) v[j] *= tm[j];
             }
             if (e.post_rs) {
-              const float prs = e.post_rs[m / e.post_rs_div];
+              const float prs = e.post_rs[e.post_rs_div > 1 ? m / e.post_rs_div : m];
 #pragma unroll
               for (int j = 0; j < 8; j++) v[j] *= prs;
             }
             if (e.res1) {
-              float t[8];
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t);
-              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
 #pragma unroll
-              for (int j = 0; j < 8; j++) v[j] += t[j] * (e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale);
+              for (int j = 0; j < 8; j++) v[j] = fmaf(t1[j], cs1[j], v[j]);
             }
             if (e.res2) {
-              float t[8];
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t);
-              else for (int j = 0; j < 8; j++) t[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
 #pragma unroll
-              for (int j = 0; j < 8; j++) v[j] += t[j];
+              for (int j = 0; j < 8; j++) v[j] += t2[j];
             }
-            if (e.act_after_res && e.act != CENET_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] = apply_act(v[j], e.act, e.slope);
-            }
+            if (e.act_after_res) apply_act8(v, e.act, e.slope);
             if (full) {
               if (e.c_dtype == CENET_BF16) stv<8>(reinterpret_cast<bf16*>(e.C) + m * e.ldc + n, v);
               else stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
@@ -605,7 +612,7 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     // (its 72 KB filter bank leaves room for one CTA per SM only) -> halo mode for narrow outputs (N <= 32)
     p.halo = halo_on && a->KH > 1 && a->Cin % 16 == 0 && a->Cin <= 128 && pick_bn(a->N) <= 32 && a->N <= 32 &&
              (long long)p.num_kb * wblk_h <= 120 * 1024;
-    p.tile_h = p.halo ? 16 : TILE_H; p.tile_w = p.halo ? 8 : TILE_W;
+    p.tile_h = p.halo ? 16 : TILE_H; p.tile_w = p.halo ? 8 : TILE_W; p.tw_shift = p.halo ? 3 : 4;
     p.Hh = p.tile_h + 2 * a->pad; p.Wh = p.tile_w + 2 * a->pad;
     p.ablk = (p.Hh * p.Wh * 16 + 127) & ~127;
     p.tiles_h = cdiv(a->H, p.tile_h); p.tiles_w = cdiv(a->W, p.tile_w);
@@ -626,7 +633,7 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     if (encode_map(&tmW, a->Wt, 2, wd, ws, wb, swz)) return -1;
   } else {
     p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0;
-    p.halo = 0; p.Hh = p.Wh = p.ablk = 0; p.tile_h = TILE_H; p.tile_w = TILE_W;
+    p.halo = 0; p.Hh = p.Wh = p.ablk = 0; p.tile_h = TILE_H; p.tile_w = TILE_W; p.tw_shift = 4;
     p.bk = 64;
     p.num_kb = cdiv(a->K, 64);
     p.num_m_tiles = cdiv(a->M, BM);

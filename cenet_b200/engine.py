@@ -44,6 +44,7 @@ class _TimedOps:
     def __init__(self, inner):
         self._inner = inner
         self.records = []          # (op name, tag, start event, end event)
+        self.gemm_launches = []    # (op, tag, algorithmic bytes, FLOPs, start, end) of every tensor-core GEMM / conv launch
         self.work = {}             # op name -> [algorithmic bytes, FLOPs, launches] of the tensor-core GEMM / conv calls
         self.tag = ""
 
@@ -86,6 +87,7 @@ class _TimedOps:
                 if wk is not None:
                     acc = self.work.setdefault(name, [0.0, 0.0, 0])
                     acc[0] += wk[0]; acc[1] += wk[1]; acc[2] += 1
+                    self.gemm_launches.append((name, self.tag, wk[0], wk[1], e0, e1))
             return r
         return timed
 
@@ -731,4 +733,6 @@ class Engine:
         finally:
             ops = real
         self.last_gemm_work = {k: (v[0] / steps, v[1] / steps, v[2] // steps) for k, v in timed.work.items()}
+        n1 = len(timed.gemm_launches) // steps                     # per-launch list of the LAST pass
+        self.last_gemm_launches = [(op, tag, by, fl, e0.elapsed_time(e1)) for op, tag, by, fl, e0, e1 in timed.gemm_launches[-n1:]]
         return {k: (t / steps, n // steps) for k, (t, n) in timed.summary().items()}

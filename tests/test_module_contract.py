@@ -68,8 +68,9 @@ def test_error_conventions():
         CENet(dec_up_block="bogus")                                    # decoders.py:47
     with pytest.raises(AssertionError):
         CENet(out_merge_mode="bogus")                                  # out.py:31
+    CENetOrg()                                                         # f2: built (inference path)
     with pytest.raises(NotImplementedError):
-        CENetOrg()
+        CENetOrg(skip_mode="add")
     CENet(encoder="not_an_encoder")                                    # encoder.py:48-52: silent fallback to b2
 
 
