@@ -24,6 +24,12 @@ class AttnTcArgs(C.Structure):
                 ("B", i32), ("heads", i32), ("Nq", i32), ("Nk", i32), ("D", i32), ("scale", f32), ("lse_base2", i32)]
 
 
+class WgradJob(C.Structure):
+    """Mirror of `cenet_wgrad_job` (include/cenet_b200.h)."""
+    _fields_ = [("src", vp), ("dst", vp), ("stride", ll), ("S", i32), ("N", i32), ("K", i32), ("T", i32), ("blk0", i32),
+                ("reserved", i32)]
+
+
 class GemmArgs(C.Structure):
     """Mirror of `cenet_gemm_args` (include/cenet_b200.h)."""
     _fields_ = [
@@ -78,6 +84,9 @@ _SIGS = {
     # ---- training (see include/cenet_b200.h) ----
     "cenet_dwconv3x3_train": [vp, i32, ll, vp, i32, ll, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
     "cenet_gemm_wgrad": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, vp, vp, i32, vp, ll, vp],
+    "cenet_gemm_wgrad_partial": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, ll,
+                                 C.POINTER(i32), C.POINTER(i32), vp],
+    "cenet_wgrad_reduce_batch": [vp, i32, i32, vp],
     "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
     "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
     "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, ll, vp],
@@ -125,6 +134,8 @@ _PLAIN = {  # no stream, different return types
     "cenet_launch_count": ([], ll),
     "cenet_ccu_nchunk": ([i32], i32),
     "cenet_loss_nblocks": ([ll], i32),
+    "cenet_wgrad_reduce_blocks": ([C.POINTER(WgradJob)], i32),
+    "cenet_wgrad_plan_query": ([ll, i32, i32, i32, i32, i32, ll, C.POINTER(i32)], i32),
 }
 EXPORTS = sorted(list(_SIGS) + list(_PLAIN))
 

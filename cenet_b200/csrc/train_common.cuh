@@ -10,6 +10,11 @@
 
 constexpr int kColThreads = 256;
 
+// tile / split plan of the tcgen05 weight-gradient kernel (wgrad_tc.cu)
+struct cenet_wgrad_plan {
+  int bn, S, per_group, parts, cps, cpg, groups, rows_per_group, total_chunks;
+};
+
 struct ColPlan {
   int V, ngrp, nrl, nrb, rows_per_block, gy;
 };

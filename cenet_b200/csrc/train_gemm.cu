@@ -235,6 +235,75 @@ __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __
       if (c0 + v < C) ws[(size_t)blockIdx.x * C + c0 + v] = s1[v];
   }
 }
+
+// ---- deferred, batched reduction of weight-gradient partials --------------------------------------------------------------
+// One launch reduces the partials of MANY weight-gradient GEMMs (a whole gradient bucket): job j owns the blocks
+// [blk0_j, blk0_{j+1}).  A block is 256 threads = `sl` split lanes x 256/sl outputs; lane l adds the partials z = l, l+sl, ...
+// and the lanes are then added in lane order (fixed summation order -> bit-reproducible, no float atomics).
+__host__ __device__ inline int wgrad_reduce_lanes(int S) { return S <= 8 ? 1 : (S <= 64 ? 8 : 32); }
+__host__ __device__ inline bool wgrad_reduce_vec(const cenet_wgrad_job& j) {
+  return j.T == 1 && (((long long)j.N * j.K) & 3) == 0 && (j.stride & 3) == 0 && ((((uintptr_t)j.src) | ((uintptr_t)j.dst)) & 15) == 0;
+}
+__global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const cenet_wgrad_job* __restrict__ jobs, int njobs) {
+  __shared__ int sj;
+  __shared__ float4 red[256];
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {                                  // last job whose first block is <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    sj = lo;
+  }
+  __syncthreads();
+  const cenet_wgrad_job j = jobs[sj];
+  const int lb = blockIdx.x - j.blk0;
+  const int sl = wgrad_reduce_lanes(j.S), per = 256 / sl;
+  const int o = threadIdx.x % per, lane = threadIdx.x / per;
+  const long long nk = (long long)j.N * j.K;
+  if (wgrad_reduce_vec(j)) {
+    const long long i = (long long)lb * per + o, nk4 = nk >> 2, st4 = j.stride >> 2;
+    const float4* src = reinterpret_cast<const float4*>(j.src);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nk4) {
+#pragma unroll 4
+      for (int z = lane; z < j.S; z += sl) {
+        const float4 v = src[(size_t)z * st4 + i];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    }
+    if (sl > 1) {
+      red[threadIdx.x] = a;
+      __syncthreads();
+      if (lane == 0) {
+        for (int l = 1; l < sl; l++) {
+          const float4 v = red[l * per + o];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      }
+    }
+    if (lane == 0 && i < nk4) reinterpret_cast<float4*>(j.dst)[i] = a;
+  } else {
+    const long long i = (long long)lb * per + o;
+    float a = 0.f;
+    if (i < nk) {
+#pragma unroll 4
+      for (int z = lane; z < j.S; z += sl) a += j.src[(size_t)z * j.stride + i];
+    }
+    if (sl > 1) {
+      float* r1 = reinterpret_cast<float*>(red);
+      r1[threadIdx.x] = a;
+      __syncthreads();
+      if (lane == 0)
+        for (int l = 1; l < sl; l++) a += r1[l * per + o];
+    }
+    if (lane == 0 && i < nk) {
+      const int n = (int)(i / j.K), k = (int)(i % j.K), Cin = j.K / j.T;
+      const int tt = k / Cin, ci = k % Cin;
+      j.dst[(size_t)n * j.K + (size_t)ci * j.T + tt] = a;            // k = (tap, ci) -> the reference's [Cout, Cin, KH, KW]
+    }
+  }
+}
 }  // namespace
 
 static inline void launch_wgrad_finalize(const float* ws, int S, int N, int K, int T, float* dw, cudaStream_t s) {
@@ -266,15 +335,18 @@ int launch_colsum(const void* x, int dtype, long long ld, long long rows, int C,
 
 bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
                              int K, const float* rs, int rs_div);
-int cenet_wgrad_tc(const void* dy, long long ldy, const void* x, long long ldx, long long M, int N, int K, const float* rs, int rs_div,
-                   float* ws, long long ws_elems, cudaStream_t s);
+void cenet_wgrad_tc_plan(long long M, int N, int K, bool has_rs, int rs_div, bool binary, long long max_partials, cenet_wgrad_plan* pl);
+int cenet_wgrad_tc_launch(const cenet_wgrad_plan* pl, const void* dy, long long ldy, const void* x, long long ldx, int N, int K,
+                          const float* rs, bool binary, float* out, long long out_stride, float* bias, long long bias_stride,
+                          cudaStream_t s);
 
 bool cenet_conv_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int Cin, int N,
                                   int ksize);
 int cenet_conv_wgrad_tc(const void* dy, const void* x, int B, int H, int W, int Cin, int ksize, int N, float* ws, long long ws_elems,
                         cudaStream_t s);
 
-static int launch_wgrad_mma(WgParams p, int T, float* dw, long long ws_elems, cudaStream_t s) {
+// mma.sync path: writes S partials [N][K] into p.ws and returns S
+static int launch_wgrad_mma(WgParams p, long long ws_elems, cudaStream_t s) {
   const long long nk = (long long)p.N * p.K;
   const int ntiles = cdiv(p.N, TN) * cdiv(p.K, TK);
   long long want = cdiv(3 * kNumSMs, ntiles);
@@ -289,9 +361,7 @@ static int launch_wgrad_mma(WgParams p, int T, float* dw, long long ws_elems, cu
   CENET_REQUIRE(grid.y <= 65535, "wgrad: K too large");
   wgrad_mma_kernel<<<grid, WG_THREADS, 0, s>>>(p);
   CENET_LAUNCH_CHECK("wgrad_mma");
-  launch_wgrad_finalize(p.ws, S, p.N, p.K, T, dw, s);
-  CENET_LAUNCH_CHECK("wgrad_finalize");
-  return 0;
+  return S;
 }
 
 // weight gradient of a dense stride-1 "same" conv without materialising im2col: x is the NHWC image [B,H,W,Cin] (pitch ldx)
@@ -317,25 +387,51 @@ extern "C" int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, con
   p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
   p.conv = 1; p.H = H; p.W = W; p.Cin = Cin; p.KS = ksize; p.pad = ksize / 2;
   CENET_REQUIRE((long long)N * p.K <= ws_elems, "cenet_conv_wgrad: workspace too small");
-  return launch_wgrad_mma(p, ksize * ksize, dw, ws_elems, to_stream(st));
+  const int S = launch_wgrad_mma(p, ws_elems, to_stream(st));
+  if (S < 0) return -1;
+  launch_wgrad_finalize(ws, S, N, p.K, ksize * ksize, dw, to_stream(st));
+  CENET_LAUNCH_CHECK("wgrad_finalize");
+  return 0;
 }
 
-extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M,
-                                int N, int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias,
-                                int bias_unscaled, float* ws, long long ws_elems, cenet_stream_t st) {
-  CENET_REQUIRE(dy && x && dw && ws, "cenet_gemm_wgrad: null pointer");
+// Partial products of one weight-gradient GEMM.  On return *n_partials == 0 means dw (and dbias) already hold the final
+// result; otherwise ws holds S = *n_partials partial matrices [N][K] (S*N*K floats), followed -- when *bias_partials != 0 -- by
+// S partial bias rows [N]; they are reduced by cenet_wgrad_reduce_batch (any number of GEMMs in one launch) or, in
+// cenet_gemm_wgrad, immediately.
+extern "C" int cenet_gemm_wgrad_partial(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx,
+                                        long long M, int N, int K, int T, const float* row_scale, int rs_div, int rs_binary,
+                                        float* dw, float* dbias, int bias_unscaled, float* ws, long long ws_elems, int* n_partials,
+                                        int* bias_partials, cenet_stream_t st) {
+  CENET_REQUIRE(dy && x && dw && ws && n_partials && bias_partials, "cenet_gemm_wgrad: null pointer");
   CENET_REQUIRE(M > 0 && N > 0 && K > 0 && T >= 1 && K % T == 0, "cenet_gemm_wgrad: bad shape M=%lld N=%d K=%d T=%d", M, N, K, T);
   CENET_REQUIRE(rs_div >= 1, "cenet_gemm_wgrad: rs_div must be >= 1");
   cudaStream_t s = to_stream(st);
-  if (dbias) {
-    if (launch_colsum(dy, dy_dtype, ldy, M, N, bias_unscaled ? nullptr : row_scale, rs_div, dbias, ws, ws_elems, s)) return -1;
-  }
+  *n_partials = 0; *bias_partials = 0;
   const long long nk = (long long)N * K;
   CENET_REQUIRE(nk <= ws_elems, "cenet_gemm_wgrad: workspace too small (N*K = %lld)", nk);
+  static const bool use_tc = getenv("CENET_B200_WGRAD_TC") == nullptr || atoi(getenv("CENET_B200_WGRAD_TC")) != 0;
+  const bool tc = use_tc && cenet_wgrad_tc_eligible(dy, dy_dtype, ldy, x, x_dtype, ldx, M, N, K, row_scale, rs_div);
+  cenet_wgrad_plan pl = {};
+  const bool bias_in_tc = tc && dbias && !(bias_unscaled && row_scale);
+  bool tc_ok = false;
+  if (tc) {
+    cenet_wgrad_tc_plan(M, N, K, row_scale != nullptr, rs_div, rs_binary != 0, ws_elems / (nk + (bias_in_tc ? N : 0)), &pl);
+    tc_ok = (long long)pl.S * (nk + (bias_in_tc ? N : 0)) <= ws_elems;      // (a per-group plan cannot go below one split per group)
+  }
+  if (dbias && !(tc_ok && bias_in_tc)) {
+    if (launch_colsum(dy, dy_dtype, ldy, M, N, bias_unscaled ? nullptr : row_scale, rs_div, dbias, ws, ws_elems, s)) return -1;
+  }
+  if (tc_ok) {
+    const bool direct = pl.S == 1 && T == 1;
+    float* out = direct ? dw : ws;
+    float* bout = bias_in_tc ? (direct ? dbias : ws + (size_t)pl.S * nk) : nullptr;
+    if (cenet_wgrad_tc_launch(&pl, dy, ldy, x, ldx, N, K, row_scale, rs_binary != 0, out, nk, bout, N, s)) return -1;
+    if (!direct) { *n_partials = pl.S; *bias_partials = bias_in_tc ? 1 : 0; }
+    return 0;
+  }
   int S;
   if (dy_dtype == CENET_F32 && x_dtype == CENET_F32) {
     // validation precision: CUDA-core GEMM  C_z[N,K] = A_z^T W_z  over row chunks, z = split
-    CENET_REQUIRE(row_scale == nullptr || rs_div >= 1, "cenet_gemm_wgrad");
     S = 1;
     for (int c = 2; c <= 64; c++)
       if (M % c == 0 && (long long)c * nk <= ws_elems && M / c >= 64) S = c;
@@ -349,25 +445,45 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
     g.k_scale = row_scale; g.k_scale_div = rs_div; g.k_scale_bs = chunk;
     if (cenet_gemm_simt(&g, s)) return -1;
   } else {
-    static const bool use_tc = getenv("CENET_B200_WGRAD_TC") == nullptr || atoi(getenv("CENET_B200_WGRAD_TC")) != 0;
-    if (use_tc && cenet_wgrad_tc_eligible(dy, dy_dtype, ldy, x, x_dtype, ldx, M, N, K, row_scale, rs_div)) {
-      const int St = cenet_wgrad_tc(dy, ldy, x, ldx, M, N, K, row_scale, rs_div, ws, ws_elems, s);
-      if (St == -1) return -1;
-      if (St > 0) {
-        launch_wgrad_finalize(ws, St, N, K, T, dw, s);
-        CENET_LAUNCH_CHECK("wgrad_finalize");
-        return 0;
-      }
-    }
     WgParams p = {};
     p.dy = dy; p.dy_dtype = dy_dtype; p.ldy = ldy; p.x = x; p.x_dtype = x_dtype; p.ldx = ldx;
     p.M = M; p.N = N; p.K = K; p.rs = row_scale; p.rs_div = rs_div;
     p.ws = ws;
     p.fast_y = dy_dtype == CENET_BF16 && ldy % 8 == 0 && ((uintptr_t)dy & 15) == 0;
     p.fast_x = x_dtype == CENET_BF16 && ldx % 8 == 0 && ((uintptr_t)x & 15) == 0;
-    return launch_wgrad_mma(p, T, dw, ws_elems, s);
+    S = launch_wgrad_mma(p, ws_elems, s);
+    if (S < 0) return -1;
   }
+  *n_partials = S;
+  return 0;
+}
+
+extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M,
+                                int N, int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias,
+                                int bias_unscaled, float* ws, long long ws_elems, cenet_stream_t st) {
+  int S = 0, bp = 0;
+  if (cenet_gemm_wgrad_partial(dy, dy_dtype, ldy, x, x_dtype, ldx, M, N, K, T, row_scale, rs_div, 0, dw, dbias, bias_unscaled, ws,
+                               ws_elems, &S, &bp, st))
+    return -1;
+  if (S == 0) return 0;
+  cudaStream_t s = to_stream(st);
   launch_wgrad_finalize(ws, S, N, K, T, dw, s);
   CENET_LAUNCH_CHECK("wgrad_finalize");
+  if (bp) return launch_finalize(ws + (size_t)S * N * K, S, N, dbias, N, nullptr, 1.f, s);
+  return 0;
+}
+
+// number of 256-thread blocks job j needs in cenet_wgrad_reduce_batch (the caller lays out blk0 with it)
+extern "C" int cenet_wgrad_reduce_blocks(const cenet_wgrad_job* j) {
+  const long long nk = (long long)j->N * j->K;
+  const int per = 256 / wgrad_reduce_lanes(j->S);
+  return cdiv(wgrad_reduce_vec(*j) ? nk / 4 : nk, per);
+}
+
+// jobs: DEVICE array of njobs descriptors whose blk0 fields are the running sum of cenet_wgrad_reduce_blocks; nblocks = the total
+extern "C" int cenet_wgrad_reduce_batch(const cenet_wgrad_job* jobs, int njobs, int nblocks, cenet_stream_t st) {
+  CENET_REQUIRE(jobs && njobs > 0 && nblocks > 0, "cenet_wgrad_reduce_batch: empty job list");
+  wgrad_reduce_batch_kernel<<<nblocks, 256, 0, to_stream(st)>>>(jobs, njobs);
+  CENET_LAUNCH_CHECK("wgrad_reduce_batch");
   return 0;
 }

@@ -13,6 +13,8 @@
 #include "train_common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 constexpr int WT_THREADS = 192;
@@ -220,13 +222,24 @@ struct WtParams {
   int N, K;               // output rows (dY columns) / columns (X columns)
   int bn;                 // X-column tile: multiple of 64, <= 256
   int stages, tmem_cols;
-  int rows_per_group;     // rows of one group (sample)
-  int parts;              // splits per group
-  int rows_per_part;      // multiple of 64
+  int rows_per_group;     // rows of one group (sample); M when there is no row scale
+  int groups, cpg;        // groups, 64-row chunks per group
+  int per_group;          // 1: a split stays inside one group (arbitrary per-sample scale, applied in the epilogue)
+  int parts;              // per_group: splits per group
+  int cps;                // chunks per split
+  int total_chunks;       // flat mode: groups * cpg
+  int binary;             // flat mode with a row scale: rs is {0, c} -- groups with rs == 0 are skipped, c scales the result
   const float* rs;        // per-group scale or NULL
-  float* ws;              // [S][N][K]
+  float* out;             // partial z -> out + z * out_stride, [N][K]   (the final gradient itself when there is one split)
+  long long out_stride;
+  float* bias;            // column sums of dY (bias gradient): partial z -> bias + z * bias_stride, [N]; NULL: not wanted
+  long long bias_stride;
 };
 
+// One CTA = one 128 (n) x bn (k) tile of one split.  Flat mode walks the 64-row chunks [z*cps, (z+1)*cps) of the
+// (group, chunk) enumeration and -- with a binary DropPath mask -- skips the chunks of dropped samples, so the number of
+// splits no longer grows with the batch.  The bias gradient rides along as one more N=16 MMA per k-step against a constant
+// all-ones B tile (columns [bn, bn+16) of the accumulator; only the CTAs of the first k tile do it).
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                 const __grid_constant__ CUtensorMap tmX, const WtParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -234,16 +247,28 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xboxes = p.bn / 64;
   const uint32_t stage_bytes = (2 + xboxes) * BOX_BYTES;
-  const uint32_t bar_base = sbase + p.stages * stage_bytes;
+  const uint32_t ones_base = sbase + p.stages * stage_bytes;          // 2 KB of bf16 1.0 (16 contraction rows x 64 columns)
+  const uint32_t bar_base = ones_base + 2048;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (p.stages + s) * 8; };
   const uint32_t tfull_bar = bar_base + 2 * p.stages * 8;
   const uint32_t tmem_slot = tfull_bar + 8;
   const int n0 = blockIdx.x * 128, k0 = blockIdx.y * p.bn;
-  const int z = blockIdx.z, grp = z / p.parts, part = z % p.parts;
-  const int row_lo = part * p.rows_per_part;
-  const int row_hi = min(p.rows_per_group, row_lo + p.rows_per_part);
-  const int nchunks = (row_hi - row_lo + CH - 1) / CH;
+  const int z = blockIdx.z;
+  const bool do_bias = p.bias != nullptr && blockIdx.y == 0;
+  // this split's chunk range: [c_lo, c_hi) of group grp0 (per_group) or of the flat (group, chunk) enumeration
+  int grp0, cig0, nwalk;
+  if (p.per_group) {
+    grp0 = z / p.parts;
+    cig0 = (z % p.parts) * p.cps;
+    nwalk = max(0, min(p.cpg, cig0 + p.cps) - cig0);
+  } else {
+    const int g0 = z * p.cps;
+    grp0 = g0 / p.cpg;
+    cig0 = g0 % p.cpg;
+    nwalk = max(0, min(p.total_chunks, g0 + p.cps) - g0);
+  }
+  const bool mask = p.binary && p.rs != nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
@@ -256,6 +281,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (do_bias && warp >= 2) {                      // 128 threads x 16 bytes = the 2 KB ones tile
+    const uint32_t a = ones_base + (threadIdx.x - 64) * 16;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0x3F803F80u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,52 +296,87 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;                               // ring position kept incrementally: no integer division on the issue path
-      for (int c = 0; c < nchunks; c++) {
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = sbase + s * stage_bytes;
-        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-        const int r0 = row_lo + c * CH;
-        tma_load_3d(sa, &tmY, full_bar(s), n0, r0, grp);
-        tma_load_3d(sa + BOX_BYTES, &tmY, full_bar(s), n0 + 64, r0, grp);
-        for (int j = 0; j < xboxes; j++) tma_load_3d(sa + (2 + j) * BOX_BYTES, &tmX, full_bar(s), k0 + 64 * j, r0, grp);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+      int grp = grp0, cig = cig0;
+      bool live = !mask || p.rs[grp < p.groups ? grp : 0] != 0.f;
+      for (int c = 0; c < nwalk; c++) {
+        if (live) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = sbase + s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          const int r0 = cig * CH;
+          tma_load_3d(sa, &tmY, full_bar(s), n0, r0, grp);
+          tma_load_3d(sa + BOX_BYTES, &tmY, full_bar(s), n0 + 64, r0, grp);
+          for (int j = 0; j < xboxes; j++) tma_load_3d(sa + (2 + j) * BOX_BYTES, &tmX, full_bar(s), k0 + 64 * j, r0, grp);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if (++cig == p.cpg) {
+          cig = 0; grp++;
+          live = !mask || (grp < p.groups && p.rs[grp] != 0.f);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), A and B MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.bn >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = idesc0 | ((uint32_t)(p.bn >> 3) << 17);
+      const uint32_t idesc_b = idesc0 | ((uint32_t)(16 >> 3) << 17);
+      const uint64_t odesc = make_desc_mn(ones_base, BOX_BYTES, 1024);
       int s = 0;
       uint32_t ph = 0;
-      for (int c = 0; c < nchunks; c++) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = sbase + s * stage_bytes;
-        const uint64_t adesc = make_desc_mn(sa, BOX_BYTES, 1024), bdesc = make_desc_mn(sa + 2 * BOX_BYTES, BOX_BYTES, 1024);
+      uint32_t started = 0;
+      int grp = grp0, cig = cig0;
+      bool live = !mask || p.rs[grp < p.groups ? grp : 0] != 0.f;
+      for (int c = 0; c < nwalk; c++) {
+        if (live) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = sbase + s * stage_bytes;
+          const uint64_t adesc = make_desc_mn(sa, BOX_BYTES, 1024), bdesc = make_desc_mn(sa + 2 * BOX_BYTES, BOX_BYTES, 1024);
 #pragma unroll
-        for (int k = 0; k < CH / 16; k++)      // 16 contraction rows = two 8-row groups = 2048 bytes = +128 in the address field
-          umma_f16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (c | k) != 0);
-        umma_commit(empty_bar(s));
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+          for (int k = 0; k < CH / 16; k++) {    // 16 contraction rows = two 8-row groups = 2048 bytes = +128 in the address field
+            umma_f16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, started | k);
+            if (do_bias) umma_f16(tmem_base + p.bn, adesc + (uint64_t)(128 * k), odesc, idesc_b, started | k);
+          }
+          started = 1;
+          umma_commit(empty_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if (++cig == p.cpg) {
+          cig = 0; grp++;
+          live = !mask || (grp < p.groups && p.rs[grp] != 0.f);
+        }
       }
       umma_commit(tfull_bar);
     }
   } else {
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read (warps 2..5 -> 2,3,0,1)
     const int n = n0 + quarter * 32 + lane;
+    // scale of this split and whether any chunk was accumulated at all (an untouched accumulator holds garbage)
     float scale = 1.f;
-    if (p.rs) scale = p.rs[grp];
+    bool any = nwalk > 0;
+    if (p.rs) {
+      if (p.per_group) {
+        scale = p.rs[grp0];
+      } else if (mask) {
+        float c = 0.f;
+        for (int g = 0; g < p.groups; g++) c = fmaxf(c, p.rs[g]);     // the common value of the kept samples
+        scale = c;
+        any = false;
+        const int g_last = nwalk > 0 ? (z * p.cps + nwalk - 1) / p.cpg : -1;
+        for (int g = grp0; g <= g_last && g < p.groups; g++) any |= p.rs[g] != 0.f;
+      }
+    }
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    float* out = p.ws + ((size_t)z * p.N + n) * p.K;
+    float* out = p.out + (size_t)z * p.out_stride + (size_t)n * p.K;
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       if (k0 + c0 >= p.K) break;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, acc);
       tmem_ld_wait();
       if (n < p.N) {
-        if (nchunks == 0) {
+        if (!any) {
 #pragma unroll
           for (int j = 0; j < 32; j++) acc[j] = 0u;
         }
@@ -326,6 +391,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
           for (int j = 0; j < 32 && kk + j < p.K; j++) out[kk + j] = __uint_as_float(acc[j]) * scale;
         }
       }
+    }
+    if (do_bias) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)p.bn, acc);
+      tmem_ld_wait();
+      if (n < p.N) p.bias[(size_t)z * p.bias_stride + n] = any ? __uint_as_float(acc[0]) * scale : 0.f;
     }
   }
   tc_fence_before();
@@ -420,54 +491,105 @@ int cenet_conv_wgrad_tc(const void* dy, const void* x, int B, int H, int W, int 
   return grid;
 }
 
-namespace {
-}
-
 // eligibility: bf16 operands, 16-byte aligned bases and pitches, per-sample (or no) row scale
 bool cenet_wgrad_tc_eligible(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
                              int K, const float* rs, int rs_div) {
   if (dy_dtype != CENET_BF16 || x_dtype != CENET_BF16) return false;
   if (ldy % 8 || ldx % 8 || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15)) return false;
-  if (M < 512 || N < 32 || K < 32) return false;
+  if (M < 512 || N < 32 || K < 8) return false;
   if (rs && (rs_div < 16 || M % rs_div != 0)) return false;      // a group shorter than the 64-row TMA box is zero-filled (7x7 level: 49)
   return true;
 }
 
-// writes S partial tiles [N][K] into ws and returns S (or -1)
-int cenet_wgrad_tc(const void* dy, long long ldy, const void* x, long long ldx, long long M, int N, int K, const float* rs, int rs_div,
-                   float* ws, long long ws_elems, cudaStream_t s) {
+// Tile width and split count.  A CTA's time is modelled as pipeline fill + chunks x max(MMA, shared-memory fill) + epilogue,
+// the reduction of S partials as their write + read; the (bn, S) pair with the smallest estimate wins.  Few, long splits
+// for large outputs over short contractions (stage 3/4: N*K up to 2 M, M = 1-5 k rows), many splits of a narrow tile for the
+// small outputs over long contractions (stage 1, head: N*K = 4-16 k, M = 75 k-1.2 M rows).
+static inline int wt_stages(int bn) { return bn <= 64 ? 4 : (bn <= 128 ? 5 : 4); }   // 96 / 160 / 160 / 192 KB rings
+void cenet_wgrad_tc_plan(long long M, int N, int K, bool has_rs, int rs_div, bool binary, long long max_partials, cenet_wgrad_plan* pl) {
+  const bool per_group = has_rs && !binary;
+  pl->groups = (int)(has_rs ? M / rs_div : 1);
+  pl->rows_per_group = (int)(has_rs ? rs_div : M);
+  pl->cpg = cdiv(pl->rows_per_group, CH);
+  pl->total_chunks = pl->groups * pl->cpg;
+  pl->per_group = per_group;
   const long long nk = (long long)N * K;
+  const int walk = per_group ? pl->cpg : pl->total_chunks;          // chunks one "unit" (group / whole problem) offers for splitting
+  const int units = per_group ? pl->groups : 1;
+  double best = 1e30;
+  pl->bn = 64; pl->parts = 1; pl->cps = walk;
+  const int kr = (K + 63) / 64 * 64;
+  // Calibrated on the B200 (tools/sweep_wgrad.py): the best plans put about one CTA on every SM; their time is the bytes all
+  // CTAs pull through L2 (~5 TB/s for these boxes: every dY tile is re-read once per k tile, every X tile once per n tile)
+  // unless a CTA's own chain of chunks (tensor pipe / fill bandwidth / TMA round trip over the ring depth) is longer.
+  for (int bn = 64; bn <= 256 && bn <= std::max(64, kr); bn += 64) {
+    const int tiles = cdiv(N, 128) * cdiv(K, bn);
+    const int occ = bn == 64 ? 2 : 1;
+    const double eb = (std::min(128, N) + std::min(bn, K)) * 128.0;            // bytes a chunk really fetches (OOB box parts are free)
+    const double t_mma = 128.0 * bn * 64 * 2 / 9.0e6, t_fill = eb / 0.12e6;
+    const double t_lat = 2.4 / wt_stages(bn);                                  // loaded TMA round trip hidden by the ring depth
+    const double t_epi = 128.0 * std::min(bn, kr) * 4 / 0.12e6;
+    const double t_mem = (double)tiles * units * (double)walk * eb / 5.0e6;
+    const int target = std::max(1, (int)((kNumSMs + tiles * units / 2) / ((long long)tiles * units)));
+    const int cand[4] = {target, std::max(1, target / 2), target * 2, 1};
+    for (int ci = 0; ci < 4; ci++) {
+      const int parts = std::min(cand[ci], std::max(1, walk / 2));
+      const int cps = cdiv(walk, parts);
+      const int rparts = cdiv(walk, cps);
+      const long long S = (long long)units * rparts;
+      if (S > max_partials || S > 65535) continue;
+      const long long ctas = S * tiles;
+      const long long waves = (ctas + (long long)kNumSMs * occ - 1) / ((long long)kNumSMs * occ);
+      const double share = ctas > kNumSMs ? std::min((double)occ, (double)ctas / kNumSMs) : 1.0;   // co-resident CTAs share an SM
+      const double t_cta = 2.5 + cps * std::max(share * std::max(t_mma, t_fill), t_lat) + share * t_epi;
+      double t = std::max(waves * t_cta, t_mem);
+      if (S > 1) t += (double)S * nk * 8 / 10.0e6;                 // write + batched read of the partials
+      if (t < best) { best = t; pl->bn = bn; pl->parts = rparts; pl->cps = cps; }
+    }
+  }
+  if (const char* f = getenv("CENET_B200_WGRAD_PLAN")) {            // tuning override: "bn,parts"
+    int fbn = 0, fparts = 0;
+    if (sscanf(f, "%d,%d", &fbn, &fparts) == 2 && fbn >= 64 && fbn <= 256 && fbn % 64 == 0 && fparts >= 1) {
+      fparts = std::min(fparts, walk);
+      pl->bn = std::min(fbn, std::max(64, kr));
+      pl->cps = cdiv(walk, fparts);
+      pl->parts = cdiv(walk, pl->cps);
+    }
+  }
+  pl->S = units * pl->parts;
+}
+
+// host-only introspection of the plan (tools/one_wgrad.py, tests): out = {bn, S, per_group, parts, cps, cpg, groups, rows_per_group,
+// total_chunks}
+extern "C" int cenet_wgrad_plan_query(long long M, int N, int K, int has_rs, int rs_div, int binary, long long max_partials, int* out) {
+  cenet_wgrad_plan pl = {};
+  cenet_wgrad_tc_plan(M, N, K, has_rs != 0, rs_div, binary != 0, max_partials, &pl);
+  const int v[9] = {pl.bn, pl.S, pl.per_group, pl.parts, pl.cps, pl.cpg, pl.groups, pl.rows_per_group, pl.total_chunks};
+  for (int i = 0; i < 9; i++) out[i] = v[i];
+  return 0;
+}
+
+int cenet_wgrad_tc_launch(const cenet_wgrad_plan* pl, const void* dy, long long ldy, const void* x, long long ldx, int N, int K,
+                          const float* rs, bool binary, float* out, long long out_stride, float* bias, long long bias_stride,
+                          cudaStream_t s) {
   WtParams p = {};
-  p.N = N; p.K = K; p.rs = rs; p.ws = ws;
-  const int kt = cdiv(K, 256);
-  p.bn = (cdiv(K, kt) + 63) / 64 * 64;
-  const int tiles = cdiv(N, 128) * cdiv(K, p.bn);
-  const long long groups = rs ? M / rs_div : 1;
-  p.rows_per_group = (int)(rs ? rs_div : M);
-  // splits: enough CTAs to fill the machine, at least 256 rows each, bounded by the workspace
-  long long want = cdiv(2 * kNumSMs, tiles);
-  long long max_ws = ws_elems / nk;
-  if (max_ws < groups) return -2;                                   // caller falls back
-  long long parts = std::max<long long>(1, want / groups);
-  parts = std::min<long long>(parts, std::max<long long>(1, p.rows_per_group / 256));
-  parts = std::min<long long>(parts, max_ws / groups);
-  p.rows_per_part = (int)(((p.rows_per_group + parts - 1) / parts + CH - 1) / CH * CH);
-  p.parts = (p.rows_per_group + p.rows_per_part - 1) / p.rows_per_part;
-  const long long S = groups * p.parts;
-  if (S > 65535) return -2;
+  p.N = N; p.K = K; p.rs = rs; p.bn = pl->bn;
+  p.rows_per_group = pl->rows_per_group; p.groups = pl->groups; p.cpg = pl->cpg; p.per_group = pl->per_group;
+  p.parts = pl->parts; p.cps = pl->cps; p.total_chunks = pl->total_chunks; p.binary = binary ? 1 : 0;
+  p.out = out; p.out_stride = out_stride; p.bias = bias; p.bias_stride = bias_stride;
   CUtensorMap tmY, tmX;
-  if (encode_3d(&tmY, dy, N, ldy, p.rows_per_group, groups)) return -1;
-  if (encode_3d(&tmX, x, K, ldx, p.rows_per_group, groups)) return -1;
+  if (encode_3d(&tmY, dy, N, ldy, p.rows_per_group, p.groups)) return -1;
+  if (encode_3d(&tmX, x, K, ldx, p.rows_per_group, p.groups)) return -1;
   const int stage_bytes = (2 + p.bn / 64) * BOX_BYTES;
-  p.stages = 4;
+  p.stages = wt_stages(p.bn);
   int cols = 32;
-  while (cols < p.bn) cols <<= 1;
+  while (cols < p.bn + (bias ? 16 : 0)) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 16 + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 2048 + (2 * p.stages + 2) * 8 + 16 + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] { cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
-  dim3 grid(cdiv(N, 128), cdiv(K, p.bn), (unsigned)S);
+  dim3 grid(cdiv(N, 128), cdiv(K, p.bn), (unsigned)pl->S);
   wgrad_tc_kernel<<<grid, WT_THREADS, smem, s>>>(tmY, tmX, p);
   CENET_LAUNCH_CHECK("wgrad_tc");
-  return (int)S;
+  return 0;
 }

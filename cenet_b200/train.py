@@ -161,6 +161,7 @@ class TrainEngine:
         self._written = set()
         self.tape = TrainEngine._Tape()
         self._graphs = {}
+        self._wg_pending, self._wg_off, self._wg_flush_idx, self._wg_tables = [], 0, 0, {}   # deferred wgrad reductions
         self.taps = None
         self.launches_per_step = None
         self._ab_graphs = {}                  # (B,H,W) -> forward / backward CUDA graphs of the autograd-boundary path
@@ -446,6 +447,32 @@ class TrainEngine:
         else:
             self.side.run(reads, fn)
 
+    # Weight-gradient GEMMs leave split partials in `ws.wgrad`; ONE batched launch per gradient bucket reduces them all
+    # (autograd: one AccumulateGrad per parameter; the first version of this engine: a finalize launch per GEMM).
+    def _wg_gemm(self, dy, x, dw, **kw):
+        """tops.gemm_wgrad with the reduction deferred to the next `_wg_flush`; call inside `_wgrad` (side stream)"""
+        ws = self.buf("ws.wgrad.big", (1 << (27 if self.dev.type == "cuda" else 22),), torch.float32)
+        nk = kw["N"] * (kw["K"] + 1)
+        if self._wg_off + 32 * nk > ws.numel():
+            self._wg_flush()
+        jobs, used = tops.gemm_wgrad_partial(dy, x, dw, ws=ws[self._wg_off:], **kw)
+        self._wg_pending += jobs
+        self._wg_off += _rup(used, 4)
+
+    def _wg_flush(self):
+        jobs, self._wg_pending, self._wg_off = self._wg_pending, [], 0
+        if not jobs:
+            return
+        key = (self._plan_key, self._wg_flush_idx)
+        self._wg_flush_idx += 1
+        ent = self._wg_tables.get(key)
+        if ent is None or ent[0] != jobs:
+            if self.dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("weight-gradient reduction table changed between the warm-up step and the graph capture")
+            tab, nj, nb = tops.wgrad_reduce_table(jobs)
+            ent = self._wg_tables[key] = (jobs, tab.to(self.dev), nj, nb)
+        self._wgrad((), lambda: tops.wgrad_reduce_batch(ent[1], ent[2], ent[3]))
+
     # ------------------------------------------------------------------------------------------------ primitives
     def lin(self, x, name, out, *, M=None, N=None, K=None, lda=None, a_off=0, ldc=None, c_off=0, bias=None,
             wname=None, drop=None, drop_div=1, res1=None, dmul=None, x_needs_grad=True, wgrads=None):
@@ -486,8 +513,8 @@ class TrainEngine:
             def wg():
                 for pn, r0, nr in wgrads:
                     gb = self.GP.get(pn + ".bias") if (bias is not None) else None
-                    tops.gemm_wgrad(dy, x, self.GP[pn + ".weight"], M=M, N=nr, K=Kr, ldy=ldc, y_off=c_off + r0, ldx=lda,
-                                    x_off=a_off, row_scale=drop, rs_div=drop_div, dbias=gb, ws=self._wws())
+                    self._wg_gemm(dy, x, self.GP[pn + ".weight"], M=M, N=nr, K=Kr, ldy=ldc, y_off=c_off + r0, ldx=lda,
+                                  x_off=a_off, row_scale=drop, rs_div=drop_div, rs_binary=drop is not None, dbias=gb)
             self._wgrad((dy, x), wg)            # (drop is written only before the forward)
         self.tape.append(bwd)
         return out
@@ -607,9 +634,11 @@ class TrainEngine:
             tgt = gw if wgrad_fix is None else self.buf(key + ".gw1", (Cout, Cin, k, k), torch.float32)
 
             def wg():
-                tops.gemm_wgrad(dy, col, tgt, M=M, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0, ldx=Kp, x_off=0, T=k * k,
-                                dbias=self.GP[name + ".bias"], ws=self._wws())
-                if wgrad_fix is not None:
+                kw = dict(M=M, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0, ldx=Kp, x_off=0, T=k * k, dbias=self.GP[name + ".bias"])
+                if wgrad_fix is None:
+                    self._wg_gemm(dy, col, tgt, **kw)
+                else:                                                 # the fix-up reads the finished gradient right away
+                    tops.gemm_wgrad(dy, col, tgt, ws=self._wws(), **kw)
                     wgrad_fix(tgt, gw)
             self._wgrad((dy, col), wg)
             if x_needs_grad:
@@ -1032,7 +1061,8 @@ class TrainEngine:
             WT = self.w[p + ".mixer.wT"]
             ops.gemm(dout, WT, self.G(zt), M=M, N=E, K=Cc, lda=Cc, ldw=WT.stride(0), ldc=E, impl=self.gemm_impl)
             self.wr(zt)
-            tops.gemm_wgrad(dout, zt, GP[p + ".mixer.weight"], M=M, N=Cc, K=E, ldy=Cc, y_off=0, ldx=E, x_off=0, ws=self._ws(0))
+            self._wgrad((dout, zt), lambda: self._wg_gemm(dout, zt, GP[p + ".mixer.weight"], M=M, N=Cc, K=E, ldy=Cc, y_off=0,
+                                                          ldx=E, x_off=0))
             for t in (skip, dec):                                   # residual operands: d += dout
                 tops.add_(self.G(t), dout, M * Cc, self.wr(t))
         self.tape.append(mix_bwd)
@@ -1113,10 +1143,13 @@ class TrainEngine:
             Kp = _rup(25 * Cin, 8)
             col = self.buf("head.rb.col", (Mf, Kp))
             ops.im2col(xc, col, B, H, W, Cin, 5, 1, 2, H, W, Kp)
-            tops.gemm_wgrad(self.G(o1raw), col, GP["out.rb.0.conv1.conv.weight"], M=Mf, N=om, K=25 * Cin, ldy=om, y_off=0,
-                            ldx=Kp, x_off=0, T=25, ws=self._ws(0))
-            tops.gemm_wgrad(self.G(rraw), xc, GP["out.rb.0.conv3.conv.weight"], M=Mf, N=om, K=Cin, ldy=om, y_off=0, ldx=Cin,
-                            x_off=0, ws=self._ws(0))
+            do1, drr = self.G(o1raw), self.G(rraw)
+
+            def wg():
+                self._wg_gemm(do1, col, GP["out.rb.0.conv1.conv.weight"], M=Mf, N=om, K=25 * Cin, ldy=om, y_off=0, ldx=Kp,
+                              x_off=0, T=25)
+                self._wg_gemm(drr, xc, GP["out.rb.0.conv3.conv.weight"], M=Mf, N=om, K=Cin, ldy=om, y_off=0, ldx=Cin, x_off=0)
+            self._wgrad((do1, col, drr, xc), wg)
         self.tape.append(stem_bwd)
         o1 = self.buf("head.rb.o1", (B, H, W, om))
         self.bn_act(o1raw.view(Mf, om), Mf, om, "out.rb.0.norm1", o1.view(Mf, om), "head.rb.bn1", act=ACT_LEAKY, slope=0.01)
@@ -1196,9 +1229,11 @@ class TrainEngine:
         """d(logits) must already be in G(logits)."""
         self.wr(logits)
         _hazards.cur = self.side
+        self._wg_flush_idx = 0
         try:
             for tag, fn in reversed(self.tape):
                 if tag == "bucket":
+                    self._wg_flush()                        # one batched reduction of the bucket's weight-gradient partials
                     if self.on_bucket is not None:
                         if self.side is not None:
                             self.side.join()                # the bucket's weight gradients must be final
@@ -1206,6 +1241,7 @@ class TrainEngine:
                     continue
                 ops.tag = tag + ".bwd"
                 fn()
+            self._wg_flush()
             if self.side is not None:
                 self.side.join()
         finally:

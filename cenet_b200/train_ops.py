@@ -42,6 +42,42 @@ def gemm_wgrad(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=Non
            rs_div, _f32(dw, "dw"), _f32(dbias, "dbias"), int(bias_unscaled), wp, wn, _stream())
 
 
+def gemm_wgrad_partial(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=None, rs_div=1, rs_binary=False,
+                       dbias=None, bias_unscaled=False, ws=None):
+    """gemm_wgrad with the reduction of its split partials deferred.  Returns the reduction jobs still to run -- a list of
+    (src pointer, dst pointer, stride, S, N, K, T) for `wgrad_reduce_batch` (empty: dw / dbias are already final) -- and the
+    number of workspace floats the partials occupy."""
+    wp, wn = _ws(ws)
+    S, bp = C.c_int(0), C.c_int(0)
+    L.call("cenet_gemm_wgrad_partial", _po(dy, y_off), dt(dy), ldy, _po(x, x_off), dt(x), ldx, M, N, K, T,
+           _f32(row_scale, "row_scale"), rs_div, int(rs_binary), _f32(dw, "dw"), _f32(dbias, "dbias"), int(bias_unscaled), wp, wn,
+           C.byref(S), C.byref(bp), _stream())
+    S, bp = S.value, bp.value
+    if S == 0:
+        return [], 0
+    jobs = [(wp, _p(dw), N * K, S, N, K, T)]
+    if bp:
+        jobs.append((wp + 4 * S * N * K, _p(dbias), N, S, 1, N, 1))
+    return jobs, S * (N * K + (N if bp else 0))
+
+
+def wgrad_reduce_table(jobs):
+    """host side of `wgrad_reduce_batch`: packs the job list (see gemm_wgrad_partial) into the C descriptor array and lays out
+    the block ranges; returns (uint8 CPU tensor to be copied to the device, number of jobs, number of blocks)"""
+    arr = (L.WgradJob * len(jobs))()
+    blk = 0
+    lib = L.load()
+    for a, (src, dst, stride, S, N, K, T) in zip(arr, jobs):
+        a.src, a.dst, a.stride, a.S, a.N, a.K, a.T, a.blk0 = src, dst, stride, S, N, K, T, blk
+        blk += lib.cenet_wgrad_reduce_blocks(C.byref(a))
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone(), len(jobs), blk
+
+
+def wgrad_reduce_batch(table, njobs, nblocks):
+    """table: the device copy of wgrad_reduce_table's tensor"""
+    L.call("cenet_wgrad_reduce_batch", _p(table), njobs, nblocks, _stream())
+
+
 def conv_wgrad(dy, x4, dw, ksize, ws):
     """dw [N,Cin,k,k] of a stride-1 'same' conv: dy [B*H*W, N] contiguous, x4 [B,H,W,Cin] contiguous (no im2col buffer)"""
     B, H, W, Cin = x4.shape

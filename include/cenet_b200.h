@@ -247,6 +247,35 @@ int cenet_dwconv3x3_train(const void* x, int x_dtype, long long ldx, void* y, in
 int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M, int N,
                      int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias, int bias_unscaled, float* ws,
                      long long ws_elems, cenet_stream_t s);
+/* The same GEMM with the reduction of its split partials DEFERRED, so that one launch (cenet_wgrad_reduce_batch) can reduce
+ * the partials of a whole gradient bucket -- autograd runs one AccumulateGrad per parameter; here ~150 finalize launches
+ * per step become ~6.  bf16 operands run on the tcgen05 kernel: TMA-fed MN-major operands, accumulator in TMEM, the bias
+ * gradient as one more N=16 MMA per k-step against a constant ones tile.  rs_binary != 0 declares row_scale to be a DropPath mask
+ * (every entry 0 or one common value c, timm drop_path: bernoulli(keep)/keep per sample): dropped samples are skipped and the
+ * split count no longer grows with the batch.
+ * On return *n_partials == 0: dw / dbias hold the final result.  Otherwise ws holds S = *n_partials partial matrices
+ * [N][K] (S*N*K floats) followed, when *bias_partials != 0, by S partial bias rows [N]; dbias is final when
+ * *bias_partials == 0. */
+int cenet_gemm_wgrad_partial(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, long long M,
+                             int N, int K, int T, const float* row_scale, int rs_div, int rs_binary, float* dw, float* dbias,
+                             int bias_unscaled, float* ws, long long ws_elems, int* n_partials, int* bias_partials,
+                             cenet_stream_t s);
+/* one reduction job: dst[n, ci, t] = sum_{z<S} src[z*stride + n*K + t*Cin + ci]  (K = T*Cin; a bias row is N=1, K=len, T=1) */
+typedef struct {
+  const float* src;
+  float* dst;
+  long long stride;
+  int S, N, K, T;
+  int blk0;          /* first block of this job = running sum of cenet_wgrad_reduce_blocks over the preceding jobs */
+  int reserved;
+} cenet_wgrad_job;
+/* host-only: the tile / split plan the tcgen05 weight-gradient kernel would use; out[9] = {bn, S, per_group, parts, chunks per
+ * split, chunks per group, groups, rows per group, total chunks} */
+int cenet_wgrad_plan_query(long long M, int N, int K, int has_rs, int rs_div, int binary, long long max_partials, int* out);
+/* 256-thread blocks job j needs (host-side helper, no launch) */
+int cenet_wgrad_reduce_blocks(const cenet_wgrad_job* j);
+/* jobs: DEVICE array; fixed summation order (bit-reproducible, no float atomics) */
+int cenet_wgrad_reduce_batch(const cenet_wgrad_job* jobs, int njobs, int nblocks, cenet_stream_t s);
 /* weight gradient of a dense stride-1 "same" conv WITHOUT im2col: x is the NHWC image [B,H,W,Cin] (pitch ldx), dy [B*H*W, N] (pitch
  * ldy); dw in the reference layout [N, Cin, k, k].  The X operand tile is gathered tap by tap inside the kernel. */
 int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int B, int H, int W,

@@ -55,6 +55,20 @@ def gemm_wgrad(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=Non
         dbias.view(-1)[:N].copy_((dyv if bias_unscaled else dys).sum(0))
 
 
+def gemm_wgrad_partial(dy, x, dw, *, rs_binary=False, **kw):
+    """the emulation has no split partials: the result is final, nothing is left to reduce"""
+    gemm_wgrad(dy, x, dw, **kw)
+    return [], 0
+
+
+def wgrad_reduce_table(jobs):
+    raise AssertionError("the emulation never defers a reduction")
+
+
+def wgrad_reduce_batch(table, njobs, nblocks):
+    raise AssertionError("the emulation never defers a reduction")
+
+
 def conv_wgrad(dy, x4, dw, ksize, ws):
     _LAUNCHES[0] += 2
     B, H, W, Cin = x4.shape

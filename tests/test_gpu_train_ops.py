@@ -122,6 +122,69 @@ def test_gemm_wgrad_tcgen05(M, N, K, ldy, ldx, rsdiv):
     check("gemm_wgrad", [dy, x, dw], kw, [2, "dbias"], 1.5e-2)
 
 
+def test_gemm_wgrad_deferred_batch():
+    """several weight-gradient GEMMs leave their split partials in one workspace; ONE cenet_wgrad_reduce_batch launch reduces
+    them all.  Covers: DropPath mask mode (binary row scale, dropped samples skipped), bias through the ones-MMA, a direct
+    single-split result, the tap permutation (T=25) of an im2col'ed conv with K padded to the pitch, the mma.sync path
+    (K=3), and a general per-sample scale."""
+    from cenet_b200 import train_ops as tops
+    keep = 0.8
+    cases = [  # M, N, K, ldx, T, rs_div, binary, bias
+        (6 * 3136, 64, 256, 256, 1, 3136, True, True),
+        (6 * 196, 1280, 320, 320, 1, 196, True, True),
+        (24 * 49, 512, 2048, 2048, 1, 49, True, True),
+        (4704, 320, 320, 320, 1, 0, False, True),
+        (640, 96, 64, 64, 1, 0, False, True),                 # few chunks: may run as one split (direct)
+        (20000, 32, 25, 32, 25, 0, False, False),             # stem 5x5: K = 25 taps x 1 channel in a 32-wide im2col buffer
+        (9000, 32, 3, 3, 1, 0, False, False),                 # mma.sync fallback (pitch not a multiple of 8)
+        (4 * 784, 128, 128, 128, 1, 784, False, True),        # general per-sample scale
+    ]
+    wsb = torch.zeros(1 << 25, device=DEV)
+    off, jobs, outs = 0, [], []
+    for i, (M, N, K, ldx, T, rsdiv, binary, bias) in enumerate(cases):
+        dy, x = rn((M, N), BF16, 10 + i), rn((M, ldx), BF16, 20 + i)
+        rs = None
+        if rsdiv:
+            rs = torch.rand(M // rsdiv, generator=gen(30 + i))
+            rs = ((rs < keep).float() / keep) if binary else rs + 0.5
+            if binary:
+                rs[1] = 0.0
+        dw_c, db_c = torch.zeros(N * K), torch.zeros(N)
+        FT.gemm_wgrad(dy, x, dw_c, M=M, N=N, K=K, ldy=N, y_off=0, ldx=ldx, x_off=0, T=T, row_scale=rs, rs_div=rsdiv or 1,
+                      dbias=db_c if bias else None)
+        dw_g, db_g = torch.zeros(N * K, device=DEV), torch.zeros(N, device=DEV)
+        j, used = tops.gemm_wgrad_partial(dy.to(DEV), x.to(DEV), dw_g, M=M, N=N, K=K, ldy=N, y_off=0, ldx=ldx, x_off=0, T=T,
+                                          row_scale=None if rs is None else rs.to(DEV), rs_div=rsdiv or 1, rs_binary=binary,
+                                          dbias=db_g if bias else None, ws=wsb[off:])
+        off += (used + 3) // 4 * 4
+        jobs += j
+        outs.append((dw_c, db_c if bias else None, dw_g, db_g))
+    assert jobs and off < wsb.numel()
+    tab, nj, nb = tops.wgrad_reduce_table(jobs)
+    tops.wgrad_reduce_batch(tab.to(DEV), nj, nb)
+    torch.cuda.synchronize()
+    for i, (dw_c, db_c, dw_g, db_g) in enumerate(outs):
+        assert rel(dw_g, dw_c) < 1.5e-2, (i, rel(dw_g, dw_c))
+        if db_c is not None:
+            assert rel(db_g, db_c) < 1.5e-2, (i, "bias", rel(db_g, db_c))
+
+
+def test_gemm_wgrad_mask_all_dropped():
+    """every sample dropped: the accumulator is never written -- the result must be exact zeros, not TMEM garbage"""
+    from cenet_b200 import train_ops as tops
+    M, N, K = 4 * 196, 320, 320
+    dy, x = rn((M, N), BF16, 1).to(DEV), rn((M, K), BF16, 2).to(DEV)
+    dw, db = torch.ones(N * K, device=DEV), torch.ones(N, device=DEV)
+    wsb = torch.zeros(1 << 22, device=DEV)
+    jobs, _ = tops.gemm_wgrad_partial(dy, x, dw, M=M, N=N, K=K, ldy=N, y_off=0, ldx=K, x_off=0, row_scale=torch.zeros(4, device=DEV),
+                                      rs_div=196, rs_binary=True, dbias=db, ws=wsb)
+    if jobs:
+        tab, nj, nb = tops.wgrad_reduce_table(jobs)
+        tops.wgrad_reduce_batch(tab.to(DEV), nj, nb)
+    torch.cuda.synchronize()
+    assert float(dw.abs().max()) == 0.0 and float(db.abs().max()) == 0.0
+
+
 def test_gemm_wgrad_mixed_dtypes_unscaled_bias():
     M, N, K = 5000, 4, 64                                   # head: fp32 logits gradient x bf16 activations
     dy, x = rn((M, N), F32, 1), rn((M, K), BF16, 2)
