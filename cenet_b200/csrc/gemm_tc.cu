@@ -102,6 +102,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t l
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
 
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+}
+
 struct TcParams {
   int M, N, K;
   int bn;            // N tile (multiple of 16, <= 256)
@@ -139,6 +145,168 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   warp 0   : TMA producer (weights once if resident, then the A ring)
 //   warp 1   : TMEM alloc + tcgen05.mma issue into accumulator stage (tile & 1)
 //   warps 2-9: epilogue of the previous tile out of the other accumulator stage, overlapping the next tile's loads+MMAs
+// Vector epilogue of one 32x32 accumulator block for the 4 rows x 8 columns a lane owns, specialised at COMPILE time on which
+// operands exist (FLAGS): the all-runtime version executed ~950 instructions per block, most of them flag tests, constant
+// reloads and branches, at an IPC of 0.35 (two epilogue warps per scheduler cannot hide dependent-issue latency), which made a
+// ReLU cost 2.7x the plain store.  Here the four rows are independent instruction chains the scheduler can interleave, every
+// operand row is requested before the first use, and the activation code exists once (two-pass loop).
+enum { VF_MUL = 1, VF_R1 = 2, VF_R2 = 4, VF_ROW = 8, VF_R1F32 = 16 };   // R1F32: res1 is an fp32 row (encoder residual stream)
+__device__ __forceinline__ void act32(float (&v)[4][8], int act, float slope) {
+  switch (act) {
+    case CENET_ACT_RELU:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = fmaxf(v[r][j], 0.0f);
+      break;
+    case CENET_ACT_LEAKY:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = v[r][j] > 0.0f ? v[r][j] : v[r][j] * slope;
+      break;
+    case CENET_ACT_SILU:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = v[r][j] * sigmoid_fast(v[r][j]);
+      break;
+    case CENET_ACT_SIGMOID:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = sigmoid_fast(v[r][j]);
+      break;
+    case CENET_ACT_GELU:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = gelu_erf(v[r][j]);
+      break;
+    case CENET_ACT_GELU_GRAD:
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = gelu_grad_fast(v[r][j]);
+      break;
+    default: break;
+  }
+}
+
+template <int FLAGS>
+__device__ __forceinline__ void epi_vec_block(const EpiParams& e, const float* slab, int lane, int n, const long long (&mrow)[4],
+                                              const bool (&okrow)[4], const float (&rs)[4], const float (&prs)[4],
+                                              const float (&brow)[4]) {
+  const int cg = (lane & 3) * 8;
+  uint4 um[4], u1[4], u2[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const long long m = mrow[r];                                     // 0 for rows outside the matrix: loads stay in bounds
+    if (FLAGS & VF_MUL) um[r] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n);
+    if (FLAGS & VF_R1F32) {                          // (never together with R2: u2 holds the second half of the fp32 row)
+      const float* rp = reinterpret_cast<const float*>(e.res1) + m * e.ldr1 + n;
+      u1[r] = *reinterpret_cast<const uint4*>(rp);
+      u2[r] = *reinterpret_cast<const uint4*>(rp + 4);
+    } else {
+      if (FLAGS & VF_R1) u1[r] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n);
+      if (FLAGS & VF_R2) u2[r] = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n);
+    }
+  }
+  float bcol[8], cs1[8];
+  if (e.bias && !e.bias_per_row) ldv<8>(e.bias + n, bcol);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) bcol[j] = 0.f;
+  }
+  if (FLAGS & (VF_R1 | VF_R1F32)) {
+    if (e.res1_cscale) ldv<8>(e.res1_cscale + n, cs1);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) cs1[j] = e.res1_scale;
+    }
+  }
+  float v[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int rr = r * 8 + (lane >> 2);
+    const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
+    const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
+    const float a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[r][j] = fmaf(a[j], rs[r], bcol[j] + brow[r]);
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    if (e.act != CENET_ACT_NONE && pass == (e.act_after_res ? 1 : 0)) act32(v, e.act, e.slope);
+    if (pass) break;
+    if (FLAGS & VF_MUL) {
+      const int ma = e.mul_act;                     // GELU' (Mix-FFN dgrad), SiLU (gated CFAM branch) or none on this path
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        float t[8];
+        unpack8(um[r], t);
+        if (ma == CENET_ACT_GELU_GRAD) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) t[j] = gelu_grad_fast(t[j]);
+        } else if (ma == CENET_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) t[j] = t[j] * sigmoid_fast(t[j]);
+        } else if (ma != CENET_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) t[j] = apply_act(t[j], ma, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] *= t[j];
+      }
+    }
+    if (FLAGS & VF_ROW) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] *= prs[r];
+    }
+    if (FLAGS & VF_R1F32) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const float t[8] = {__uint_as_float(u1[r].x), __uint_as_float(u1[r].y), __uint_as_float(u1[r].z), __uint_as_float(u1[r].w),
+                            __uint_as_float(u2[r].x), __uint_as_float(u2[r].y), __uint_as_float(u2[r].z), __uint_as_float(u2[r].w)};
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = fmaf(t[j], cs1[j], v[r][j]);
+      }
+    } else if (FLAGS & VF_R1) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        float t[8];
+        unpack8(u1[r], t);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] = fmaf(t[j], cs1[j], v[r][j]);
+      }
+    }
+    if ((FLAGS & VF_R2) && !(FLAGS & VF_R1F32)) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        float t[8];
+        unpack8(u2[r], t);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[r][j] += t[j];
+      }
+    }
+  }
+  if (e.c_dtype == CENET_BF16) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (okrow[r]) stv<8>(reinterpret_cast<bf16*>(e.C) + mrow[r] * e.ldc + n, v[r]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (okrow[r]) stv<8>(reinterpret_cast<float*>(e.C) + mrow[r] * e.ldc + n, v[r]);
+  }
+}
+
+// EPI selects the ONE epilogue compiled into an instantiation (ncu on the all-in-one kernel: 9 k SASS instructions, the epilogue
+// warps' top stall reason was `no_instruction` -- instruction-cache misses -- and a ReLU cost 2.7x the plain store):
+enum { EPI_SPLITK = 0, EPI_FAST = 1, EPI_VEC = 3, EPI_SCALAR = 4 };
+template <int EPI, int FLAGS>
 __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -332,13 +500,23 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
       const bool own_ok = row_index(quarter * 32 + lane, m_own);
       // fast path bookkeeping: the 4 rows this lane serves in phase B (4 lanes per row, 8 rows per pass)
       bf16* crow[4];
-      const bf16* rrow[4];
+      long long mrow[4];
+      bool okrow[4];
+      float rsv[4], prsv[4], browv[4];
 #pragma unroll
       for (int itr = 0; itr < 4; itr++) {
         long long m;
         const bool ok = row_index(quarter * 32 + itr * 8 + (lane >> 2), m);
+        mrow[itr] = ok ? m : 0; okrow[itr] = ok;
+        // per-row factors do not depend on the column chunk: once per tile (rows < 2^31: 32-bit divisions)
+        rsv[itr] = e.alpha; prsv[itr] = 1.f; browv[itr] = 0.f;
+        if constexpr (EPI == EPI_VEC && (FLAGS & VF_ROW) != 0) {
+          const unsigned mu = (unsigned)mrow[itr];
+          if (e.row_scale) rsv[itr] *= e.row_scale[e.rs_div > 1 ? mu / (unsigned)e.rs_div : mu];
+          if (e.post_rs) prsv[itr] = e.post_rs[e.post_rs_div > 1 ? mu / (unsigned)e.post_rs_div : mu];
+          if (e.bias && e.bias_per_row) browv[itr] = e.bias[mu];
+        }
         crow[itr] = ok ? reinterpret_cast<bf16*>(e.C) + m * e.ldc : nullptr;
-        rrow[itr] = reinterpret_cast<const bf16*>(e.res1) + (ok ? m * e.ldr1 : 0);
       }
       mbar_wait(tfull_bar + 8 * as, use & 1);
       tc_fence_after();
@@ -354,7 +532,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]), __uint_as_float(acc[4 * q + 2]),
                           __uint_as_float(acc[4 * q + 3]));
         __syncwarp();
-        if (p.splits > 1) {
+        if constexpr (EPI == EPI_SPLITK) {
           // split-K: raw fp32 partial tile -> split_ws[z][m][n]  (N % 8 == 0; bias / cast happen in the reduce kernel)
           const int cg = (lane & 3) * 8;
           const int n = nbase + cg;
@@ -369,33 +547,8 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
             }
           }
-        } else if (p.epi_fast == 3) {
-          // fp32 residual stream (encoder): C = acc + bias + res1, both fp32 rows (two 16-byte accesses per lane)
-          const int cg = (lane & 3) * 8;
-          const int n = nbase + cg;
-          if (n < nlim) {
-            float bcol[8];
-            if (e.bias) ldv<8>(e.bias + n, bcol);
-            else {
-#pragma unroll
-              for (int j = 0; j < 8; j++) bcol[j] = 0.f;
-            }
-#pragma unroll
-            for (int itr = 0; itr < 4; itr++) {
-              long long m;
-              if (!row_index(quarter * 32 + itr * 8 + (lane >> 2), m)) continue;
-              const int rr = itr * 8 + (lane >> 2);
-              const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
-              const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
-              float t[8];
-              ldv<8>(reinterpret_cast<const float*>(e.res1) + m * e.ldr1 + n, t);
-              float v[8] = {lo.x + bcol[0] + t[0], lo.y + bcol[1] + t[1], lo.z + bcol[2] + t[2], lo.w + bcol[3] + t[3],
-                            hi.x + bcol[4] + t[4], hi.y + bcol[5] + t[5], hi.z + bcol[6] + t[6], hi.w + bcol[7] + t[7]};
-              stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
-            }
-          }
-        } else if (p.epi_fast) {
-          // C = bf16(acc + bias [+ res1]); N % 8 == 0, so an 8-column group is entirely inside or outside the tile
+        } else if constexpr (EPI == EPI_FAST) {
+          // C = bf16(acc + bias); N % 8 == 0, so an 8-column group is entirely inside or outside the tile
           const int cg = (lane & 3) * 8;
           const int n = nbase + cg;
           if (n < nlim) {
@@ -413,87 +566,16 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
               const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
               float v[8] = {lo.x + bcol[0], lo.y + bcol[1], lo.z + bcol[2], lo.w + bcol[3],
                             hi.x + bcol[4], hi.y + bcol[5], hi.z + bcol[6], hi.w + bcol[7]};
-              if (p.epi_fast == 2) {
-                float t[8];
-                ldv<8>(rrow[itr] + n, t);
-#pragma unroll
-                for (int j = 0; j < 8; j++) v[j] += t[j];
-              }
               stv<8>(crow[itr] + n, v);
             }
           }
-        } else if (p.epi_vec) {
-          const int cg = (lane & 3) * 8;
-          const int n = nbase + cg;
-          float bcol[8], cs1[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) bcol[j] = (e.bias && !e.bias_per_row && n + j < p.N) ? e.bias[n + j] : 0.f;
-          // per-column residual scale: loaded ONCE per 8-column group (it used to be 8 dependent global loads per row,
-          // which made the decoder GEMMs with a BatchNorm-scaled shortcut 5x slower than their bytes allow)
-#pragma unroll
-          for (int j = 0; j < 8; j++) cs1[j] = e.res1_cscale ? (n + j < p.N ? e.res1_cscale[n + j] : 0.f) : e.res1_scale;
-#pragma unroll 2
-          for (int itr = 0; itr < 4; itr++) {
-            const int rr = itr * 8 + (lane >> 2);
-            long long m;
-            const bool ok = row_index(quarter * 32 + rr, m);
-            if (!ok || n >= nlim) continue;
-            float v[8];
-            {
-              const float4 lo = *reinterpret_cast<const float4*>(slab + rr * 36 + cg);
-              const float4 hi = *reinterpret_cast<const float4*>(slab + rr * 36 + cg + 4);
-              v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-            }
-            // (64-bit divisions only when a per-sample divisor is really in use)
-            const float rs = e.alpha * (e.row_scale ? e.row_scale[e.rs_div > 1 ? m / e.rs_div : m] : 1.f);
-            const float brow = (e.bias && e.bias_per_row) ? e.bias[m] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = fmaf(v[j], rs, bcol[j] + brow);
-            const bool full = n + 8 <= nlim;
-            // all operand rows are requested BEFORE any of them is used: three dependent load -> use sequences per row
-            // made this path latency-bound (2x the plain epilogue at the same bytes)
-            float tm[8], t1[8], t2[8];
-            if (e.mul) {
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.mul) + m * e.ldmul + n, tm);
-              else for (int j = 0; j < 8; j++) tm[j] = n + j < nlim ? ld_any(e.mul, e.mul_dtype, m * e.ldmul + n + j) : 0.f;
-            }
-            if (e.res1) {
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res1) + m * e.ldr1 + n, t1);
-              else for (int j = 0; j < 8; j++) t1[j] = n + j < nlim ? ld_any(e.res1, e.res1_dtype, m * e.ldr1 + n + j) : 0.f;
-            }
-            if (e.res2) {
-              if (full) ldv<8>(reinterpret_cast<const bf16*>(e.res2) + m * e.ldr2 + n, t2);
-              else for (int j = 0; j < 8; j++) t2[j] = n + j < nlim ? ld_any(e.res2, e.res2_dtype, m * e.ldr2 + n + j) : 0.f;
-            }
-            if (!e.act_after_res) apply_act8(v, e.act, e.slope);
-            if (e.mul) {
-              apply_act8(tm, e.mul_act, 0.f);
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] *= tm[j];
-            }
-            if (e.post_rs) {
-              const float prs = e.post_rs[e.post_rs_div > 1 ? m / e.post_rs_div : m];
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] *= prs;
-            }
-            if (e.res1) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] = fmaf(t1[j], cs1[j], v[j]);
-            }
-            if (e.res2) {
-#pragma unroll
-              for (int j = 0; j < 8; j++) v[j] += t2[j];
-            }
-            if (e.act_after_res) apply_act8(v, e.act, e.slope);
-            if (full) {
-              if (e.c_dtype == CENET_BF16) stv<8>(reinterpret_cast<bf16*>(e.C) + m * e.ldc + n, v);
-              else stv<8>(reinterpret_cast<float*>(e.C) + m * e.ldc + n, v);
-            } else {
-              for (int j = 0; j < 8 && n + j < nlim; j++) epi_store(e, v[j], m, n + j, 0);
-            }
-          }
+        } else if constexpr (EPI == EPI_VEC) {
+          // general vector epilogue: N % 8 == 0 and every operand 16-byte addressable (the host routes the rest to EPI_SCALAR),
+          // so an 8-column group is entirely inside or outside the tile
+          const int n = nbase + (lane & 3) * 8;
+          if (n < nlim) epi_vec_block<FLAGS>(e, slab, lane, n, mrow, okrow, rsv, prsv, browv);
         } else if (own_ok) {
-          // operands that are not 16-byte addressable (odd pitches / channel-slice outputs): element-wise epilogue
+          // EPI_SCALAR: operands that are not 16-byte addressable (odd pitches / channel-slice outputs): element-wise epilogue
 #pragma unroll 1
           for (int c = 0; c < 32; c++) {
             const int n = nbase + c;
@@ -705,15 +787,36 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
       a->act == CENET_ACT_NONE && !a->mul && !a->res2 && a->N % 8 == 0 && (!a->bias || (((uintptr_t)a->bias & 15) == 0)))
     p.epi_fast = 3;                                          // fp32 residual stream of the encoder
   const size_t smem = (size_t)wres + (size_t)stages * stage_bytes + (2 * stages + 5) * 8 + 32 + slab_bytes + 1024;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
   int gx = kNumSMs * ctas_per_sm / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.num_m_tiles) gx = p.num_m_tiles;
   dim3 grid(gx, n_tiles, p.splits);
-  gemm_tc_kernel<<<grid, 64 + 32 * p.n_epi, smem, s>>>(tmA, tmW, p);
+  const bool vec16 = p.epi_vec && a->N % 8 == 0 && (!a->bias || a->bias_per_row || (((uintptr_t)a->bias & 15) == 0)) &&
+                     (!a->res1_cscale || (((uintptr_t)a->res1_cscale & 15) == 0));
+  const int nthr = 64 + 32 * p.n_epi;
+  const int vflags = (a->mul ? VF_MUL : 0) | (a->res1 ? VF_R1 : 0) | (a->res2 ? VF_R2 : 0) |
+                     ((a->row_scale || a->post_row_scale || (a->bias && a->bias_per_row)) ? VF_ROW : 0);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const TcParams);
+  static const KernelFn vec_kernels[16] = {
+      gemm_tc_kernel<EPI_VEC, 0>,  gemm_tc_kernel<EPI_VEC, 1>,  gemm_tc_kernel<EPI_VEC, 2>,  gemm_tc_kernel<EPI_VEC, 3>,
+      gemm_tc_kernel<EPI_VEC, 4>,  gemm_tc_kernel<EPI_VEC, 5>,  gemm_tc_kernel<EPI_VEC, 6>,  gemm_tc_kernel<EPI_VEC, 7>,
+      gemm_tc_kernel<EPI_VEC, 8>,  gemm_tc_kernel<EPI_VEC, 9>,  gemm_tc_kernel<EPI_VEC, 10>, gemm_tc_kernel<EPI_VEC, 11>,
+      gemm_tc_kernel<EPI_VEC, 12>, gemm_tc_kernel<EPI_VEC, 13>, gemm_tc_kernel<EPI_VEC, 14>, gemm_tc_kernel<EPI_VEC, 15>};
+  // (the batched-load vector block also beats the older dedicated paths for bias + bf16 / fp32 residual: 60 vs 112 us on the
+  // M=75264, N=512, K=64 GEMM; only the plain C = acc + bias store keeps its own minimal kernel)
+  KernelFn kern = p.splits > 1 ? gemm_tc_kernel<EPI_SPLITK, 0>
+                  : p.epi_fast == 3 ? gemm_tc_kernel<EPI_VEC, VF_R1F32>
+                  : p.epi_fast == 1 ? gemm_tc_kernel<EPI_FAST, 0>
+                  : vec16 ? vec_kernels[vflags] : gemm_tc_kernel<EPI_SCALAR, 0>;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(gemm_tc_kernel<EPI_SPLITK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel<EPI_FAST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel<EPI_VEC, VF_R1F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gemm_tc_kernel<EPI_SCALAR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    for (int i = 0; i < 16; i++) cudaFuncSetAttribute(vec_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  kern<<<grid, nthr, smem, s>>>(tmA, tmW, p);
   CENET_LAUNCH_CHECK("gemm_tc");
   if (p.splits > 1) {
     const long long groups = (long long)a->M * (a->N / 8);
