@@ -323,6 +323,17 @@ class Engine:
             P(d + ".dw.s", s); P(d + ".dw.t", t)
             s, t = self._bn_fold(sd, d + ".pointwise_bn")
             M(d + ".pw.w", sd[d + ".pointwise.weight"].flatten(1) * s[:, None]); P(d + ".pw.b", t)
+        # the three pointwise convs as ONE block-diagonal GEMM over the padded depthwise buffer: [Cc, 3*ap] with zero rows for
+        # the pooled slice (its columns of `cat` are written by pool_branch afterwards).  The slice widths (20 / 40 / 100 / 160
+        # of 64 / 128 / 320 / 512 channels) are not multiples of 8, which sent three GEMMs per block to the scalar epilogue.
+        ap = _rup(sl[0][1] - sl[0][0], 8)
+        wbd = torch.zeros(Cc, 3 * ap, device=self.dev, dtype=torch.float32)
+        bbd = torch.zeros(Cc, device=self.dev, dtype=torch.float32)
+        for i in range(3):
+            a0, a1 = sl[i]
+            wbd[a0:a1, i * ap:i * ap + (a1 - a0)] = self.w[f"{v}.dlps.{i}.pw.w"][:, :a1 - a0].float()
+            bbd[a0:a1] = self.w[f"{v}.dlps.{i}.pw.b"].float()
+        M(v + ".dlps_bd.w", wbd); P(v + ".dlps_bd.b", bbd)
         d = f"{v}.dlps.3"
         P(d + ".w", sd[d + ".1.weight"].flatten(1))
         s, t = self._bn_fold(sd, d + ".2")
@@ -527,8 +538,8 @@ class Engine:
             d = f"{v}.dlps.{i}"
             ops.dwconv3x3(x1, dwb, w[d + ".dw.w"], B, H, W, a1 - a0, ldx=Cc, ldy=3 * ap, x_off=a0, y_off=i * ap,
                           scale=w[d + ".dw.s"], shift=w[d + ".dw.t"], dil=rate, act=ACT_RELU)
-            ops.gemm(dwb, w[d + ".pw.w"], cat, M=Mtok, N=a1 - a0, K=ap, lda=3 * ap, ldw=w[d + ".pw.w"].shape[1], ldc=Cc,
-                     bias=w[d + ".pw.b"], act=ACT_RELU, a_off=i * ap, c_off=a0, impl=self.gemm_impl)
+        ops.gemm(dwb, w[v + ".dlps_bd.w"], cat, M=Mtok, N=Cc, K=3 * ap, lda=3 * ap, ldw=3 * ap, ldc=Cc, bias=w[v + ".dlps_bd.b"],
+                 act=ACT_RELU, impl=self.gemm_impl)
         r0, r1 = sl[3]
         d = f"{v}.dlps.3"
         pooled = self.buf(key + ".pooled", (B * 49 * (r1 - r0),), torch.float32)
