@@ -591,6 +591,10 @@ def run_product(args):
                 t_act = sum(ms for *_, ms in gl)
                 roof["per_launch_view"] = {"t_roofline_ms": t_roof, "t_measured_ms": t_act, "frac": t_roof / t_act,
                                            "note": "sum over launches of max(bytes/HBM peak, FLOPs/bf16 peak) / measured time"}
+                hb, tf = peaks["hbm_gbs"] * 1e9, peaks["tf_sustained"] * 1e12
+                exc = sorted(gl, key=lambda r: -(r[4] - max(r[2] / hb, r[3] / tf) * 1e3))[:12]
+                roof["top_excess"] = [{"op": op, "tag": tag, "ms": round(ms, 4), "roofline_ms": round(max(by / hb, fl / tf) * 1e3, 4)}
+                                      for op, tag, by, fl, ms in exc]
                 worst = sorted(gl, key=lambda r: -r[4])[:16]
                 roof["top_launches"] = [{"op": op, "tag": tag, "ms": round(ms, 4), "MB": round(by / 1e6, 1), "GFLOP": round(fl / 1e9, 2),
                                          "GB/s": round(by / ms / 1e6), "TFLOP/s": round(fl / ms / 1e9, 1)} for op, tag, by, fl, ms in worst]

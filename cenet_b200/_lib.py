@@ -27,7 +27,7 @@ class AttnTcArgs(C.Structure):
 class WgradJob(C.Structure):
     """Mirror of `cenet_wgrad_job` (include/cenet_b200.h)."""
     _fields_ = [("src", vp), ("dst", vp), ("stride", ll), ("S", i32), ("N", i32), ("K", i32), ("T", i32), ("blk0", i32),
-                ("reserved", i32)]
+                ("src_ld", i32)]
 
 
 class GemmArgs(C.Structure):

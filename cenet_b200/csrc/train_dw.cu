@@ -29,11 +29,15 @@ __device__ __forceinline__ void unpack_raw(const RawVec<T, V>& r, float (&o)[V])
 template <typename T, int V, bool WINDOW>
 __global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ dz,
                                                                        long long ldz, int B, int H, int W, int C, int dil, int up2,
-                                                                       int ngrp, int nrl, int rows_per_block, float* __restrict__ ws) {
+                                                                       int ngrp, int nrl, int rows_per_block, int wsegs,
+                                                                       float* __restrict__ ws) {
   __shared__ float smem[V * kColThreads];
   const int grp = threadIdx.x % ngrp, rl = threadIdx.x / ngrp;
   const int c0 = (blockIdx.y * ngrp + grp) * V;
-  const int R = B * H;
+  // generic branch only: a work unit is one of `wsegs` column segments of an image row, so that narrow channel slices at a
+  // small batch (dec1: 20 channels, 24 x 56 rows = 42 blocks) still put a block on every SM
+  const int R = B * H * wsegs;
+  const int wseg = (W + wsegs - 1) / wsegs;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
   const int Hi = up2 ? H >> 1 : H, Wi = up2 ? W >> 1 : W;
@@ -43,7 +47,9 @@ __global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const 
 #pragma unroll
     for (int v = 0; v < V; v++) acc[k][v] = 0.f;
   if (c0 < C) {
-    for (int r = r0 + rl; r < r1; r += nrl) {
+    for (int rr = r0 + rl; rr < r1; rr += nrl) {
+      const int r = WINDOW ? rr : rr / wsegs;
+      const int w_lo = WINDOW ? 0 : (rr - r * wsegs) * wseg, w_hi = WINDOW ? W : min(W, w_lo + wseg);
       const int b = r / H, h = r - b * H;
       const T* zrow = dz + (long long)r * W * ldz + c0;
       if constexpr (WINDOW) {
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(kColThreads, 2) dw_wgrad_partial_kernel(const 
         }
       } else {
         const T* xb = x + (long long)b * Hi * Wi * ldx + c0;
-        for (int w = 0; w < W; w++) {
+        for (int w = w_lo; w < w_hi; w++) {
           float g[V];
           ldv<V>(zrow + (long long)w * ldz, g);
 #pragma unroll
@@ -394,7 +400,11 @@ extern "C" int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, 
     }
     // rows of the plan are IMAGE rows (b, h); every thread takes whole rows, at least one
     ColPlan p = plan_cols(rows, C, Vv);
-    const int R = B * H;
+    const bool window = dil == 1 && !up2;
+    int wsegs = 1;
+    if (!window)
+      while (wsegs < 8 && (long long)cdiv(B * H * wsegs, p.nrl) * p.gy < 2 * kNumSMs && W / (2 * wsegs) >= 7) wsegs *= 2;
+    const int R = B * H * wsegs;
     {
       long long want = (R + p.nrl - 1) / p.nrl;
       long long cap = std::max(1, 8 * kNumSMs / p.gy);
@@ -404,12 +414,12 @@ extern "C" int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, 
       p.nrb = (R + p.rows_per_block - 1) / p.rows_per_block;
     }
     CENET_REQUIRE((long long)p.nrb * 10 * C <= ws_elems, "cenet_dwconv3x3_wgrad: workspace too small");
-    if (dil == 1 && !up2) {
+    if (window) {
       DISPATCH_V(Vv, (dw_wgrad_partial_kernel<T, V, true><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
-                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, ws)));
+                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, 1, ws)));
     } else {
       DISPATCH_V(Vv, (dw_wgrad_partial_kernel<T, V, false><<<dim3(p.nrb, p.gy), kColThreads, 0, s>>>(
-                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, ws)));
+                          (const T*)x, ldx, (const T*)dz, ldz, B, H, W, C, dil, up2, p.ngrp, p.nrl, p.rows_per_block, wsegs, ws)));
     }
     CENET_LAUNCH_CHECK("dw_wgrad_partial");
     dw_wgrad_finalize_kernel<<<cdiv(10 * C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, dw, dbias);

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kColThreads) colsum_partial_kernel(const T* __
 // and the lanes are then added in lane order (fixed summation order -> bit-reproducible, no float atomics).
 __host__ __device__ inline int wgrad_reduce_lanes(int S) { return S <= 8 ? 1 : (S <= 64 ? 8 : 32); }
 __host__ __device__ inline bool wgrad_reduce_vec(const cenet_wgrad_job& j) {
-  return j.T == 1 && (((long long)j.N * j.K) & 3) == 0 && (j.stride & 3) == 0 && ((((uintptr_t)j.src) | ((uintptr_t)j.dst)) & 15) == 0;
+  return j.T == 1 && (j.K & 3) == 0 && (j.src_ld & 3) == 0 && (j.stride & 3) == 0 && ((((uintptr_t)j.src) | ((uintptr_t)j.dst)) & 15) == 0;
 }
 __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const cenet_wgrad_job* __restrict__ jobs, int njobs) {
   __shared__ int sj;
@@ -261,14 +261,17 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const cenet_wgr
   const int sl = wgrad_reduce_lanes(j.S), per = 256 / sl;
   const int o = threadIdx.x % per, lane = threadIdx.x / per;
   const long long nk = (long long)j.N * j.K;
+  const int sld = j.src_ld > 0 ? j.src_ld : j.K;          // the N x K block may sit inside wider partial rows (block-diagonal GEMMs)
   if (wgrad_reduce_vec(j)) {
     const long long i = (long long)lb * per + o, nk4 = nk >> 2, st4 = j.stride >> 2;
     const float4* src = reinterpret_cast<const float4*>(j.src);
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < nk4) {
+      const long long e0 = i * 4;
+      const size_t so = sld == j.K ? (size_t)i : (size_t)(((e0 / j.K) * sld + (e0 % j.K)) >> 2);
 #pragma unroll 4
       for (int z = lane; z < j.S; z += sl) {
-        const float4 v = src[(size_t)z * st4 + i];
+        const float4 v = src[(size_t)z * st4 + so];
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
     }
@@ -287,8 +290,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const cenet_wgr
     const long long i = (long long)lb * per + o;
     float a = 0.f;
     if (i < nk) {
+      const size_t so = sld == j.K ? (size_t)i : (size_t)((i / j.K) * sld + (i % j.K));
 #pragma unroll 4
-      for (int z = lane; z < j.S; z += sl) a += j.src[(size_t)z * j.stride + i];
+      for (int z = lane; z < j.S; z += sl) a += j.src[(size_t)z * j.stride + so];
     }
     if (sl > 1) {
       float* r1 = reinterpret_cast<float*>(red);
@@ -402,7 +406,7 @@ extern "C" int cenet_gemm_wgrad_partial(const void* dy, int dy_dtype, long long 
                                         long long M, int N, int K, int T, const float* row_scale, int rs_div, int rs_binary,
                                         float* dw, float* dbias, int bias_unscaled, float* ws, long long ws_elems, int* n_partials,
                                         int* bias_partials, cenet_stream_t st) {
-  CENET_REQUIRE(dy && x && dw && ws && n_partials && bias_partials, "cenet_gemm_wgrad: null pointer");
+  CENET_REQUIRE(dy && x && ws && n_partials && bias_partials, "cenet_gemm_wgrad: null pointer");
   CENET_REQUIRE(M > 0 && N > 0 && K > 0 && T >= 1 && K % T == 0, "cenet_gemm_wgrad: bad shape M=%lld N=%d K=%d T=%d", M, N, K, T);
   CENET_REQUIRE(rs_div >= 1, "cenet_gemm_wgrad: rs_div must be >= 1");
   cudaStream_t s = to_stream(st);
@@ -422,7 +426,7 @@ extern "C" int cenet_gemm_wgrad_partial(const void* dy, int dy_dtype, long long 
     if (launch_colsum(dy, dy_dtype, ldy, M, N, bias_unscaled ? nullptr : row_scale, rs_div, dbias, ws, ws_elems, s)) return -1;
   }
   if (tc_ok) {
-    const bool direct = pl.S == 1 && T == 1;
+    const bool direct = pl.S == 1 && T == 1 && dw != nullptr;     // dw == NULL: the caller wants the partials (block extraction)
     float* out = direct ? dw : ws;
     float* bout = bias_in_tc ? (direct ? dbias : ws + (size_t)pl.S * nk) : nullptr;
     if (cenet_wgrad_tc_launch(&pl, dy, ldy, x, ldx, N, K, row_scale, rs_binary != 0, out, nk, bout, N, s)) return -1;
@@ -462,6 +466,7 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
                                 int N, int K, int T, const float* row_scale, int rs_div, float* dw, float* dbias,
                                 int bias_unscaled, float* ws, long long ws_elems, cenet_stream_t st) {
   int S = 0, bp = 0;
+  CENET_REQUIRE(dw, "cenet_gemm_wgrad: null pointer");
   if (cenet_gemm_wgrad_partial(dy, dy_dtype, ldy, x, x_dtype, ldx, M, N, K, T, row_scale, rs_div, 0, dw, dbias, bias_unscaled, ws,
                                ws_elems, &S, &bp, st))
     return -1;

@@ -69,7 +69,9 @@ class _TimedOps:
             M, N, K = k["M"], k["N"], k["K"]
             in_elems = M * K
         extra = sum(M * N * t.element_size() for t in (k.get("res1"), k.get("res2"), k.get("mul")) if t is not None)
-        return (in_elems + N * K) * 2 + M * N * es_o + extra, 2.0 * M * N * K
+        desc = f"M{M} N{N} K{K}" + "".join(f" +{f}" for f in ("res1", "res2", "mul", "row_scale", "post_rs") if k.get(f) is not None) + \
+               (f" act{k['act']}" if k.get("act") else "")
+        return (in_elems + N * K) * 2 + M * N * es_o + extra, 2.0 * M * N * K, desc
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
@@ -87,7 +89,7 @@ class _TimedOps:
                 if wk is not None:
                     acc = self.work.setdefault(name, [0.0, 0.0, 0])
                     acc[0] += wk[0]; acc[1] += wk[1]; acc[2] += 1
-                    self.gemm_launches.append((name, self.tag, wk[0], wk[1], e0, e1))
+                    self.gemm_launches.append((name, self.tag + " " + wk[2], wk[0], wk[1], e0, e1))
             return r
         return timed
 

@@ -351,7 +351,18 @@ class TrainEngine:
             for i in range(3):
                 d = f"{v}.dlps.{i}"
                 self._pack_dw(d + ".depthwise", P[d + ".depthwise.weight"])
-                self._pack_mat(d + ".pointwise", P[d + ".pointwise.weight"].flatten(1))
+            # the three pointwise convs as ONE block-diagonal GEMM [Cc, 3*ap] over the padded depthwise buffer (zero rows for the
+            # pooled slice): slice widths 20 / 40 / 100 / 160 are not multiples of 8, which put three forward GEMMs per block on
+            # the scalar epilogue, their dgrads on the CUDA-core GEMM and their weight gradients on the mma.sync kernel
+            from .networks.cenet import channel_slices
+            sl_ = channel_slices(Cc)
+            a_ = sl_[0][1] - sl_[0][0]
+            ap_ = _rup(a_, 8)
+            w0 = P[f"{v}.dlps.0.pointwise.weight"]
+            bd = torch.zeros(Cc, 3 * ap_, device=w0.device, dtype=w0.dtype)
+            for i in range(3):
+                bd[sl_[i][0]:sl_[i][1], i * ap_:i * ap_ + a_] = P[f"{v}.dlps.{i}.pointwise.weight"].flatten(1)
+            self._pack_mat(v + ".dlps_bd", bd)
             self._pack_mat(f"{v}.dlps.3.1", P[f"{v}.dlps.3.1.weight"].flatten(1))
             self._pack_mat(v + ".PW_conv", P[v + ".PW_conv.weight"].flatten(1))
             self._pack_mat(m + ".proj_2", P[m + ".proj_2.weight"].flatten(1))
@@ -449,9 +460,12 @@ class TrainEngine:
 
     # Weight-gradient GEMMs leave split partials in `ws.wgrad`; ONE batched launch per gradient bucket reduces them all
     # (autograd: one AccumulateGrad per parameter; the first version of this engine: a finalize launch per GEMM).
+    def _wg_ws(self):
+        return self.buf("ws.wgrad.big", (1 << (27 if self.dev.type == "cuda" else 22),), torch.float32)
+
     def _wg_gemm(self, dy, x, dw, **kw):
         """tops.gemm_wgrad with the reduction deferred to the next `_wg_flush`; call inside `_wgrad` (side stream)"""
-        ws = self.buf("ws.wgrad.big", (1 << (27 if self.dev.type == "cuda" else 22),), torch.float32)
+        ws = self._wg_ws()
         nk = kw["N"] * (kw["K"] + 1)
         if self._wg_off + 32 * nk > ws.numel():
             self._wg_flush()
@@ -518,6 +532,31 @@ class TrainEngine:
             self._wgrad((dy, x), wg)            # (drop is written only before the forward)
         self.tape.append(bwd)
         return out
+
+    def _pw_blockdiag(self, dwb, catraw, v, sl, a, ap, M, Cc):
+        """catraw[:, slice i] = dwb[:, i*ap : i*ap+a] W_i^T for the three dilated branches of MultiOrderDWConv (cfam.py:227-241) as
+        one block-diagonal GEMM; the weight gradient is one tcgen05 launch whose reduction jobs pick the diagonal blocks."""
+        W, WT = self.w[v + ".dlps_bd.w"], self.w[v + ".dlps_bd.wT"]
+        ops.gemm(dwb, W, catraw, M=M, N=Cc, K=3 * ap, lda=3 * ap, ldw=W.stride(0), ldc=Cc, impl=self.gemm_impl)
+
+        def bwd():
+            dy = self.G(catraw)                       # (columns of the pooled slice are never written: zeros)
+            dx = self.G(dwb)
+            acc = self.wr(dwb)
+            ops.gemm(dy, WT, dx, M=M, N=3 * ap, K=Cc, lda=Cc, ldw=WT.stride(0), ldc=3 * ap, res1=dx if acc else None,
+                     ldr1=3 * ap, impl=self.gemm_impl)
+            blocks = [(self.GP[f"{v}.dlps.{i}.pointwise.weight"], sl[i][0], a, i * ap, a) for i in range(3)]
+
+            def wg():
+                ws = self._wg_ws()
+                if self._wg_off + 32 * Cc * 3 * ap > ws.numel():
+                    self._wg_flush()
+                jobs, used = tops.gemm_wgrad_blocks(dy, dwb, blocks, M=M, N=Cc, K=3 * ap, ldy=Cc, y_off=0, ldx=3 * ap, x_off=0,
+                                                    ws=ws[self._wg_off:])
+                self._wg_pending += jobs
+                self._wg_off += _rup(used, 4)
+            self._wgrad((dy, dwb), wg)
+        self.tape.append(bwd)
 
     def ln(self, x, name, out, eps):
         g, b = self.P[name + ".weight"], self.P[name + ".bias"]
@@ -817,7 +856,10 @@ class TrainEngine:
             self.dwconv(x1, dwraw, d + ".depthwise", B, H, W, a, dil=rate, ldx=Cc, x_off=a0, ldy=3 * ap, y_off=i * ap)
             self.bn_act(dwraw, M, a, d + ".depthwise_bn", dwb, f"{key}.dl{i}.dbn", act=ACT_RELU, ldx=3 * ap, x_off=i * ap,
                         ldo=3 * ap, o_off=i * ap)
-            self.lin(dwb, d + ".pointwise", catraw, M=M, N=a, K=ap, lda=3 * ap, a_off=i * ap, ldc=Cc, c_off=a0, bias=False)
+        self._pw_blockdiag(dwb, catraw, v, sl, a, ap, M, Cc)
+        for i in range(3):
+            a0, a1 = sl[i]
+            d = f"{v}.dlps.{i}"
             self.bn_act(catraw, M, a, d + ".pointwise_bn", cat, f"{key}.dl{i}.pbn", act=ACT_RELU, ldx=Cc, x_off=a0, ldo=Cc,
                         o_off=a0)
         # image-pooling branch: AdaptiveAvgPool(7) -> 1x1 -> BN -> LeakyReLU(0.01) -> bilinear x7 (align) -> bilinear (H,W)

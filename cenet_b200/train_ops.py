@@ -45,7 +45,7 @@ def gemm_wgrad(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=Non
 def gemm_wgrad_partial(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_scale=None, rs_div=1, rs_binary=False,
                        dbias=None, bias_unscaled=False, ws=None):
     """gemm_wgrad with the reduction of its split partials deferred.  Returns the reduction jobs still to run -- a list of
-    (src pointer, dst pointer, stride, S, N, K, T) for `wgrad_reduce_batch` (empty: dw / dbias are already final) -- and the
+    (src pointer, dst pointer, stride, S, N, K, T, src_ld) for `wgrad_reduce_batch` (empty: dw / dbias are already final) -- and the
     number of workspace floats the partials occupy."""
     wp, wn = _ws(ws)
     S, bp = C.c_int(0), C.c_int(0)
@@ -55,10 +55,18 @@ def gemm_wgrad_partial(dy, x, dw, *, M, N, K, ldy, y_off, ldx, x_off, T=1, row_s
     S, bp = S.value, bp.value
     if S == 0:
         return [], 0
-    jobs = [(wp, _p(dw), N * K, S, N, K, T)]
+    jobs = [(wp, _p(dw), N * K, S, N, K, T, 0)] if dw is not None else [(wp, None, N * K, S, N, K, T, 0)]
     if bp:
-        jobs.append((wp + 4 * S * N * K, _p(dbias), N, S, 1, N, 1))
+        jobs.append((wp + 4 * S * N * K, _p(dbias), N, S, 1, N, 1, 0))
     return jobs, S * (N * K + (N if bp else 0))
+
+
+def gemm_wgrad_blocks(dy, x, blocks, *, M, N, K, ldy, y_off, ldx, x_off, ws):
+    """weight gradient of a BLOCK-DIAGONAL GEMM: one tcgen05 launch computes all N x K partials, the reduction jobs pick the
+    blocks.  blocks: [(dw tensor [rows*cols], row0, rows, col0, cols)].  Returns (jobs, workspace floats used)."""
+    jobs, used = gemm_wgrad_partial(dy, x, None, M=M, N=N, K=K, ldy=ldy, y_off=y_off, ldx=ldx, x_off=x_off, ws=ws)
+    src, _, stride, S, _, _, _, _ = jobs[0]
+    return [(src + 4 * (r0 * K + c0), _p(dw), stride, S, rows, cols, 1, K) for dw, r0, rows, c0, cols in blocks], used
 
 
 def wgrad_reduce_table(jobs):
@@ -67,8 +75,8 @@ def wgrad_reduce_table(jobs):
     arr = (L.WgradJob * len(jobs))()
     blk = 0
     lib = L.load()
-    for a, (src, dst, stride, S, N, K, T) in zip(arr, jobs):
-        a.src, a.dst, a.stride, a.S, a.N, a.K, a.T, a.blk0 = src, dst, stride, S, N, K, T, blk
+    for a, (src, dst, stride, S, N, K, T, src_ld) in zip(arr, jobs):
+        a.src, a.dst, a.stride, a.S, a.N, a.K, a.T, a.blk0, a.src_ld = src, dst, stride, S, N, K, T, blk, src_ld
         blk += lib.cenet_wgrad_reduce_blocks(C.byref(a))
     return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone(), len(jobs), blk
 

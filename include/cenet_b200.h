@@ -260,14 +260,16 @@ int cenet_gemm_wgrad_partial(const void* dy, int dy_dtype, long long ldy, const 
                              int N, int K, int T, const float* row_scale, int rs_div, int rs_binary, float* dw, float* dbias,
                              int bias_unscaled, float* ws, long long ws_elems, int* n_partials, int* bias_partials,
                              cenet_stream_t s);
-/* one reduction job: dst[n, ci, t] = sum_{z<S} src[z*stride + n*K + t*Cin + ci]  (K = T*Cin; a bias row is N=1, K=len, T=1) */
+/* one reduction job: dst[n, ci, t] = sum_{z<S} src[z*stride + n*src_ld + t*Cin + ci]  (K = T*Cin; a bias row is N=1, K=len, T=1;
+ * src_ld = 0 means K; src_ld > K addresses an N x K block inside wider partial rows: the diagonal blocks of a block-diagonal
+ * GEMM, for which cenet_gemm_wgrad_partial is called with dw = NULL so that it always leaves partials) */
 typedef struct {
   const float* src;
   float* dst;
   long long stride;
   int S, N, K, T;
   int blk0;          /* first block of this job = running sum of cenet_wgrad_reduce_blocks over the preceding jobs */
-  int reserved;
+  int src_ld;
 } cenet_wgrad_job;
 /* host-only: the tile / split plan the tcgen05 weight-gradient kernel would use; out[9] = {bn, S, per_group, parts, chunks per
  * split, chunks per group, groups, rows per group, total chunks} */

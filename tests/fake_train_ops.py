@@ -61,6 +61,14 @@ def gemm_wgrad_partial(dy, x, dw, *, rs_binary=False, **kw):
     return [], 0
 
 
+def gemm_wgrad_blocks(dy, x, blocks, *, M, N, K, ldy, y_off, ldx, x_off, ws):
+    full = torch.zeros(N * K)
+    gemm_wgrad(dy, x, full, M=M, N=N, K=K, ldy=ldy, y_off=y_off, ldx=ldx, x_off=x_off)
+    for dw, r0, rows, c0, cols in blocks:
+        dw.view(-1)[:rows * cols].copy_(full.view(N, K)[r0:r0 + rows, c0:c0 + cols].reshape(-1))
+    return [], 0
+
+
 def wgrad_reduce_table(jobs):
     raise AssertionError("the emulation never defers a reduction")
 

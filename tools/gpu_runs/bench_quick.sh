@@ -9,5 +9,6 @@ print({k: d.get(k) for k in ("value", "ms_per_step", "launches_per_step", "eager
 r = d["roofline"]
 print({k: r.get(k) for k in ("achieved", "frac", "ms_per_launch", "share_of_step")}, r.get("per_launch_view"))
 for t in r.get("top_launches", []): print(t)
+for t in r.get("top_excess", []): print("excess", t)
 print(d["op_family_ms"])
 PY
