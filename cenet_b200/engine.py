@@ -23,8 +23,6 @@ import torch
 from . import ops
 from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SILU, GEMM_AUTO, GEMM_SIMT
 
-_PVT = dict(embed_dims=(64, 128, 320, 512), heads=(1, 2, 5, 8), mlp_ratios=(8, 8, 4, 4), depths=(3, 4, 6, 3),
-            sr_ratios=(8, 4, 2, 1))
 _MCA_RATES = {64: (2, 3, 5), 128: (1, 2, 4), 320: (1, 2, 3), 512: (1, 2, 2)}
 
 
@@ -120,6 +118,7 @@ class Engine:
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
+        self.pvt = module.backbone.pvt_cfg                    # widths / depths / ratios of the PVTv2 variant (pvtv2.py:385-431)
         self.w = {}
         self._wver = None
         self._bufs = {}
@@ -205,13 +204,13 @@ class Engine:
             M(pe + ".w", self._conv_mat(w))
             P(pe + ".b", sd[pe + ".proj.bias"])
             P(pe + ".ln_g", sd[pe + ".norm.weight"]); P(pe + ".ln_b", sd[pe + ".norm.bias"])
-            for i in range(_PVT["depths"][s]):
+            for i in range(self.pvt["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 for n in ("norm1", "norm2"):
                     P(f"{b}.{n}.g", sd[f"{b}.{n}.weight"]); P(f"{b}.{n}.b", sd[f"{b}.{n}.bias"])
                 for n in ("attn.q", "attn.kv", "attn.proj", "mlp.fc1", "mlp.fc2"):
                     M(f"{b}.{n}.w", sd[f"{b}.{n}.weight"]); P(f"{b}.{n}.b", sd[f"{b}.{n}.bias"])
-                if _PVT["sr_ratios"][s] > 1:
+                if self.pvt["sr_ratios"][s] > 1:
                     M(f"{b}.attn.sr.w", self._conv_mat(sd[f"{b}.attn.sr.weight"]))
                     P(f"{b}.attn.sr.b", sd[f"{b}.attn.sr.bias"])
                     P(f"{b}.attn.norm.g", sd[f"{b}.attn.norm.weight"]); P(f"{b}.attn.norm.b", sd[f"{b}.attn.norm.bias"])
@@ -289,6 +288,9 @@ class Engine:
             self._put(f"{p}.c{i}.b", t)
 
     def _pack_up(self, sd, p, kind):
+        if kind == "uprb":                                  # blocks.py:188-204: bilinear x2 + UnetResBlock(k=3)
+            self._pack_resblock(sd, p + ".up.1", 3)
+            return
         if kind == "eucb":
             dw = sd[p + ".up_dwc.1.weight"]
             self._put(p + ".dw.w", dw.reshape(dw.shape[0], 9).t())
@@ -407,8 +409,8 @@ class Engine:
         cur, curC = x_nhwc, Cin
         for s in range(4):
             ops.tag = f"enc{s+1}"
-            Cc, heads, sr = _PVT["embed_dims"][s], _PVT["heads"][s], _PVT["sr_ratios"][s]
-            hid = Cc * _PVT["mlp_ratios"][s]
+            Cc, heads, sr = self.pvt["embed_dims"][s], self.pvt["heads"][s], self.pvt["sr_ratios"][s]
+            hid = Cc * self.pvt["mlp_ratios"][s]
             k, st = (7, 4) if s == 0 else (3, 2)
             pe = f"backbone.patch_embed{s+1}"
             Ho = (H + 2 * (k // 2) - k) // st + 1
@@ -429,7 +431,7 @@ class Engine:
             h2 = self.buf(f"enc{s}.h2", (Mtok, hid))
             Nk = (H // sr) * (W // sr)
             kv = self.buf(f"enc{s}.kv", (B * Nk, 2 * Cc))
-            for i in range(_PVT["depths"][s]):
+            for i in range(self.pvt["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 ops.layernorm(t, xn, w[b + ".norm1.g"], w[b + ".norm1.b"], 1e-6)
                 self._lin(xn, b + ".attn.q", q)
@@ -581,6 +583,12 @@ class Engine:
         if out is None:
             out = self.buf(key + ".out", (Mo, Cout))
             ldc = Cout
+        if kind == "uprb":
+            t = self.buf(key + ".up", (B, 2 * H, 2 * W, Cin))
+            ops.upsample2x_ac(x, t, B, H, W, Cin)
+            self._resblock(t.view(Mo, Cin), B, 2 * H, 2 * W, Cin, Cout, 3, p + ".up.1", key, out=out, ldc=ldc, c_off=c_off)
+            ops.tag = key
+            return out
         if kind == "eucb":
             t = self.buf(key + ".dw", (Mo, Cin))
             ops.dwconv3x3(x, t, w[p + ".dw.w"], B, 2 * H, 2 * W, Cin, scale=w[p + ".dw.s"], shift=w[p + ".dw.t"],
@@ -598,10 +606,17 @@ class Engine:
         """dseb.py:153-165; returns mixer(z) + skip + dec  (== dec + DSEBlock(skip, dec), decoders.py:95)"""
         w = self.w
         ops.tag = key
-        HW, E = H * W, 2 * Cc
+        add = self.cfg.get("skip_mode", "cat") == "add"                # dseb.py:155: y = dec + skip instead of cat
+        HW, E = H * W, (Cc if add else 2 * Cc)
         y = self.buf(key + ".y", (B, E, H, W))                         # NCHW cat([dec, skip])
-        ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
-        ops.nhwc_to_nchw(skip, y, B, HW, Cc, E, Cc)
+        if add:
+            ysum = self.buf(key + ".ysum", (B * HW, Cc))
+            ops.add_(ysum, dec, B * HW * Cc, False)
+            ops.add_(ysum, skip, B * HW * Cc, True)
+            ops.nhwc_to_nchw(ysum, y, B, HW, Cc, E, 0)
+        else:
+            ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
+            ops.nhwc_to_nchw(skip, y, B, HW, Cc, E, Cc)
         tok = y.view(B * HW, E)                                        # the reference's `.view` reinterpretation
         gate = self._diff_attention(tok, B, HW, E, heads, p + ".diffattn", key + ".da")
         z = self.buf(key + ".z", (B, E, H, W))
@@ -614,7 +629,7 @@ class Engine:
             self.taps[p] = (out.float() - dec.float()).reshape(B, H, W, Cc).permute(0, 3, 1, 2).clone()
         return out
 
-    def _resblock(self, x, B, H, W, Cin, Cout, k, p, key):
+    def _resblock(self, x, B, H, W, Cin, Cout, k, p, key, out=None, ldc=None, c_off=0):
         """modules/unet.py:201-214 with BN folded; x [B,H,W,Cin] -> [B*H*W,Cout]"""
         w = self.w
         ops.tag = key
@@ -629,9 +644,10 @@ class Engine:
                      bias=w[p + ".c3.b"], impl=self.gemm_impl)
         else:
             r = x
-        o2 = self.buf(key + ".o2", (Mtok, Cout))
+        o2 = self.buf(key + ".o2", (Mtok, Cout)) if out is None else out
+        kw = {} if out is None else dict(N=Cout, ldc=ldc, c_off=c_off)
         ops.conv_nhwc(o1, w[p + ".c2.w"], o2, k, 1, k // 2, bias=w[p + ".c2.b"], act=ACT_LEAKY, slope=0.01,
-                      act_after_res=True, res1=r, ldr1=Cout, impl=self.gemm_impl)
+                      act_after_res=True, res1=r, ldr1=Cout, impl=self.gemm_impl, **kw)
         return o2
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -657,7 +673,9 @@ class Engine:
         # ---- OutHead (out.py:69-75) ----
         om = C1 // 2
         Hh, Wh = H // 2, W // 2
-        z = self.buf("head.z", (B * Hh * Wh, 2 * om))
+        madd = cfg.get("out_merge_mode", "cat") == "add"                # out.py:58-64: up(dec) + w*rb(x) instead of cat
+        mix = om if madd else 2 * om
+        z = self.buf("head.z", (B * Hh * Wh, mix))
         # out.rb.0: stem kernel (conv1+BN+LReLU and the 1x1 residual branch), then the 5x5 32->32 conv on tensor cores
         ops.tag = "head.rb"
         o1 = self.buf("head.rb.o1", (B, H, W, om))
@@ -667,9 +685,15 @@ class Engine:
         rb = self.buf("head.rb.o2", (B * H * W, om))
         ops.conv_nhwc(o1, w["out.rb.0.c2.w"], rb, 5, 1, 2, bias=w["out.rb.0.c2.b"], act=ACT_LEAKY, slope=0.01,
                       act_after_res=True, res1=rres, ldr1=om, impl=self.gemm_impl)
-        ops.maxpool2_scale(rb, z, 2 * om, om, w["out.w"], B, H, W, om)
-        self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
-        o = self._resblock(z, B, Hh, Wh, 2 * om, 2 * om, 3, "out.out.0", "head.out")
+        if madd:
+            rbp = self.buf("head.rbp", (B * Hh * Wh, om))
+            ops.maxpool2_scale(rb, rbp, om, 0, w["out.w"], B, H, W, om)
+            self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=om, c_off=0)
+            ops.add_(z, rbp, B * Hh * Wh * om, True)
+        else:
+            ops.maxpool2_scale(rb, z, 2 * om, om, w["out.w"], B, H, W, om)
+            self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
+        o = self._resblock(z, B, Hh, Wh, mix, mix, 3, "out.out.0", "head.out")
         yh = self.buf("head.y", (B * Hh * Wh, ncls), torch.float32)
         ops.tag = "head.logits"
         self._lin(o, "out.head", yh)

@@ -18,6 +18,15 @@ __all__ = ["CENet"]
 
 _PVT_B2 = dict(embed_dims=(64, 128, 320, 512), heads=(1, 2, 5, 8), mlp_ratios=(8, 8, 4, 4), depths=(3, 4, 6, 3),
                sr_ratios=(8, 4, 2, 1), drop_path_rate=0.1)          # pvtv2.py:400-406
+# the PVTv2 variants that share b2's widths (pvtv2.py:392-431): same kernels, other depths / MLP ratios.  b0 (widths 32..256,
+# head_dim 32, decoder channels [256,160,64,32]) and the ResNets (encoder.py:34-47) are not built.
+PVT_VARIANTS = {
+    "pvt_v2_b1": dict(_PVT_B2, depths=(2, 2, 2, 2)),
+    "pvt_v2_b2": _PVT_B2,
+    "pvt_v2_b3": dict(_PVT_B2, depths=(3, 4, 18, 3)),
+    "pvt_v2_b4": dict(_PVT_B2, depths=(3, 8, 27, 3)),
+    "pvt_v2_b5": dict(_PVT_B2, depths=(3, 6, 40, 3), mlp_ratios=(4, 4, 4, 4)),
+}
 _MCA_RATES = {64: (2, 3, 5), 128: (1, 2, 4), 320: (1, 2, 3), 512: (1, 2, 2)}   # decoders.py:64
 
 
@@ -92,9 +101,10 @@ def _pvt_block(dim, heads, ratio, sr):
     return blk
 
 
-def _pvt_v2_b2(in_chans=3):
+def _pvt_v2(name="pvt_v2_b2", in_chans=3):
     bb = _Holder()
-    c = _PVT_B2
+    c = PVT_VARIANTS[name]
+    bb.pvt_cfg = c
     prev = in_chans
     for s in range(4):
         pe = _Holder()
@@ -198,12 +208,17 @@ def _make_up(kind, cin, cout, ks=3):
         return _eucb(cin, cout)
     if kind == "upcn":
         return _up_conv(cin, cout, ks)
-    raise NotImplementedError(f"up block '{kind}' is outside the accelerated hot path (SURVEY.md section 2 row 9)")
+    if kind == "uprb":                                                      # blocks.py:188-204
+        m = _Holder()
+        m.up = _Seq(_1=_res_block(cin, cout, ks))
+        m.kind = "uprb"
+        return m
+    raise NotImplementedError("up block 'uptc' (ConvTranspose2d, blocks.py:223-243) is not built: see DESIGN.md section 7")
 
 
-def _dse_block(dim, scale_factors, heads, depth):
+def _dse_block(dim, scale_factors, heads, depth, mode="cat"):
     m = _Holder()
-    E = 2 * dim
+    E = 2 * dim if mode == "cat" else dim                                  # dseb.py:96
     b = _Holder()
     b.w = nn.Parameter(torch.randn(1, E, 1, 1) + 0.5)                      # dseb.py:35
     m.boundary = b
@@ -219,17 +234,17 @@ def _dse_block(dim, scale_factors, heads, depth):
     return m
 
 
-def _decoder(channels, scale_factors, heads, up_block):
+def _decoder(channels, scale_factors, heads, up_block, skip_mode="cat"):
     d = _Holder()
     d.dec4 = _cfa_module(channels[0])
     d.up3 = _make_up(up_block, channels[0], channels[1])
-    d.skip_enhancer3 = _dse_block(channels[1], scale_factors, heads[0], 4)
+    d.skip_enhancer3 = _dse_block(channels[1], scale_factors, heads[0], 4, skip_mode)
     d.dec3 = _cfa_module(channels[1])
     d.up2 = _make_up(up_block, channels[1], channels[2])
-    d.skip_enhancer2 = _dse_block(channels[2], scale_factors, heads[1], 3)
+    d.skip_enhancer2 = _dse_block(channels[2], scale_factors, heads[1], 3, skip_mode)
     d.dec2 = _cfa_module(channels[2])
     d.up1 = _make_up(up_block, channels[2], channels[3])
-    d.skip_enhancer1 = _dse_block(channels[3], scale_factors, heads[2], 2)
+    d.skip_enhancer1 = _dse_block(channels[3], scale_factors, heads[2], 2, skip_mode)
     d.dec1 = _cfa_module(channels[3])
     return d
 
@@ -254,15 +269,14 @@ def _res_block(cin, cout, k):
 def _out_head(dec_ch, x_ch, ncls, merge_mode, up_block, up_ks):
     if merge_mode not in ("cat", "add"):
         raise AssertionError(f"Invalid merge_mode: {merge_mode}")
-    if merge_mode != "cat":
-        raise NotImplementedError("out_merge_mode='add' is outside the accelerated hot path (SURVEY.md 8f row 4)")
     o = _Holder()
     om = dec_ch // 2
+    mix = om if merge_mode == "add" else 2 * om                            # out.py:47
     o.w = nn.Parameter(torch.randn(1, om, 1, 1) + 0.75)                    # out.py:39
     ob = _Holder()
-    ob.conv = _conv_only(2 * om, ncls, 1, bias=True)
+    ob.conv = _conv_only(mix, ncls, 1, bias=True)
     ob.apply(_init_unet)
-    o.out = _Seq(_0=_res_block(2 * om, 2 * om, 3), _1=ob)
+    o.out = _Seq(_0=_res_block(mix, mix, 3), _1=ob)
     o.up = _make_up(up_block, dec_ch, om, up_ks)
     o.rb = _Seq(_0=_res_block(x_ch, om, 5))
     return o
@@ -300,17 +314,19 @@ class CENet(nn.Module):
         super().__init__()
         self.writer = writer
         num_classes = int(num_classes)
-        if encoder in ("pvt_v2_b0", "pvt_v2_b1", "pvt_v2_b3", "pvt_v2_b4", "pvt_v2_b5") or "resnet" in str(encoder):
-            raise NotImplementedError(f"encoder '{encoder}': only pvt_v2_b2 is on the accelerated path "
-                                      "(SURVEY.md section 2 row 3)")
-        path = f"{base_ptdir}/pvt/pvt_v2_b2.pth"
-        if encoder != "pvt_v2_b2":                                          # encoder.py:48-52 silent fallback
+        if encoder == "pvt_v2_b0" or "resnet" in str(encoder):
+            raise NotImplementedError(f"encoder '{encoder}': the accelerated path covers pvt_v2_b1 .. b5 (the variants with the "
+                                      "widths 64/128/320/512, encoder.py:14-33); see DESIGN.md section 7")
+        path = f"{base_ptdir}/pvt/{encoder}.pth"                            # encoder.py:15-33
+        if encoder not in PVT_VARIANTS:                                     # encoder.py:48-52 silent fallback
             print("Encoder not implemented! Continuing with default encoder pvt_v2_b2.")
+            encoder = "pvt_v2_b2"
             path = f"{base_ptdir}/pretrained_pth/pvt/pvt_v2_b2.pth"
-        if skip_mode.lower() != "cat":
-            raise NotImplementedError("skip_mode='add' is outside the accelerated hot path (SURVEY.md 8f row 4)")
+        skip_mode = skip_mode.lower()
+        if skip_mode not in ("cat", "add"):                                 # (the reference treats anything but 'add' as cat)
+            skip_mode = "cat"
         channels = [512, 320, 128, 64]
-        self.backbone = _pvt_v2_b2(3)
+        self.backbone = _pvt_v2(encoder, 3)
         if enc_pretrain and base_ptdir:                                     # encoder.py:73-84
             print(f"Loading pretrained weights from {path}")
             saved = torch.load(path)
@@ -322,11 +338,11 @@ class CENet(nn.Module):
                     p.requires_grad = False
         else:
             print("No pretrained weights loaded! ...")
-        self.decoder = _decoder(channels, scale_factors, diffatt_num_heads, dec_up_block)
+        self.decoder = _decoder(channels, scale_factors, diffatt_num_heads, dec_up_block, skip_mode)
         self.out = _out_head(channels[-1], input_channels, num_classes, out_merge_mode, out_up_block, out_up_ks)
         self.cfg = dict(input_channels=input_channels, num_classes=num_classes, scale_factors=list(scale_factors),
                         diffatt_num_heads=list(diffatt_num_heads), dec_up_block=dec_up_block,
-                        out_up_block=out_up_block)
+                        out_up_block=out_up_block, encoder=encoder, skip_mode=skip_mode, out_merge_mode=out_merge_mode)
         self._engines = {}
 
     # engines hold device workspaces + packed weights; they are rebuilt lazily and never copied / pickled
@@ -376,6 +392,10 @@ class CENet(nn.Module):
             raise RuntimeError("cenet_b200.CENet has no CPU path: move the module and the input to a B200 "
                                "(`.cuda()`); the CPU oracle lives in oracle/ and is test-only")
         if self.training:
+            c = self.cfg
+            if c["skip_mode"] != "cat" or c["out_merge_mode"] != "cat" or "uprb" in (c["dec_up_block"], c["out_up_block"]):
+                raise NotImplementedError("train() mode covers skip_mode='cat', out_merge_mode='cat' and the eucb / upcn up blocks; "
+                                          "the 'add' modes and 'uprb' are inference-only here (DESIGN.md section 7)")
             if torch.is_grad_enabled():
                 params = [p for p in self.parameters()]
                 return _TrainForward.apply(self, x, *params)

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .cenet import (_Holder, _Seq, _conv_only, _eucb, _init_normal, _init_unet, _pvt_v2_b2, _res_block, _sep_conv_bn,
+from .cenet import (_Holder, _Seq, _conv_only, _eucb, _init_normal, _init_unet, _pvt_v2, _res_block, _sep_conv_bn,
                     channel_slices)
 
 __all__ = ["CENetOrg"]
@@ -105,7 +105,7 @@ class CENetOrg(nn.Module):
             self.conv = nn.Sequential(nn.Conv2d(1, 3, kernel_size=1), nn.BatchNorm2d(3), nn.ReLU(inplace=True))
         else:
             self.conv = nn.Identity()
-        self.backbone = _pvt_v2_b2(3)
+        self.backbone = _pvt_v2("pvt_v2_b2", 3)
         if pretrain:                                                        # net.py:75-84 (failure is only printed)
             path = f"{base_ptdir}/pretrained_pth/pvt/pvt_v2_b2.pth"
             try:

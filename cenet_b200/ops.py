@@ -104,6 +104,11 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ksize: int, s
                 conv=(B, H, W, Cin, ksize, ksize, stride, pad, Ho, Wo), **kw)
 
 
+def add_(dst, src, n, acc):
+    """dst[:n] (+)= src[:n]  (DSEBlock / OutHead 'add' merge modes, dseb.py:155, out.py:61)"""
+    L.call("cenet_add", _p(dst), _p(src), dt(dst), n, int(acc), _stream())
+
+
 # ------------------------------------------------------------------------------------------------------ norms
 def layernorm(x2d, out, gamma, beta, eps):
     rows, Cc = x2d.shape

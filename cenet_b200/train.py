@@ -32,7 +32,7 @@ import torch
 
 from . import ops as _ops_mod
 from . import train_ops as _tops_mod
-from .engine import _MCA_RATES, _PVT, _rup, lambda_init
+from .engine import _MCA_RATES, _rup, lambda_init
 from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT
 from .train_ops import ACT_GELU_GRAD
 
@@ -152,6 +152,7 @@ class TrainEngine:
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
+        self.pvt = module.backbone.pvt_cfg                    # widths / depths / ratios of the PVTv2 variant (pvtv2.py:385-431)
         self.drop_path = True                 # stochastic depth of the encoder (pvtv2.py:146-147); tests switch it off
         self.momentum = 0.1
         self.w = {}                           # packed (compute-dtype / re-laid-out) weights
@@ -336,11 +337,11 @@ class TrainEngine:
             pe = f"backbone.patch_embed{s+1}"
             if s > 0:
                 self._pack_conv(pe + ".proj", P[pe + ".proj.weight"], im2col=True)
-            for i in range(_PVT["depths"][s]):
+            for i in range(self.pvt["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 for n in ("attn.q", "attn.kv", "attn.proj", "mlp.fc1", "mlp.fc2"):
                     self._pack_mat(f"{b}.{n}", P[f"{b}.{n}.weight"])
-                if _PVT["sr_ratios"][s] > 1:
+                if self.pvt["sr_ratios"][s] > 1:
                     self._pack_conv(f"{b}.attn.sr", P[f"{b}.attn.sr.weight"], im2col=True)
                 self._pack_dw(f"{b}.mlp.dwconv.dwconv", P[f"{b}.mlp.dwconv.dwconv.weight"])
         for name, Cc in (("dec4", 512), ("dec3", 320), ("dec2", 128), ("dec1", 64)):
@@ -751,8 +752,8 @@ class TrainEngine:
         for s in range(4):
             ops.tag = f"enc{s+1}"
             self._mark_bucket(s)
-            Cc, heads, sr = _PVT["embed_dims"][s], _PVT["heads"][s], _PVT["sr_ratios"][s]
-            hid = Cc * _PVT["mlp_ratios"][s]
+            Cc, heads, sr = self.pvt["embed_dims"][s], self.pvt["heads"][s], self.pvt["sr_ratios"][s]
+            hid = Cc * self.pvt["mlp_ratios"][s]
             k, st = (7, 4) if s == 0 else (3, 2)
             pe = f"backbone.patch_embed{s+1}"
             traw = self.buf(f"enc{s}.traw", (B * ((H + 2 * (k // 2) - k) // st + 1) * ((W + 2 * (k // 2) - k) // st + 1), Cc))
@@ -765,7 +766,7 @@ class TrainEngine:
             Mtok = B * H * W
             t = self.ln(traw, pe + ".norm", self.buf(f"enc{s}.t0", (Mtok, Cc)), 1e-5)
             Nk = (H // sr) * (W // sr)
-            for i in range(_PVT["depths"][s]):
+            for i in range(self.pvt["depths"][s]):
                 b = f"backbone.block{s+1}.{i}"
                 kb = f"enc{s}.b{i}"
                 drop = drop2 = None                                          # two independent draws per block:

@@ -33,12 +33,21 @@ class Cfg:
     diffatt_num_heads: List[int] = field(default_factory=lambda: [2, 2, 2])
     dec_up_block: str = "eucb"
     out_up_block: str = "eucb"
-    # pvt_v2_b2 (pvtv2.py:400-406)
+    skip_mode: str = "cat"                 # DSEBlock: cat([dec, skip]) or dec + skip (dseb.py:155)
+    out_merge_mode: str = "cat"            # OutHead.merge (out.py:58-64)
+    encoder: str = "pvt_v2_b2"
+    # pvt_v2_b2 (pvtv2.py:400-406); b1 / b3 / b4 / b5 differ in depths and MLP ratios only (pvtv2.py:392-431)
     embed_dims: tuple = (64, 128, 320, 512)
     enc_heads: tuple = (1, 2, 5, 8)
     mlp_ratios: tuple = (8, 8, 4, 4)
     depths: tuple = (3, 4, 6, 3)
     sr_ratios: tuple = (8, 4, 2, 1)
+
+    def __post_init__(self):
+        table = {"pvt_v2_b1": ((2, 2, 2, 2), (8, 8, 4, 4)), "pvt_v2_b2": ((3, 4, 6, 3), (8, 8, 4, 4)),
+                 "pvt_v2_b3": ((3, 4, 18, 3), (8, 8, 4, 4)), "pvt_v2_b4": ((3, 8, 27, 3), (8, 8, 4, 4)),
+                 "pvt_v2_b5": ((3, 6, 40, 3), (4, 4, 4, 4))}
+        self.depths, self.mlp_ratios = table[self.encoder]
 
 
 MCA_RATES = {64: (2, 3, 5), 128: (1, 2, 4), 320: (1, 2, 3), 512: (1, 2, 2)}  # decoders.py:64
@@ -184,9 +193,9 @@ def diff_attention(sd, p, t, heads, depth):
     return F.linear(o, sd[p + ".out_proj.weight"])
 
 
-def dse_block(sd, p, skip, dec, scale_factors, heads, depth):
-    """dseb.py:153-165 + 114-118 (A4), mode='cat', use_command='dat-fea'."""
-    y = torch.cat([dec, skip], 1).contiguous()
+def dse_block(sd, p, skip, dec, scale_factors, heads, depth, mode="cat"):
+    """dseb.py:153-165 + 114-118 (A4), use_command='dat-fea'; mode 'cat' or 'add' (dseb.py:155)."""
+    y = (dec + skip) if mode == "add" else torch.cat([dec, skip], 1).contiguous()
     B, C2, H, W = y.shape
     x_fea = fea(sd, p + ".boundary", y, scale_factors) + y
     tok = y.view(B, H * W, C2)                                  # pure reinterpretation of the CHW buffer
@@ -300,11 +309,19 @@ def up_conv(sd, p, x, training=False):
     return F.leaky_relu(_bn(sd, p + ".up.2", x, training), 0.2)
 
 
+def up_rb(sd, p, x, training=False):
+    """blocks.py:188-204: bilinear x2 (align_corners=True) -> UnetResBlock(k=3)."""
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    return unet_res_block(sd, p + ".up.1", x, 3, training)
+
+
 def _up_block(kind):
     if kind == "eucb":
         return eucb
     if kind == "upcn":
         return up_conv
+    if kind == "uprb":
+        return up_rb
     raise NotImplementedError(f"up block '{kind}' is outside the BASELINE configs (SURVEY section 2 row 9)")
 
 
@@ -317,7 +334,7 @@ def decoder(sd, cfg: Cfg, x4, skips, training=False, taps=None):
     for lvl, skip, depth, hi in ((3, skips[0], 4, 0), (2, skips[1], 3, 1), (1, skips[2], 2, 2)):
         d = up(sd, f"decoder.up{lvl}", d, training)
         s = dse_block(sd, f"decoder.skip_enhancer{lvl}", skip, d, cfg.scale_factors, cfg.diffatt_num_heads[hi],
-                      depth)
+                      depth, cfg.skip_mode.lower())
         if taps is not None:
             taps[f"decoder.up{lvl}"] = d
             taps[f"decoder.skip_enhancer{lvl}"] = s
@@ -343,7 +360,7 @@ def out_head(sd, cfg: Cfg, dec, x, training=False, taps=None):
     """out.py:69-75."""
     rb = sd["out.w"] * F.max_pool2d(unet_res_block(sd, "out.rb.0", x, 5, training), 2)
     d = _up_block(cfg.out_up_block)(sd, "out.up", dec, training)
-    z = torch.cat([d, rb], 1)
+    z = (d + rb) if cfg.out_merge_mode == "add" else torch.cat([d, rb], 1)
     y = unet_res_block(sd, "out.out.0", z, 3, training)
     y = F.conv2d(y, sd["out.out.1.conv.conv.weight"], sd["out.out.1.conv.conv.bias"])
     if taps is not None:

@@ -16,6 +16,16 @@ CONFIGS = {
                     out_up_block="upcn"),
     "skin": dict(input_channels=3, num_classes=2, scale_factors=[1.0, 0.75, 0.5], diffatt_num_heads=[2, 2, 2],
                  out_up_block="upcn"),
+    # the other PVTv2 variants (encoder.py:14-33) -- same kernels, other depths / MLP ratios
+    "acdc_b1": dict(input_channels=1, num_classes=4, scale_factors=[1.0, 0.5], diffatt_num_heads=[4, 4, 4],
+                    out_up_block="upcn", encoder="pvt_v2_b1"),
+    # ... and the merge / up-block variants (dseb.py:155, out.py:58-64, blocks.py:188-204)
+    "acdc_add": dict(input_channels=1, num_classes=4, scale_factors=[1.0, 0.5], diffatt_num_heads=[4, 4, 4],
+                     out_up_block="upcn", skip_mode="add", out_merge_mode="add"),
+    "synapse_uprb": dict(input_channels=1, num_classes=9, scale_factors=[0.8, 0.4], diffatt_num_heads=[16, 8, 8],
+                         out_up_block="uprb", dec_up_block="uprb"),
+    "acdc_b5": dict(input_channels=1, num_classes=4, scale_factors=[1.0, 0.5], diffatt_num_heads=[4, 4, 4],
+                    out_up_block="upcn", encoder="pvt_v2_b5"),
 }
 
 
@@ -47,6 +57,7 @@ def synth_input(name: str, batch: int, size: int = 224, seed: int = 0) -> torch.
     """Synthetic slices shaped like each dataset's pre-processed input."""
     g = torch.Generator().manual_seed(seed)
     cin = CONFIGS[name]["input_channels"]
+    name = name.split("_")[0]                    # variants (acdc_b1, ...) use the input statistics of their base config
     if name == "synapse":
         return (torch.randn(batch, cin, size, size, generator=g) * 0.5).clamp_(-1, 1)
     if name == "skin":

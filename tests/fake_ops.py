@@ -198,6 +198,12 @@ def upsample2x_ac(x, out, B, H, W, Cc):
     return out
 
 
+def add_(dst, src, n, acc):
+    _LAUNCHES[0] += 1
+    d = _flat(dst)[:n]
+    d.copy_((d.float() + _flat(src)[:n].float()) if acc else _flat(src)[:n].float())
+
+
 def maxpool2_scale(x, out, ldy, coff, wch, B, H, W, Cc):
     _LAUNCHES[0] += 1
     xi = _flat(x).view(B, H, W, Cc).float().permute(0, 3, 1, 2)

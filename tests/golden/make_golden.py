@@ -276,6 +276,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "loss":          # only the loss fixtures (no model import needed)
         loss_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":      # other PVTv2 encoders
+        nets = ref_shim.import_reference()
+        model_fixture(nets, "acdc_b1", 1)
+        model_fixture(nets, "acdc_b5", 1)
+        model_fixture(nets, "acdc_add", 1)
+        model_fixture(nets, "synapse_uprb", 1)
+        sys.exit(0)
     nets = ref_shim.import_reference()
     module_fixtures(nets)
     loss_fixture()

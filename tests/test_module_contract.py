@@ -72,6 +72,11 @@ def test_error_conventions():
     with pytest.raises(NotImplementedError):
         CENetOrg(skip_mode="add")
     CENet(encoder="not_an_encoder")                                    # encoder.py:48-52: silent fallback to b2
+    with pytest.raises(NotImplementedError):
+        CENet(encoder="pvt_v2_b0")                                     # widths 32..256: not built
+    n1 = sum(p.numel() for p in CENet(encoder="pvt_v2_b1").backbone.parameters())
+    n3 = sum(p.numel() for p in CENet(encoder="pvt_v2_b3").backbone.parameters())
+    assert n1 < n3                                                     # pvtv2.py:392-413: depths (2,2,2,2) vs (3,4,18,3)
 
 
 def test_no_cpu_path():

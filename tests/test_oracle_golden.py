@@ -102,7 +102,8 @@ def test_boundary_dou_loss(golden_loss_boundary):
         assert torch.equal(S, torch.bincount(c["labels"].flatten(), minlength=ncls)) and bool((C <= S).all())
 
 
-@pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1)])
+@pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1), ("acdc_b1", 1), ("acdc_b5", 1),
+                                        ("acdc_add", 1), ("synapse_uprb", 1)])
 def test_whole_model(name, batch):
     """Rebuild the deterministic weights, run the oracle, compare with what the reference produced."""
     from cenet_b200.networks import CENet
