@@ -87,6 +87,9 @@ _SIGS = {
     "cenet_gemm_wgrad_partial": [vp, i32, ll, vp, i32, ll, ll, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, ll,
                                  C.POINTER(i32), C.POINTER(i32), vp],
     "cenet_wgrad_reduce_batch": [vp, i32, i32, vp],
+    "cenet_colsum": [vp, i32, ll, ll, i32, vp, i32, vp, vp, ll, vp],
+    "cenet_row_scale": [vp, i32, vp, vp, ll, i32, vp],
+    "cenet_smallk_dgrad": [vp, i32, vp, ll, vp, i32, ll, ll, i32, i32, vp],
     "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
     "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
     "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, ll, vp],

@@ -478,6 +478,14 @@ extern "C" int cenet_gemm_wgrad(const void* dy, int dy_dtype, long long ldy, con
   return 0;
 }
 
+// out[c] = sum_r rs[r / rs_div] * x[r, c]   (bias gradients; with rs = a one-channel input image it is the weight gradient of a
+// 1x1 conv with Cin = 1, unet.py:205-207 at input_channels = 1)
+extern "C" int cenet_colsum(const void* x, int dtype, long long ld, long long rows, int C, const float* row_scale, int rs_div, float* out,
+                            float* ws, long long ws_elems, cenet_stream_t st) {
+  CENET_REQUIRE(x && out && ws && rs_div >= 1, "cenet_colsum: bad arguments");
+  return launch_colsum(x, dtype, ld, rows, C, row_scale, rs_div, out, ws, ws_elems, to_stream(st));
+}
+
 // number of 256-thread blocks job j needs in cenet_wgrad_reduce_batch (the caller lays out blk0 with it)
 extern "C" int cenet_wgrad_reduce_blocks(const cenet_wgrad_job* j) {
   const long long nk = (long long)j->N * j->K;

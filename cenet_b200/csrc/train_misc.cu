@@ -181,6 +181,52 @@ __global__ void __launch_bounds__(256) add_kernel(T* __restrict__ dst, const T* 
   }
 }
 
+// out[m, c] = x[m, c] * rs[m]   (the per-pixel SRM gate applied to d(fc2 output), so that its weight gradient is a plain GEMM)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) row_scale_kernel(const T* __restrict__ x, const float* __restrict__ rs, T* __restrict__ out,
+                                                        long long rows, int C) {
+  const int groups = C / V;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int c0 = (int)(i % groups) * V;
+    float a[V];
+    ldv<V>(x + r * C + c0, a);
+    const float sc = rs[r];
+#pragma unroll
+    for (int j = 0; j < V; j++) a[j] *= sc;
+    stv<V>(out + r * C + c0, a);
+  }
+}
+
+// dx[m, 0:N) (+)= sum_{k<K} dy[m, k] * w[k, n]    with a tiny contraction (K <= 16: the class dimension of the logits): every
+// thread owns 8 output columns of one row; w lives in shared memory.  Replaces a CUDA-core GEMM launch whose tiles did K = 4.
+template <typename T>
+__global__ void __launch_bounds__(256) smallk_dgrad_kernel(const float* __restrict__ dy, int K, const float* __restrict__ w, long long ldw,
+                                                           T* __restrict__ dx, long long ldx, long long rows, int N, int acc) {
+  extern __shared__ float sw[];                 // [K][N]
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) sw[i] = w[(long long)(i / N) * ldw + (i % N)];
+  __syncthreads();
+  const int groups = N / 8;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int c0 = (int)(i % groups) * 8;
+    float o[8];
+    if (acc) ldv<8>(dx + r * ldx + c0, o);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = 0.f;
+    }
+    for (int k = 0; k < K; k++) {
+      const float g = dy[r * K + k];
+#pragma unroll
+      for (int j = 0; j < 8; j++) o[j] = fmaf(g, sw[k * N + c0 + j], o[j]);
+    }
+    stv<8>(dx + r * ldx + c0, o);
+  }
+}
+
 // y[b,i,j,c] (+)= sum_{a in taps_h(i)} sum_{e in taps_w(j)} wh[a] ww[e] x[b, hi[a], wi[e], c]
 template <typename TI, typename TO, int V>
 __global__ void __launch_bounds__(256) resample_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y, long long ldy, int B,
@@ -409,6 +455,31 @@ extern "C" int cenet_add(void* dst, const void* src, int dtype, long long n, int
     const int Vv = vec_of(sizeof(T), {dst, src}, {n});
     DISPATCH_V(Vv, (add_kernel<T, V><<<ew_blocks(n / Vv), 256, 0, to_stream(st)>>>((T*)dst, (const T*)src, n, acc)));
     CENET_LAUNCH_CHECK("add");
+  });
+  return 0;
+}
+
+extern "C" int cenet_row_scale(const void* x, int dtype, const float* rs, void* out, long long rows, int C, cenet_stream_t st) {
+  CENET_REQUIRE(x && rs && out, "cenet_row_scale: null pointer");
+  if (rows == 0) return 0;
+  CENET_DISPATCH(dtype, T, {
+    const int Vv = vec_of(sizeof(T), {x, out}, {C});
+    DISPATCH_V(Vv, (row_scale_kernel<T, V><<<ew_blocks(rows * (C / Vv)), 256, 0, to_stream(st)>>>((const T*)x, rs, (T*)out, rows, C)));
+    CENET_LAUNCH_CHECK("row_scale");
+  });
+  return 0;
+}
+
+extern "C" int cenet_smallk_dgrad(const float* dy, int K, const float* w, long long ldw, void* dx, int dx_dtype, long long ldx,
+                                  long long rows, int N, int acc, cenet_stream_t st) {
+  CENET_REQUIRE(dy && w && dx, "cenet_smallk_dgrad: null pointer");
+  CENET_REQUIRE(K >= 1 && K <= 16 && N % 8 == 0 && N <= 512 && ldx % 8 == 0 && (((uintptr_t)dx & 15) == 0),
+                "cenet_smallk_dgrad: K=%d N=%d ldx=%lld not supported (K <= 16, N %% 8 == 0, 16-byte rows)", K, N, ldx);
+  if (rows == 0) return 0;
+  CENET_DISPATCH(dx_dtype, T, {
+    smallk_dgrad_kernel<T><<<ew_blocks(rows * (N / 8)), 256, (size_t)K * N * sizeof(float), to_stream(st)>>>(dy, K, w, ldw, (T*)dx, ldx,
+                                                                                                            rows, N, acc);
+    CENET_LAUNCH_CHECK("smallk_dgrad");
   });
   return 0;
 }

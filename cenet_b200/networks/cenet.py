@@ -305,6 +305,22 @@ class _TrainForward(torch.autograd.Function):
         return (None, None) + grads
 
 
+class _EvalForward(torch.autograd.Function):
+    """eval()-mode forward under grad mode (ACDC `val()` main_acdc.py:226, utils_skin.py:104,143 and the FLOP-counter warm-ups
+    utils.py:184-185 run the network that way and never call backward): the logits come from the inference launch plan and carry
+    a graph node like the reference's output does (`requires_grad`, `.detach()`, `.item()` behave the same).  A backward pass through
+    the eval-mode network (running-statistics BatchNorm) is not built: it raises instead of returning wrong gradients."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        return module._engine(x).forward(x)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        raise NotImplementedError("cenet_b200: backward through an eval()-mode forward is not built (the reference scripts never "
+                                  "call it); switch to train() for gradients -- DESIGN.md section 7")
+
+
 class CENet(nn.Module):
     """Same constructor as the reference `networks.CENet` (net.py:9-22)."""
 
@@ -400,6 +416,8 @@ class CENet(nn.Module):
                 params = [p for p in self.parameters()]
                 return _TrainForward.apply(self, x, *params)
             return self.train_engine(x.device).forward_logits(x).clone()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _EvalForward.apply(self, x, *self.parameters())
         return self._engine(x).forward(x)
 
     @torch.no_grad()

@@ -520,10 +520,17 @@ class TrainEngine:
                 tgt = dmul if dmul is not None else x
                 dx = self.G(tgt)
                 acc = self.wr(tgt, a_off)
-                ops.gemm(dy, WT, dx, M=M, N=Kr, K=N, lda=ldc, ldw=WT.stride(0), ldc=lda, a_off=c_off, c_off=a_off,
-                         row_scale=drop, rs_div=drop_div, mul=dmul, ldmul=dmul.stride(0) if dmul is not None else 0,
-                         mul_act=ACT_GELU_GRAD if dmul is not None else ACT_NONE,
-                         res1=dx if acc else None, ldr1=lda, r1_off=a_off, impl=self.gemm_impl)
+                Wf = self.P.get(wn + ".weight")
+                if (self.T == torch.bfloat16 and dy.dtype == torch.float32 and N <= 16 and Kr % 8 == 0 and drop is None
+                        and dmul is None and a_off == 0 and c_off == 0 and ldc == N and Wf is not None and Wf.numel() == N * Kr):
+                    # fp32 gradient of a layer with a handful of outputs (the class logits): K = N_classes is too short for a
+                    # GEMM tile -- one element-wise pass with the fp32 master weight in shared memory
+                    tops.smallk_dgrad(dy, Wf, dx, rows=M, K=N, N=Kr, ldw=Kr, ldx=lda, acc=acc)
+                else:
+                    ops.gemm(dy, WT, dx, M=M, N=Kr, K=N, lda=ldc, ldw=WT.stride(0), ldc=lda, a_off=c_off, c_off=a_off,
+                             row_scale=drop, rs_div=drop_div, mul=dmul, ldmul=dmul.stride(0) if dmul is not None else 0,
+                             mul_act=ACT_GELU_GRAD if dmul is not None else ACT_NONE,
+                             res1=dx if acc else None, ldr1=lda, r1_off=a_off, impl=self.gemm_impl)
 
             def wg():
                 for pn, r0, nr in wgrads:
@@ -942,8 +949,19 @@ class TrainEngine:
             dmo = self.G(mo)
             dh3 = self.buf(key + ".dh3", (M, 4 * Cc))
             ops.gemm(dmo, W2T, dh3, M=M, N=4 * Cc, K=Cc, lda=Cc, ldw=W2T.stride(0), ldc=4 * Cc, impl=self.gemm_impl)
-            tops.gemm_wgrad(dmo, h2, GP[q + ".fc2.weight"], M=M, N=Cc, K=4 * Cc, ldy=Cc, y_off=0, ldx=4 * Cc, x_off=0,
-                            row_scale=gm, dbias=GP[q + ".fc2.bias"], bias_unscaled=True, ws=self._ws(0))
+            if self.T == torch.bfloat16:
+                # mo = gm * (h2 W^T) + b: fold the per-pixel gate into d(mo) once, then the weight gradient is a plain tcgen05 GEMM
+                # (a per-row scale kept it on the mma.sync kernel) and the bias gradient a column sum of the unscaled d(mo)
+                dmo_s = self.buf(key + ".dmo_s", (M, Cc))
+                tops.row_scale(dmo, gm, dmo_s, M, Cc)
+
+                def wg():
+                    self._wg_gemm(dmo_s, h2, GP[q + ".fc2.weight"], M=M, N=Cc, K=4 * Cc, ldy=Cc, y_off=0, ldx=4 * Cc, x_off=0)
+                    tops.colsum(dmo, GP[q + ".fc2.bias"], rows=M, C=Cc, ld=Cc, ws=self._wws())
+                self._wgrad((dmo_s, h2, dmo), wg)
+            else:
+                tops.gemm_wgrad(dmo, h2, GP[q + ".fc2.weight"], M=M, N=Cc, K=4 * Cc, ldy=Cc, y_off=0, ldx=4 * Cc, x_off=0,
+                                row_scale=gm, dbias=GP[q + ".fc2.bias"], bias_unscaled=True, ws=self._ws(0))
             dgm = self.buf(key + ".srm_dg", (M,), torch.float32)
             tops.row_dot(dh3, h2, dgm, M, 4 * Cc)
             dsu = self.buf(key + ".srm_du", (M, 3), torch.float32)
@@ -1191,8 +1209,12 @@ class TrainEngine:
             def wg():
                 self._wg_gemm(do1, col, GP["out.rb.0.conv1.conv.weight"], M=Mf, N=om, K=25 * Cin, ldy=om, y_off=0, ldx=Kp,
                               x_off=0, T=25)
-                self._wg_gemm(drr, xc, GP["out.rb.0.conv3.conv.weight"], M=Mf, N=om, K=Cin, ldy=om, y_off=0, ldx=Cin, x_off=0)
-            self._wgrad((do1, col, drr, xc), wg)
+                if Cin == 1 and x_in.dtype == torch.float32:
+                    # 1x1 conv over ONE input channel: dW[n] = sum_m dY[m, n] * x[m] is a column sum weighted by the image
+                    tops.colsum(drr, GP["out.rb.0.conv3.conv.weight"], rows=Mf, C=om, ld=om, row_scale=x_in.view(-1), ws=self._wws())
+                else:
+                    self._wg_gemm(drr, xc, GP["out.rb.0.conv3.conv.weight"], M=Mf, N=om, K=Cin, ldy=om, y_off=0, ldx=Cin, x_off=0)
+            self._wgrad((do1, col, drr, xc, x_in), wg)
         self.tape.append(stem_bwd)
         o1 = self.buf("head.rb.o1", (B, H, W, om))
         self.bn_act(o1raw.view(Mf, om), Mf, om, "out.rb.0.norm1", o1.view(Mf, om), "head.rb.bn1", act=ACT_LEAKY, slope=0.01)

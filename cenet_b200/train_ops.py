@@ -86,6 +86,22 @@ def wgrad_reduce_batch(table, njobs, nblocks):
     L.call("cenet_wgrad_reduce_batch", _p(table), njobs, nblocks, _stream())
 
 
+def colsum(x, out, *, rows, C, ld, x_off=0, row_scale=None, rs_div=1, ws=None):
+    """out[c] = sum_r row_scale[r // rs_div] * x[r, c]"""
+    wp, wn = _ws(ws)
+    L.call("cenet_colsum", _po(x, x_off), dt(x), ld, rows, C, _f32(row_scale, "row_scale"), rs_div, _f32(out, "out"), wp, wn, _stream())
+
+
+def row_scale(x, rs, out, rows, C):
+    """out[m, :] = x[m, :] * rs[m]   (contiguous [rows, C])"""
+    L.call("cenet_row_scale", _p(x), dt(x), _f32(rs, "rs"), _p(out), rows, C, _stream())
+
+
+def smallk_dgrad(dy, w, dx, *, rows, K, N, ldw, ldx, acc):
+    """dx[m, :N] (+)= dy[m, :K] @ w[:K, :N]   (dy fp32 contiguous, w fp32 with pitch ldw)"""
+    L.call("cenet_smallk_dgrad", _f32(dy, "dy"), K, _f32(w, "w"), ldw, _p(dx), dt(dx), ldx, rows, N, int(acc), _stream())
+
+
 def conv_wgrad(dy, x4, dw, ksize, ws):
     """dw [N,Cin,k,k] of a stride-1 'same' conv: dy [B*H*W, N] contiguous, x4 [B,H,W,Cin] contiguous (no im2col buffer)"""
     B, H, W, Cin = x4.shape

@@ -278,6 +278,16 @@ int cenet_wgrad_plan_query(long long M, int N, int K, int has_rs, int rs_div, in
 int cenet_wgrad_reduce_blocks(const cenet_wgrad_job* j);
 /* jobs: DEVICE array; fixed summation order (bit-reproducible, no float atomics) */
 int cenet_wgrad_reduce_batch(const cenet_wgrad_job* jobs, int njobs, int nblocks, cenet_stream_t s);
+/* out[c] = sum_r rs[r / rs_div] * x[r, c] (rs nullable): bias gradients, and the weight gradient of a 1x1 conv over a ONE-channel
+ * image (rs = the image; unet.py:205-207 with input_channels = 1).  Two-stage fixed-order reduction through ws. */
+int cenet_colsum(const void* x, int dtype, long long ld, long long rows, int C, const float* row_scale, int rs_div, float* out,
+                 float* ws, long long ws_elems, cenet_stream_t s);
+/* out[m, c] = x[m, c] * rs[m]  (contiguous [rows, C]; the per-pixel SRM gate folded into d(fc2 output), cfam.py:157) */
+int cenet_row_scale(const void* x, int dtype, const float* rs, void* out, long long rows, int C, cenet_stream_t s);
+/* dx[m, 0:N) (+)= sum_{k<K} dy[m, k] * w[k*ldw + n]: input gradient of a layer with a tiny output width (K <= 16 classes of the
+ * segmentation head, unet.py:357-381): dy fp32 [rows, K] contiguous, w fp32, dx [rows, N] (pitch ldx), N % 8 == 0 */
+int cenet_smallk_dgrad(const float* dy, int K, const float* w, long long ldw, void* dx, int dx_dtype, long long ldx, long long rows,
+                       int N, int acc, cenet_stream_t s);
 /* weight gradient of a dense stride-1 "same" conv WITHOUT im2col: x is the NHWC image [B,H,W,Cin] (pitch ldx), dy [B*H*W, N] (pitch
  * ldy); dw in the reference layout [N, Cin, k, k].  The X operand tile is gathered tap by tap inside the kernel. */
 int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int B, int H, int W,

@@ -77,6 +77,26 @@ def wgrad_reduce_batch(table, njobs, nblocks):
     raise AssertionError("the emulation never defers a reduction")
 
 
+def colsum(x, out, *, rows, C, ld, x_off=0, row_scale=None, rs_div=1, ws=None):
+    _LAUNCHES[0] += 2
+    v = _m(x, rows, C, ld, x_off).float()
+    if row_scale is not None:
+        v = v * row_scale.view(-1)[torch.arange(rows) // rs_div][:, None]
+    out.view(-1)[:C].copy_(v.sum(0))
+
+
+def row_scale(x, rs, out, rows, C):
+    _LAUNCHES[0] += 1
+    _flat(out)[:rows * C].view(rows, C).copy_(_flat(x)[:rows * C].view(rows, C).float() * rs.view(-1)[:rows, None])
+
+
+def smallk_dgrad(dy, w, dx, *, rows, K, N, ldw, ldx, acc):
+    _LAUNCHES[0] += 1
+    wv = _as(_flat(w), (K, N), (ldw, 1), 0).float()
+    v = dy.view(rows, K).float() @ wv
+    _store(_m(dx, rows, N, ldx, 0), v, acc)
+
+
 def conv_wgrad(dy, x4, dw, ksize, ws):
     _LAUNCHES[0] += 2
     B, H, W, Cin = x4.shape

@@ -180,3 +180,18 @@ def test_other_batch_and_dropin_host_behaviour():
         y_tr = m(xb.to(DEV))
     assert y_tr.shape == y.shape and torch.isfinite(y_tr).all()
     m.eval()
+
+
+def test_eval_forward_under_grad_mode_carries_a_graph():
+    """main_acdc.py:226 / utils_skin.py:104: eval() forward WITHOUT no_grad -- same values as the no_grad call, output requires grad
+    (as the reference's does), and a backward through it is an explicit error, not silence"""
+    m, x, _, _ = build("acdc", 1)
+    xg = x.to(DEV)
+    with torch.no_grad():
+        y0 = m(xg)
+    y1 = m(xg)
+    assert y1.requires_grad and y1.grad_fn is not None and not y0.requires_grad
+    assert torch.equal(y0, y1.detach())
+    assert torch.argmax(torch.softmax(y1, 1), 1).shape == (1, 224, 224)          # what val() does with it
+    with pytest.raises(NotImplementedError):
+        y1.sum().backward()

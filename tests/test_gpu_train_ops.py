@@ -185,6 +185,20 @@ def test_gemm_wgrad_mask_all_dropped():
     assert float(dw.abs().max()) == 0.0 and float(db.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_colsum_row_scale_smallk(dtype):
+    rows, C = 5000, 32
+    x = rn((rows, C), dtype, 1)
+    rs = torch.rand(rows, generator=gen(2)) + 0.5
+    check("colsum", [x, torch.zeros(C)], dict(rows=rows, C=C, ld=C, row_scale=rs, ws=ws()), [1], 3e-4 if dtype == F32 else 1.5e-2)
+    check("colsum", [x, torch.zeros(C)], dict(rows=rows, C=C, ld=C, ws=ws()), [1], 3e-4 if dtype == F32 else 1.5e-2)
+    check("row_scale", [x, rs, torch.zeros(rows, C, dtype=dtype), rows, C], {}, [2], TOL[dtype])
+    K, N = 4, 64
+    dy, w = rn((rows, K), F32, 3), rn((K, N), F32, 4)
+    for acc in (False, True):
+        check("smallk_dgrad", [dy, w, rn((rows, N), dtype, 5)], dict(rows=rows, K=K, N=N, ldw=N, ldx=N, acc=acc), [2], TOL[dtype])
+
+
 def test_gemm_wgrad_mixed_dtypes_unscaled_bias():
     M, N, K = 5000, 4, 64                                   # head: fp32 logits gradient x bf16 activations
     dy, x = rn((M, N), F32, 1), rn((M, K), BF16, 2)
