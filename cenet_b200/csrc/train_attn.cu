@@ -169,6 +169,11 @@ struct FlashArgs {
   long long ldq, ldk, ldv, ldo;
   int maps, Nq, Nk, vdiv;
   float scale, c;        // c = scale * log2(e)
+  // dK / dV of a SHORT key set (<= 64 keys: the SR attention of the encoder, 49 reduced keys) -- the key-parallel kernel would
+  // be B x heads CTAs walking all queries; instead blockIdx.x splits the QUERIES, every CTA leaves fp32 partials
+  // part[split][b][map][64][D] and flash_kv_reduce_kernel adds them in split order (deterministic)
+  int qsplit, qchunk;
+  float *partK, *partV;
 };
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -412,7 +417,9 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
   __shared__ __align__(16) bf16 sGb[KT * BQ * (DV + 8)];
   __shared__ float sLb[KT * BQ], sDb[KT * BQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.z, vh = blockIdx.y, kr0 = blockIdx.x * BKEY + warp * 16;
+  const bool split = p.qsplit > 1;
+  const int b = blockIdx.z, vh = blockIdx.y, kr0 = (split ? 0 : blockIdx.x * BKEY) + warp * 16;
+  const int q_lo = split ? blockIdx.x * p.qchunk : 0, q_hi = split ? min(p.Nq, q_lo + p.qchunk) : p.Nq;
   const bf16* Vp = p.V + (long long)b * p.Nk * p.ldv + vh * DV;
   constexpr int KS = (DQK + 15) / 16;
   constexpr bool DO_DV = MODE != 2, DO_DK = MODE != 1;
@@ -451,19 +458,19 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
     TileRegs<DV, QR> rg;
     float rl[SR], rd[SR];
     auto fetch = [&](int qt0) {
-      fetch_tile<DQK, QR>(rq, Qp, p.ldq, qt0, p.Nq, tid);
-      fetch_tile<DV, QR>(rg, dOp, p.ldo, qt0, p.Nq, tid);
+      fetch_tile<DQK, QR>(rq, Qp, p.ldq, qt0, q_hi, tid);
+      fetch_tile<DV, QR>(rg, dOp, p.ldo, qt0, q_hi, tid);
 #pragma unroll
       for (int k = 0; k < SR; k++) {
         const int i = tid + k * FT;
-        const bool in = i < QR && qt0 + i < p.Nq;
+        const bool in = i < QR && qt0 + i < q_hi;
         rl[k] = in ? lsep[qt0 + i] : INFINITY;
         rd[k] = in ? dlp[qt0 + i] : 0.f;
       }
     };
     constexpr bool PREF = DQK >= 32;                      // small head dims: plain load (registers buy occupancy there)
-    if constexpr (PREF) fetch(0);
-    for (int qt0 = 0; qt0 < p.Nq; qt0 += QR) {
+    if constexpr (PREF) fetch(q_lo);
+    for (int qt0 = q_lo; qt0 < q_hi; qt0 += QR) {
       __syncthreads();
       if constexpr (!PREF) fetch(qt0);
       store_tile<DQK, QR>(sQb, rq, tid);
@@ -475,10 +482,10 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
       }
       __syncthreads();
       if constexpr (PREF) {
-        if (qt0 + QR < p.Nq) fetch(qt0 + QR);
+        if (qt0 + QR < q_hi) fetch(qt0 + QR);
       }
      for (int sb = 0; sb < KT; sb++) {
-      if (qt0 + sb * BQ >= p.Nq) break;
+      if (qt0 + sb * BQ >= q_hi) break;
       const bf16* sQ = sQb + sb * BQ * (DQK + 8);
       const bf16* sG = sGb + sb * BQ * (DV + 8);
       const float* sL = sLb + sb * BQ;
@@ -521,6 +528,17 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
      }
     }
     if constexpr (DO_DK) {
+      if (split) {
+        float* pk = p.partK + ((((long long)blockIdx.x * gridDim.z + b) * p.maps + m) * BKEY) * DQK;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int r = kr0 + g + h * 8;
+#pragma unroll
+          for (int j = 0; j < DQK / 8; j++)
+            *reinterpret_cast<float2*>(pk + (long long)r * DQK + j * 8 + 2 * t) = make_float2(dk[j][2 * h], dk[j][2 * h + 1]);
+        }
+        continue;
+      }
       bf16* dKp = p.dK + (long long)b * p.Nk * p.ldk + m * DQK;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
@@ -534,6 +552,17 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
     }
   }
   if constexpr (DO_DV) {
+    if (split) {
+      float* pv = p.partV + ((((long long)blockIdx.x * gridDim.z + b) * gridDim.y + vh) * BKEY) * DV;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int r = kr0 + g + h * 8;
+#pragma unroll
+        for (int j = 0; j < DV / 8; j++)
+          *reinterpret_cast<float2*>(pv + (long long)r * DV + j * 8 + 2 * t) = make_float2(dv[j][2 * h], dv[j][2 * h + 1]);
+      }
+      return;
+    }
     bf16* dVp = p.dV + (long long)b * p.Nk * p.ldv + vh * DV;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -544,6 +573,27 @@ __global__ void __launch_bounds__(FT) flash_bwd_dkv_kernel(const FlashArgs p) {
         *reinterpret_cast<uint32_t*>(dVp + (long long)r * p.ldv + j * 8 + 2 * t) = pack_bf16(dv[j][2 * h], dv[j][2 * h + 1]);
     }
   }
+}
+
+// out[b, r, h*D + c] = mult * sum_split part[split][b][h][r][c]   (r < Nk; fixed summation order); two columns per thread
+__global__ void __launch_bounds__(256) flash_kv_reduce_kernel(const float* __restrict__ part, int nsplit, int B, int H, int D, int Nk,
+                                                              bf16* __restrict__ out, long long ld, float mult) {
+  const long long total = (long long)B * H * Nk * (D / 2);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % (D / 2)) * 2;
+  long long t = i / (D / 2);
+  const int r = (int)(t % Nk); t /= Nk;
+  const int h = (int)(t % H);
+  const int b = (int)(t / H);
+  const long long stride = (long long)B * H * BKEY * D;
+  const float* src = part + (((long long)b * H + h) * BKEY + r) * D + c;
+  float2 a = make_float2(0.f, 0.f);
+  for (int z = 0; z < nsplit; z++) {
+    const float2 v = *reinterpret_cast<const float2*>(src + z * stride);
+    a.x += v.x; a.y += v.y;
+  }
+  *reinterpret_cast<uint32_t*>(out + ((long long)b * Nk + r) * ld + h * D + c) = pack_bf16(a.x * mult, a.y * mult);
 }
 
 // ------------------------------------------------------------------------------------------------ materialised path
@@ -767,7 +817,8 @@ extern "C" int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long
 
 extern "C" int cenet_flash_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,
                                const void* dO, long long ldo, const float* lse, float* delta, void* dQ, void* dK, void* dV, int B,
-                               int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t st) {
+                               int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, float* ws, long long ws_elems,
+                               cenet_stream_t st) {
   FlashArgs a = make_args(Q, ldq, K, ldk, V, ldv, const_cast<void*>(O), ldo, maps, Nq, Nk, vdiv, scale);
   a.dO = (const bf16*)dO; a.lse = const_cast<float*>(lse); a.delta = delta;
   a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
@@ -787,8 +838,31 @@ extern "C" int cenet_flash_bwd(const void* Q, long long ldq, const void* K, long
     FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 2><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
     CENET_LAUNCH_CHECK("flash_bwd_dk");
   } else {
-    FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 0><<<dim3(cdiv(Nk, BKEY), maps / vdiv, B), FT, 0, s>>>(a)));
-    CENET_LAUNCH_CHECK("flash_bwd_dkv");
+    // few keys, many queries (SR attention: 49 keys, up to 3136 queries): split the queries over CTAs, reduce fp32 partials
+    const int hv = maps / vdiv;
+    int qsplit = 1;
+    if (ws && Nk <= BKEY && Nq >= 4 * BQ) {
+      const int qr = (dqk <= 16 ? 4 : (dqk <= 32 ? 2 : 1)) * BQ;      // queries staged per round (KTiles)
+      qsplit = std::min(cdiv(Nq, 2 * qr), std::max(1, cdiv(2 * kNumSMs, B * hv)));
+      a.qchunk = cdiv(cdiv(Nq, qsplit), qr) * qr;
+      qsplit = cdiv(Nq, a.qchunk);
+      const long long need = (long long)qsplit * B * BKEY * ((long long)maps * dqk + (long long)hv * dv);
+      if (qsplit < 2 || need > ws_elems) qsplit = 1;
+    }
+    a.qsplit = qsplit;
+    if (qsplit > 1) {
+      a.partK = ws;
+      a.partV = ws + (long long)qsplit * B * maps * BKEY * dqk;
+      FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 0><<<dim3(qsplit, hv, B), FT, 0, s>>>(a)));
+      CENET_LAUNCH_CHECK("flash_bwd_dkv(split)");
+      flash_kv_reduce_kernel<<<cdiv((long long)B * maps * Nk * (dqk / 2), 256), 256, 0, s>>>(a.partK, qsplit, B, maps, dqk, Nk, a.dK, ldk,
+                                                                                         scale);
+      flash_kv_reduce_kernel<<<cdiv((long long)B * hv * Nk * (dv / 2), 256), 256, 0, s>>>(a.partV, qsplit, B, hv, dv, Nk, a.dV, ldv, 1.f);
+      CENET_LAUNCH_CHECK("flash_kv_reduce");
+    } else {
+      FLASH_DISPATCH(dqk, dv, (flash_bwd_dkv_kernel<DQK, DV, 0><<<dim3(cdiv(Nk, BKEY), hv, B), FT, 0, s>>>(a)));
+      CENET_LAUNCH_CHECK("flash_bwd_dkv");
+    }
   }
   return 0;
 }

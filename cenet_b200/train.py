@@ -711,7 +711,7 @@ class TrainEngine:
                 dO = self.G(O)
                 delta = self.buf(key + ".delta", (B * maps * Nq,), torch.float32)
                 tops.flash_bwd(Q, Km, V, O, dO, lse, delta, self.G(Q), self.G(Km), self.G(V), B, maps, Nq, Nk, dqk, dv, vdiv,
-                               scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo)
+                               scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo, ws=self._ws(0))
                 for t in (Q, Km, V):
                     self.wr(t)
             self.tape.append(bwd)

@@ -174,11 +174,12 @@ def flash_fwd(Q, K, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, l
 
 
 def flash_bwd(Q, K, V, O, dO, lse, delta, dQ, dK, dV, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo,
-              oo):
+              oo, ws=None):
     _bf16(Q, K, V, O, dO, dQ, dK, dV)
+    wp, wn = _ws(ws) if ws is not None else (None, 0)
     L.call("cenet_flash_bwd", _po(Q, qo), ldq, _po(K, ko), ldk, _po(V, vo), ldv, _po(O, oo), _po(dO, oo), ldo,
            _f32(lse, "lse"), _f32(delta, "delta"), _po(dQ, qo), _po(dK, ko), _po(dV, vo), B, maps, Nq, Nk, dqk, dv, vdiv,
-           scale, _stream())
+           scale, wp, wn, _stream())
 
 
 def softmax_bwd_rows_(P, dP, rows, n):

@@ -323,10 +323,12 @@ int cenet_col2im(const void* dcol, int c_dtype, void* dx, int x_dtype, int B, in
  * (dqk, dv) in {(8,16),(16,32),(32,64),(64,64),(128,128),(80,160)}.  Serves pvtv2.py:88-105, nlb.py:116-137, multihead_diffattn.py:92-116. */
 int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O, long long ldo,
                     float* lse, int B, int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
-/* its backward: delta = rowsum(dO*O) (workspace [B,maps,Nq]); dQ, dK, dV written with the layouts of Q, K, V (no atomics) */
+/* its backward: delta = rowsum(dO*O) (workspace [B,maps,Nq]); dQ, dK, dV written with the layouts of Q, K, V (no atomics).
+ * ws (nullable): fp32 scratch; with <= 64 keys (the encoder's SR attention: 49) the dK / dV kernel splits the QUERIES over CTAs and
+ * a fixed-order reduction adds the partials -- 2*148 CTAs instead of B*heads. */
 int cenet_flash_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, const void* O,
                     const void* dO, long long ldo, const float* lse, float* delta, void* dQ, void* dK, void* dV, int B, int maps,
-                    int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
+                    int Nq, int Nk, int dqk, int dv, int vdiv, float scale, float* ws, long long ws_elems, cenet_stream_t s);
 /* materialised attention backward: dP <- P * (dP - rowsum(P*dP)) in place, rows of length n */
 int cenet_softmax_bwd_rows(const void* P, void* dP, int dtype, long long rows, int n, cenet_stream_t s);
 /* lambda = exp(q1.k1) - exp(q2.k2) + lambda_init on the device (multihead_diffattn.py:110-112) and its backward */

@@ -211,7 +211,8 @@ def flash_fwd(Q, K, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, l
     _as(_flat(O), (B, maps, Nq, dv), (Nq * ldo, dv, ldo, 1), oo).copy_(torch.softmax(s, -1) @ v)
 
 
-def flash_bwd(Q, K, V, O, dO, lse, delta, dQ, dK, dV, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo):
+def flash_bwd(Q, K, V, O, dO, lse, delta, dQ, dK, dV, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo,
+              ws=None):
     _LAUNCHES[0] += 3
     q = _heads(Q, B, Nq, ldq, qo, maps, dqk).float().requires_grad_(True)
     k = _heads(K, B, Nk, ldk, ko, maps, dqk).float().requires_grad_(True)

@@ -314,6 +314,30 @@ def test_flash_fwd_bwd(dqk, dv, vdiv, maps, Nq, Nk):
         assert rel(ga[i], ca[i]) < 2e-2, (n, rel(ga[i], ca[i]))
 
 
+@pytest.mark.parametrize("maps,Nq,Nk,B", [(1, 3136, 49, 3), (2, 784, 49, 2), (5, 300, 49, 2), (1, 1000, 64, 2)])
+def test_flash_bwd_query_split(maps, Nq, Nk, B):
+    """short key sets (SR attention, 49 reduced keys): with a workspace the dK / dV kernel splits the QUERIES over CTAs and a
+    fixed-order reduction adds the fp32 partials; same results as the unsplit kernel (bf16 rounding), bit-identical run to run"""
+    from cenet_b200 import train_ops as tops
+    d = 64
+    ld = maps * d
+    Q, K, V = rn((B * Nq, ld), BF16, 1).to(DEV), rn((B * Nk, 2 * ld), BF16, 2).to(DEV), None
+    O, lse = torch.zeros(B * Nq, ld, dtype=BF16, device=DEV), torch.zeros(B * maps * Nq, device=DEV)
+    scale = d ** -0.5
+    tail = [B, maps, Nq, Nk, d, d, 1, scale, ld, 0, 2 * ld, 0, 2 * ld, ld, ld, 0]        # K | V interleaved like the kv GEMM output
+    tops.flash_fwd(Q, K, K, O, lse, *tail)
+    dO = rn((B * Nq, ld), BF16, 4).to(DEV)
+    delta = torch.zeros(B * maps * Nq, device=DEV)
+    outs = []
+    for wsb in (None, torch.zeros(1 << 22, device=DEV), torch.zeros(1 << 22, device=DEV)):
+        dQ, dKV = torch.zeros_like(Q), torch.zeros_like(K)
+        tops.flash_bwd(Q, K, K, O, dO, lse, delta, dQ, dKV, dKV, *tail, ws=wsb)
+        torch.cuda.synchronize()
+        outs.append((dQ.clone(), dKV.clone()))
+    assert rel(outs[1][1], outs[0][1]) < 1e-2 and torch.equal(outs[1][0], outs[0][0])
+    assert torch.equal(outs[1][1], outs[2][1])
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 def test_softmax_bwd_and_diff_rmsnorm(dtype):
     rows, n = 500, 196
