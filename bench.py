@@ -48,8 +48,8 @@ UNIT = "slices/s"
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures of this workload (profiles/, per round)
-NCU_TRAFFIC = {"source": "profiles/r1_ncu_top_kernels.md, profiles/r1_gemm_traffic.md", "diffattn_flash_kernel": 193.4e6,
-               "gemm_tc_kernel": 39.67e6}     # mean over the 154 launches of one forward
+NCU_TRAFFIC = {"source": "profiles/r2_ncu_top_kernels.md, profiles/r2_gemm_traffic.md", "diffattn_flash_kernel": 191.4e6,
+               "gemm_tc_kernel": 43.9e6}      # mean over the 146 launches of one forward
 
 
 def workload_config(world=1):
@@ -605,7 +605,7 @@ def run_product(args):
         if ms_da:
             fl = diffattn_flops(N1, E1, BATCH)
             ach = fl / (ms_da / 1e3) / 1e12
-            roof_attn = {"bound": "tensor", "kernel": "diffattn_flash_kernel<8,16> (DSEB 56x56, 16 softmax maps, head_dim 8)",
+            roof_attn = {"bound": "tensor", "kernel": "diffattn_tc_kernel<8,1> (tcgen05; DSEB 56x56, 16 softmax maps, head_dim 8)",
                          "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
                          "traffic": NCU_TRAFFIC.get("diffattn_flash_kernel"), "ms_per_launch": ms_da,
                          "share_of_step": ms_da / total_ms, "peak_source": peaks["source"] + ", sustained bf16",
