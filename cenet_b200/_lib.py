@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libcenet_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID, ACT_GELU_GRAD = range(7)
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_MMA = -1, 0, 1, 2
 
 vp, ll, i32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 

@@ -29,7 +29,12 @@ extern "C" int cenet_gemm(const cenet_gemm_args* a, cenet_stream_t s) {
     CENET_REQUIRE(a->batch == 1, "cenet_gemm(conv): batch must be 1");
   }
   int impl = a->impl;
-  if (impl == CENET_GEMM_AUTO) impl = cenet_gemm_tc_eligible(a) ? CENET_GEMM_TCGEN05 : CENET_GEMM_SIMT;
+  if (impl == CENET_GEMM_AUTO)
+    impl = cenet_gemm_tc_eligible(a) ? CENET_GEMM_TCGEN05 : (cenet_gemm_mma_eligible(a) ? CENET_GEMM_MMA : CENET_GEMM_SIMT);
+  if (impl == CENET_GEMM_MMA) {
+    CENET_REQUIRE(cenet_gemm_mma_eligible(a), "cenet_gemm: the mma.sync path needs bf16 A and W, no conv, no k_scale");
+    return cenet_gemm_mma(a, to_stream(s));
+  }
   if (impl == CENET_GEMM_TCGEN05) {
     CENET_REQUIRE(cenet_gemm_tc_eligible(a), "cenet_gemm: tcgen05 path needs bf16 K-major operands, K%%8==0, "
                   "16-byte aligned rows (M=%d N=%d K=%d conv=%d)", a->M, a->N, a->K, a->conv);

@@ -290,6 +290,8 @@ static inline EpiParams make_epi(const cenet_gemm_args* a) {
 int cenet_gemm_simt(const cenet_gemm_args* a, cudaStream_t s);
 int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s);
 bool cenet_gemm_tc_eligible(const cenet_gemm_args* a);
+int cenet_gemm_mma(const cenet_gemm_args* a, cudaStream_t s);
+bool cenet_gemm_mma_eligible(const cenet_gemm_args* a);
 
 // ---- cp.async (LDGSTS): 16-byte global -> shared copies that cost no registers while in flight; src_bytes = 0 zero-fills
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {

@@ -21,7 +21,7 @@ import os
 import torch
 
 from . import ops
-from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SILU, GEMM_AUTO, GEMM_SIMT
+from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SILU, GEMM_AUTO, GEMM_MMA, GEMM_SIMT
 
 _MCA_RATES = {64: (2, 3, 5), 128: (1, 2, 4), 320: (1, 2, 3), 512: (1, 2, 2)}
 
@@ -115,6 +115,8 @@ class Engine:
         self.precision = precision
         self.T = torch.bfloat16 if precision == "bf16" else torch.float32
         self.gemm_impl = GEMM_AUTO if precision == "bf16" else GEMM_SIMT
+        # materialised attention (batched / transposed operands): mma.sync tensor-core GEMM in bf16, CUDA cores in fp32 validation
+        self.attn_gemm_impl = GEMM_MMA if precision == "bf16" else GEMM_SIMT
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
@@ -483,13 +485,13 @@ class Engine:
             S = self.buf(key + ".S", (B * 2 * heads, N, N))
             ops.gemm(qkv, qkv, S, M=N, N=N, K=hd, lda=3 * E, ldw=3 * E, ldc=N, alpha=hd ** -0.5, batch=B * 2 * heads,
                      batch_inner=2 * heads, a_bs=(N * 3 * E, hd), w_bs=(N * 3 * E, hd), c_bs=(2 * heads * N * N, N * N),
-                     w_off=E, impl=GEMM_SIMT)
+                     w_off=E, impl=self.attn_gemm_impl)
             ops.softmax_rows_(S, B * 2 * heads * N, N, N)
             ops.diff_combine_(S, B * heads, N * N, lam)
             oraw = self.buf(key + ".oraw", (B * N, E))
             ops.gemm(S, qkv, oraw, M=N, N=2 * hd, K=N, lda=N, ldw=3 * E, ldc=E, batch=B * heads, batch_inner=heads,
                      a_bs=(2 * heads * N * N, 2 * N * N), w_bs=(N * 3 * E, 2 * hd), c_bs=(N * E, 2 * hd), w_off=2 * E,
-                     w_nmajor=True, impl=GEMM_SIMT)
+                     w_nmajor=True, impl=self.attn_gemm_impl)
             ops.rmsnorm_seg(oraw, o, 2 * hd, 1e-5, 1.0 - li)
         gate = self.buf(key + ".gate", (B * N, E))
         ops.linear(o, w[p + ".out.w"], gate, impl=self.gemm_impl)
@@ -505,10 +507,10 @@ class Engine:
         else:
             S = self.buf(key + ".S", (B, N, N))
             ops.gemm(tpg, tpg, S, M=N, N=N, K=Cc, lda=3 * Cc, ldw=3 * Cc, ldc=N, alpha=Cc ** -0.5, batch=B,
-                     a_bs=(N * 3 * Cc, 0), w_bs=(N * 3 * Cc, 0), c_bs=(N * N, 0), w_off=Cc, impl=GEMM_SIMT)
+                     a_bs=(N * 3 * Cc, 0), w_bs=(N * 3 * Cc, 0), c_bs=(N * N, 0), w_off=Cc, impl=self.attn_gemm_impl)
             ops.softmax_rows_(S, B * N, N, N)
             ops.gemm(S, tpg, att, M=N, N=Cc, K=N, lda=N, ldw=3 * Cc, ldc=Cc, batch=B, a_bs=(N * N, 0),
-                     w_bs=(N * 3 * Cc, 0), c_bs=(N * Cc, 0), w_off=2 * Cc, w_nmajor=True, impl=GEMM_SIMT)
+                     w_bs=(N * 3 * Cc, 0), c_bs=(N * Cc, 0), w_off=2 * Cc, w_nmajor=True, impl=self.attn_gemm_impl)
         return att
 
     # ---- decoder blocks -----------------------------------------------------------------------------------------

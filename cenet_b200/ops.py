@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib as L
-from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, F32, GEMM_AUTO, GEMM_SIMT,
+from ._lib import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, BF16, F32, GEMM_AUTO, GEMM_MMA, GEMM_SIMT,
                    GEMM_TCGEN05, GemmArgs)
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}

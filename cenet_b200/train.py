@@ -33,7 +33,7 @@ import torch
 from . import ops as _ops_mod
 from . import train_ops as _tops_mod
 from .engine import _MCA_RATES, _rup, lambda_init
-from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_SIMT
+from .ops import ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, GEMM_AUTO, GEMM_MMA, GEMM_SIMT
 from .train_ops import ACT_GELU_GRAD
 
 
@@ -149,6 +149,8 @@ class TrainEngine:
         self.precision = precision
         self.T = torch.bfloat16 if precision == "bf16" else torch.float32
         self.gemm_impl = GEMM_AUTO if precision == "bf16" else GEMM_SIMT
+        # materialised attention (batched / transposed operands): mma.sync tensor-core GEMM in bf16, CUDA cores in fp32 validation
+        self.attn_gemm_impl = GEMM_MMA if precision == "bf16" else GEMM_SIMT
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
@@ -719,12 +721,12 @@ class TrainEngine:
         hv = maps // vdiv
         S = self.buf(key + ".S", (B * maps, Nq, Nk))
         ops.gemm(Q, Km, S, M=Nq, N=Nk, K=dqk, lda=ldq, ldw=ldk, ldc=Nk, alpha=scale, batch=B * maps, batch_inner=maps,
-                 a_bs=(Nq * ldq, dqk), w_bs=(Nk * ldk, dqk), c_bs=(maps * Nq * Nk, Nq * Nk), a_off=qo, w_off=ko, impl=GEMM_SIMT)
+                 a_bs=(Nq * ldq, dqk), w_bs=(Nk * ldk, dqk), c_bs=(maps * Nq * Nk, Nq * Nk), a_off=qo, w_off=ko, impl=self.attn_gemm_impl)
         ops.softmax_rows_(S, B * maps * Nq, Nk, Nk)
         for j in range(vdiv):
             ops.gemm(S, V, O, M=Nq, N=dv, K=Nk, lda=Nk, ldw=ldv, ldc=ldo, batch=B * hv, batch_inner=hv,
                      a_bs=(maps * Nq * Nk, vdiv * Nq * Nk), a_off=j * Nq * Nk, w_bs=(Nk * ldv, dv), w_off=vo, w_nmajor=True,
-                     c_bs=(Nq * ldo, vdiv * dv), c_off=oo + j * dv, impl=GEMM_SIMT)
+                     c_bs=(Nq * ldo, vdiv * dv), c_off=oo + j * dv, impl=self.attn_gemm_impl)
 
         def bwd():
             dO = self.G(O)
@@ -733,19 +735,19 @@ class TrainEngine:
             for j in range(vdiv):
                 ops.gemm(dO, V, dP, M=Nq, N=Nk, K=dv, lda=ldo, ldw=ldv, ldc=Nk, batch=B * hv, batch_inner=hv,
                          a_bs=(Nq * ldo, vdiv * dv), a_off=oo + j * dv, w_bs=(Nk * ldv, dv), w_off=vo,
-                         c_bs=(maps * Nq * Nk, vdiv * Nq * Nk), c_off=j * Nq * Nk, impl=GEMM_SIMT)
+                         c_bs=(maps * Nq * Nk, vdiv * Nq * Nk), c_off=j * Nq * Nk, impl=self.attn_gemm_impl)
                 # dV_h (+)= P_m^T dO_m
                 ops.gemm(S, dO, dV, M=Nk, N=dv, K=Nq, lda=Nk, a_mmajor=True, ldw=ldo, w_nmajor=True, ldc=ldv, batch=B * hv,
                          batch_inner=hv, a_bs=(maps * Nq * Nk, vdiv * Nq * Nk), a_off=j * Nq * Nk, w_bs=(Nq * ldo, vdiv * dv),
                          w_off=oo + j * dv, c_bs=(Nk * ldv, dv), c_off=vo, res1=dV if j > 0 else None, ldr1=ldv, r1_off=vo,
-                         impl=GEMM_SIMT)
+                         impl=self.attn_gemm_impl)
             tops.softmax_bwd_rows_(S, dP, B * maps * Nq, Nk)
             ops.gemm(dP, Km, dQ, M=Nq, N=dqk, K=Nk, lda=Nk, ldw=ldk, w_nmajor=True, ldc=ldq, alpha=scale, batch=B * maps,
                      batch_inner=maps, a_bs=(maps * Nq * Nk, Nq * Nk), w_bs=(Nk * ldk, dqk), w_off=ko, c_bs=(Nq * ldq, dqk),
-                     c_off=qo, impl=GEMM_SIMT)
+                     c_off=qo, impl=self.attn_gemm_impl)
             ops.gemm(dP, Q, dK, M=Nk, N=dqk, K=Nq, lda=Nk, a_mmajor=True, ldw=ldq, w_nmajor=True, ldc=ldk, alpha=scale,
                      batch=B * maps, batch_inner=maps, a_bs=(maps * Nq * Nk, Nq * Nk), w_bs=(Nq * ldq, dqk), w_off=qo,
-                     c_bs=(Nk * ldk, dqk), c_off=ko, impl=GEMM_SIMT)
+                     c_bs=(Nk * ldk, dqk), c_off=ko, impl=self.attn_gemm_impl)
             for t in (Q, Km, V):
                 self.wr(t)
         self.tape.append(bwd)

@@ -29,7 +29,7 @@ typedef void* cenet_stream_t; /* cudaStream_t */
 enum { CENET_F32 = 0, CENET_BF16 = 1 };
 enum { CENET_ACT_NONE = 0, CENET_ACT_GELU = 1, CENET_ACT_RELU = 2, CENET_ACT_LEAKY = 3, CENET_ACT_SILU = 4,
        CENET_ACT_SIGMOID = 5, CENET_ACT_GELU_GRAD = 6 /* d gelu(v)/dv: `mul_act` of training dgrad GEMMs */ };
-enum { CENET_GEMM_AUTO = -1, CENET_GEMM_SIMT = 0, CENET_GEMM_TCGEN05 = 1 };
+enum { CENET_GEMM_AUTO = -1, CENET_GEMM_SIMT = 0, CENET_GEMM_TCGEN05 = 1, CENET_GEMM_MMA = 2 };
 
 /* ---- library ---------------------------------------------------------------------------------------- */
 const char* cenet_last_error(void);
@@ -49,7 +49,9 @@ long long cenet_launch_count(void);
  * conv != 0: A is an NHWC image [Bimg,H,W,Cin]; M = Bimg*Ho*Wo; K = KH*KW*Cin ordered (kh,kw,cin);
  *            W is [N, KH*KW*Cin] (the reference's [Cout,Cin,KH,KW] weight permuted once at pack time).
  * batch > 1: z = zo*batch_inner + zi; pointer offsets are zo*bs_outer + zi*bs_inner elements.
- * impl: CENET_GEMM_TCGEN05 needs bf16 A and W, K-major W, K % 8 == 0, 16-byte aligned rows.
+ * impl: CENET_GEMM_TCGEN05 needs bf16 A and W, K-major W, K % 8 == 0, 16-byte aligned rows, batch == 1.
+ *       CENET_GEMM_MMA (mma.sync, bf16 A and W): batched problems and the transposed operand layouts (a_mmajor / w_nmajor) --
+ *       the materialised attention of the training path.  CENET_GEMM_AUTO: tcgen05 if eligible, else mma.sync if bf16, else CUDA cores.
  */
 typedef struct {
   int M, N, K;

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID, ACT_GELU_GRAD = range(7)
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = -1, 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_MMA = -1, 0, 1, 2
 F32, BF16 = 0, 1
 _LAUNCHES = [0]
 

@@ -154,6 +154,41 @@ def test_gemm_batched_nmajor():
     assert rel(o, S @ v) < 1e-5
 
 
+@pytest.mark.parametrize("Bt,N,d,dv", [(6, 196, 320, 320), (4, 49, 512, 512), (3, 50, 20, 44), (2, 130, 40, 80)])
+def test_gemm_mma_batched_all_layouts(Bt, N, d, dv):
+    """the mma.sync tensor-core GEMM behind the materialised attention of the training path: batched problems and the four
+    transpose combinations (S = Q K^T, O = P V, dV = P^T dO, dQ = dS K), aligned and unaligned pitches, against torch fp32"""
+    from cenet_b200 import ops
+    bf = torch.bfloat16
+    q = torch.randn(Bt, N, d, generator=g(1)).to(DEV, bf)
+    k = torch.randn(Bt, N, d, generator=g(2)).to(DEV, bf)
+    v = torch.randn(Bt, N, dv, generator=g(3)).to(DEV, bf)
+    qf, kf, vf = q.float(), k.float(), v.float()
+    S = torch.empty(Bt, N, N, device=DEV, dtype=bf)
+    ops.gemm(q, k, S, M=N, N=N, K=d, lda=d, ldw=d, ldc=N, alpha=0.3, batch=Bt, a_bs=(N * d, 0), w_bs=(N * d, 0), c_bs=(N * N, 0),
+             impl=ops.GEMM_MMA)                                                     # A [M,K] x W [N,K]^T
+    assert rel(S, 0.3 * qf @ kf.transpose(1, 2)) < 6e-3
+    Sf = S.float()
+    o = torch.empty(Bt, N, dv, device=DEV, dtype=bf)
+    ops.gemm(S, v, o, M=N, N=dv, K=N, lda=N, ldw=dv, ldc=dv, batch=Bt, a_bs=(N * N, 0), w_bs=(N * dv, 0), c_bs=(N * dv, 0),
+             w_nmajor=True, impl=ops.GEMM_MMA)                                      # A [M,K] x W [K,N]
+    assert rel(o, Sf @ vf) < 6e-3
+    do = torch.randn(Bt, N, dv, generator=g(4)).to(DEV, bf)
+    dvv = torch.empty(Bt, N, dv, device=DEV, dtype=torch.float32)
+    ops.gemm(S, do, dvv, M=N, N=dv, K=N, lda=N, a_mmajor=True, ldw=dv, w_nmajor=True, ldc=dv, batch=Bt, a_bs=(N * N, 0),
+             w_bs=(N * dv, 0), c_bs=(N * dv, 0), impl=ops.GEMM_MMA)                  # A [K,M]^T x W [K,N], fp32 out
+    assert rel(dvv, Sf.transpose(1, 2) @ do.float()) < 6e-3
+    dk = torch.empty(Bt, N, d, device=DEV, dtype=bf)
+    res = torch.randn(Bt, N, d, generator=g(5)).to(DEV, bf)
+    ops.gemm(S, q, dk, M=N, N=d, K=N, lda=N, a_mmajor=True, ldw=d, w_nmajor=True, ldc=d, batch=Bt, a_bs=(N * N, 0), w_bs=(N * d, 0),
+             c_bs=(N * d, 0), res1=res, ldr1=d, impl=ops.GEMM_MMA)                   # + accumulate into a gradient buffer
+    assert rel(dk, Sf.transpose(1, 2) @ qf + res.float()) < 6e-3
+    # AUTO picks it for what the tcgen05 kernel cannot take
+    S2 = torch.empty_like(S)
+    ops.gemm(q, k, S2, M=N, N=N, K=d, lda=d, ldw=d, ldc=N, alpha=0.3, batch=Bt, a_bs=(N * d, 0), w_bs=(N * d, 0), c_bs=(N * N, 0))
+    assert torch.equal(S, S2)
+
+
 # ------------------------------------------------------------------------------------------------------------ rows
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layernorm_softmax_stats_rms(dtype):
