@@ -92,10 +92,10 @@ _SIGS = {
     "cenet_smallk_dgrad": [vp, i32, vp, ll, vp, i32, ll, ll, i32, i32, vp],
     "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
     "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
-    "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, ll, vp],
+    "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, ll, vp],
     "cenet_affine_act": [vp, i32, ll, vp, vp, vp, i32, ll, vp, vp, vp, i32, ll, ll, i32, i32, f32, vp],
     "cenet_bn_bwd": [vp, i32, vp, i32, ll, vp, i32, ll, vp, vp, vp, ll, i32, i32, f32, vp, i32, i32, vp, vp, vp, i32, ll,
-                     i32, vp, ll, vp],
+                     i32, i32, vp, ll, vp],
     "cenet_dwconv3x3_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, vp, ll, vp],
     "cenet_sumpool2": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_col2im": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -110,14 +110,14 @@ _SIGS = {
     "cenet_nchw_to_nhwc_slice": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_add": [vp, vp, i32, ll, i32, vp],
     "cenet_ccu_stats": [vp, i32, vp, vp, i32, i32, i32, vp, ll, vp],
-    "cenet_ccu_mlp_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, i32, i32, vp],
-    "cenet_ccu_mlp_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp],
+    "cenet_ccu_mlp_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, i32, i32, i32, vp],
+    "cenet_ccu_mlp_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
     "cenet_ccu_dgate": [vp, vp, i32, vp, i32, i32, i32, vp, ll, vp],
     "cenet_ccu_apply_bwd": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
     "cenet_row_stats_arg": [vp, i32, vp, vp, ll, i32, vp],
-    "cenet_srm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_srm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp],
     "cenet_row_dot": [vp, vp, i32, vp, ll, i32, vp],
-    "cenet_srm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, ll, vp],
+    "cenet_srm_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, ll, vp],
     "cenet_srm_apply_bwd": [vp, vp, vp, i32, vp, vp, vp, vp, vp, ll, i32, vp],
     "cenet_silu_mul_fwd": [vp, vp, vp, i32, ll, vp],
     "cenet_silu_mul_bwd": [vp, vp, vp, vp, vp, i32, ll, vp],

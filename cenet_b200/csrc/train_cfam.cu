@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(kColThreads) ccu_dgate_kernel(const T* __restr
 // thread = channel; save[b,c,:] = z1[0..2], z2, xhat, rstd
 __global__ void ccu_mlp_fwd_kernel(const float* __restrict__ u, const float* __restrict__ fc1, const float* __restrict__ fc2,
                                    const float* gamma, const float* beta, float* rmean, float* rvar, long long* nbt, float momentum,
-                                   float eps, float* __restrict__ gate, float* __restrict__ save, int B, int C) {
+                                   float eps, float* __restrict__ gate, float* __restrict__ save, int B, int C, int frozen) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && gamma && nbt) *nbt += 1;
+  if (c == 0 && gamma && nbt && !frozen) *nbt += 1;
   if (c >= C) return;
   float w1[9], w2[3];
 #pragma unroll
@@ -119,7 +119,10 @@ __global__ void ccu_mlp_fwd_kernel(const float* __restrict__ u, const float* __r
     s1 += z2; s2 = fmaf(z2, z2, s2);
   }
   float mu = 0.f, rs = 1.f, g = 1.f, bt = 0.f;
-  if (gamma) {
+  if (gamma && frozen) {                      // eval-mode BatchNorm1d: running statistics, no update
+    mu = rmean[c]; rs = rsqrtf(rvar[c] + eps);
+    g = gamma[c]; bt = beta[c];
+  } else if (gamma) {
     mu = s1 / B;
     float var = 0.f;
     for (int b = 0; b < B; b++) { const float d = save[((long long)b * C + c) * 8 + 3] - mu; var = fmaf(d, d, var); }
@@ -139,7 +142,8 @@ __global__ void ccu_mlp_fwd_kernel(const float* __restrict__ u, const float* __r
 
 __global__ void ccu_mlp_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ u, const float* __restrict__ fc1,
                                    const float* __restrict__ fc2, const float* gamma, const float* beta, const float* __restrict__ save,
-                                   float* __restrict__ du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C) {
+                                   float* __restrict__ du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C,
+                                   int frozen) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float w1[9], w2[3], g1[9], g2[3];
@@ -162,7 +166,7 @@ __global__ void ccu_mlp_bwd_kernel(const float* __restrict__ dgate, const float*
     const float* up = u + ((long long)b * C + c) * 3;
     const float gt = sigmoidf_(gamma ? fmaf(g, sp[4], bt) : sp[4]);
     const float dzn = dgate[(long long)b * C + c] * gt * (1.f - gt);
-    const float dz2 = gamma ? g * sp[5] * (dzn - sb / B - sp[4] * sg / B) : dzn;
+    const float dz2 = gamma ? (frozen ? g * sp[5] * dzn : g * sp[5] * (dzn - sb / B - sp[4] * sg / B)) : dzn;
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -320,8 +324,13 @@ __global__ void __launch_bounds__(256) srm_fwd_a_kernel(const float* __restrict_
 }
 
 __global__ void srm_fwd_b_kernel(const float* __restrict__ ws, int nblk, long long M, float* rmean, float* rvar, long long* nbt,
-                                 float momentum, float eps, float* st) {
+                                 float momentum, float eps, float* st, int frozen) {
   if (threadIdx.x != 0) return;
+  if (frozen) {                               // eval-mode BatchNorm2d(1): running statistics, no update
+    st[0] = rmean[0];
+    st[1] = rsqrtf(rvar[0] + eps);
+    return;
+  }
   double a = 0.0, b = 0.0;
   for (int i = 0; i < nblk; i++) { a += ws[i * 2]; b += ws[i * 2 + 1]; }
   const double mu = a / (double)M;
@@ -356,11 +365,11 @@ __global__ void __launch_bounds__(256) srm_bwd_a_kernel(const float* __restrict_
   s2 = block_sum_256(s2, red);
   if (threadIdx.x == 0) { ws[blockIdx.x * 2] = s1; ws[blockIdx.x * 2 + 1] = s2; }
 }
-__global__ void srm_bwd_b_kernel(const float* __restrict__ ws, int nblk, float* sums, float* dgamma, float* dbeta) {
+__global__ void srm_bwd_b_kernel(const float* __restrict__ ws, int nblk, float* sums, float* dgamma, float* dbeta, int frozen) {
   if (threadIdx.x != 0) return;
   float a = 0.f, b = 0.f;
   for (int i = 0; i < nblk; i++) { a += ws[i * 2]; b += ws[i * 2 + 1]; }
-  sums[0] = a; sums[1] = b;
+  sums[0] = frozen ? 0.f : a; sums[1] = frozen ? 0.f : b;
   dbeta[0] = a; dgamma[0] = b;
 }
 // stage c: df_pre[m] -> save[m*2+1] (fg is dead from here on)
@@ -637,18 +646,19 @@ extern "C" int cenet_ccu_dgate(const void* dx1, const void* xb, int dtype, float
 }
 extern "C" int cenet_ccu_mlp_fwd(const float* u, const float* fc1, const float* fc2, const float* gamma, const float* beta, float* rmean,
                                  float* rvar, long long* nbt, float momentum, float eps, float* gate, float* save, int B, int C,
-                                 cenet_stream_t st) {
+                                 int frozen, cenet_stream_t st) {
   CENET_REQUIRE(u && fc1 && fc2 && gate && save, "cenet_ccu_mlp_fwd: null pointer");
+  CENET_REQUIRE(!(frozen && gamma) || (rmean && rvar), "cenet_ccu_mlp_fwd(frozen): running statistics required");
   CENET_REQUIRE((gamma == nullptr) == (beta == nullptr), "cenet_ccu_mlp_fwd: gamma and beta come together");
-  ccu_mlp_fwd_kernel<<<cdiv(C, 64), 64, 0, to_stream(st)>>>(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C);
+  ccu_mlp_fwd_kernel<<<cdiv(C, 64), 64, 0, to_stream(st)>>>(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C, frozen);
   CENET_LAUNCH_CHECK("ccu_mlp_fwd");
   return 0;
 }
 extern "C" int cenet_ccu_mlp_bwd(const float* dgate, const float* u, const float* fc1, const float* fc2, const float* gamma,
                                  const float* beta, const float* save, float* du, float* dfc1, float* dfc2, float* dgamma, float* dbeta,
-                                 int B, int C, cenet_stream_t st) {
+                                 int B, int C, int frozen, cenet_stream_t st) {
   CENET_REQUIRE(dgate && u && fc1 && fc2 && save && du && dfc1 && dfc2, "cenet_ccu_mlp_bwd: null pointer");
-  ccu_mlp_bwd_kernel<<<cdiv(C, 64), 64, 0, to_stream(st)>>>(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C);
+  ccu_mlp_bwd_kernel<<<cdiv(C, 64), 64, 0, to_stream(st)>>>(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C, frozen);
   CENET_LAUNCH_CHECK("ccu_mlp_bwd");
   return 0;
 }
@@ -682,7 +692,7 @@ extern "C" int cenet_row_dot(const void* a, const void* b, int dtype, float* out
 
 extern "C" int cenet_srm_fwd(const float* u, const float* pw, const float* dw, const float* gamma, const float* beta, float* rmean,
                              float* rvar, long long* nbt, float momentum, float eps, float* gm, float* save, float* stt, int B, int H,
-                             int W, float* ws, long long ws_elems, cenet_stream_t st) {
+                             int W, int frozen, float* ws, long long ws_elems, cenet_stream_t st) {
   CENET_REQUIRE(u && pw && dw && gamma && beta && gm && save && stt && ws, "cenet_srm_fwd: null pointer");
   cudaStream_t s = to_stream(st);
   const long long M = (long long)B * H * W;
@@ -690,7 +700,7 @@ extern "C" int cenet_srm_fwd(const float* u, const float* pw, const float* dw, c
   CENET_REQUIRE(2LL * nblk <= ws_elems, "cenet_srm_fwd: workspace too small");
   srm_fwd_a_kernel<<<nblk, 256, 0, s>>>(u, pw, dw, save, ws, B, H, W);
   CENET_LAUNCH_CHECK("srm_fwd_a");
-  srm_fwd_b_kernel<<<1, 32, 0, s>>>(ws, nblk, M, rmean, rvar, nbt, momentum, eps, stt);
+  srm_fwd_b_kernel<<<1, 32, 0, s>>>(ws, nblk, M, rmean, rvar, nbt, momentum, eps, stt, frozen);
   CENET_LAUNCH_CHECK("srm_fwd_b");
   srm_fwd_c_kernel<<<cdiv(M, 256), 256, 0, s>>>(save, stt, gamma, beta, gm, M);
   CENET_LAUNCH_CHECK("srm_fwd_c");
@@ -698,7 +708,7 @@ extern "C" int cenet_srm_fwd(const float* u, const float* pw, const float* dw, c
 }
 extern "C" int cenet_srm_bwd(const float* dgm, const float* u, const float* gm, float* save, const float* stt, const float* pw,
                              const float* dw, const float* gamma, const float* beta, float* du, float* dpw, float* ddw, float* dgamma,
-                             float* dbeta, int B, int H, int W, float* ws, long long ws_elems, cenet_stream_t st) {
+                             float* dbeta, int B, int H, int W, int frozen, float* ws, long long ws_elems, cenet_stream_t st) {
   CENET_REQUIRE(dgm && u && gm && save && stt && pw && dw && gamma && du && dpw && ddw && dgamma && dbeta && ws, "cenet_srm_bwd: null pointer");
   cudaStream_t s = to_stream(st);
   const long long M = (long long)B * H * W;
@@ -707,7 +717,7 @@ extern "C" int cenet_srm_bwd(const float* dgm, const float* u, const float* gm, 
   float* sums = ws + 30LL * nblk;
   srm_bwd_a_kernel<<<nblk, 256, 0, s>>>(dgm, gm, save, stt, ws, M);
   CENET_LAUNCH_CHECK("srm_bwd_a");
-  srm_bwd_b_kernel<<<1, 32, 0, s>>>(ws, nblk, sums, dgamma, dbeta);
+  srm_bwd_b_kernel<<<1, 32, 0, s>>>(ws, nblk, sums, dgamma, dbeta, frozen);
   CENET_LAUNCH_CHECK("srm_bwd_b");
   srm_bwd_c_kernel<<<cdiv(M, 256), 256, 0, s>>>(dgm, gm, save, stt, sums, gamma, M);
   CENET_LAUNCH_CHECK("srm_bwd_c");

@@ -84,6 +84,15 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ ws, int nblk,
   }
 }
 
+// eval-mode ("frozen") BatchNorm: the running statistics ARE the statistics; nothing is updated
+__global__ void bn_frozen_stats_kernel(int C, const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps,
+                                       float* scale, float* shift, float* mean, float* rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float r = rsqrtf(rvar[c] + eps), g = gamma ? gamma[c] : 1.f, bb = beta ? beta[c] : 0.f;
+  mean[c] = rmean[c]; rstd[c] = r; scale[c] = g * r; shift[c] = bb - rmean[c] * g * r;
+}
+
 // ------------------------------------------------------------------------------------------------ affine + act
 template <typename T, int V>
 __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ a, long long lda, const float* __restrict__ sa,
@@ -164,15 +173,15 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const T* __
 }
 
 // sums[0..C) = d(beta), sums[C..2C) = d(gamma); also written to the parameter gradients
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* sums, float* dgamma, float* dbeta) {
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ ws, int nblk, int C, float* sums, float* dgamma, float* dbeta, int frozen) {
   __shared__ float sm[2 * kFinThreads];
   const int c = blockIdx.x * kFinOut + threadIdx.x % kFinOut;
   float t[2];
   fin_lane_sums<2>(nblk, c < C, t, sm, [&](int i, int k) { return ws[((size_t)i * 2 + k) * C + c]; });
   if (threadIdx.x >= kFinOut || c >= C) return;
   const float a = t[0], b = t[1];
-  sums[c] = a;
-  sums[C + c] = b;
+  sums[c] = frozen ? 0.f : a;                // frozen statistics: d(input) = gamma * rstd * g, no batch terms
+  sums[C + c] = frozen ? 0.f : b;
   if (dbeta) dbeta[c] = a;
   if (dgamma) dgamma[c] = b;
 }
@@ -353,11 +362,17 @@ int vec_for(const void* p0, const void* p1, const void* p2, const void* p3, std:
 
 extern "C" int cenet_bn_stats(const void* x, int x_dtype, long long ldx, long long rows, int C, const float* gamma,
                               const float* beta, float* rmean, float* rvar, long long* nbt, float momentum, float eps,
-                              float* scale, float* shift, float* mean, float* rstd, float* ws, long long ws_elems,
+                              int frozen, float* scale, float* shift, float* mean, float* rstd, float* ws, long long ws_elems,
                               cenet_stream_t st) {
   CENET_REQUIRE(x && scale && shift && mean && rstd && ws, "cenet_bn_stats: null pointer");
   CENET_REQUIRE(rows > 0 && C > 0, "cenet_bn_stats: bad shape");
   cudaStream_t s = to_stream(st);
+  if (frozen) {                               // eval-mode BatchNorm inside a gradient-enabled pass
+    CENET_REQUIRE(rmean && rvar, "cenet_bn_stats(frozen): running statistics required");
+    bn_frozen_stats_kernel<<<cdiv(C, 128), 128, 0, s>>>(C, gamma, beta, rmean, rvar, eps, scale, shift, mean, rstd);
+    CENET_LAUNCH_CHECK("bn_frozen_stats");
+    return 0;
+  }
   CENET_DISPATCH(x_dtype, T, {
     int Vv = vec_for<T>(x, nullptr, nullptr, nullptr, {C, ldx});
     if (sizeof(T) == 4 && Vv > 4) Vv = 4;
@@ -396,7 +411,8 @@ extern "C" int cenet_affine_act(const void* a, int a_dtype, long long lda, const
 extern "C" int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_dtype, long long ldy, const void* a, int a_dtype,
                             long long lda, const float* mean, const float* rstd, const float* gamma, long long rows, int C,
                             int act, float slope, void* da, int da_dtype, int acc_da, float* dgamma, float* dbeta, void* dres,
-                            int dres_dtype, long long lddres, int acc_dres, float* ws, long long ws_elems, cenet_stream_t st) {
+                            int dres_dtype, long long lddres, int acc_dres, int frozen, float* ws, long long ws_elems,
+                            cenet_stream_t st) {
   CENET_REQUIRE(dy && a && da && mean && rstd && gamma && ws, "cenet_bn_bwd: null pointer");
   CENET_REQUIRE(dy_dtype == a_dtype && da_dtype == a_dtype && (!y || y_dtype == a_dtype) && (!dres || dres_dtype == a_dtype),
                 "cenet_bn_bwd: operands must share one dtype");
@@ -413,7 +429,7 @@ extern "C" int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_d
                         (const T*)dy, (const T*)y, ldy, (const T*)a, lda, mean, rstd, rows, C, act, slope, p.ngrp, p.nrl,
                         p.rows_per_block, ws)));
     CENET_LAUNCH_CHECK("bn_bwd_partial");
-    bn_bwd_finalize_kernel<<<cdiv(C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, sums, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<cdiv(C, kFinOut), kFinThreads, 0, s>>>(ws, p.nrb, C, sums, dgamma, dbeta, frozen);
     CENET_LAUNCH_CHECK("bn_bwd_finalize");
     const long long total = rows * (C / Vv);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 8LL * kNumSMs);

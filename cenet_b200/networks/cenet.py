@@ -309,16 +309,32 @@ class _EvalForward(torch.autograd.Function):
     """eval()-mode forward under grad mode (ACDC `val()` main_acdc.py:226, utils_skin.py:104,143 and the FLOP-counter warm-ups
     utils.py:184-185 run the network that way and never call backward): the logits come from the inference launch plan and carry
     a graph node like the reference's output does (`requires_grad`, `.detach()`, `.item()` behave the same).  A backward pass through
-    the eval-mode network (running-statistics BatchNorm) is not built: it raises instead of returning wrong gradients."""
+    the eval-mode network recomputes the forward with the training launch plan in frozen-statistics mode (see `backward`)."""
 
     @staticmethod
     def forward(ctx, module, x, *params):
+        ctx.module, ctx.x = module, x.detach()
+        ctx.names = [n for n, _ in module.named_parameters()]
+        ctx.needs = [p.requires_grad for p in params]
         return module._engine(x).forward(x)
 
     @staticmethod
     def backward(ctx, dlogits):
-        raise NotImplementedError("cenet_b200: backward through an eval()-mode forward is not built (the reference scripts never "
-                                  "call it); switch to train() for gradients -- DESIGN.md section 7")
+        # Rare path (the reference scripts never call it): recompute the forward with the training launch plan in FROZEN-statistics
+        # mode -- BatchNorm / BatchNorm1d(CCU) / BatchNorm2d(1)(SRM) use their running statistics and update nothing, DropPath is
+        # the identity, i.e. exactly eval() semantics -- then run its recorded backward.  Eager, no CUDA graphs.
+        eng = ctx.module.train_engine(ctx.x.device)
+        saved = (eng.frozen_stats, eng.use_graph)
+        eng.frozen_stats, eng.use_graph = True, False
+        try:
+            eng.forward_logits(ctx.x)
+            eng.backward_from(dlogits.contiguous())
+        finally:
+            eng.frozen_stats, eng.use_graph = saved
+        flat = eng.gflat.clone()
+        grads = tuple(flat[eng.param_offsets[n]:eng.param_offsets[n] + eng.GP[n].numel()].view(eng.GP[n].shape) if need else None
+                      for n, need in zip(ctx.names, ctx.needs))
+        return (None, None) + grads
 
 
 class CENet(nn.Module):

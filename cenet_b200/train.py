@@ -164,6 +164,9 @@ class TrainEngine:
         self._written = set()
         self.tape = TrainEngine._Tape()
         self._graphs = {}
+        # eval()-mode semantics inside a gradient pass (networks.CENet._EvalForward): BatchNorm uses its running statistics and
+        # updates nothing, DropPath is the identity; the plan runs eagerly (no graphs are cached for this rare path)
+        self.frozen_stats = False
         self._wg_pending, self._wg_off, self._wg_flush_idx, self._wg_tables = [], 0, 0, {}   # deferred wgrad reductions
         self.taps = None
         self.launches_per_step = None
@@ -589,7 +592,7 @@ class TrainEngine:
                   rows=rows, C=Cc, name=name)
         tops.bn_stats(x, rows, Cc, self.P[name + ".weight"], self.P[name + ".bias"], self.BUF[name + ".running_mean"],
                       self.BUF[name + ".running_var"], self.BUF[name + ".num_batches_tracked"], self.momentum, 1e-5,
-                      st["scale"], st["shift"], st["mean"], st["rstd"], self._ws(0), ldx=ld, x_off=off)
+                      st["scale"], st["shift"], st["mean"], st["rstd"], self._ws(0), ldx=ld, x_off=off, frozen=self.frozen_stats)
         return st
 
     def bn_bwd(self, st, dy, y, a, *, act=ACT_NONE, slope=0.0, ldy=None, y_off=0, lda=None, a_off=0, dres=None,
@@ -601,7 +604,7 @@ class TrainEngine:
         tops.bn_bwd(dy, y, a, st["mean"], st["rstd"], self.P[name + ".weight"], rows, Cc, da_t, self.GP[name + ".weight"],
                     self.GP[name + ".bias"], self._ws(0), act=act, slope=slope, acc_da=acc, dres=dres, acc_dres=dres_acc,
                     ldy=Cc if ldy is None else ldy, y_off=y_off, lda=Cc if lda is None else lda, a_off=a_off,
-                    lddres=lddres or Cc, dres_off=dres_off)
+                    lddres=lddres or Cc, dres_off=dres_off, frozen=self.frozen_stats)
 
     def bn_act(self, x, rows, Cc, name, out, key, *, act=ACT_NONE, slope=0.0, ldx=None, x_off=0, ldo=None, o_off=0):
         """out = act(BN_train(x)) with its backward."""
@@ -779,7 +782,7 @@ class TrainEngine:
                 b = f"backbone.block{s+1}.{i}"
                 kb = f"enc{s}.b{i}"
                 drop = drop2 = None                                          # two independent draws per block:
-                if self.drop_path and self.mod.backbone.drop_path_probs[dp_i] > 0:   # attention and MLP branch (pvtv2.py:146-147)
+                if self.drop_path and not self.frozen_stats and self.mod.backbone.drop_path_probs[dp_i] > 0:   # (pvtv2.py:146-147)
                     drop, drop2 = self.dp_scale[2 * dp_i], self.dp_scale[2 * dp_i + 1]
                 dp_i += 1
                 xn = self.ln(t, b + ".norm1", self.buf(kb + ".xn1", (Mtok, Cc)), 1e-6)
@@ -831,7 +834,7 @@ class TrainEngine:
         cb = m + ".ccu.bn"
         tops.ccu_mlp_fwd(u, P[m + ".ccu.fc1.weight"], P[m + ".ccu.fc2.weight"], P[cb + ".weight"] if bn1d else None,
                          P[cb + ".bias"] if bn1d else None, self.BUF[cb + ".running_mean"], self.BUF[cb + ".running_var"],
-                         self.BUF[cb + ".num_batches_tracked"], self.momentum, 1e-5, gate, csave, B, Cc)
+                         self.BUF[cb + ".num_batches_tracked"], self.momentum, 1e-5, gate, csave, B, Cc, frozen=self.frozen_stats)
         x1 = self.buf(key + ".x1", (M, Cc))
         ops.affine_gate(xb, x1, None, None, gate, B, HW, Cc)
 
@@ -842,7 +845,7 @@ class TrainEngine:
             du = self.buf(key + ".ccu_du", (B, Cc, 3), torch.float32)
             tops.ccu_mlp_bwd(dgate, u, P[m + ".ccu.fc1.weight"], P[m + ".ccu.fc2.weight"], P[cb + ".weight"] if bn1d else None,
                              P[cb + ".bias"] if bn1d else None, csave, du, GP[m + ".ccu.fc1.weight"], GP[m + ".ccu.fc2.weight"], GP[cb + ".weight"],
-                             GP[cb + ".bias"], B, Cc)
+                             GP[cb + ".bias"], B, Cc, frozen=self.frozen_stats)
             dxb = self.G(xb)
             acc = self.wr(xb)
             tops.ccu_apply_bwd(dx1, xb, gate, u, arg, du, dxb, acc, B, HW, Cc)
@@ -941,7 +944,7 @@ class TrainEngine:
         sb = q + ".srm.bn"
         tops.srm_fwd(su, P[q + ".srm.pwc.weight"], P[q + ".srm.dwc.weight"], P[sb + ".weight"], P[sb + ".bias"],
                      self.BUF[sb + ".running_mean"], self.BUF[sb + ".running_var"], self.BUF[sb + ".num_batches_tracked"],
-                     self.momentum, 1e-5, gm, ssave, sst, B, H, W, self._ws(0))
+                     self.momentum, 1e-5, gm, ssave, sst, B, H, W, self._ws(0), frozen=self.frozen_stats)
         mo = self.buf(key + ".mo", (M, Cc))
         W2, W2T = self.w[q + ".fc2.w"], self.w[q + ".fc2.wT"]
         ops.gemm(h2, W2, mo, M=M, N=Cc, K=4 * Cc, lda=4 * Cc, ldw=W2.stride(0), ldc=Cc, bias=P[q + ".fc2.bias"], row_scale=gm,
@@ -970,7 +973,7 @@ class TrainEngine:
             tops.srm_bwd(dgm, su, gm, ssave, sst, P[q + ".srm.pwc.weight"], P[q + ".srm.dwc.weight"], P[sb + ".weight"],
                          P[sb + ".bias"], dsu,
                          GP[q + ".srm.pwc.weight"], GP[q + ".srm.dwc.weight"], GP[sb + ".weight"], GP[sb + ".bias"], B, H, W,
-                         self._ws(0))
+                         self._ws(0), frozen=self.frozen_stats)
             # d(h2) = dh3 * gm + statistics terms, then * gelu'(z) -> d(z)
             tops.srm_apply_bwd(dh3, h2, z, gm, su, sarg, dsu, self.G(z), M, 4 * Cc)
             self.wr(z)
@@ -1265,7 +1268,7 @@ class TrainEngine:
         probs = self.mod.backbone.drop_path_probs
         n = 2 * len(probs)                                          # rows 2i / 2i+1: attention / MLP branch of block i
         ds = self.buf("dp_scale", (n, B), torch.float32)
-        if self.drop_path:
+        if self.drop_path and not self.frozen_stats:
             keep = self.dp_keep
             rnd = self.buf("dp_rand", (n, B), torch.float32)
             rnd.uniform_()
@@ -1450,7 +1453,8 @@ class TrainEngine:
             self.tape, self._written, self._galias = st["tape"], st["written"], st["galias"]
             st["fwd"].replay()
         self._last_logits = logits
-        self._touch_weights()                                       # BatchNorm running statistics moved
+        if not self.frozen_stats:
+            self._touch_weights()                                   # BatchNorm running statistics moved
         return logits
 
     def backward_from(self, dlogits):

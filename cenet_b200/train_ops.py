@@ -118,13 +118,14 @@ def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ BatchNorm
-def bn_stats(x, rows, C_, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift, mean, rstd, ws, ldx=None, x_off=0):
+def bn_stats(x, rows, C_, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift, mean, rstd, ws, ldx=None, x_off=0,
+             frozen=False):
     wp, wn = _ws(ws)
     if nbt.dtype != torch.int64:
         raise TypeError("num_batches_tracked must be int64")
     L.call("cenet_bn_stats", _po(x, x_off), dt(x), C_ if ldx is None else ldx, rows, C_, _f32(gamma, "gamma"),
            _f32(beta, "beta"), _f32(rmean, "running_mean"), _f32(rvar, "running_var"), _p(nbt), momentum, eps,
-           _f32(scale, "scale"), _f32(shift, "shift"), _f32(mean, "mean"), _f32(rstd, "rstd"), wp, wn, _stream())
+           int(frozen), _f32(scale, "scale"), _f32(shift, "shift"), _f32(mean, "mean"), _f32(rstd, "rstd"), wp, wn, _stream())
 
 
 def affine_act(a, out, rows, C_, sa=None, ta=None, b=None, sb=None, tb=None, act=ACT_NONE, slope=0.0, lda=None, a_off=0,
@@ -135,14 +136,14 @@ def affine_act(a, out, rows, C_, sa=None, ta=None, b=None, sb=None, tb=None, act
 
 
 def bn_bwd(dy, y, a, mean, rstd, gamma, rows, C_, da, dgamma, dbeta, ws, act=ACT_NONE, slope=0.0, acc_da=False, dres=None,
-           acc_dres=False, ldy=None, y_off=0, lda=None, a_off=0, lddres=None, dres_off=0):
+           acc_dres=False, ldy=None, y_off=0, lda=None, a_off=0, lddres=None, dres_off=0, frozen=False):
     wp, wn = _ws(ws)
     ldy = C_ if ldy is None else ldy
     lda = C_ if lda is None else lda
     L.call("cenet_bn_bwd", _po(dy, y_off), dt(dy), _po(y, y_off), dt(y) if y is not None else 0, ldy, _po(a, a_off), dt(a), lda,
            _f32(mean, "mean"), _f32(rstd, "rstd"), _f32(gamma, "gamma"), rows, C_, act, slope, _po(da, a_off), dt(da),
            int(acc_da), _f32(dgamma, "dgamma"), _f32(dbeta, "dbeta"), _po(dres, dres_off),
-           dt(dres) if dres is not None else 0, C_ if lddres is None else lddres, int(acc_dres), wp, wn, _stream())
+           dt(dres) if dres is not None else 0, C_ if lddres is None else lddres, int(acc_dres), int(frozen), wp, wn, _stream())
 
 
 # ------------------------------------------------------------------------------------------------------ depthwise
@@ -251,16 +252,16 @@ def ccu_stats(xb, u, arg, B, HW, C_, ws):
     L.call("cenet_ccu_stats", _p(xb), dt(xb), _f32(u, "u"), _i32(arg, "arg"), B, HW, C_, wp, wn, _stream())
 
 
-def ccu_mlp_fwd(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C_):
+def ccu_mlp_fwd(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C_, frozen=False):
     L.call("cenet_ccu_mlp_fwd", _f32(u, "u"), _f32(fc1, "fc1"), _f32(fc2, "fc2"), _f32(gamma, "gamma"), _f32(beta, "beta"),
            _f32(rmean, "rmean"), _f32(rvar, "rvar"), _p(nbt), momentum, eps, _f32(gate, "gate"), _f32(save, "save"), B, C_,
-           _stream())
+           int(frozen), _stream())
 
 
-def ccu_mlp_bwd(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C_):
+def ccu_mlp_bwd(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C_, frozen=False):
     L.call("cenet_ccu_mlp_bwd", _f32(dgate, "dgate"), _f32(u, "u"), _f32(fc1, "fc1"), _f32(fc2, "fc2"), _f32(gamma, "gamma"),
            _f32(beta, "beta"), _f32(save, "save"), _f32(du, "du"), _f32(dfc1, "dfc1"), _f32(dfc2, "dfc2"), _f32(dgamma, "dgamma"),
-           _f32(dbeta, "dbeta"), B, C_, _stream())
+           _f32(dbeta, "dbeta"), B, C_, int(frozen), _stream())
 
 
 def ccu_dgate(dx1, xb, dgate, B, HW, C_, ws):
@@ -278,22 +279,22 @@ def row_stats_arg(x, u, arg, M, C_):
     L.call("cenet_row_stats_arg", _p(x), dt(x), _f32(u, "u"), _i32(arg, "arg"), M, C_, _stream())
 
 
-def srm_fwd(u, pw, dw, gamma, beta, rmean, rvar, nbt, momentum, eps, gm, save, st, B, H, W, ws):
+def srm_fwd(u, pw, dw, gamma, beta, rmean, rvar, nbt, momentum, eps, gm, save, st, B, H, W, ws, frozen=False):
     wp, wn = _ws(ws)
     L.call("cenet_srm_fwd", _f32(u, "u"), _f32(pw, "pw"), _f32(dw, "dw"), _f32(gamma, "gamma"), _f32(beta, "beta"),
            _f32(rmean, "rmean"), _f32(rvar, "rvar"), _p(nbt), momentum, eps, _f32(gm, "gm"), _f32(save, "save"), _f32(st, "st"),
-           B, H, W, wp, wn, _stream())
+           B, H, W, int(frozen), wp, wn, _stream())
 
 
 def row_dot(a, b, out, M, C_):
     L.call("cenet_row_dot", _p(a), _p(b), dt(a), _f32(out, "out"), M, C_, _stream())
 
 
-def srm_bwd(dgm, u, gm, save, st, pw, dw, gamma, beta, du, dpw, ddw, dgamma, dbeta, B, H, W, ws):
+def srm_bwd(dgm, u, gm, save, st, pw, dw, gamma, beta, du, dpw, ddw, dgamma, dbeta, B, H, W, ws, frozen=False):
     wp, wn = _ws(ws)
     L.call("cenet_srm_bwd", _f32(dgm, "dgm"), _f32(u, "u"), _f32(gm, "gm"), _f32(save, "save"), _f32(st, "st"), _f32(pw, "pw"),
            _f32(dw, "dw"), _f32(gamma, "gamma"), _f32(beta, "beta"), _f32(du, "du"), _f32(dpw, "dpw"), _f32(ddw, "ddw"), _f32(dgamma, "dgamma"),
-           _f32(dbeta, "dbeta"), B, H, W, wp, wn, _stream())
+           _f32(dbeta, "dbeta"), B, H, W, int(frozen), wp, wn, _stream())
 
 
 def srm_apply_bwd(dh3, h2, z, gm, u, arg, du, dz, M, C_):

@@ -299,9 +299,12 @@ int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, const float* g
                         int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems, cenet_stream_t s);
 /* train-mode BatchNorm statistics of x[rows, C]: mean, rstd (biased var), scale = gamma*rstd, shift = beta - mean*scale; updates
  * running_mean / running_var (unbiased) with `momentum` and increments num_batches_tracked (all nullable) */
+/* `frozen` != 0 (here and in cenet_bn_bwd / cenet_ccu_mlp_* / cenet_srm_*): eval-mode normalisation inside a gradient-enabled pass
+ * -- the running statistics ARE the statistics, nothing is updated, and the backward has no batch terms (main_acdc.py:226 runs
+ * `net.eval()` under grad mode). */
 int cenet_bn_stats(const void* x, int x_dtype, long long ldx, long long rows, int C, const float* gamma, const float* beta,
-                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps, float* scale,
-                   float* shift, float* mean, float* rstd, float* ws, long long ws_elems, cenet_stream_t s);
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps, int frozen,
+                   float* scale, float* shift, float* mean, float* rstd, float* ws, long long ws_elems, cenet_stream_t s);
 /* out = act( a*sa+ta [+ (sb ? b*sb+tb : b)] )  -- BatchNorm apply (+ residual branch of UnetResBlock, unet.py:201-214) */
 int cenet_affine_act(const void* a, int a_dtype, long long lda, const float* sa, const float* ta, const void* b, int b_dtype,
                      long long ldb, const float* sb, const float* tb, void* out, int o_dtype, long long ldo, long long rows, int C,
@@ -311,7 +314,7 @@ int cenet_affine_act(const void* a, int a_dtype, long long lda, const float* sa,
  * dy and y share (ldy); a and da share (lda). */
 int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_dtype, long long ldy, const void* a, int a_dtype, long long lda,
                  const float* mean, const float* rstd, const float* gamma, long long rows, int C, int act, float slope, void* da,
-                 int da_dtype, int acc_da, float* dgamma, float* dbeta, void* dres, int dres_dtype, long long lddres, int acc_dres,
+                 int da_dtype, int acc_da, float* dgamma, float* dbeta, void* dres, int dres_dtype, long long lddres, int acc_dres, int frozen,
                  float* ws, long long ws_elems, cenet_stream_t s);
 /* filter / bias gradient of the depthwise 3x3 family: dw [C,1,3,3], dbias [C] (nullable); x as in cenet_dwconv3x3 (up2) */
 int cenet_dwconv3x3_wgrad(const void* x, int x_dtype, long long ldx, const void* dz, int dz_dtype, long long ldz, int B, int H, int W,
@@ -357,12 +360,12 @@ int cenet_add(void* dst, const void* src, int dtype, long long n, int acc, cenet
  * BatchNorm1d over B (gamma == NULL: skipped, the reference's B == 1 case); and the three backward pieces */
 int cenet_ccu_stats(const void* xb, int dtype, float* u, int* arg, int B, int HW, int C, float* ws, long long ws_elems, cenet_stream_t s);
 int cenet_ccu_mlp_fwd(const float* u, const float* fc1, const float* fc2, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, long long* nbt, float momentum, float eps, float* gate, float* save_bc8, int B, int C,
+                      float* running_var, long long* nbt, float momentum, float eps, float* gate, float* save_bc8, int B, int C, int frozen,
                       cenet_stream_t s);
 int cenet_ccu_dgate(const void* dx1, const void* xb, int dtype, float* dgate, int B, int HW, int C, float* ws, long long ws_elems,
                     cenet_stream_t s);
 int cenet_ccu_mlp_bwd(const float* dgate, const float* u, const float* fc1, const float* fc2, const float* gamma, const float* beta,
-                      const float* save_bc8, float* du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C,
+                      const float* save_bc8, float* du, float* dfc1, float* dfc2, float* dgamma, float* dbeta, int B, int C, int frozen,
                       cenet_stream_t s);
 int cenet_ccu_apply_bwd(const void* dx1, const void* xb, int dtype, const float* gate, const float* u, const int* arg, const float* du,
                         void* dxb, int acc, int B, int HW, int C, cenet_stream_t s);
@@ -370,11 +373,11 @@ int cenet_ccu_apply_bwd(const void* dx1, const void* xb, int dtype, const float*
 int cenet_row_stats_arg(const void* x, int dtype, float* u, int* arg, long long rows, int C, cenet_stream_t s);
 int cenet_srm_fwd(const float* u, const float* pw, const float* dw, const float* gamma, const float* beta, float* running_mean,
                   float* running_var, long long* nbt, float momentum, float eps, float* gm, float* save_m2, float* st, int B, int H,
-                  int W, float* ws, long long ws_elems, cenet_stream_t s);
+                  int W, int frozen, float* ws, long long ws_elems, cenet_stream_t s);
 int cenet_row_dot(const void* a, const void* b, int dtype, float* out, long long rows, int C, cenet_stream_t s);
 int cenet_srm_bwd(const float* dgm, const float* u, const float* gm, float* save_m2, const float* st, const float* pw, const float* dw,
                   const float* gamma, const float* beta, float* du, float* dpw, float* ddw, float* dgamma, float* dbeta, int B, int H,
-                  int W, float* ws, long long ws_elems, cenet_stream_t s);
+                  int W, int frozen, float* ws, long long ws_elems, cenet_stream_t s);
 int cenet_srm_apply_bwd(const void* dh3, const void* h2, const void* z, int dtype, const float* gm, const float* u, const int* arg,
                         const float* du, void* dz, long long rows, int C, cenet_stream_t s);
 /* SiLU(g)*SiLU(v) (cfam.py:303-304) and backward */

@@ -119,8 +119,13 @@ def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws):
 
 
 # ------------------------------------------------------------------------------------------------------ BatchNorm
-def bn_stats(x, rows, C, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift, mean, rstd, ws, ldx=None, x_off=0):
+def bn_stats(x, rows, C, gamma, beta, rmean, rvar, nbt, momentum, eps, scale, shift, mean, rstd, ws, ldx=None, x_off=0,
+             frozen=False):
     _LAUNCHES[0] += 2
+    if frozen:                                   # eval-mode BatchNorm: running statistics, nothing updated
+        r = torch.rsqrt(rvar + eps)
+        mean.copy_(rmean); rstd.copy_(r); scale.copy_(gamma * r); shift.copy_(beta - rmean * gamma * r)
+        return
     xv = _m(x, rows, C, ldx, x_off).float()
     mu = xv.mean(0)
     var = xv.var(0, unbiased=False)
@@ -149,7 +154,7 @@ def affine_act(a, out, rows, C, sa=None, ta=None, b=None, sb=None, tb=None, act=
 
 
 def bn_bwd(dy, y, a, mean, rstd, gamma, rows, C, da, dgamma, dbeta, ws, act=ACT_NONE, slope=0.0, acc_da=False, dres=None,
-           acc_dres=False, ldy=None, y_off=0, lda=None, a_off=0, lddres=None, dres_off=0):
+           acc_dres=False, ldy=None, y_off=0, lda=None, a_off=0, lddres=None, dres_off=0, frozen=False):
     _LAUNCHES[0] += 3
     g = _m(dy, rows, C, ldy, y_off).float()
     if y is not None and act != ACT_NONE:
@@ -157,7 +162,7 @@ def bn_bwd(dy, y, a, mean, rstd, gamma, rows, C, da, dgamma, dbeta, ws, act=ACT_
     xh = (_m(a, rows, C, lda, a_off).float() - mean) * rstd
     db = g.sum(0)
     dg = (g * xh).sum(0)
-    dx = gamma * rstd * (g - db / rows - xh * dg / rows)
+    dx = gamma * rstd * (g if frozen else (g - db / rows - xh * dg / rows))
     _store(_m(da, rows, C, lda, a_off), dx, acc_da)
     dgamma.copy_(dg)
     dbeta.copy_(db)
@@ -314,28 +319,33 @@ def ccu_stats(xb, u, arg, B, HW, C, ws):
     arg.copy_(idx.to(torch.int32))
 
 
-def _ccu_mlp(u, fc1, fc2, gamma, beta, eps):
+def _ccu_mlp(u, fc1, fc2, gamma, beta, eps, stats=None):
     C = u.shape[1]
     z1 = torch.einsum("cjk,bck->bcj", fc1.view(C, 3, 3), u)
     z2 = torch.einsum("cj,bcj->bc", fc2.view(C, 3), F.relu(z1))
     if gamma is not None:
-        mu, var = z2.mean(0), z2.var(0, unbiased=False)
+        mu, var = stats if stats is not None else (z2.mean(0), z2.var(0, unbiased=False))
         z2n = (z2 - mu) * torch.rsqrt(var + eps) * gamma + beta
         return torch.sigmoid(z2n), z2, mu, var
     return torch.sigmoid(z2), z2, None, None
 
 
-def ccu_mlp_fwd(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C):
+def ccu_mlp_fwd(u, fc1, fc2, gamma, beta, rmean, rvar, nbt, momentum, eps, gate, save, B, C, frozen=False):
     _LAUNCHES[0] += 1
-    g, z2, mu, var = _ccu_mlp(u, fc1, fc2, gamma, beta, eps)
+    frozen = frozen and gamma is not None
+    g, z2, mu, var = _ccu_mlp(u, fc1, fc2, gamma, beta, eps, (rmean.clone(), rvar.clone()) if frozen else None)
     gate.copy_(g)
+    if frozen:                                   # (emulation only: the statistics travel to the backward in two free save slots)
+        sv = save.view(B, C, 8)
+        sv[:, :, 6] = rmean; sv[:, :, 7] = rvar
+        return
     if gamma is not None:
         rmean.mul_(1 - momentum).add_(momentum * mu)
         rvar.mul_(1 - momentum).add_(momentum * var * (B / max(B - 1, 1)))
         nbt.add_(1)
 
 
-def ccu_mlp_bwd(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C):
+def ccu_mlp_bwd(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, dbeta, B, C, frozen=False):
     _LAUNCHES[0] += 1
     uu = u.detach().clone().requires_grad_(True)
     f1 = fc1.detach().clone().requires_grad_(True)
@@ -343,7 +353,8 @@ def ccu_mlp_bwd(dgate, u, fc1, fc2, gamma, beta, save, du, dfc1, dfc2, dgamma, d
     if gamma is not None:
         ga = gamma.detach().clone().requires_grad_(True)
         be = beta.detach().clone().requires_grad_(True)
-        g = _ccu_mlp(uu, f1, f2, ga, be, 1e-5)[0]
+        sv = save.view(B, C, 8)
+        g = _ccu_mlp(uu, f1, f2, ga, be, 1e-5, (sv[0, :, 6].clone(), sv[0, :, 7].clone()) if frozen else None)[0]
         a, b, c, d, e = torch.autograd.grad(g, (uu, f1, f2, ga, be), dgate)
         dgamma.copy_(d)
         dbeta.copy_(e)
@@ -383,16 +394,24 @@ def row_stats_arg(x, u, arg, M, C):
     arg.copy_(idx.to(torch.int32))
 
 
-def _srm(u, pw, dw, gamma, beta, eps, B, H, W):
+def _srm(u, pw, dw, gamma, beta, eps, B, H, W, stats=None):
     uf = u.view(B, H, W, 3).permute(0, 3, 1, 2)
     f = F.gelu(F.conv2d(uf, pw.view(1, 3, 1, 1)) + F.conv2d(uf, dw.view(1, 3, 3, 3), padding=1))
     mu, var = f.mean(), f.var(unbiased=False)
+    if stats is not None:                        # frozen: (mean, rstd) constants
+        fn = (f - stats[0]) * stats[1] * gamma + beta
+        return torch.sigmoid(fn).reshape(-1), mu, var
     fn = (f - mu) * torch.rsqrt(var + eps) * gamma + beta
     return torch.sigmoid(fn).reshape(-1), mu, var
 
 
-def srm_fwd(u, pw, dw, gamma, beta, rmean, rvar, nbt, momentum, eps, gm, save, st, B, H, W, ws):
+def srm_fwd(u, pw, dw, gamma, beta, rmean, rvar, nbt, momentum, eps, gm, save, st, B, H, W, ws, frozen=False):
     _LAUNCHES[0] += 3
+    if frozen:
+        st.view(-1)[0] = rmean.view(-1)[0]
+        st.view(-1)[1] = torch.rsqrt(rvar.view(-1)[0] + eps)
+        gm.copy_(_srm(u, pw, dw, gamma, beta, eps, B, H, W, (st.view(-1)[0].clone(), st.view(-1)[1].clone()))[0])
+        return
     g, mu, var = _srm(u, pw, dw, gamma, beta, eps, B, H, W)
     gm.copy_(g)
     n = B * H * W
@@ -406,14 +425,14 @@ def row_dot(a, b, out, M, C):
     out.copy_((a.float() * b.float()).sum(1))
 
 
-def srm_bwd(dgm, u, gm, save, st, pw, dw, gamma, beta, du, dpw, ddw, dgamma, dbeta, B, H, W, ws):
+def srm_bwd(dgm, u, gm, save, st, pw, dw, gamma, beta, du, dpw, ddw, dgamma, dbeta, B, H, W, ws, frozen=False):
     _LAUNCHES[0] += 4
     uu = u.detach().clone().requires_grad_(True)
     p = pw.detach().clone().requires_grad_(True)
     d = dw.detach().clone().requires_grad_(True)
     ga = gamma.detach().clone().requires_grad_(True)
     be = beta.detach().clone().requires_grad_(True)
-    g = _srm(uu, p, d, ga, be, 1e-5, B, H, W)[0]
+    g = _srm(uu, p, d, ga, be, 1e-5, B, H, W, (st.view(-1)[0].clone(), st.view(-1)[1].clone()) if frozen else None)[0]
     a, b, c, e, f = torch.autograd.grad(g, (uu, p, d, ga, be), dgm)
     du.copy_(a)
     dpw.copy_(b)

@@ -297,3 +297,47 @@ def test_eval_after_fused_steps_uses_new_weights():
         y2 = fresh(xd)
     assert (y1 - y0).abs().max().item() > 1e-3                    # training moved the output ...
     assert torch.equal(y1, y2)                                    # ... and the cached engine followed it exactly
+
+
+@pytest.mark.parametrize("name,batch,size", [("acdc", 2, 96), ("skin", 1, 96)])
+def test_eval_mode_backward_matches_oracle_autograd(name, batch, size, monkeypatch):
+    """SURVEY 8b "Call": the autograd path must also work in eval() (running-statistics BatchNorm, no DropPath; B = 1 included:
+    the CCU skips its BatchNorm1d).  `net.eval(); loss = crit(net(x)); loss.backward()` on the drop-in (fp32 validation precision)
+    against torch autograd through the oracle's eval-mode forward: every parameter gradient, and the buffers must not move."""
+    from cenet_b200.networks import CENet
+    monkeypatch.setenv("CENET_B200_PRECISION", "fp32")
+    kw = fixtures.CONFIGS[name]
+    torch.manual_seed(1234)
+    sd = fixtures.perturb_state(CENet(**kw).state_dict(), 1234)
+    x = fixtures.synth_input(name, batch, size=size)
+    labels = torch.randint(0, kw["num_classes"], (batch, size, size), generator=torch.Generator().manual_seed(5))
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits_ref = O.cenet_forward(leaf, O.Cfg(**kw), x, training=False)
+    loss_ref = O.criterion_dice_ce(logits_ref, labels, kw["num_classes"])
+    gref = dict(zip(names, torch.autograd.grad(loss_ref, [leaf[k] for k in names], allow_unused=True)))
+    m = CENet(**kw)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    y = m(x.to(DEV))                                                      # eval() forward under grad mode
+    assert y.requires_grad
+    assert ((y.detach().cpu() - logits_ref.detach()).norm() / logits_ref.norm()).item() < 1e-4
+    yl = y.detach().cpu().requires_grad_(True)
+    loss = O.criterion_dice_ce(yl, labels, kw["num_classes"])
+    loss.backward()
+    y.backward(yl.grad.to(DEV))
+    bad = []
+    gn = max(g.norm().item() for g in gref.values() if g is not None)
+    for k, p in m.named_parameters():
+        g = gref[k]
+        if g is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0
+            continue
+        err = (p.grad.cpu() - g).norm().item()
+        if not err < 2e-3 * g.norm().item() + 1e-6 * gn:
+            bad.append((k, err / max(g.norm().item(), 1e-12)))
+    assert not bad, bad[:20]
+    after = m.state_dict()
+    for k, v in sd.items():
+        if "running_" in k or "num_batches" in k:
+            assert torch.equal(after[k].cpu(), v), k                   # eval mode: statistics untouched

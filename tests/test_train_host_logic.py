@@ -67,6 +67,39 @@ def test_train_step_matches_oracle_autograd(name, batch, size, flash):
     assert not bad, bad[:20]
 
 
+@pytest.mark.parametrize("name,batch", [("acdc", 2), ("skin", 1)])
+def test_frozen_statistics_pass_matches_oracle_eval_autograd(name, batch):
+    """eval() semantics inside a gradient pass (what `net.eval(); net(x).backward()` runs, networks.cenet._EvalForward): BatchNorm,
+    the CCU's BatchNorm1d and the SRM's BatchNorm2d(1) use their running statistics and update nothing; loss and every parameter
+    gradient against autograd through the oracle's EVAL-mode forward."""
+    m, eng, sd, kw = _build(name, True)
+    size = 64
+    x = fixtures.synth_input(name, batch, size=size)
+    labels = torch.randint(0, kw["num_classes"], (batch, size, size), generator=torch.Generator().manual_seed(5))
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits = O.cenet_forward(leaf, O.Cfg(**kw), x, training=False)
+    loss_ref = O.criterion_dice_ce(logits, labels, kw["num_classes"])
+    gref = dict(zip(names, torch.autograd.grad(loss_ref, [leaf[k] for k in names], allow_unused=True)))
+    eng.frozen_stats = True
+    out = eng.train_step(x, labels, optimize=False)
+    assert abs(out[0].item() - loss_ref.item()) < 2e-5 * max(1.0, abs(loss_ref.item()))
+    bad = []
+    for k, gr in gref.items():
+        mine = eng.GP[k]
+        if gr is None:
+            assert mine.abs().max().item() == 0.0, k
+            continue
+        err = (mine - gr).norm().item()
+        if not err < 2e-3 * gr.norm().item() + 1e-6:
+            bad.append((k, err, gr.norm().item()))
+    assert not bad, bad[:20]
+    after = m.state_dict()
+    for k, v in sd.items():
+        if "running_" in k or "num_batches" in k:
+            assert torch.equal(after[k], v), k
+
+
 def test_running_stats_and_adamw_step():
     m, eng, sd, kw = _build("acdc")
     x = fixtures.synth_input("acdc", 2, size=64)
