@@ -424,10 +424,6 @@ class CENet(nn.Module):
             raise RuntimeError("cenet_b200.CENet has no CPU path: move the module and the input to a B200 "
                                "(`.cuda()`); the CPU oracle lives in oracle/ and is test-only")
         if self.training:
-            c = self.cfg
-            if c["skip_mode"] != "cat" or c["out_merge_mode"] != "cat" or "uprb" in (c["dec_up_block"], c["out_up_block"]):
-                raise NotImplementedError("train() mode covers skip_mode='cat', out_merge_mode='cat' and the eucb / upcn up blocks; "
-                                          "the 'add' modes and 'uprb' are inference-only here (DESIGN.md section 7)")
             if torch.is_grad_enabled():
                 params = [p for p in self.parameters()]
                 return _TrainForward.apply(self, x, *params)

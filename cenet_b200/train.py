@@ -405,6 +405,12 @@ class TrainEngine:
             self._pack_mat(p + ".pwc.0", P[p + ".pwc.0.weight"].flatten(1))
         elif kind == "upcn":
             self._pack_conv(p + ".up.1", P[p + ".up.1.weight"])
+        elif kind == "uprb":                                        # blocks.py:188-204: bilinear x2 + UnetResBlock(k=3)
+            q = p + ".up.1"
+            self._pack_conv(q + ".conv1.conv", P[q + ".conv1.conv.weight"])
+            self._pack_conv(q + ".conv2.conv", P[q + ".conv2.conv.weight"])
+            if (q + ".conv3.conv.weight") in P:
+                self._pack_mat(q + ".conv3.conv", P[q + ".conv3.conv.weight"].flatten(1))
         else:
             raise NotImplementedError(kind)
 
@@ -1037,6 +1043,18 @@ class TrainEngine:
         if out is None:
             out = self.buf(key + ".out", (Mo, Cout))
             ldc = Cout
+        if kind == "uprb":
+            t = self.buf(key + ".up", (B, 2 * H, 2 * W, Cin))
+            ops.upsample2x_ac(x, t, B, H, W, Cin)
+            tb = self._up2_tables(H, W)
+
+            def uprb_bwd():
+                acc = self.wr(x)
+                tops.resample(self.G(t), self.G(x), B, 2 * H, 2 * W, H, W, Cin, tb["up_T"], ldx=Cin, x_off=0, ldy=Cin, y_off=0,
+                              acc=acc)
+            self.tape.append(uprb_bwd)
+            self._resblock(t, B, 2 * H, 2 * W, Cin, Cout, 3, p + ".up.1", key, out, ldc, c_off)
+            return out
         if kind == "eucb":
             raw = self.buf(key + ".dwraw", (Mo, Cin))
             self.dwconv(x, raw, p + ".up_dwc.1", B, 2 * H, 2 * W, Cin, up2=True)
@@ -1063,16 +1081,30 @@ class TrainEngine:
         """dseb.py:153-165 (+ the decoder's `d + s`, decoders.py:95): returns mixer(z) + skip + dec"""
         P, GP = self.P, self.GP
         ops.tag = key
-        HW, E, M = H * W, 2 * Cc, B * H * W
+        add = self.cfg.get("skip_mode", "cat") == "add"               # dseb.py:155: y = dec + skip instead of cat([dec, skip])
+        HW, E, M = H * W, (Cc if add else 2 * Cc), B * H * W
         y = self.buf(key + ".y", (B, E, H, W))
-        ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
-        ops.nhwc_to_nchw(skip, y, B, HW, Cc, E, Cc)
+        if add:
+            ysum = self.buf(key + ".ysum", (M, Cc))
+            tops.add_(ysum, dec, M * Cc, False)
+            tops.add_(ysum, skip, M * Cc, True)
+            ops.nhwc_to_nchw(ysum, y, B, HW, Cc, E, 0)
 
-        def cat_bwd():
-            dy = self.G(y)
-            tops.nchw_to_nhwc_slice(dy, self.G(dec), B, HW, Cc, E, 0, self.wr(dec))
-            tops.nchw_to_nhwc_slice(dy, self.G(skip), B, HW, Cc, E, Cc, self.wr(skip))
-        self.tape.append(cat_bwd)
+            def add_bwd():
+                dsum = self.G(ysum)
+                tops.nchw_to_nhwc_slice(self.G(y), dsum, B, HW, Cc, E, 0, False)
+                for t in (dec, skip):
+                    tops.add_(self.G(t), dsum, M * Cc, self.wr(t))
+            self.tape.append(add_bwd)
+        else:
+            ops.nhwc_to_nchw(dec, y, B, HW, Cc, E, 0)
+            ops.nhwc_to_nchw(skip, y, B, HW, Cc, E, Cc)
+
+            def cat_bwd():
+                dy = self.G(y)
+                tops.nchw_to_nhwc_slice(dy, self.G(dec), B, HW, Cc, E, 0, self.wr(dec))
+                tops.nchw_to_nhwc_slice(dy, self.G(skip), B, HW, Cc, E, Cc, self.wr(skip))
+            self.tape.append(cat_bwd)
         tok = y.view(M, E)
         # ---- differential attention on the reinterpreted buffer
         d = p + ".diffattn"
@@ -1158,22 +1190,42 @@ class TrainEngine:
         return t
 
     # ------------------------------------------------------------------------------------------------ head
-    def _resblock_tail(self, c2raw, rraw, st3name, out, Mtok, Cc, p, key):
-        """out = LeakyReLU(BN2(c2raw) + (BN3(rraw) | rraw))"""
+    def _resblock_tail(self, c2raw, rraw, st3name, out, Mtok, Cc, p, key, ldo=None, o_off=0):
+        """out = LeakyReLU(BN2(c2raw) + (BN3(rraw) | rraw)); out may be a channel slice (pitch ldo, offset o_off)"""
         st2 = self.bn_stats(c2raw, Mtok, Cc, p + ".norm2", key + ".bn2")
         st3 = self.bn_stats(rraw, Mtok, Cc, st3name, key + ".bn3") if st3name else None
         tops.affine_act(c2raw, out, Mtok, Cc, sa=st2["scale"], ta=st2["shift"], b=rraw,
-                        sb=st3["scale"] if st3 else None, tb=st3["shift"] if st3 else None, act=ACT_LEAKY, slope=0.01)
+                        sb=st3["scale"] if st3 else None, tb=st3["shift"] if st3 else None, act=ACT_LEAKY, slope=0.01,
+                        ldo=ldo, o_off=o_off)
 
         def bwd():
             dy = self.G(out)
             if st3:
-                self.bn_bwd(st3, dy, out, rraw, act=ACT_LEAKY, slope=0.01)
-                self.bn_bwd(st2, dy, out, c2raw, act=ACT_LEAKY, slope=0.01)
+                self.bn_bwd(st3, dy, out, rraw, act=ACT_LEAKY, slope=0.01, ldy=ldo, y_off=o_off)
+                self.bn_bwd(st2, dy, out, c2raw, act=ACT_LEAKY, slope=0.01, ldy=ldo, y_off=o_off)
             else:
                 acc = self.wr(rraw)
-                self.bn_bwd(st2, dy, out, c2raw, act=ACT_LEAKY, slope=0.01, dres=self.G(rraw), dres_acc=acc)
+                self.bn_bwd(st2, dy, out, c2raw, act=ACT_LEAKY, slope=0.01, ldy=ldo, y_off=o_off, dres=self.G(rraw), dres_acc=acc)
         self.tape.append(bwd)
+
+    def _resblock(self, x4, B, H, W, Cin, Cout, k, p, key, out, ldo=None, o_off=0):
+        """UnetResBlock (unet.py:201-214) in train mode: conv k x k -> BN -> LeakyReLU -> conv k x k -> BN; residual through
+        1x1 conv + BN when Cin != Cout; add; LeakyReLU(0.01).  x4 [B,H,W,Cin] contiguous."""
+        Mtok = B * H * W
+        c1raw = self.buf(key + ".c1raw", (Mtok, Cout))
+        self.conv(x4, p + ".conv1.conv", c1raw, k, key + ".c1")
+        a1 = self.buf(key + ".a1", (B, H, W, Cout))
+        self.bn_act(c1raw, Mtok, Cout, p + ".norm1", a1.view(Mtok, Cout), key + ".bn1", act=ACT_LEAKY, slope=0.01)
+        c2raw = self.buf(key + ".c2raw", (Mtok, Cout))
+        self.conv(a1, p + ".conv2.conv", c2raw, k, key + ".c2")
+        x2 = x4.view(Mtok, Cin)
+        if (p + ".conv3.conv.weight") in self.P:
+            rraw = self.buf(key + ".rraw", (Mtok, Cout))
+            self.lin(x2, p + ".conv3.conv", rraw, bias=False)
+            self._resblock_tail(c2raw, rraw, p + ".norm3", out, Mtok, Cout, p, key, ldo, o_off)
+        else:
+            self._resblock_tail(c2raw, x2, None, out, Mtok, Cout, p, key, ldo, o_off)
+        return out
 
     def _run_forward(self, x_in, B, H, W, logits):
         cfg, P, GP = self.cfg, self.P, self.GP
@@ -1227,26 +1279,47 @@ class TrainEngine:
         self.conv(o1, "out.rb.0.conv2.conv", c2raw, 5, "head.rb.c2")
         rb = self.buf("head.rb.out", (Mf, om))
         self._resblock_tail(c2raw, rraw, "out.rb.0.norm3", rb, Mf, om, "out.rb.0", "head.rb")
-        z = self.buf("head.z", (Mh, 2 * om))
-        ops.maxpool2_scale(rb, z, 2 * om, om, P["out.w"].reshape(-1), B, H, W, om)
+        madd = cfg.get("out_merge_mode", "cat") == "add"            # out.py:58-64: up(dec) + w*rb(x) instead of cat
+        mix = om if madd else 2 * om
+        z = self.buf("head.z", (Mh, mix))
+        if madd:
+            rbp = self.buf("head.rbp", (Mh, om))
+            ops.maxpool2_scale(rb, rbp, om, 0, P["out.w"].reshape(-1), B, H, W, om)
 
-        def pool_bwd():
-            tops.maxpool2_scale_bwd(self.G(z), 2 * om, om, rb, P["out.w"].reshape(-1), self.G(rb), GP["out.w"], B, H, W, om,
-                                    self._ws(0))
-            self.wr(rb)
-        self.tape.append(pool_bwd)
-        self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
+            def pool_bwd():
+                tops.maxpool2_scale_bwd(self.G(rbp), om, 0, rb, P["out.w"].reshape(-1), self.G(rb), GP["out.w"], B, H, W, om,
+                                        self._ws(0))
+                self.wr(rb)
+            self.tape.append(pool_bwd)
+            zu = self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up")
+            tops.add_(z, zu, Mh * om, False)
+            tops.add_(z, rbp, Mh * om, True)
+
+            def merge_bwd():                                          # z = up + rbp: both operands receive dz
+                dz = self.G(z)
+                tops.add_(self.G(zu), dz, Mh * om, self.wr(zu))
+                tops.add_(self.G(rbp), dz, Mh * om, self.wr(rbp))
+            self.tape.append(merge_bwd)
+        else:
+            ops.maxpool2_scale(rb, z, 2 * om, om, P["out.w"].reshape(-1), B, H, W, om)
+
+            def pool_bwd():
+                tops.maxpool2_scale_bwd(self.G(z), 2 * om, om, rb, P["out.w"].reshape(-1), self.G(rb), GP["out.w"], B, H, W, om,
+                                        self._ws(0))
+                self.wr(rb)
+            self.tape.append(pool_bwd)
+            self._up(d, B, H1, W1, C1, om, "out.up", cfg["out_up_block"], "head.up", out=z, ldc=2 * om, c_off=0)
         ops.tag = "head.out"
         p = "out.out.0"
-        z4 = z.view(B, Hh, Wh, 2 * om)
-        r1raw = self.buf("head.out.r1raw", (Mh, 2 * om))
+        z4 = z.view(B, Hh, Wh, mix)
+        r1raw = self.buf("head.out.r1raw", (Mh, mix))
         self.conv(z4, p + ".conv1.conv", r1raw, 3, "head.out.c1")
-        a1 = self.buf("head.out.a1", (B, Hh, Wh, 2 * om))
-        self.bn_act(r1raw, Mh, 2 * om, p + ".norm1", a1.view(Mh, 2 * om), "head.out.bn1", act=ACT_LEAKY, slope=0.01)
-        r2raw = self.buf("head.out.r2raw", (Mh, 2 * om))
+        a1 = self.buf("head.out.a1", (B, Hh, Wh, mix))
+        self.bn_act(r1raw, Mh, mix, p + ".norm1", a1.view(Mh, mix), "head.out.bn1", act=ACT_LEAKY, slope=0.01)
+        r2raw = self.buf("head.out.r2raw", (Mh, mix))
         self.conv(a1, p + ".conv2.conv", r2raw, 3, "head.out.c2")
-        o = self.buf("head.out.o", (Mh, 2 * om))
-        self._resblock_tail(r2raw, z, None, o, Mh, 2 * om, p, "head.out")
+        o = self.buf("head.out.o", (Mh, mix))
+        self._resblock_tail(r2raw, z, None, o, Mh, mix, p, "head.out")
         ops.tag = "head.logits"
         yh = self.buf("head.y", (Mh, ncls), torch.float32)
         self.lin(o, "out.out.1.conv.conv", yh)
