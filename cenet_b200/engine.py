@@ -117,6 +117,7 @@ class Engine:
         self.gemm_impl = GEMM_AUTO if precision == "bf16" else GEMM_SIMT
         # materialised attention (batched / transposed operands): mma.sync tensor-core GEMM in bf16, CUDA cores in fp32 validation
         self.attn_gemm_impl = GEMM_MMA if precision == "bf16" else GEMM_SIMT
+        self._tables = {}                                   # resampling tap tables (zero insertion of the uptc up block)
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
@@ -290,6 +291,11 @@ class Engine:
             self._put(f"{p}.c{i}.b", t)
 
     def _pack_up(self, sd, p, kind):
+        if kind == "uptc":                                  # blocks.py:223-243: ConvTranspose2d(k, stride 2) = zero insertion + the
+            w = sd[p + ".up.conv.weight"]                   # stride-1 conv whose filter is the transposed, tap-flipped weight
+            self._put_mat(p + ".tc.w", self._conv_mat(w.permute(1, 0, 2, 3).flip(2, 3)))
+            self._tables[p + ".ks"] = int(w.shape[-1])
+            return
         if kind == "uprb":                                  # blocks.py:188-204: bilinear x2 + UnetResBlock(k=3)
             self._pack_resblock(sd, p + ".up.1", 3)
             return
@@ -585,6 +591,15 @@ class Engine:
         if out is None:
             out = self.buf(key + ".out", (Mo, Cout))
             ldc = Cout
+        if kind == "uptc":
+            t = self.buf(key + ".zi", (B, 2 * H, 2 * W, Cin))
+            tk = ("zi", H, W)
+            if tk not in self._tables:
+                self._tables[tk] = ops.zero_insert_tables(H, W, self.dev)
+            ops.resample(x, t, B, H, W, 2 * H, 2 * W, Cin, self._tables[tk])
+            ks = self._tables[p + ".ks"]
+            ops.conv_nhwc(t, w[p + ".tc.w"], out, ks, 1, ks // 2, N=Cout, ldc=ldc, c_off=c_off, impl=self.gemm_impl)
+            return out
         if kind == "uprb":
             t = self.buf(key + ".up", (B, 2 * H, 2 * W, Cin))
             ops.upsample2x_ac(x, t, B, H, W, Cin)

@@ -213,7 +213,14 @@ def _make_up(kind, cin, cout, ks=3):
         m.up = _Seq(_1=_res_block(cin, cout, ks))
         m.kind = "uprb"
         return m
-    raise NotImplementedError("up block 'uptc' (ConvTranspose2d, blocks.py:223-243) is not built: see DESIGN.md section 7")
+    # uptc (blocks.py:223-243): monai Convolution(conv_only=True, is_transposed=True) == Sequential(conv=ConvTranspose2d) with
+    # padding (k - s + 1) // 2 and output_padding 2p + s - k (unet.py:16-48); the decoder calls it with stride 2
+    m = _Holder()
+    pad = (ks - 2 + 1) // 2
+    m.up = _Seq(conv=nn.ConvTranspose2d(cin, cout, ks, stride=2, padding=pad, output_padding=2 * pad + 2 - ks, bias=False))
+    m.apply(_init_normal)
+    m.kind = "uptc"
+    return m
 
 
 def _dse_block(dim, scale_factors, heads, depth, mode="cat"):

@@ -104,6 +104,27 @@ def conv_nhwc(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, ksize: int, s
                 conv=(B, H, W, Cin, ksize, ksize, stride, pad, Ho, Wo), **kw)
 
 
+def zero_insert_tables(H, W, dev):
+    """CSR tap tables of the 2x zero-insertion [H,W] -> [2H,2W] (y[2i,2j] = x[i,j], zeros elsewhere) for `resample`: a transposed
+    conv with stride 2 is that followed by a stride-1 conv with flipped taps (uptc up block, blocks.py:223-243)"""
+    def csr(n):
+        start = torch.zeros(2 * n + 1, dtype=torch.int32)
+        start[1::2] = torch.arange(1, n + 1, dtype=torch.int32)            # even output rows own one tap, odd rows none
+        start[2::2] = torch.arange(1, n + 1, dtype=torch.int32)
+        return start.to(dev), torch.arange(n, dtype=torch.int32).to(dev), torch.ones(n, dtype=torch.float32).to(dev)
+    hs, hi, hw = csr(H)
+    ws, wi, ww = csr(W)
+    return dict(hs=hs, hi=hi, hw=hw, ws=ws, wi=wi, ww=ww)
+
+
+def resample(x, y, B, Hi, Wi, Ho, Wo, C_, tables, ldx=None, x_off=0, ldy=None, y_off=0, acc=False):
+    """sparse separable resampling (cenet_resample): out[i,j] = sum over the CSR taps of row i / column j"""
+    t = tables
+    L.call("cenet_resample", _p(x) + x_off * x.element_size(), dt(x), C_ if ldx is None else ldx, _p(y) + y_off * y.element_size(), dt(y),
+           C_ if ldy is None else ldy, B, Hi, Wi, Ho, Wo, C_, _p(t["hs"]), _p(t["hi"]), _f32(t["hw"], "hw"), _p(t["ws"]), _p(t["wi"]),
+           _f32(t["ww"], "ww"), int(acc), _stream())
+
+
 def add_(dst, src, n, acc):
     """dst[:n] (+)= src[:n]  (DSEBlock / OutHead 'add' merge modes, dseb.py:155, out.py:61)"""
     L.call("cenet_add", _p(dst), _p(src), dt(dst), n, int(acc), _stream())

@@ -405,6 +405,9 @@ class TrainEngine:
             self._pack_mat(p + ".pwc.0", P[p + ".pwc.0.weight"].flatten(1))
         elif kind == "upcn":
             self._pack_conv(p + ".up.1", P[p + ".up.1.weight"])
+        elif kind == "uptc":                                        # blocks.py:223-243: ConvTranspose2d(k, stride 2) as zero insertion +
+            w = P[p + ".up.conv.weight"]                            # the stride-1 conv with the transposed, tap-flipped filter
+            self._pack_conv(p + ".up.conv", w.permute(1, 0, 2, 3).flip(2, 3))
         elif kind == "uprb":                                        # blocks.py:188-204: bilinear x2 + UnetResBlock(k=3)
             q = p + ".up.1"
             self._pack_conv(q + ".conv1.conv", P[q + ".conv1.conv.weight"])
@@ -649,8 +652,9 @@ class TrainEngine:
         self.tape.append(bwd)
         return out
 
-    def conv(self, x4, name, out, k, key):
-        """dense stride-1 'same' conv without bias: out[M,Cout] raw.  x4: [B,H,W,Cin] contiguous."""
+    def conv(self, x4, name, out, k, key, gw=None, gw_fix=None):
+        """dense stride-1 'same' conv without bias: out[M,Cout] raw.  x4: [B,H,W,Cin] contiguous.
+        gw / gw_fix: weight-gradient destination [Cout,Cin,k,k] other than the parameter's own gradient + a fix-up run after it."""
         B, H, W, Cin = x4.shape
         Wm, WT = self.w[name + ".w"], self.w[name + ".wT"]
         Cout = out.shape[-1]
@@ -662,14 +666,21 @@ class TrainEngine:
             acc = self.wr(x4)
             ops.conv_nhwc(dy.view(B, H, W, Cout), WT, dx.view(B * H * W, Cin), k, 1, k // 2, res1=dx if acc else None,
                           ldr1=Cin, impl=self.gemm_impl)
+            dst = self.GP[name + ".weight"] if gw is None else gw
             if self.T == torch.bfloat16:                                                # taps gathered inside the kernel
-                self._wgrad((dy, x4), lambda: tops.conv_wgrad(dy, x4, self.GP[name + ".weight"], k, self._wws()))
+                def wg():
+                    tops.conv_wgrad(dy, x4, dst, k, self._wws())
+                    if gw_fix is not None:
+                        gw_fix()
+                self._wgrad((dy, x4), wg)
             else:
                 Kp = _rup(k * k * Cin, 8)
                 col = self.buf(key + ".col", (B * H * W, Kp))
                 ops.im2col(x4, col, B, H, W, Cin, k, 1, k // 2, H, W, Kp)
-                tops.gemm_wgrad(dy, col, self.GP[name + ".weight"], M=B * H * W, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0,
+                tops.gemm_wgrad(dy, col, dst, M=B * H * W, N=Cout, K=k * k * Cin, ldy=Cout, y_off=0,
                                 ldx=Kp, x_off=0, T=k * k, ws=self._ws(0))
+                if gw_fix is not None:
+                    gw_fix()
         self.tape.append(bwd)
         return out
 
@@ -1022,6 +1033,20 @@ class TrainEngine:
             TrainEngine._TABLES[k] = t
         return t
 
+    def _zi_tables(self, H, W):
+        """2x zero insertion [H,W] -> [2H,2W] (y[2i,2j] = x[i,j]) and its adjoint as resampling tap tables"""
+        k = ("zi", H, W, str(self.dev))
+        t = TrainEngine._TABLES.get(k)
+        if t is None:
+            def z(n):
+                m = torch.zeros(2 * n, n)
+                m[torch.arange(n) * 2, torch.arange(n)] = 1.0
+                return m
+            Zh, Zw = z(H), z(W)
+            t = dict(zi=tops.make_tables(Zh, Zw, self.dev), zi_T=tops.make_tables(Zh.t().contiguous(), Zw.t().contiguous(), self.dev))
+            TrainEngine._TABLES[k] = t
+        return t
+
     def _up2_tables(self, H, W):
         k = ("up2ac", H, W, str(self.dev))
         t = TrainEngine._TABLES.get(k)
@@ -1043,6 +1068,33 @@ class TrainEngine:
         if out is None:
             out = self.buf(key + ".out", (Mo, Cout))
             ldc = Cout
+        if kind == "uptc":
+            t = self.buf(key + ".zi", (B, 2 * H, 2 * W, Cin))
+            tb = self._zi_tables(H, W)
+            tops.resample(x, t, B, H, W, 2 * H, 2 * W, Cin, tb["zi"], ldx=Cin, x_off=0, ldy=Cin, y_off=0, acc=False)
+
+            def zi_bwd():                                             # adjoint of the zero insertion: dx[i,j] = dt[2i,2j]
+                acc = self.wr(x)
+                tops.resample(self.G(t), self.G(x), B, 2 * H, 2 * W, H, W, Cin, tb["zi_T"], ldx=Cin, x_off=0, ldy=Cin, y_off=0,
+                              acc=acc)
+            self.tape.append(zi_bwd)
+            name = p + ".up.conv"
+            gw = self.GP[name + ".weight"]                            # reference layout [Cin, Cout, k, k]
+            ks = gw.shape[-1]
+            raw = out if (ldc == Cout and c_off == 0) else self.buf(key + ".raw", (Mo, Cout))
+            tmp = self.buf(key + ".gw_eq", (Cout, Cin, ks, ks), torch.float32)
+
+            def fix():                                                # d(equivalent conv filter) -> d(ConvTranspose2d weight)
+                gw.copy_(tmp.permute(1, 0, 2, 3).flip(2, 3))
+            self.conv(t, name, raw, ks, key + ".conv", gw=tmp, gw_fix=fix)
+            if raw is not out:                                        # channel slice of the head's concat buffer
+                tops.affine_act(raw, out, Mo, Cout, ldo=ldc, o_off=c_off)
+
+                def copy_bwd():
+                    tops.affine_act(self.G(out), self.G(raw), Mo, Cout, lda=ldc, a_off=c_off)
+                    self.wr(raw)
+                self.tape.append(copy_bwd)
+            return out
         if kind == "uprb":
             t = self.buf(key + ".up", (B, 2 * H, 2 * W, Cin))
             ops.upsample2x_ac(x, t, B, H, W, Cin)

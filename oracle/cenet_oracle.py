@@ -315,6 +315,14 @@ def up_rb(sd, p, x, training=False):
     return unet_res_block(sd, p + ".up.1", x, 3, training)
 
 
+def up_tconv(sd, p, x, training=False):
+    """blocks.py:223-243: ConvTranspose2d(k, stride 2, padding (k-1)//2, output_padding 2p+2-k), no bias / norm / activation."""
+    w = sd[p + ".up.conv.weight"]
+    k = w.shape[-1]
+    pad = (k - 2 + 1) // 2
+    return F.conv_transpose2d(x, w, stride=2, padding=pad, output_padding=2 * pad + 2 - k)
+
+
 def _up_block(kind):
     if kind == "eucb":
         return eucb
@@ -322,6 +330,8 @@ def _up_block(kind):
         return up_conv
     if kind == "uprb":
         return up_rb
+    if kind == "uptc":
+        return up_tconv
     raise NotImplementedError(f"up block '{kind}' is outside the BASELINE configs (SURVEY section 2 row 9)")
 
 

@@ -24,6 +24,8 @@ CONFIGS = {
                      out_up_block="upcn", skip_mode="add", out_merge_mode="add"),
     "synapse_uprb": dict(input_channels=1, num_classes=9, scale_factors=[0.8, 0.4], diffatt_num_heads=[16, 8, 8],
                          out_up_block="uprb", dec_up_block="uprb"),
+    "acdc_uptc": dict(input_channels=1, num_classes=4, scale_factors=[1.0, 0.5], diffatt_num_heads=[4, 4, 4],
+                      out_up_block="uptc", dec_up_block="uptc"),
     "acdc_b5": dict(input_channels=1, num_classes=4, scale_factors=[1.0, 0.5], diffatt_num_heads=[4, 4, 4],
                     out_up_block="upcn", encoder="pvt_v2_b5"),
 }

@@ -198,6 +198,25 @@ def upsample2x_ac(x, out, B, H, W, Cc):
     return out
 
 
+def zero_insert_tables(H, W, dev):
+    """emulation: dense per-axis matrices [2n, n] with Z[2i, i] = 1"""
+    def z(n):
+        m = torch.zeros(2 * n, n)
+        m[torch.arange(n) * 2, torch.arange(n)] = 1.0
+        return m
+    return dict(Mh=z(H), Mw=z(W))
+
+
+def resample(x, y, B, Hi, Wi, Ho, Wo, C, tables, ldx=None, x_off=0, ldy=None, y_off=0, acc=False):
+    _LAUNCHES[0] += 1
+    ldx = C if ldx is None else ldx
+    ldy = C if ldy is None else ldy
+    xi = _as(_flat(x), (B, Hi, Wi, C), (Hi * Wi * ldx, Wi * ldx, ldx, 1), x_off).float()
+    o = torch.einsum("ih,bhwc,jw->bijc", tables["Mh"], xi, tables["Mw"])
+    yv = _as(_flat(y), (B, Ho, Wo, C), (Ho * Wo * ldy, Wo * ldy, ldy, 1), y_off)
+    yv.copy_(yv.float() + o if acc else o)
+
+
 def add_(dst, src, n, acc):
     _LAUNCHES[0] += 1
     d = _flat(dst)[:n]

@@ -282,6 +282,7 @@ if __name__ == "__main__":
         model_fixture(nets, "acdc_b5", 1)
         model_fixture(nets, "acdc_add", 1)
         model_fixture(nets, "synapse_uprb", 1)
+        model_fixture(nets, "acdc_uptc", 1)
         sys.exit(0)
     nets = ref_shim.import_reference()
     module_fixtures(nets)

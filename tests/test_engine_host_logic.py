@@ -32,7 +32,8 @@ def _patch_ops(monkeypatch):
 
 
 @pytest.mark.parametrize("name,batch,flash", [("acdc", 1, False), ("synapse", 2, True), ("skin", 1, True),
-                                              ("acdc_b1", 1, True), ("acdc_add", 1, True), ("synapse_uprb", 1, True)])
+                                              ("acdc_b1", 1, True), ("acdc_add", 1, True), ("synapse_uprb", 1, True),
+                                              ("acdc_uptc", 1, True)])
 def test_launch_plan_reproduces_oracle(name, batch, flash):
     eng, sd, kw = _engine(name, flash=flash)
     x = fixtures.synth_input(name, batch)

@@ -63,7 +63,7 @@ def run_with_taps(m, x, precision):
 
 
 @pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1), ("acdc_b1", 1), ("acdc_add", 1),
-                                        ("synapse_uprb", 1)])
+                                        ("synapse_uprb", 1), ("acdc_uptc", 1)])
 def test_fp32_precision_matches_oracle(name, batch):
     """fp32 storage + CUDA-core GEMMs + materialised attention: isolates launch-plan logic from bf16 rounding."""
     m, x, y_ref, taps_ref = build(name, batch)
@@ -78,7 +78,7 @@ def test_fp32_precision_matches_oracle(name, batch):
 
 
 @pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1), ("acdc_b1", 1), ("acdc_b5", 1),
-                                        ("acdc_add", 1), ("synapse_uprb", 1)])
+                                        ("acdc_add", 1), ("synapse_uprb", 1), ("acdc_uptc", 1)])
 def test_bf16_precision_matches_oracle(name, batch):
     m, x, y_ref, taps_ref = build(name, batch)
     y, taps = run_with_taps(m, x, "bf16")
@@ -99,7 +99,7 @@ def test_bf16_precision_matches_oracle(name, batch):
 
 
 @pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1), ("acdc_b1", 1), ("acdc_b5", 1),
-                                        ("acdc_add", 1), ("synapse_uprb", 1)])
+                                        ("acdc_add", 1), ("synapse_uprb", 1), ("acdc_uptc", 1)])
 def test_against_reference_golden(name, batch):
     """The committed outputs of the reference itself (tests/golden/model_*.pt)."""
     g = torch.load(os.path.join(GOLDEN, f"model_{name}_b{batch}.pt"), weights_only=False)

@@ -58,7 +58,7 @@ def _dump(tag, rows):
 
 
 @pytest.mark.parametrize("name,batch,size", [("acdc", 2, 224), ("synapse", 2, 96), ("skin", 2, 96), ("acdc_b1", 2, 96),
-                                             ("acdc_add", 2, 96), ("synapse_uprb", 2, 64)])   # (uprb at 96: a max-pool near-tie makes even the fp32 emulation differ by 3e-3)
+                                             ("acdc_add", 2, 96), ("synapse_uprb", 2, 64), ("acdc_uptc", 2, 64)])   # (uprb at 96: a max-pool near-tie makes even the fp32 emulation differ by 3e-3)
 def test_train_step_fp32_matches_oracle_autograd(name, batch, size):
     kw, sd, x, labels, loss_ref, logits_ref, gref = _ref(name, batch, size)
     m, eng = _engine(name, "fp32", sd)

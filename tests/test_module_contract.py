@@ -74,6 +74,9 @@ def test_error_conventions():
     CENet(encoder="not_an_encoder")                                    # encoder.py:48-52: silent fallback to b2
     with pytest.raises(NotImplementedError):
         CENet(encoder="pvt_v2_b0")                                     # widths 32..256: not built
+    for kind in ("uprb", "uptc", "upcn", "eucb"):                      # decoders.py:47-60: all four up blocks construct
+        CENet(dec_up_block=kind, out_up_block=kind)
+    CENet(skip_mode="add", out_merge_mode="add")
     n1 = sum(p.numel() for p in CENet(encoder="pvt_v2_b1").backbone.parameters())
     n3 = sum(p.numel() for p in CENet(encoder="pvt_v2_b3").backbone.parameters())
     assert n1 < n3                                                     # pvtv2.py:392-413: depths (2,2,2,2) vs (3,4,18,3)

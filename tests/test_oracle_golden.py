@@ -103,7 +103,7 @@ def test_boundary_dou_loss(golden_loss_boundary):
 
 
 @pytest.mark.parametrize("name,batch", [("acdc", 1), ("synapse", 2), ("skin", 1), ("acdc_b1", 1), ("acdc_b5", 1),
-                                        ("acdc_add", 1), ("synapse_uprb", 1)])
+                                        ("acdc_add", 1), ("synapse_uprb", 1), ("acdc_uptc", 1)])
 def test_whole_model(name, batch):
     """Rebuild the deterministic weights, run the oracle, compare with what the reference produced."""
     from cenet_b200.networks import CENet

@@ -46,7 +46,7 @@ def _oracle_grads(sd, kw, x, labels):
 
 @pytest.mark.parametrize("name,batch,size,flash", [("acdc", 2, 64, False), ("synapse", 2, 64, True), ("skin", 2, 64, True),
                                                    ("acdc", 1, 224, True), ("acdc_add", 2, 64, True),
-                                                   ("synapse_uprb", 2, 64, True), ("acdc_b1", 2, 64, True)])
+                                                   ("synapse_uprb", 2, 64, True), ("acdc_b1", 2, 64, True), ("acdc_uptc", 2, 64, True)])
 def test_train_step_matches_oracle_autograd(name, batch, size, flash):
     m, eng, sd, kw = _build(name, flash)
     x = fixtures.synth_input(name, batch, size=size)
