@@ -78,7 +78,7 @@ _SIGS = {
     "cenet_srm_gate": [vp, vp, vp, vp, f32, f32, i32, i32, i32, vp],
     "cenet_pool_branch": [vp, i32, ll, i32, vp, i32, ll, i32, vp, vp, vp, f32, vp, i32, i32, i32, i32, vp],
     "cenet_stem5x5": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp],
-    "cenet_head_upsample_argmax": [vp, vp, vp, i32, i32, i32, i32, vp],
+    "cenet_head_upsample_argmax": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "cenet_dice_ce": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, vp],
     "cenet_seg_loss": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp],
     # ---- training (see include/cenet_b200.h) ----

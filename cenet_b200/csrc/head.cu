@@ -10,7 +10,7 @@ constexpr int kMaxCls = 16;
 template <int NC>
 __global__ void __launch_bounds__(256) head_upsample_argmax_kernel(const float* __restrict__ y, float* __restrict__ logits,
                                                                    long long* __restrict__ labels, int B, int h, int w,
-                                                                   int ncls_rt) {
+                                                                   int ncls_rt, int ldy) {
   const int ncls = NC > 0 ? NC : ncls_rt;
   const int Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)B * Ho * Wo;
@@ -22,10 +22,10 @@ __global__ void __launch_bounds__(256) head_upsample_argmax_kernel(const float* 
   float lh, lw;
   bilin_src(ho, 0.5f, h, h0, h1, lh);
   bilin_src(wo, 0.5f, w, w0, w1, lw);
-  const float* p00 = y + ((b * h + h0) * w + w0) * ncls;
-  const float* p01 = y + ((b * h + h0) * w + w1) * ncls;
-  const float* p10 = y + ((b * h + h1) * w + w0) * ncls;
-  const float* p11 = y + ((b * h + h1) * w + w1) * ncls;
+  const float* p00 = y + ((b * h + h0) * w + w0) * ldy;
+  const float* p01 = y + ((b * h + h0) * w + w1) * ldy;
+  const float* p10 = y + ((b * h + h1) * w + w0) * ldy;
+  const float* p11 = y + ((b * h + h1) * w + w1) * ldy;
   float v[NC > 0 ? NC : kMaxCls];
   float mx = -INFINITY;
 #pragma unroll
@@ -215,16 +215,18 @@ __global__ void __launch_bounds__(256) seg_loss_grad_kernel(const float* __restr
 }  // namespace
 
 extern "C" int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w,
-                                          int ncls, cenet_stream_t s) {
+                                          int ncls, int ldy, cenet_stream_t s) {
   if (B == 0) return 0;
   CENET_REQUIRE(y && (logits_nchw || labels), "cenet_head_upsample_argmax: null pointer");
   CENET_REQUIRE(ncls >= 1 && ncls <= kMaxCls, "cenet_head_upsample_argmax: 1..%d classes supported, got %d", kMaxCls, ncls);
+  if (ldy <= 0) ldy = ncls;
+  CENET_REQUIRE(ldy >= ncls, "cenet_head_upsample_argmax: pitch %d < %d classes", ldy, ncls);
   const long long total = (long long)B * 4 * h * w;
   const int grid = cdiv(total, 256);
-  if (ncls == 9) head_upsample_argmax_kernel<9><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls);
-  else if (ncls == 4) head_upsample_argmax_kernel<4><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls);
-  else if (ncls == 2) head_upsample_argmax_kernel<2><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls);
-  else head_upsample_argmax_kernel<0><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls);
+  if (ncls == 9) head_upsample_argmax_kernel<9><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls, ldy);
+  else if (ncls == 4) head_upsample_argmax_kernel<4><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls, ldy);
+  else if (ncls == 2) head_upsample_argmax_kernel<2><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls, ldy);
+  else head_upsample_argmax_kernel<0><<<grid, 256, 0, to_stream(s)>>>(y, logits_nchw, labels, B, h, w, ncls, ldy);
   CENET_LAUNCH_CHECK("head_upsample_argmax");
   return 0;
 }

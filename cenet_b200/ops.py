@@ -318,10 +318,11 @@ def stem5x5(x, w1, b1, w3, b3, o1, r, B, H, W, Cin, slope):
 
 
 # ------------------------------------------------------------------------------------------------------ head / loss
-def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
+def head_upsample_argmax(y, logits, labels, B, h, w, ncls, ldy=0):
+    """ldy: pixel pitch of y in elements (0 = ncls)"""
     if labels is not None and labels.dtype != torch.int64:
         raise TypeError("labels must be int64")
-    L.call("cenet_head_upsample_argmax", _f32(y, "y"), _f32(logits, "logits"), _p(labels), B, h, w, ncls, _stream())
+    L.call("cenet_head_upsample_argmax", _f32(y, "y"), _f32(logits, "logits"), _p(labels), B, h, w, ncls, ldy, _stream())
 
 
 def volume_labels_counts(pred_patch, iy, ix, label, pred_out, counts, ncls):

@@ -186,9 +186,10 @@ int cenet_stem5x5(const void* x, int x_dtype, const float* w1, const float* b1, 
                   void* o1, void* r, int o_dtype, int B, int H, int W, int Cin, float slope, cenet_stream_t s);
 
 /* ---- head (out.py:74 + metrics_eval.py:52) -------------------------------------------------------------------
- * y: [B,h,w,ncls] fp32 (NHWC) -> logits [B,ncls,2h,2w] fp32 (bilinear x2, align_corners=False) and / or
+ * y: [B,h,w,ncls] fp32 (NHWC, pixel pitch ldy >= ncls; 0 = ncls: the inference plan pads the class dimension to a multiple of 8 so
+ * that the producing 1x1 conv stays on the vector epilogue) -> logits [B,ncls,2h,2w] fp32 (bilinear x2, align_corners=False) and / or
  * labels [B,2h,2w] int64 = argmax over classes, lowest index on ties.  Either output may be NULL. */
-int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls,
+int cenet_head_upsample_argmax(const float* y, float* logits_nchw, long long* labels, int B, int h, int w, int ncls, int ldy,
                                cenet_stream_t s);
 
 /* ---- tcgen05 flash attention, head width 64 or 128, or ONE head of width 192..1024 (multiple of 64; lse must be NULL)

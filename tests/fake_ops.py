@@ -368,9 +368,10 @@ def stem5x5(x, w1, b1, w3, b3, o1, r, B, H, W, Cin, slope):
     return o1, r
 
 
-def head_upsample_argmax(y, logits, labels, B, h, w, ncls):
+def head_upsample_argmax(y, logits, labels, B, h, w, ncls, ldy=0):
     _LAUNCHES[0] += 1
-    v = F.interpolate(y.view(B, h, w, ncls).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")
+    ldy = ldy or ncls
+    v = F.interpolate(_flat(y)[:B * h * w * ldy].view(B, h, w, ldy)[..., :ncls].permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")
     if logits is not None:
         logits.copy_(v)
     if labels is not None:
