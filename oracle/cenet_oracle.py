@@ -136,15 +136,22 @@ def patch_embed(sd, p, x, k, s):
     return _ln(sd, p + ".norm", y.flatten(2).transpose(1, 2), 1e-5), H, W
 
 
-def encoder(sd, cfg: Cfg, x, taps=None):
-    """pvtv2.py:312-348.  Returns the four NCHW pyramid maps."""
+def encoder(sd, cfg: Cfg, x, taps=None, drop_masks=None):
+    """pvtv2.py:312-348.  Returns the four NCHW pyramid maps.
+    drop_masks: optional [2*n_blocks, B] DropPath multipliers (0 or 1/keep; timm drop_path, pvtv2.py:146-147): row 2i scales the
+    attention branch of block i, row 2i+1 its MLP branch -- the draws a train-mode step used, so that it can be checked exactly."""
     outs = []
     B = x.shape[0]
+    bi = 0
     for s in range(4):
         k, st = (7, 4) if s == 0 else (3, 2)
         t, H, W = patch_embed(sd, f"backbone.patch_embed{s+1}", x, k, st)
         for i in range(cfg.depths[s]):
-            t = pvt_block(sd, f"backbone.block{s+1}.{i}", t, H, W, cfg.enc_heads[s], cfg.sr_ratios[s])
+            m1 = m2 = None
+            if drop_masks is not None:
+                m1, m2 = drop_masks[2 * bi].view(B, 1, 1), drop_masks[2 * bi + 1].view(B, 1, 1)
+            bi += 1
+            t = pvt_block(sd, f"backbone.block{s+1}.{i}", t, H, W, cfg.enc_heads[s], cfg.sr_ratios[s], m1, m2)
         t = _ln(sd, f"backbone.norm{s+1}", t, 1e-6)
         x = t.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
         outs.append(x)
@@ -381,20 +388,20 @@ def out_head(sd, cfg: Cfg, dec, x, training=False, taps=None):
 
 
 def cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None,
-                  new_stats: Optional[dict] = None):
+                  new_stats: Optional[dict] = None, drop_masks: Optional[Tensor] = None):
     """new_stats: dict that receives the BatchNorm buffers after one train-mode forward (only with training=True)"""
     global _STATS_SINK
     _STATS_SINK = new_stats if training else None
     try:
-        return _cenet_forward(sd, cfg, x, training, taps)
+        return _cenet_forward(sd, cfg, x, training, taps, drop_masks)
     finally:
         _STATS_SINK = None
 
 
-def _cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None):
+def _cenet_forward(sd: Dict[str, Tensor], cfg: Cfg, x: Tensor, training=False, taps: Optional[dict] = None, drop_masks=None):
     """net.py:53-64.  x: [B,Cin,H,W] fp32 -> logits [B,ncls,H,W]."""
     y = torch.cat([x, x, x], 1) if x.shape[1] == 1 else x
-    x1, x2, x3, x4 = encoder(sd, cfg, y, taps)
+    x1, x2, x3, x4 = encoder(sd, cfg, y, taps, drop_masks)
     d = decoder(sd, cfg, x4, [x3, x2, x1], training, taps)
     return out_head(sd, cfg, d, x, training, taps)
 

@@ -342,3 +342,46 @@ def test_eval_mode_backward_matches_oracle_autograd(name, batch, size, monkeypat
     for k, v in sd.items():
         if "running_" in k or "num_batches" in k:
             assert torch.equal(after[k].cpu(), v), k                   # eval mode: statistics untouched
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_with_droppath_matches_oracle_given_the_same_masks(precision):
+    """DropPath ON, as the bench runs it: the masks the step drew are read back (TrainEngine.dp_scale) and handed to the oracle.
+    fp32: loss + every gradient to 2e-3.  bf16: the product path, where the tcgen05 weight gradient runs in MASK mode (dropped
+    samples skipped, one common scale) -- gradient cosine / norm like the DropPath-free bf16 test."""
+    from cenet_b200.networks import CENet
+    from cenet_b200.train import TrainEngine
+    kw = fixtures.CONFIGS["acdc"]
+    torch.manual_seed(1234)
+    m = CENet(**kw)
+    sd = fixtures.perturb_state(m.state_dict(), 1234)
+    m.load_state_dict(sd)
+    m.backbone.drop_path_probs = [min(0.6, 4.0 * p) for p in m.backbone.drop_path_probs]
+    m = m.to(DEV).train()
+    eng = TrainEngine(m, DEV, precision)
+    eng.use_graph = False
+    batch, size = 4, 96
+    x = fixtures.synth_input("acdc", batch, size=size)
+    labels = torch.randint(0, 4, (batch, size, size), generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(11)
+    out = eng.train_step(x.to(DEV), labels.to(DEV), optimize=False)
+    torch.cuda.synchronize()
+    masks = eng.dp_scale.float().cpu().clone()
+    assert (masks == 0).any() and (masks > 1).any()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits = O.cenet_forward(leaf, O.Cfg(**kw), x, training=True, drop_masks=masks)
+    loss_ref = O.criterion_dice_ce(logits, labels, 4)
+    gref = dict(zip(names, torch.autograd.grad(loss_ref, [leaf[k] for k in names], allow_unused=True)))
+    if precision == "fp32":
+        assert abs(out[0].item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+        gn = max(g.norm().item() for g in gref.values() if g is not None)
+        bad = [(k, (eng.GP[k].cpu() - g).norm().item() / max(g.norm().item(), 1e-12)) for k, g in gref.items()
+               if g is not None and not (eng.GP[k].cpu() - g).norm().item() < 2e-3 * g.norm().item() + 1e-6 * gn]
+        assert not bad, bad[:20]
+    else:
+        assert abs(out[0].item() - loss_ref.item()) < 1e-2 * max(1.0, abs(loss_ref.item()))
+        a = torch.cat([eng.GP[k].cpu().flatten() for k, g in gref.items() if g is not None])
+        b = torch.cat([g.flatten() for g in gref.values() if g is not None])
+        cos = torch.dot(a, b) / (a.norm() * b.norm())
+        assert cos > 0.99 and abs(a.norm() / b.norm() - 1) < 0.05, (cos.item(), (a.norm() / b.norm()).item())

@@ -101,6 +101,37 @@ def test_frozen_statistics_pass_matches_oracle_eval_autograd(name, batch):
             assert torch.equal(after[k], v), k
 
 
+def test_train_step_with_droppath_matches_oracle_given_the_same_masks():
+    """DropPath ON (as in the bench): the step's own Bernoulli draws (two independent rows per block, pvtv2.py:146-147) are read
+    back and handed to the oracle; loss and every gradient must then agree -- this also drives the mask mode of the weight
+    gradient (dropped samples skipped) through the whole model."""
+    m, eng, sd, kw = _build("acdc", True)
+    eng.drop_path = True
+    m.backbone.drop_path_probs = [min(0.6, 4.0 * p) for p in m.backbone.drop_path_probs]      # enough drops at batch 4
+    eng.dp_keep = (1.0 - torch.tensor(m.backbone.drop_path_probs).repeat_interleave(2).view(-1, 1))
+    batch, size = 4, 64
+    x = fixtures.synth_input("acdc", batch, size=size)
+    labels = torch.randint(0, 4, (batch, size, size), generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(11)
+    out = eng.train_step(x, labels, optimize=False)
+    masks = eng.dp_scale.clone()
+    assert (masks == 0).any() and (masks > 1).any()
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits = O.cenet_forward(leaf, O.Cfg(**kw), x, training=True, drop_masks=masks)
+    loss_ref = O.criterion_dice_ce(logits, labels, 4)
+    gref = dict(zip(names, torch.autograd.grad(loss_ref, [leaf[k] for k in names], allow_unused=True)))
+    assert abs(out[0].item() - loss_ref.item()) < 2e-5 * max(1.0, abs(loss_ref.item()))
+    bad = []
+    for k, gr in gref.items():
+        if gr is None:
+            continue
+        err = (eng.GP[k] - gr).norm().item()
+        if not err < 2e-3 * gr.norm().item() + 1e-6:
+            bad.append((k, err, gr.norm().item()))
+    assert not bad, bad[:20]
+
+
 def test_running_stats_and_adamw_step():
     m, eng, sd, kw = _build("acdc")
     x = fixtures.synth_input("acdc", 2, size=64)
