@@ -89,6 +89,7 @@ _SIGS = {
     "cenet_wgrad_reduce_batch": [vp, i32, i32, vp],
     "cenet_colsum": [vp, i32, ll, ll, i32, vp, i32, vp, vp, ll, vp],
     "cenet_row_scale": [vp, i32, vp, vp, ll, i32, vp],
+    "cenet_droppath_mask": [vp, vp, i32, i32, C.c_ulonglong, vp, vp],
     "cenet_smallk_dgrad": [vp, i32, vp, ll, vp, i32, ll, ll, i32, i32, vp],
     "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
     "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],

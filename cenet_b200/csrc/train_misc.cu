@@ -362,6 +362,25 @@ __global__ void __launch_bounds__(256) head_upsample_bwd_kernel(const float* __r
   dyh[i] = s;
 }
 
+// DropPath masks of one training step (timm drop_path, pvtv2.py:146-147: bernoulli(keep) / keep per sample and per branch):
+// out[r, b] = u(seed, counter, r, b) < keep[r] ? 1 / keep[r] : 0 with a counter-based generator (splitmix64 finaliser); the
+// device-resident counter advances by one per launch, so every CUDA-graph replay draws fresh masks.  One block.
+__global__ void __launch_bounds__(256) droppath_mask_kernel(float* __restrict__ out, const float* __restrict__ keep, int n, int B,
+                                                            unsigned long long seed, unsigned long long* counter) {
+  const unsigned long long c = *counter;
+  for (int i = threadIdx.x; i < n * B; i += blockDim.x) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (c * 0x100000001B3ull + (unsigned long long)i + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);          // 24 random bits -> [0, 1)
+    const float k = keep[i / B];
+    out[i] = u < k ? 1.0f / k : 0.0f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *counter = c + 1ull;
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, long long n, const float* __restrict__ hyper) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step = hyper[5];
@@ -456,6 +475,14 @@ extern "C" int cenet_add(void* dst, const void* src, int dtype, long long n, int
     DISPATCH_V(Vv, (add_kernel<T, V><<<ew_blocks(n / Vv), 256, 0, to_stream(st)>>>((T*)dst, (const T*)src, n, acc)));
     CENET_LAUNCH_CHECK("add");
   });
+  return 0;
+}
+
+extern "C" int cenet_droppath_mask(float* out, const float* keep, int n, int B, unsigned long long seed, unsigned long long* counter,
+                                   cenet_stream_t st) {
+  CENET_REQUIRE(out && keep && counter && n >= 1 && B >= 1, "cenet_droppath_mask: bad arguments");
+  droppath_mask_kernel<<<1, 256, 0, to_stream(st)>>>(out, keep, n, B, seed, counter);
+  CENET_LAUNCH_CHECK("droppath_mask");
   return 0;
 }
 

@@ -167,6 +167,7 @@ class TrainEngine:
         # eval()-mode semantics inside a gradient pass (networks.CENet._EvalForward): BatchNorm uses its running statistics and
         # updates nothing, DropPath is the identity; the plan runs eagerly (no graphs are cached for this rare path)
         self.frozen_stats = False
+        self._dp_counter = self._dp_seed = None                 # DropPath generator state (device counter, seed)
         self._wg_pending, self._wg_off, self._wg_flush_idx, self._wg_tables = [], 0, 0, {}   # deferred wgrad reductions
         self.taps = None
         self.launches_per_step = None
@@ -1394,10 +1395,13 @@ class TrainEngine:
         n = 2 * len(probs)                                          # rows 2i / 2i+1: attention / MLP branch of block i
         ds = self.buf("dp_scale", (n, B), torch.float32)
         if self.drop_path and not self.frozen_stats:
-            keep = self.dp_keep
-            rnd = self.buf("dp_rand", (n, B), torch.float32)
-            rnd.uniform_()
-            ds.copy_((rnd < keep).float() / keep)                   # timm DropPath: bernoulli(keep) / keep per sample
+            # timm DropPath: bernoulli(keep) / keep per sample and branch; one kernel of the library with a device-side counter
+            # (fresh masks on every CUDA-graph replay); the seed comes from torch's generator, so `torch.manual_seed` still
+            # decides the sequence
+            if self._dp_counter is None:
+                self._dp_counter = torch.zeros(1, device=self.dev, dtype=torch.int64)
+                self._dp_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            tops.droppath_mask(ds, self.dp_keep.reshape(-1).contiguous(), n, B, self._dp_seed, self._dp_counter)
         self.dp_scale = ds
 
     def _touch_weights(self):

@@ -92,6 +92,11 @@ def colsum(x, out, *, rows, C, ld, x_off=0, row_scale=None, rs_div=1, ws=None):
     L.call("cenet_colsum", _po(x, x_off), dt(x), ld, rows, C, _f32(row_scale, "row_scale"), rs_div, _f32(out, "out"), wp, wn, _stream())
 
 
+def droppath_mask(out, keep, n, B, seed, counter):
+    """out [n, B] fp32 = bernoulli(keep[r]) / keep[r]; counter: int64 device tensor [1], advanced by the kernel"""
+    L.call("cenet_droppath_mask", _f32(out, "out"), _f32(keep, "keep"), n, B, int(seed) & 0xFFFFFFFFFFFFFFFF, _p(counter), _stream())
+
+
 def row_scale(x, rs, out, rows, C):
     """out[m, :] = x[m, :] * rs[m]   (contiguous [rows, C])"""
     L.call("cenet_row_scale", _p(x), dt(x), _f32(rs, "rs"), _p(out), rows, C, _stream())

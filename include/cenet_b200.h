@@ -285,6 +285,10 @@ int cenet_wgrad_reduce_batch(const cenet_wgrad_job* jobs, int njobs, int nblocks
  * image (rs = the image; unet.py:205-207 with input_channels = 1).  Two-stage fixed-order reduction through ws. */
 int cenet_colsum(const void* x, int dtype, long long ld, long long rows, int C, const float* row_scale, int rs_div, float* out,
                  float* ws, long long ws_elems, cenet_stream_t s);
+/* DropPath masks of one step (timm drop_path via pvtv2.py:123,146-147): out[r, b] = bernoulli(keep[r]) / keep[r], r = branch row
+ * (2 per encoder block), b = sample; counter-based generator, *counter (device) advances by one per launch */
+int cenet_droppath_mask(float* out, const float* keep, int n, int B, unsigned long long seed, unsigned long long* counter,
+                        cenet_stream_t s);
 /* out[m, c] = x[m, c] * rs[m]  (contiguous [rows, C]; the per-pixel SRM gate folded into d(fc2 output), cfam.py:157) */
 int cenet_row_scale(const void* x, int dtype, const float* rs, void* out, long long rows, int C, cenet_stream_t s);
 /* dx[m, 0:N) (+)= sum_{k<K} dy[m, k] * w[k*ldw + n]: input gradient of a layer with a tiny output width (K <= 16 classes of the

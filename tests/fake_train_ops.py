@@ -85,6 +85,14 @@ def colsum(x, out, *, rows, C, ld, x_off=0, row_scale=None, rs_div=1, ws=None):
     out.view(-1)[:C].copy_(v.sum(0))
 
 
+def droppath_mask(out, keep, n, B, seed, counter):
+    _LAUNCHES[0] += 1
+    g = torch.Generator().manual_seed(int(seed) % (2 ** 31) + int(counter.item()))
+    k = keep.view(n, 1).float().cpu()
+    out.copy_((torch.rand(n, B, generator=g) < k).float() / k)
+    counter.add_(1)
+
+
 def row_scale(x, rs, out, rows, C):
     _LAUNCHES[0] += 1
     _flat(out)[:rows * C].view(rows, C).copy_(_flat(x)[:rows * C].view(rows, C).float() * rs.view(-1)[:rows, None])

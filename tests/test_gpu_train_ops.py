@@ -199,6 +199,28 @@ def test_colsum_row_scale_smallk(dtype):
         check("smallk_dgrad", [dy, w, rn((rows, N), dtype, 5)], dict(rows=rows, K=K, N=N, ldw=N, ldx=N, acc=acc), [2], TOL[dtype])
 
 
+def test_droppath_mask_kernel():
+    """values are 0 or 1/keep, the keep rate is right, a row with keep = 1 never drops, and every launch draws a new mask"""
+    from cenet_b200 import train_ops as tops
+    n, B = 32, 4096
+    keep = torch.linspace(1.0, 0.5, n).to(DEV)
+    out = torch.empty(n, B, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    tops.droppath_mask(out, keep, n, B, 1234, counter)
+    a = out.clone()
+    tops.droppath_mask(out, keep, n, B, 1234, counter)
+    torch.cuda.synchronize()
+    assert int(counter.item()) == 2 and not torch.equal(a, out)
+    k = keep.view(n, 1)
+    assert bool(((a == 0) | ((a - 1 / k).abs() < 1e-6)).all())
+    assert bool((a[0] == 1).all())
+    rate = (a > 0).float().mean(1)
+    assert (rate - keep).abs().max().item() < 0.04                      # 4096 draws per row: sigma <= 0.008
+    counter.zero_()
+    tops.droppath_mask(out, keep, n, B, 1234, counter)
+    assert torch.equal(out, a)                                          # same (seed, counter) -> same mask
+
+
 def test_gemm_wgrad_mixed_dtypes_unscaled_bias():
     M, N, K = 5000, 4, 64                                   # head: fp32 logits gradient x bf16 activations
     dy, x = rn((M, N), F32, 1), rn((M, K), BF16, 2)
