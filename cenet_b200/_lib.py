@@ -92,7 +92,7 @@ _SIGS = {
     "cenet_droppath_mask": [vp, vp, i32, i32, C.c_ulonglong, vp, vp],
     "cenet_smallk_dgrad": [vp, i32, vp, ll, vp, i32, ll, ll, i32, i32, vp],
     "cenet_conv_wgrad": [vp, i32, ll, vp, i32, ll, i32, i32, i32, i32, i32, i32, vp, vp, ll, vp],
-    "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, vp],
+    "cenet_layernorm_bwd": [vp, vp, i32, vp, f32, ll, i32, vp, i32, vp, vp, vp, ll, C.POINTER(i32), vp],
     "cenet_bn_stats": [vp, i32, ll, ll, i32, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, ll, vp],
     "cenet_affine_act": [vp, i32, ll, vp, vp, vp, i32, ll, vp, vp, vp, i32, ll, ll, i32, i32, f32, vp],
     "cenet_bn_bwd": [vp, i32, vp, i32, ll, vp, i32, ll, vp, vp, vp, ll, i32, i32, f32, vp, i32, i32, vp, vp, vp, i32, ll,

@@ -443,9 +443,10 @@ extern "C" int cenet_bn_bwd(const void* dy, int dy_dtype, const void* y, int y_d
 
 extern "C" int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, const float* gamma, float eps, long long rows, int C,
                                    void* dx, int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems,
-                                   cenet_stream_t st) {
+                                   int* n_partials, cenet_stream_t st) {
   CENET_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && ws, "cenet_layernorm_bwd: null pointer");
   CENET_REQUIRE(C == 64 || C == 128 || C == 320 || C == 512, "cenet_layernorm_bwd: C=%d not instantiated (64/128/320/512)", C);
+  if (n_partials) *n_partials = 0;
   if (rows == 0) return 0;
   cudaStream_t s = to_stream(st);
   CENET_REQUIRE(((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx) & 15) == 0), "cenet_layernorm_bwd: rows must be 16-byte aligned");
@@ -463,5 +464,9 @@ extern "C" int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, con
   });
 #undef LN_CASE
   // ws layout per block: [2][C] = d(gamma) | d(beta)
+  if (n_partials) {                 // deferred: the caller reduces the partials with cenet_wgrad_reduce_batch (two jobs, N = 1, K = C)
+    *n_partials = nblk;
+    return 0;
+  }
   return launch_finalize(ws, nblk, 2 * C, dgamma, C, dbeta, 1.f, s);
 }

@@ -501,7 +501,8 @@ class TrainEngine:
                 raise RuntimeError("weight-gradient reduction table changed between the warm-up step and the graph capture")
             tab, nj, nb = tops.wgrad_reduce_table(jobs)
             ent = self._wg_tables[key] = (jobs, tab.to(self.dev), nj, nb)
-        self._wgrad((), lambda: tops.wgrad_reduce_batch(ent[1], ent[2], ent[3]))
+        # (registered as a READER of the workspace: a later main-stream kernel that writes partials into it waits for this launch)
+        self._wgrad((self._wg_ws(),), lambda: tops.wgrad_reduce_batch(ent[1], ent[2], ent[3]))
 
     # ------------------------------------------------------------------------------------------------ primitives
     def lin(self, x, name, out, *, M=None, N=None, K=None, lda=None, a_off=0, ldc=None, c_off=0, bias=None,
@@ -588,8 +589,20 @@ class TrainEngine:
         def bwd():
             dx = self.G(x)
             acc = self.wr(x)
-            tops.layernorm_bwd(self.G(out), x, g, eps, dx, acc, self.GP[name + ".weight"], self.GP[name + ".bias"],
-                               self._ws(0))
+            if self.dev.type == "cuda" and self.side is not None and _hazards.cur is self.side:
+                # d(gamma) / d(beta) stay as partial rows in the weight-gradient workspace: the per-bucket batched reduction on the
+                # side stream finalises them (53 finalize launches off the critical path).  The guard orders this main-stream
+                # writer after a pending reduction that still reads the workspace (`_wg_flush` registers it as a reader).
+                ws = self._wg_ws()
+                if self._wg_off + 16 * 2 * x.shape[1] * 1184 > ws.numel():
+                    self._wg_flush()
+                jobs, used = tops.layernorm_bwd(self.G(out), x, g, eps, dx, acc, self.GP[name + ".weight"], self.GP[name + ".bias"],
+                                                ws[self._wg_off:], defer=True)
+                self._wg_pending += jobs
+                self._wg_off += _rup(used, 4)
+            else:
+                tops.layernorm_bwd(self.G(out), x, g, eps, dx, acc, self.GP[name + ".weight"], self.GP[name + ".bias"],
+                                   self._ws(0))
         self.tape.append(bwd)
         return out
 

@@ -115,11 +115,19 @@ def conv_wgrad(dy, x4, dw, ksize, ws):
     L.call("cenet_conv_wgrad", _p(dy), dt(dy), N, _p(x4), dt(x4), Cin, B, H, W, Cin, ksize, N, _f32(dw, "dw"), wp, wn, _stream())
 
 
-def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws):
+def layernorm_bwd(dy, x, gamma, eps, dx, acc, dgamma, dbeta, ws, defer=False):
+    """defer: leave d(gamma) / d(beta) as partial rows in ws and return (reduction jobs for wgrad_reduce_batch, floats used)"""
     rows, Cc = x.shape
     wp, wn = _ws(ws)
+    nb = C.c_int(0)
     L.call("cenet_layernorm_bwd", _p(dy), _p(x), dt(x), _f32(gamma, "gamma"), eps, rows, Cc, _p(dx), int(acc),
-           _f32(dgamma, "dgamma"), _f32(dbeta, "dbeta"), wp, wn, _stream())
+           _f32(dgamma, "dgamma"), _f32(dbeta, "dbeta"), wp, wn, C.byref(nb) if defer else None, _stream())
+    if not defer:
+        return [], 0
+    S = nb.value
+    if S == 0:
+        return [], 0
+    return [(wp, _p(dgamma), 2 * Cc, S, 1, Cc, 1, 0), (wp + 4 * Cc, _p(dbeta), 2 * Cc, S, 1, Cc, 1, 0)], S * 2 * Cc
 
 
 # ------------------------------------------------------------------------------------------------------ BatchNorm

@@ -300,8 +300,10 @@ int cenet_smallk_dgrad(const float* dy, int K, const float* w, long long ldw, vo
 int cenet_conv_wgrad(const void* dy, int dy_dtype, long long ldy, const void* x, int x_dtype, long long ldx, int B, int H, int W,
                      int Cin, int ksize, int N, float* dw, float* ws, long long ws_elems, cenet_stream_t s);
 /* LayerNorm backward (pvtv2.py:146-147,189,320): dx (+)= ..., dgamma, dbeta; statistics are recomputed from x.  C in {64,128,320,512} */
+/* n_partials (nullable): when given, d(gamma) / d(beta) are NOT finalised: ws holds *n_partials partial rows [2][C] (d(gamma) then
+ * d(beta)) for cenet_wgrad_reduce_batch -- the 53 LayerNorm parameter gradients of a step ride in the per-bucket batched reduction */
 int cenet_layernorm_bwd(const void* dy, const void* x, int dtype, const float* gamma, float eps, long long rows, int C, void* dx,
-                        int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems, cenet_stream_t s);
+                        int acc, float* dgamma, float* dbeta, float* ws, long long ws_elems, int* n_partials, cenet_stream_t s);
 /* train-mode BatchNorm statistics of x[rows, C]: mean, rstd (biased var), scale = gamma*rstd, shift = beta - mean*scale; updates
  * running_mean / running_var (unbiased) with `momentum` and increments num_batches_tracked (all nullable) */
 /* `frozen` != 0 (here and in cenet_bn_bwd / cenet_ccu_mlp_* / cenet_srm_*): eval-mode normalisation inside a gradient-enabled pass
