@@ -989,12 +989,12 @@ class TrainEngine:
                 # mo = gm * (h2 W^T) + b: fold the per-pixel gate into d(mo) once, then the weight gradient is a plain tcgen05 GEMM
                 # (a per-row scale kept it on the mma.sync kernel) and the bias gradient a column sum of the unscaled d(mo)
                 dmo_s = self.buf(key + ".dmo_s", (M, Cc))
-                tops.row_scale(dmo, gm, dmo_s, M, Cc)
 
                 def wg():
+                    tops.row_scale(dmo, gm, dmo_s, M, Cc)
                     self._wg_gemm(dmo_s, h2, GP[q + ".fc2.weight"], M=M, N=Cc, K=4 * Cc, ldy=Cc, y_off=0, ldx=4 * Cc, x_off=0)
                     tops.colsum(dmo, GP[q + ".fc2.bias"], rows=M, C=Cc, ld=Cc, ws=self._wws())
-                self._wgrad((dmo_s, h2, dmo), wg)
+                self._wgrad((dmo, gm, h2), wg)
             else:
                 tops.gemm_wgrad(dmo, h2, GP[q + ".fc2.weight"], M=M, N=Cc, K=4 * Cc, ldy=Cc, y_off=0, ldx=4 * Cc, x_off=0,
                                 row_scale=gm, dbias=GP[q + ".fc2.bias"], bias_unscaled=True, ws=self._ws(0))
@@ -1326,10 +1326,10 @@ class TrainEngine:
         def stem_bwd():
             Kp = _rup(25 * Cin, 8)
             col = self.buf("head.rb.col", (Mf, Kp))
-            ops.im2col(xc, col, B, H, W, Cin, 5, 1, 2, H, W, Kp)
             do1, drr = self.G(o1raw), self.G(rraw)
 
             def wg():
+                ops.im2col(xc, col, B, H, W, Cin, 5, 1, 2, H, W, Kp)    # (only the weight gradient reads it: off the main stream)
                 self._wg_gemm(do1, col, GP["out.rb.0.conv1.conv.weight"], M=Mf, N=om, K=25 * Cin, ldy=om, y_off=0, ldx=Kp,
                               x_off=0, T=25)
                 if Cin == 1 and x_in.dtype == torch.float32:
