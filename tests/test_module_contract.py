@@ -1,5 +1,6 @@
 """Drop-in boundary: constructor signature, state_dict contract, host-side behaviour.  CPU-only."""
 import copy
+import os
 import inspect
 
 import pytest
@@ -86,3 +87,20 @@ def test_no_cpu_path():
     m = CENet(**fixtures.CONFIGS["acdc"]).eval()
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(torch.zeros(1, 1, 224, 224))
+
+
+def test_run_main_launcher_resolves_networks_to_the_drop_in(tmp_path):
+    """`python -m cenet_b200.run_main script.py`: a script that sits next to ANOTHER `networks` package (as the reference's mains
+    do) still gets this repo's classes"""
+    import subprocess
+    import sys
+    (tmp_path / "networks").mkdir()
+    (tmp_path / "networks" / "__init__.py").write_text("raise ImportError('the shadowed package must not be imported')\n")
+    (tmp_path / "utils_local.py").write_text("X = 7\n")
+    (tmp_path / "main_x.py").write_text("import sys\nfrom networks import CENet, CENetOrg\nimport utils_local\n"
+                                        "print('OK', CENet.__module__, CENetOrg.__module__, utils_local.X, sys.argv[1:])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "cenet_b200.run_main", str(tmp_path / "main_x.py"), "--flag", "1"], cwd=str(tmp_path),
+                       env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK cenet_b200.networks.cenet cenet_b200.networks.cenet_org 7 ['--flag', '1']" in r.stdout, r.stdout
