@@ -560,7 +560,7 @@ def run_product(args):
         value = replicas.job_throughput(BATCH, args.steps, t_dev_ms)
         e2e = replicas.job_throughput(BATCH, args.steps, t_e2e_ms)
         # ---- roofline of the dominant kernel, timed live (eager launches bracketed by CUDA events) ----
-        prof = eng.profile_ops(x_dev, labels=True, steps=2)
+        prof = eng.profile_ops(x_dev, labels=True, steps=4)
         total_ms = sum(v[0] for v in prof.values())
         by_op = {}
         for (op, tag), (ms, n) in prof.items():

@@ -101,6 +101,7 @@ _SIGS = {
     "cenet_sumpool2": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_col2im": [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "cenet_flash_fwd": [vp, ll, vp, ll, vp, ll, vp, ll, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+    "cenet_diffattn_fwd_train": [vp, vp, vp, i32, i32, i32, i32, vp, vp],
     "cenet_flash_bwd": [vp, ll, vp, ll, vp, ll, vp, vp, ll, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, ll, vp],
     "cenet_softmax_bwd_rows": [vp, vp, i32, ll, i32, vp],
     "cenet_lambda_fwd": [vp, vp, vp, vp, i32, f32, vp, vp],

@@ -12,8 +12,8 @@
 #include <type_traits>
 
 bool cenet_attn_tc_eligible(const cenet_attn_tc_args* a);   // attn_tc.cu
-int cenet_diffattn_tc(const void* qkv, void* out, int B, int N, int heads, int hd, float lambda, float eps, float mult,
-                      const float* kmax, cudaStream_t s);        // diffattn_tc.cu: 0 done, 1 not applicable, -1 error
+int cenet_diffattn_tc(const void* qkv, void* out, void* om, float* lse, int B, int N, int heads, int hd, float lambda, float eps,
+                      float mult, const float* kmax, cudaStream_t s);        // diffattn_tc.cu: 0 done, 1 not applicable, -1 error
 
 namespace {
 
@@ -607,6 +607,35 @@ static int diffattn_dispatch(const bf16* q, bf16* o, int B, int N, int heads, in
   CENET_FAIL("cenet_diffattn_flash: no kernel for padded head_dim %d / value width %d; use the materialised path", hdp, dvp);
 }
 
+static int launch_kmax(const void* qkv, float* kmax_ws, int B, int N, int E, int heads, int hd, cenet_stream_t s) {
+  const long long row = 3LL * E;
+  switch (hd) {
+    case 8: kmax_kernel<8><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+    case 16: kmax_kernel<16><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+    case 32: kmax_kernel<32><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+    default: kmax_kernel<64><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
+  }
+  CENET_LAUNCH_CHECK("diffattn_kmax");
+  return 0;
+}
+
+// Training forward of the differential attention on the tcgen05 kernel: Om[:, m*2hd : +2hd] = softmax(q_m k_m^T / sqrt(hd)) v_{m/2}
+// for the 2*heads maps of every image and lse (log2 units, [B, 2*heads, N]) for cenet_flash_bwd; qkv rows are
+// [q: 2h x hd | k: 2h x hd | v: h x 2hd] (multihead_diffattn.py:92-113).   head_dim in {8,16,32,64}.
+extern "C" int cenet_diffattn_fwd_train(const void* qkv, void* om, float* lse, int B, int N, int E, int heads, float* kmax_ws,
+                                        cenet_stream_t s) {
+  if (B == 0 || N == 0) return 0;
+  CENET_REQUIRE(qkv && om && lse, "cenet_diffattn_fwd_train: null pointer");
+  CENET_REQUIRE(heads >= 1 && E % (2 * heads) == 0, "cenet_diffattn_fwd_train: E=%d not divisible by 2*heads=%d", E, 2 * heads);
+  const int hd = E / (2 * heads);
+  CENET_REQUIRE((hd == 8 || hd == 16 || hd == 32 || hd == 64) && B <= 65535 && heads <= 65535,
+                "cenet_diffattn_fwd_train: head_dim %d has no tcgen05 instantiation (8/16/32/64); use cenet_flash_fwd", hd);
+  if (kmax_ws && launch_kmax(qkv, kmax_ws, B, N, E, heads, hd, s)) return -1;
+  const int rc = cenet_diffattn_tc(qkv, nullptr, om, lse, B, N, heads, hd, 0.f, 0.f, 1.f, kmax_ws, to_stream(s));
+  CENET_REQUIRE(rc <= 0, "cenet_diffattn_fwd_train: operands must be 16-byte aligned");
+  return rc;
+}
+
 extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, int E, int heads, float lambda, float eps,
                                     float mult, float* kmax_ws, cenet_stream_t s) {
   if (B == 0 || N == 0) return 0;
@@ -616,17 +645,8 @@ extern "C" int cenet_diffattn_flash(const void* qkv, void* out, int B, int N, in
   const int hd = E / (2 * heads);
   if (hd == 8 || hd == 16 || hd == 32 || hd == 64) {
     // tcgen05 / TMEM / TMA kernel (diffattn_tc.cu); the kmax pre-pass feeds its fixed softmax shift
-    if (kmax_ws) {
-      const long long row = 3LL * E;
-      switch (hd) {
-        case 8: kmax_kernel<8><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
-        case 16: kmax_kernel<16><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
-        case 32: kmax_kernel<32><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
-        default: kmax_kernel<64><<<dim3(2 * heads, B), 256, 0, to_stream(s)>>>((const bf16*)qkv, kmax_ws, N, row, E); break;
-      }
-      CENET_LAUNCH_CHECK("diffattn_kmax");
-    }
-    const int rc = cenet_diffattn_tc(qkv, out, B, N, heads, hd, lambda, eps, mult, kmax_ws, to_stream(s));
+    if (kmax_ws && launch_kmax(qkv, kmax_ws, B, N, E, heads, hd, s)) return -1;
+    const int rc = cenet_diffattn_tc(qkv, out, nullptr, nullptr, B, N, heads, hd, lambda, eps, mult, kmax_ws, to_stream(s));
     if (rc <= 0) return rc;
     return diffattn_dispatch((const bf16*)qkv, (bf16*)out, B, N, heads, hd, 2 * hd, hd, lambda, eps, mult, nullptr, to_stream(s));
   }

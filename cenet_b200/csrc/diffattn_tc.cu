@@ -54,6 +54,8 @@ struct DCfg {
 
 struct DaParams {
   bf16* out;
+  bf16* om;                  // training forward: per-map normalised outputs [B*N, 2*heads*DV] (then `out` is unused) ...
+  float* lse;                // ... and log2-sum-exp per (image, map, query) for the flash backward (train_attn.cu)
   const float* kmax;         // [B, 2*heads] max key norm per map, or NULL (online max everywhere)
   int N, heads;
   float scale_log2, lambda, eps, mult, dv_real;
@@ -377,6 +379,23 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       l = __uint_as_float(t[0]);
     }
     const float inv = 1.f / l;
+    if (p.om != nullptr) {
+      // training forward: every map keeps its own softmax(QK^T)V and LSE; A1 - lambda A2 + RMSNorm is a separate kernel there
+      // (lambda lives in device memory and the backward needs the per-map outputs)
+      const int n = q0 + row;
+      if (n < p.N) {
+        const int mi = 2 * head + mp;
+        bf16* op = p.om + ((long long)b * p.N + n) * (2LL * p.heads * DV) + mi * DV;
+#pragma unroll
+        for (int c = 0; c < DV; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = o[c + i] * inv;
+          stv<8>(op + c, v);
+        }
+        p.lse[((long long)b * (2 * p.heads) + mi) * p.N + n] = m + log2f(l);
+      }
+    } else {
     float* xch = reinterpret_cast<float*>(smem_raw + (sKV - smem_u32(smem_raw)));      // [DV][128] fp32 (the K/V ring is idle now)
     if (mp == 1) {
       const float f = p.lambda * inv;
@@ -404,6 +423,7 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -414,14 +434,15 @@ diffattn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 template <int HD, int PP>
-int launch(const bf16* qkv, bf16* out, int B, int N, int heads, float lambda, float eps, float mult, const float* kmax, cudaStream_t s) {
+int launch(const bf16* qkv, bf16* out, bf16* om, float* lse, int B, int N, int heads, float lambda, float eps, float mult, const float* kmax,
+           cudaStream_t s) {
   using C = DCfg<HD>;
   const long long row = 4LL * heads * HD + (long long)heads * C::DV;     // [ q: 2h x HD | k: 2h x HD | v: h x 2HD ]
   CUtensorMap tmQ, tmKV;
   if (encode3(&tmQ, qkv, row, N, B, row, (long long)N * row, 8, QT, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
   if (encode3(&tmKV, qkv, row, N, B, row, (long long)N * row, 8, KT, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
   DaParams p;
-  p.out = out; p.kmax = kmax; p.N = N; p.heads = heads;
+  p.out = out; p.om = om; p.lse = lse; p.kmax = kmax; p.N = N; p.heads = heads;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
   p.lambda = lambda; p.eps = eps; p.mult = mult; p.dv_real = (float)C::DV;
   auto kern = diffattn_tc_kernel<HD, PP>;
@@ -436,20 +457,22 @@ int launch(const bf16* qkv, bf16* out, int B, int N, int heads, float lambda, fl
 
 // Called by cenet_diffattn_flash (attn_flash.cu) for the natural (unpadded) layouts.  Returns 1 when this kernel does not
 // apply (the caller falls back to the mma.sync kernel), 0 on success, -1 on error.
-int cenet_diffattn_tc(const void* qkv, void* out, int B, int N, int heads, int hd, float lambda, float eps, float mult,
-                      const float* kmax, cudaStream_t s) {
+// `om` / `lse` non-NULL: training forward (per-map outputs + LSE instead of the combined, normalised `out`).
+int cenet_diffattn_tc(const void* qkv, void* out, void* om_, float* lse, int B, int N, int heads, int hd, float lambda, float eps,
+                      float mult, const float* kmax, cudaStream_t s) {
   static const int mode = getenv("CENET_B200_DIFFATTN_TC") ? atoi(getenv("CENET_B200_DIFFATTN_TC")) : 1;
   static const int pp = getenv("CENET_DA_TC_POLY") ? atoi(getenv("CENET_DA_TC_POLY")) : 1;
   if (mode == 0) return 1;
-  if ((((uintptr_t)qkv | (uintptr_t)out) & 15) != 0 || B > 65535 || heads > 65535) return 1;
+  if ((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)om_) & 15) != 0 || B > 65535 || heads > 65535) return 1;
   const bf16* q = (const bf16*)qkv;
   bf16* o = (bf16*)out;
+  bf16* om = (bf16*)om_;
 #define DA_GO(HD_)                                                                              \
   do {                                                                                          \
-    if (pp == 0) return launch<HD_, 0>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
-    if (pp == 1) return launch<HD_, 1>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
-    if (pp == 3) return launch<HD_, 3>(q, o, B, N, heads, lambda, eps, mult, kmax, s);          \
-    return launch<HD_, 2>(q, o, B, N, heads, lambda, eps, mult, kmax, s);                       \
+    if (pp == 0) return launch<HD_, 0>(q, o, om, lse, B, N, heads, lambda, eps, mult, kmax, s);          \
+    if (pp == 1) return launch<HD_, 1>(q, o, om, lse, B, N, heads, lambda, eps, mult, kmax, s);          \
+    if (pp == 3) return launch<HD_, 3>(q, o, om, lse, B, N, heads, lambda, eps, mult, kmax, s);          \
+    return launch<HD_, 2>(q, o, om, lse, B, N, heads, lambda, eps, mult, kmax, s);                       \
   } while (0)
   switch (hd) {
     case 8: DA_GO(8);

@@ -91,12 +91,17 @@ class _TimedOps:
             return r
         return timed
 
-    def summary(self):
-        """{(op, tag): (total ms, launches)} -- call after a synchronize."""
+    def summary(self, passes=1):
+        """{(op, tag): (total ms, launches)} -- call after a synchronize. With `passes` > 1 the records are `passes` repetitions
+        of the same launch sequence: every launch is charged the MINIMUM over its repetitions (a host hiccup that lets the
+        device run dry shows up in the events around one launch of one pass), and the totals are per `passes` passes."""
+        n1 = len(self.records) // passes
         out = {}
-        for name, tag, e0, e1 in self.records:
+        for i in range(n1):
+            name, tag = self.records[i][0], self.records[i][1]
+            ms = min(self.records[q * n1 + i][2].elapsed_time(self.records[q * n1 + i][3]) for q in range(passes))
             t, n = out.get((name, tag), (0.0, 0))
-            out[(name, tag)] = (t + e0.elapsed_time(e1), n + 1)
+            out[(name, tag)] = (t + ms * passes, n + passes)
         return out
 
 
@@ -795,6 +800,8 @@ class Engine:
         finally:
             ops = real
         self.last_gemm_work = {k: (v[0] / steps, v[1] / steps, v[2] // steps) for k, v in timed.work.items()}
-        n1 = len(timed.gemm_launches) // steps                     # per-launch list of the LAST pass
-        self.last_gemm_launches = [(op, tag, by, fl, e0.elapsed_time(e1)) for op, tag, by, fl, e0, e1 in timed.gemm_launches[-n1:]]
-        return {k: (t / steps, n // steps) for k, (t, n) in timed.summary().items()}
+        n1 = len(timed.gemm_launches) // steps
+        gl = timed.gemm_launches                                   # per-launch list: minimum over the passes
+        self.last_gemm_launches = [(gl[i][0], gl[i][1], gl[i][2], gl[i][3],
+                                    min(gl[q * n1 + i][4].elapsed_time(gl[q * n1 + i][5]) for q in range(steps))) for i in range(n1)]
+        return {k: (t / steps, n // steps) for k, (t, n) in timed.summary(steps).items()}

@@ -152,6 +152,7 @@ class TrainEngine:
         # materialised attention (batched / transposed operands): mma.sync tensor-core GEMM in bf16, CUDA cores in fp32 validation
         self.attn_gemm_impl = GEMM_MMA if precision == "bf16" else GEMM_SIMT
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
+        self.use_diffattn_tc = os.environ.get("CENET_B200_DIFFATTN_TC", "1") != "0"     # 0: per-map mma.sync flash forward
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
         self.cfg = module.cfg
         self.pvt = module.backbone.pvt_cfg                    # widths / depths / ratios of the PVTv2 variant (pvtv2.py:385-431)
@@ -735,13 +736,19 @@ class TrainEngine:
         return Ho, Wo
 
     # ---- attention ----------------------------------------------------------------------------------------------
-    def attention(self, Q, Km, V, O, *, B, maps, Nq, Nk, dqk, dv, vdiv, scale, key, ldq, qo, ldk, ko, ldv, vo, ldo, oo):
+    def attention(self, Q, Km, V, O, *, B, maps, Nq, Nk, dqk, dv, vdiv, scale, key, ldq, qo, ldk, ko, ldv, vo, ldo, oo,
+                  diff_qkv=False):
         """O[:, oo + m*dv : +dv] = softmax(scale * Q_m K_m^T) V_{m // vdiv} for m < maps, per image.
         Q_m = Q[:, qo + m*dqk : +dqk] etc.; all operands are row-major token matrices, images are consecutive row blocks."""
         flash = self.use_flash and (dqk, dv) in FLASH_DIMS
         if flash:
             lse = self.buf(key + ".lse", (B * maps * Nq,), torch.float32)
-            tops.flash_fwd(Q, Km, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo)
+            if diff_qkv and dqk in tops.DIFFATTN_TC_HEAD_DIMS and Q.dtype == torch.bfloat16 and self.use_diffattn_tc:
+                # the differential attention's own layout: all 2h maps on the tcgen05 kernel (diffattn_tc.cu, training epilogue)
+                tops.diffattn_fwd_train(Q, O, lse, B, Nq, maps * dqk, maps // 2,
+                                        self.buf(key + ".kmax", (B * maps,), torch.float32))
+            else:
+                tops.flash_fwd(Q, Km, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo)
 
             def bwd():
                 dO = self.G(O)
@@ -1183,7 +1190,7 @@ class TrainEngine:
                        wgrads=[(d + ".q_proj", 0, E), (d + ".k_proj", E, E), (d + ".v_proj", 2 * E, E)])
         Om = self.buf(key + ".Om", (M, 2 * E))
         self.attention(qkv, qkv, qkv, Om, B=B, maps=2 * heads, Nq=HW, Nk=HW, dqk=hd, dv=2 * hd, vdiv=2, scale=hd ** -0.5,
-                       key=key + ".da", ldq=3 * E, qo=0, ldk=3 * E, ko=E, ldv=3 * E, vo=2 * E, ldo=2 * E, oo=0)
+                       key=key + ".da", ldq=3 * E, qo=0, ldk=3 * E, ko=E, ldv=3 * E, vo=2 * E, ldo=2 * E, oo=0, diff_qkv=True)
         o = self.buf(key + ".o", (M, E))
         tops.diff_rmsnorm_fwd(Om, lam, o, M, heads, 2 * hd, 1e-5, 1.0 - li)
 

@@ -187,6 +187,16 @@ def flash_fwd(Q, K, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, l
            Nq, Nk, dqk, dv, vdiv, scale, _stream())
 
 
+DIFFATTN_TC_HEAD_DIMS = (8, 16, 32, 64)
+
+
+def diffattn_fwd_train(qkv, Om, lse, B, N, E, heads, kmax_ws=None):
+    """tcgen05 forward of all 2*heads softmax maps of the differential attention (per-map outputs + log2 LSE)"""
+    _bf16(qkv, Om)
+    L.call("cenet_diffattn_fwd_train", _p(qkv), _p(Om), _f32(lse, "lse"), B, N, E, heads,
+           _f32(kmax_ws, "kmax_ws") if kmax_ws is not None else None, _stream())
+
+
 def flash_bwd(Q, K, V, O, dO, lse, delta, dQ, dK, dV, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo,
               oo, ws=None):
     _bf16(Q, K, V, O, dO, dQ, dK, dV)

@@ -335,6 +335,11 @@ int cenet_col2im(const void* dcol, int c_dtype, void* dx, int x_dtype, int B, in
  * (dqk, dv) in {(8,16),(16,32),(32,64),(64,64),(128,128),(80,160)}.  Serves pvtv2.py:88-105, nlb.py:116-137, multihead_diffattn.py:92-116. */
 int cenet_flash_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O, long long ldo,
                     float* lse, int B, int maps, int Nq, int Nk, int dqk, int dv, int vdiv, float scale, cenet_stream_t s);
+/* training forward of the differential attention on the tcgen05 / TMEM / TMA kernel (diffattn_tc.cu): qkv rows
+ * [q: 2h x hd | k: 2h x hd | v: h x 2hd] (bf16, [B*N, 3E]); om [B*N, 2E] = the 2h per-map outputs softmax(q_m k_m^T / sqrt(hd)) v_{m/2},
+ * lse [B, 2h, N] in log2 units -- the operands cenet_flash_bwd and cenet_diff_rmsnorm_fwd expect.  head_dim in {8,16,32,64};
+ * kmax_ws (nullable) [B*2h] floats enables the fixed softmax shift.  multihead_diffattn.py:92-113. */
+int cenet_diffattn_fwd_train(const void* qkv, void* om, float* lse, int B, int N, int E, int heads, float* kmax_ws, cenet_stream_t s);
 /* its backward: delta = rowsum(dO*O) (workspace [B,maps,Nq]); dQ, dK, dV written with the layouts of Q, K, V (no atomics).
  * ws (nullable): fp32 scratch; with <= 64 keys (the encoder's SR attention: 49) the dK / dV kernel splits the QUERIES over CTAs and
  * a fixed-order reduction adds the partials -- 2*148 CTAs instead of B*heads. */

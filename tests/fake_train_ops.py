@@ -225,6 +225,14 @@ def flash_fwd(Q, K, V, O, lse, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, l
     _as(_flat(O), (B, maps, Nq, dv), (Nq * ldo, dv, ldo, 1), oo).copy_(torch.softmax(s, -1) @ v)
 
 
+DIFFATTN_TC_HEAD_DIMS = (8, 16, 32, 64)
+
+
+def diffattn_fwd_train(qkv, Om, lse, B, N, E, heads, kmax_ws=None):
+    hd = E // (2 * heads)
+    flash_fwd(qkv, qkv, qkv, Om, lse, B, 2 * heads, N, N, hd, 2 * hd, 2, hd ** -0.5, 3 * E, 0, 3 * E, E, 3 * E, 2 * E, 2 * E, 0)
+
+
 def flash_bwd(Q, K, V, O, dO, lse, delta, dQ, dK, dV, B, maps, Nq, Nk, dqk, dv, vdiv, scale, ldq, qo, ldk, ko, ldv, vo, ldo, oo,
               ws=None):
     _LAUNCHES[0] += 3

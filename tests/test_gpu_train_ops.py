@@ -336,6 +336,35 @@ def test_flash_fwd_bwd(dqk, dv, vdiv, maps, Nq, Nk):
         assert rel(ga[i], ca[i]) < 2e-2, (n, rel(ga[i], ca[i]))
 
 
+@pytest.mark.parametrize("hd,heads,N,B,kmax", [(16, 4, 300, 2, True), (8, 8, 196, 3, True), (8, 8, 784, 2, False), (32, 2, 130, 2, True),
+                                               (64, 1, 257, 2, True), (16, 4, 3136, 1, True)])
+def test_diffattn_fwd_train_tc(hd, heads, N, B, kmax):
+    """training forward of the differential attention on the tcgen05 kernel: per-map outputs and log2 LSE against the emulation
+    (and against the per-map mma.sync flash forward), then the flash backward on ITS results"""
+    from cenet_b200 import train_ops as tops
+    E = 2 * heads * hd
+    maps = 2 * heads
+    qkv = rn((B * N, 3 * E), BF16, 1)
+    Om, lse = torch.zeros(B * N, 2 * E, dtype=BF16), torch.zeros(B * maps * N)
+    kw = {"kmax_ws": torch.zeros(B * maps)} if kmax else {}
+    ca, ck, ga, gk = run_pair(FT, tops, "diffattn_fwd_train", [qkv, Om, lse, B, N, E, heads], kw)
+    assert rel(ga[1], ca[1]) < 1.5e-2, rel(ga[1], ca[1])
+    assert (ga[2].cpu() / math.log2(math.e) - ca[2]).abs().max().item() < 2e-2
+    # same operands through the per-map flash forward
+    q = qkv.to(DEV)
+    O2, lse2 = torch.zeros_like(ga[1]), torch.zeros_like(ga[2])
+    tail = [B, maps, N, N, hd, 2 * hd, 2, hd ** -0.5, 3 * E, 0, 3 * E, E, 3 * E, 2 * E, 2 * E, 0]
+    tops.flash_fwd(q, q, q, O2, lse2, *tail)
+    torch.cuda.synchronize()
+    assert rel(ga[1], O2) < 1e-2 and (ga[2] - lse2).abs().max().item() < 5e-3
+    dO = rn((B * N, 2 * E), BF16, 4)
+    dq, dk, dv = torch.zeros_like(qkv), torch.zeros_like(qkv), torch.zeros_like(qkv)
+    delta = torch.zeros(B * maps * N)
+    ca, ck, ga2, gk = run_pair(FT, tops, "flash_bwd", [qkv, qkv, qkv, ga[1].cpu(), dO, ga[2].cpu(), delta, dq, dk, dv] + tail, {})
+    for i, (c0, c1) in ((7, (0, E)), (8, (E, 2 * E)), (9, (2 * E, 3 * E))):
+        assert rel(ga2[i][:, c0:c1], ca[i][:, c0:c1]) < 2e-2, (i, rel(ga2[i][:, c0:c1], ca[i][:, c0:c1]))
+
+
 @pytest.mark.parametrize("maps,Nq,Nk,B", [(1, 3136, 49, 3), (2, 784, 49, 2), (5, 300, 49, 2), (1, 1000, 64, 2)])
 def test_flash_bwd_query_split(maps, Nq, Nk, B):
     """short key sets (SR attention, 49 reduced keys): with a workspace the dK / dV kernel splits the QUERIES over CTAs and a
