@@ -569,7 +569,8 @@ def run_product(args):
         # (a) the dominant kernel of the step: gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv; every nn.Linear, 1x1,
         #     3x3 and 5x5 conv) -- all its launches of one forward, algorithmic bytes (each operand once) over the
         #     summed launch durations.  Mostly K <= 128 shapes -> HBM-bound; the tensor-pipe view is stated next to it.
-        gw = eng.last_gemm_work
+        gw = dict(eng.last_gemm_work)
+        mf_work = gw.pop("mixffn_tail", None)
         g_bytes = sum(v[0] for v in gw.values()); g_flops = sum(v[1] for v in gw.values()); g_n = sum(v[2] for v in gw.values())
         g_ms = sum(by_op.get(op, [0.0, 0])[0] for op in ("linear", "gemm", "conv_nhwc"))
         roof = None
@@ -598,6 +599,16 @@ def run_product(args):
                 worst = sorted(gl, key=lambda r: -r[4])[:16]
                 roof["top_launches"] = [{"op": op, "tag": tag, "ms": round(ms, 4), "MB": round(by / 1e6, 1), "GFLOP": round(fl / 1e9, 2),
                                          "GB/s": round(by / ms / 1e6), "TFLOP/s": round(fl / ms / 1e9, 1)} for op, tag, by, fl, ms in worst]
+        # (a2) the fused Mix-FFN tail (depthwise 3x3 + GELU -> fc2 MMAs + residual, mixffn_tc.cu): HBM view on its algorithmic bytes
+        roof_mf = None
+        if mf_work and by_op.get("mixffn_tail", [0.0, 0])[0] > 0:
+            mf_ms = by_op["mixffn_tail"][0]
+            ach = mf_work[0] / (mf_ms / 1e3) / 1e9
+            roof_mf = {"bound": "hbm", "kernel": f"mixffn_tail_kernel (tcgen05 + TMA), {mf_work[2]} launches per forward", "achieved": ach,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "ms_per_launch": mf_ms / mf_work[2],
+                       "share_of_step": mf_ms / total_ms, "bytes_per_launch": mf_work[0] / mf_work[2],
+                       "note": "replaces dwconv3x3 + the fc2 GEMM of the stage-1/2 encoder blocks; CUDA-core bound "
+                               "(~27 instructions per depthwise output), see DESIGN.md 4a"}
         # (b) the largest single launch: differential flash attention of the 56x56 DSE block (exp-bound)
         E1, N1 = 128, (SIZE // 4) ** 2
         ms_da, n_da = prof.get(("diffattn_flash", "se1"), (None, 0))
@@ -625,6 +636,7 @@ def run_product(args):
             "clocks": clocks.summary(),
             "roofline": roof,
             "roofline_attention": roof_attn,
+            "roofline_mixffn": roof_mf,
             "sustained": {"steps": n_sus, "value": replicas.job_throughput(BATCH, n_sus, t_sus_ms), "unit": UNIT,
                           "ms_per_step": t_sus_ms / n_sus},
             "latency_b1": latency_b1,

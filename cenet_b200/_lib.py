@@ -59,6 +59,7 @@ _SIGS = {
     "cenet_layernorm": [vp, i32, vp, i32, vp, vp, ll, i32, f32, vp],
     "cenet_softmax_rows": [vp, i32, ll, i32, ll, vp],
     "cenet_row_stats": [vp, i32, ll, i32, ll, i32, vp, vp],
+    "cenet_mixffn_tail": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "cenet_dwconv3x3": [vp, i32, ll, vp, i32, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
     "cenet_nhwc_to_nchw": [vp, i32, ll, vp, i32, i32, i32, i32, i32, i32, vp],
     "cenet_nchw_to_nhwc": [vp, i32, vp, i32, ll, i32, i32, i32, vp],
@@ -136,6 +137,7 @@ _SIGS = {
 _PLAIN = {  # no stream, different return types
     "cenet_last_error": ([], C.c_char_p),
     "cenet_abi_version": ([], i32),
+    "cenet_mixffn_tail_supported": ([i32, i32, i32, i32], i32),
     "cenet_launch_count": ([], ll),
     "cenet_ccu_nchunk": ([i32], i32),
     "cenet_loss_nblocks": ([ll], i32),

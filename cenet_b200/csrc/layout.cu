@@ -149,6 +149,34 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, T
   }
 }
 
+// Few input channels (the 1- or 3-channel image: patch_embed1 7x7 s4, the 5x5 stem of the output head in training): a V-wide vector
+// of the generic kernel would be one element (V divides Cin), i.e. one 64-bit index decomposition and one 2-byte store per
+// element.  Here a thread produces 8 consecutive k of one output row: one decomposition, 8 scalar gathers (L1), one 16-byte store.
+template <typename TI>
+__global__ void __launch_bounds__(256) im2col_gather8_kernel(const TI* __restrict__ x, bf16* __restrict__ out, int B, int H, int W,
+                                                             int Cin, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int kv = Kpad >> 3;
+  const int K = KH * KW * Cin;
+  const long long total = (long long)B * Ho * Wo * kv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / kv;
+    const int k0 = (int)(idx - m * kv) * 8;
+    const int mi = (int)m;                                   // B * Ho * Wo < 2^31 (checked by the launcher)
+    const int wo = mi % Wo, t = mi / Wo, ho = t % Ho, b = t / Ho;
+    int ci = k0 % Cin, tap = k0 / Cin, kw = tap % KW, kh = tap / KW;
+    const int hb = ho * stride - pad, wb = wo * stride - pad;
+    const TI* xb = x + (long long)b * H * W * Cin;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int h = hb + kh, w = wb + kw;
+      v[i] = (k0 + i < K && h >= 0 && h < H && w >= 0 && w < W) ? ldf(xb + ((long long)h * W + w) * Cin + ci) : 0.f;
+      if (++ci == Cin) { ci = 0; if (++kw == KW) { kw = 0; kh++; } }
+    }
+    stv<8>(out + m * Kpad + k0, v);
+  }
+}
+
 inline int ew_grid(long long total) { return (int)std::min<long long>(cdiv(total, 256), (long long)kNumSMs * 32); }
 }  // namespace
 
@@ -232,6 +260,12 @@ extern "C" int cenet_im2col(const void* x, int x_dtype, void* out, int o_dtype, 
   int V = pick_vec({Cin, Kpad});
   const int maxv = (x_dtype == CENET_F32 || o_dtype == CENET_F32) ? 4 : 8;
   const long long total = (long long)B * Ho * Wo * Kpad;
+  if (V < 4 && o_dtype == CENET_BF16 && Kpad % 8 == 0 && (((uintptr_t)out) & 15) == 0 && (long long)B * Ho * Wo < (1LL << 31)) {
+    CENET_DISPATCH(x_dtype, TI, (im2col_gather8_kernel<TI><<<ew_grid(total / 8), 256, 0, to_stream(s)>>>(
+        (const TI*)x, (bf16*)out, B, H, W, Cin, KH, KW, stride, pad, Ho, Wo, Kpad)));
+    CENET_LAUNCH_CHECK("im2col_gather8");
+    return 0;
+  }
   DISPATCH_V(V, maxv, CENET_DISPATCH(x_dtype, TI, CENET_DISPATCH(o_dtype, TO,
       (im2col_kernel<TI, TO, VV><<<ew_grid(total / VV), 256, 0, to_stream(s)>>>((const TI*)x, (TO*)out, B, H, W, Cin, KH, KW,
                                                                                stride, pad, Ho, Wo, Kpad)))));

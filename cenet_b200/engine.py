@@ -73,7 +73,7 @@ class _TimedOps:
 
     def __getattr__(self, name):
         fn = getattr(self._inner, name)
-        if not callable(fn) or name in ("ccu_nchunk", "loss_nblocks", "launch_count", "dt"):
+        if not callable(fn) or name in ("ccu_nchunk", "loss_nblocks", "launch_count", "dt", "mixffn_tail_supported"):
             return fn
 
         def timed(*a, **k):
@@ -82,6 +82,11 @@ class _TimedOps:
             r = fn(*a, **k)
             e1.record()
             self.records.append((name, self.tag, e0, e1))
+            if name == "mixffn_tail":                         # algorithmic bytes: hidden once + residual stream read and written + weights
+                B_, H_, W_, Ch_, Cc_ = a[6:11]
+                acc = self.work.setdefault(name, [0.0, 0.0, 0])
+                acc[0] += B_ * H_ * W_ * (Ch_ * 2 + 2 * Cc_ * 4) + Ch_ * Cc_ * 2 + 10 * Ch_ * 4
+                acc[1] += 2.0 * B_ * H_ * W_ * Ch_ * (Cc_ + 9); acc[2] += 1
             if name in ("linear", "gemm", "conv_nhwc"):
                 wk = self._gemm_work(name, a, k)
                 if wk is not None:
@@ -125,6 +130,7 @@ class Engine:
         self._tables = {}                                   # resampling tap tables (zero insertion of the uptc up block)
         self.use_flash = precision == "bf16" and os.environ.get("CENET_B200_ATTN", "flash") == "flash"
         self.use_graph = os.environ.get("CENET_B200_GRAPH", "1") == "1"
+        self.fuse_mixffn = precision == "bf16" and os.environ.get("CENET_B200_MIXFFN_FUSED", "1") != "0"
         self.cfg = module.cfg
         self.pvt = module.backbone.pvt_cfg                    # widths / depths / ratios of the PVTv2 variant (pvtv2.py:385-431)
         self.w = {}
@@ -448,7 +454,9 @@ class Engine:
             q = self.buf(f"enc{s}.q", (Mtok, Cc))
             att = self.buf(f"enc{s}.att", (Mtok, Cc))
             h1 = self.buf(f"enc{s}.h1", (Mtok, hid))
-            h2 = self.buf(f"enc{s}.h2", (Mtok, hid))
+            fuse_tail = self.fuse_mixffn and w[f"backbone.block{s+1}.0.mlp.fc2.w"].stride(0) == hid and \
+                ops.mixffn_tail_supported(H, W, hid, Cc)
+            h2 = None if fuse_tail else self.buf(f"enc{s}.h2", (Mtok, hid))
             Nk = (H // sr) * (W // sr)
             kv = self.buf(f"enc{s}.kv", (B * Nk, 2 * Cc))
             for i in range(self.pvt["depths"][s]):
@@ -467,8 +475,14 @@ class Engine:
                 self._lin(att, b + ".attn.proj", t, res1=t, ldr1=Cc)                # x += proj(attn)
                 ops.layernorm(t, xn, w[b + ".norm2.g"], w[b + ".norm2.b"], 1e-6)
                 self._lin(xn, b + ".mlp.fc1", h1)
-                ops.dwconv3x3(h1, h2, w[b + ".mlp.dw.w"], B, H, W, hid, bias=w[b + ".mlp.dw.b"], act=ACT_GELU)
-                self._lin(h2, b + ".mlp.fc2", t, res1=t, ldr1=Cc)                   # x += fc2(...)
+                if fuse_tail:
+                    # depthwise 3x3 + GELU produced straight into the A operand of the fc2 MMAs (mixffn_tc.cu): the hidden
+                    # activation (mlp_ratio x C wide) is read once and its GELU'd copy never reaches HBM
+                    ops.mixffn_tail(h1, t, w[b + ".mlp.dw.w"], w[b + ".mlp.dw.b"], w[b + ".mlp.fc2.w"], w[b + ".mlp.fc2.b"],
+                                    B, H, W, hid, Cc)
+                else:
+                    ops.dwconv3x3(h1, h2, w[b + ".mlp.dw.w"], B, H, W, hid, bias=w[b + ".mlp.dw.b"], act=ACT_GELU)
+                    self._lin(h2, b + ".mlp.fc2", t, res1=t, ldr1=Cc)               # x += fc2(...)
             f = self.buf(f"enc{s}.out", (Mtok, Cc))
             ops.layernorm(t, f, w[f"backbone.norm{s+1}.g"], w[f"backbone.norm{s+1}.b"], 1e-6)
             self._tap(f"backbone.stage{s+1}", f, B, H, W, Cc)

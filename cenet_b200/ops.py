@@ -156,6 +156,21 @@ def rmsnorm_seg(x2d, out, seg, eps, mult):
 
 
 # ------------------------------------------------------------------------------------------------------ dwconv
+def mixffn_tail_supported(H, W, Ch, Cc) -> bool:
+    return bool(L.load().cenet_mixffn_tail_supported(H, W, Ch, Cc))
+
+
+def mixffn_tail(h, t, w9c, dw_bias, w2, b2, B, H, W, Ch, Cc):
+    """t (fp32 residual stream, in place) += fc2(GELU(dwconv3x3(h) + dw_bias)) + b2 -- one tcgen05 kernel (mixffn_tc.cu)"""
+    if h.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16 or t.dtype != torch.float32:
+        raise TypeError("mixffn_tail: bf16 hidden / weight and an fp32 residual stream")
+    if w2.stride(0) != Ch or w2.shape[0] < Cc:
+        raise ValueError("mixffn_tail: w2 must be [C, Ch] with contiguous rows")
+    L.call("cenet_mixffn_tail", _p(h), _p(t), _f32(w9c, "w9c"), _f32(dw_bias, "dw_bias"), _p(w2), _f32(b2, "b2"), B, H, W, Ch, Cc,
+           _stream())
+    return t
+
+
 def dwconv3x3(x, out, w9c, B, H, W, Cc, *, ldx=None, ldy=None, x_off=0, y_off=0, bias=None, scale=None, shift=None,
               dil=1, up2=False, act=ACT_NONE, slope=0.0, zout=None):
     """H, W are OUTPUT sizes; with up2 the input is [B,H/2,W/2,C].  zout (training): contiguous [B,H,W,C] buffer that

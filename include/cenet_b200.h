@@ -88,6 +88,13 @@ int cenet_softmax_rows(void* x, int dtype, long long rows, int n, long long ld, 
 int cenet_row_stats(const void* x, int dtype, long long rows, int C, long long ld, int unbiased, float* stats,
                     cenet_stream_t s);
 
+/* Mix-FFN tail in one tcgen05 kernel (mixffn_tc.cu): t[B*H*W, C] (fp32, in place) += fc2(GELU(dwconv3x3(h) + dw_bias)) + b2, with
+ * h [B,H,W,Ch] bf16 the fc1 output, w9c [9][Ch] / dw_bias [Ch] fp32 the depthwise filter, w2 [C][Ch] bf16, b2 [C] fp32 (nullable).
+ * The GELU'd depthwise result goes from registers into the shared-memory A operand of the MMA and never reaches global memory.
+ * pvtv2.py:40-47,364-370.  C in {64,128}, Ch % 64 == 0, W % 4 == 0, W <= 128: cenet_mixffn_tail_supported() answers 1. */
+int cenet_mixffn_tail_supported(int H, int W, int Ch, int C);
+int cenet_mixffn_tail(const void* h, void* t, const float* w9c, const float* dw_bias, const void* w2, const float* b2, int B, int H,
+                      int W, int Ch, int C, cenet_stream_t s);
 /* ---- depthwise 3x3 family -----------------------------------------------------------------------------
  * y[b,h,w,c] = act( (sum_taps w[tap,c]*x[b,h+dh*dil,w+dw*dil,c] + bias[c]) * scale[c] + shift[c] )
  * Mix-FFN DWConv+GELU (pvtv2.py:364-370,42-43), CFAM Mlp dwconv+GELU (cfam.py:151-152), SepConvBN depthwise

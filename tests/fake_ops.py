@@ -163,6 +163,27 @@ def dwconv3x3(x, out, w9c, B, H, W, Cc, *, ldx=None, ldy=None, x_off=0, y_off=0,
     return out
 
 
+def mixffn_tail_supported(H, W, Ch, Cc):
+    if not (W % 4 == 0 and 8 <= W <= 128 and Cc in (64, 128) and Ch % 64 == 0 and Ch >= 64 and H >= 1):
+        return False
+    TR = 128 // W
+    smem = 2 * 16384 + 2 * ((TR + 2) * (W + 2) * 128 + Cc * 128) + 10 * Ch * 4 + 256 + 1024      # ring depth 2 is the minimum
+    return smem <= 220 * 1024
+
+
+def mixffn_tail(h, t, w9c, dw_bias, w2, b2, B, H, W, Ch, Cc):
+    _LAUNCHES[0] += 1
+    xi = _flat(h)[:B * H * W * Ch].view(B, H, W, Ch).float().permute(0, 3, 1, 2)
+    v = F.gelu(F.conv2d(xi, w9c.t().reshape(Ch, 1, 3, 3), dw_bias, padding=1, groups=Ch))
+    a = v.permute(0, 2, 3, 1).reshape(B * H * W, Ch).to(h.dtype).float()
+    y = a @ w2[:Cc, :Ch].float().t()
+    if b2 is not None:
+        y = y + b2
+    tv = _flat(t)[:B * H * W * Cc].view(B * H * W, Cc)
+    tv.add_(y.to(tv.dtype))
+    return t
+
+
 def nhwc_to_nchw(x, out, B, HW, Cc, Ctot, coff, ldx=None):
     _LAUNCHES[0] += 1
     ldx = Cc if ldx is None else ldx

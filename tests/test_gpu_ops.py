@@ -138,6 +138,28 @@ def test_conv_strided_simt_and_im2col():
     assert torch.equal(col2, ref2)
 
 
+@pytest.mark.parametrize("Cin,k,st,pd,H,W,in_dt", [(1, 7, 4, 3, 64, 64, "f32"), (3, 7, 4, 3, 36, 44, "bf16"), (1, 5, 1, 2, 24, 40, "bf16"),
+                                                     (3, 5, 1, 2, 17, 23, "f32"), (2, 3, 2, 1, 16, 16, "bf16")])
+def test_im2col_few_channels(Cin, k, st, pd, H, W, in_dt):
+    """the gather-8 im2col (1- / 3-channel images: patch_embed1, the 5x5 stem in training): bit-exact against F.unfold of the
+    bf16-rounded input, zero padding of the K tail included"""
+    from cenet_b200 import ops
+    B = 2
+    Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
+    K = k * k * Cin
+    Kp = (K + 7) // 8 * 8 + 8
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.float32 if in_dt == "f32" else torch.bfloat16)
+    col = torch.full((B * Ho * Wo, Kp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.im2col(xn, col, B, H, W, Cin, k, st, pd, Ho, Wo, Kp)
+    xr = xn.float().cpu().permute(0, 3, 1, 2)
+    u = F.unfold(xr, k, padding=pd, stride=st)                      # [B, Cin*k*k, L], rows ordered (ci, kh, kw)
+    u = u.reshape(B, Cin, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, K)        # -> (kh, kw, ci)
+    ref = torch.zeros(B * Ho * Wo, Kp)
+    ref[:, :K] = u
+    assert torch.equal(col.float().cpu(), ref.to(torch.bfloat16).float())
+
+
 def test_gemm_batched_nmajor():
     from cenet_b200 import ops
     Bt, N, d = 6, 50, 24
@@ -291,6 +313,45 @@ def test_dwconv_staged_rows(B, H, W, C, ldx, xo):
     ops.dwconv3x3(xn, y2, w9, B, H, W, C, ldx=ldx, x_off=xo, scale=sc.to(DEV), shift=sh.to(DEV), act=ops.ACT_RELU)
     ref = F.relu(F.conv2d(xr, wt, padding=1, groups=C) * sc[None, :, None, None] + sh[None, :, None, None])
     assert rel(y2, ref.permute(0, 2, 3, 1)) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,Ch,C", [(2, 56, 56, 512, 64), (3, 28, 28, 1024, 128), (2, 7, 28, 256, 128), (1, 5, 128, 128, 64),
+                                        (2, 9, 64, 320, 128), (1, 3, 8, 64, 64), (2, 13, 12, 192, 64)])
+def test_mixffn_tail(B, H, W, Ch, C):
+    """fused Mix-FFN tail (depthwise 3x3 + GELU produced into the A operand of the fc2 tcgen05 MMAs): against plain torch fp32
+    on the same bf16 inputs, against the unfused kernels (dwconv3x3 + linear), bit-identical run to run; image heights that
+    are not a multiple of the CTA's row band, one- and two-CTA-per-SM shared-memory footprints"""
+    from cenet_b200 import ops
+    assert ops.mixffn_tail_supported(H, W, Ch, C)
+    M = B * H * W
+    h = torch.randn(B, H, W, Ch, generator=g(1)).to(DEV, torch.bfloat16)
+    wt = torch.randn(Ch, 1, 3, 3, generator=g(2)) / 3
+    bdw = torch.randn(Ch, generator=g(3))
+    w2 = (torch.randn(C, Ch, generator=g(4)) / math.sqrt(Ch)).to(DEV, torch.bfloat16)
+    b2 = torch.randn(C, generator=g(5))
+    t0 = torch.randn(M, C, generator=g(6))
+    w9 = wt.reshape(Ch, 9).t().contiguous().to(DEV)
+    t = t0.clone().to(DEV)
+    ops.mixffn_tail(h, t, w9, bdw.to(DEV), w2, b2.to(DEV), B, H, W, Ch, C)
+    torch.cuda.synchronize()
+    a = F.gelu(F.conv2d(h.float().cpu().permute(0, 3, 1, 2), wt, bdw, padding=1, groups=Ch)).permute(0, 2, 3, 1).reshape(M, Ch)
+    ref = t0 + a.to(torch.bfloat16).float() @ w2.float().cpu().t() + b2
+    e = rel(t, ref)
+    record(f"mixffn_tail_{H}x{W}x{Ch}x{C}", e)
+    assert e < 3e-3, e
+    # the unfused kernels on the same operands
+    h2 = torch.empty(M, Ch, device=DEV, dtype=torch.bfloat16)
+    t2 = t0.clone().to(DEV)
+    ops.dwconv3x3(h, h2, w9, B, H, W, Ch, bias=bdw.to(DEV), act=ops.ACT_GELU)
+    ops.linear(h2, w2, t2, bias=b2.to(DEV), res1=t2, ldr1=C)
+    assert rel(t, t2) < 1e-3, rel(t, t2)
+    for _ in range(2):
+        t3 = t0.clone().to(DEV)
+        ops.mixffn_tail(h, t3, w9, bdw.to(DEV), w2, b2.to(DEV), B, H, W, Ch, C)
+        assert torch.equal(t, t3)
+    t4 = t0.clone().to(DEV)                                         # no fc2 bias
+    ops.mixffn_tail(h, t4, w9, bdw.to(DEV), w2, None, B, H, W, Ch, C)
+    assert rel(t4.cpu() + b2, ref) < 3e-3
 
 
 def test_layout_ops():

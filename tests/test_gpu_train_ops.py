@@ -350,6 +350,8 @@ def test_diffattn_fwd_train_tc(hd, heads, N, B, kmax):
     ca, ck, ga, gk = run_pair(FT, tops, "diffattn_fwd_train", [qkv, Om, lse, B, N, E, heads], kw)
     assert rel(ga[1], ca[1]) < 1.5e-2, rel(ga[1], ca[1])
     assert (ga[2].cpu() / math.log2(math.e) - ca[2]).abs().max().item() < 2e-2
+    if hd == 64:
+        return                                                       # (64, 128) has no mma.sync flash instantiation to compare with
     # same operands through the per-map flash forward
     q = qkv.to(DEV)
     O2, lse2 = torch.zeros_like(ga[1]), torch.zeros_like(ga[2])
