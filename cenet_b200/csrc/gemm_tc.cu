@@ -120,7 +120,8 @@ struct TcParams {
   int w_resident;    // the whole [bn x K] weight slice stays in shared memory for the CTA's lifetime
   int n_epi;         // epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating column chunks)
   // conv mode
-  int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;
+  int conv, H, W, Cin, KH, KW, pad, tiles_h, tiles_w, cblks;   // H, W: OUTPUT extent (= input extent for the stride-1 'same' convs)
+  int stride;        // conv stride: the tap boxes are TMA boxes with element strides (stride, stride) over the input image
   int tile_h, tile_w;  // M tile in pixels: 8 x 16 (shifted boxes) or 16 x 8 (halo mode)
   int tw_shift;        // log2(tile_w)
   int halo, Hh, Wh;    // halo mode: halo tile extent
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS_P, 1) gemm_tc_kernel(const __grid_con
           const uint32_t sa = ring_base + s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), a_bytes + (p.w_resident ? 0 : w_bytes));
           if (p.conv) {
-            tma_load_4d(sa, &tmA, full_bar(s), cb * p.bk, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            tma_load_4d(sa, &tmA, full_bar(s), cb * p.bk, w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
             if (!p.w_resident) tma_load_2d(sa + a_bytes, &tmW, full_bar(s), tap * p.Cin + cb * p.bk, n0);
             if (++cb == p.cblks) { cb = 0; tap++; if (++kw == p.KW) { kw = 0; kh++; } }
           } else {
@@ -616,10 +617,11 @@ EncodeTiledFn get_encode() {
 }
 
 int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, CUtensorMapSwizzle swz) {
+               const cuuint32_t* box, CUtensorMapSwizzle swz, int pixel_stride = 1) {
   EncodeTiledFn enc = get_encode();
   CENET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (pixel_stride > 1) estr[1] = estr[2] = (cuuint32_t)pixel_stride;     // strided conv: every stride-th pixel of the W / H box extent
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -641,8 +643,15 @@ bool cenet_gemm_tc_eligible(const cenet_gemm_args* a) {
   if (a->w_nmajor || a->a_mmajor || a->k_scale || a->batch != 1) return false;
   if (a->ldw % 8 != 0 || ((uintptr_t)a->Wt & 15)) return false;
   if (a->conv) {
-    // stride-1 "same" convolutions whose channel count fills a swizzle atom
-    if (a->stride != 1 || a->KH != a->KW || a->pad != a->KH / 2 || a->Ho != a->H || a->Wo != a->W) return false;
+    // square filters whose channel count fills a swizzle atom: stride-1 "same" convolutions, and strided ones (patch embeds 3x3 s2,
+    // SR convs k = s; pvtv2.py:164-165, 68) through element-strided TMA boxes
+    if (a->KH != a->KW || a->stride < 1) return false;
+    if (a->stride == 1) {
+      if (a->pad != a->KH / 2 || a->Ho != a->H || a->Wo != a->W) return false;
+    } else {
+      if (a->Ho != (a->H + 2 * a->pad - a->KH) / a->stride + 1 || a->Wo != (a->W + 2 * a->pad - a->KW) / a->stride + 1) return false;
+      if ((TILE_W - 1) * a->stride + 1 > 256 || a->Cin % 64 != 0 || a->Ho < 1 || a->Wo < 1) return false;
+    }
     if (!(a->Cin == 32 || a->Cin % 64 == 0)) return false;
     if (a->lda != a->Cin || ((uintptr_t)a->A & 15)) return false;
     return true;
@@ -683,7 +692,7 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
   p.epi = make_epi(a);
   CUtensorMap tmA, tmW;
   if (a->conv) {
-    p.H = a->H; p.W = a->W; p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.pad = a->pad;
+    p.H = a->Ho; p.W = a->Wo; p.Cin = a->Cin; p.KH = a->KH; p.KW = a->KW; p.pad = a->pad; p.stride = a->stride;
     p.bk = a->Cin == 32 ? 32 : 64;
     p.cblks = a->Cin / p.bk;
     p.num_kb = a->KH * a->KW * p.cblks;
@@ -692,12 +701,12 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     const int wblk_h = ((pick_bn(a->N) * p.bk * 2) + 1023) & ~1023;
     // measured (tools/one_conv.py, B=64): 5x5 32->32 0.79 -> 0.67 ms, 3x3 64->32 0.186 -> 0.176 ms, but 3x3 64->64 0.307 -> 0.336 ms
     // (its 72 KB filter bank leaves room for one CTA per SM only) -> halo mode for narrow outputs (N <= 32)
-    p.halo = halo_on && a->KH > 1 && a->Cin % 16 == 0 && a->Cin <= 128 && pick_bn(a->N) <= 32 && a->N <= 32 &&
+    p.halo = halo_on && a->stride == 1 && a->KH > 1 && a->Cin % 16 == 0 && a->Cin <= 128 && pick_bn(a->N) <= 32 && a->N <= 32 &&
              (long long)p.num_kb * wblk_h <= 120 * 1024;
     p.tile_h = p.halo ? 16 : TILE_H; p.tile_w = p.halo ? 8 : TILE_W; p.tw_shift = p.halo ? 3 : 4;
     p.Hh = p.tile_h + 2 * a->pad; p.Wh = p.tile_w + 2 * a->pad;
     p.ablk = (p.Hh * p.Wh * 16 + 127) & ~127;
-    p.tiles_h = cdiv(a->H, p.tile_h); p.tiles_w = cdiv(a->W, p.tile_w);
+    p.tiles_h = cdiv(a->Ho, p.tile_h); p.tiles_w = cdiv(a->Wo, p.tile_w);
     p.num_m_tiles = a->Bimg * p.tiles_h * p.tiles_w;
     const CUtensorMapSwizzle swz = p.bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t dims[4] = {(cuuint64_t)a->Cin, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->Bimg};
@@ -706,15 +715,15 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
       cuuint32_t box[4] = {8, (cuuint32_t)p.Wh, (cuuint32_t)p.Hh, 1};
       if (encode_map(&tmA, a->A, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     } else {
-      cuuint32_t box[4] = {(cuuint32_t)p.bk, TILE_W, TILE_H, 1};
-      if (encode_map(&tmA, a->A, 4, dims, str, box, swz)) return -1;
+      cuuint32_t box[4] = {(cuuint32_t)p.bk, (cuuint32_t)((TILE_W - 1) * a->stride + 1), (cuuint32_t)((TILE_H - 1) * a->stride + 1), 1};
+      if (encode_map(&tmA, a->A, 4, dims, str, box, swz, a->stride)) return -1;
     }
     cuuint64_t wd[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N};
     cuuint64_t ws[1] = {(cuuint64_t)a->ldw * 2};
     cuuint32_t wb[2] = {(cuuint32_t)p.bk, (cuuint32_t)p.bn};
     if (encode_map(&tmW, a->Wt, 2, wd, ws, wb, swz)) return -1;
   } else {
-    p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0;
+    p.H = p.W = p.Cin = p.KH = p.KW = p.pad = p.tiles_h = p.tiles_w = p.cblks = 0; p.stride = 1;
     p.halo = 0; p.Hh = p.Wh = p.ablk = 0; p.tile_h = TILE_H; p.tile_w = TILE_W; p.tw_shift = 4;
     p.bk = 64;
     p.num_kb = cdiv(a->K, 64);
@@ -737,7 +746,8 @@ int cenet_gemm_tc(const cenet_gemm_args* a, cudaStream_t s) {
     const bool plain_epi = a->c_dtype == CENET_BF16 && a->alpha == 1.0f && !a->row_scale && !a->post_row_scale && !a->bias_per_row &&
                            a->act == CENET_ACT_NONE && !a->mul && !a->res1 && !a->res2 && a->N % 8 == 0 && a->ldc % 8 == 0 &&
                            (((uintptr_t)a->C & 15) == 0) && (!a->bias || (((uintptr_t)a->bias & 15) == 0));
-    if (!a->conv && a->split_ws && (((uintptr_t)a->split_ws & 15) == 0) && plain_epi && ctas * 2 <= kNumSMs && p.num_kb >= 8) {
+    // (plain GEMMs and the strided convs: few output tiles -- 7x7 tokens per image for the SR convs -- and K = k*k*Cin up to 4096)
+    if ((!a->conv || a->stride > 1) && a->split_ws && (((uintptr_t)a->split_ws & 15) == 0) && plain_epi && ctas * 2 <= kNumSMs && p.num_kb >= 8) {
       int want = (int)std::min<long long>(kNumSMs / ctas, p.num_kb / 4);            // >= 4 k-blocks (256 columns) per slice
       const long long room = a->split_ws_elems / ((long long)a->M * a->N);
       if (want > room) want = (int)room;

@@ -27,13 +27,14 @@ constexpr int MF_NTH = MF_T + 64;         // + the TMA producer warp + the MMA w
 constexpr int MF_PW = 4;                  // pixels per thread and pass
 constexpr int MF_A_BYTES = 128 * 128;     // one A tile: 128 pixels x 64 channels bf16
 constexpr int MF_MAXNR = 4;
+constexpr int MF_MAXNA = 2;               // A tiles between the depthwise warps and the MMAs (3-4 measured slower: they cost ring depth)
 
 struct MfParams {
   float* t;
   const float* w9c;    // [9][Ch]
   const float* dwb;    // [Ch]
   const float* b2;     // [C] or NULL
-  int H, W, Ch, C, TR, nch, NR, bands, ntiles;
+  int H, W, Ch, C, TR, nch, NR, NA, bands, ntiles;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -60,23 +61,23 @@ __global__ void __launch_bounds__(MF_NTH, 1) mixffn_tail_kernel(const __grid_con
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int W = p.W, H = p.H, C = p.C, Ch = p.Ch, TR = p.TR, nch = p.nch, NR = p.NR;
+  const int W = p.W, H = p.H, C = p.C, Ch = p.Ch, TR = p.TR, nch = p.nch, NR = p.NR, NA = p.NA;
   const int rowB = (W + 2) * 128;                     // one staged row: pixels -1 .. W of a 64-channel chunk
   const int ringB = (TR + 2) * rowB;                  // = the bytes of one TMA box
   const uint32_t wbytes = (uint32_t)C * 128u;
-  const uint32_t sA = sbase;                          // [2] A tiles
-  const uint32_t sW = sA + 2 * MF_A_BYTES;            // [NR] W2 slices, C rows x 128 bytes
+  const uint32_t sA = sbase;                          // [NA] A tiles
+  const uint32_t sW = sA + NA * MF_A_BYTES;            // [NR] W2 slices, C rows x 128 bytes
   const uint32_t sR = sW + NR * wbytes;               // [NR] input boxes
   const uint32_t sF = sR + NR * ringB;                // depthwise filter + bias of ALL hidden channels: [10][Ch] fp32
   const uint32_t bar = sF + 10 * Ch * 4;
   const uint32_t h_full = bar, h_empty = bar + 8 * MF_MAXNR, w_full = bar + 16 * MF_MAXNR, w_empty = bar + 24 * MF_MAXNR;
-  const uint32_t a_full = bar + 32 * MF_MAXNR, a_empty = a_full + 16, d_full = a_empty + 16, tmem_slot = d_full + 16;
+  const uint32_t a_full = bar + 32 * MF_MAXNR, a_empty = a_full + 8 * MF_MAXNA, d_full = a_empty + 8 * MF_MAXNA, tmem_slot = d_full + 16;
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     for (int i = 0; i < MF_MAXNR; i++) { mbar_init(h_full + 8 * i, 1); mbar_init(h_empty + 8 * i, MF_CW); mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(a_full + 8 * i, MF_CW); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < MF_MAXNA; i++) { mbar_init(a_full + 8 * i, MF_CW); mbar_init(a_empty + 8 * i, 1); }
     mbar_init(d_full, 1); mbar_init(d_full + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -123,9 +124,9 @@ __global__ void __launch_bounds__(MF_NTH, 1) mixffn_tail_kernel(const __grid_con
       for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, it++) {
         const uint32_t acc = tmem_base + (uint32_t)((it & 1) * C);
         for (int j = 0; j < nch; j++, g++) {
-          const int s = g & 1, slot = g % NR;
+          const int s = g % NA, slot = g % NR;
           mbar_wait(w_full + 8 * slot, (g / NR) & 1);
-          mbar_wait(a_full + 8 * s, (g >> 1) & 1);
+          mbar_wait(a_full + 8 * s, (g / NA) & 1);
           tc_fence_after();
           const uint64_t ad = desc_k(sA + s * MF_A_BYTES), bd = desc_k(sW + slot * wbytes);
 #pragma unroll
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(MF_NTH, 1) mixffn_tail_kernel(const __grid_con
     for (int ti = blockIdx.x; ti < p.ntiles; ti += gridDim.x, it++) {
       const int b = ti / p.bands, h0 = (ti - b * p.bands) * TR;
       for (int j = 0; j < nch; j++, g++) {
-        const int s = g & 1, slot = g % NR;
+        const int s = g % NA, slot = g % NR;
         // filter taps / bias of this thread's 4 channels of chunk j
         const uint32_t fa = sF + (uint32_t)(j * 64 + cv * 4) * 4;
         f32x2 wv[9][2], bv[2];
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(MF_NTH, 1) mixffn_tail_kernel(const __grid_con
           else { bv[0] = pk2(w4.x, w4.y); bv[1] = pk2(w4.z, w4.w); }
         }
         mbar_wait(h_full + 8 * slot, (g / NR) & 1);                  // the chunk's input box has landed
-        if (g >= 2) mbar_wait(a_empty + 8 * s, ((g >> 1) - 1) & 1);  // the MMAs of chunk g-2 have read A tile s
+        if (g >= NA) mbar_wait(a_empty + 8 * s, (g / NA - 1) & 1);   // the MMAs of chunk g - NA have read A tile s
         const uint32_t ring = sR + slot * ringB + cv * 8;
         const uint32_t at = sA + s * MF_A_BYTES + (cv & 1) * 8;
 #pragma unroll
@@ -249,14 +250,23 @@ __global__ void __launch_bounds__(MF_NTH, 1) mixffn_tail_kernel(const __grid_con
   }
 }
 
-// ring depth / shared-memory footprint of a shape; 0 when it does not fit
-inline int mf_plan(int W, int C, int Ch, size_t* smem_out) {
+// pipeline depths / shared-memory footprint of a shape: NR input boxes + W2 slices in flight, NA A tiles between the depthwise
+// warps and the MMAs (how far a fast warp may run ahead of the slowest).  Returns NR (0 when nothing fits).
+inline int mf_plan(int W, int C, int Ch, size_t* smem_out, int* na_out = nullptr) {
   const int TR = 128 / W;
   const size_t ringB = (size_t)(TR + 2) * (W + 2) * 128, wbytes = (size_t)C * 128;
-  for (int nr = MF_MAXNR; nr >= 2; nr--) {
-    const size_t smem = 2 * MF_A_BYTES + nr * (ringB + wbytes) + (size_t)10 * Ch * 4 + 256 + 1024;
-    if (smem <= 220 * 1024) { if (smem_out) *smem_out = smem; return nr; }
-  }
+  const size_t fixed = (size_t)10 * Ch * 4 + 512 + 1024, cap = 220 * 1024;
+  for (int pass = 0; pass < 2; pass++)                          // first: at least 3 boxes in flight, as many A tiles as fit
+    for (int na = MF_MAXNA; na >= 2; na--) {
+      if (fixed + (size_t)na * MF_A_BYTES >= cap) continue;
+      int nr = (int)((cap - fixed - (size_t)na * MF_A_BYTES) / (ringB + wbytes));
+      if (nr > MF_MAXNR) nr = MF_MAXNR;
+      if (nr >= (pass == 0 ? 3 : 2)) {
+        if (smem_out) *smem_out = fixed + (size_t)na * MF_A_BYTES + (size_t)nr * (ringB + wbytes);
+        if (na_out) *na_out = na;
+        return nr;
+      }
+    }
   return 0;
 }
 }  // namespace
@@ -280,7 +290,7 @@ extern "C" int cenet_mixffn_tail(const void* h, void* t, const float* w9c, const
   p.t = (float*)t; p.w9c = w9c; p.dwb = dw_bias; p.b2 = b2;
   p.H = H; p.W = W; p.Ch = Ch; p.C = C; p.TR = 128 / W; p.nch = Ch / 64;
   size_t smem = 0;
-  p.NR = mf_plan(W, C, Ch, &smem);
+  p.NR = mf_plan(W, C, Ch, &smem, &p.NA);
   p.bands = cdiv(H, p.TR);
   p.ntiles = p.bands * B;
   CUtensorMap tmW, tmH;

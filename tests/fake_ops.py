@@ -167,7 +167,7 @@ def mixffn_tail_supported(H, W, Ch, Cc):
     if not (W % 4 == 0 and 8 <= W <= 128 and Cc in (64, 128) and Ch % 64 == 0 and Ch >= 64 and H >= 1):
         return False
     TR = 128 // W
-    smem = 2 * 16384 + 2 * ((TR + 2) * (W + 2) * 128 + Cc * 128) + 10 * Ch * 4 + 256 + 1024      # ring depth 2 is the minimum
+    smem = 2 * 16384 + 2 * ((TR + 2) * (W + 2) * 128 + Cc * 128) + 10 * Ch * 4 + 512 + 1024      # depth 2 / 2 is the minimum
     return smem <= 220 * 1024
 
 

@@ -3,6 +3,8 @@ in every encoder stage, 16384-token differential / non-local attention at the 12
 through the same drop-in boundary as the 224x224 cases.  Also the B=1 train-mode edge of SURVEY 8b (BatchNorm statistics
 over H*W only, CCU without its BatchNorm1d)."""
 import pytest
+
+from conftest import assert_labels_match
 import torch
 
 from oracle import cenet_oracle as O
@@ -38,7 +40,7 @@ def test_skin_512_bf16_matches_oracle_and_labels_are_exact():
         yb = m(x.to(DEV))                                             # public call, CUDA-graph path, batch of 1
         lab = m.predict(x.to(DEV)).cpu()
     assert lab.shape == (1, 512, 512) and lab.dtype == torch.int64
-    assert torch.equal(lab, O.predict_labels(yb.cpu()))              # bit-exact integer labels on identical logits
+    assert_labels_match(lab, yb)              # bit-exact integer labels on identical logits
     assert rel(yb, y) < 1e-5                                          # graph replay == eager
 
 

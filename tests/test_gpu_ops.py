@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import ROOT
+from conftest import ROOT, assert_labels_match
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -111,6 +111,37 @@ def test_conv_same(impl, Cin, Cout, k, H, W):
     e = rel(out, ref)
     record(f"conv_{impl}_{Cin}_{Cout}_{k}_{H}x{W}", e)
     assert e < 4e-3, e
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("Cin,Cout,k,st,pd,H,W,B", [(64, 64, 8, 8, 0, 56, 56, 3), (128, 128, 4, 4, 0, 28, 28, 2), (320, 320, 2, 2, 0, 14, 14, 2),
+                                                    (64, 128, 3, 2, 1, 56, 56, 2), (128, 320, 3, 2, 1, 28, 28, 3), (320, 512, 3, 2, 1, 14, 14, 2),
+                                                    (64, 64, 8, 8, 0, 128, 128, 1), (64, 96, 3, 2, 1, 37, 45, 2), (128, 64, 4, 4, 0, 40, 72, 2)])
+def test_conv_strided_tc(Cin, Cout, k, st, pd, H, W, B, split):
+    """strided convolutions on the tcgen05 kernel (element-strided TMA boxes, no im2col): the patch embeds (3x3 s2 p1) and the
+    SR convs (k = s) of every stage, odd sizes with partial tiles, with and without the split-K workspace; also against the
+    im2col + GEMM pair it replaces"""
+    from cenet_b200 import ops
+    Ho, Wo = (H + 2 * pd - k) // st + 1, (W + 2 * pd - k) // st + 1
+    x = torch.randn(B, Cin, H, W, generator=g(1))
+    wt = torch.randn(Cout, Cin, k, k, generator=g(2)) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g(3))
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    wm = wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(DEV, torch.bfloat16)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ws = torch.zeros(1 << 22, device=DEV) if split else None
+    ops.conv_nhwc(xn, wm, out, k, st, pd, bias=bias.to(DEV), impl=ops.GEMM_TCGEN05, split_ws=ws)
+    ref = F.conv2d(xn.float().cpu().permute(0, 3, 1, 2), wm.float().cpu().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), bias,
+                   stride=st, padding=pd).permute(0, 2, 3, 1)
+    e = rel(out, ref)
+    record(f"conv_strided_tc_{Cin}_{Cout}_{k}s{st}_{H}x{W}_{int(split)}", e)
+    assert e < 4e-3, e
+    col = torch.empty(B * Ho * Wo, k * k * Cin, device=DEV, dtype=torch.bfloat16)
+    ops.im2col(xn, col, B, H, W, Cin, k, st, pd, Ho, Wo, k * k * Cin)
+    out2 = torch.empty(B * Ho * Wo, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(col, wm, out2, M=B * Ho * Wo, N=Cout, K=k * k * Cin, lda=k * k * Cin, ldw=k * k * Cin, ldc=Cout, bias=bias.to(DEV),
+             impl=ops.GEMM_TCGEN05)
+    assert rel(out.reshape(-1, Cout), out2) < 2e-3
 
 
 def test_conv_strided_simt_and_im2col():
@@ -570,7 +601,7 @@ def test_head_upsample_argmax_bit_exact(ncls):
     ref = F.interpolate(y, scale_factor=2, mode="bilinear")
     torch.testing.assert_close(logits.cpu(), ref, rtol=1e-6, atol=1e-6)
     # integer contract: labels are bit-exact w.r.t. argmax(softmax(.)) of OUR logits (metrics_eval.py:52)
-    assert torch.equal(labels.cpu(), O.predict_labels(logits.cpu()))
+    assert_labels_match(labels, logits)
     # ties resolve to the lowest index
     yt = torch.zeros(1, 3, 3, ncls, device=DEV)
     lab = torch.empty(1, 6, 6, device=DEV, dtype=torch.int64)
