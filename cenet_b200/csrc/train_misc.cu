@@ -18,9 +18,10 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
                                                       const float* __restrict__ wch, T* __restrict__ dy, int acc_dy, T* __restrict__ dgate,
                                                       int C2, int H, int W, const float* __restrict__ mats,
                                                       const int* __restrict__ bands, int nmax, int ns, float* __restrict__ ws,
-                                                      int nplanes, float* __restrict__ scratch, int ident_mask) {
+                                                      int nplanes, float* __restrict__ scratch, int ident_mask, int tab_off) {
   extern __shared__ float sm_dyn[];
   __shared__ float red[16];
+  __shared__ int s_nb;
   const int nthr = blockDim.x;                               // 256, or 512 for planes >= 2048 pixels (more threads per plane:
                                                              // the separable passes are latency-bound, shared memory caps the CTAs per SM)
   const int HW = H * W;
@@ -31,6 +32,69 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
   float* ACC = Tm + HW;
   float* R = ACC + HW;                 // [ns][HW]
   const int tid = threadIdx.x;
+  // ---- compact band tables (shared memory, built once per CTA): the separable operators are banded (bilinear taps), at most
+  //      NB = 4 or 8 non-zeros per row / column.  Table u of scale s: u = 0 rows of A_h (forward, vertical), 1 rows of A_w (forward,
+  //      horizontal), 2 columns of A_w (backward, horizontal), 3 columns of A_h (backward, vertical); entry i keeps its first tap
+  //      index lo (shifted down so that lo + NB stays inside the axis) and NB coefficients.  The passes become fixed-length
+  //      unrolled dot products on shared memory (the first version walked [lo, hi) with one __ldg per tap: L1 latency inside every
+  //      dependent FMA chain, ~0.5 warp instructions per cycle and SM).  nb == 0 -> a band is wider than 8: generic loops below.
+  const int nax = max(H, W);
+  float* tcoef = sm_dyn + tab_off;                      // [ns*4][nax][8]
+  int* tlo = reinterpret_cast<int*>(tcoef + (size_t)ns * 4 * nax * 8);
+  {
+    int wmax = 0;
+    for (int i = tid; i < ns * 4 * nax; i += nthr) {
+      const int s = i / (4 * nax), u = (i / nax) & 3, e = i % nax;
+      const int ax = (u == 0 || u == 3) ? 0 : 1, n = ax ? W : H;
+      if (((ident_mask >> s) & 1) || e >= n) continue;
+      const int* bd = bands + ((((size_t)s * 2 + ax) * 2 + (u >= 2)) * nmax + e) * 2;
+      wmax = max(wmax, bd[1] - bd[0]);
+    }
+    if (tid == 0) s_nb = 0;
+    __syncthreads();
+    if (wmax > 0) atomicMax(&s_nb, wmax);
+    __syncthreads();
+    const int wm = s_nb;
+    __syncthreads();
+    const int nb = (wm <= 4 && H >= 4 && W >= 4) ? 4 : ((wm <= 8 && H >= 8 && W >= 8) ? 8 : 0);
+    if (tid == 0) s_nb = nb;
+    if (nb) {
+      for (int i = tid; i < ns * 4 * nax; i += nthr) {
+        const int s = i / (4 * nax), u = (i / nax) & 3, e = i % nax;
+        const int ax = (u == 0 || u == 3) ? 0 : 1, n = ax ? W : H;
+        float* cf = tcoef + (size_t)i * 8;
+        if (((ident_mask >> s) & 1) || e >= n) {
+          for (int t = 0; t < 8; t++) cf[t] = 0.f;
+          tlo[i] = 0;
+          continue;
+        }
+        const int* bd = bands + ((((size_t)s * 2 + ax) * 2 + (u >= 2)) * nmax + e) * 2;
+        const float* A = mats + ((size_t)s * 2 + ax) * nmax * nmax;
+        const int lo = min(bd[0], n - nb);
+        for (int t = 0; t < 8; t++) {
+          const int k = lo + t;
+          cf[t] = (t < nb && k >= bd[0] && k < bd[1]) ? (u < 2 ? A[(size_t)e * nmax + k] : A[(size_t)k * nmax + e]) : 0.f;
+        }
+        tlo[i] = lo;
+      }
+    }
+    __syncthreads();
+  }
+  const int nb = s_nb;
+  const unsigned wmagic = 0xFFFFFFFFu / (unsigned)W + 1u;           // i / W for i < 2^16 (HW < 65536 is checked by the launcher)
+  // dot product of table entry e of (s, u) with src[base + t * stride], t < nb
+  auto band_dot = [&](int s, int u, int e, const float* src, int base0, int stride) -> float {
+    const int ti = (s * 4 + u) * nax + e;
+    const float4 c0 = *reinterpret_cast<const float4*>(tcoef + (size_t)ti * 8);
+    const float* q = src + base0 + tlo[ti] * stride;
+    float a = c0.x * q[0];
+    a = fmaf(c0.y, q[stride], a); a = fmaf(c0.z, q[2 * stride], a); a = fmaf(c0.w, q[3 * stride], a);
+    if (nb == 8) {
+      const float4 c1 = *reinterpret_cast<const float4*>(tcoef + (size_t)ti * 8 + 4);
+      a = fmaf(c1.x, q[4 * stride], a); a = fmaf(c1.y, q[5 * stride], a); a = fmaf(c1.z, q[6 * stride], a); a = fmaf(c1.w, q[7 * stride], a);
+    }
+    return a;
+  };
   for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
   const int c = plane % C2;
   const long long base = (long long)plane * HW;
@@ -49,6 +113,19 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
     // the operators are banded (bilinear taps): [lo, hi) of the non-zeros of every row / column comes from the host
     const int* rbh = bands + (((size_t)s * 2 + 0) * 2 + 0) * nmax * 2;     // row bands of A_h
     const int* rbw = bands + (((size_t)s * 2 + 1) * 2 + 0) * nmax * 2;     // row bands of A_w
+    if (nb) {
+      for (int i = tid; i < HW; i += nthr) {
+        const int r = (int)__umulhi((unsigned)i, wmagic), w = i - r * W;
+        Tm[i] = band_dot(s, 0, r, Y, w, W);
+      }
+      __syncthreads();
+      for (int i = tid; i < HW; i += nthr) {
+        const int r = (int)__umulhi((unsigned)i, wmagic), j = i - r * W;
+        R[s * HW + i] = Y[i] - band_dot(s, 1, j, Tm, r * W, 1);
+      }
+      __syncthreads();
+      continue;
+    }
     for (int i = tid; i < HW; i += nthr) {
       const int r = i / W, w = i % W;
       float a = 0.f;
@@ -104,6 +181,19 @@ __global__ void __launch_bounds__(512) fea_bwd_kernel(const T* __restrict__ y, c
     const float* G = R + s * HW;
     const int* cbh = bands + (((size_t)s * 2 + 0) * 2 + 1) * nmax * 2;     // column bands of A_h
     const int* cbw = bands + (((size_t)s * 2 + 1) * 2 + 1) * nmax * 2;     // column bands of A_w
+    if (nb) {
+      for (int i = tid; i < HW; i += nthr) {
+        const int r = (int)__umulhi((unsigned)i, wmagic), w = i - r * W;
+        Tm[i] = band_dot(s, 2, w, G, r * W, 1);
+      }
+      __syncthreads();
+      for (int i = tid; i < HW; i += nthr) {
+        const int h = (int)__umulhi((unsigned)i, wmagic), w = i - h * W;
+        ACC[i] += G[i] - band_dot(s, 3, h, Tm, w, W);
+      }
+      __syncthreads();
+      continue;
+    }
     for (int i = tid; i < HW; i += nthr) {
       const int r = i / W, w = i % W;
       float a = 0.f;
@@ -428,17 +518,26 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
   CENET_REQUIRE(nscales >= 1 && nscales <= 3, "cenet_fea_bwd: 1..3 scales");
   CENET_REQUIRE(H <= nmax && W <= nmax, "cenet_fea_bwd: operator matrices smaller than the plane");
   CENET_REQUIRE((long long)B * C2 <= ws_elems, "cenet_fea_bwd: workspace too small");
+  CENET_REQUIRE((long long)H * W < 65536, "cenet_fea_bwd: plane too large");
   const size_t slab = (size_t)(4 + nscales) * H * W;            // floats of working set per plane
-  size_t smem = slab * sizeof(float);
+  const int nax = H > W ? H : W;
+  const size_t tab_bytes = (size_t)nscales * 4 * nax * (8 * sizeof(float) + sizeof(int));     // compact band tables
+  size_t smem = slab * sizeof(float) + tab_bytes;
   const int nplanes = B * C2;
   int blocks = nplanes;
+  int tab_off = (int)slab;
   float* scratch = nullptr;
   if (smem > 200 * 1024) {                                      // big planes: working set in the workspace, after the partials
     const long long room = (ws_elems - nplanes) / (long long)slab;
     CENET_REQUIRE(room >= 1, "cenet_fea_bwd: plane %dx%d needs %zu workspace floats per block", H, W, slab);
     blocks = (int)std::min<long long>(std::min<long long>(nplanes, room), 2LL * kNumSMs);
     scratch = ws + nplanes;
-    smem = 0;
+    smem = tab_bytes;
+    tab_off = 0;
+  } else {
+    // persistent blocks striding over the planes: the band tables are built once per block
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(227 * 1024 / (smem + 1024), 2048 / (H * W >= 2048 ? 512 : 256)));
+    blocks = std::min(nplanes, per_sm * kNumSMs);
   }
   cudaStream_t s = to_stream(st);
   CENET_DISPATCH(dtype, T, {
@@ -448,7 +547,7 @@ extern "C" int cenet_fea_bwd(const void* y, const void* gate, const void* dz, in
       configured.store(200 * 1024);
     }
     fea_bwd_kernel<T><<<blocks, H * W >= 2048 ? 512 : 256, smem, s>>>((const T*)y, (const T*)gate, (const T*)dz, w, (T*)dy, acc_dy, (T*)dgate, C2, H, W, mats,
-                                                bands, nmax, nscales, ws, nplanes, scratch, ident_mask);
+                                                bands, nmax, nscales, ws, nplanes, scratch, ident_mask, tab_off);
     CENET_LAUNCH_CHECK("fea_bwd");
   });
   fea_dw_finalize_kernel<<<cdiv(C2, 128), 128, 0, s>>>(ws, B, C2, dw);
