@@ -2,6 +2,7 @@
 // helpers of the materialised (validation) differential-attention path.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 constexpr int kMaxScales = 3;
@@ -12,6 +13,9 @@ struct FeaScales {
   float up_h[kMaxScales], up_w[kMaxScales];  // source scale of the up pass = hd/H  (size= semantics)
   int identity[kMaxScales];               // s == 1.0 -> edge term exactly 0
   int off[kMaxScales];                    // smem offset (floats) of each down buffer
+  int off2[kMaxScales];                   // smem offset of the horizontally up-sampled copy [hd][W] (separable up pass)
+  int sep;                                // 1: the up pass runs separably (W even and the extra buffers fit)
+  int goff;                               // >= 0: smem offset (floats) of the staged bf16 gate plane (HW / 2 floats); -1: gate from global
 };
 
 // A CTA handles PPB consecutive (b,c) planes, each by a team of 256/PPB threads (PPB = 1 for 56x56 planes, 4 for 28x28,
@@ -57,10 +61,26 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
   const long long pl = (long long)blockIdx.x * ppb + tm;
   const bool live = pl < nplanes;
   const int HW = H * W;
-  float* plane = sm + 2 * tcount + (size_t)tm * plane_floats;     // LerpTab = 8 bytes = 2 floats
+  float* plane = sm + ((2 * tcount + 3) & ~3) + (size_t)tm * plane_floats;     // LerpTab = 8 bytes = 2 floats; 16-byte aligned planes
   if (live) {
     const T* yp = y + pl * HW;
-    for (int i = tt; i < HW; i += team) plane[i] = ldf(yp + i);
+    if (sizeof(T) == 2 && (HW & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+      for (int i = tt * 8; i < HW; i += team * 8) {                  // 16 bytes per load
+        float v[8];
+        ldv<8>(yp + i, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) plane[i + j] = v[j];
+      }
+    } else {
+      for (int i = tt; i < HW; i += team) plane[i] = ldf(yp + i);
+    }
+    // the gate plane is staged with 16-byte loads as well: read per pixel inside the final loop it left ~4 bytes per thread in
+    // flight (8 KB per SM against the ~40 KB the HBM latency needs) and the kernel ran at 0.7 TB/s
+    if (sc.goff >= 0 && gate) {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(gate + pl * HW);
+      uint4* gdst = reinterpret_cast<uint4*>(plane + sc.goff);
+      for (int i = tt; i < (HW >> 3); i += team) gdst[i] = gsrc[i];
+    }
   }
   __syncthreads();
   if (live) {
@@ -79,13 +99,79 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
     }
   }
   __syncthreads();
-  if (!live) return;
-  const int c = (int)(pl % C2);
+  const int c = live ? (int)(pl % C2) : 0;
   const float wc = w_c[c];
   const int npair = sc.n * (sc.n - 1) / 2;
   const float inv_pair = npair > 0 ? 1.f / (float)npair : 0.f;
   const T* gp = gate ? gate + pl * HW : nullptr;
   T* zp = z + pl * HW;
+  if (sc.sep) {
+    // ---- separable up pass: T2_k[r][w] = horizontal lerp of down row r, then the final pass needs ONE vertical lerp per scale
+    //      (2 shared-memory reads instead of 4 + two table entries) and handles two adjacent pixels per thread.  The arithmetic
+    //      (lerp order) is that of the direct form below: results are bit-identical. ----
+    if (live) {
+      for (int k = 0; k < sc.n; k++) {
+        if (sc.identity[k]) continue;
+        const float* d = plane + sc.off[k];
+        float* t2 = plane + sc.off2[k];
+        const int wd = sc.wd[k], n2 = sc.hd[k] * W;
+        for (int i = tt; i < n2; i += team) {
+          const int r = (int)__umulhi((unsigned)i, wmagic), w = i - r * W;
+          const LerpTab bcol = tab[toff[k][3] + w];
+          const float d0 = d[r * wd + bcol.i0];
+          t2[i] = fmaf(bcol.l, d[r * wd + bcol.i1] - d0, d0);
+        }
+      }
+    }
+    __syncthreads();
+    if (!live) return;
+    for (int i2 = tt; i2 < (HW >> 1); i2 += team) {
+      const int i = 2 * i2;
+      const int h = (int)__umulhi((unsigned)i, wmagic), w = i - h * W;
+      const float2 x = *reinterpret_cast<const float2*>(plane + i);
+      float e0[kMaxScales], e1[kMaxScales];
+#pragma unroll
+      for (int k = 0; k < kMaxScales; k++) {
+        e0[k] = mode == 1 ? x.x : 0.f; e1[k] = mode == 1 ? x.y : 0.f;
+        if (k < sc.n && !sc.identity[k]) {
+          const float* t2 = plane + sc.off2[k];
+          const LerpTab a = tab[toff[k][2] + h];
+          const float2 top = *reinterpret_cast<const float2*>(t2 + a.i0 * W + w);
+          const float2 bot = *reinterpret_cast<const float2*>(t2 + a.i1 * W + w);
+          const float y0 = fmaf(a.l, bot.x - top.x, top.x), y1 = fmaf(a.l, bot.y - top.y, top.y);
+          e0[k] = mode == 1 ? y0 : fabsf(x.x - y0);
+          e1[k] = mode == 1 ? y1 : fabsf(x.y - y1);
+        }
+      }
+      float z0, z1;
+      if (mode == 1) {
+        z0 = fmaf(wc, fabsf(e0[0] - e0[1]), x.x); z1 = fmaf(wc, fabsf(e1[0] - e1[1]), x.y);
+      } else {
+        float g0, g1;
+        if (sc.goff >= 0) {
+          const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(plane + sc.goff)[i2]);
+          g0 = g.x; g1 = g.y;
+        } else if (sizeof(T) == 2) {
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gp + i));
+          g0 = g.x; g1 = g.y;
+        } else {
+          g0 = ldf(gp + i); g1 = ldf(gp + i + 1);
+        }
+        float ed0 = 0.f, ed1 = 0.f;
+#pragma unroll
+        for (int a = 0; a < kMaxScales; a++)
+#pragma unroll
+          for (int b = a + 1; b < kMaxScales; b++)
+            if (b < sc.n) { ed0 += fabsf(e0[a] - e0[b]); ed1 += fabsf(e1[a] - e1[b]); }
+        z0 = fmaf(wc * inv_pair, ed0, fmaf(g0, x.x, 2.f * x.x));
+        z1 = fmaf(wc * inv_pair, ed1, fmaf(g1, x.y, 2.f * x.y));
+      }
+      if (sizeof(T) == 2) *reinterpret_cast<__nv_bfloat162*>(zp + i) = __floats2bfloat162_rn(z0, z1);
+      else { stf(zp + i, z0); stf(zp + i + 1, z1); }
+    }
+    return;
+  }
+  if (!live) return;
   for (int i = tt; i < HW; i += team) {
     const int h = (int)__umulhi((unsigned)i, wmagic), w = i - h * W;
     const float x = plane[i];
@@ -158,15 +244,33 @@ static int fea_launch(const void* y, const void* gate, void* z, int dtype, const
     sc.up_h[k] = (float)sc.hd[k] / (float)H;
     sc.up_w[k] = (float)sc.wd[k] / (float)W;
     sc.off[k] = off;
-    if (!sc.identity[k]) off += sc.hd[k] * sc.wd[k];
+    if (!sc.identity[k]) off += (sc.hd[k] * sc.wd[k] + 1) & ~1;            // even offsets: the pair pass reads float2
   }
-  const int plane_floats = off;
+  const int HW_ = H * W;
+  const int ppb_ = HW_ >= 2048 ? 1 : (HW_ >= 512 ? 4 : 8);
+  int off2 = off, tc2 = 0;
+  for (int k = 0; k < kMaxScales; k++) {
+    sc.off2[k] = off2;
+    if (k < nscales && !sc.identity[k]) { off2 += sc.hd[k] * W; tc2 += sc.hd[k] + sc.wd[k] + H + W; }
+  }
+  // separable up pass when the planes are even (pairs of pixels, 8-byte accesses) and the extra buffers fit; mode 2 has no scales
+  static const bool sep_on = !(getenv("CENET_B200_FEA_SEP") && atoi(getenv("CENET_B200_FEA_SEP")) == 0);
+  sc.sep = sep_on && mode != 2 && (W % 2 == 0) && (HW_ % 2 == 0) && ((size_t)2 * tc2 + (size_t)ppb_ * off2) * sizeof(float) <= 200 * 1024;
+  if (sc.sep) off = off2;
+  sc.goff = -1;
+  if (sc.sep && dtype == CENET_BF16 && gate && mode == 0 && HW_ % 8 == 0 && (((uintptr_t)gate & 15) == 0)) {
+    off = (off + 3) & ~3;                                                  // 16-byte aligned staging area
+    sc.goff = off;
+    off += HW_ / 2;
+    off = (off + 1) & ~1;
+  }
+  const int plane_floats = (off + 3) & ~3;
   int tcount = 0;
   for (int k = 0; k < nscales; k++)
     if (!sc.identity[k]) tcount += sc.hd[k] + sc.wd[k] + H + W;
   const int HW = H * W;
   const int ppb = HW >= 2048 ? 1 : (HW >= 512 ? 4 : 8);
-  const size_t smem = ((size_t)2 * tcount + (size_t)ppb * plane_floats) * sizeof(float);
+  const size_t smem = ((((size_t)2 * tcount + 3) & ~(size_t)3) + (size_t)ppb * plane_floats) * sizeof(float);
   CENET_REQUIRE(smem <= 227 * 1024, "cenet_fea_combine: plane %dx%d needs %zu bytes of shared memory", H, W, smem);
   CENET_REQUIRE(H <= 32767 && W <= 32767 && HW < 65536, "cenet_fea_combine: plane too large");
   const long long planes = (long long)B * C2;
