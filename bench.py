@@ -49,7 +49,7 @@ UNIT = "slices/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu captures of this workload (profiles/, per round)
 NCU_TRAFFIC = {"source": "profiles/r2_ncu_top_kernels.md, profiles/r2_gemm_traffic.md", "diffattn_flash_kernel": 191.4e6,
-               "gemm_tc_kernel": 43.9e6}      # mean over the 146 launches of one forward
+               "gemm_tc_kernel": 43.6e6}      # mean over the 146 launches of one forward
 
 
 def workload_config(world=1):

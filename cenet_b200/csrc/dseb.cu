@@ -1,6 +1,7 @@
 // DSEB pieces that are not GEMMs (dseb.py): Feature-Edge-Amplifier fused with the final combine, and the two small
 // helpers of the materialised (validation) differential-attention path.
 #include "common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -207,6 +208,177 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- v2
+// Same arithmetic (bit-identical lerp order), organised for instruction count -- ncu on the first kernel: 172 thread instructions
+// per pixel, issue-bound at 0.7 TB/s.  Persistent CTAs (tables built once), 16-byte table entries with pre-multiplied row offsets,
+// and every pass gives a thread ONE column (or column pair) and a run of rows, so the column taps live in registers, the row taps
+// are one broadcast LDS.128 and the addresses advance by additions:
+//   down   D[r][q]   = lerp_rows(lerp_cols(plane))          thread = down column q x row chunk
+//   up-h   T2[r][w]  = lerp_cols(D[r])                      thread = column w x row chunk
+//   final  z[h][w..w+1] from x, lerp_rows(T2), gate         thread = column pair x row chunk
+struct Tab4 { int a, b; float l; int pad; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict__ y, const T* __restrict__ gate, T* __restrict__ z,
+                                                             const float* __restrict__ w_c, int C2, int H, int W, long long nplanes,
+                                                             int ppb, const FeaScales sc, int plane_floats, int mode, int ngroups) {
+  extern __shared__ __align__(16) float sm2[];
+  Tab4* tab = reinterpret_cast<Tab4*>(sm2);
+  // per active scale: DR (hd rows), DC (wd cols), UR (H rows), UC (W cols)
+  int tb[kMaxScales][4], act[kMaxScales], hdv[kMaxScales], wdv[kMaxScales], offv[kMaxScales], off2v[kMaxScales];
+  int tcount = 0, nact = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxScales; k++) {
+    act[k] = (k < sc.n && !sc.identity[k]) ? 1 : 0;
+    hdv[k] = sc.hd[k]; wdv[k] = sc.wd[k]; offv[k] = sc.off[k]; off2v[k] = sc.off2[k];
+    tb[k][0] = tcount; tcount += act[k] ? hdv[k] : 0;
+    tb[k][1] = tcount; tcount += act[k] ? wdv[k] : 0;
+    tb[k][2] = tcount; tcount += act[k] ? H : 0;
+    tb[k][3] = tcount; tcount += act[k] ? W : 0;
+    nact += act[k];
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxScales; k++) {
+    if (!act[k]) continue;
+    const int hd = hdv[k], wd = wdv[k];
+    for (int i = threadIdx.x; i < hd + wd + H + W; i += blockDim.x) {
+      int i0, i1; float l; Tab4 e;
+      if (i < hd) { bilin_src(i, sc.inv_s[k], H, i0, i1, l); e.a = i0 * W; e.b = i1 * W; e.l = l; e.pad = 0; tab[tb[k][0] + i] = e; }
+      else if (i < hd + wd) { bilin_src(i - hd, sc.inv_s[k], W, i0, i1, l); e.a = i0; e.b = i1; e.l = l; e.pad = 0; tab[tb[k][1] + i - hd] = e; }
+      else if (i < hd + wd + H) { bilin_src(i - hd - wd, sc.up_h[k], hd, i0, i1, l); e.a = i0 * W; e.b = i1 * W; e.l = l; e.pad = 0; tab[tb[k][2] + i - hd - wd] = e; }
+      else { bilin_src(i - hd - wd - H, sc.up_w[k], wd, i0, i1, l); e.a = i0; e.b = i1; e.l = l; e.pad = 0; tab[tb[k][3] + i - hd - wd - H] = e; }
+    }
+  }
+  const int team = blockDim.x / ppb, tm = threadIdx.x / team, tt = threadIdx.x - tm * team;
+  const int HW = H * W;
+  float* plane = sm2 + 4 * tcount + (size_t)tm * plane_floats;
+  const int npair = sc.n * (sc.n - 1) / 2;
+  const float inv_pair = npair > 0 ? 1.f / (float)npair : 0.f;
+  // thread -> (column, row chunk) of each pass
+  auto split = [&](int ncols, int nrows, int& col, int& r0, int& r1) {
+    const int cw = min(ncols, team), nchunk = max(1, team / cw), rpc = (nrows + nchunk - 1) / nchunk;
+    const int ch = tt / cw;
+    col = tt - ch * cw;
+    r0 = min(nrows, ch * rpc); r1 = ch < nchunk ? min(nrows, r0 + rpc) : r0;
+    return cw;
+  };
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long pl = (long long)grp * ppb + tm;
+    const bool live = pl < nplanes;
+    __syncthreads();                                                   // tables ready / previous group done with the planes
+    if (live) {
+      const T* yp = y + pl * HW;
+      if (sizeof(T) == 2 && (HW & 7) == 0 && ((reinterpret_cast<uintptr_t>(yp) & 15) == 0)) {
+        for (int i = tt * 8; i < HW; i += team * 8) {
+          float v[8];
+          ldv<8>(yp + i, v);
+          *reinterpret_cast<float4*>(plane + i) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(plane + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else {
+        for (int i = tt; i < HW; i += team) plane[i] = ldf(yp + i);
+      }
+      if (sc.goff >= 0 && gate) {
+        const uint4* gsrc = reinterpret_cast<const uint4*>(gate + pl * HW);
+        uint4* gdst = reinterpret_cast<uint4*>(plane + sc.goff);
+        for (int i = tt; i < (HW >> 3); i += team) gdst[i] = gsrc[i];
+      }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < kMaxScales; k++) {
+        if (!act[k]) continue;
+        float* d = plane + offv[k];
+        const int hd = hdv[k], wd = wdv[k];
+        int q, r0, r1;
+        const int cw = split(wd, hd, q, r0, r1);
+        for (; q < wd; q += cw) {
+          const Tab4 bc = tab[tb[k][1] + q];
+          for (int r = r0; r < r1; r++) {
+            const Tab4 rt = tab[tb[k][0] + r];
+            const float* p0 = plane + rt.a;
+            const float* p1 = plane + rt.b;
+            const float top = fmaf(bc.l, p0[bc.b] - p0[bc.a], p0[bc.a]);
+            const float bot = fmaf(bc.l, p1[bc.b] - p1[bc.a], p1[bc.a]);
+            d[r * wd + q] = fmaf(rt.l, bot - top, top);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < kMaxScales; k++) {
+        if (!act[k]) continue;
+        const float* d = plane + offv[k];
+        float* t2 = plane + off2v[k];
+        const int hd = hdv[k], wd = wdv[k];
+        int w, r0, r1;
+        const int cw = split(W, hd, w, r0, r1);
+        for (; w < W; w += cw) {
+          const Tab4 bc = tab[tb[k][3] + w];
+          for (int r = r0; r < r1; r++) {
+            const float d0 = d[r * wd + bc.a];
+            t2[r * W + w] = fmaf(bc.l, d[r * wd + bc.b] - d0, d0);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (live) {
+      const float wc = w_c[(int)(pl % C2)];
+      const T* gp = gate ? gate + pl * HW : nullptr;
+      T* zp = z + pl * HW;
+      int cp, r0, r1;
+      const int cw = split(W >> 1, H, cp, r0, r1);
+      for (; cp < (W >> 1); cp += cw) {
+        const int w = 2 * cp;
+        for (int h = r0; h < r1; h++) {
+          const int i = h * W + w;
+          const float2 x = *reinterpret_cast<const float2*>(plane + i);
+          float e0[kMaxScales], e1[kMaxScales];
+#pragma unroll
+          for (int k = 0; k < kMaxScales; k++) {
+            e0[k] = mode == 1 ? x.x : 0.f; e1[k] = mode == 1 ? x.y : 0.f;
+            if (act[k]) {
+              const float* t2 = plane + off2v[k] + w;
+              const Tab4 a = tab[tb[k][2] + h];
+              const float2 top = *reinterpret_cast<const float2*>(t2 + a.a);
+              const float2 bot = *reinterpret_cast<const float2*>(t2 + a.b);
+              const float y0 = fmaf(a.l, bot.x - top.x, top.x), y1 = fmaf(a.l, bot.y - top.y, top.y);
+              e0[k] = mode == 1 ? y0 : fabsf(x.x - y0);
+              e1[k] = mode == 1 ? y1 : fabsf(x.y - y1);
+            }
+          }
+          float z0, z1;
+          if (mode == 1) {
+            z0 = fmaf(wc, fabsf(e0[0] - e0[1]), x.x); z1 = fmaf(wc, fabsf(e1[0] - e1[1]), x.y);
+          } else {
+            float g0, g1;
+            if (sc.goff >= 0) {
+              const float2 g = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(plane + sc.goff)[i >> 1]);
+              g0 = g.x; g1 = g.y;
+            } else {
+              g0 = ldf(gp + i); g1 = ldf(gp + i + 1);
+            }
+            float ed0 = 0.f, ed1 = 0.f;
+#pragma unroll
+            for (int a = 0; a < kMaxScales; a++)
+#pragma unroll
+              for (int b = a + 1; b < kMaxScales; b++)
+                if (b < sc.n) { ed0 += fabsf(e0[a] - e0[b]); ed1 += fabsf(e1[a] - e1[b]); }
+            z0 = fmaf(wc * inv_pair, ed0, fmaf(g0, x.x, 2.f * x.x));
+            z1 = fmaf(wc * inv_pair, ed1, fmaf(g1, x.y, 2.f * x.y));
+          }
+          if (sizeof(T) == 2) *reinterpret_cast<__nv_bfloat162*>(zp + i) = __floats2bfloat162_rn(z0, z1);
+          else { stf(zp + i, z0); stf(zp + i + 1, z1); }
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) diff_combine_kernel(T* __restrict__ P, long long npairs, long long map_elems,
                                                            float lambda) {
@@ -281,6 +453,25 @@ static int fea_launch(const void* y, const void* gate, void* z, int dtype, const
     if (smem > 48 * 1024) cudaFuncSetAttribute(fea_combine_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     fea_combine_kernel<T><<<grid, 256, smem, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, planes, ppb, wmagic, sc, plane_floats, mode); \
   } while (0)
+  static const bool v2_on = !(getenv("CENET_B200_FEA_V2") && atoi(getenv("CENET_B200_FEA_V2")) == 0);
+  if (sc.sep && v2_on) {
+    // persistent column-ownership kernel; 16-byte table entries
+    const size_t smem2 = ((size_t)4 * tcount + (size_t)ppb * plane_floats) * sizeof(float);
+    if (smem2 <= 200 * 1024) {
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, 227 * 1024 / (smem2 + 1024)));
+      const int ngroups = (int)grid;
+      const int blocks = std::min(ngroups, per_sm * kNumSMs);
+#define LAUNCH_FEA2(T)                                                                                        \
+      do {                                                                                                    \
+        if (smem2 > 48 * 1024) cudaFuncSetAttribute(fea_combine_v2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+        fea_combine_v2_kernel<T><<<blocks, 256, smem2, to_stream(s)>>>((const T*)y, (const T*)gate, (T*)z, w_c, C2, H, W, planes, ppb, sc, plane_floats, mode, ngroups); \
+      } while (0)
+      CENET_DISPATCH(dtype, T, LAUNCH_FEA2(T));
+#undef LAUNCH_FEA2
+      CENET_LAUNCH_CHECK("fea_combine_v2");
+      return 0;
+    }
+  }
   CENET_DISPATCH(dtype, T, LAUNCH_FEA(T));
 #undef LAUNCH_FEA
   CENET_LAUNCH_CHECK("fea_combine");
