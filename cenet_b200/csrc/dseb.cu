@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) fea_combine_kernel(const T* __restrict__ 
 struct Tab4 { int a, b; float l; int pad; };
 
 template <typename T>
-__global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict__ y, const T* __restrict__ gate, T* __restrict__ z,
+__global__ void __launch_bounds__(256, 4) fea_combine_v2_kernel(const T* __restrict__ y, const T* __restrict__ gate, T* __restrict__ z,
                                                              const float* __restrict__ w_c, int C2, int H, int W, long long nplanes,
                                                              int ppb, const FeaScales sc, int plane_floats, int mode, int ngroups) {
   extern __shared__ __align__(16) float sm2[];
@@ -262,6 +262,19 @@ __global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict
     r0 = min(nrows, ch * rpc); r1 = ch < nchunk ? min(nrows, r0 + rpc) : r0;
     return cw;
   };
+  // the (column, row chunk) assignment of every pass depends on the plane geometry only: computed once (the integer divisions of
+  // `split` inside the plane loop were 20 % of all instructions)
+  int dq[kMaxScales], dr0[kMaxScales], dr1[kMaxScales], dcw[kMaxScales], uw[kMaxScales], ur0[kMaxScales], ur1[kMaxScales], ucw[kMaxScales];
+#pragma unroll
+  for (int k = 0; k < kMaxScales; k++) {
+    dq[k] = dr0[k] = dr1[k] = uw[k] = ur0[k] = ur1[k] = 0; dcw[k] = ucw[k] = 1;
+    if (act[k]) {
+      dcw[k] = split(wdv[k], hdv[k], dq[k], dr0[k], dr1[k]);
+      ucw[k] = split(W, hdv[k], uw[k], ur0[k], ur1[k]);
+    }
+  }
+  int fcp, fr0, fr1;
+  const int fcw = split(W >> 1, H, fcp, fr0, fr1);
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long pl = (long long)grp * ppb + tm;
     const bool live = pl < nplanes;
@@ -291,9 +304,8 @@ __global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict
         if (!act[k]) continue;
         float* d = plane + offv[k];
         const int hd = hdv[k], wd = wdv[k];
-        int q, r0, r1;
-        const int cw = split(wd, hd, q, r0, r1);
-        for (; q < wd; q += cw) {
+        const int r0 = dr0[k], r1 = dr1[k], cw = dcw[k];
+        for (int q = dq[k]; q < wd; q += cw) {
           const Tab4 bc = tab[tb[k][1] + q];
           for (int r = r0; r < r1; r++) {
             const Tab4 rt = tab[tb[k][0] + r];
@@ -314,9 +326,8 @@ __global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict
         const float* d = plane + offv[k];
         float* t2 = plane + off2v[k];
         const int hd = hdv[k], wd = wdv[k];
-        int w, r0, r1;
-        const int cw = split(W, hd, w, r0, r1);
-        for (; w < W; w += cw) {
+        const int r0 = ur0[k], r1 = ur1[k], cw = ucw[k];
+        for (int w = uw[k]; w < W; w += cw) {
           const Tab4 bc = tab[tb[k][3] + w];
           for (int r = r0; r < r1; r++) {
             const float d0 = d[r * wd + bc.a];
@@ -330,9 +341,8 @@ __global__ void __launch_bounds__(256) fea_combine_v2_kernel(const T* __restrict
       const float wc = w_c[(int)(pl % C2)];
       const T* gp = gate ? gate + pl * HW : nullptr;
       T* zp = z + pl * HW;
-      int cp, r0, r1;
-      const int cw = split(W >> 1, H, cp, r0, r1);
-      for (; cp < (W >> 1); cp += cw) {
+      const int r0 = fr0, r1 = fr1, cw = fcw;
+      for (int cp = fcp; cp < (W >> 1); cp += cw) {
         const int w = 2 * cp;
         for (int h = r0; h < r1; h++) {
           const int i = h * W + w;
