@@ -141,6 +141,28 @@ def test_benchmarked_batch_64_matches_oracle_on_an_image_subset():
         assert e < 1e-2, (pair, e)
 
 
+def test_optional_plans_match_the_default_plan():
+    """the opt-in / switchable launch plans give the default plan's logits: fused Mix-FFN tail (mixffn_tc.cu) on, implicit strided
+    convolutions off (im2col + GEMM instead of element-strided TMA boxes); bf16 storage differs only by accumulation order"""
+    from cenet_b200.engine import Engine
+    m, x, y_ref, _ = build("synapse", 2)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        y0 = m._engine(xd).forward(xd).clone()
+    for attr, val in (("fuse_mixffn", True), ("implicit_strided", False)):
+        eng = Engine(m, xd.device, "bf16")
+        assert getattr(eng, attr) != val
+        setattr(eng, attr, val)
+        with torch.no_grad():
+            y1 = eng.forward(xd).clone()
+            y1b = eng.forward(xd).clone()                             # second call: CUDA-graph replay of the same plan
+        assert torch.equal(y1, y1b)
+        e = rel(y1, y0)
+        _record(f"bf16_synapse_plan_{attr}_{val}", e)
+        assert e < 3e-3, (attr, e)
+        assert rel(y1, y_ref) < 1e-2
+
+
 def test_graph_replay_equals_eager_and_weight_update():
     m, x, y_ref, _ = build("acdc", 1)
     xd = x.to(DEV)
