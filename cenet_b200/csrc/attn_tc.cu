@@ -27,10 +27,7 @@ constexpr int KT = 64;     // keys per tile
 constexpr int NTH = 192;
 constexpr int STAGES = 3;
 
-// ST = depth of the K/V ring: 3 in general; 1 for key sets of one tile (the encoder's SR attention: 49 keys) -- one score buffer,
-// one P buffer, 128 TMEM columns and ~50 KB of shared memory, so that 3 CTAs share an SM instead of 2 (that case is bound by the
-// latency of its single S -> softmax -> P V round trip per CTA, not by any pipe)
-template <int D, int ST = STAGES>
+template <int D>
 struct Cfg {
   static constexpr int KB = D / 64;                 // 64-column blocks of Q / K / V rows
   static constexpr int Q_BYTES = KB * QT * 128;
@@ -38,11 +35,9 @@ struct Cfg {
   static constexpr int V_BYTES = KB * KT * 128;
   static constexpr int STAGE = K_BYTES + V_BYTES;
   static constexpr int P_BYTES = QT * KT * 2;
-  static constexpr int PB = ST == 1 ? 1 : 2;        // P buffers
-  static constexpr int OCOL = ST == 1 ? KT : 2 * KT;   // first TMEM column of the output accumulator
-  static constexpr int TMEM_COLS = ST == 1 ? 128 : 256;   // (1 | 2) x 64 score columns + D (<= 128) output columns
+  static constexpr int TMEM_COLS = 256;             // 2 x 64 score columns + D (<= 128) output columns
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM = Q_BYTES + ST * STAGE + PB * P_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM = Q_BYTES + STAGES * STAGE + 2 * P_BYTES + BAR_BYTES + 1024;
 };
 
 struct TcAttnParams {
@@ -61,14 +56,14 @@ struct SoftmaxBars {
 // [0,64) / [64,128) (two buffers), output accumulator of DOUT columns at column 128; P tiles [2][128 x 64] bf16 at sP.
 template <int DOUT>
 __device__ __forceinline__ void softmax_role(uint32_t tmem_base, uint32_t sP, const SoftmaxBars& B_, int nt, const TcAttnParams& p, int warp,
-                                             int lane, int q0, int b, int out_col0, int lse_map, int o_col = 2 * KT) {
+                                             int lane, int q0, int b, int out_col0, int lse_map) {
   constexpr int P_BYTES = QT * KT * 2;
   const uint32_t s_full = B_.s_full, s_empty = B_.s_empty, p_full = B_.p_full, p_empty = B_.p_empty, o_ready = B_.o_ready,
                  o_final = B_.o_final;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t t_o = tmem_base + lane_off + o_col;
+    const uint32_t t_o = tmem_base + lane_off + 2 * KT;
     float m = -INFINITY, l = 0.f;
     const float sc = p.scale_log2;
     for (int j = 0; j < nt; j++) {
@@ -164,20 +159,20 @@ __device__ __forceinline__ void softmax_role(uint32_t tmem_base, uint32_t sP, co
       p.lse[((long long)b * p.heads + lse_map) * p.Nq + n] = (m + log2f(l)) * p.lse_mul;
 }
 
-template <int D, int ST>
-__global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+template <int D>
+__global__ void __launch_bounds__(NTH, D == 64 ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                       const __grid_constant__ CUtensorMap tmK,
                                                                       const __grid_constant__ CUtensorMap tmV,
                                                                       const TcAttnParams p) {
-  using C = Cfg<D, ST>;
+  using C = Cfg<D>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
   const uint32_t sQ = sbase;
   const uint32_t sKV = sQ + C::Q_BYTES;
-  const uint32_t sP = sKV + ST * C::STAGE;
-  const uint32_t bar = sP + C::PB * C::P_BYTES;
+  const uint32_t sP = sKV + STAGES * C::STAGE;
+  const uint32_t bar = sP + 2 * C::P_BYTES;
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8 + s * 8; };
   auto kv_empty = [&](int s) { return bar + 8 + (STAGES + s) * 8; };
@@ -221,8 +216,8 @@ __global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_
 #pragma unroll
       for (int kb = 0; kb < C::KB; kb++) tma_load_3d(sQ + kb * QT * 128, &tmQ, q_full, head * D + kb * 64, q0, b);
       for (int j = 0; j < nt; j++) {
-        const int s = j % ST;
-        mbar_wait(kv_empty(s), ((j / ST) & 1) ^ 1);
+        const int s = j % STAGES;
+        mbar_wait(kv_empty(s), ((j / STAGES) & 1) ^ 1);
         const uint32_t sk = sKV + s * C::STAGE, sv = sk + C::K_BYTES;
         mbar_arrive_expect_tx(kv_full(s), C::STAGE);
 #pragma unroll
@@ -238,10 +233,10 @@ __global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_
       // D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), N>>3 at [17,23), M>>4 at [24,29); bit 16: B is MN-major (the V tile)
       const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
-      const uint32_t t_o = tmem_base + C::OCOL;
+      const uint32_t t_o = tmem_base + 2 * KT;
       auto issue_qk = [&](int j) {
-        const int s = j % ST;
-        mbar_wait(kv_full(s), (j / ST) & 1);
+        const int s = j % STAGES;
+        mbar_wait(kv_full(s), (j / STAGES) & 1);
         mbar_wait(s_empty + 8 * (j & 1), ((j >> 1) & 1) ^ 1);        // the softmax has read S(j-2) out of this buffer
         tc_fence_after();
         const uint32_t sk = sKV + s * C::STAGE;
@@ -258,7 +253,7 @@ __global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_
       issue_qk(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) issue_qk(j + 1);                             // scores of the next tile while the softmax works on this one
-        const int s = j % ST;
+        const int s = j % STAGES;
         mbar_wait(p_full + 8 * (j & 1), (j >> 1) & 1);
         tc_fence_after();
         const uint64_t ad = desc_k(sP + (j & 1) * C::P_BYTES);
@@ -274,7 +269,7 @@ __global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_
   } else {
     // ===================== softmax warps: one thread per query row =====================
     SoftmaxBars sb{s_full, s_empty, p_full, p_empty, o_ready, o_final};
-    softmax_role<D>(tmem_base, sP, sb, nt, p, warp, lane, q0, b, head * D, head, C::OCOL);
+    softmax_role<D>(tmem_base, sP, sb, nt, p, warp, lane, q0, b, head * D, head);
   }
   tc_fence_before();
   __syncthreads();
@@ -285,9 +280,9 @@ __global__ void __launch_bounds__(NTH, ST == 1 ? 3 : (D == 64 ? 2 : 1)) attn_tc_
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
-template <int D, int ST>
+template <int D>
 int launch(const cenet_attn_tc_args& a, cudaStream_t s) {
-  using C = Cfg<D, ST>;
+  using C = Cfg<D>;
   CUtensorMap tmQ, tmK, tmV;
   if (encode3(&tmQ, a.q, (long long)a.heads * D, a.Nq, a.B, a.ldq, a.bq, 64, QT, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
   if (encode3(&tmK, a.k, (long long)a.heads * D, a.Nk, a.B, a.ldk, a.bk, 64, KT, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
@@ -296,7 +291,7 @@ int launch(const cenet_attn_tc_args& a, cudaStream_t s) {
   p.o = (bf16*)a.o; p.lse = a.lse; p.ldo = a.ldo; p.bo = a.bo; p.Nq = a.Nq; p.Nk = a.Nk; p.heads = a.heads;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.lse_mul = a.lse_base2 ? 1.f : 0.6931471805599453f;
-  auto kern = attn_tc_kernel<D, ST>;
+  auto kern = attn_tc_kernel<D>;
   static std::once_flag once;
   std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM); });
   dim3 grid(cdiv(a.Nq, QT), a.heads, a.B);
@@ -459,8 +454,7 @@ extern "C" int cenet_attn_tc(const cenet_attn_tc_args* a, cenet_stream_t s) {
   CENET_REQUIRE(a && a->q && a->k && a->v && a->o, "cenet_attn_tc: null pointer");
   CENET_REQUIRE(cenet_attn_tc_eligible(a), "cenet_attn_tc: needs bf16 operands with head width 64 or 128 (or one head of 192..1024, multiple of 64), 16-byte aligned pointers and "
                 "row / image strides that are multiples of 8 elements (D=%d)", a->D);
-  static const bool short_on = !(getenv("CENET_B200_ATTN_SHORT") && atoi(getenv("CENET_B200_ATTN_SHORT")) == 0);
-  if (a->D == 64) return (short_on && a->Nk <= KT) ? launch<64, 1>(*a, to_stream(s)) : launch<64, STAGES>(*a, to_stream(s));
-  if (a->D == 128) return launch<128, STAGES>(*a, to_stream(s));
+  if (a->D == 64) return launch<64>(*a, to_stream(s));
+  if (a->D == 128) return launch<128>(*a, to_stream(s));
   return launch_wide(*a, to_stream(s));              // one head of width 192..1024 (multiple of 64): streamed contraction
 }
