@@ -117,3 +117,26 @@ def test_cenet_org_contract():
         m.eval()(torch.zeros(1, 1, 224, 224))                    # no CPU path
     with pytest.raises(NotImplementedError):
         CENetOrg(encoder="resnet50")
+
+
+def test_bf16_plan_variants_on_the_emulation():
+    """the bf16 launch plan (implicit strided convolutions through conv_nhwc, flash attention entry points) and its switchable
+    variants -- fused Mix-FFN tail on, im2col strided convolutions -- agree with each other and with the oracle on the emulation"""
+    x = fixtures.synth_input("synapse", 2, size=64)
+    outs = {}
+    for tag, attrs in (("default", {}), ("mixffn", {"fuse_mixffn": True}), ("im2col", {"implicit_strided": False})):
+        eng, sd, kw = _engine("synapse", precision="bf16", flash=True)
+        assert eng.implicit_strided and not eng.fuse_mixffn
+        for k, v in attrs.items():
+            setattr(eng, k, v)
+        n0 = fake_ops.launch_count()
+        outs[tag] = eng.forward(x).float().clone()
+        outs[tag + ".launches"] = fake_ops.launch_count() - n0
+    with torch.no_grad():
+        y_ref = O.cenet_forward(sd, O.Cfg(**kw), x)
+    for tag in ("default", "mixffn", "im2col"):
+        e = ((outs[tag] - y_ref).norm() / y_ref.norm()).item()
+        assert e < 2e-2, (tag, e)
+        assert ((outs[tag] - outs["default"]).norm() / outs["default"].norm()).item() < 1e-2, tag
+    assert outs["mixffn.launches"] == outs["default.launches"] - 7          # dwconv3x3 + fc2 -> one launch in the 3 + 4 blocks of stages 1-2
+    assert outs["im2col.launches"] > outs["default.launches"]
