@@ -1,6 +1,8 @@
 """Epilogue variants of the narrow decoder GEMM (M=200704, N=64, K=64) timed with CUDA events, L2 flushed.
 B200: plain 27.3, SiLU 27.0, mul 29.3, mul + SiLU 37.5, SiLU(g)*SiLU(v) 44.4, residual 27.6 us (roofline 8-12 us): these launches are
-bound by the 4 epilogue warps per CTA (168 registers per thread allow 2 CTAs x 192 threads per SM, not 8 epilogue warps each)."""
+bound by the 4 epilogue warps per CTA (168 registers per thread allow 2 CTAs x 192 threads per SM, not 8 epilogue warps each).
+Tried: 96-register "lean" instantiations with 2 x (2 + 8) warps per SM -- this shape 26.7 -> 23.4 us (SiLU*SiLU 44.4 -> 33.5), but the
+register cap slows the 4-warp launches by as much: forward 10.25 ms either way; everywhere (convs included) 10.43 ms.  Not kept."""
 import os, sys, math, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cenet_b200 import ops
